@@ -1,0 +1,511 @@
+"""Batched tensor-in / tensor-out API over libisr (hand-written sm_100a kernels).
+
+Every function takes numpy arrays or torch tensors (host or device), moves them to the
+current CUDA device if needed, and launches on torch's current stream.  Nothing here
+computes on the CPU: without a GPU and csrc/libisr.so these functions raise.
+
+Reference mapping (file:line into the reference repository):
+  transform_points    pc.dot(R.T)+t            verfication.py:83-85, icp.py:68; PointCloud.transform icp.py:110
+  nearest_neighbors   KD-tree 1-NN             verfication.py:97,99; icp.py:97-103; choosePose.py:21-22
+  chamfer_distance    Chamfer                  verfication.py:97-101; icp.py:113-117
+  adds                ADDS                     choosePose.py:20-22
+  verify_poses        candidate loop + argmin  verfication.py:61-108; choosePose.py:124-138
+  evaluate_registration / icp                  icp.py:96-103
+  multistart_icp      symmetry-seeded starts   README.md:42-46 (config 5 of BASELINE.json)
+  refine_pose         (R, t, loss) convention  pose_refine.py:21-22,101-104
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------------------
+# plumbing
+# --------------------------------------------------------------------------------------
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("CUDA device required: this package has no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+_NP_OF = {torch.float32: np.float32, torch.float64: np.float64, torch.uint8: np.uint8,
+          torch.int32: np.int32, torch.int64: np.int64}
+
+
+def _to_dev(x, dtype, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=_NP_OF[dtype]))
+    if t.device != device:
+        # convert on the side that avoids an extra host pass: dtype first for host tensors
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        t = t.to(device, non_blocking=True)
+    elif t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _points(x, device) -> torch.Tensor:
+    t = _to_dev(x, torch.float32, device)
+    if t.dim() < 2 or t.shape[-1] != 3:
+        raise ValueError(f"points must have shape [..., N, 3], got {tuple(t.shape)}")
+    return t
+
+
+def _poses(x, device) -> torch.Tensor:
+    t = _to_dev(x, torch.float64, device)
+    if t.dim() == 2:
+        t = t[None]
+    if t.dim() != 3 or t.shape[-2:] != (4, 4):
+        raise ValueError(f"poses must have shape [B, 4, 4], got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def pose_from_Rt(R, t) -> np.ndarray:
+    """4x4 float64 pose (column-vector convention) from a 3x3 rotation and a translation."""
+    T = np.eye(4)
+    T[:3, :3] = np.asarray(R, dtype=np.float64).reshape(3, 3)
+    T[:3, 3] = np.asarray(t, dtype=np.float64).reshape(3)
+    return T
+
+
+# --------------------------------------------------------------------------------------
+# K1 -- transform
+# --------------------------------------------------------------------------------------
+def transform_points(points, poses, device=None) -> torch.Tensor:
+    """out[b] = points @ poses[b,:3,:3].T + poses[b,:3,3]  ->  float32 [B, N, 3] (FP64 math)."""
+    device = _device(device)
+    pts = _points(points, device)
+    if pts.dim() != 2:
+        raise ValueError("transform_points expects points of shape [N, 3]")
+    P = _poses(poses, device)
+    n, b = pts.shape[0], P.shape[0]
+    out = torch.empty((b, n, 3), dtype=torch.float32, device=device)
+    lib = _lib.load()
+    # grid.y carries the batch: chunk at 65535
+    for b0 in range(0, b, 65535):
+        bc = min(65535, b - b0)
+        _lib.check(lib.isr_transform_points(_ptr(pts), n, _ptr(P[b0:]), bc, _ptr(out[b0:]), _stream()))
+    return out
+
+
+@dataclasses.dataclass
+class SoaCloud:
+    """A cloud (or batch of clouds) in the padded plane layout K2 streams: [B, 3, npad]."""
+    data: torch.Tensor
+    n: int
+
+    @property
+    def npad(self) -> int:
+        return self.data.shape[-1]
+
+    @property
+    def batch(self) -> int:
+        return self.data.shape[0]
+
+
+def pack_soa(points, poses=None, device=None) -> SoaCloud:
+    """Repack [N,3] (optionally transformed by each of poses [B,4,4]) into SoA planes."""
+    device = _device(device)
+    pts = _points(points, device)
+    if pts.dim() != 2:
+        raise ValueError("pack_soa expects points of shape [N, 3]")
+    n = pts.shape[0]
+    npad = _lib.soa_padded_len(n)
+    lib = _lib.load()
+    if poses is None:
+        out = torch.empty((1, 3, npad), dtype=torch.float32, device=device)
+        _lib.check(lib.isr_transform_points_soa(_ptr(pts), n, None, 16, 1, _ptr(out), npad, None, 0,
+                                                _stream()))
+        return SoaCloud(out, n)
+    P = _poses(poses, device)
+    b = P.shape[0]
+    out = torch.empty((b, 3, npad), dtype=torch.float32, device=device)
+    for b0 in range(0, b, 65535):
+        bc = min(65535, b - b0)
+        _lib.check(lib.isr_transform_points_soa(_ptr(pts), n, _ptr(P[b0:]), 16, bc, _ptr(out[b0:]),
+                                                npad, None, 0, _stream()))
+    return SoaCloud(out, n)
+
+
+def _pack_batched(points, device) -> SoaCloud:
+    """[N,3] or [B,N,3] -> SoaCloud with batch 1 or B (no transform)."""
+    pts = _points(points, device)
+    if pts.dim() == 2:
+        return pack_soa(pts, device=device)
+    if pts.dim() != 3:
+        raise ValueError("points must be [N,3] or [B,N,3]")
+    b, n = pts.shape[0], pts.shape[1]
+    npad = _lib.soa_padded_len(n)
+    out = torch.empty((b, 3, npad), dtype=torch.float32, device=device)
+    lib = _lib.load()
+    for k in range(b):
+        _lib.check(lib.isr_transform_points_soa(_ptr(pts[k]), n, None, 16, 1, _ptr(out[k]), npad,
+                                                None, 0, _stream()))
+    return SoaCloud(out, n)
+
+
+# --------------------------------------------------------------------------------------
+# K2 -- nearest neighbour, Chamfer, ADD-S
+# --------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class NNResult:
+    d2: torch.Tensor            # float32 [B, Nq] squared distance (kernel arithmetic, bit-exact)
+    idx: Optional[torch.Tensor]  # int32 [B, Nq] nearest target index (lowest index on ties)
+
+    @property
+    def dist(self) -> torch.Tensor:
+        """Euclidean distances, float64 (what compute_point_cloud_distance returns)."""
+        return torch.sqrt(self.d2.to(torch.float64))
+
+
+def nearest_neighbors_soa(q: SoaCloud, t: SoaCloud, return_index: bool = True) -> NNResult:
+    if t.n < 1:
+        raise ValueError("nearest_neighbors: empty target cloud")
+    qb, tb = q.batch, t.batch
+    batch = max(qb, tb)
+    if qb not in (1, batch) or tb not in (1, batch):
+        raise ValueError(f"batch mismatch: query {qb}, target {tb}")
+    device = q.data.device
+    d2 = torch.empty((batch, q.n), dtype=torch.float32, device=device)
+    idx = torch.empty((batch, q.n), dtype=torch.int32, device=device) if return_index else None
+    if q.n == 0:
+        return NNResult(d2, idx)
+    lib = _lib.load()
+    for b0 in range(0, batch, 65535):
+        bc = min(65535, batch - b0)
+        ws = _workspace(lib.isr_nn_workspace_bytes(q.n, t.n, bc), device)
+        qd = q.data[b0:] if qb > 1 else q.data
+        td = t.data[b0:] if tb > 1 else t.data
+        _lib.check(lib.isr_nn_soa(
+            _ptr(qd), q.n, q.npad, 3 * q.npad if qb > 1 else 0,
+            _ptr(td), t.n, t.npad, 3 * t.npad if tb > 1 else 0,
+            bc, _ptr(d2[b0:]), _ptr(idx[b0:]) if idx is not None else None, None, 0,
+            _ptr(ws), ws.numel(), _stream()))
+    return NNResult(d2, idx)
+
+
+def nearest_neighbors(query, target, return_index: bool = True, device=None) -> NNResult:
+    """Brute-force exact 1-NN of query [Nq,3] / [B,Nq,3] in target [Nt,3] / [B,Nt,3]."""
+    device = _device(device)
+    q = _pack_batched(query, device)
+    t = _pack_batched(target, device)
+    res = nearest_neighbors_soa(q, t, return_index)
+    if _points(query, device).dim() == 2 and _points(target, device).dim() == 2:
+        res = NNResult(res.d2[0], None if res.idx is None else res.idx[0])
+    return res
+
+
+def _mean_sqrt(d2: torch.Tensor) -> torch.Tensor:
+    """FP64 mean of sqrt(d2) per row, deterministic order."""
+    b, n = d2.shape
+    out = torch.empty((b,), dtype=torch.float64, device=d2.device)
+    _lib.check(_lib.load().isr_mean_sqrt(_ptr(d2), n, b, _ptr(out), _stream()))
+    return out
+
+
+def point_cloud_distance(source, target, device=None) -> torch.Tensor:
+    """Open3D compute_point_cloud_distance: float64 [N] distances; empty target -> zeros."""
+    device = _device(device)
+    src = _points(source, device)
+    tgt = _points(target, device)
+    if tgt.shape[0] == 0:
+        return torch.zeros((src.shape[0],), dtype=torch.float64, device=device)
+    if src.shape[0] == 0:
+        return torch.zeros((0,), dtype=torch.float64, device=device)
+    return nearest_neighbors(src, tgt, return_index=False, device=device).dist
+
+
+def chamfer_distance(a, b, device=None) -> torch.Tensor:
+    """(mean d(a->b) + mean d(b->a)) / 2, unsquared, float64 scalar tensor
+    (verfication.py:97-101).  Accepts [N,3] or batched [B,N,3]."""
+    device = _device(device)
+    A = _pack_batched(a, device)
+    B = _pack_batched(b, device)
+    ab = _mean_sqrt(nearest_neighbors_soa(A, B, return_index=False).d2)
+    ba = _mean_sqrt(nearest_neighbors_soa(B, A, return_index=False).d2)
+    out = (ab + ba) / 2
+    return out[0] if _points(a, device).dim() == 2 and _points(b, device).dim() == 2 else out
+
+
+@dataclasses.dataclass
+class VerifyResult:
+    losses: torch.Tensor   # float64 [B] on device; +inf for invalid candidates
+    best: torch.Tensor     # int64 [2] on device: {argmin index, bits of the float64 loss}
+
+    @property
+    def best_index(self) -> int:
+        return int(self.best[0].item())
+
+    @property
+    def best_loss(self) -> float:
+        return float(self.best[1:2].view(torch.float64).item())
+
+
+def verify_poses(cloud_q, poses_q, poses_t, cloud_t=None, mode: str = "chamfer",
+                 valid_mask=None, device=None) -> VerifyResult:
+    """Score B candidate poses and select the first minimum, entirely on the device.
+
+    Candidate k compares ``poses_q[k] . cloud_q`` with ``poses_t[k] . cloud_t``
+    (cloud_t defaults to cloud_q).  mode='chamfer': bidirectional mean distance / 2
+    (verfication.py:97-101); mode='adds': one-directional mean distance query->target
+    (choosePose.py:20-22).
+    """
+    if mode not in ("chamfer", "adds"):
+        raise ValueError("mode must be 'chamfer' or 'adds'")
+    device = _device(device)
+    cq = _points(cloud_q, device)
+    ct = cq if cloud_t is None else _points(cloud_t, device)
+    Pq = _poses(poses_q, device)
+    Pt = _poses(poses_t, device)
+    if Pq.shape[0] != Pt.shape[0]:
+        raise ValueError("poses_q and poses_t must have the same batch size")
+    b = Pq.shape[0]
+    if b == 0:
+        raise ValueError("verify_poses: empty candidate list")
+    if cq.shape[0] == 0 or ct.shape[0] == 0:
+        raise ValueError("verify_poses: empty cloud")
+    valid = None
+    if valid_mask is not None:
+        valid = _to_dev(np.asarray(valid_mask).astype(np.uint8) if not isinstance(
+            valid_mask, torch.Tensor) else valid_mask.to(torch.uint8), torch.uint8, device)
+        if valid.numel() != b:
+            raise ValueError("valid_mask must have one entry per candidate")
+    bidir = 1 if mode == "chamfer" else 0
+    lib = _lib.load()
+    ws = _workspace(lib.isr_verify_workspace_bytes(cq.shape[0], ct.shape[0], b, bidir), device)
+    losses = torch.empty((b,), dtype=torch.float64, device=device)
+    best = torch.empty((2,), dtype=torch.int64, device=device)
+    _lib.check(lib.isr_verify_poses(_ptr(cq), cq.shape[0], _ptr(ct), ct.shape[0], _ptr(Pq), _ptr(Pt),
+                                    _ptr(valid), b, bidir, _ptr(losses), _ptr(best), _ptr(ws),
+                                    ws.numel(), _stream()))
+    return VerifyResult(losses, best)
+
+
+def adds(verts, gtR, gtT, R, T, surface_points, device=None) -> torch.Tensor:
+    """Batched ADDS (choosePose.py:20-22): mean 1-NN distance from verts.gtR^T+gtT to
+    surface.R^T+T.  gtR/R may be [3,3] or [B,3,3]; returns float64 [B] (or scalar)."""
+    gtR = np.asarray(gtR, dtype=np.float64)
+    single = gtR.ndim == 2
+    gtR = gtR.reshape(-1, 3, 3)
+    R = np.asarray(R, dtype=np.float64).reshape(-1, 3, 3)
+    gtT = np.asarray(gtT, dtype=np.float64).reshape(-1, 3)
+    T = np.asarray(T, dtype=np.float64).reshape(-1, 3)
+    b = len(gtR)
+    Pq = np.tile(np.eye(4), (b, 1, 1))
+    Pt = np.tile(np.eye(4), (b, 1, 1))
+    Pq[:, :3, :3], Pq[:, :3, 3] = gtR, gtT
+    Pt[:, :3, :3], Pt[:, :3, 3] = R, T
+    res = verify_poses(verts, Pq, Pt, cloud_t=surface_points, mode="adds", device=device)
+    return res.losses[0] if single else res.losses
+
+
+# --------------------------------------------------------------------------------------
+# K3 -- ICP
+# --------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class IcpResult:
+    """Mirror of Open3D's RegistrationResult (icp.py:99,104-106)."""
+    transformation: np.ndarray
+    fitness: float
+    inlier_rmse: float
+    n_corr: int
+    iterations: int
+    converged: bool
+    _corr_idx: Optional[torch.Tensor] = None
+    _inlier: Optional[torch.Tensor] = None
+
+    @property
+    def correspondence_set(self) -> np.ndarray:
+        """k x 2 int32 (source index, target index), like Open3D's correspondence_set_."""
+        if self._corr_idx is None:
+            return np.zeros((0, 2), dtype=np.int32)
+        src = torch.nonzero(self._inlier, as_tuple=False)[:, 0]
+        tgt = self._corr_idx[src].to(torch.int64)
+        return torch.stack([src, tgt], dim=1).to(torch.int32).cpu().numpy()
+
+    def __repr__(self) -> str:
+        return (f"RegistrationResult with fitness={self.fitness:e}, inlier_rmse={self.inlier_rmse:e},"
+                f" and correspondence_set size of {self.n_corr}\n"
+                "Access transformation to get result.")
+
+
+class IcpProblem:
+    """Device-side buffers of one (source, target) pair for `starts` simultaneous ICP starts.
+
+    Exposed so that the multi-GPU driver (dist.py) can interleave its all-reduce between
+    `accumulate` and `solve`; single-GPU callers use `run`.
+    """
+
+    def __init__(self, source, target, inits, device=None):
+        self.device = _device(device)
+        self.src = _points(source, self.device)
+        self.tgt = _points(target, self.device)
+        if self.src.dim() != 2 or self.tgt.dim() != 2:
+            raise ValueError("icp: source and target must be [N,3]")
+        self.ns, self.nt = self.src.shape[0], self.tgt.shape[0]
+        if self.nt < 1:
+            raise ValueError("icp: empty target cloud")
+        inits = np.asarray(inits, dtype=np.float64).reshape(-1, 4, 4)
+        self.starts = len(inits)
+        st = np.zeros(self.starts, dtype=_lib.ICP_STATE_DTYPE)
+        st["T"] = inits.reshape(self.starts, 16)
+        self.states = torch.from_numpy(st.view(np.uint8).reshape(self.starts, -1).copy()).to(self.device)
+        self.tgt_soa = pack_soa(self.tgt, device=self.device)
+        lib = _lib.load()
+        ns1 = max(self.ns, 1)
+        self.ws = _workspace(lib.isr_icp_workspace_bytes(ns1, self.nt, self.starts), self.device)
+        self.sums = torch.zeros((self.starts, _lib.ISR_ICP_NSUMS), dtype=torch.float64,
+                                device=self.device)
+        self.corr_idx = torch.zeros((self.starts, ns1), dtype=torch.int32, device=self.device)
+        self.inlier = torch.zeros((self.starts, ns1), dtype=torch.uint8, device=self.device)
+
+    def accumulate(self, max_dist: float) -> torch.Tensor:
+        if self.ns == 0:
+            self.sums.zero_()
+            return self.sums
+        _lib.check(_lib.load().isr_icp_accumulate(
+            _ptr(self.states), self.starts, _ptr(self.src), self.ns, _ptr(self.tgt),
+            _ptr(self.tgt_soa.data), self.nt, self.tgt_soa.npad, float(max_dist), _ptr(self.sums),
+            _ptr(self.corr_idx), _ptr(self.inlier), _ptr(self.ws), self.ws.numel(), _stream()))
+        return self.sums
+
+    def solve(self, ns_total: int, rel_fitness: float, rel_rmse: float, final_eval: bool,
+              sums: Optional[torch.Tensor] = None) -> None:
+        sums = self.sums if sums is None else sums
+        _lib.check(_lib.load().isr_icp_solve(_ptr(self.states), self.starts, _ptr(sums), int(ns_total),
+                                             float(rel_fitness), float(rel_rmse),
+                                             1 if final_eval else 0, _stream()))
+
+    def run(self, max_dist: float, max_iteration: int, rel_fitness: float, rel_rmse: float) -> None:
+        if self.ns == 0:
+            for k in range(max_iteration + 1):
+                self.accumulate(max_dist)
+                self.solve(0, rel_fitness, rel_rmse, k == max_iteration)
+            return
+        _lib.check(_lib.load().isr_icp_run(
+            _ptr(self.states), self.starts, _ptr(self.src), self.ns, _ptr(self.tgt),
+            _ptr(self.tgt_soa.data), self.nt, self.tgt_soa.npad, float(max_dist), int(max_iteration),
+            float(rel_fitness), float(rel_rmse), _ptr(self.sums), _ptr(self.corr_idx),
+            _ptr(self.inlier), _ptr(self.ws), self.ws.numel(), _stream()))
+
+    def results(self, with_correspondences: bool = True) -> list:
+        st = self.states.cpu().numpy().view(_lib.ICP_STATE_DTYPE).reshape(self.starts)
+        out = []
+        for k in range(self.starts):
+            s = st[k]
+            out.append(IcpResult(
+                transformation=s["T"].reshape(4, 4).copy(), fitness=float(s["fitness"]),
+                inlier_rmse=float(s["inlier_rmse"]), n_corr=int(s["n_corr"]),
+                iterations=int(s["iters"]), converged=bool(s["done"]),
+                _corr_idx=self.corr_idx[k] if with_correspondences and self.ns > 0 else None,
+                _inlier=self.inlier[k] if with_correspondences and self.ns > 0 else None))
+        return out
+
+
+def evaluate_registration(source, target, max_correspondence_distance: float,
+                          transformation=None, device=None) -> IcpResult:
+    """o3d.pipelines.registration.evaluate_registration (icp.py:97-98)."""
+    T = np.eye(4) if transformation is None else np.asarray(transformation, dtype=np.float64)
+    prob = IcpProblem(source, target, T[None], device)
+    prob.run(max_correspondence_distance, 0, 0.0, 0.0)
+    return prob.results()[0]
+
+
+def icp(source, target, init=None, max_correspondence_distance: float = 20.0,
+        max_iteration: int = 30, relative_fitness: float = 1e-6, relative_rmse: float = 1e-6,
+        device=None) -> IcpResult:
+    """Point-to-point ICP with Open3D's loop and default criteria (icp.py:101-103)."""
+    T = np.eye(4) if init is None else np.asarray(init, dtype=np.float64)
+    prob = IcpProblem(source, target, T[None], device)
+    prob.run(max_correspondence_distance, max_iteration, relative_fitness, relative_rmse)
+    return prob.results()[0]
+
+
+@dataclasses.dataclass
+class MultiStartResult:
+    results: list               # IcpResult per start
+    chamfer: np.ndarray         # float64 [S] Chamfer(transformed source, target) per start
+    order: np.ndarray           # starts sorted by ascending Chamfer (stable: first minimum first)
+
+    @property
+    def best(self) -> IcpResult:
+        return self.results[int(self.order[0])]
+
+
+def multistart_icp(source, target, inits, max_correspondence_distance: float = 20.0,
+                   max_iteration: int = 30, relative_fitness: float = 1e-6,
+                   relative_rmse: float = 1e-6, device=None) -> MultiStartResult:
+    """All starts advance together (batch dimension in every kernel); each is then scored
+    by the Chamfer distance of its registered source against the target (icp.py:113-117)
+    and ranked ascending, first minimum first."""
+    inits = np.asarray(inits, dtype=np.float64).reshape(-1, 4, 4)
+    prob = IcpProblem(source, target, inits, device)
+    prob.run(max_correspondence_distance, max_iteration, relative_fitness, relative_rmse)
+    res = prob.results()
+    Ts = np.stack([r.transformation for r in res])
+    s = len(res)
+    vr = verify_poses(prob.src, Ts, np.tile(np.eye(4), (s, 1, 1)), cloud_t=prob.tgt, mode="chamfer",
+                      device=prob.device)
+    ch = vr.losses.cpu().numpy()
+    return MultiStartResult(res, ch, np.argsort(ch, kind="stable"))
+
+
+def refine_pose(R, t, source, target, max_correspondence_distance: float = 20.0,
+                max_iteration: int = 30, device=None):
+    """ICP refinement with the return convention of pose_refine.py:21-22,101-104:
+    ``(R, t, loss)``.  (R, t) maps `source` into the frame of `target`; the loss is the
+    inlier RMSE of the final evaluation.  The reference's own objective (NeRF keys + GL
+    renderer, rotation frozen) is out of scope; only its call/return shape is kept."""
+    res = icp(source, target, pose_from_Rt(R, t), max_correspondence_distance, max_iteration,
+              device=device)
+    T = res.transformation
+    return T[:3, :3].copy(), T[:3, 3].copy(), res.inlier_rmse
+
+
+# --------------------------------------------------------------------------------------
+# measurement helper
+# --------------------------------------------------------------------------------------
+def measure_fp32_peak(packed: bool = False, iters: int = 4096, reps: int = 5) -> float:
+    """FFMA-chain microbenchmark -> measured FP32 TFLOP/s of the current device."""
+    device = _device()
+    lib = _lib.load()
+    import ctypes
+    sm = ctypes.c_int(0)
+    _lib.check(lib.isr_device_info(ctypes.byref(sm), None, None))
+    sink = torch.zeros(4, dtype=torch.float32, device=device)
+    flops = ctypes.c_double(0)
+    blocks = sm.value * 8
+    best = 0.0
+    for _ in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.isr_bench_ffma(blocks, iters, 1 if packed else 0, _ptr(sink),
+                                      ctypes.byref(flops), _stream()))
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = max(best, flops.value / (ms * 1e-3) / 1e12)
+    return best

@@ -1,0 +1,361 @@
+// K3 -- point-to-point ICP with the iteration loop resident on the device.
+//
+// Replaces o3d.pipelines.registration.evaluate_registration / registration_icp with
+// TransformationEstimationPointToPoint (icp.py:96-103).  Upstream semantics restated:
+//   evaluation   : transform source by T, 1-NN per point, keep d2 < max_dist^2 (strict),
+//                  fitness = #corr / n_source, inlier_rmse = sqrt(sum d2 / #corr);
+//   update       : Eigen::umeyama(src[corr], tgt[corr], no scaling) -> U;  T <- U T;
+//   loop         : evaluate; repeat { update; evaluate; break if |dfitness| < rf and
+//                  |drmse| < rr } at most max_iteration times; the result is the last
+//                  evaluation; an empty correspondence set gives U = I.
+//
+// One evaluation = K1 (FP64 transform -> FP32 SoA) + K2 (FP32 brute-force 1-NN, indices)
+// + icp_accumulate_kernel (HBM-bound gather: 12 B source + 4 B index + 12 B gathered
+// target (+ 1 B flag written) per source point).  The gather re-derives every
+// correspondence distance in FP64 from the original source point and the FP64 pose, so
+// the inlier test, fitness, rmse and the 17 Kabsch sums carry no FP32 error; only the
+// choice of neighbour is made in FP32.  Sums are reduced warp -> CTA -> last-arriving CTA
+// in a fixed order (no floating-point atomics).  icp_solve_kernel (one warp per start)
+// applies the break test, solves the 3x3 SVD by one-sided Jacobi in FP64 and composes
+// T <- U T.  A finished start sets `done`; all later kernels for it exit at once, so the
+// host enqueues max_iteration + 1 passes without ever reading the device.
+#include <math_constants.h>
+
+#include "isr_common.cuh"
+
+namespace isr {
+
+constexpr int kAccThreads = 256;
+constexpr int kNS = ISR_ICP_NSUMS;
+constexpr int kStateInts = (int)(sizeof(IsrIcpState) / sizeof(int32_t));
+constexpr int kStateDoubles = (int)(sizeof(IsrIcpState) / sizeof(double));
+static_assert(sizeof(IsrIcpState) % 8 == 0, "IsrIcpState must be a whole number of doubles");
+
+// grid: (nblk, starts)
+__global__ void __launch_bounds__(kAccThreads)
+icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__restrict__ src,
+                      int64_t ns, const float *__restrict__ tgt, const int32_t *__restrict__ idx,
+                      double max_d2, double *__restrict__ partials, unsigned *__restrict__ tickets,
+                      double *__restrict__ sums, uint8_t *__restrict__ inlier) {
+    const int s = blockIdx.y;
+    const IsrIcpState &stt = states[s];
+    if (stt.done != 0) return;
+    __shared__ double red[kAccThreads / 32][kNS];
+    __shared__ bool is_last;
+
+    double T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = stt.T[k];
+    double acc[kNS];
+#pragma unroll
+    for (int k = 0; k < kNS; ++k) acc[k] = 0.0;
+
+    const int32_t *ids = idx + (int64_t)s * ns;
+    uint8_t *inl = inlier != nullptr ? inlier + (int64_t)s * ns : nullptr;
+    for (int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i < ns;
+         i += (int64_t)gridDim.x * kAccThreads) {
+        const double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
+        const double sx = ((T[0] * px + T[1] * py) + T[2] * pz) + T[3];
+        const double sy = ((T[4] * px + T[5] * py) + T[6] * pz) + T[7];
+        const double sz = ((T[8] * px + T[9] * py) + T[10] * pz) + T[11];
+        const int64_t j = ids[i];
+        const double tx = tgt[3 * j], ty = tgt[3 * j + 1], tz = tgt[3 * j + 2];
+        const double dx = sx - tx, dy = sy - ty, dz = sz - tz;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        const bool in = d2 < max_d2;
+        if (inl != nullptr) inl[i] = in ? 1 : 0;
+        if (in) {
+            acc[0] += sx; acc[1] += sy; acc[2] += sz;
+            acc[3] += tx; acc[4] += ty; acc[5] += tz;
+            acc[6] += tx * sx; acc[7] += tx * sy; acc[8] += tx * sz;
+            acc[9] += ty * sx; acc[10] += ty * sy; acc[11] += ty * sz;
+            acc[12] += tz * sx; acc[13] += tz * sy; acc[14] += tz * sz;
+            acc[15] += d2;
+            acc[16] += 1.0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kNS; ++k) acc[k] = warp_sum(acc[k]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kNS; ++k) red[warp][k] = acc[k];
+    }
+    __syncthreads();
+    double *my = partials + ((int64_t)s * gridDim.x + blockIdx.x) * kNS;
+    if (threadIdx.x < kNS) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kAccThreads / 32; ++w) v += red[w][threadIdx.x];
+        my[threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&tickets[s], 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (threadIdx.x < kNS) {
+            const double *base = partials + (int64_t)s * gridDim.x * kNS;
+            double v = 0.0;
+            for (unsigned bk = 0; bk < gridDim.x; ++bk) v += base[(int64_t)bk * kNS + threadIdx.x];
+            sums[(int64_t)s * kNS + threadIdx.x] = v;
+        }
+        if (threadIdx.x == 0) tickets[s] = 0;
+    }
+}
+
+// ---- 3x3 SVD (one-sided Jacobi, FP64) and Kabsch ---------------------------------------
+__device__ void svd3(const double M[3][3], double U[3][3], double D[3], double V[3][3]) {
+    double A[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            A[i][j] = M[i][j];
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    const int P[3] = {0, 0, 1}, Qc[3] = {1, 2, 2};
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        bool rotated = false;
+        for (int pr = 0; pr < 3; ++pr) {
+            const int p = P[pr], q = Qc[pr];
+            double alpha = 0, beta = 0, gamma = 0;
+            for (int k = 0; k < 3; ++k) {
+                alpha += A[k][p] * A[k][p];
+                beta += A[k][q] * A[k][q];
+                gamma += A[k][p] * A[k][q];
+            }
+            if (gamma == 0.0 || fabs(gamma) <= 2.3e-16 * sqrt(alpha * beta)) continue;
+            rotated = true;
+            const double zeta = (beta - alpha) / (2.0 * gamma);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+            for (int k = 0; k < 3; ++k) {
+                const double ap = A[k][p], aq = A[k][q];
+                A[k][p] = c * ap - sn * aq;
+                A[k][q] = sn * ap + c * aq;
+                const double vp = V[k][p], vq = V[k][q];
+                V[k][p] = c * vp - sn * vq;
+                V[k][q] = sn * vp + c * vq;
+            }
+        }
+        if (!rotated) break;
+    }
+    for (int j = 0; j < 3; ++j)
+        D[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
+    // sort singular values descending (column permutation of A and V)
+    for (int a = 0; a < 2; ++a)
+        for (int b = a + 1; b < 3; ++b)
+            if (D[b] > D[a]) {
+                const double td = D[a]; D[a] = D[b]; D[b] = td;
+                for (int k = 0; k < 3; ++k) {
+                    const double ta = A[k][a]; A[k][a] = A[k][b]; A[k][b] = ta;
+                    const double tv = V[k][a]; V[k][a] = V[k][b]; V[k][b] = tv;
+                }
+            }
+    const double tiny = D[0] * 1e-14;
+    int rank = 0;
+    for (int j = 0; j < 3; ++j) {
+        if (D[j] > tiny && D[j] > 0.0) {
+            for (int k = 0; k < 3; ++k) U[k][j] = A[k][j] / D[j];
+            ++rank;
+        }
+    }
+    if (rank == 0) {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) U[i][j] = (i == j) ? 1.0 : 0.0;
+    } else {
+        if (rank == 1) {
+            // any unit vector orthogonal to U[:,0]
+            int m = 0;
+            if (fabs(U[1][0]) < fabs(U[m][0])) m = 1;
+            if (fabs(U[2][0]) < fabs(U[m][0])) m = 2;
+            double e[3] = {0, 0, 0};
+            e[m] = 1.0;
+            const double dp = U[m][0];
+            double w[3], nn = 0;
+            for (int k = 0; k < 3; ++k) { w[k] = e[k] - dp * U[k][0]; nn += w[k] * w[k]; }
+            nn = sqrt(nn);
+            for (int k = 0; k < 3; ++k) U[k][1] = w[k] / nn;
+        }
+        if (rank <= 2) {
+            U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+            U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+            U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+        }
+    }
+}
+
+__device__ __forceinline__ double det3(const double M[3][3]) {
+    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) -
+           M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+}
+
+// one warp per start; lane 0 carries the (tiny, serial) FP64 solve.
+__global__ void __launch_bounds__(32)
+icp_solve_kernel(IsrIcpState *__restrict__ states, const double *__restrict__ sums,
+                 int64_t ns_total, double rel_fitness, double rel_rmse, int final_eval) {
+    if (threadIdx.x != 0) return;
+    IsrIcpState &st = states[blockIdx.x];
+    if (st.done != 0) return;
+    const double *S = sums + (int64_t)blockIdx.x * kNS;
+    const double cnt = S[16];
+    const double fitness = ns_total > 0 ? cnt / (double)ns_total : 0.0;
+    const double rmse = cnt > 0.0 ? sqrt(S[15] / cnt) : 0.0;
+    const bool had_prev = st.evals > 0;
+    const double pf = st.fitness, pr = st.inlier_rmse;
+    st.prev_fitness = pf;
+    st.prev_rmse = pr;
+    st.fitness = fitness;
+    st.inlier_rmse = rmse;
+    st.n_corr = (int64_t)cnt;
+    st.evals += 1;
+    if (had_prev && fabs(pf - fitness) < rel_fitness && fabs(pr - rmse) < rel_rmse) {
+        st.done = 1;
+        return;
+    }
+    if (final_eval) {
+        st.done = 1;
+        return;
+    }
+    st.iters += 1;
+    if (!(cnt > 0.0)) return;  // empty correspondence set: U = I
+
+    // Eigen::umeyama without scaling: Sigma = (1/n) sum (t - mu_t)(s - mu_s)^T
+    const double inv = 1.0 / cnt;
+    const double ms[3] = {S[0] * inv, S[1] * inv, S[2] * inv};
+    const double mt[3] = {S[3] * inv, S[4] * inv, S[5] * inv};
+    double Sig[3][3], U[3][3], V[3][3], D[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Sig[i][j] = S[6 + 3 * i + j] * inv - mt[i] * ms[j];
+    svd3(Sig, U, D, V);
+    const double sgn = (det3(U) * det3(V) < 0.0) ? -1.0 : 1.0;
+    double R[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            R[i][j] = U[i][0] * V[j][0] + U[i][1] * V[j][1] + sgn * U[i][2] * V[j][2];
+    double tr[3];
+    for (int i = 0; i < 3; ++i)
+        tr[i] = mt[i] - (R[i][0] * ms[0] + R[i][1] * ms[1] + R[i][2] * ms[2]);
+    // T <- [R tr; 0 1] . T
+    double Tn[12];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double v = R[i][0] * st.T[0 + j] + R[i][1] * st.T[4 + j] + R[i][2] * st.T[8 + j];
+            if (j == 3) v += tr[i];
+            Tn[4 * i + j] = v;
+        }
+    for (int k = 0; k < 12; ++k) st.T[k] = Tn[k];
+    st.T[12] = 0.0; st.T[13] = 0.0; st.T[14] = 0.0; st.T[15] = 1.0;
+}
+
+static int acc_blocks(int64_t ns, int64_t starts) {
+    int64_t want = (ns + kAccThreads * 8 - 1) / (kAccThreads * 8);
+    int64_t cap = (int64_t)sm_count() * 8 / (starts > 0 ? starts : 1);
+    if (cap < 8) cap = 8;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+struct IcpLayout {
+    size_t xs, d2, partials, tickets, nnws, total;
+    int nblk;
+};
+
+static IcpLayout icp_layout(int64_t ns, int64_t nt, int64_t starts) {
+    IcpLayout L;
+    const int64_t nsp = isr_soa_padded_len(ns);
+    // nblk must not depend on the device so that workspace sizing works without a GPU
+    // context: size for the largest grid acc_blocks() can pick (cap >= want).
+    size_t off = 0;
+    L.xs = off;       off += align256((size_t)starts * 3 * nsp * 4);
+    L.d2 = off;       off += align256((size_t)starts * ns * 4);
+    const int64_t max_blk = (ns + kAccThreads * 8 - 1) / (kAccThreads * 8) + 1;
+    L.partials = off; off += align256((size_t)starts * max_blk * kNS * 8);
+    L.tickets = off;  off += align256((size_t)starts * 4);
+    L.nnws = off;     off += isr_nn_workspace_bytes(ns, nt, starts);
+    L.total = off;
+    L.nblk = 0;
+    return L;
+}
+
+}  // namespace isr
+
+extern "C" {
+
+size_t isr_icp_workspace_bytes(int64_t ns, int64_t nt, int64_t starts) {
+    if (ns < 1 || nt < 1 || starts < 1) return 256;
+    return isr::icp_layout(ns, nt, starts).total;
+}
+
+int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, int64_t ns,
+                       const float *tgt, const float *tgt_soa, int64_t nt, int64_t nt_pad,
+                       double max_dist, double *sums, int32_t *corr_idx, uint8_t *inlier,
+                       void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(starts >= 1 && ns >= 1 && nt >= 1, ISR_E_SHAPE,
+                "icp: need starts, ns, nt >= 1 (starts=%lld ns=%lld nt=%lld)", (long long)starts,
+                (long long)ns, (long long)nt);
+    ISR_REQUIRE(states && src && tgt && tgt_soa && sums && corr_idx, ISR_E_INVALID_ARG,
+                "icp: null pointer");
+    ISR_REQUIRE(starts <= 65535, ISR_E_SHAPE, "icp: starts %lld > 65535", (long long)starts);
+    IcpLayout L = icp_layout(ns, nt, starts);
+    ISR_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, ISR_E_WORKSPACE,
+                "icp: workspace %zu < %zu bytes", workspace_bytes, L.total);
+    ISR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ISR_E_ALIGN,
+                "icp: workspace not 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = reinterpret_cast<char *>(workspace);
+    float *xs = reinterpret_cast<float *>(ws + L.xs);
+    float *d2 = reinterpret_cast<float *>(ws + L.d2);
+    double *partials = reinterpret_cast<double *>(ws + L.partials);
+    unsigned *tickets = reinterpret_cast<unsigned *>(ws + L.tickets);
+    const int64_t nsp = isr_soa_padded_len(ns);
+    const int32_t *done = &states[0].done;  // device address arithmetic only
+
+    if (max_dist <= 0.0) {
+        // upstream: a non-positive distance yields an empty result
+        return check_cuda(cudaMemsetAsync(sums, 0, (size_t)starts * kNS * 8, st), "icp memset");
+    }
+    ISR_TRY(isr_transform_points_soa(src, ns, &states[0].T[0], kStateDoubles, starts, xs, nsp, done,
+                                     kStateInts, stream));
+    ISR_TRY(isr_nn_soa(xs, ns, nsp, 3 * nsp, tgt_soa, nt, nt_pad, 0, starts, d2, corr_idx, done,
+                       kStateInts, ws + L.nnws, L.total - L.nnws, stream));
+    ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
+    const int nblk = acc_blocks(ns, starts);
+    dim3 grid((unsigned)nblk, (unsigned)starts);
+    icp_accumulate_kernel<<<grid, kAccThreads, 0, st>>>(states, src, ns, tgt, corr_idx,
+                                                        max_dist * max_dist, partials, tickets, sums,
+                                                        inlier);
+    return launched("icp_accumulate_kernel");
+}
+
+int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64_t ns_total,
+                  double rel_fitness, double rel_rmse, int final_eval, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(starts >= 1 && states && sums, ISR_E_INVALID_ARG, "icp_solve: bad argument");
+    icp_solve_kernel<<<(unsigned)starts, 32, 0, (cudaStream_t)stream>>>(
+        states, sums, ns_total, rel_fitness, rel_rmse, final_eval);
+    return launched("icp_solve_kernel");
+}
+
+int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, int64_t ns, const float *tgt,
+                const float *tgt_soa, int64_t nt, int64_t nt_pad, double max_dist, int max_iteration,
+                double rel_fitness, double rel_rmse, double *sums, int32_t *corr_idx, uint8_t *inlier,
+                void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(max_iteration >= 0, ISR_E_INVALID_ARG, "icp_run: max_iteration < 0");
+    for (int k = 0; k <= max_iteration; ++k) {
+        ISR_TRY(isr_icp_accumulate(states, starts, src, ns, tgt, tgt_soa, nt, nt_pad, max_dist, sums,
+                                   corr_idx, inlier, workspace, workspace_bytes, stream));
+        ISR_TRY(isr_icp_solve(states, starts, sums, ns, rel_fitness, rel_rmse,
+                              k == max_iteration ? 1 : 0, stream));
+    }
+    return ISR_OK;
+}
+
+}  // extern "C"

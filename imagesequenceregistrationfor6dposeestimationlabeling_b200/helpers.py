@@ -1,0 +1,99 @@
+"""The reference scripts' helper functions, same names / argument order / returns.
+
+  calculate_relative_pose   verfication.py:9-19
+  compute_rel_poses         choosePose.py:43-51
+  relative_pose_table       choosePose.py:98-107   (the n x n x 4 x 4 table)
+  ADD, ADDS                 choosePose.py:18-22, inference.py:116-120
+  choose_image              choosePose.py:121-151  (ADD-S vote, argmax, top-50)
+  draw_registration_result, vp   verfication.py:21-31, icp.py:8-27  (GUI; no-ops here)
+
+Pose algebra is host-side float64 numpy (3x3 / 4x4, negligible work); everything that
+touches a point cloud goes to the CUDA library through ``api``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+
+#: the reference's ADDS reads this module global (choosePose.py:21,160); assign it, or
+#: pass ``surface_points=`` explicitly.
+surfacePointsScaled = None
+
+
+def calculate_relative_pose(R1, T1, R2, T2):
+    """Rel = [R2|T2] . inv([R1|T1]) -> (Rel[:3,:3], Rel[:3,3])."""
+    T1_column = np.asarray(T1, dtype=np.float64).reshape(-1, 1)
+    RT1 = np.vstack([np.hstack((np.asarray(R1, dtype=np.float64), T1_column)), [0, 0, 0, 1]])
+    T2_column = np.asarray(T2, dtype=np.float64).reshape(-1, 1)
+    RT2 = np.vstack([np.hstack((np.asarray(R2, dtype=np.float64), T2_column)), [0, 0, 0, 1]])
+    Rel = np.dot(RT2, np.linalg.inv(RT1))
+    return Rel[:3, :3], Rel[:3, -1]
+
+
+def compute_rel_poses(R1, t1, R2, t2):
+    """(R1^T R2, t2 - t1).  Not an SE(3) composition -- kept exactly as the reference."""
+    return np.dot(np.asarray(R1).T, R2), np.asarray(t2) - np.asarray(t1)
+
+
+def relative_pose_table(RList, TList) -> np.ndarray:
+    """relative_poses[i][j] = 4x4 of compute_rel_poses(R_i, t_i, R_j, t_j); vectorised."""
+    R = np.asarray(RList, dtype=np.float64).reshape(-1, 3, 3)
+    t = np.asarray(TList, dtype=np.float64).reshape(-1, 3)
+    n = len(t)
+    out = np.zeros((n, n, 4, 4))
+    out[:, :, :3, :3] = np.einsum("iba,jbc->ijac", R, R)  # R_i^T R_j
+    out[:, :, :3, 3] = t[None, :, :] - t[:, None, :]
+    out[:, :, 3, 3] = 1.0
+    return out
+
+
+def ADD(verts, gtR1, gtT1, R1, T1):
+    """mean ||(V gtR^T + gtT) - (V R^T + T)|| on the device (K1 twice + FP64 mean)."""
+    import torch
+
+    V = api._points(verts, api._device())
+    P = np.stack([api.pose_from_Rt(gtR1, gtT1), api.pose_from_Rt(R1, T1)])
+    out = api.transform_points(V, P).to(torch.float64)
+    return float(torch.linalg.norm(out[0] - out[1], dim=-1).mean().item())
+
+
+def ADDS(verts, gtR1, gtT1, R1, T1, surface_points=None):
+    """mean 1-NN distance from verts.gtR^T+gtT into surface.R^T+T (one direction)."""
+    S = surfacePointsScaled if surface_points is None else surface_points
+    if S is None:
+        raise NameError("surfacePointsScaled is not set (choosePose.py:160 defines it as a global)")
+    return float(api.adds(verts, gtR1, gtT1, R1, T1, S).item())
+
+
+def choose_image(pred_rel_poses, gt_rel_poses, modelVerts, diameter, surface_points=None,
+                 chunk: int = 4096):
+    """ADD-S vote over all pose pairs -> (error n x n, image_id, top-50 indices)."""
+    S = surfacePointsScaled if surface_points is None else surface_points
+    if S is None:
+        raise NameError("surfacePointsScaled is not set")
+    pred = np.asarray(pred_rel_poses, dtype=np.float64)
+    gt = np.asarray(gt_rel_poses, dtype=np.float64)
+    n0, n1 = pred.shape[:2]
+    P = pred.reshape(-1, 4, 4)
+    G = gt.reshape(-1, 4, 4)
+    dev = api._device()
+    V = api._points(modelVerts, dev)
+    Sd = api._points(S, dev)
+    losses = np.empty(len(P))
+    for k0 in range(0, len(P), chunk):
+        r = api.verify_poses(V, G[k0:k0 + chunk], P[k0:k0 + chunk], cloud_t=Sd, mode="adds")
+        losses[k0:k0 + chunk] = r.losses.cpu().numpy()
+    error = (losses.reshape(n0, n1) < 0.1 * diameter).astype(np.float64)
+    votes = np.sum(error, axis=1)
+    return error, int(np.argmax(votes)), np.argsort(-votes)[:50]
+
+
+def draw_registration_result(source, target, transformation):
+    """Open3D GUI in the reference (blocking); a no-op here."""
+    return None
+
+
+def vp(finalV):
+    """Point-cloud viewer in the reference; a no-op here."""
+    return None

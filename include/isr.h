@@ -1,0 +1,167 @@
+/* libisr -- C ABI of the B200-native registration-and-verification hot path.
+ *
+ * Drop-in boundary for the arithmetic that the reference
+ * (Kudo510/ImageSequenceRegistrationfor6DPoseEstimationLabeling) delegates to Open3D
+ * and scikit-learn.  The reference has no native code and no FFI of its own; the
+ * calls below are what a binding for this path would replace, cited per entry point
+ * as <reference file>:<line>.
+ *
+ * Conventions
+ *  - Every function returns an int status: ISR_OK (0) or a negative ISR_E_* code.
+ *    No C++ exception crosses the boundary.  isr_last_error() returns a thread-local
+ *    message for the most recent failure on the calling thread.
+ *  - All data pointers are DEVICE pointers owned by the caller (PyTorch's allocator in
+ *    this repo) unless the parameter name ends in _host.  The library allocates no
+ *    persistent memory; scratch is passed in as `workspace` (size from the matching
+ *    *_workspace_bytes function, 256-byte aligned).
+ *  - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work; none
+ *    synchronises unless documented.
+ *  - Points: row-major float32 [n][3] ("AoS", the reference's numpy N x 3 layout,
+ *    genFeat.py:223-228).  Internally clouds are repacked to padded planes
+ *    [3][npad] ("SoA", npad = isr_soa_padded_len(n)); padded slots hold ISR_PAD_COORD.
+ *  - Poses: row-major float64 [16] 4x4, column-vector convention p' = T[:3,:3] p + T[:3,3]
+ *    (Open3D PointCloud.transform, icp.py:22,110).  The reference's right-multiplication
+ *    `pc.dot(M)` (verfication.py:83-85) is the pose with rotation M^T.
+ *  - Indices int32 (n < 2^31 - 1024), counts int64.
+ *  - Arithmetic: nearest-neighbour search in FP32 direct-difference form
+ *    d2 = fma(dz,dz, fma(dy,dy, dx*dx)), dx = q.x - p.x; lowest target index on exact
+ *    ties.  Transforms, distances fed to ICP, all reductions, Kabsch: FP64.
+ */
+#ifndef ISR_H_
+#define ISR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISR_VERSION 100 /* 0.1.0 */
+
+#define ISR_OK 0
+#define ISR_E_INVALID_ARG (-1)
+#define ISR_E_SHAPE (-2)
+#define ISR_E_ALIGN (-3)
+#define ISR_E_CUDA (-4)
+#define ISR_E_WORKSPACE (-5)
+
+#define ISR_SOA_TILE 1024      /* SoA planes are padded to a multiple of this        */
+#define ISR_PAD_COORD 1.0e18f  /* coordinate stored in padded slots (d2 ~ 3e36, finite) */
+
+/* ---- library / device --------------------------------------------------------------- */
+int isr_version(void);
+const char *isr_last_error(void);
+/* SM count, max SM clock (kHz), shared memory per SM (bytes) of the current device. */
+int isr_device_info(int *sm_count, int *sm_clock_khz, int *smem_per_sm);
+/* Number of CUDA kernels this library has launched since the last reset (process-wide). */
+uint64_t isr_launch_count(void);
+void isr_reset_launch_count(void);
+
+/* ---- K1: batched rigid transform ---------------------------------------------------- */
+int64_t isr_soa_padded_len(int64_t n);
+
+/* out[b][i][:] = R_b pts[i] + t_b, float32 [b][n][3].  Replaces `pc.dot(R.T) + t`
+ * (verfication.py:83-85, icp.py:68, choosePose.py:21-22) and PointCloud.transform
+ * (icp.py:22,110).  FP64 math, one rounding to float32. */
+int isr_transform_points(const float *pts, int64_t n, const double *poses, int64_t b,
+                         float *out, void *stream);
+
+/* Same transform written as padded planes out[b][3][npad] (the layout K2 consumes).
+ * poses == NULL copies the cloud unchanged (b must be 1).  `pose_stride` is in doubles
+ * (16 for a dense [b][16] array; larger when poses live inside IsrIcpState records).
+ * `skip`, if not NULL, is an int32 per batch at stride `skip_stride` ints: non-zero
+ * -> that batch is left untouched (finished ICP starts). */
+int isr_transform_points_soa(const float *pts, int64_t n, const double *poses,
+                             int64_t pose_stride, int64_t b, float *out_soa, int64_t npad,
+                             const int32_t *skip, int64_t skip_stride, void *stream);
+
+/* ---- K2: brute-force nearest neighbour ---------------------------------------------- */
+/* For every query of every batch: squared distance to, and index of, its nearest target.
+ * q_soa [batch][3][nq_pad] (q_bstride floats between batches, 0 = shared),
+ * t_soa likewise.  out_d2 float32 [batch][nq]; out_idx int32 [batch][nq] or NULL.
+ * Replaces PointCloud.compute_point_cloud_distance (verfication.py:97,99; icp.py:113,115),
+ * the KD-tree 1-NN inside registration_icp / evaluate_registration (icp.py:97-103) and
+ * sklearn KDTree.query(k=1) (choosePose.py:21-22). */
+size_t isr_nn_workspace_bytes(int64_t nq, int64_t nt, int64_t batch);
+int isr_nn_soa(const float *q_soa, int64_t nq, int64_t nq_pad, int64_t q_bstride,
+               const float *t_soa, int64_t nt, int64_t nt_pad, int64_t t_bstride,
+               int64_t batch, float *out_d2, int32_t *out_idx, const int32_t *skip,
+               int64_t skip_stride, void *workspace, size_t workspace_bytes, void *stream);
+
+/* out_mean[b] = mean_i sqrt(d2[b][i]) in FP64, fixed summation order (deterministic).
+ * np.mean(np.asarray(compute_point_cloud_distance(..))) -- verfication.py:98,100. */
+int isr_mean_sqrt(const float *d2, int64_t n, int64_t batch, double *out_mean, void *stream);
+
+/* ---- batched candidate verification ------------------------------------------------- */
+/* Candidate k compares X_k = Pq[k] . cloud_q with Y_k = Pt[k] . cloud_t:
+ *   bidirectional != 0: loss = (mean d(X->Y) + mean d(Y->X)) / 2  -- the Chamfer loop of
+ *                       verfication.py:61-102 (icp.py:113-117);
+ *   bidirectional == 0: loss = mean d(X->Y)                      -- ADDS, choosePose.py:20-22.
+ * valid (uint8 [b], may be NULL): 0 marks a failed PnP candidate (choosePose.py:29-33);
+ * its loss is +inf.  out_loss float64 [b].  out_best: int64 [2] = {argmin index with the
+ * first minimum winning (verfication.py:105-106), bit pattern of its float64 loss}. */
+size_t isr_verify_workspace_bytes(int64_t nq, int64_t nt, int64_t b, int bidirectional);
+int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int64_t nt,
+                     const double *poses_q, const double *poses_t, const uint8_t *valid,
+                     int64_t b, int bidirectional, double *out_loss, int64_t *out_best,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- K3: point-to-point ICP --------------------------------------------------------- */
+/* Device-resident state of one ICP start (one per symmetry-seeded start when batched). */
+typedef struct IsrIcpState {
+    double T[16];          /* current transformation, row-major 4x4                   */
+    double fitness;        /* #correspondences / n_source of the last evaluation       */
+    double inlier_rmse;    /* sqrt(sum d2 / #correspondences) of the last evaluation   */
+    double prev_fitness;
+    double prev_rmse;
+    int64_t n_corr;        /* correspondences of the last evaluation                   */
+    int32_t iters;         /* updates applied so far                                   */
+    int32_t evals;         /* evaluations done so far                                  */
+    int32_t done;          /* 1 once the loop has finished (criteria or max_iteration) */
+    int32_t reserved;
+} IsrIcpState;
+
+#define ISR_ICP_NSUMS 17 /* sum s[3], sum t[3], sum t s^T [9], sum d2, count */
+
+/* One evaluation pass for `starts` states: transform src by state.T, 1-NN into the
+ * target, and reduce the 17 FP64 sums over correspondences with d2 < max_dist^2 (strict)
+ * into sums[starts][17].  corr_idx int32 [starts][ns] receives the NN index of every
+ * source point, inlier uint8 [starts][ns] its correspondence flag.  States whose `done`
+ * is set are skipped.  This is GetRegistrationResultAndCorrespondences of Open3D's
+ * RegistrationICP (icp.py:97-103, upstream). */
+size_t isr_icp_workspace_bytes(int64_t ns, int64_t nt, int64_t starts);
+int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, int64_t ns,
+                       const float *tgt, const float *tgt_soa, int64_t nt, int64_t nt_pad,
+                       double max_dist, double *sums, int32_t *corr_idx, uint8_t *inlier,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Consume sums[starts][17] (already reduced over all source shards): set fitness / rmse
+ * (ns_total = global source count), apply Open3D's break test against the previous
+ * evaluation, and otherwise solve Kabsch (Eigen::umeyama without scaling, 3x3 Jacobi SVD,
+ * det-sign fix) and update T <- U T.  `final_eval` != 0 marks the evaluation after the
+ * last allowed update (sets done).  TransformationEstimationPointToPoint, icp.py:101-103. */
+int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64_t ns_total,
+                  double rel_fitness, double rel_rmse, int final_eval, void *stream);
+
+/* Full loop: states[i].T must hold init_i (other fields zero).  Enqueues
+ * max_iteration + 1 evaluation passes; converged starts skip the rest on the device.
+ * o3d.pipelines.registration.registration_icp, icp.py:101-103; with max_iteration == 0
+ * it is evaluate_registration, icp.py:97-98. */
+int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, int64_t ns,
+                const float *tgt, const float *tgt_soa, int64_t nt, int64_t nt_pad,
+                double max_dist, int max_iteration, double rel_fitness, double rel_rmse,
+                double *sums, int32_t *corr_idx, uint8_t *inlier, void *workspace,
+                size_t workspace_bytes, void *stream);
+
+/* ---- measurement helpers ------------------------------------------------------------ */
+/* FFMA-chain microbenchmark: launches `blocks` x 256 threads, each running `iters`
+ * rounds of 16 independent FMAs (packed != 0: fma.rn.f32x2).  flops_out_host receives the
+ * number of FP32 flops executed.  Used by bench.py to report the measured FP32 peak. */
+int isr_bench_ffma(int blocks, int iters, int packed, float *sink, double *flops_out_host,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISR_H_ */

@@ -1,0 +1,48 @@
+"""Developer probe (not the bench): raw kernel timings on one GPU."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import imagesequenceregistrationfor6dposeestimationlabeling_b200 as isr
+from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth, api, _lib
+
+torch.cuda.set_device(0)
+def timeit(fn, reps=3, warm=1):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return min(ts), float(np.median(ts))
+
+print("ffma scalar TF/s", isr.measure_fp32_peak(False), "packed", isr.measure_fp32_peak(True))
+which = sys.argv[1:] or ["nn", "verify", "icp"]
+if "nn" in which:
+    N = 100000
+    cloud = synth.make_cloud(N, 1)
+    for B in (32, 128):
+        P = np.tile(np.eye(4), (B, 1, 1))
+        rng = np.random.default_rng(0)
+        for k in range(B): P[k, :3, :3] = synth.random_rotation(rng)
+        q = api.pack_soa(cloud, P); t = api.pack_soa(cloud)
+        for idx in (False, True):
+            best, med = timeit(lambda: api.nearest_neighbors_soa(q, t, return_index=idx))
+            fl = 8.0 * N * N * B
+            print(f"nn B={B} idx={idx}: {best*1e3:.1f} ms best, {med*1e3:.1f} med -> {fl/best/1e12:.2f} TF/s algorithmic ({fl/best/1e12/74.5*100:.1f}% of 74.5)")
+if "verify" in which:
+    N = 100000; B = 256
+    cloud = synth.make_cloud(N, 1)
+    R_true, _ = synth.true_pose(3)
+    Rs, _, k0 = synth.make_candidates(B, 10, R_true=R_true, t_true=np.zeros(3))
+    Mq, Mt = synth.verification_matrices(Rs, R_true)
+    cd = api._points(cloud, api._device()); Mqd = api._poses(Mq, api._device()); Mtd = api._poses(Mt, api._device())
+    best, med = timeit(lambda: isr.verify_poses(cd, Mqd, Mtd), reps=2)
+    print(f"verify B={B}: {best:.3f}s -> {B/best:.1f} cand/s; {16.0*N*N*B/best/1e12:.2f} TF/s")
+if "icp" in which:
+    src, tgt, _ = synth.icp_pair(1000000, 1000000, 4, 5)
+    prob = isr.IcpProblem(src, tgt, np.eye(4)[None])
+    def one():
+        prob.accumulate(20.0); prob.solve(prob.ns, 0.0, 0.0, False)
+    best, med = timeit(one, reps=2)
+    print(f"icp 1Mx1M one iteration: {best:.3f}s -> {1/best:.2f} it/s; {8e12/best/1e12:.2f} TF/s")

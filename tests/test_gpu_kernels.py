@@ -1,0 +1,329 @@
+"""GPU parity tests proper: every call goes through the C ABI (csrc/libisr.so)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_poses(b, seed, trans=100.0):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    rng = np.random.default_rng(seed)
+    P = np.tile(np.eye(4), (b, 1, 1))
+    for k in range(b):
+        P[k, :3, :3] = synth.random_rotation(rng)
+        P[k, :3, 3] = rng.normal(scale=trans, size=3)
+    return P
+
+
+# ---- K1 ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 5, 256, 1000, 4099])
+def test_transform_points_matches_float64(gpu, n):
+    rng = np.random.default_rng(n)
+    pts = rng.normal(scale=60, size=(n, 3)).astype(np.float32)
+    P = _rand_poses(7, n + 1, trans=700.0)
+    got = gpu.transform_points(pts, P).cpu().numpy()
+    ref = np.stack([oracle.transform(pts, P[k]) for k in range(len(P))])
+    assert got.shape == (7, n, 3) and got.dtype == np.float32
+    # FP64 math, one rounding to float32: at most half an ulp from the float64 result
+    # (+1 ulp slack for the different summation order inside BLAS)
+    ulp = np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64)
+    assert np.all(np.abs(got.astype(np.float64) - ref) <= 1.0 * ulp)
+
+
+def test_pack_soa_layout_and_padding(gpu):
+    pts = np.arange(30, dtype=np.float32).reshape(10, 3)
+    soa = gpu.pack_soa(pts)
+    d = soa.data.cpu().numpy()
+    assert d.shape == (1, 3, 1024) and soa.n == 10
+    np.testing.assert_array_equal(d[0, :, :10], pts.T)
+    assert np.all(d[0, :, 10:] == np.float32(1e18))
+
+
+# ---- K2 ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("nq,nt", [(1, 1), (7, 3), (1000, 1000), (1025, 4097), (3000, 20000),
+                                   (300, 70000)])
+def test_nn_bit_exact_vs_fma_emulation(gpu, nq, nt):
+    """d2 bits and indices equal the C float32 emulation of the kernel's rounding sequence."""
+    rng = np.random.default_rng(nq * 7 + nt)
+    q = rng.normal(scale=40, size=(nq, 3)).astype(np.float32)
+    t = rng.normal(scale=40, size=(nt, 3)).astype(np.float32)
+    res = gpu.nearest_neighbors(q, t)
+    d2, idx = res.d2.cpu().numpy(), res.idx.cpu().numpy()
+    rd2, ridx = c_oracle.nn_f32_fma(q, t)
+    np.testing.assert_array_equal(d2.view(np.uint32), rd2.view(np.uint32))
+    np.testing.assert_array_equal(idx, ridx)
+
+
+def test_nn_indices_match_float64_oracle_on_surface_cloud(gpu):
+    """FP32 direct-difference argmin == float64 KD-tree argmin."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    t = synth.make_cloud(100000, seed=1)
+    q = synth.make_cloud(20000, seed=2)
+    for offset in (np.zeros(3, np.float32), np.array([0, 0, 700], np.float32)):
+        res = gpu.nearest_neighbors(q + offset, t + offset)
+        dk, ik = oracle.nearest(q + offset, t + offset)
+        idx = res.idx.cpu().numpy()
+        mism = np.nonzero(idx != ik)[0]
+        # any mismatch must be a float32-resolution tie in the oracle's own distances
+        if len(mism):
+            d_alt = np.linalg.norm((q + offset)[mism].astype(np.float64)
+                                   - (t + offset)[idx[mism]].astype(np.float64), axis=1)
+            assert np.all(np.abs(d_alt - dk[mism]) <= 1e-6 * np.maximum(dk[mism], 1e-3))
+        assert len(mism) <= 2
+        np.testing.assert_allclose(res.dist.cpu().numpy(), dk, rtol=1e-5, atol=1e-6)
+
+
+def test_nn_lattice_ties_pick_lowest_index(gpu):
+    g = np.stack(np.meshgrid(np.arange(6), np.arange(6), np.arange(6), indexing="ij"), -1)
+    t = g.reshape(-1, 3).astype(np.float32)
+    t = np.concatenate([t, t], axis=0)  # every target duplicated: ties everywhere
+    q = (g.reshape(-1, 3) + 0.5).astype(np.float32)  # cell centres: 8-way ties (x2)
+    res = gpu.nearest_neighbors(q, t)
+    rd2, ridx = c_oracle.nn_f32_fma(q, t)
+    np.testing.assert_array_equal(res.idx.cpu().numpy(), ridx)
+    assert np.all(res.idx.cpu().numpy() < len(t) // 2)
+    np.testing.assert_array_equal(res.d2.cpu().numpy(), rd2)
+
+
+def test_nn_identical_and_shifted_clouds(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    a = synth.make_cloud(5000, seed=9)
+    res = gpu.nearest_neighbors(a, a)
+    assert np.all(res.d2.cpu().numpy() == 0)
+    d64, i64 = c_oracle.nn_f64(a, a)
+    np.testing.assert_array_equal(res.idx.cpu().numpy(), i64)  # identity unless duplicates
+    assert float(gpu.chamfer_distance(a, a)) == 0.0
+
+
+def test_nn_batched_shared_target(gpu):
+    rng = np.random.default_rng(3)
+    q = rng.normal(scale=30, size=(5, 700, 3)).astype(np.float32)
+    t = rng.normal(scale=30, size=(2500, 3)).astype(np.float32)
+    res = gpu.nearest_neighbors(q, t)
+    for b in range(5):
+        rd2, ridx = c_oracle.nn_f32_fma(q[b], t)
+        np.testing.assert_array_equal(res.d2[b].cpu().numpy(), rd2)
+        np.testing.assert_array_equal(res.idx[b].cpu().numpy(), ridx)
+
+
+def test_chamfer_and_distance_match_oracle(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    a = synth.make_cloud(30000, seed=11)
+    b = synth.make_cloud(25000, seed=12)
+    np.testing.assert_allclose(float(gpu.chamfer_distance(a, b)), oracle.chamfer(a, b), rtol=1e-6)
+    d = gpu.point_cloud_distance(a, b).cpu().numpy()
+    np.testing.assert_allclose(d, oracle.compute_point_cloud_distance(a, b), rtol=1e-5, atol=1e-6)
+    assert np.all(gpu.point_cloud_distance(a, np.zeros((0, 3))).cpu().numpy() == 0)
+
+
+# ---- verification ---------------------------------------------------------------------
+def test_verify_chamfer_matches_oracle_and_selects_k0(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    cloud = synth.make_cloud(20000, seed=1)
+    R_true, _ = synth.true_pose(3)
+    Rs, _, k0 = synth.make_candidates(40, seed=10, R_true=R_true, t_true=np.zeros(3))
+    Mq, Mt = synth.verification_matrices(Rs, R_true)
+    res = gpu.verify_poses(cloud, Mq, Mt, mode="chamfer")
+    ref, ref_best = oracle.verify_matrices(cloud, cloud, Mq, Mt, bidirectional=True)
+    np.testing.assert_allclose(res.losses.cpu().numpy(), ref, rtol=1e-5)
+    assert res.best_index == ref_best == k0
+    np.testing.assert_allclose(res.best_loss, ref[ref_best], rtol=1e-5)
+
+
+def test_verify_reference_loop_form(gpu):
+    """Same numbers as the literal loop of verfication.py:61-108 (image pairs i, i+1)."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import helpers, synth
+    pc1 = synth.make_cloud(8000, seed=4)
+    rng = np.random.default_rng(0)
+    n = 9
+    gt_R = [synth.random_rotation(rng) for _ in range(n)]
+    gt_T = [rng.normal(scale=50, size=3) + [0, 0, 700] for _ in range(n)]
+    pred_R = [gt_R[i] @ synth.rotvec_to_matrix(rng.normal(scale=0.05, size=3)) for i in range(n)]
+    pred_T = [gt_T[i] + rng.normal(scale=2, size=3) for i in range(n)]
+    ref_list, ref_idx, ref_min = oracle.verify_chamfer(pc1, gt_R, gt_T, pred_R, pred_T)
+    Mq = np.tile(np.eye(4), (n - 1, 1, 1))
+    Mt = np.tile(np.eye(4), (n - 1, 1, 1))
+    for i in range(n - 1):
+        R_rel, _ = helpers.calculate_relative_pose(gt_R[i], gt_T[i], gt_R[i + 1], gt_T[i + 1])
+        Mq[i, :3, :3] = pred_R[i + 1].T            # pcpred = pc1 . R2pred
+        Mt[i, :3, :3] = R_rel.T @ pred_R[i]        # pcgt = pc1 . R1pred^T . R_rel
+    res = gpu.verify_poses(pc1, Mq, Mt, mode="chamfer")
+    np.testing.assert_allclose(res.losses.cpu().numpy(), ref_list, rtol=1e-5)
+    assert res.best_index == ref_idx
+    np.testing.assert_allclose(res.best_loss, ref_min, rtol=1e-5)
+
+
+def test_verify_duplicates_first_min_and_invalid_mask(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    cloud = synth.make_cloud(3000, seed=2)
+    P = _rand_poses(6, 5, trans=0.0)
+    Mq = np.concatenate([P, P])          # candidates 6..11 duplicate 0..5
+    Mt = np.tile(np.eye(4), (12, 1, 1))
+    res = gpu.verify_poses(cloud, Mq, Mt)
+    losses = res.losses.cpu().numpy()
+    np.testing.assert_array_equal(losses[:6], losses[6:])   # deterministic, bit-identical
+    assert res.best_index == int(np.argmin(losses)) < 6
+    valid = np.ones(12, dtype=bool)
+    valid[res.best_index] = False
+    res2 = gpu.verify_poses(cloud, Mq, Mt, valid_mask=valid)
+    assert res2.best_index == res.best_index + 6
+    assert np.isinf(res2.losses.cpu().numpy()[res.best_index])
+
+
+def test_adds_matches_sklearn_restatement(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    surface = synth.make_cloud(15000, seed=1).astype(np.float64)
+    verts = synth.make_cloud(4000, seed=3).astype(np.float64)
+    P = _rand_poses(5, 1, trans=5.0)
+    G = _rand_poses(5, 2, trans=5.0)
+    got = gpu.adds(verts, G[:, :3, :3], G[:, :3, 3], P[:, :3, :3], P[:, :3, 3], surface).cpu().numpy()
+    for k in range(5):
+        ref = oracle.ADDS(verts, G[k, :3, :3], G[k, :3, 3], P[k, :3, :3], P[k, :3, 3], surface)
+        np.testing.assert_allclose(got[k], ref, rtol=1e-5)
+
+
+# ---- ICP --------------------------------------------------------------------------------
+def _close_T(T, Tref, rtol=1e-5):
+    assert np.linalg.norm(T[:3, :3] - Tref[:3, :3]) <= rtol * np.linalg.norm(Tref[:3, :3])
+    assert np.linalg.norm(T[:3, 3] - Tref[:3, 3]) <= rtol * max(np.linalg.norm(Tref[:3, 3]), 1.0)
+
+
+def test_evaluate_registration_matches_oracle(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    src, tgt, _ = synth.icp_pair(20000, 25000, 6, 7, half=True)
+    T = synth.pose_matrix(synth.rotvec_to_matrix([0.01, -0.02, 0.015]), [0.5, -0.3, 0.2])
+    r = gpu.evaluate_registration(src, tgt, 20.0, T)
+    o = oracle.evaluate_registration(src, tgt, 20.0, T)
+    assert r.n_corr == len(o.correspondence_set)
+    assert r.fitness == o.fitness
+    np.testing.assert_allclose(r.inlier_rmse, o.inlier_rmse, rtol=1e-6)
+    cs = r.correspondence_set
+    assert cs.shape == o.correspondence_set.shape
+    assert np.mean(cs[:, 1] == o.correspondence_set[:, 1]) > 0.9999
+    np.testing.assert_array_equal(cs[:, 0], o.correspondence_set[:, 0])
+
+
+def test_icp_matches_oracle(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    src, tgt, Tm = synth.icp_pair(30000, 30000, 4, 5)
+    r = gpu.icp(src, tgt, np.eye(4), 20.0)
+    o = oracle.registration_icp(src, tgt, 20.0, np.eye(4))
+    assert r.iterations == o.iterations
+    _close_T(r.transformation, o.transformation)
+    assert abs(r.fitness - o.fitness) <= 1.0 / len(src)
+    np.testing.assert_allclose(r.inlier_rmse, o.inlier_rmse, rtol=1e-5)
+
+
+def test_icp_recovers_known_motion_and_converges(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    tgt = synth.make_cloud(20000, seed=8)
+    Tm = synth.pose_matrix(synth.rotvec_to_matrix([0.004, 0.003, -0.005]), [0.05, -0.04, 0.03])
+    src = oracle.transform(tgt, Tm).astype(np.float32)
+    r = gpu.icp(src, tgt, np.eye(4), 20.0)
+    assert r.fitness == 1.0 and r.iterations < 30 and r.converged
+    np.testing.assert_allclose(r.transformation, np.linalg.inv(Tm), atol=2e-5)
+
+
+def test_icp_script_flow_config1_small(gpu):
+    """icp.py:64-117 end to end (camera-frame source, init = inverse predicted pose)."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    import imagesequenceregistrationfor6dposeestimationlabeling_b200.o3d_compat as o3d
+    upper = synth.make_cloud(20000, seed=1, half="upper")
+    lower = synth.make_cloud(20000, seed=2, half="lower")
+    cad = synth.make_cloud(10000, seed=3).astype(np.float64)
+    R_GT, t_GT = synth.true_pose(3)
+    R_pred = R_GT @ synth.rotvec_to_matrix(np.deg2rad(2.0) * np.array([0.6, 0.0, 0.8]))
+    t_pred = t_GT + np.array([1.2, -1.0, 1.2])
+    ev_o, reg_o, ch_o = oracle.icp_script(upper, lower, R_GT, t_GT, R_pred, t_pred, cad)
+
+    actual_upper = upper.dot(R_GT.T) + t_GT
+    source = o3d.geometry.PointCloud()
+    source.points = o3d.utility.Vector3dVector(actual_upper)
+    target = o3d.geometry.PointCloud()
+    target.points = o3d.utility.Vector3dVector(lower)
+    M = np.eye(4); M[:3, :3] = R_pred; M[:3, 3] = t_pred
+    init = np.linalg.inv(M)
+    ev = o3d.pipelines.registration.evaluate_registration(source, target, 20, init)
+    reg = o3d.pipelines.registration.registration_icp(
+        source, target, 20, init, o3d.pipelines.registration.TransformationEstimationPointToPoint())
+    assert abs(ev.fitness - ev_o.fitness) <= 1.0 / len(upper)
+    np.testing.assert_allclose(ev.inlier_rmse, ev_o.inlier_rmse, rtol=1e-5)
+    _close_T(reg.transformation, reg_o.transformation)
+    assert abs(reg.fitness - reg_o.fitness) <= 1.0 / len(upper)
+    np.testing.assert_allclose(reg.inlier_rmse, reg_o.inlier_rmse, rtol=1e-5)
+    assert "RegistrationResult with fitness=" in repr(reg)
+    transformed_source = source.transform(reg.transformation)
+    assert transformed_source is source
+    full = transformed_source + target
+    assert len(full) == len(upper) + len(lower)
+    cadpc = o3d.geometry.PointCloud(); cadpc.points = o3d.utility.Vector3dVector(cad)
+    d1 = np.mean(np.asarray(full.compute_point_cloud_distance(cadpc)))
+    d2 = np.mean(np.asarray(cadpc.compute_point_cloud_distance(full)))
+    np.testing.assert_allclose((d1 + d2) / 2, ch_o, rtol=1e-5)
+
+
+def test_icp_threshold_edge_and_empty_correspondences(gpu):
+    tgt = np.array([[0, 0, 0], [100, 0, 0]], dtype=np.float32)
+    src = np.array([[0, 0, 20.0], [100, 0, 20.0 * (1 - 1e-6)]], dtype=np.float32)
+    r = gpu.evaluate_registration(src, tgt, 20.0)
+    assert r.n_corr == 1 and r.fitness == 0.5          # d == thr is excluded (strict <)
+    np.testing.assert_array_equal(r.correspondence_set, [[1, 1]])
+    far = src + np.float32(1000)
+    r = gpu.icp(far, tgt, np.eye(4), 20.0)
+    assert r.n_corr == 0 and r.fitness == 0 and r.inlier_rmse == 0
+    np.testing.assert_array_equal(r.transformation, np.eye(4))
+    o = oracle.registration_icp(far, tgt, 20.0, np.eye(4))
+    assert r.iterations == o.iterations == 1
+
+
+def test_multistart_icp_matches_individual_runs(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    src, tgt, _ = synth.icp_pair(8000, 9000, 6, 7)
+    inits = np.stack([synth.pose_matrix(synth.rotvec_to_matrix([0, 0, 2 * np.pi * k / 8]), [0, 0, 0])
+                      for k in range(8)])
+    ms = gpu.multistart_icp(src, tgt, inits, 20.0, max_iteration=15)
+    for k in (0, 3, 5):
+        single = gpu.icp(src, tgt, inits[k], 20.0, max_iteration=15)
+        np.testing.assert_array_equal(ms.results[k].transformation, single.transformation)
+        assert ms.results[k].iterations == single.iterations
+        o = oracle.registration_icp(src, tgt, 20.0, inits[k], max_iteration=15)
+        _close_T(ms.results[k].transformation, o.transformation, rtol=1e-4)
+    assert ms.order[0] == int(np.argmin(ms.chamfer))
+    ch0 = oracle.chamfer(oracle.transform(src, ms.results[0].transformation), tgt)
+    np.testing.assert_allclose(ms.chamfer[0], ch0, rtol=1e-5)
+
+
+def test_kdtree_shim_and_helpers(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import helpers, synth
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200.compat import KDTree
+    surface = synth.make_cloud(5000, seed=1).astype(np.float64)
+    verts = synth.make_cloud(1200, seed=3).astype(np.float64)
+    d, i = KDTree(surface, leaf_size=2).query(verts, k=1)
+    dk, ik = oracle.nearest(verts.astype(np.float32), surface.astype(np.float32))
+    assert d.shape == (1200, 1) and i.shape == (1200, 1) and i.dtype == np.int64
+    np.testing.assert_array_equal(i[:, 0], ik)
+    np.testing.assert_allclose(d[:, 0], dk, rtol=1e-5)
+    P = _rand_poses(2, 3, trans=4.0)
+    a = helpers.ADD(verts, P[0, :3, :3], P[0, :3, 3], P[1, :3, :3], P[1, :3, 3])
+    np.testing.assert_allclose(a, oracle.ADD(verts, P[0, :3, :3], P[0, :3, 3], P[1, :3, :3], P[1, :3, 3]),
+                               rtol=1e-5)
+    helpers.surfacePointsScaled = surface
+    s = helpers.ADDS(verts, P[0, :3, :3], P[0, :3, 3], P[1, :3, :3], P[1, :3, 3])
+    np.testing.assert_allclose(
+        s, oracle.ADDS(verts, P[0, :3, :3], P[0, :3, 3], P[1, :3, :3], P[1, :3, 3], surface), rtol=1e-5)
+    helpers.surfacePointsScaled = None
+
+
+def test_bad_arguments_raise(gpu):
+    with pytest.raises(ValueError):
+        gpu.nearest_neighbors(np.zeros((4, 2)), np.zeros((4, 3)))
+    with pytest.raises(ValueError):
+        gpu.nearest_neighbors(np.zeros((4, 3)), np.zeros((0, 3)))
+    with pytest.raises(ValueError):
+        gpu.verify_poses(np.zeros((4, 3)), np.zeros((2, 4, 4)), np.zeros((3, 4, 4)))
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import _lib
+    lib = _lib.load()
+    st = lib.isr_nn_soa(None, 5, 1000, 0, None, 5, 1024, 0, 1, None, None, None, 0, None, 0, None)
+    assert st < 0 and len(lib.isr_last_error()) > 0
