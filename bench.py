@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Bench of the registration-and-verification hot path (BASELINE.json metric:
+"candidate poses verified/sec @100k pts; ICP iters/sec @1M pts; % FP32 peak").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one pass of the hot path over one batch of synthetic input: the Chamfer
+verification of `--candidates` (default 1000 = BASELINE configs[1], T-LESS-shaped)
+PnP-RANSAC candidate poses against a 100k-point cloud, including the best-pose selection.
+With N > 1 (torchrun, one rank per GPU) every rank scores its own 1000 candidates (weak
+scaling, BASELINE configs[2] shards candidates) and the ranks agree on the argmin through
+NCCL inside the timed region.  Rank 0 prints ONE JSON line.
+
+  value      candidates/s with all inputs resident in HBM (device-timed, max over ranks)
+  e2e        the same through the public API with pinned HOST inputs and the result read
+             back to the host every step (copies inside the timed region)
+  roofline   the nearest-neighbour kernel (K2): algorithmic FP32 flops (8 per point pair,
+             SURVEY.md 8(d)) / its live CUDA-event duration, against the FP32 CUDA-core peak
+  cpu_baseline  the float64 CPU oracle (scipy cKDTree stand-in for Open3D) on a bounded
+             sample of the same candidates, on this box's host cores
+  secondary  ICP iterations/s on a 1M x 1M pair (BASELINE configs[3], per rank source shard
+             under N > 1) and the K1 / K3 HBM rooflines
+
+`--impl reference` times the reference's own CPU path instead (its arithmetic lives in
+Open3D, not installable here, so the oracle port stands in): same metric, unit and config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "candidate poses verified/sec @100k pts"
+UNIT = "candidates/s"
+N_POINTS = 100_000
+CLOUD_SEED, POSE_SEED, CAND_SEED = 1, 3, 10
+FLOP_PER_PAIR = 8.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--candidates", type=int, default=1000, help="candidates per GPU per step")
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--icp-points", type=int, default=1_000_000)
+    ap.add_argument("--icp-iters", type=int, default=10)
+    ap.add_argument("--skip-icp", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def make_workload(n_points, n_cand, world):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+
+    cloud = synth.make_cloud(n_points, CLOUD_SEED)
+    R_true, _ = synth.true_pose(POSE_SEED)
+    Rs, _, k0 = synth.make_candidates(n_cand * world, CAND_SEED, R_true=R_true, t_true=np.zeros(3))
+    Mq, Mt = synth.verification_matrices(Rs, R_true)
+    return cloud, Mq, Mt, k0
+
+
+def config_dict(args, world):
+    return {
+        "workload": f"T-LESS-shaped pose verification (BASELINE configs[1]): {args.candidates} "
+                    f"PnP-RANSAC candidates x {args.points}-pt cloud per GPU, bidirectional Chamfer "
+                    "+ first-min selection",
+        "candidates_per_gpu": args.candidates,
+        "points": args.points,
+        "global_candidates": args.candidates * world,
+        "parallelism": f"candidate-sharded x{world}" if world > 1 else "single GPU",
+        "l2_policy": "inputs larger than L2: each step streams 2 x candidates x 1.2 MB of "
+                     "transformed clouds (2.4 GB at 1000 candidates) through a 126 MB L2",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "power_w_max": float(max(pw)) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_verify_sample(cloud, Mq, Mt, seconds_target=15.0, max_n=256):
+    """Oracle (float64, scipy cKDTree with every host thread) on the first n candidates."""
+    from oracle import oracle
+
+    t0 = time.perf_counter()
+    oracle.verify_matrices(cloud, cloud, Mq[:2], Mt[:2], bidirectional=True)
+    per = (time.perf_counter() - t0) / 2
+    n = int(min(max_n, max(4, seconds_target / max(per, 1e-3)), len(Mq)))
+    t0 = time.perf_counter()
+    losses, best = oracle.verify_matrices(cloud, cloud, Mq[:n], Mt[:n], bidirectional=True)
+    dt = time.perf_counter() - t0
+    return n, dt, losses
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port: Open3D not installable)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from oracle import oracle
+
+    cloud, Mq, Mt, k0 = make_workload(args.points, args.candidates, 1)
+    cores = len(os.sched_getaffinity(0))
+    t0 = time.perf_counter()
+    oracle.verify_matrices(cloud, cloud, Mq[:2], Mt[:2], bidirectional=True)
+    per = (time.perf_counter() - t0) / 2
+    total = args.steps + args.warmup
+    s = int(min(64, max(2, 90.0 / max(per * total, 1e-3))))
+    times = []
+    for it in range(total):
+        lo = (it * s) % max(1, len(Mq) - s)
+        t0 = time.perf_counter()
+        oracle.verify_matrices(cloud, cloud, Mq[lo:lo + s], Mt[lo:lo + s], bidirectional=True)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    tot = float(np.sum(times))
+    value = s * len(times) / tot
+    sample = (f"{s} of the {args.candidates} candidates per step (float64 KD-tree Chamfer, both "
+              f"directions, {args.points} pts), scipy cKDTree workers=-1 as the Open3D stand-in")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as td
+
+    import imagesequenceregistrationfor6dposeestimationlabeling_b200 as isr
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import _lib, api, dist, synth
+
+    rank, world = dist.init_from_env()
+    if world != args.gpus and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    lib = _lib.load()
+
+    cloud, Mq, Mt, k0 = make_workload(args.points, args.candidates, world)
+    lo, hi = dist.shard_bounds(len(Mq), rank, world)
+    b_local = hi - lo
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident arm: `value` + roofline -------------------------
+    cloud_d = api._points(cloud, dev)
+    Mq_d = api._poses(Mq[lo:hi], dev)
+    Mt_d = api._poses(Mt[lo:hi], dev)
+    off = torch.tensor([lo], dtype=torch.int64, device=dev)
+
+    def step_resident():
+        res = api.verify_poses(cloud_d, Mq_d, Mt_d, mode="chamfer")
+        return dist.global_first_argmin(res.best[1:2].view(torch.float64), res.best[0:1] + off)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    lib.isr_profile_enable(1)
+    lib.isr_profile_collect(None, None)
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        best_loss, best_idx = step_resident()
+    e1.record()
+    barrier()
+    t_resident = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    launches = _lib.launch_count()
+    ms_kind = (ctypes.c_double * 5)()
+    n_kind = (ctypes.c_uint64 * 5)()
+    _lib.check(lib.isr_profile_collect(ms_kind, n_kind))
+    lib.isr_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    sel_idx, sel_loss = int(best_idx.item()), float(best_loss.item())
+
+    value = args.candidates * world * args.steps / t_resident
+    nn_ms, nn_launches = float(ms_kind[1]), int(n_kind[1])
+    pairs_total = 2.0 * args.points * args.points * b_local * args.steps  # both directions
+    achieved = FLOP_PER_PAIR * pairs_total / (nn_ms * 1e-3) / 1e12 if nn_ms > 0 else None
+
+    # ---------------- end-to-end arm: host buffers in, host result out -------------------
+    cloud_h = torch.from_numpy(cloud).pin_memory()
+    Mq_h = torch.from_numpy(np.ascontiguousarray(Mq[lo:hi])).pin_memory()
+    Mt_h = torch.from_numpy(np.ascontiguousarray(Mt[lo:hi])).pin_memory()
+    losses_h = torch.empty((b_local,), dtype=torch.float64).pin_memory()
+    h2d = cloud_h.numel() * 4 + Mq_h.numel() * 8 + Mt_h.numel() * 8
+    d2h = losses_h.numel() * 8 + 16
+
+    def step_e2e():
+        res = api.verify_poses(cloud_h, Mq_h, Mt_h, mode="chamfer")  # H2D inside
+        bl, bi = dist.global_first_argmin(res.best[1:2].view(torch.float64), res.best[0:1] + off)
+        losses_h.copy_(res.losses, non_blocking=True)
+        return int(bi.item()), float(bl.item())  # D2H + sync
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_idx, e2e_loss = step_e2e()
+    e1.record()
+    barrier()
+    t_e2e = max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, 0.0))
+    t_e2e_wall = max_over_ranks(time.perf_counter() - t0)
+    t_e2e = max(t_e2e, t_e2e_wall)
+    e2e_value = args.candidates * world * args.steps / t_e2e
+    assert e2e_idx == sel_idx, (e2e_idx, sel_idx)
+
+    # ---------------- FP32 peak (nominal + live FFMA chain) ------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    sm_count = ctypes.c_int(0)
+    clock_khz = ctypes.c_int(0)
+    _lib.check(lib.isr_device_info(ctypes.byref(sm_count), ctypes.byref(clock_khz), None))
+    sm_max_mhz = float(peaks.get("sm_max_mhz", clock_khz.value / 1e3))
+    peak_nominal = sm_count.value * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    ffma_measured = api.measure_fp32_peak(packed=False)
+
+    # ---------------- secondary: ICP iterations/s on a 1M x 1M pair ----------------------
+    secondary = {}
+    if not args.skip_icp:
+        src, tgt, _ = synth.icp_pair(args.icp_points, args.icp_points, 4, 5)
+        slo, shi = dist.shard_bounds(len(src), rank, world)
+        prob = api.IcpProblem(src[slo:shi], tgt, np.eye(4)[None])
+
+        def icp_iter(final=False):
+            sums = prob.accumulate(20.0)
+            if world > 1:
+                td.all_reduce(sums, op=td.ReduceOp.SUM)
+            prob.solve(len(src), 0.0, 0.0, final, sums)
+
+        icp_iter()
+        barrier()
+        lib.isr_profile_enable(1)
+        lib.isr_profile_collect(None, None)
+        e0.record()
+        for k in range(args.icp_iters):
+            icp_iter()
+        e1.record()
+        barrier()
+        t_icp = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        _lib.check(lib.isr_profile_collect(ms_kind, n_kind))
+        lib.isr_profile_enable(0)
+        r = prob.results(with_correspondences=False)[0]
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        ns_local = shi - slo
+        k1_bytes = ns_local * 12 + ns_local * 12            # read AoS + write SoA planes
+        k3_bytes = ns_local * 32                            # 12 src + 4 idx + 4 d2 + 12 tgt
+        secondary = {
+            "icp_iters_per_s": args.icp_iters / t_icp,
+            "icp_config": f"dense ICP refine (BASELINE configs[3]): {args.icp_points} x {args.icp_points} "
+                          f"points, {args.icp_iters} forced iterations, source sharded x{world}",
+            "icp_nn_tflops": FLOP_PER_PAIR * ns_local * args.icp_points * n_kind[1] / (ms_kind[1] * 1e-3) / 1e12,
+            "icp_fitness": r.fitness, "icp_inlier_rmse": r.inlier_rmse,
+            "k1_transform_gbs": k1_bytes * n_kind[0] / (ms_kind[0] * 1e-3) / 1e9 if ms_kind[0] > 0 else None,
+            "k3_gather_reduce_gbs": k3_bytes * n_kind[3] / (ms_kind[3] * 1e-3) / 1e9 if ms_kind[3] > 0 else None,
+            "hbm_peak_gbs": hbm,
+        }
+        del prob
+
+    # ---------------- CPU baseline (rank 0, N == 1 only) ---------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        n_cpu, dt_cpu, cpu_losses = cpu_verify_sample(cloud, Mq, Mt)
+        res = api.verify_poses(cloud_d, api._poses(Mq[:n_cpu], dev), api._poses(Mt[:n_cpu], dev))
+        gl = res.losses.cpu().numpy()
+        rel = float(np.max(np.abs(gl - cpu_losses) / np.abs(cpu_losses)))
+        assert rel < 1e-5, f"GPU losses differ from the oracle: {rel}"
+        assert res.best_index == int(np.argmin(cpu_losses))
+        cpu = {"value": n_cpu / dt_cpu, "unit": UNIT, "cores": len(os.sched_getaffinity(0)),
+               "kind": "port",
+               "sample": f"first {n_cpu} of the {args.candidates} candidates, float64 scipy cKDTree "
+                         f"(workers=-1) Chamfer; GPU losses on the same sample agree to {rel:.1e} rel"}
+
+    if rank != 0:
+        return
+
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    per_launch_flop = FLOP_PER_PAIR * pairs_total / max(nn_launches, 1)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_resident / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(args, world),
+        "selected_candidate": sel_idx, "planted_candidate": k0, "selected_loss": sel_loss,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {
+            "kernel": "nn_kernel (K2 brute-force nearest neighbour)",
+            "bound": "fp32", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
+            "frac": achieved / peak_nominal if achieved else None,
+            "peak_source": f"nominal {sm_count.value} SM x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz "
+                           "(MEASURED_PEAKS.json holds no FP32 CUDA-core figure)",
+            "peak_measured_ffma": ffma_measured,
+            "frac_of_measured_ffma": achieved / ffma_measured if achieved else None,
+            "instruction_mix_ceiling": 8.0 / 12.0,
+            "flop_per_launch": per_launch_flop, "launches": nn_launches,
+            "avg_launch_ms": nn_ms / max(nn_launches, 1),
+            "kernel_share_of_step": nn_ms * 1e-3 / t_resident,
+            "traffic": traffic,
+        },
+        "cpu_baseline": cpu,
+        "secondary": secondary,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

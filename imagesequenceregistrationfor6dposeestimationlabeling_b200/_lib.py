@@ -56,6 +56,8 @@ SIGNATURES = {
     "isr_device_info": (_I, [_P, _P, _P]),
     "isr_launch_count": (ctypes.c_uint64, []),
     "isr_reset_launch_count": (None, []),
+    "isr_profile_enable": (_I, [_I]),
+    "isr_profile_collect": (_I, [_P, _P]),
     "isr_soa_padded_len": (_I64, [_I64]),
     "isr_transform_points": (_I, [_P, _I64, _P, _I64, _P, _P]),
     "isr_transform_points_soa": (_I, [_P, _I64, _P, _I64, _I64, _P, _I64, _P, _I64, _P]),

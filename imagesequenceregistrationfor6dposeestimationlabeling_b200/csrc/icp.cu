@@ -328,6 +328,7 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, in
     ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
     const int nblk = acc_blocks(ns, starts);
     dim3 grid((unsigned)nblk, (unsigned)starts);
+    ProfScope prof(kProfIcpAcc, st);
     icp_accumulate_kernel<<<grid, kAccThreads, 0, st>>>(states, src, ns, tgt, corr_idx,
                                                         max_dist * max_dist, partials, tickets, sums,
                                                         inlier);
@@ -338,6 +339,7 @@ int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64
                   double rel_fitness, double rel_rmse, int final_eval, void *stream) {
     using namespace isr;
     ISR_REQUIRE(starts >= 1 && states && sums, ISR_E_INVALID_ARG, "icp_solve: bad argument");
+    ProfScope prof(kProfIcpSolve, (cudaStream_t)stream);
     icp_solve_kernel<<<(unsigned)starts, 32, 0, (cudaStream_t)stream>>>(
         states, sums, ns_total, rel_fitness, rel_rmse, final_eval);
     return launched("icp_solve_kernel");

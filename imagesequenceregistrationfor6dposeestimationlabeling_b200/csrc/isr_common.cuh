@@ -27,6 +27,25 @@ inline int launched(const char *name) {
     return check_cuda(cudaGetLastError(), name);
 }
 
+// Optional per-kernel device timing (isr_profile_*): when enabled, a launch site brackets
+// its kernel with a pair of CUDA events on the launching stream.
+enum ProfKind { kProfTransform = 0, kProfNN = 1, kProfReduce = 2, kProfIcpAcc = 3, kProfIcpSolve = 4,
+                kProfKinds = 5 };
+bool prof_enabled();
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
+struct ProfScope {
+    int kind;
+    cudaStream_t st;
+    bool on;
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s), on(prof_enabled()) {
+        if (on) prof_begin(kind, st);
+    }
+    ~ProfScope() {
+        if (on) prof_end(kind, st);
+    }
+};
+
 #define ISR_TRY(expr)                 \
     do {                              \
         int _s = (expr);              \

@@ -243,6 +243,7 @@ struct NNVariant {
                                "nn smem attr"));
             configured_dev = dev;
         }
+        ProfScope prof(kProfNN, st);
         kern<<<grid, THREADS, kSmem, st>>>(p);
         return launched("nn_kernel");
     }
@@ -342,6 +343,7 @@ int isr_mean_sqrt(const float *d2, int64_t n, int64_t batch, double *out_mean, v
     ISR_REQUIRE(n >= 0 && batch >= 0, ISR_E_SHAPE, "mean_sqrt: negative size");
     if (batch == 0) return ISR_OK;
     ISR_REQUIRE(out_mean && (d2 || n == 0), ISR_E_INVALID_ARG, "mean_sqrt: null pointer");
+    ProfScope prof(kProfReduce, (cudaStream_t)stream);
     mean_sqrt_kernel<<<(unsigned)batch, kMeanThreads, 0, (cudaStream_t)stream>>>(d2, n, out_mean);
     return launched("mean_sqrt_kernel");
 }

@@ -119,6 +119,7 @@ int isr_transform_points(const float *pts, int64_t n, const double *poses, int64
     ISR_REQUIRE(b <= 65535, ISR_E_SHAPE, "transform_points: batch %lld > 65535", (long long)b);
     const int vec_ok = (n % 4 == 0) && aligned16(out);
     dim3 grid((unsigned)((n + kTfThreads - 1) / kTfThreads), (unsigned)b);
+    ProfScope prof(kProfTransform, (cudaStream_t)stream);
     transform_aos_kernel<<<grid, kTfThreads, 0, (cudaStream_t)stream>>>(pts, n, poses, out, vec_ok);
     return launched("transform_aos_kernel");
 }
@@ -137,6 +138,7 @@ int isr_transform_points_soa(const float *pts, int64_t n, const double *poses, i
     ISR_REQUIRE(b <= 65535, ISR_E_SHAPE, "transform_points_soa: batch %lld > 65535", (long long)b);
     ISR_REQUIRE(aligned16(out_soa), ISR_E_ALIGN, "transform_points_soa: out not 16-byte aligned");
     dim3 grid((unsigned)(npad / kTfThreads), (unsigned)b);
+    ProfScope prof(kProfTransform, (cudaStream_t)stream);
     transform_soa_kernel<<<grid, kTfThreads, 0, (cudaStream_t)stream>>>(
         pts, n, poses, pose_stride, out_soa, npad, skip, skip_stride);
     return launched("transform_soa_kernel");

@@ -58,6 +58,15 @@ int isr_device_info(int *sm_count, int *sm_clock_khz, int *smem_per_sm);
 uint64_t isr_launch_count(void);
 void isr_reset_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline: while enabled, every launch of a
+ * profiled kernel kind is bracketed by CUDA events on its stream.  collect() waits for
+ * the recorded events, writes total milliseconds and launch counts per kind
+ * (0 transform, 1 nearest-neighbour, 2 mean-sqrt reduce, 3 ICP accumulate, 4 ICP solve;
+ * arrays of ISR_PROFILE_KINDS) and clears the records. */
+#define ISR_PROFILE_KINDS 5
+int isr_profile_enable(int on);
+int isr_profile_collect(double *ms_by_kind_host, uint64_t *launches_by_kind_host);
+
 /* ---- K1: batched rigid transform ---------------------------------------------------- */
 int64_t isr_soa_padded_len(int64_t n);
 

@@ -1,0 +1,210 @@
+"""The CPU oracle against the reference's golden vectors and hand-computable known answers.
+(No GPU.)  SURVEY.md section 8(c) lists the KATs; the reference itself has no tests."""
+import os
+
+import numpy as np
+import pytest
+
+from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+from oracle import c_oracle, oracle
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_helpers.npz"))
+
+
+# ---- pinned by the reference's own functions (tests/golden/make_golden.py) ---------------
+def test_golden_add_adds():
+    n = len(GOLD["R"])
+    for i in range(n):
+        for j in range(n):
+            a = oracle.ADD(GOLD["verts"], GOLD["R"][i], GOLD["t"][i], GOLD["R"][j], GOLD["t"][j])
+            s = oracle.ADDS(GOLD["verts"], GOLD["R"][i], GOLD["t"][i], GOLD["R"][j], GOLD["t"][j],
+                            GOLD["surface"])
+            assert a == GOLD["ADD"][i, j]
+            assert s == GOLD["ADDS"][i, j]
+    for k in range(5):
+        s = oracle.ADDS(GOLD["verts"], GOLD["R"][0], GOLD["t"][0], GOLD["Rp"][k], GOLD["tp"][k],
+                        GOLD["surface"])
+        assert s == GOLD["ADDS_p"][k]
+
+
+def test_golden_relative_poses():
+    n = len(GOLD["R"])
+    for i in range(n):
+        for j in range(n):
+            r, t = oracle.compute_rel_poses(GOLD["R"][i], GOLD["t"][i], GOLD["R"][j], GOLD["t"][j])
+            np.testing.assert_array_equal(r, GOLD["rel_R"][i, j])
+            np.testing.assert_array_equal(t, GOLD["rel_t"][i, j])
+            r, t = oracle.calculate_relative_pose(GOLD["R"][i], GOLD["t"][i], GOLD["R"][j], GOLD["t"][j])
+            np.testing.assert_allclose(r, GOLD["cal_R"][i, j], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(t, GOLD["cal_T"][i, j], rtol=0, atol=1e-9)
+    tab = oracle.rel_pose_table(GOLD["R"], GOLD["t"])
+    np.testing.assert_array_equal(tab[:, :, :3, :3], GOLD["rel_R"])
+    np.testing.assert_array_equal(tab[:, :, :3, 3], GOLD["rel_t"])
+
+
+def test_adds_kdtree_equals_bruteforce_definition():
+    """sklearn KDTree(leaf_size=2) 1-NN == brute-force float64 definition."""
+    S = GOLD["surface"].dot(GOLD["Rp"][2].T) + GOLD["tp"][2]
+    V = GOLD["verts"].dot(GOLD["R"][0].T) + GOLD["t"][0]
+    d2, _ = c_oracle.nn_f64(V, S)
+    np.testing.assert_allclose(np.sqrt(d2).mean(), GOLD["ADDS_p"][2], rtol=1e-13)
+
+
+# ---- KAT 1-3: nearest neighbour ------------------------------------------------------------
+def test_identical_clouds():
+    a = synth.make_cloud(3000, seed=1)
+    d, i = oracle.nearest(a, a)
+    assert np.all(d == 0)
+    np.testing.assert_array_equal(i, np.arange(len(a)))
+    assert oracle.chamfer(a, a) == 0.0
+
+
+def test_small_shift_keeps_identity_correspondence():
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-50, 50, size=(500, 3)).round(0)          # >= 1 apart (or duplicate)
+    a = np.unique(a, axis=0)
+    delta = np.array([0.2, -0.1, 0.2])
+    d, i = oracle.nearest(a + delta, a)
+    np.testing.assert_array_equal(i, np.arange(len(a)))
+    np.testing.assert_allclose(d, np.linalg.norm(delta), rtol=1e-12)
+    np.testing.assert_allclose(oracle.chamfer(a + delta, a), np.linalg.norm(delta), rtol=1e-12)
+
+
+def test_lattice_ties_lowest_index_bruteforce():
+    g = np.stack(np.meshgrid(np.arange(4), np.arange(4), np.arange(4), indexing="ij"), -1).reshape(-1, 3)
+    t = np.concatenate([g, g]).astype(np.float32)
+    q = (g + 0.5).astype(np.float32)
+    d2, idx = c_oracle.nn_f64(q, t)
+    d2f, idxf = c_oracle.nn_f32_fma(q, t)
+    np.testing.assert_array_equal(idx, idxf)
+    assert np.all(idx < len(g)) and np.all(d2 == 0.75) and np.all(d2f == 0.75)
+    # lowest index among the 8 corners of each cell = the corner at the cell origin
+    for k in (0, 5, 21):
+        cell = g[k]
+        if np.all(cell < 3):
+            assert idx[k] == k
+
+
+def test_ckdtree_equals_bruteforce_on_surface_clouds():
+    """Pins the scipy stand-in for Open3D's nanoflann search against the definition."""
+    t = synth.make_cloud(30000, seed=1)
+    q = synth.make_cloud(4000, seed=2)
+    for off in (0.0, 700.0):
+        d, i = oracle.nearest(q + np.float32(off), t + np.float32(off))
+        d2, ib = c_oracle.nn_f64(q + np.float32(off), t + np.float32(off))
+        np.testing.assert_array_equal(i, ib)
+        np.testing.assert_allclose(d, np.sqrt(d2), rtol=1e-14)
+        # SURVEY section 7 probe: the float32 direct-difference form finds the same neighbours
+        _, i32 = c_oracle.nn_f32_fma(q + np.float32(off), t + np.float32(off))
+        assert np.mean(i32 == ib) > 0.9995
+
+
+def test_empty_target_and_source():
+    a = synth.make_cloud(10, seed=1)
+    assert np.all(oracle.compute_point_cloud_distance(a, np.zeros((0, 3))) == 0)
+    assert len(oracle.compute_point_cloud_distance(np.zeros((0, 3)), a)) == 0
+
+
+# ---- KAT 4: Kabsch ------------------------------------------------------------------------
+def test_umeyama_recovers_exact_motion_and_fixes_reflection():
+    rng = np.random.default_rng(5)
+    src = rng.normal(scale=40, size=(200, 3))
+    R = synth.random_rotation(rng)
+    t = np.array([3.0, -700.0, 12.5])
+    T = oracle.umeyama(src, src @ R.T + t)
+    np.testing.assert_allclose(T[:3, :3], R, atol=1e-12)
+    np.testing.assert_allclose(T[:3, 3], t, atol=1e-9)
+    # a mirrored target must still yield a proper rotation
+    M = np.diag([1.0, 1.0, -1.0])
+    T = oracle.umeyama(src, src @ M.T)
+    assert abs(np.linalg.det(T[:3, :3]) - 1.0) < 1e-12
+    np.testing.assert_allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-12)
+
+
+# ---- KAT 5-7: ICP -------------------------------------------------------------------------
+def test_icp_recovers_small_motion():
+    tgt = synth.make_cloud(8000, seed=8)
+    Tm = synth.pose_matrix(synth.rotvec_to_matrix([0.004, 0.003, -0.005]), [0.05, -0.04, 0.03])
+    src = oracle.transform(tgt, Tm)
+    r = oracle.registration_icp(src, tgt, 20.0, np.eye(4))
+    assert r.fitness == 1.0 and r.iterations < 30
+    np.testing.assert_allclose(r.transformation, np.linalg.inv(Tm), atol=1e-9)
+    assert r.inlier_rmse < 1e-9
+
+
+def test_icp_threshold_is_strict_and_empty_set_is_identity():
+    tgt = np.array([[0, 0, 0], [100, 0, 0]], dtype=np.float64)
+    src = np.array([[0, 0, 20.0], [100, 0, 20.0 * (1 - 1e-6)]])
+    r = oracle.evaluate_registration(src, tgt, 20.0)
+    assert r.fitness == 0.5 and len(r.correspondence_set) == 1
+    np.testing.assert_array_equal(r.correspondence_set, [[1, 1]])
+    r = oracle.registration_icp(src + 1000.0, tgt, 20.0, np.eye(4))
+    assert r.fitness == 0 and r.inlier_rmse == 0 and r.iterations == 1
+    np.testing.assert_array_equal(r.transformation, np.eye(4))
+    r = oracle.evaluate_registration(src, tgt, 0.0)
+    assert r.fitness == 0 and len(r.correspondence_set) == 0
+
+
+def test_icp_max_iteration_zero_is_evaluation():
+    src, tgt, _ = synth.icp_pair(2000, 2500, 6, 7)
+    a = oracle.registration_icp(src, tgt, 20.0, np.eye(4), max_iteration=0)
+    b = oracle.evaluate_registration(src, tgt, 20.0, np.eye(4))
+    assert a.fitness == b.fitness and a.inlier_rmse == b.inlier_rmse and a.iterations == 0
+
+
+# ---- KAT 8-9: pose algebra and selection ----------------------------------------------------
+def test_relative_pose_identities():
+    rng = np.random.default_rng(1)
+    R, t = synth.random_rotation(rng), rng.normal(size=3)
+    r, tt = oracle.calculate_relative_pose(R, t, R, t)
+    np.testing.assert_allclose(r, np.eye(3), atol=1e-14)
+    np.testing.assert_allclose(tt, 0, atol=1e-12)
+    R2, t2 = synth.random_rotation(rng), rng.normal(size=3)
+    r, tt = oracle.compute_rel_poses(R, t, R2, t2)
+    np.testing.assert_array_equal(r, R.T @ R2)
+    np.testing.assert_array_equal(tt, t2 - t)
+
+
+def test_verify_selects_first_occurrence_of_true_pose():
+    cloud = synth.make_cloud(2000, seed=1)
+    R_true, _ = synth.true_pose(3)
+    Rs, _, k0 = synth.make_candidates(10, seed=10, R_true=R_true, t_true=np.zeros(3))
+    Rs = np.concatenate([Rs, Rs[k0:k0 + 1]])  # duplicate of the best candidate at the end
+    Mq, Mt = synth.verification_matrices(Rs, R_true)
+    losses, best = oracle.verify_matrices(cloud, cloud, Mq, Mt)
+    assert best == k0 and losses[k0] == losses[-1]
+
+
+def test_verify_loop_form_equals_matrix_form():
+    pc1 = synth.make_cloud(1500, seed=4)
+    rng = np.random.default_rng(0)
+    n = 5
+    gt_R = [synth.random_rotation(rng) for _ in range(n)]
+    gt_T = [rng.normal(scale=50, size=3) for _ in range(n)]
+    pred_R = [gt_R[i] @ synth.rotvec_to_matrix(rng.normal(scale=0.05, size=3)) for i in range(n)]
+    pred_T = gt_T
+    ref, idx, mn = oracle.verify_chamfer(pc1, gt_R, gt_T, pred_R, pred_T)
+    Mq = np.tile(np.eye(4), (n - 1, 1, 1))
+    Mt = np.tile(np.eye(4), (n - 1, 1, 1))
+    for i in range(n - 1):
+        R_rel, _ = oracle.calculate_relative_pose(gt_R[i], gt_T[i], gt_R[i + 1], gt_T[i + 1])
+        Mq[i, :3, :3] = pred_R[i + 1].T
+        Mt[i, :3, :3] = R_rel.T @ pred_R[i]
+    losses, best = oracle.verify_matrices(pc1, pc1, Mq, Mt)
+    np.testing.assert_allclose(losses, ref, rtol=1e-12)
+    assert best == idx
+
+
+def test_choose_image_vote():
+    rng = np.random.default_rng(3)
+    surface = synth.make_cloud(800, seed=1).astype(np.float64)
+    verts = synth.make_cloud(200, seed=3).astype(np.float64)
+    n = 4
+    R = [synth.random_rotation(rng) for _ in range(n)]
+    t = [rng.normal(scale=5, size=3) for _ in range(n)]
+    gt = oracle.rel_pose_table(R, t)
+    tp = [t[0], t[1], t[2] + np.array([0, 0, 80.0]), t[3]]  # image 2's prediction is wrong
+    pred = oracle.rel_pose_table(R, tp)
+    err, image_id, top = oracle.choose_image(pred, gt, verts, surface, diameter=120.0)
+    assert err.shape == (n, n) and err[0, 1] == 1 and err[0, 2] == 0
+    assert image_id in (0, 1, 3) and top[0] == image_id and top[-1] == 2
