@@ -26,6 +26,7 @@
 //    balance): partial results meet in a packed (d2 bits << 32 | idx) atomicMin, which
 //    is order-independent and keeps the lowest-index tie rule.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "isr_common.cuh"
 
@@ -55,7 +56,7 @@ __device__ __forceinline__ float dist2_scalar(float qx, float qy, float qz, floa
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
-template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, bool WITH_IDX, int MINB>
+template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, bool WITH_IDX, int MINB, int UNR>
 __global__ void __launch_bounds__(THREADS, MINB) nn_kernel(const NNParams p) {
     static_assert(STAGE % SUB == 0 && SUB % 8 == 0, "tile shapes");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(THREADS, MINB) nn_kernel(const NNParams p) {
             float mo[Q];
 #pragma unroll
             for (int r = 0; r < Q; ++r) mo[r] = m[r];
-#pragma unroll 2
+#pragma unroll UNR
             for (int g = 0; g < SUB / 4; ++g) {
                 const float4 X = sx[sub * (SUB / 4) + g];
                 const float4 Y = sy[sub * (SUB / 4) + g];
@@ -226,14 +227,14 @@ mean_sqrt_kernel(const float *__restrict__ d2, long long n, double *__restrict__
 }
 
 // ---- host-side launch ----------------------------------------------------------------
-template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB>
+template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR = 2>
 struct NNVariant {
     static constexpr int kQueriesPerCta = Q * THREADS;
     static constexpr size_t kSmem = (size_t)NSTAGES * 3 * STAGE * 4 + NSTAGES * 8;
 
     template <bool WITH_IDX>
     static int launch(const NNParams &p, dim3 grid, cudaStream_t st) {
-        auto kern = nn_kernel<Q, THREADS, STAGE, NSTAGES, SUB, WITH_IDX, MINB>;
+        auto kern = nn_kernel<Q, THREADS, STAGE, NSTAGES, SUB, WITH_IDX, MINB, UNR>;
         static thread_local int configured_dev = -1;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -250,7 +251,7 @@ struct NNVariant {
 
     static int ctas_per_sm() {
         int n = 0;
-        auto kern = nn_kernel<Q, THREADS, STAGE, NSTAGES, SUB, true, MINB>;
+        auto kern = nn_kernel<Q, THREADS, STAGE, NSTAGES, SUB, true, MINB, UNR>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS, kSmem) != cudaSuccess ||
             n < 1)
@@ -263,6 +264,77 @@ struct NNVariant {
 // (= ISR_SOA_TILE), 1024-target stages, 3 in flight (36 KB), 256-target sub-tiles.
 using NNMain = NNVariant<8, 128, 1024, 3, 256, 4>;
 static_assert(ISR_SOA_TILE % 1024 == 0, "stage must divide the SoA padding");
+
+struct NNCall {
+    const float *q_soa; int64_t nq, nq_pad, q_bstride;
+    const float *t_soa; int64_t nt, nt_pad, t_bstride;
+    int64_t batch;
+    float *out_d2; int32_t *out_idx;
+    const int32_t *skip; int64_t skip_stride;
+    void *workspace; size_t workspace_bytes;
+    cudaStream_t st;
+};
+
+template <class V, int STAGE>
+static int nn_dispatch(const NNCall &c) {
+    const int nqb = (int)((c.nq + V::kQueriesPerCta - 1) / V::kQueriesPerCta);
+    const int stages = (int)(c.nt_pad / STAGE);
+    // target split: fill the machine when there are few query blocks, and cut the tail
+    // when the grid is only a few waves deep.
+    static thread_local int slots = 0;
+    if (slots == 0) slots = sm_count() * V::ctas_per_sm();
+    int splits = 1;
+    const long long ctas = (long long)nqb * c.batch;
+    if (ctas < 6ll * slots) {
+        long long want = (8ll * slots + ctas - 1) / ctas;
+        int max_splits = stages / 4 > 0 ? stages / 4 : 1;  // >= 4 stages per split
+        splits = (int)(want < max_splits ? want : max_splits);
+        if (splits < 1) splits = 1;
+    }
+    int per = (stages + splits - 1) / splits;
+    splits = (stages + per - 1) / per;  // no empty split
+    ISR_REQUIRE(splits <= 65535, ISR_E_SHAPE, "nn: too many target splits");
+
+    NNParams p;
+    p.q = c.q_soa; p.q_bstride = c.q_bstride; p.nq = (int)c.nq; p.nq_pad = (int)c.nq_pad;
+    p.t = c.t_soa; p.t_bstride = c.t_bstride; p.nt_pad = (int)c.nt_pad;
+    p.out_d2 = c.out_d2; p.out_idx = c.out_idx; p.out_packed = nullptr;
+    p.skip = c.skip; p.skip_stride = c.skip_stride;
+    p.stages_total = stages; p.stages_per_split = per;
+    dim3 grid((unsigned)nqb, (unsigned)splits, (unsigned)c.batch);
+
+    if (splits == 1) {
+        if (c.out_idx != nullptr) return V::template launch<true>(p, grid, c.st);
+        return V::template launch<false>(p, grid, c.st);
+    }
+    const size_t need = (size_t)c.nq * (size_t)c.batch * sizeof(u64);
+    ISR_REQUIRE(c.workspace != nullptr && c.workspace_bytes >= need, ISR_E_WORKSPACE,
+                "nn: workspace %zu < %zu bytes", c.workspace_bytes, need);
+    p.out_packed = reinterpret_cast<u64 *>(c.workspace);
+    // skipped batches keep their previous outputs: the unpack kernel honours `skip` too
+    ISR_TRY(check_cuda(cudaMemsetAsync(c.workspace, 0xff, need, c.st), "nn memset"));
+    ISR_TRY(V::template launch<true>(p, grid, c.st));
+    const long long total = (long long)c.nq * c.batch;
+    nn_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.st>>>(
+        p.out_packed, total, c.out_d2, c.out_idx, c.skip, c.skip_stride, (long long)c.nq);
+    return launched("nn_unpack_kernel");
+}
+
+#ifdef ISR_NN_TUNING
+// Developer-only shapes selected with ISR_NN_VARIANT (built with -DISR_NN_TUNING).
+using NNT1 = NNVariant<8, 256, 1024, 3, 256, 2>;
+using NNT2 = NNVariant<4, 128, 1024, 3, 256, 7>;
+using NNT3 = NNVariant<4, 256, 1024, 3, 256, 3>;
+using NNT4 = NNVariant<6, 128, 1024, 3, 256, 5>;
+using NNT5 = NNVariant<8, 128, 1024, 3, 256, 4, 1>;
+using NNT6 = NNVariant<8, 128, 1024, 3, 256, 4, 4>;
+using NNT7 = NNVariant<8, 128, 2048, 3, 256, 3>;
+using NNT8 = NNVariant<8, 128, 512, 4, 256, 4>;
+using NNT9 = NNVariant<8, 64, 1024, 3, 256, 8>;
+using NNT10 = NNVariant<4, 128, 1024, 3, 256, 8, 4>;
+using NNT11 = NNVariant<6, 128, 1024, 3, 256, 5, 1>;
+using NNT12 = NNVariant<8, 128, 1024, 3, 256, 5, 1>;
+#endif
 
 }  // namespace isr
 
@@ -279,7 +351,6 @@ int isr_nn_soa(const float *q_soa, int64_t nq, int64_t nq_pad, int64_t q_bstride
                float *out_d2, int32_t *out_idx, const int32_t *skip, int64_t skip_stride,
                void *workspace, size_t workspace_bytes, void *stream) {
     using namespace isr;
-    using V = NNMain;
     ISR_REQUIRE(nq >= 0 && nt >= 1 && batch >= 0, ISR_E_SHAPE,
                 "nn: need nq >= 0, nt >= 1, batch >= 0 (nq=%lld nt=%lld batch=%lld)",
                 (long long)nq, (long long)nt, (long long)batch);
@@ -293,49 +364,31 @@ int isr_nn_soa(const float *q_soa, int64_t nq, int64_t nq_pad, int64_t q_bstride
     ISR_REQUIRE(batch <= 65535, ISR_E_SHAPE, "nn: batch %lld > 65535", (long long)batch);
     ISR_REQUIRE(aligned16(t_soa) && (t_bstride % 4 == 0), ISR_E_ALIGN,
                 "nn: target planes must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-
-    const int nqb = (int)((nq + V::kQueriesPerCta - 1) / V::kQueriesPerCta);
-    const int stages = (int)(nt_pad / 1024);
-    // target split: fill the machine when there are few query blocks, and cut the tail
-    // when the grid is only a few waves deep.
-    static thread_local int slots = 0;
-    if (slots == 0) slots = sm_count() * V::ctas_per_sm();
-    int splits = 1;
-    const long long ctas = (long long)nqb * batch;
-    if (ctas < 6ll * slots) {
-        long long want = (8ll * slots + ctas - 1) / ctas;
-        int max_splits = stages / 4 > 0 ? stages / 4 : 1;  // >= 4 stages per split
-        splits = (int)(want < max_splits ? want : max_splits);
-        if (splits < 1) splits = 1;
+    const NNCall c{q_soa, nq, nq_pad, q_bstride, t_soa, nt, nt_pad, t_bstride, batch, out_d2, out_idx,
+                   skip, skip_stride, workspace, workspace_bytes, (cudaStream_t)stream};
+#ifdef ISR_NN_TUNING
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("ISR_NN_VARIANT");
+        variant = e ? atoi(e) : 0;
     }
-    int per = (stages + splits - 1) / splits;
-    splits = (stages + per - 1) / per;  // no empty split
-    ISR_REQUIRE(splits <= 65535, ISR_E_SHAPE, "nn: too many target splits");
-
-    NNParams p;
-    p.q = q_soa; p.q_bstride = q_bstride; p.nq = (int)nq; p.nq_pad = (int)nq_pad;
-    p.t = t_soa; p.t_bstride = t_bstride; p.nt_pad = (int)nt_pad;
-    p.out_d2 = out_d2; p.out_idx = out_idx; p.out_packed = nullptr;
-    p.skip = skip; p.skip_stride = skip_stride;
-    p.stages_total = stages; p.stages_per_split = per;
-    dim3 grid((unsigned)nqb, (unsigned)splits, (unsigned)batch);
-
-    if (splits == 1) {
-        if (out_idx != nullptr) return V::launch<true>(p, grid, st);
-        return V::launch<false>(p, grid, st);
+    switch (variant) {
+        case 1: return nn_dispatch<NNT1, 1024>(c);
+        case 2: return nn_dispatch<NNT2, 1024>(c);
+        case 3: return nn_dispatch<NNT3, 1024>(c);
+        case 4: return nn_dispatch<NNT4, 1024>(c);
+        case 5: return nn_dispatch<NNT5, 1024>(c);
+        case 6: return nn_dispatch<NNT6, 1024>(c);
+        case 7: return nn_dispatch<NNT7, 2048>(c);
+        case 8: return nn_dispatch<NNT8, 512>(c);
+        case 9: return nn_dispatch<NNT9, 1024>(c);
+        case 10: return nn_dispatch<NNT10, 1024>(c);
+        case 11: return nn_dispatch<NNT11, 1024>(c);
+        case 12: return nn_dispatch<NNT12, 1024>(c);
+        default: break;
     }
-    const size_t need = (size_t)nq * (size_t)batch * sizeof(u64);
-    ISR_REQUIRE(workspace != nullptr && workspace_bytes >= need, ISR_E_WORKSPACE,
-                "nn: workspace %zu < %zu bytes", workspace_bytes, need);
-    p.out_packed = reinterpret_cast<u64 *>(workspace);
-    // skipped batches keep their previous outputs: the unpack kernel honours `skip` too
-    ISR_TRY(check_cuda(cudaMemsetAsync(workspace, 0xff, need, st), "nn memset"));
-    ISR_TRY(V::launch<true>(p, grid, st));
-    const long long total = (long long)nq * batch;
-    nn_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        p.out_packed, total, out_d2, out_idx, skip, skip_stride, (long long)nq);
-    return launched("nn_unpack_kernel");
+#endif
+    return nn_dispatch<NNMain, 1024>(c);
 }
 
 int isr_mean_sqrt(const float *d2, int64_t n, int64_t batch, double *out_mean, void *stream) {

@@ -1,0 +1,18 @@
+"""Short driver for ncu captures of K2: B candidates x N x N, one direction, no indices."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth, api
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+idx = len(sys.argv) > 3 and sys.argv[3] == "idx"
+torch.cuda.set_device(0)
+cloud = synth.make_cloud(N, 1)
+rng = np.random.default_rng(0)
+P = np.tile(np.eye(4), (B, 1, 1))
+for k in range(B): P[k, :3, :3] = synth.random_rotation(rng)
+q = api.pack_soa(cloud, P); t = api.pack_soa(cloud)
+for _ in range(3):
+    r = api.nearest_neighbors_soa(q, t, return_index=idx)
+torch.cuda.synchronize()
+print("ok", float(r.d2.sum()))
