@@ -64,15 +64,20 @@ SIGNATURES = {
     "isr_nn_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "isr_nn_soa": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P,
                         _SZ, _P]),
+    "isr_centroid": (_I, [_P, _I64, _P, _P]),
+    "isr_prepare_cloud": (_I, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
+    "isr_nn2_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "isr_nn2": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64, _I, _P, _P, _P, _I64, _P,
+                     _SZ, _P]),
     "isr_mean_sqrt": (_I, [_P, _I64, _I64, _P, _P]),
     "isr_verify_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I]),
     "isr_verify_poses": (_I, [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I, _P, _P, _P, _SZ, _P]),
     "isr_icp_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
-    "isr_icp_accumulate": (_I, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _D, _P, _P, _P, _P, _SZ,
-                                _P]),
+    "isr_icp_accumulate": (_I, [_P, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I64, _D, _P, _P, _P, _P,
+                                _SZ, _P]),
     "isr_icp_solve": (_I, [_P, _I64, _P, _I64, _D, _D, _I, _P]),
-    "isr_icp_run": (_I, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _D, _I, _D, _D, _P, _P, _P, _P,
-                         _SZ, _P]),
+    "isr_icp_run": (_I, [_P, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I64, _D, _I, _D, _D, _P, _P, _P,
+                         _P, _SZ, _P]),
     "isr_bench_ffma": (_I, [_I, _I, _I, _P, _P, _P]),
 }
 

@@ -66,6 +66,20 @@ def _points(x, device) -> torch.Tensor:
     return t
 
 
+def _points_hilo(x, device):
+    """float64 input -> (float32 hi, float32 lo) with hi + lo == x to ~2^-48; float32 input ->
+    (x, None).  The library's point type is float32; the lo part lets float64 callers
+    (icp.py:68 builds a float64 source) lose nothing."""
+    is64 = (isinstance(x, torch.Tensor) and x.dtype == torch.float64) or (
+        not isinstance(x, torch.Tensor) and np.asarray(x).dtype == np.float64)
+    if not is64:
+        return _points(x, device), None
+    t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+    hi = t.to(torch.float32)
+    lo = (t - hi.to(torch.float64)).to(torch.float32)
+    return _points(hi, device), _points(lo, device)
+
+
 def _poses(x, device) -> torch.Tensor:
     t = _to_dev(x, torch.float64, device)
     if t.dim() == 2:
@@ -113,9 +127,18 @@ def transform_points(points, poses, device=None) -> torch.Tensor:
 
 @dataclasses.dataclass
 class SoaCloud:
-    """A cloud (or batch of clouds) in the padded plane layout K2 streams: [B, 3, npad]."""
+    """A cloud (or batch of clouds) in the padded plane layout K2 streams.
+
+    3 planes (x, y, z): the direct-difference kernel.  7 planes (hi xyz, |hi|^2, lo xyz,
+    centred): the production filtered-exact kernel; `centroid` is the centre it was
+    prepared with (both clouds of a search must share it)."""
     data: torch.Tensor
     n: int
+    centroid: Optional[torch.Tensor] = None
+
+    @property
+    def planes(self) -> int:
+        return self.data.shape[1]
 
     @property
     def npad(self) -> int:
@@ -150,6 +173,43 @@ def pack_soa(points, poses=None, device=None) -> SoaCloud:
     return SoaCloud(out, n)
 
 
+def centroid_of(points, device=None) -> torch.Tensor:
+    """FP64 centroid [3] of an [N,3] cloud, on the device (deterministic order)."""
+    device = _device(device)
+    pts = _points(points, device)
+    out = torch.zeros((3,), dtype=torch.float64, device=device)
+    if pts.shape[0] > 0:
+        _lib.check(_lib.load().isr_centroid(_ptr(pts), pts.shape[0], _ptr(out), _stream()))
+    return out
+
+
+def prepare_cloud(points, poses=None, centroid=None, centre_poses=None, device=None) -> SoaCloud:
+    """[N,3] (optionally transformed by poses [B,4,4]) -> centred hi/lo SoA7 planes [B,7,npad].
+    The centre of batch item b is centre_poses[b] . centroid (centre_poses None: centroid).
+    float64 input keeps its precision (hi/lo split)."""
+    device = _device(device)
+    pts, pts_lo = _points_hilo(points, device)
+    if pts.dim() != 2:
+        raise ValueError("prepare_cloud expects points of shape [N, 3]")
+    n = pts.shape[0]
+    npad = _lib.soa_padded_len(n)
+    lib = _lib.load()
+    P = None if poses is None else _poses(poses, device)
+    C = None if centre_poses is None else _poses(centre_poses, device)
+    b = 1 if P is None else P.shape[0]
+    if C is not None and C.shape[0] != b:
+        raise ValueError("centre_poses must match poses in batch size")
+    cen = None if centroid is None else _to_dev(centroid, torch.float64, device)
+    out = torch.empty((b, 7, npad), dtype=torch.float32, device=device)
+    for b0 in range(0, b, 65535):
+        bc = min(65535, b - b0)
+        _lib.check(lib.isr_prepare_cloud(
+            _ptr(pts), _ptr(pts_lo), n, None if P is None else _ptr(P[b0:]), 16,
+            None if C is None else _ptr(C[b0:]), 16, _ptr(cen), bc, _ptr(out[b0:]), npad, None, 0,
+            _stream()))
+    return SoaCloud(out, n, cen)
+
+
 def _pack_batched(points, device) -> SoaCloud:
     """[N,3] or [B,N,3] -> SoaCloud with batch 1 or B (no transform)."""
     pts = _points(points, device)
@@ -181,9 +241,14 @@ class NNResult:
         return torch.sqrt(self.d2.to(torch.float64))
 
 
-def nearest_neighbors_soa(q: SoaCloud, t: SoaCloud, return_index: bool = True) -> NNResult:
+def nearest_neighbors_soa(q: SoaCloud, t: SoaCloud, return_index: bool = True,
+                          use_lo: bool = True) -> NNResult:
+    """K2 on prepared clouds.  7-plane clouds run the production filtered-exact kernel
+    (isr_nn2), 3-plane clouds the direct-difference kernel (isr_nn_soa)."""
     if t.n < 1:
         raise ValueError("nearest_neighbors: empty target cloud")
+    if q.planes != t.planes:
+        raise ValueError("query and target were prepared for different kernels")
     qb, tb = q.batch, t.batch
     batch = max(qb, tb)
     if qb not in (1, batch) or tb not in (1, batch):
@@ -194,26 +259,61 @@ def nearest_neighbors_soa(q: SoaCloud, t: SoaCloud, return_index: bool = True) -
     if q.n == 0:
         return NNResult(d2, idx)
     lib = _lib.load()
+    pl = q.planes
     for b0 in range(0, batch, 65535):
         bc = min(65535, batch - b0)
-        ws = _workspace(lib.isr_nn_workspace_bytes(q.n, t.n, bc), device)
         qd = q.data[b0:] if qb > 1 else q.data
         td = t.data[b0:] if tb > 1 else t.data
-        _lib.check(lib.isr_nn_soa(
-            _ptr(qd), q.n, q.npad, 3 * q.npad if qb > 1 else 0,
-            _ptr(td), t.n, t.npad, 3 * t.npad if tb > 1 else 0,
-            bc, _ptr(d2[b0:]), _ptr(idx[b0:]) if idx is not None else None, None, 0,
-            _ptr(ws), ws.numel(), _stream()))
+        if pl == 7:
+            ws = _workspace(lib.isr_nn2_workspace_bytes(q.n, t.n, bc), device)
+            _lib.check(lib.isr_nn2(
+                _ptr(qd), q.n, q.npad, pl * q.npad if qb > 1 else 0,
+                _ptr(td), t.n, t.npad, pl * t.npad if tb > 1 else 0,
+                bc, 1 if use_lo else 0, _ptr(d2[b0:]), _ptr(idx[b0:]) if idx is not None else None,
+                None, 0, _ptr(ws), ws.numel(), _stream()))
+        else:
+            ws = _workspace(lib.isr_nn_workspace_bytes(q.n, t.n, bc), device)
+            _lib.check(lib.isr_nn_soa(
+                _ptr(qd), q.n, q.npad, pl * q.npad if qb > 1 else 0,
+                _ptr(td), t.n, t.npad, pl * t.npad if tb > 1 else 0,
+                bc, _ptr(d2[b0:]), _ptr(idx[b0:]) if idx is not None else None, None, 0,
+                _ptr(ws), ws.numel(), _stream()))
     return NNResult(d2, idx)
 
 
-def nearest_neighbors(query, target, return_index: bool = True, device=None) -> NNResult:
-    """Brute-force exact 1-NN of query [Nq,3] / [B,Nq,3] in target [Nt,3] / [B,Nt,3]."""
+def nearest_neighbors(query, target, return_index: bool = True, mode: str = "exact",
+                      device=None) -> NNResult:
+    """Brute-force 1-NN of query [Nq,3] / [B,Nq,3] in target [Nt,3] / [B,Nt,3].
+
+    mode='exact' (default): FP32 filter + FP64 resolve; the index is the float64 argmin,
+    d2 the float64 squared distance rounded to float32.  mode='direct': FP32
+    direct-difference kernel; d2/idx follow fma(dz,dz,fma(dy,dy,dx*dx)) bit for bit."""
+    if mode not in ("exact", "direct"):
+        raise ValueError("mode must be 'exact' or 'direct'")
     device = _device(device)
-    q = _pack_batched(query, device)
-    t = _pack_batched(target, device)
-    res = nearest_neighbors_soa(q, t, return_index)
-    if _points(query, device).dim() == 2 and _points(target, device).dim() == 2:
+    qp, tp = _points(query, device), _points(target, device)
+    single = qp.dim() == 2 and tp.dim() == 2
+    if mode == "direct":
+        res = nearest_neighbors_soa(_pack_batched(qp, device), _pack_batched(tp, device), return_index)
+    elif tp.dim() == 2:
+        if tp.shape[0] < 1:
+            raise ValueError("nearest_neighbors: empty target cloud")
+        cen = centroid_of(tp, device)
+        t7 = prepare_cloud(tp, centroid=cen, device=device)
+        if qp.dim() == 2:
+            q7 = prepare_cloud(qp, centroid=cen, device=device)
+        else:
+            q7 = SoaCloud(torch.cat([prepare_cloud(qp[k], centroid=cen, device=device).data
+                                     for k in range(qp.shape[0])]), qp.shape[1], cen)
+        res = nearest_neighbors_soa(q7, t7, return_index)
+    else:
+        outs = []
+        for k in range(tp.shape[0]):
+            qk = qp if qp.dim() == 2 else qp[k]
+            outs.append(nearest_neighbors(qk, tp[k], return_index, mode, device))
+        return NNResult(torch.stack([o.d2 for o in outs]),
+                        torch.stack([o.idx for o in outs]) if return_index else None)
+    if single:
         res = NNResult(res.d2[0], None if res.idx is None else res.idx[0])
     return res
 
@@ -242,12 +342,20 @@ def chamfer_distance(a, b, device=None) -> torch.Tensor:
     """(mean d(a->b) + mean d(b->a)) / 2, unsquared, float64 scalar tensor
     (verfication.py:97-101).  Accepts [N,3] or batched [B,N,3]."""
     device = _device(device)
-    A = _pack_batched(a, device)
-    B = _pack_batched(b, device)
+    pa, pb = _points(a, device), _points(b, device)
+    single = pa.dim() == 2 and pb.dim() == 2
+    if not single:
+        if pa.dim() != 3 or pb.dim() != 3 or pa.shape[0] != pb.shape[0]:
+            raise ValueError("batched chamfer_distance expects [B,N,3] and [B,M,3]")
+        return torch.stack([chamfer_distance(pa[k], pb[k], device) for k in range(pa.shape[0])])
+    if pa.shape[0] == 0 or pb.shape[0] == 0:
+        raise ValueError("chamfer_distance: empty cloud")
+    cen = centroid_of(pb, device)
+    A = prepare_cloud(pa, centroid=cen, device=device)
+    B = prepare_cloud(pb, centroid=cen, device=device)
     ab = _mean_sqrt(nearest_neighbors_soa(A, B, return_index=False).d2)
     ba = _mean_sqrt(nearest_neighbors_soa(B, A, return_index=False).d2)
-    out = (ab + ba) / 2
-    return out[0] if _points(a, device).dim() == 2 and _points(b, device).dim() == 2 else out
+    return ((ab + ba) / 2)[0]
 
 
 @dataclasses.dataclass
@@ -361,7 +469,7 @@ class IcpProblem:
 
     def __init__(self, source, target, inits, device=None):
         self.device = _device(device)
-        self.src = _points(source, self.device)
+        self.src, self.src_lo = _points_hilo(source, self.device)
         self.tgt = _points(target, self.device)
         if self.src.dim() != 2 or self.tgt.dim() != 2:
             raise ValueError("icp: source and target must be [N,3]")
@@ -373,7 +481,8 @@ class IcpProblem:
         st = np.zeros(self.starts, dtype=_lib.ICP_STATE_DTYPE)
         st["T"] = inits.reshape(self.starts, 16)
         self.states = torch.from_numpy(st.view(np.uint8).reshape(self.starts, -1).copy()).to(self.device)
-        self.tgt_soa = pack_soa(self.tgt, device=self.device)
+        self.centroid = centroid_of(self.tgt, self.device)
+        self.tgt_soa = prepare_cloud(self.tgt, centroid=self.centroid, device=self.device)
         lib = _lib.load()
         ns1 = max(self.ns, 1)
         self.ws = _workspace(lib.isr_icp_workspace_bytes(ns1, self.nt, self.starts), self.device)
@@ -387,9 +496,10 @@ class IcpProblem:
             self.sums.zero_()
             return self.sums
         _lib.check(_lib.load().isr_icp_accumulate(
-            _ptr(self.states), self.starts, _ptr(self.src), self.ns, _ptr(self.tgt),
-            _ptr(self.tgt_soa.data), self.nt, self.tgt_soa.npad, float(max_dist), _ptr(self.sums),
-            _ptr(self.corr_idx), _ptr(self.inlier), _ptr(self.ws), self.ws.numel(), _stream()))
+            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), self.ns, _ptr(self.tgt),
+            _ptr(self.tgt_soa.data), _ptr(self.centroid), self.nt, self.tgt_soa.npad, float(max_dist),
+            _ptr(self.sums), _ptr(self.corr_idx), _ptr(self.inlier), _ptr(self.ws), self.ws.numel(),
+            _stream()))
         return self.sums
 
     def solve(self, ns_total: int, rel_fitness: float, rel_rmse: float, final_eval: bool,
@@ -406,8 +516,9 @@ class IcpProblem:
                 self.solve(0, rel_fitness, rel_rmse, k == max_iteration)
             return
         _lib.check(_lib.load().isr_icp_run(
-            _ptr(self.states), self.starts, _ptr(self.src), self.ns, _ptr(self.tgt),
-            _ptr(self.tgt_soa.data), self.nt, self.tgt_soa.npad, float(max_dist), int(max_iteration),
+            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), self.ns, _ptr(self.tgt),
+            _ptr(self.tgt_soa.data), _ptr(self.centroid), self.nt, self.tgt_soa.npad, float(max_dist),
+            int(max_iteration),
             float(rel_fitness), float(rel_rmse), _ptr(self.sums), _ptr(self.corr_idx),
             _ptr(self.inlier), _ptr(self.ws), self.ws.numel(), _stream()))
 

@@ -34,7 +34,7 @@ static_assert(sizeof(IsrIcpState) % 8 == 0, "IsrIcpState must be a whole number 
 // grid: (nblk, starts)
 __global__ void __launch_bounds__(kAccThreads)
 icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__restrict__ src,
-                      int64_t ns, const float *__restrict__ tgt, const int32_t *__restrict__ idx,
+                      const float *__restrict__ src_lo, int64_t ns, const float *__restrict__ tgt, const int32_t *__restrict__ idx,
                       double max_d2, double *__restrict__ partials, unsigned *__restrict__ tickets,
                       double *__restrict__ sums, uint8_t *__restrict__ inlier) {
     const int s = blockIdx.y;
@@ -54,7 +54,10 @@ icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__res
     uint8_t *inl = inlier != nullptr ? inlier + (int64_t)s * ns : nullptr;
     for (int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i < ns;
          i += (int64_t)gridDim.x * kAccThreads) {
-        const double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
+        double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
+        if (src_lo != nullptr) {
+            px += (double)src_lo[3 * i]; py += (double)src_lo[3 * i + 1]; pz += (double)src_lo[3 * i + 2];
+        }
         const double sx = ((T[0] * px + T[1] * py) + T[2] * pz) + T[3];
         const double sy = ((T[4] * px + T[5] * py) + T[6] * pz) + T[7];
         const double sz = ((T[8] * px + T[9] * py) + T[10] * pz) + T[11];
@@ -272,12 +275,13 @@ static IcpLayout icp_layout(int64_t ns, int64_t nt, int64_t starts) {
     // nblk must not depend on the device so that workspace sizing works without a GPU
     // context: size for the largest grid acc_blocks() can pick (cap >= want).
     size_t off = 0;
-    L.xs = off;       off += align256((size_t)starts * 3 * nsp * 4);
+    L.xs = off;       off += align256((size_t)starts * 7 * nsp * 4);
     L.d2 = off;       off += align256((size_t)starts * ns * 4);
     const int64_t max_blk = (ns + kAccThreads * 8 - 1) / (kAccThreads * 8) + 1;
     L.partials = off; off += align256((size_t)starts * max_blk * kNS * 8);
     L.tickets = off;  off += align256((size_t)starts * 4);
-    L.nnws = off;     off += isr_nn_workspace_bytes(ns, nt, starts);
+    const size_t w1 = isr_nn_workspace_bytes(ns, nt, starts), w2 = isr_nn2_workspace_bytes(ns, nt, starts);
+    L.nnws = off;     off += w1 > w2 ? w1 : w2;
     L.total = off;
     L.nblk = 0;
     return L;
@@ -292,15 +296,15 @@ size_t isr_icp_workspace_bytes(int64_t ns, int64_t nt, int64_t starts) {
     return isr::icp_layout(ns, nt, starts).total;
 }
 
-int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, int64_t ns,
-                       const float *tgt, const float *tgt_soa, int64_t nt, int64_t nt_pad,
-                       double max_dist, double *sums, int32_t *corr_idx, uint8_t *inlier,
-                       void *workspace, size_t workspace_bytes, void *stream) {
+int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                       int64_t ns, const float *tgt, const float *tgt_soa7, const double *centroid, int64_t nt,
+                       int64_t nt_pad, double max_dist, double *sums, int32_t *corr_idx,
+                       uint8_t *inlier, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace isr;
     ISR_REQUIRE(starts >= 1 && ns >= 1 && nt >= 1, ISR_E_SHAPE,
                 "icp: need starts, ns, nt >= 1 (starts=%lld ns=%lld nt=%lld)", (long long)starts,
                 (long long)ns, (long long)nt);
-    ISR_REQUIRE(states && src && tgt && tgt_soa && sums && corr_idx, ISR_E_INVALID_ARG,
+    ISR_REQUIRE(states && src && tgt && tgt_soa7 && centroid && sums && corr_idx, ISR_E_INVALID_ARG,
                 "icp: null pointer");
     ISR_REQUIRE(starts <= 65535, ISR_E_SHAPE, "icp: starts %lld > 65535", (long long)starts);
     IcpLayout L = icp_layout(ns, nt, starts);
@@ -321,15 +325,16 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, in
         // upstream: a non-positive distance yields an empty result
         return check_cuda(cudaMemsetAsync(sums, 0, (size_t)starts * kNS * 8, st), "icp memset");
     }
-    ISR_TRY(isr_transform_points_soa(src, ns, &states[0].T[0], kStateDoubles, starts, xs, nsp, done,
-                                     kStateInts, stream));
-    ISR_TRY(isr_nn_soa(xs, ns, nsp, 3 * nsp, tgt_soa, nt, nt_pad, 0, starts, d2, corr_idx, done,
-                       kStateInts, ws + L.nnws, L.total - L.nnws, stream));
+    // source: FP64 pose from the device state, centred on the target's centroid, hi/lo planes
+    ISR_TRY(isr_prepare_cloud(src, src_lo, ns, &states[0].T[0], kStateDoubles, nullptr, 0, centroid, starts,
+                              xs, nsp, done, kStateInts, stream));
+    ISR_TRY(isr_nn2(xs, ns, nsp, 7 * nsp, tgt_soa7, nt, nt_pad, 0, starts, 1, d2, corr_idx, done,
+                    kStateInts, ws + L.nnws, L.total - L.nnws, stream));
     ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
     const int nblk = acc_blocks(ns, starts);
     dim3 grid((unsigned)nblk, (unsigned)starts);
     ProfScope prof(kProfIcpAcc, st);
-    icp_accumulate_kernel<<<grid, kAccThreads, 0, st>>>(states, src, ns, tgt, corr_idx,
+    icp_accumulate_kernel<<<grid, kAccThreads, 0, st>>>(states, src, src_lo, ns, tgt, corr_idx,
                                                         max_dist * max_dist, partials, tickets, sums,
                                                         inlier);
     return launched("icp_accumulate_kernel");
@@ -345,15 +350,18 @@ int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64
     return launched("icp_solve_kernel");
 }
 
-int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, int64_t ns, const float *tgt,
-                const float *tgt_soa, int64_t nt, int64_t nt_pad, double max_dist, int max_iteration,
-                double rel_fitness, double rel_rmse, double *sums, int32_t *corr_idx, uint8_t *inlier,
-                void *workspace, size_t workspace_bytes, void *stream) {
+int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo, int64_t ns,
+                const float *tgt,
+                const float *tgt_soa7, const double *centroid, int64_t nt, int64_t nt_pad,
+                double max_dist, int max_iteration, double rel_fitness, double rel_rmse, double *sums,
+                int32_t *corr_idx, uint8_t *inlier, void *workspace, size_t workspace_bytes,
+                void *stream) {
     using namespace isr;
     ISR_REQUIRE(max_iteration >= 0, ISR_E_INVALID_ARG, "icp_run: max_iteration < 0");
     for (int k = 0; k <= max_iteration; ++k) {
-        ISR_TRY(isr_icp_accumulate(states, starts, src, ns, tgt, tgt_soa, nt, nt_pad, max_dist, sums,
-                                   corr_idx, inlier, workspace, workspace_bytes, stream));
+        ISR_TRY(isr_icp_accumulate(states, starts, src, src_lo, ns, tgt, tgt_soa7, centroid, nt, nt_pad,
+                                   max_dist, sums, corr_idx, inlier, workspace, workspace_bytes,
+                                   stream));
         ISR_TRY(isr_icp_solve(states, starts, sums, ns, rel_fitness, rel_rmse,
                               k == max_iteration ? 1 : 0, stream));
     }

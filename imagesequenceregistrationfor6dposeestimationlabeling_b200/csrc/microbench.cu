@@ -35,7 +35,96 @@ __global__ void __launch_bounds__(256) ffma_chain_kernel(int iters, float *sink)
     }
 }
 
+// FFMA2 operand-pattern probes (developer tuning): 16 accumulator pairs per thread.
+//  mode 2: acc = fma2(S_k.F32 scalar, bb, acc)   -- scalar-broadcast A operand (the scan's form)
+//  mode 3: acc = fma2(S_k pair, bb, acc)         -- distinct A pairs
+//  mode 4: mode 2 plus one FMNMX3 per two FFMA2  -- the scan's instruction mix
+template <int MODE>
+__global__ void __launch_bounds__(256) ffma2_pattern_kernel(int iters, float *sink, const float *src) {
+    u64 a[16];
+    float sc[16];
+    u64 sp[16];
+    const u64 bb = pack2(src[0], src[1]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        a[k] = pack2(1.0f + threadIdx.x * 1e-6f + k, 2.0f + k);
+        sc[k] = src[2 + k];
+        sp[k] = pack2(src[2 + k], src[3 + k]);
+    }
+    float m0 = 1e30f, m1 = 1e30f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (MODE == 3) a[k] = fma2(sp[k], bb, a[k]);
+            else a[k] = fma2(pack2(sc[k], sc[k]), bb, a[k]);
+        }
+        if (MODE == 4) {
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+                float lo, hi;
+                unpack2(a[k], lo, hi);
+                m0 = min3(m0, lo, hi);
+                unpack2(a[k + 1], lo, hi);
+                m1 = min3(m1, lo, hi);
+            }
+        }
+        if (MODE == 5) {  // two 2-input FMNMX per pair
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+                float lo, hi;
+                unpack2(a[k], lo, hi);
+                m0 = fminf(m0, lo); m1 = fminf(m1, hi);
+                unpack2(a[k + 1], lo, hi);
+                m0 = fminf(m0, lo); m1 = fminf(m1, hi);
+            }
+        }
+        if (MODE == 6) {  // three-input signed integer min on the bit patterns
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                float lo, hi;
+                unpack2(a[k], lo, hi);
+                m0 = __int_as_float(min(min(__float_as_int(m0), __float_as_int(lo)), __float_as_int(hi)));
+            }
+        }
+        if (MODE == 7) {  // LOP3: OR-accumulate both halves (sign-bit flagging)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                float lo, hi;
+                unpack2(a[k], lo, hi);
+                m0 = __int_as_float(__float_as_int(m0) | __float_as_int(lo) | __float_as_int(hi));
+            }
+        }
+        if (MODE == 8) {  // one FMNMX3 per FOUR values... (half the mins) reference point
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+                float lo, hi;
+                unpack2(a[k], lo, hi);
+                m0 = min3(m0, lo, hi);
+            }
+        }
+    }
+    float s = m0 + m1;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { float lo, hi; unpack2(a[k], lo, hi); s += lo + hi; }
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace isr
+
+extern "C" int isr_bench_ffma2_pattern(int blocks, int iters, int mode, float *sink, const float *src,
+                                       double *flops_out_host, void *stream) {
+    using namespace isr;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 2) ffma2_pattern_kernel<2><<<blocks, 256, 0, st>>>(iters, sink, src);
+    else if (mode == 3) ffma2_pattern_kernel<3><<<blocks, 256, 0, st>>>(iters, sink, src);
+    else if (mode == 5) ffma2_pattern_kernel<5><<<blocks, 256, 0, st>>>(iters, sink, src);
+    else if (mode == 6) ffma2_pattern_kernel<6><<<blocks, 256, 0, st>>>(iters, sink, src);
+    else if (mode == 7) ffma2_pattern_kernel<7><<<blocks, 256, 0, st>>>(iters, sink, src);
+    else if (mode == 8) ffma2_pattern_kernel<8><<<blocks, 256, 0, st>>>(iters, sink, src);
+    else ffma2_pattern_kernel<4><<<blocks, 256, 0, st>>>(iters, sink, src);
+    if (flops_out_host) *flops_out_host = (double)blocks * 256.0 * (double)iters * 16.0 * 4.0;
+    return launched("ffma2_pattern_kernel");
+}
 
 extern "C" int isr_bench_ffma(int blocks, int iters, int packed, float *sink, double *flops_out_host,
                               void *stream) {

@@ -1,0 +1,453 @@
+// K2 (production) -- brute-force nearest neighbour: FP32 filter scan + exact FP64 resolve.
+//
+// Replaces the KD-tree 1-NN of Open3D (verfication.py:97,99; icp.py:97-103,113,115) and
+// sklearn (choosePose.py:21-22).  Every (query, target) pair is still visited -- this is
+// brute force -- but the per-pair work is the cheapest FP32 form that can be made exact:
+//
+//   scan    a_j = fma(-2qx, px, fma(-2qy, py, fma(-2qz, pz, |p_j|^2)))   ~ d_j^2 - |q|^2
+//           3 FFMA per pair (packed: 3 FFMA2 per target pair) + 1/2 FMNMX3, all on the
+//           FP32 CUDA cores.  a_j carries cancellation error, so it is only a FILTER:
+//           |a_j - A_j| <= 13 u R^2 (u = 2^-24, R = |q| + d), proven from the three fma
+//           roundings and the rounding of |p|^2 (clouds are centred by prepare.cu so R is
+//           the object radius, not the camera distance).
+//   flag    per 32-target sub-tile one compare per query: does the sub-tile minimum come
+//           within the window W of the running minimum?  (one FSETP per query per 32 targets)
+//   resolve only then: re-derive the sub-tile's a_j, and for the targets inside the window
+//           compute the distance EXACTLY in FP64 from the hi/lo coordinates; keep the
+//           smallest (strict <, ascending index => lowest index on exact ties).
+//
+// Exactness: let j* be the true nearest neighbour and m the running minimum of a when j* is
+// visited.  m = a_i for some visited i with D_i >= D_j*, hence
+//     a_j* <= D_j* - |q|^2 + E <= D_i - |q|^2 + E <= a_i + 2E = m + 2E <= m + W,
+// so j*'s sub-tile is flagged and j* is inside the window: it is always resolved exactly.
+// The returned index therefore equals the float64 brute-force argmin of the prepared
+// (hi+lo) coordinates; the returned d2 is that FP64 distance rounded once to float32.
+//
+// Roofline: FP32 CUDA cores.  Algorithmic work stays 8 flop per pair;
+// executed FP32-pipe work is 3 lane-ops per pair, so the algorithmic rate can exceed the
+// nominal FMA peak (cap 8/6) -- bench.py reports both.
+#include <math_constants.h>
+#include <stdlib.h>
+
+#include "isr_common.cuh"
+
+namespace isr {
+
+struct NN2Params {
+    const float *q;          // SoA7 [batch][7][nq_pad]
+    long long q_bstride;
+    int nq;
+    int nq_pad;
+    const float *t;          // SoA7 [batch][7][nt_pad]
+    long long t_bstride;
+    int nt_pad;
+    float *out_d2;
+    int *out_idx;
+    double *part_D;          // [splits][batch*nq] when the target range is split
+    int *part_idx;
+    long long part_stride;
+    const int *skip;
+    long long skip_stride;
+    int stages_total;
+    int stages_per_split;
+    int use_lo;
+    int debug_no_resolve;  // tuning only: never flag (pure filter-scan rate)
+};
+
+// Upper threshold for "could still be the nearest neighbour": running minimum + window.
+// mt = running min of a (~ d^2 - |q|^2), nq2 = |q|^2, qn = |q| (float32, hi part).
+// W >= 2 (13 u R^2 + 8 u R d) with R = |q| + d and d an upper bound on the best distance;
+// every constant carries slack for the float32 evaluation of this very formula.
+__device__ __forceinline__ float filter_threshold(float mt, float nq2, float qn) {
+    const float u = 5.9604645e-8f;  // 2^-24
+    const float s = sqrtf(fmaxf(mt + nq2, 0.f));
+    const float dub = (s + 1.5e-3f * qn) * 1.002f + 1e-20f;
+    const float R = (qn + dub) * 1.00001f;
+    const float W = (26.f * u * R * R + 16.f * u * R * dub) * 1.001f + 1e-30f;
+    return __fadd_ru(mt, W);
+}
+
+template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR>
+__global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
+    static_assert(STAGE % SUB == 0 && SUB % 8 == 0 && Q <= 16, "tile shapes");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *sbuf = reinterpret_cast<float *>(smem_raw);  // [NSTAGES][4][STAGE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSTAGES * 4 * STAGE * 4);
+
+    const int b = blockIdx.z;
+    if (p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) return;
+    const int tid = threadIdx.x;
+    const float *__restrict__ gq = p.q + (long long)b * p.q_bstride;
+    const float *__restrict__ gt = p.t + (long long)b * p.t_bstride;
+    const int s_begin = blockIdx.y * p.stages_per_split;
+    const int nst = min(p.stages_per_split, p.stages_total - s_begin);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NSTAGES; ++i) mbar_init(&full[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int sl) {
+        const int slot = sl % NSTAGES;
+        float *dst = sbuf + (size_t)slot * 4 * STAGE;
+        const float *src = gt + (long long)(s_begin + sl) * STAGE;
+        mbar_expect_tx(&full[slot], 4u * STAGE * 4u);
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl)
+            bulk_g2s(dst + pl * STAGE, src + (long long)pl * p.nt_pad, STAGE * 4u, &full[slot]);
+    };
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGES - 1 && i < nst; ++i) issue(i);
+    }
+
+    // Scan state, in registers: -2 * query (hi part) and the flag threshold.
+    float q2x[Q], q2y[Q], q2z[Q], thr[Q];
+    // Resolve state, touched only on the rare path and indexed at run time there, which
+    // places it in (L1-resident) local memory and keeps it out of the scan's registers.
+    float mt_l[Q], thr_l[Q], tm_l[Q];
+    double Dbest_l[Q];
+    int ibest_l[Q];
+    const int q0 = blockIdx.x * (THREADS * Q);
+#pragma unroll
+    for (int r = 0; r < Q; ++r) {
+        const int i = min(q0 + r * THREADS + tid, p.nq_pad - 1);
+        q2x[r] = -2.0f * gq[i];
+        q2y[r] = -2.0f * gq[p.nq_pad + i];
+        q2z[r] = -2.0f * gq[2ll * p.nq_pad + i];
+        thr[r] = p.debug_no_resolve ? -CUDART_INF_F : CUDART_INF_F;
+    }
+    for (int r = 0; r < Q; ++r) {  // run-time loop on purpose
+        mt_l[r] = CUDART_INF_F;
+        thr_l[r] = CUDART_INF_F;
+        Dbest_l[r] = CUDART_INF;
+        ibest_l[r] = s_begin * STAGE;
+    }
+
+    for (int sl = 0; sl < nst; ++sl) {
+        if (tid == 0 && sl + NSTAGES - 1 < nst) issue(sl + NSTAGES - 1);
+        const int slot = sl % NSTAGES;
+        mbar_wait(&full[slot], (sl / NSTAGES) & 1);
+        const float4 *sx = reinterpret_cast<const float4 *>(sbuf + (size_t)slot * 4 * STAGE);
+        const float4 *sy = sx + STAGE / 4;
+        const float4 *sz = sy + STAGE / 4;
+        const float4 *sn = sz + STAGE / 4;
+#pragma unroll 1
+        for (int sub = 0; sub < STAGE / SUB; ++sub) {
+            float tm[Q];
+#pragma unroll
+            for (int r = 0; r < Q; ++r) tm[r] = CUDART_INF_F;
+#pragma unroll UNR
+            for (int g = 0; g < SUB / 4; ++g) {
+                const float4 X = sx[sub * (SUB / 4) + g];
+                const float4 Y = sy[sub * (SUB / 4) + g];
+                const float4 Z = sz[sub * (SUB / 4) + g];
+                const float4 N = sn[sub * (SUB / 4) + g];
+                const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+                const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+                const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+                const u64 n01 = pack2(N.x, N.y), n23 = pack2(N.z, N.w);
+                // level-major over the Q queries: consecutive FFMA2 are independent and share
+                // the target-pair operand (operand-reuse cache); the query rides as a scalar
+                u64 acc[Q];
+#pragma unroll
+                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2z[r], q2z[r]), z01, n01);
+#pragma unroll
+                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2y[r], q2y[r]), y01, acc[r]);
+#pragma unroll
+                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2x[r], q2x[r]), x01, acc[r]);
+#pragma unroll
+                for (int r = 0; r < Q; ++r) {
+                    float a0, a1;
+                    unpack2(acc[r], a0, a1);
+                    tm[r] = min3(tm[r], a0, a1);
+                }
+#pragma unroll
+                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2z[r], q2z[r]), z23, n23);
+#pragma unroll
+                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2y[r], q2y[r]), y23, acc[r]);
+#pragma unroll
+                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2x[r], q2x[r]), x23, acc[r]);
+#pragma unroll
+                for (int r = 0; r < Q; ++r) {
+                    float a0, a1;
+                    unpack2(acc[r], a0, a1);
+                    tm[r] = min3(tm[r], a0, a1);
+                }
+            }
+            unsigned flags = 0;
+#pragma unroll
+            for (int r = 0; r < Q; ++r) flags |= (tm[r] <= thr[r]) ? (1u << r) : 0u;
+            if (flags != 0) {
+                // ---- resolve: rare, divergent; one pass serves every flagged lane ----------
+#pragma unroll
+                for (int r = 0; r < Q; ++r) tm_l[r] = tm[r];
+                const float *fx = reinterpret_cast<const float *>(sx) + sub * SUB;
+                const float *fy = reinterpret_cast<const float *>(sy) + sub * SUB;
+                const float *fz = reinterpret_cast<const float *>(sz) + sub * SUB;
+                const float *fn = reinterpret_cast<const float *>(sn) + sub * SUB;
+                const int gbase = (s_begin + sl) * STAGE + sub * SUB;
+                for (unsigned f = flags; f != 0; f &= f - 1) {
+                    const int r = __ffs(f) - 1;
+                    const int qi = min(q0 + r * THREADS + tid, p.nq_pad - 1);
+                    const float qhx = gq[qi], qhy = gq[p.nq_pad + qi], qhz = gq[2ll * p.nq_pad + qi];
+                    const float cx = -2.0f * qhx, cy = -2.0f * qhy, cz = -2.0f * qhz;
+                    const float nq2 = __fmaf_rn(qhz, qhz, __fmaf_rn(qhy, qhy, qhx * qhx));
+                    const float m = fminf(mt_l[r], tm_l[r]);
+                    const float th = filter_threshold(m, nq2, sqrtf(nq2));
+                    mt_l[r] = m;
+                    thr_l[r] = th;
+                    double qlx = 0.0, qly = 0.0, qlz = 0.0;
+                    if (p.use_lo) {
+                        qlx = gq[4ll * p.nq_pad + qi];
+                        qly = gq[5ll * p.nq_pad + qi];
+                        qlz = gq[6ll * p.nq_pad + qi];
+                    }
+                    double Db = Dbest_l[r];
+                    int ib = ibest_l[r];
+#pragma unroll 4
+                    for (int j = 0; j < SUB; ++j) {
+                        const float px = fx[j], py = fy[j], pz = fz[j];
+                        const float a = __fmaf_rn(cx, px, __fmaf_rn(cy, py, __fmaf_rn(cz, pz, fn[j])));
+                        if (a <= th) {
+                            double dx = (double)qhx - (double)px, dy = (double)qhy - (double)py,
+                                   dz = (double)qhz - (double)pz;
+                            if (p.use_lo) {
+                                const long long gj = gbase + j;
+                                dx += qlx - (double)gt[4ll * p.nt_pad + gj];
+                                dy += qly - (double)gt[5ll * p.nt_pad + gj];
+                                dz += qlz - (double)gt[6ll * p.nt_pad + gj];
+                            }
+                            const double D = fma(dz, dz, fma(dy, dy, dx * dx));
+                            if (D < Db) {
+                                Db = D;
+                                ib = gbase + j;
+                            }
+                        }
+                    }
+                    Dbest_l[r] = Db;
+                    ibest_l[r] = ib;
+                }
+#pragma unroll
+                for (int r = 0; r < Q; ++r) thr[r] = thr_l[r];
+            }
+        }
+        __syncthreads();  // every warp is done with this slot before it is refilled
+    }
+
+    for (int r = 0; r < Q; ++r) {
+        const int i = q0 + r * THREADS + tid;
+        if (i < p.nq) {
+            const long long o = (long long)b * p.nq + i;
+            if (p.part_D != nullptr) {
+                p.part_D[(long long)blockIdx.y * p.part_stride + o] = Dbest_l[r];
+                p.part_idx[(long long)blockIdx.y * p.part_stride + o] = ibest_l[r];
+            } else {
+                p.out_d2[o] = (float)Dbest_l[r];
+                if (p.out_idx != nullptr) p.out_idx[o] = ibest_l[r];
+            }
+        }
+    }
+}
+
+// splits ascend over the target range, so the first strict minimum is the lowest index
+__global__ void nn2_combine_kernel(const double *__restrict__ part_D, const int *__restrict__ part_idx,
+                                   long long total, int splits, float *__restrict__ out_d2,
+                                   int *__restrict__ out_idx, const int *__restrict__ skip,
+                                   long long skip_stride, long long per_batch) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    if (skip != nullptr && skip[(i / per_batch) * skip_stride] != 0) return;
+    double best = part_D[i];
+    int bi = part_idx[i];
+    for (int s = 1; s < splits; ++s) {
+        const double d = part_D[(long long)s * total + i];
+        if (d < best) {
+            best = d;
+            bi = part_idx[(long long)s * total + i];
+        }
+    }
+    out_d2[i] = (float)best;
+    if (out_idx != nullptr) out_idx[i] = bi;
+}
+
+// ---- host-side launch ----------------------------------------------------------------
+template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR = 2>
+struct NN2Variant {
+    static constexpr int kQueriesPerCta = Q * THREADS;
+    static constexpr int kStage = STAGE;
+    static constexpr size_t kSmem = (size_t)NSTAGES * 4 * STAGE * 4 + NSTAGES * 8;
+
+    static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
+        auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR>;
+        static thread_local int configured_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (configured_dev != dev) {
+            ISR_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)kSmem),
+                               "nn2 smem attr"));
+            configured_dev = dev;
+        }
+        ProfScope prof(kProfNN, st);
+        kern<<<grid, THREADS, kSmem, st>>>(p);
+        return launched("nn2_kernel");
+    }
+
+    static int ctas_per_sm() {
+        int n = 0;
+        auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS, kSmem) != cudaSuccess ||
+            n < 1)
+            n = 1;
+        return n;
+    }
+};
+
+using NN2Main = NN2Variant<8, 128, 1024, 3, 32, 4>;
+constexpr int kMaxSplits = 32;
+constexpr int kSlotsUpperBound = 148 * 8;  // for workspace sizing without a device
+
+static int choose_splits(long long ctas, int stages, int slots) {
+    int splits = 1;
+    if (ctas < 6ll * slots) {
+        long long want = (8ll * slots + ctas - 1) / ctas;
+        int max_splits = stages / 4 > 0 ? stages / 4 : 1;  // >= 4 stages per split
+        if (max_splits > kMaxSplits) max_splits = kMaxSplits;
+        splits = (int)(want < max_splits ? want : max_splits);
+        if (splits < 1) splits = 1;
+    }
+    return splits;
+}
+
+struct NN2Call {
+    const float *q; int64_t nq, nq_pad, q_bstride;
+    const float *t; int64_t nt, nt_pad, t_bstride;
+    int64_t batch;
+    int use_lo;
+    float *out_d2; int32_t *out_idx;
+    const int32_t *skip; int64_t skip_stride;
+    void *workspace; size_t workspace_bytes;
+    cudaStream_t st;
+};
+
+template <class V>
+static int nn2_dispatch(const NN2Call &c) {
+    const int nqb = (int)((c.nq + V::kQueriesPerCta - 1) / V::kQueriesPerCta);
+    const int stages = (int)(c.nt_pad / V::kStage);
+    static thread_local int slots = 0;
+    if (slots == 0) slots = sm_count() * V::ctas_per_sm();
+    int splits = choose_splits((long long)nqb * c.batch, stages, slots);
+    const int per = (stages + splits - 1) / splits;
+    splits = (stages + per - 1) / per;  // no empty split
+
+    NN2Params p;
+    p.q = c.q; p.q_bstride = c.q_bstride; p.nq = (int)c.nq; p.nq_pad = (int)c.nq_pad;
+    p.t = c.t; p.t_bstride = c.t_bstride; p.nt_pad = (int)c.nt_pad;
+    p.out_d2 = c.out_d2; p.out_idx = c.out_idx;
+    p.part_D = nullptr; p.part_idx = nullptr; p.part_stride = 0;
+    p.skip = c.skip; p.skip_stride = c.skip_stride;
+    p.stages_total = stages; p.stages_per_split = per;
+    p.use_lo = c.use_lo;
+    {
+        static int nores = -1;
+        if (nores < 0) { const char *e = getenv("ISR_NN2_NORESOLVE"); nores = (e && atoi(e)) ? 1 : 0; }
+        p.debug_no_resolve = nores;
+    }
+    dim3 grid((unsigned)nqb, (unsigned)splits, (unsigned)c.batch);
+    if (splits == 1) return V::launch(p, grid, c.st);
+
+    const long long total = (long long)c.nq * c.batch;
+    const size_t need = align256((size_t)total * splits * 8) + (size_t)total * splits * 4;
+    ISR_REQUIRE(c.workspace != nullptr && c.workspace_bytes >= need, ISR_E_WORKSPACE,
+                "nn: workspace %zu < %zu bytes", c.workspace_bytes, need);
+    p.part_D = reinterpret_cast<double *>(c.workspace);
+    p.part_idx = reinterpret_cast<int *>(reinterpret_cast<char *>(c.workspace) +
+                                         align256((size_t)total * splits * 8));
+    p.part_stride = total;
+    ISR_TRY(V::launch(p, grid, c.st));
+    nn2_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.st>>>(
+        p.part_D, p.part_idx, total, splits, c.out_d2, c.out_idx, c.skip, c.skip_stride,
+        (long long)c.nq);
+    return launched("nn2_combine_kernel");
+}
+
+#ifdef ISR_NN_TUNING
+using NN2T1 = NN2Variant<8, 128, 1024, 3, 16, 4>;
+using NN2T2 = NN2Variant<8, 128, 1024, 3, 64, 4>;
+using NN2T3 = NN2Variant<8, 128, 1024, 3, 32, 4, 4>;
+using NN2T4 = NN2Variant<8, 128, 1024, 3, 32, 4, 1>;
+using NN2T5 = NN2Variant<4, 128, 1024, 3, 32, 6>;
+using NN2T6 = NN2Variant<8, 256, 1024, 3, 32, 2>;
+using NN2T7 = NN2Variant<12, 128, 1024, 3, 32, 3>;
+using NN2T8 = NN2Variant<16, 64, 1024, 3, 32, 4>;
+using NN2T9 = NN2Variant<8, 128, 512, 4, 32, 4>;
+using NN2T10 = NN2Variant<8, 128, 1024, 3, 32, 3, 4>;
+using NN2T11 = NN2Variant<6, 128, 1024, 3, 32, 5>;
+using NN2T12 = NN2Variant<8, 128, 1024, 3, 128, 4>;
+#endif
+
+}  // namespace isr
+
+extern "C" {
+
+size_t isr_nn2_workspace_bytes(int64_t nq, int64_t nt, int64_t batch) {
+    using namespace isr;
+    if (nq <= 0 || batch <= 0 || nt <= 0) return 256;
+    const int64_t nt_pad = isr_soa_padded_len(nt);
+    const int nqb = (int)((nq + 2047) / 2048);  // largest CTA tile of any variant
+    const int splits = choose_splits((long long)nqb * batch, (int)(nt_pad / 512), kSlotsUpperBound);
+    if (splits <= 1) return 256;
+    const size_t total = (size_t)nq * (size_t)batch;
+    return align256(total * splits * 8) + align256(total * splits * 4);
+}
+
+int isr_nn2(const float *q_soa7, int64_t nq, int64_t nq_pad, int64_t q_bstride, const float *t_soa7,
+            int64_t nt, int64_t nt_pad, int64_t t_bstride, int64_t batch, int use_lo, float *out_d2,
+            int32_t *out_idx, const int32_t *skip, int64_t skip_stride, void *workspace,
+            size_t workspace_bytes, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(nq >= 0 && nt >= 1 && batch >= 0, ISR_E_SHAPE,
+                "nn: need nq >= 0, nt >= 1, batch >= 0 (nq=%lld nt=%lld batch=%lld)",
+                (long long)nq, (long long)nt, (long long)batch);
+    if (nq == 0 || batch == 0) return ISR_OK;
+    ISR_REQUIRE(q_soa7 && t_soa7 && out_d2, ISR_E_INVALID_ARG, "nn: null pointer");
+    ISR_REQUIRE(nq_pad >= nq && nq_pad % ISR_SOA_TILE == 0 && nt_pad >= nt &&
+                    nt_pad % ISR_SOA_TILE == 0,
+                ISR_E_SHAPE, "nn: padded lengths must be multiples of %d covering n", ISR_SOA_TILE);
+    ISR_REQUIRE(nq_pad < (1ll << 31) - 2048 && nt_pad < (1ll << 31) - 2048, ISR_E_SHAPE,
+                "nn: clouds beyond int32 indexing");
+    ISR_REQUIRE(batch <= 65535, ISR_E_SHAPE, "nn: batch %lld > 65535", (long long)batch);
+    ISR_REQUIRE(aligned16(t_soa7) && (t_bstride % 4 == 0), ISR_E_ALIGN,
+                "nn: target planes must be 16-byte aligned");
+    const NN2Call c{q_soa7, nq, nq_pad, q_bstride, t_soa7, nt, nt_pad, t_bstride, batch, use_lo,
+                    out_d2, out_idx, skip, skip_stride, workspace, workspace_bytes,
+                    (cudaStream_t)stream};
+#ifdef ISR_NN_TUNING
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("ISR_NN_VARIANT");
+        variant = e ? atoi(e) : 0;
+    }
+    switch (variant) {
+        case 1: return nn2_dispatch<NN2T1>(c);
+        case 2: return nn2_dispatch<NN2T2>(c);
+        case 3: return nn2_dispatch<NN2T3>(c);
+        case 4: return nn2_dispatch<NN2T4>(c);
+        case 5: return nn2_dispatch<NN2T5>(c);
+        case 6: return nn2_dispatch<NN2T6>(c);
+        case 7: return nn2_dispatch<NN2T7>(c);
+        case 8: return nn2_dispatch<NN2T8>(c);
+        case 9: return nn2_dispatch<NN2T9>(c);
+        case 10: return nn2_dispatch<NN2T10>(c);
+        case 11: return nn2_dispatch<NN2T11>(c);
+        case 12: return nn2_dispatch<NN2T12>(c);
+        default: break;
+    }
+#endif
+    return nn2_dispatch<NN2Main>(c);
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// K1' -- cloud preparation for the filtered nearest-neighbour kernel (nn2.cu).
+//
+// Same rigid transform as K1 (FP64 R.p + t; verfication.py:83-85, icp.py:68,110), but the
+// result is (a) shifted by a per-batch centre c so that coordinates are small, and (b) kept
+// at FP64 accuracy as a float32 hi/lo pair.  Output "SoA7" planes per cloud, each npad long:
+//   0,1,2  hi.x hi.y hi.z    float32( R.p + t - c )
+//   3      norm              fl32 |hi|^2 = fma(z,z, fma(y,y, x*x))
+//   4,5,6  lo.x lo.y lo.z    float32( (R.p + t - c) - hi )
+// Distances are translation invariant, so subtracting the same c from both clouds of a pair
+// changes nothing mathematically; hi+lo reproduces the FP64 coordinate to ~2^-48.
+// Padded slots: hi = ISR_PAD_COORD, norm = 3 ISR_PAD_COORD^2 (finite), lo = 0.
+//
+// The centre is c = C . m with m the centroid of a cloud (FP64, centroid_kernel) and C the
+// "centre pose" of the batch item (NULL = identity): for candidate verification both clouds
+// of candidate k use c_k = Pt_k . centroid(cloud_t).
+// HBM: reads n*12 B (L2-resident across the batch), writes 7 planes * 4 B per point.
+#include "isr_common.cuh"
+
+namespace isr {
+
+constexpr int kPrepThreads = 256;
+
+// single CTA, fixed order => deterministic.  out[0..2] = mean of pts (FP64).
+__global__ void __launch_bounds__(1024)
+centroid_kernel(const float *__restrict__ pts, int64_t n, double *__restrict__ out) {
+    __shared__ double red[3][32];
+    double sx = 0, sy = 0, sz = 0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        sx += pts[3 * i];
+        sy += pts[3 * i + 1];
+        sz += pts[3 * i + 2];
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = sx; red[1][threadIdx.x >> 5] = sy; red[2][threadIdx.x >> 5] = sz;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        sx = warp_sum(red[0][threadIdx.x]);
+        sy = warp_sum(red[1][threadIdx.x]);
+        sz = warp_sum(red[2][threadIdx.x]);
+        if (threadIdx.x == 0) {
+            const double inv = n > 0 ? 1.0 / (double)n : 0.0;
+            out[0] = sx * inv; out[1] = sy * inv; out[2] = sz * inv;
+        }
+    }
+}
+
+// grid: (npad / 256, b)
+__global__ void __launch_bounds__(kPrepThreads)
+prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts_lo, int64_t n,
+                    const double *__restrict__ poses,
+                    int64_t pose_stride, const double *__restrict__ centre_poses,
+                    int64_t centre_pose_stride, const double *__restrict__ centroid,
+                    float *__restrict__ out, int64_t npad, const int32_t *__restrict__ skip,
+                    int64_t skip_stride) {
+    __shared__ float stage[kPrepThreads * 3];
+    const int b = blockIdx.y;
+    if (skip != nullptr && skip[(int64_t)b * skip_stride] != 0) return;
+    const int64_t p0 = (int64_t)blockIdx.x * kPrepThreads;
+    const int cnt = (int)max((int64_t)0, min((int64_t)kPrepThreads, n - p0));
+    const int tid = threadIdx.x;
+    const float *src = pts + p0 * 3;
+    for (int k = tid; k < cnt * 3; k += kPrepThreads) stage[k] = src[k];
+    __syncthreads();
+
+    float hx = ISR_PAD_COORD, hy = ISR_PAD_COORD, hz = ISR_PAD_COORD;
+    float lx = 0.f, ly = 0.f, lz = 0.f;
+    if (tid < cnt) {
+        // centre of this batch item
+        double cx = 0, cy = 0, cz = 0;
+        if (centroid != nullptr) {
+            cx = centroid[0]; cy = centroid[1]; cz = centroid[2];
+            if (centre_poses != nullptr) {
+                const double *C = centre_poses + (int64_t)b * centre_pose_stride;
+                const double mx = cx, my = cy, mz = cz;
+                cx = ((C[0] * mx + C[1] * my) + C[2] * mz) + C[3];
+                cy = ((C[4] * mx + C[5] * my) + C[6] * mz) + C[7];
+                cz = ((C[8] * mx + C[9] * my) + C[10] * mz) + C[11];
+            }
+        }
+        double px = stage[tid * 3], py = stage[tid * 3 + 1], pz = stage[tid * 3 + 2];
+        if (pts_lo != nullptr) {  // float64 input carried as a float32 hi/lo pair
+            const float *l = pts_lo + (p0 + tid) * 3;
+            px += (double)l[0]; py += (double)l[1]; pz += (double)l[2];
+        }
+        double x = px, y = py, z = pz;
+        if (poses != nullptr) {
+            const double *P = poses + (int64_t)b * pose_stride;
+            x = ((P[0] * px + P[1] * py) + P[2] * pz) + P[3];
+            y = ((P[4] * px + P[5] * py) + P[6] * pz) + P[7];
+            z = ((P[8] * px + P[9] * py) + P[10] * pz) + P[11];
+        }
+        x -= cx; y -= cy; z -= cz;
+        hx = (float)x; hy = (float)y; hz = (float)z;
+        lx = (float)(x - (double)hx); ly = (float)(y - (double)hy); lz = (float)(z - (double)hz);
+    }
+    const float nrm = __fmaf_rn(hz, hz, __fmaf_rn(hy, hy, __fmul_rn(hx, hx)));
+    float *o = out + (int64_t)b * 7 * npad + p0 + tid;
+    o[0] = hx;
+    o[npad] = hy;
+    o[2 * npad] = hz;
+    o[3 * npad] = nrm;
+    o[4 * npad] = lx;
+    o[5 * npad] = ly;
+    o[6 * npad] = lz;
+}
+
+}  // namespace isr
+
+extern "C" {
+
+int isr_centroid(const float *pts, int64_t n, double *out3, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(n >= 0 && out3 != nullptr && (pts != nullptr || n == 0), ISR_E_INVALID_ARG,
+                "centroid: bad argument");
+    ProfScope prof(kProfTransform, (cudaStream_t)stream);
+    centroid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pts, n, out3);
+    return launched("centroid_kernel");
+}
+
+int isr_prepare_cloud(const float *pts, const float *pts_lo, int64_t n, const double *poses,
+                      int64_t pose_stride,
+                      const double *centre_poses, int64_t centre_pose_stride,
+                      const double *centroid, int64_t b, float *out_soa7, int64_t npad,
+                      const int32_t *skip, int64_t skip_stride, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(n >= 0 && b >= 1, ISR_E_SHAPE, "prepare_cloud: bad size");
+    ISR_REQUIRE(out_soa7 && (pts || n == 0), ISR_E_INVALID_ARG, "prepare_cloud: null pointer");
+    ISR_REQUIRE(npad >= n && npad % ISR_SOA_TILE == 0 && npad > 0, ISR_E_SHAPE,
+                "prepare_cloud: npad %lld must be a positive multiple of %d and >= n",
+                (long long)npad, ISR_SOA_TILE);
+    ISR_REQUIRE(poses != nullptr || b == 1, ISR_E_INVALID_ARG,
+                "prepare_cloud: repack (poses NULL) needs b == 1");
+    ISR_REQUIRE(b <= 65535, ISR_E_SHAPE, "prepare_cloud: batch %lld > 65535", (long long)b);
+    ISR_REQUIRE(aligned16(out_soa7), ISR_E_ALIGN, "prepare_cloud: out not 16-byte aligned");
+    dim3 grid((unsigned)(npad / kPrepThreads), (unsigned)b);
+    ProfScope prof(kProfTransform, (cudaStream_t)stream);
+    prepare_soa7_kernel<<<grid, kPrepThreads, 0, (cudaStream_t)stream>>>(
+        pts, pts_lo, n, poses, pose_stride, centre_poses, centre_pose_stride, centroid, out_soa7, npad,
+        skip, skip_stride);
+    return launched("prepare_soa7_kernel");
+}
+
+}  // extern "C"

@@ -8,6 +8,8 @@
 // The selection is a single-CTA first-minimum argmin (list.index(min(...)),
 // verfication.py:105-106).  No float atomics anywhere: results are run-to-run identical.
 #include <math_constants.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "isr_common.cuh"
 
@@ -66,10 +68,10 @@ argmin_first_kernel(const double *__restrict__ loss, int64_t n, int64_t *__restr
 }
 
 static int verify_chunk(int64_t nq, int64_t nt, int64_t b) {
-    // cap the SoA scratch near 2 GiB and the grid z-dimension; at least 1
+    // cap the SoA scratch near 4 GiB and the grid z-dimension; at least 1
     const int64_t nqp = isr_soa_padded_len(nq), ntp = isr_soa_padded_len(nt);
-    const int64_t per = (nqp + ntp) * 12;
-    int64_t c = (int64_t(2) << 30) / per;
+    const int64_t per = (nqp + ntp) * 28;
+    int64_t c = (int64_t(4) << 30) / per;
     if (c > 256) c = 256;
     if (c > b) c = b;
     if (c < 1) c = 1;
@@ -77,21 +79,36 @@ static int verify_chunk(int64_t nq, int64_t nt, int64_t b) {
 }
 
 struct VerifyLayout {
-    size_t xs, ys, d2a, d2b, means, nnws, total;
+    size_t xs, ys, d2a, d2b, means, centroid, nnws, total;
     int chunk;
 };
+
+// 1 = direct-difference K2 (nn.cu, 3 planes), 0 = filtered exact K2 (nn2.cu, 7 planes)
+bool nn_mode_direct() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("ISR_NN_MODE");
+        mode = (e != nullptr && strcmp(e, "direct") == 0) ? 1 : 0;
+    }
+    return mode == 1;
+}
 
 static VerifyLayout verify_layout(int64_t nq, int64_t nt, int64_t b, int bidirectional) {
     VerifyLayout L;
     L.chunk = verify_chunk(nq, nt, b);
     const int64_t nqp = isr_soa_padded_len(nq), ntp = isr_soa_padded_len(nt);
+    const int planes = 7;  // sized for the larger layout so either mode fits
+    const int64_t big = nq > nt ? nq : nt;
     size_t off = 0;
-    L.xs = off;   off += align256((size_t)L.chunk * 3 * nqp * 4);
-    L.ys = off;   off += align256((size_t)L.chunk * 3 * ntp * 4);
+    L.xs = off;   off += align256((size_t)L.chunk * planes * nqp * 4);
+    L.ys = off;   off += align256((size_t)L.chunk * planes * ntp * 4);
     L.d2a = off;  off += align256((size_t)L.chunk * nq * 4);
     L.d2b = off;  off += bidirectional ? align256((size_t)L.chunk * nt * 4) : 0;
     L.means = off; off += align256((size_t)2 * L.chunk * 8);
-    L.nnws = off; off += isr_nn_workspace_bytes(nq > nt ? nq : nt, nq > nt ? nq : nt, L.chunk);
+    L.centroid = off; off += 256;
+    const size_t w1 = isr_nn_workspace_bytes(big, big, L.chunk);
+    const size_t w2 = isr_nn2_workspace_bytes(nq < nt ? nq : nt, big, L.chunk);
+    L.nnws = off; off += w1 > w2 ? w1 : w2;
     L.total = off;
     return L;
 }
@@ -131,18 +148,35 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
     const size_t nnws_bytes = L.total - L.nnws;
     const int64_t nqp = isr_soa_padded_len(nq), ntp = isr_soa_padded_len(nt);
 
+    const bool direct = nn_mode_direct();
+    double *centroid = reinterpret_cast<double *>(ws + L.centroid);
+    if (!direct) ISR_TRY(isr_centroid(cloud_t, nt, centroid, stream));
     for (int64_t k0 = 0; k0 < b; k0 += L.chunk) {
         const int c = (int)((b - k0) < L.chunk ? (b - k0) : L.chunk);
-        ISR_TRY(isr_transform_points_soa(cloud_q, nq, poses_q + k0 * 16, 16, c, xs, nqp, nullptr, 0,
-                                         stream));
-        ISR_TRY(isr_transform_points_soa(cloud_t, nt, poses_t + k0 * 16, 16, c, ys, ntp, nullptr, 0,
-                                         stream));
-        ISR_TRY(isr_nn_soa(xs, nq, nqp, 3 * nqp, ys, nt, ntp, 3 * ntp, c, d2a, nullptr, nullptr, 0,
-                           nnws, nnws_bytes, stream));
+        if (direct) {
+            ISR_TRY(isr_transform_points_soa(cloud_q, nq, poses_q + k0 * 16, 16, c, xs, nqp, nullptr,
+                                             0, stream));
+            ISR_TRY(isr_transform_points_soa(cloud_t, nt, poses_t + k0 * 16, 16, c, ys, ntp, nullptr,
+                                             0, stream));
+            ISR_TRY(isr_nn_soa(xs, nq, nqp, 3 * nqp, ys, nt, ntp, 3 * ntp, c, d2a, nullptr, nullptr,
+                               0, nnws, nnws_bytes, stream));
+        } else {
+            // both clouds of candidate k are centred on c_k = Pt_k . centroid(cloud_t)
+            ISR_TRY(isr_prepare_cloud(cloud_q, nullptr, nq, poses_q + k0 * 16, 16, poses_t + k0 * 16, 16,
+                                      centroid, c, xs, nqp, nullptr, 0, stream));
+            ISR_TRY(isr_prepare_cloud(cloud_t, nullptr, nt, poses_t + k0 * 16, 16, poses_t + k0 * 16, 16,
+                                      centroid, c, ys, ntp, nullptr, 0, stream));
+            ISR_TRY(isr_nn2(xs, nq, nqp, 7 * nqp, ys, nt, ntp, 7 * ntp, c, 0, d2a, nullptr, nullptr,
+                            0, nnws, nnws_bytes, stream));
+        }
         ISR_TRY(isr_mean_sqrt(d2a, nq, c, means, stream));
         if (bidirectional) {
-            ISR_TRY(isr_nn_soa(ys, nt, ntp, 3 * ntp, xs, nq, nqp, 3 * nqp, c, d2b, nullptr, nullptr,
-                               0, nnws, nnws_bytes, stream));
+            if (direct)
+                ISR_TRY(isr_nn_soa(ys, nt, ntp, 3 * ntp, xs, nq, nqp, 3 * nqp, c, d2b, nullptr,
+                                   nullptr, 0, nnws, nnws_bytes, stream));
+            else
+                ISR_TRY(isr_nn2(ys, nt, ntp, 7 * ntp, xs, nq, nqp, 7 * nqp, c, 0, d2b, nullptr,
+                                nullptr, 0, nnws, nnws_bytes, stream));
             ISR_TRY(isr_mean_sqrt(d2b, nt, c, means + L.chunk, stream));
         }
         verify_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(means, means + L.chunk, valid, k0, c,

@@ -85,7 +85,7 @@ int isr_transform_points_soa(const float *pts, int64_t n, const double *poses,
                              int64_t pose_stride, int64_t b, float *out_soa, int64_t npad,
                              const int32_t *skip, int64_t skip_stride, void *stream);
 
-/* ---- K2: brute-force nearest neighbour ---------------------------------------------- */
+/* ---- K2 (direct-difference form, kept for A/B and bit-exact FP32 checks) ---------------- */
 /* For every query of every batch: squared distance to, and index of, its nearest target.
  * q_soa [batch][3][nq_pad] (q_bstride floats between batches, 0 = shared),
  * t_soa likewise.  out_d2 float32 [batch][nq]; out_idx int32 [batch][nq] or NULL.
@@ -97,6 +97,34 @@ int isr_nn_soa(const float *q_soa, int64_t nq, int64_t nq_pad, int64_t q_bstride
                const float *t_soa, int64_t nt, int64_t nt_pad, int64_t t_bstride,
                int64_t batch, float *out_d2, int32_t *out_idx, const int32_t *skip,
                int64_t skip_stride, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- K1' + K2 (production): centred hi/lo planes and the filtered exact search --------- */
+/* out3[0..2] = FP64 centroid of pts (single CTA, fixed summation order). */
+int isr_centroid(const float *pts, int64_t n, double *out3, void *stream);
+
+/* K1 with centring and FP64-accurate output, "SoA7" planes out[b][7][npad]:
+ *   0-2 hi = float32(R_b p + t_b - c_b), 3 = fl32 |hi|^2, 4-6 lo = float32(exact - hi).
+ * c_b = C_b . centroid (centre_poses NULL: c_b = centroid; centroid NULL: c_b = 0).
+ * Both clouds of a pair must be prepared with the same c_b.  poses NULL = identity (b == 1).
+ * pts_lo (float32 [n][3], may be NULL): low part of a float64 input cloud, p = pts + pts_lo
+ * (icp.py:68 hands Open3D a float64 camera-frame source).
+ * Strides are in doubles.  Replaces the same reference lines as isr_transform_points_soa. */
+int isr_prepare_cloud(const float *pts, const float *pts_lo, int64_t n, const double *poses,
+                      int64_t pose_stride,
+                      const double *centre_poses, int64_t centre_pose_stride,
+                      const double *centroid, int64_t b, float *out_soa7, int64_t npad,
+                      const int32_t *skip, int64_t skip_stride, void *stream);
+
+/* Brute-force exact 1-NN on SoA7 clouds: FP32 3-FMA filter over every pair, FP64 resolve of
+ * the few targets inside the proven error window (nn2.cu).  out_idx equals the float64
+ * brute-force argmin of the prepared coordinates (lowest index on exact ties); out_d2 is
+ * that FP64 squared distance rounded to float32.  use_lo == 0 ignores the lo planes
+ * (distances between the float32 hi coordinates).  Same reference call sites as isr_nn_soa. */
+size_t isr_nn2_workspace_bytes(int64_t nq, int64_t nt, int64_t batch);
+int isr_nn2(const float *q_soa7, int64_t nq, int64_t nq_pad, int64_t q_bstride,
+            const float *t_soa7, int64_t nt, int64_t nt_pad, int64_t t_bstride, int64_t batch,
+            int use_lo, float *out_d2, int32_t *out_idx, const int32_t *skip, int64_t skip_stride,
+            void *workspace, size_t workspace_bytes, void *stream);
 
 /* out_mean[b] = mean_i sqrt(d2[b][i]) in FP64, fixed summation order (deterministic).
  * np.mean(np.asarray(compute_point_cloud_distance(..))) -- verfication.py:98,100. */
@@ -137,13 +165,16 @@ typedef struct IsrIcpState {
  * target, and reduce the 17 FP64 sums over correspondences with d2 < max_dist^2 (strict)
  * into sums[starts][17].  corr_idx int32 [starts][ns] receives the NN index of every
  * source point, inlier uint8 [starts][ns] its correspondence flag.  States whose `done`
- * is set are skipped.  This is GetRegistrationResultAndCorrespondences of Open3D's
+ * is set are skipped.  tgt_soa7 = isr_prepare_cloud(tgt, identity, centroid) and `centroid`
+ * (device double[3], normally isr_centroid(tgt)) are prepared once per target.  src_lo (may
+ * be NULL) is the float32 low part of a float64 source, as in isr_prepare_cloud.  This is GetRegistrationResultAndCorrespondences of Open3D's
  * RegistrationICP (icp.py:97-103, upstream). */
 size_t isr_icp_workspace_bytes(int64_t ns, int64_t nt, int64_t starts);
-int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, int64_t ns,
-                       const float *tgt, const float *tgt_soa, int64_t nt, int64_t nt_pad,
-                       double max_dist, double *sums, int32_t *corr_idx, uint8_t *inlier,
-                       void *workspace, size_t workspace_bytes, void *stream);
+int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src,
+                       const float *src_lo, int64_t ns, const float *tgt, const float *tgt_soa7, const double *centroid,
+                       int64_t nt, int64_t nt_pad, double max_dist, double *sums,
+                       int32_t *corr_idx, uint8_t *inlier, void *workspace,
+                       size_t workspace_bytes, void *stream);
 
 /* Consume sums[starts][17] (already reduced over all source shards): set fitness / rmse
  * (ns_total = global source count), apply Open3D's break test against the previous
@@ -157,11 +188,11 @@ int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64
  * max_iteration + 1 evaluation passes; converged starts skip the rest on the device.
  * o3d.pipelines.registration.registration_icp, icp.py:101-103; with max_iteration == 0
  * it is evaluate_registration, icp.py:97-98. */
-int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, int64_t ns,
-                const float *tgt, const float *tgt_soa, int64_t nt, int64_t nt_pad,
-                double max_dist, int max_iteration, double rel_fitness, double rel_rmse,
-                double *sums, int32_t *corr_idx, uint8_t *inlier, void *workspace,
-                size_t workspace_bytes, void *stream);
+int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                int64_t ns, const float *tgt, const float *tgt_soa7, const double *centroid, int64_t nt,
+                int64_t nt_pad, double max_dist, int max_iteration, double rel_fitness,
+                double rel_rmse, double *sums, int32_t *corr_idx, uint8_t *inlier,
+                void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* FFMA-chain microbenchmark: launches `blocks` x 256 threads, each running `iters`

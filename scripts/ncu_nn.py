@@ -11,7 +11,23 @@ cloud = synth.make_cloud(N, 1)
 rng = np.random.default_rng(0)
 P = np.tile(np.eye(4), (B, 1, 1))
 for k in range(B): P[k, :3, :3] = synth.random_rotation(rng)
-q = api.pack_soa(cloud, P); t = api.pack_soa(cloud)
+mode = os.environ.get("NCU_MODE", "exact")
+if os.environ.get("PROBE_SORT", "0") == "1":
+    lo, hi = cloud.min(0), cloud.max(0)
+    g = np.clip(((cloud - lo) / (hi - lo + 1e-9) * 1023).astype(np.uint64), 0, 1023)
+    def spread(v):
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+    code = spread(g[:, 0]) | (spread(g[:, 1]) << 1) | (spread(g[:, 2]) << 2)
+    cloud = cloud[np.argsort(code, kind="stable")]
+if mode == "direct":
+    q = api.pack_soa(cloud, P); t = api.pack_soa(cloud)
+else:
+    cen = api.centroid_of(cloud)
+    q = api.prepare_cloud(cloud, P, centroid=cen); t = api.prepare_cloud(cloud, centroid=cen)
 for _ in range(3):
     r = api.nearest_neighbors_soa(q, t, return_index=idx)
 torch.cuda.synchronize()

@@ -17,22 +17,38 @@ def timeit(fn, reps=3, warm=1):
     return min(ts), float(np.median(ts))
 
 print("ffma scalar TF/s", isr.measure_fp32_peak(False), "packed", isr.measure_fp32_peak(True))
+def morton_sort(c):
+    lo, hi = c.min(0), c.max(0)
+    g = np.clip(((c - lo) / (hi - lo + 1e-9) * 1023).astype(np.uint64), 0, 1023)
+    def spread(v):
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+    code = spread(g[:, 0]) | (spread(g[:, 1]) << 1) | (spread(g[:, 2]) << 2)
+    return c[np.argsort(code, kind="stable")]
+SORT = os.environ.get("PROBE_SORT", "0") == "1"
 which = sys.argv[1:] or ["nn", "verify", "icp"]
 if "nn" in which:
     N = 100000
     cloud = synth.make_cloud(N, 1)
-    for B in (32, 128):
+    if SORT: cloud = morton_sort(cloud)
+    for B in (128,):
         P = np.tile(np.eye(4), (B, 1, 1))
         rng = np.random.default_rng(0)
         for k in range(B): P[k, :3, :3] = synth.random_rotation(rng)
-        q = api.pack_soa(cloud, P); t = api.pack_soa(cloud)
-        for idx in (False, True):
-            best, med = timeit(lambda: api.nearest_neighbors_soa(q, t, return_index=idx))
-            fl = 8.0 * N * N * B
-            print(f"nn B={B} idx={idx}: {best*1e3:.1f} ms best, {med*1e3:.1f} med -> {fl/best/1e12:.2f} TF/s algorithmic ({fl/best/1e12/74.5*100:.1f}% of 74.5)")
+        cen = api.centroid_of(cloud)
+        for name, q, t in (("direct", api.pack_soa(cloud, P), api.pack_soa(cloud)),
+                           ("exact", api.prepare_cloud(cloud, P, centroid=cen), api.prepare_cloud(cloud, centroid=cen))):
+            for idx in (False, True):
+                best, med = timeit(lambda: api.nearest_neighbors_soa(q, t, return_index=idx))
+                fl = 8.0 * N * N * B
+                print(f"nn {name} B={B} idx={idx}: {best*1e3:.1f} ms best, {med*1e3:.1f} med -> {fl/best/1e12:.2f} TF/s algorithmic ({fl/best/1e12/74.5*100:.1f}% of 74.5)")
 if "verify" in which:
     N = 100000; B = 256
     cloud = synth.make_cloud(N, 1)
+    if SORT: cloud = morton_sort(cloud)
     R_true, _ = synth.true_pose(3)
     Rs, _, k0 = synth.make_candidates(B, 10, R_true=R_true, t_true=np.zeros(3))
     Mq, Mt = synth.verification_matrices(Rs, R_true)
@@ -41,6 +57,7 @@ if "verify" in which:
     print(f"verify B={B}: {best:.3f}s -> {B/best:.1f} cand/s; {16.0*N*N*B/best/1e12:.2f} TF/s")
 if "icp" in which:
     src, tgt, _ = synth.icp_pair(1000000, 1000000, 4, 5)
+    if SORT: src, tgt = morton_sort(src), morton_sort(tgt)
     prob = isr.IcpProblem(src, tgt, np.eye(4)[None])
     def one():
         prob.accumulate(20.0); prob.solve(prob.ns, 0.0, 0.0, False)

@@ -32,6 +32,27 @@ def test_transform_points_matches_float64(gpu, n):
     assert np.all(np.abs(got.astype(np.float64) - ref) <= 1.0 * ulp)
 
 
+def test_prepare_cloud_hi_lo_planes(gpu):
+    """SoA7: hi + lo reproduces the float64 transformed, centred coordinate; norm = |hi|^2."""
+    rng = np.random.default_rng(0)
+    pts = rng.normal(scale=60, size=(3000, 3)).astype(np.float32)
+    P = _rand_poses(3, 2, trans=700.0)
+    cen = rng.normal(scale=5, size=3)
+    soa = gpu.prepare_cloud(pts, P, centroid=cen, centre_poses=P)
+    d = soa.data.cpu().numpy().astype(np.float64)
+    assert d.shape == (3, 7, 3072)
+    for k in range(3):
+        c = P[k, :3, :3] @ cen + P[k, :3, 3]
+        ref = oracle.transform(pts, P[k]) - c
+        np.testing.assert_allclose(d[k, 0:3, :3000].T + d[k, 4:7, :3000].T, ref, rtol=0, atol=2e-11)
+        hi = d[k, 0:3, :3000].astype(np.float32)
+        nrm = (hi.astype(np.float64) ** 2).sum(0)
+        np.testing.assert_allclose(d[k, 3, :3000], nrm, rtol=3e-7)
+        assert np.all(d[k, 0:3, 3000:] == np.float32(1e18)) and np.all(d[k, 4:7, 3000:] == 0)
+    cg = gpu.centroid_of(pts).cpu().numpy()
+    np.testing.assert_allclose(cg, pts.astype(np.float64).mean(0), rtol=0, atol=1e-10)
+
+
 def test_pack_soa_layout_and_padding(gpu):
     pts = np.arange(30, dtype=np.float32).reshape(10, 3)
     soa = gpu.pack_soa(pts)
@@ -44,16 +65,34 @@ def test_pack_soa_layout_and_padding(gpu):
 # ---- K2 ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("nq,nt", [(1, 1), (7, 3), (1000, 1000), (1025, 4097), (3000, 20000),
                                    (300, 70000)])
-def test_nn_bit_exact_vs_fma_emulation(gpu, nq, nt):
-    """d2 bits and indices equal the C float32 emulation of the kernel's rounding sequence."""
+def test_nn_direct_bit_exact_vs_fma_emulation(gpu, nq, nt):
+    """Direct-difference kernel: d2 bits and indices equal the C float32 emulation of the
+    kernel's rounding sequence."""
     rng = np.random.default_rng(nq * 7 + nt)
     q = rng.normal(scale=40, size=(nq, 3)).astype(np.float32)
     t = rng.normal(scale=40, size=(nt, 3)).astype(np.float32)
-    res = gpu.nearest_neighbors(q, t)
+    res = gpu.nearest_neighbors(q, t, mode="direct")
     d2, idx = res.d2.cpu().numpy(), res.idx.cpu().numpy()
     rd2, ridx = c_oracle.nn_f32_fma(q, t)
     np.testing.assert_array_equal(d2.view(np.uint32), rd2.view(np.uint32))
     np.testing.assert_array_equal(idx, ridx)
+
+
+@pytest.mark.parametrize("nq,nt,scale,offset", [
+    (1, 1, 40, 0), (7, 3, 40, 0), (1000, 1000, 40, 0), (1025, 4097, 40, 0), (3000, 20000, 40, 0),
+    (300, 70000, 40, 0), (2000, 30000, 40, 700), (2000, 30000, 0.01, 0), (2000, 30000, 5000, -3000)])
+def test_nn_exact_equals_float64_bruteforce(gpu, nq, nt, scale, offset):
+    """Production kernel (FP32 filter + FP64 resolve): the index IS the float64 brute-force
+    argmin (lowest index on ties) and d2 is the float64 distance rounded to float32 --
+    for object-frame, camera-frame (700 mm offset), tiny and huge coordinate ranges."""
+    rng = np.random.default_rng(nq * 7 + nt)
+    q = (rng.normal(scale=scale, size=(nq, 3)) + offset).astype(np.float32)
+    t = (rng.normal(scale=scale, size=(nt, 3)) + offset).astype(np.float32)
+    res = gpu.nearest_neighbors(q, t)
+    d2, idx = res.d2.cpu().numpy(), res.idx.cpu().numpy()
+    rd2, ridx = c_oracle.nn_f64(q, t)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_allclose(d2, rd2, rtol=1.2e-7, atol=0)
 
 
 def test_nn_indices_match_float64_oracle_on_surface_cloud(gpu):
@@ -62,11 +101,14 @@ def test_nn_indices_match_float64_oracle_on_surface_cloud(gpu):
     t = synth.make_cloud(100000, seed=1)
     q = synth.make_cloud(20000, seed=2)
     for offset in (np.zeros(3, np.float32), np.array([0, 0, 700], np.float32)):
-        res = gpu.nearest_neighbors(q + offset, t + offset)
         dk, ik = oracle.nearest(q + offset, t + offset)
+        res = gpu.nearest_neighbors(q + offset, t + offset)
+        np.testing.assert_array_equal(res.idx.cpu().numpy(), ik)          # exact, no exceptions
+        np.testing.assert_allclose(res.dist.cpu().numpy(), dk, rtol=1e-7, atol=0)
+        res = gpu.nearest_neighbors(q + offset, t + offset, mode="direct")
         idx = res.idx.cpu().numpy()
         mism = np.nonzero(idx != ik)[0]
-        # any mismatch must be a float32-resolution tie in the oracle's own distances
+        # FP32 direct form: any mismatch must be a float32-resolution tie
         if len(mism):
             d_alt = np.linalg.norm((q + offset)[mism].astype(np.float64)
                                    - (t + offset)[idx[mism]].astype(np.float64), axis=1)
@@ -80,11 +122,12 @@ def test_nn_lattice_ties_pick_lowest_index(gpu):
     t = g.reshape(-1, 3).astype(np.float32)
     t = np.concatenate([t, t], axis=0)  # every target duplicated: ties everywhere
     q = (g.reshape(-1, 3) + 0.5).astype(np.float32)  # cell centres: 8-way ties (x2)
-    res = gpu.nearest_neighbors(q, t)
     rd2, ridx = c_oracle.nn_f32_fma(q, t)
-    np.testing.assert_array_equal(res.idx.cpu().numpy(), ridx)
-    assert np.all(res.idx.cpu().numpy() < len(t) // 2)
-    np.testing.assert_array_equal(res.d2.cpu().numpy(), rd2)
+    for mode in ("exact", "direct"):
+        res = gpu.nearest_neighbors(q, t, mode=mode)
+        np.testing.assert_array_equal(res.idx.cpu().numpy(), ridx)
+        assert np.all(res.idx.cpu().numpy() < len(t) // 2)
+        np.testing.assert_array_equal(res.d2.cpu().numpy(), rd2)
 
 
 def test_nn_identical_and_shifted_clouds(gpu):
@@ -101,11 +144,15 @@ def test_nn_batched_shared_target(gpu):
     rng = np.random.default_rng(3)
     q = rng.normal(scale=30, size=(5, 700, 3)).astype(np.float32)
     t = rng.normal(scale=30, size=(2500, 3)).astype(np.float32)
-    res = gpu.nearest_neighbors(q, t)
+    res = gpu.nearest_neighbors(q, t, mode="direct")
+    res2 = gpu.nearest_neighbors(q, t)
     for b in range(5):
         rd2, ridx = c_oracle.nn_f32_fma(q[b], t)
         np.testing.assert_array_equal(res.d2[b].cpu().numpy(), rd2)
         np.testing.assert_array_equal(res.idx[b].cpu().numpy(), ridx)
+        d64, i64 = c_oracle.nn_f64(q[b], t)
+        np.testing.assert_array_equal(res2.idx[b].cpu().numpy(), i64)
+        np.testing.assert_allclose(res2.d2[b].cpu().numpy(), d64, rtol=1.2e-7)
 
 
 def test_chamfer_and_distance_match_oracle(gpu):
@@ -206,8 +253,7 @@ def test_evaluate_registration_matches_oracle(gpu):
     np.testing.assert_allclose(r.inlier_rmse, o.inlier_rmse, rtol=1e-6)
     cs = r.correspondence_set
     assert cs.shape == o.correspondence_set.shape
-    assert np.mean(cs[:, 1] == o.correspondence_set[:, 1]) > 0.9999
-    np.testing.assert_array_equal(cs[:, 0], o.correspondence_set[:, 0])
+    np.testing.assert_array_equal(cs, o.correspondence_set)   # exact correspondences
 
 
 def test_icp_matches_oracle(gpu):
@@ -330,5 +376,5 @@ def test_bad_arguments_raise(gpu):
         gpu.verify_poses(np.zeros((4, 3)), np.zeros((2, 4, 4)), np.zeros((3, 4, 4)))
     from imagesequenceregistrationfor6dposeestimationlabeling_b200 import _lib
     lib = _lib.load()
-    st = lib.isr_nn_soa(None, 5, 1000, 0, None, 5, 1024, 0, 1, None, None, None, 0, None, 0, None)
+    st = lib.isr_nn2(None, 5, 1000, 0, None, 5, 1024, 0, 1, 1, None, None, None, 0, None, 0, None)
     assert st < 0 and len(lib.isr_last_error()) > 0
