@@ -35,6 +35,12 @@ ICP_STATE_DTYPE = np.dtype([
 assert ICP_STATE_DTYPE.itemsize == 184
 
 
+class IsrCloud(ctypes.Structure):
+    """ctypes mirror of ``struct IsrCloud`` (include/isr.h)."""
+    _fields_ = [("soa7", ctypes.c_void_p), ("n", ctypes.c_int64), ("npad", ctypes.c_int64),
+                ("bstride", ctypes.c_int64), ("stage_c", ctypes.c_void_p), ("perm", ctypes.c_void_p)]
+
+
 class IsrError(RuntimeError):
     """A libisr call returned a negative status."""
 
@@ -65,19 +71,20 @@ SIGNATURES = {
     "isr_nn_soa": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P,
                         _SZ, _P]),
     "isr_centroid": (_I, [_P, _I64, _P, _P]),
-    "isr_prepare_cloud": (_I, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
+    "isr_spatial_order_workspace_bytes": (_SZ, [_I64]),
+    "isr_spatial_order": (_I, [_P, _I64, _P, _P, _SZ, _P]),
+    "isr_prepare_cloud": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
+    "isr_stage_centroids": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P]),
     "isr_nn2_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
-    "isr_nn2": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64, _I, _P, _P, _P, _I64, _P,
-                     _SZ, _P]),
+    "isr_nn2": (_I, [_P, _P, _I64, _I, _P, _P, _P, _I64, _P, _SZ, _P]),
     "isr_mean_sqrt": (_I, [_P, _I64, _I64, _P, _P]),
     "isr_verify_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I]),
     "isr_verify_poses": (_I, [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I, _P, _P, _P, _SZ, _P]),
     "isr_icp_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
-    "isr_icp_accumulate": (_I, [_P, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I64, _D, _P, _P, _P, _P,
-                                _SZ, _P]),
+    "isr_icp_accumulate": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _D, _P, _P, _P, _P, _SZ, _P]),
     "isr_icp_solve": (_I, [_P, _I64, _P, _I64, _D, _D, _I, _P]),
-    "isr_icp_run": (_I, [_P, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I64, _D, _I, _D, _D, _P, _P, _P,
-                         _P, _SZ, _P]),
+    "isr_icp_run": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _D, _I, _D, _D, _P, _P, _P, _P, _SZ,
+                         _P]),
     "isr_bench_ffma": (_I, [_I, _I, _I, _P, _P, _P]),
 }
 

@@ -16,6 +16,7 @@ Reference mapping (file:line into the reference repository):
 """
 from __future__ import annotations
 
+import ctypes
 import dataclasses
 from typing import Optional, Sequence
 
@@ -135,10 +136,17 @@ class SoaCloud:
     data: torch.Tensor
     n: int
     centroid: Optional[torch.Tensor] = None
+    perm: Optional[torch.Tensor] = None      # int32 [n]: stored position -> original index
+    stage_c: Optional[torch.Tensor] = None   # float32 [B, npad/1024, 4] stage centroids
 
     @property
     def planes(self) -> int:
         return self.data.shape[1]
+
+    def descriptor(self, batched: bool) -> "_lib.IsrCloud":
+        """ctypes ``IsrCloud`` for this cloud (7-plane clouds only)."""
+        return _lib.IsrCloud(self.data.data_ptr(), self.n, self.npad,
+                             7 * self.npad if batched else 0, _ptr(self.stage_c), _ptr(self.perm))
 
     @property
     def npad(self) -> int:
@@ -183,10 +191,26 @@ def centroid_of(points, device=None) -> torch.Tensor:
     return out
 
 
-def prepare_cloud(points, poses=None, centroid=None, centre_poses=None, device=None) -> SoaCloud:
+def spatial_order(points, device=None) -> torch.Tensor:
+    """int32 [N] Morton-order permutation of an [N,3] cloud (perm[i] = original index)."""
+    device = _device(device)
+    pts = _points(points, device)
+    n = pts.shape[0]
+    perm = torch.empty((n,), dtype=torch.int32, device=device)
+    if n > 0:
+        lib = _lib.load()
+        ws = _workspace(lib.isr_spatial_order_workspace_bytes(n), device)
+        _lib.check(lib.isr_spatial_order(_ptr(pts), n, _ptr(perm), _ptr(ws), ws.numel(), _stream()))
+    return perm
+
+
+def prepare_cloud(points, poses=None, centroid=None, centre_poses=None, perm=None,
+                  stage_centroids: bool = False, device=None) -> SoaCloud:
     """[N,3] (optionally transformed by poses [B,4,4]) -> centred hi/lo SoA7 planes [B,7,npad].
     The centre of batch item b is centre_poses[b] . centroid (centre_poses None: centroid).
-    float64 input keeps its precision (hi/lo split)."""
+    float64 input keeps its precision (hi/lo split).  `perm` (from spatial_order) stores the
+    points in Morton order; `stage_centroids` adds the per-tile centroids a target needs for
+    nearest-stage-first scanning."""
     device = _device(device)
     pts, pts_lo = _points_hilo(points, device)
     if pts.dim() != 2:
@@ -204,10 +228,17 @@ def prepare_cloud(points, poses=None, centroid=None, centre_poses=None, device=N
     for b0 in range(0, b, 65535):
         bc = min(65535, b - b0)
         _lib.check(lib.isr_prepare_cloud(
-            _ptr(pts), _ptr(pts_lo), n, None if P is None else _ptr(P[b0:]), 16,
+            _ptr(pts), _ptr(pts_lo), _ptr(perm), n, None if P is None else _ptr(P[b0:]), 16,
             None if C is None else _ptr(C[b0:]), 16, _ptr(cen), bc, _ptr(out[b0:]), npad, None, 0,
             _stream()))
-    return SoaCloud(out, n, cen)
+    sc = None
+    if stage_centroids:
+        sc = torch.empty((b, npad // _lib.ISR_SOA_TILE, 4), dtype=torch.float32, device=device)
+        for b0 in range(0, b, 65535):
+            bc = min(65535, b - b0)
+            _lib.check(lib.isr_stage_centroids(_ptr(out[b0:]), n, npad, 7 * npad, bc, _ptr(sc[b0:]),
+                                               _stream()))
+    return SoaCloud(out, n, cen, perm, sc)
 
 
 def _pack_batched(points, device) -> SoaCloud:
@@ -266,11 +297,15 @@ def nearest_neighbors_soa(q: SoaCloud, t: SoaCloud, return_index: bool = True,
         td = t.data[b0:] if tb > 1 else t.data
         if pl == 7:
             ws = _workspace(lib.isr_nn2_workspace_bytes(q.n, t.n, bc), device)
+            qdesc = _lib.IsrCloud(qd.data_ptr(), q.n, q.npad, pl * q.npad if qb > 1 else 0, None,
+                                  _ptr(q.perm))
+            tsc = None if t.stage_c is None else (t.stage_c[b0:] if tb > 1 else t.stage_c)
+            tdesc = _lib.IsrCloud(td.data_ptr(), t.n, t.npad, pl * t.npad if tb > 1 else 0,
+                                  _ptr(tsc), _ptr(t.perm))
             _lib.check(lib.isr_nn2(
-                _ptr(qd), q.n, q.npad, pl * q.npad if qb > 1 else 0,
-                _ptr(td), t.n, t.npad, pl * t.npad if tb > 1 else 0,
-                bc, 1 if use_lo else 0, _ptr(d2[b0:]), _ptr(idx[b0:]) if idx is not None else None,
-                None, 0, _ptr(ws), ws.numel(), _stream()))
+                ctypes.byref(qdesc), ctypes.byref(tdesc), bc, 1 if use_lo else 0, _ptr(d2[b0:]),
+                _ptr(idx[b0:]) if idx is not None else None, None, 0, _ptr(ws), ws.numel(),
+                _stream()))
         else:
             ws = _workspace(lib.isr_nn_workspace_bytes(q.n, t.n, bc), device)
             _lib.check(lib.isr_nn_soa(
@@ -299,10 +334,11 @@ def nearest_neighbors(query, target, return_index: bool = True, mode: str = "exa
         if tp.shape[0] < 1:
             raise ValueError("nearest_neighbors: empty target cloud")
         cen = centroid_of(tp, device)
-        t7 = prepare_cloud(tp, centroid=cen, device=device)
+        t7 = prepare_cloud(tp, centroid=cen, perm=spatial_order(tp, device), stage_centroids=True,
+                           device=device)
         if qp.dim() == 2:
-            q7 = prepare_cloud(qp, centroid=cen, device=device)
-        else:
+            q7 = prepare_cloud(qp, centroid=cen, perm=spatial_order(qp, device), device=device)
+        else:  # a batch of query clouds against one target: stored unordered
             q7 = SoaCloud(torch.cat([prepare_cloud(qp[k], centroid=cen, device=device).data
                                      for k in range(qp.shape[0])]), qp.shape[1], cen)
         res = nearest_neighbors_soa(q7, t7, return_index)
@@ -351,8 +387,10 @@ def chamfer_distance(a, b, device=None) -> torch.Tensor:
     if pa.shape[0] == 0 or pb.shape[0] == 0:
         raise ValueError("chamfer_distance: empty cloud")
     cen = centroid_of(pb, device)
-    A = prepare_cloud(pa, centroid=cen, device=device)
-    B = prepare_cloud(pb, centroid=cen, device=device)
+    A = prepare_cloud(pa, centroid=cen, perm=spatial_order(pa, device), stage_centroids=True,
+                      device=device)
+    B = prepare_cloud(pb, centroid=cen, perm=spatial_order(pb, device), stage_centroids=True,
+                      device=device)
     ab = _mean_sqrt(nearest_neighbors_soa(A, B, return_index=False).d2)
     ba = _mean_sqrt(nearest_neighbors_soa(B, A, return_index=False).d2)
     return ((ab + ba) / 2)[0]
@@ -482,7 +520,11 @@ class IcpProblem:
         st["T"] = inits.reshape(self.starts, 16)
         self.states = torch.from_numpy(st.view(np.uint8).reshape(self.starts, -1).copy()).to(self.device)
         self.centroid = centroid_of(self.tgt, self.device)
-        self.tgt_soa = prepare_cloud(self.tgt, centroid=self.centroid, device=self.device)
+        self.tgt_soa = prepare_cloud(self.tgt, centroid=self.centroid,
+                                     perm=spatial_order(self.tgt, self.device), stage_centroids=True,
+                                     device=self.device)
+        self.tgt_desc = self.tgt_soa.descriptor(batched=False)
+        self.src_perm = spatial_order(self.src, self.device) if self.src.shape[0] > 0 else None
         lib = _lib.load()
         ns1 = max(self.ns, 1)
         self.ws = _workspace(lib.isr_icp_workspace_bytes(ns1, self.nt, self.starts), self.device)
@@ -496,8 +538,8 @@ class IcpProblem:
             self.sums.zero_()
             return self.sums
         _lib.check(_lib.load().isr_icp_accumulate(
-            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), self.ns, _ptr(self.tgt),
-            _ptr(self.tgt_soa.data), _ptr(self.centroid), self.nt, self.tgt_soa.npad, float(max_dist),
+            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), _ptr(self.src_perm),
+            self.ns, _ptr(self.tgt), ctypes.byref(self.tgt_desc), _ptr(self.centroid), float(max_dist),
             _ptr(self.sums), _ptr(self.corr_idx), _ptr(self.inlier), _ptr(self.ws), self.ws.numel(),
             _stream()))
         return self.sums
@@ -516,8 +558,8 @@ class IcpProblem:
                 self.solve(0, rel_fitness, rel_rmse, k == max_iteration)
             return
         _lib.check(_lib.load().isr_icp_run(
-            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), self.ns, _ptr(self.tgt),
-            _ptr(self.tgt_soa.data), _ptr(self.centroid), self.nt, self.tgt_soa.npad, float(max_dist),
+            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), _ptr(self.src_perm),
+            self.ns, _ptr(self.tgt), ctypes.byref(self.tgt_desc), _ptr(self.centroid), float(max_dist),
             int(max_iteration),
             float(rel_fitness), float(rel_rmse), _ptr(self.sums), _ptr(self.corr_idx),
             _ptr(self.inlier), _ptr(self.ws), self.ws.numel(), _stream()))

@@ -22,12 +22,16 @@ class KDTree:
             raise ValueError("X must be [N, 3]")
         self.data = self._pts
         self._cen = api.centroid_of(self._pts, self._dev)
-        self._soa = api.prepare_cloud(self._pts, centroid=self._cen, device=self._dev)
+        self._soa = api.prepare_cloud(self._pts, centroid=self._cen,
+                                      perm=api.spatial_order(self._pts, self._dev), stage_centroids=True,
+                                      device=self._dev)
 
     def query(self, X, k=1, return_distance=True):
         if k != 1:
             raise NotImplementedError("only k=1 is used by the reference (choosePose.py:22)")
-        q = api.prepare_cloud(api._points(X, self._dev), centroid=self._cen, device=self._dev)
+        qp = api._points(X, self._dev)
+        q = api.prepare_cloud(qp, centroid=self._cen, perm=api.spatial_order(qp, self._dev),
+                              device=self._dev)
         res = api.nearest_neighbors_soa(q, self._soa, return_index=True)
         idx = res.idx[0].to("cpu").numpy().astype(np.int64).reshape(-1, 1)
         if not return_distance:

@@ -297,15 +297,19 @@ size_t isr_icp_workspace_bytes(int64_t ns, int64_t nt, int64_t starts) {
 }
 
 int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
-                       int64_t ns, const float *tgt, const float *tgt_soa7, const double *centroid, int64_t nt,
-                       int64_t nt_pad, double max_dist, double *sums, int32_t *corr_idx,
-                       uint8_t *inlier, void *workspace, size_t workspace_bytes, void *stream) {
+                       const int32_t *src_perm, int64_t ns, const float *tgt,
+                       const IsrCloud *tgt_cloud, const double *centroid, double max_dist,
+                       double *sums, int32_t *corr_idx, uint8_t *inlier, void *workspace,
+                       size_t workspace_bytes, void *stream) {
     using namespace isr;
+    ISR_REQUIRE(tgt_cloud != nullptr, ISR_E_INVALID_ARG, "icp: null target descriptor");
+    const int64_t nt = tgt_cloud->n;
     ISR_REQUIRE(starts >= 1 && ns >= 1 && nt >= 1, ISR_E_SHAPE,
                 "icp: need starts, ns, nt >= 1 (starts=%lld ns=%lld nt=%lld)", (long long)starts,
                 (long long)ns, (long long)nt);
-    ISR_REQUIRE(states && src && tgt && tgt_soa7 && centroid && sums && corr_idx, ISR_E_INVALID_ARG,
-                "icp: null pointer");
+    ISR_REQUIRE(states && src && tgt && tgt_cloud->soa7 && centroid && sums && corr_idx,
+                ISR_E_INVALID_ARG, "icp: null pointer");
+    ISR_REQUIRE(tgt_cloud->bstride == 0, ISR_E_SHAPE, "icp: the target cloud is shared by all starts");
     ISR_REQUIRE(starts <= 65535, ISR_E_SHAPE, "icp: starts %lld > 65535", (long long)starts);
     IcpLayout L = icp_layout(ns, nt, starts);
     ISR_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, ISR_E_WORKSPACE,
@@ -326,10 +330,11 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, co
         return check_cuda(cudaMemsetAsync(sums, 0, (size_t)starts * kNS * 8, st), "icp memset");
     }
     // source: FP64 pose from the device state, centred on the target's centroid, hi/lo planes
-    ISR_TRY(isr_prepare_cloud(src, src_lo, ns, &states[0].T[0], kStateDoubles, nullptr, 0, centroid, starts,
-                              xs, nsp, done, kStateInts, stream));
-    ISR_TRY(isr_nn2(xs, ns, nsp, 7 * nsp, tgt_soa7, nt, nt_pad, 0, starts, 1, d2, corr_idx, done,
-                    kStateInts, ws + L.nnws, L.total - L.nnws, stream));
+    ISR_TRY(isr_prepare_cloud(src, src_lo, src_perm, ns, &states[0].T[0], kStateDoubles, nullptr, 0,
+                              centroid, starts, xs, nsp, done, kStateInts, stream));
+    const IsrCloud src_cloud{xs, ns, nsp, 7 * nsp, nullptr, src_perm};
+    ISR_TRY(isr_nn2(&src_cloud, tgt_cloud, starts, 1, d2, corr_idx, done, kStateInts, ws + L.nnws,
+                    L.total - L.nnws, stream));
     ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
     const int nblk = acc_blocks(ns, starts);
     dim3 grid((unsigned)nblk, (unsigned)starts);
@@ -350,16 +355,15 @@ int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64
     return launched("icp_solve_kernel");
 }
 
-int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo, int64_t ns,
-                const float *tgt,
-                const float *tgt_soa7, const double *centroid, int64_t nt, int64_t nt_pad,
-                double max_dist, int max_iteration, double rel_fitness, double rel_rmse, double *sums,
-                int32_t *corr_idx, uint8_t *inlier, void *workspace, size_t workspace_bytes,
-                void *stream) {
+int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                const int32_t *src_perm, int64_t ns, const float *tgt, const IsrCloud *tgt_cloud,
+                const double *centroid, double max_dist, int max_iteration, double rel_fitness,
+                double rel_rmse, double *sums, int32_t *corr_idx, uint8_t *inlier, void *workspace,
+                size_t workspace_bytes, void *stream) {
     using namespace isr;
     ISR_REQUIRE(max_iteration >= 0, ISR_E_INVALID_ARG, "icp_run: max_iteration < 0");
     for (int k = 0; k <= max_iteration; ++k) {
-        ISR_TRY(isr_icp_accumulate(states, starts, src, src_lo, ns, tgt, tgt_soa7, centroid, nt, nt_pad,
+        ISR_TRY(isr_icp_accumulate(states, starts, src, src_lo, src_perm, ns, tgt, tgt_cloud, centroid,
                                    max_dist, sums, corr_idx, inlier, workspace, workspace_bytes,
                                    stream));
         ISR_TRY(isr_icp_solve(states, starts, sums, ns, rel_fitness, rel_rmse,

@@ -41,6 +41,7 @@ struct NN2Params {
     const float *t;          // SoA7 [batch][7][nt_pad]
     long long t_bstride;
     int nt_pad;
+    int nt;
     float *out_d2;
     int *out_idx;
     double *part_D;          // [splits][batch*nq] when the target range is split
@@ -52,6 +53,11 @@ struct NN2Params {
     int stages_per_split;
     int use_lo;
     int debug_no_resolve;  // tuning only: never flag (pure filter-scan rate)
+    const float4 *stage_c;   // [batch][stages_total] target stage centroids, or NULL
+    long long stage_c_bstride;
+    const int *perm_q;       // stored position -> original index (NULL = identity)
+    const int *perm_t;
+    unsigned long long *dbg;  // tuning only: event counters
 };
 
 // Upper threshold for "could still be the nearest neighbour": running minimum + window.
@@ -89,19 +95,6 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
     }
     __syncthreads();
 
-    auto issue = [&](int sl) {
-        const int slot = sl % NSTAGES;
-        float *dst = sbuf + (size_t)slot * 4 * STAGE;
-        const float *src = gt + (long long)(s_begin + sl) * STAGE;
-        mbar_expect_tx(&full[slot], 4u * STAGE * 4u);
-#pragma unroll
-        for (int pl = 0; pl < 4; ++pl)
-            bulk_g2s(dst + pl * STAGE, src + (long long)pl * p.nt_pad, STAGE * 4u, &full[slot]);
-    };
-    if (tid == 0) {
-        for (int i = 0; i < NSTAGES - 1 && i < nst; ++i) issue(i);
-    }
-
     // Scan state, in registers: -2 * query (hi part) and the flag threshold.
     float q2x[Q], q2y[Q], q2z[Q], thr[Q];
     // Resolve state, touched only on the rare path and indexed at run time there, which
@@ -116,14 +109,88 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
         q2x[r] = -2.0f * gq[i];
         q2y[r] = -2.0f * gq[p.nq_pad + i];
         q2z[r] = -2.0f * gq[2ll * p.nq_pad + i];
-        thr[r] = p.debug_no_resolve ? -CUDART_INF_F : CUDART_INF_F;
+        // padded query slots (i >= nq) must never reach the resolve path: their 1e18
+        // coordinates would put every target inside the error window
+        const bool live = (q0 + r * THREADS + tid < p.nq) && !p.debug_no_resolve;
+        thr[r] = live ? CUDART_INF_F : -CUDART_INF_F;
     }
     for (int r = 0; r < Q; ++r) {  // run-time loop on purpose
         mt_l[r] = CUDART_INF_F;
-        thr_l[r] = CUDART_INF_F;
+        thr_l[r] = (q0 + r * THREADS + tid < p.nq) && !p.debug_no_resolve ? CUDART_INF_F : -CUDART_INF_F;
         Dbest_l[r] = CUDART_INF;
         ibest_l[r] = s_begin * STAGE;
     }
+
+    // Scan order: the target stage whose centroid is nearest to this CTA's query block goes
+    // first (clouds are stored in Morton order, so both are compact patches).  After that
+    // one stage every query already holds a near-final bound and the remaining stages
+    // almost never reach the resolve path.  The rest follows in ascending order.
+    int s_first = 0;
+    if (p.stage_c != nullptr && nst > 1) {
+        __shared__ float cred[4][THREADS / 32];
+        __shared__ u64 sred[THREADS / 32];
+        float cx = 0.f, cy = 0.f, cz = 0.f, cn = 0.f;
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            if (q0 + r * THREADS + tid < p.nq) {
+                cx += q2x[r]; cy += q2y[r]; cz += q2z[r]; cn += 1.f;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cx += __shfl_xor_sync(0xffffffffu, cx, o);
+            cy += __shfl_xor_sync(0xffffffffu, cy, o);
+            cz += __shfl_xor_sync(0xffffffffu, cz, o);
+            cn += __shfl_xor_sync(0xffffffffu, cn, o);
+        }
+        if ((tid & 31) == 0) {
+            cred[0][tid >> 5] = cx; cred[1][tid >> 5] = cy; cred[2][tid >> 5] = cz; cred[3][tid >> 5] = cn;
+        }
+        __syncthreads();
+        cx = cy = cz = cn = 0.f;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) {
+            cx += cred[0][w]; cy += cred[1][w]; cz += cred[2][w]; cn += cred[3][w];
+        }
+        const float inv = cn > 0.f ? -0.5f / cn : 0.f;  // q2 = -2 * query
+        cx *= inv; cy *= inv; cz *= inv;
+        const float4 *sc = p.stage_c + (long long)b * p.stage_c_bstride + s_begin;
+        u64 best = ~0ull;
+        for (int s = tid; s < nst; s += THREADS) {
+            const float4 c = sc[s];
+            const float dx = c.x - cx, dy = c.y - cy, dz = c.z - cz;
+            const float d = dx * dx + dy * dy + dz * dz;
+            const u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(unsigned)s;
+            best = key < best ? key : best;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const u64 other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
+        }
+        if ((tid & 31) == 0) sred[tid >> 5] = best;
+        __syncthreads();
+        best = sred[0];
+#pragma unroll
+        for (int w = 1; w < THREADS / 32; ++w) best = sred[w] < best ? sred[w] : best;
+        s_first = (int)(unsigned)(best & 0xffffffffull);
+        if (s_first >= nst) s_first = 0;
+    }
+    auto stage_of = [&](int pos) { return pos == 0 ? s_first : (pos - 1 < s_first ? pos - 1 : pos); };
+
+    auto issue = [&](int sl) {
+        const int slot = sl % NSTAGES;
+        float *dst = sbuf + (size_t)slot * 4 * STAGE;
+        const float *src = gt + (long long)(s_begin + stage_of(sl)) * STAGE;
+        mbar_expect_tx(&full[slot], 4u * STAGE * 4u);
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl)
+            bulk_g2s(dst + pl * STAGE, src + (long long)pl * p.nt_pad, STAGE * 4u, &full[slot]);
+    };
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGES - 1 && i < nst; ++i) issue(i);
+    }
+
 
     for (int sl = 0; sl < nst; ++sl) {
         if (tid == 0 && sl + NSTAGES - 1 < nst) issue(sl + NSTAGES - 1);
@@ -180,6 +247,13 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
 #pragma unroll
             for (int r = 0; r < Q; ++r) flags |= (tm[r] <= thr[r]) ? (1u << r) : 0u;
             if (flags != 0) {
+#ifdef ISR_NN_TUNING
+                if (p.dbg != nullptr) {
+                    const unsigned am = __activemask();
+                    if ((int)(__ffs(am) - 1) == (tid & 31)) atomicAdd(p.dbg + 0, 1ull);  // warp-level flagged sub-tiles
+                    atomicAdd(p.dbg + 1, (unsigned long long)__popc(flags));            // (query, sub-tile) events
+                }
+#endif
                 // ---- resolve: rare, divergent; one pass serves every flagged lane ----------
 #pragma unroll
                 for (int r = 0; r < Q; ++r) tm_l[r] = tm[r];
@@ -187,9 +261,15 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
                 const float *fy = reinterpret_cast<const float *>(sy) + sub * SUB;
                 const float *fz = reinterpret_cast<const float *>(sz) + sub * SUB;
                 const float *fn = reinterpret_cast<const float *>(sn) + sub * SUB;
-                const int gbase = (s_begin + sl) * STAGE + sub * SUB;
+                const int gbase = (s_begin + stage_of(sl)) * STAGE + sub * SUB;
                 for (unsigned f = flags; f != 0; f &= f - 1) {
                     const int r = __ffs(f) - 1;
+#ifdef ISR_NN_TUNING
+                    if (p.dbg != nullptr) {
+                        const unsigned am = __activemask();
+                        if ((int)(__ffs(am) - 1) == (tid & 31)) atomicAdd(p.dbg + 2, 1ull);  // warp-level resolve passes
+                    }
+#endif
                     const int qi = min(q0 + r * THREADS + tid, p.nq_pad - 1);
                     const float qhx = gq[qi], qhy = gq[p.nq_pad + qi], qhz = gq[2ll * p.nq_pad + qi];
                     const float cx = -2.0f * qhx, cy = -2.0f * qhy, cz = -2.0f * qhz;
@@ -211,6 +291,9 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
                         const float px = fx[j], py = fy[j], pz = fz[j];
                         const float a = __fmaf_rn(cx, px, __fmaf_rn(cy, py, __fmaf_rn(cz, pz, fn[j])));
                         if (a <= th) {
+#ifdef ISR_NN_TUNING
+                            if (p.dbg != nullptr) atomicAdd(p.dbg + 3, 1ull);  // exact evaluations
+#endif
                             double dx = (double)qhx - (double)px, dy = (double)qhy - (double)py,
                                    dz = (double)qhz - (double)pz;
                             if (p.use_lo) {
@@ -220,7 +303,16 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
                                 dz += qlz - (double)gt[6ll * p.nt_pad + gj];
                             }
                             const double D = fma(dz, dz, fma(dy, dy, dx * dx));
-                            if (D < Db) {
+                            // strict minimum; on an exact tie the lower ORIGINAL index wins
+                            // (stages are not visited in index order and storage is permuted)
+                            bool take = D < Db;
+                            if (D == Db) {
+                                const int cand = gbase + j;
+                                const int oc = p.perm_t != nullptr ? p.perm_t[min(cand, p.nt - 1)] : cand;
+                                const int ob = p.perm_t != nullptr ? p.perm_t[min(ib, p.nt - 1)] : ib;
+                                take = oc < ob;
+                            }
+                            if (take) {
                                 Db = D;
                                 ib = gbase + j;
                             }
@@ -239,19 +331,22 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
     for (int r = 0; r < Q; ++r) {
         const int i = q0 + r * THREADS + tid;
         if (i < p.nq) {
-            const long long o = (long long)b * p.nq + i;
+            // report in the caller's original indexing
+            const int io = p.perm_q != nullptr ? p.perm_q[i] : i;
+            const int jo = p.perm_t != nullptr ? p.perm_t[min(ibest_l[r], p.nt - 1)] : ibest_l[r];
+            const long long o = (long long)b * p.nq + io;
             if (p.part_D != nullptr) {
                 p.part_D[(long long)blockIdx.y * p.part_stride + o] = Dbest_l[r];
-                p.part_idx[(long long)blockIdx.y * p.part_stride + o] = ibest_l[r];
+                p.part_idx[(long long)blockIdx.y * p.part_stride + o] = jo;
             } else {
                 p.out_d2[o] = (float)Dbest_l[r];
-                if (p.out_idx != nullptr) p.out_idx[o] = ibest_l[r];
+                if (p.out_idx != nullptr) p.out_idx[o] = jo;
             }
         }
     }
 }
 
-// splits ascend over the target range, so the first strict minimum is the lowest index
+// partial results carry original indices; exact ties go to the lower one
 __global__ void nn2_combine_kernel(const double *__restrict__ part_D, const int *__restrict__ part_idx,
                                    long long total, int splits, float *__restrict__ out_d2,
                                    int *__restrict__ out_idx, const int *__restrict__ skip,
@@ -263,9 +358,10 @@ __global__ void nn2_combine_kernel(const double *__restrict__ part_D, const int 
     int bi = part_idx[i];
     for (int s = 1; s < splits; ++s) {
         const double d = part_D[(long long)s * total + i];
-        if (d < best) {
+        const int di = part_idx[(long long)s * total + i];
+        if (d < best || (d == best && di < bi)) {
             best = d;
-            bi = part_idx[(long long)s * total + i];
+            bi = di;
         }
     }
     out_d2[i] = (float)best;
@@ -323,8 +419,8 @@ static int choose_splits(long long ctas, int stages, int slots) {
 }
 
 struct NN2Call {
-    const float *q; int64_t nq, nq_pad, q_bstride;
-    const float *t; int64_t nt, nt_pad, t_bstride;
+    const IsrCloud *q;
+    const IsrCloud *t;
     int64_t batch;
     int use_lo;
     float *out_d2; int32_t *out_idx;
@@ -335,8 +431,9 @@ struct NN2Call {
 
 template <class V>
 static int nn2_dispatch(const NN2Call &c) {
-    const int nqb = (int)((c.nq + V::kQueriesPerCta - 1) / V::kQueriesPerCta);
-    const int stages = (int)(c.nt_pad / V::kStage);
+    const int64_t nq = c.q->n;
+    const int nqb = (int)((nq + V::kQueriesPerCta - 1) / V::kQueriesPerCta);
+    const int stages = (int)(c.t->npad / V::kStage);
     static thread_local int slots = 0;
     if (slots == 0) slots = sm_count() * V::ctas_per_sm();
     int splits = choose_splits((long long)nqb * c.batch, stages, slots);
@@ -344,9 +441,31 @@ static int nn2_dispatch(const NN2Call &c) {
     splits = (stages + per - 1) / per;  // no empty split
 
     NN2Params p;
-    p.q = c.q; p.q_bstride = c.q_bstride; p.nq = (int)c.nq; p.nq_pad = (int)c.nq_pad;
-    p.t = c.t; p.t_bstride = c.t_bstride; p.nt_pad = (int)c.nt_pad;
+    p.q = c.q->soa7; p.q_bstride = c.q->bstride; p.nq = (int)nq; p.nq_pad = (int)c.q->npad;
+    p.t = c.t->soa7; p.t_bstride = c.t->bstride; p.nt_pad = (int)c.t->npad; p.nt = (int)c.t->n;
     p.out_d2 = c.out_d2; p.out_idx = c.out_idx;
+    // stage centroids are laid out per 1024-point SoA tile; only usable when the kernel's
+    // stage is that tile
+    p.stage_c = (V::kStage == ISR_SOA_TILE) ? reinterpret_cast<const float4 *>(c.t->stage_c) : nullptr;
+    p.stage_c_bstride = c.t->bstride == 0 ? 0 : c.t->npad / ISR_SOA_TILE;
+    p.perm_q = c.q->perm; p.perm_t = c.t->perm;
+    p.dbg = nullptr;
+#ifdef ISR_NN_TUNING
+    {
+        static unsigned long long *dbg = nullptr;
+        const char *e = getenv("ISR_NN2_DEBUG");
+        if (e && atoi(e)) {
+            if (dbg == nullptr) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
+            else {
+                unsigned long long h[4];
+                cudaMemcpy(h, dbg, 32, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[nn2 dbg, previous launch] warp-flagged-subtiles=%llu query-events=%llu warp-resolve-passes=%llu exact-evals=%llu\n", h[0], h[1], h[2], h[3]);
+                cudaMemset(dbg, 0, 64);
+            }
+            p.dbg = dbg;
+        }
+    }
+#endif
     p.part_D = nullptr; p.part_idx = nullptr; p.part_stride = 0;
     p.skip = c.skip; p.skip_stride = c.skip_stride;
     p.stages_total = stages; p.stages_per_split = per;
@@ -359,7 +478,7 @@ static int nn2_dispatch(const NN2Call &c) {
     dim3 grid((unsigned)nqb, (unsigned)splits, (unsigned)c.batch);
     if (splits == 1) return V::launch(p, grid, c.st);
 
-    const long long total = (long long)c.nq * c.batch;
+    const long long total = (long long)nq * c.batch;
     const size_t need = align256((size_t)total * splits * 8) + (size_t)total * splits * 4;
     ISR_REQUIRE(c.workspace != nullptr && c.workspace_bytes >= need, ISR_E_WORKSPACE,
                 "nn: workspace %zu < %zu bytes", c.workspace_bytes, need);
@@ -370,7 +489,7 @@ static int nn2_dispatch(const NN2Call &c) {
     ISR_TRY(V::launch(p, grid, c.st));
     nn2_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.st>>>(
         p.part_D, p.part_idx, total, splits, c.out_d2, c.out_idx, c.skip, c.skip_stride,
-        (long long)c.nq);
+        (long long)nq);
     return launched("nn2_combine_kernel");
 }
 
@@ -404,27 +523,28 @@ size_t isr_nn2_workspace_bytes(int64_t nq, int64_t nt, int64_t batch) {
     return align256(total * splits * 8) + align256(total * splits * 4);
 }
 
-int isr_nn2(const float *q_soa7, int64_t nq, int64_t nq_pad, int64_t q_bstride, const float *t_soa7,
-            int64_t nt, int64_t nt_pad, int64_t t_bstride, int64_t batch, int use_lo, float *out_d2,
+int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, float *out_d2,
             int32_t *out_idx, const int32_t *skip, int64_t skip_stride, void *workspace,
             size_t workspace_bytes, void *stream) {
     using namespace isr;
-    ISR_REQUIRE(nq >= 0 && nt >= 1 && batch >= 0, ISR_E_SHAPE,
+    ISR_REQUIRE(q != nullptr && t != nullptr, ISR_E_INVALID_ARG, "nn: null cloud descriptor");
+    ISR_REQUIRE(q->n >= 0 && t->n >= 1 && batch >= 0, ISR_E_SHAPE,
                 "nn: need nq >= 0, nt >= 1, batch >= 0 (nq=%lld nt=%lld batch=%lld)",
-                (long long)nq, (long long)nt, (long long)batch);
-    if (nq == 0 || batch == 0) return ISR_OK;
-    ISR_REQUIRE(q_soa7 && t_soa7 && out_d2, ISR_E_INVALID_ARG, "nn: null pointer");
-    ISR_REQUIRE(nq_pad >= nq && nq_pad % ISR_SOA_TILE == 0 && nt_pad >= nt &&
-                    nt_pad % ISR_SOA_TILE == 0,
+                (long long)q->n, (long long)t->n, (long long)batch);
+    if (q->n == 0 || batch == 0) return ISR_OK;
+    ISR_REQUIRE(q->soa7 && t->soa7 && out_d2, ISR_E_INVALID_ARG, "nn: null pointer");
+    ISR_REQUIRE(q->npad >= q->n && q->npad % ISR_SOA_TILE == 0 && t->npad >= t->n &&
+                    t->npad % ISR_SOA_TILE == 0,
                 ISR_E_SHAPE, "nn: padded lengths must be multiples of %d covering n", ISR_SOA_TILE);
-    ISR_REQUIRE(nq_pad < (1ll << 31) - 2048 && nt_pad < (1ll << 31) - 2048, ISR_E_SHAPE,
+    ISR_REQUIRE(q->npad < (1ll << 31) - 2048 && t->npad < (1ll << 31) - 2048, ISR_E_SHAPE,
                 "nn: clouds beyond int32 indexing");
     ISR_REQUIRE(batch <= 65535, ISR_E_SHAPE, "nn: batch %lld > 65535", (long long)batch);
-    ISR_REQUIRE(aligned16(t_soa7) && (t_bstride % 4 == 0), ISR_E_ALIGN,
+    ISR_REQUIRE(aligned16(t->soa7) && (t->bstride % 4 == 0), ISR_E_ALIGN,
                 "nn: target planes must be 16-byte aligned");
-    const NN2Call c{q_soa7, nq, nq_pad, q_bstride, t_soa7, nt, nt_pad, t_bstride, batch, use_lo,
-                    out_d2, out_idx, skip, skip_stride, workspace, workspace_bytes,
-                    (cudaStream_t)stream};
+    ISR_REQUIRE(t->stage_c == nullptr || aligned16(t->stage_c), ISR_E_ALIGN,
+                "nn: stage centroids must be 16-byte aligned");
+    const NN2Call c{q, t, batch, use_lo, out_d2, out_idx, skip, skip_stride, workspace,
+                    workspace_bytes, (cudaStream_t)stream};
 #ifdef ISR_NN_TUNING
     static int variant = -1;
     if (variant < 0) {

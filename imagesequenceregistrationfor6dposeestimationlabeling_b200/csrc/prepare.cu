@@ -48,8 +48,8 @@ centroid_kernel(const float *__restrict__ pts, int64_t n, double *__restrict__ o
 
 // grid: (npad / 256, b)
 __global__ void __launch_bounds__(kPrepThreads)
-prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts_lo, int64_t n,
-                    const double *__restrict__ poses,
+prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts_lo,
+                    const int32_t *__restrict__ perm, int64_t n, const double *__restrict__ poses,
                     int64_t pose_stride, const double *__restrict__ centre_poses,
                     int64_t centre_pose_stride, const double *__restrict__ centroid,
                     float *__restrict__ out, int64_t npad, const int32_t *__restrict__ skip,
@@ -60,8 +60,13 @@ prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts
     const int64_t p0 = (int64_t)blockIdx.x * kPrepThreads;
     const int cnt = (int)max((int64_t)0, min((int64_t)kPrepThreads, n - p0));
     const int tid = threadIdx.x;
-    const float *src = pts + p0 * 3;
-    for (int k = tid; k < cnt * 3; k += kPrepThreads) stage[k] = src[k];
+    if (perm == nullptr) {
+        const float *src = pts + p0 * 3;
+        for (int k = tid; k < cnt * 3; k += kPrepThreads) stage[k] = src[k];
+    } else if (tid < cnt) {  // stored position p0+tid holds original point perm[p0+tid]
+        const float *src = pts + (int64_t)perm[p0 + tid] * 3;
+        stage[tid * 3] = src[0]; stage[tid * 3 + 1] = src[1]; stage[tid * 3 + 2] = src[2];
+    }
     __syncthreads();
 
     float hx = ISR_PAD_COORD, hy = ISR_PAD_COORD, hz = ISR_PAD_COORD;
@@ -81,7 +86,7 @@ prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts
         }
         double px = stage[tid * 3], py = stage[tid * 3 + 1], pz = stage[tid * 3 + 2];
         if (pts_lo != nullptr) {  // float64 input carried as a float32 hi/lo pair
-            const float *l = pts_lo + (p0 + tid) * 3;
+            const float *l = pts_lo + (perm != nullptr ? (int64_t)perm[p0 + tid] : p0 + tid) * 3;
             px += (double)l[0]; py += (double)l[1]; pz += (double)l[2];
         }
         double x = px, y = py, z = pz;
@@ -106,6 +111,41 @@ prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts
     o[6 * npad] = lz;
 }
 
+// centroid of the real points of every 1024-point SoA tile ("stage"): grid (stages, batch)
+__global__ void __launch_bounds__(256)
+stage_centroid_kernel(const float *__restrict__ soa7, int64_t n, int64_t npad, int64_t bstride,
+                      float4 *__restrict__ out) {
+    __shared__ float red[4][8];
+    const int s = blockIdx.x, b = blockIdx.y;
+    const float *base = soa7 + (int64_t)b * bstride + (int64_t)s * ISR_SOA_TILE;
+    float cx = 0.f, cy = 0.f, cz = 0.f, cn = 0.f;
+    for (int k = threadIdx.x; k < ISR_SOA_TILE; k += 256) {
+        if ((int64_t)s * ISR_SOA_TILE + k < n) {
+            cx += base[k]; cy += base[npad + k]; cz += base[2 * npad + k]; cn += 1.f;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cx += __shfl_xor_sync(0xffffffffu, cx, o);
+        cy += __shfl_xor_sync(0xffffffffu, cy, o);
+        cz += __shfl_xor_sync(0xffffffffu, cz, o);
+        cn += __shfl_xor_sync(0xffffffffu, cn, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = cx; red[1][threadIdx.x >> 5] = cy;
+        red[2][threadIdx.x >> 5] = cz; red[3][threadIdx.x >> 5] = cn;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cx = cy = cz = cn = 0.f;
+        for (int w = 0; w < 8; ++w) { cx += red[0][w]; cy += red[1][w]; cz += red[2][w]; cn += red[3][w]; }
+        const float inv = cn > 0.f ? 1.f / cn : 0.f;
+        // an all-padding tile gets a far-away centroid so it is never chosen first
+        out[(int64_t)b * gridDim.x + s] = cn > 0.f ? make_float4(cx * inv, cy * inv, cz * inv, cn)
+                                                   : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    }
+}
+
 }  // namespace isr
 
 extern "C" {
@@ -119,8 +159,22 @@ int isr_centroid(const float *pts, int64_t n, double *out3, void *stream) {
     return launched("centroid_kernel");
 }
 
-int isr_prepare_cloud(const float *pts, const float *pts_lo, int64_t n, const double *poses,
-                      int64_t pose_stride,
+int isr_stage_centroids(const float *soa7, int64_t n, int64_t npad, int64_t bstride, int64_t batch,
+                        float *out, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(soa7 && out && n >= 0 && npad >= n && npad % ISR_SOA_TILE == 0 && npad > 0 && batch >= 1,
+                ISR_E_INVALID_ARG, "stage_centroids: bad argument");
+    ISR_REQUIRE(batch <= 65535, ISR_E_SHAPE, "stage_centroids: batch > 65535");
+    ISR_REQUIRE(aligned16(out), ISR_E_ALIGN, "stage_centroids: out not 16-byte aligned");
+    dim3 grid((unsigned)(npad / ISR_SOA_TILE), (unsigned)batch);
+    ProfScope prof(kProfTransform, (cudaStream_t)stream);
+    stage_centroid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(soa7, n, npad, bstride,
+                                                                   reinterpret_cast<float4 *>(out));
+    return launched("stage_centroid_kernel");
+}
+
+int isr_prepare_cloud(const float *pts, const float *pts_lo, const int32_t *perm, int64_t n,
+                      const double *poses, int64_t pose_stride,
                       const double *centre_poses, int64_t centre_pose_stride,
                       const double *centroid, int64_t b, float *out_soa7, int64_t npad,
                       const int32_t *skip, int64_t skip_stride, void *stream) {
@@ -137,8 +191,8 @@ int isr_prepare_cloud(const float *pts, const float *pts_lo, int64_t n, const do
     dim3 grid((unsigned)(npad / kPrepThreads), (unsigned)b);
     ProfScope prof(kProfTransform, (cudaStream_t)stream);
     prepare_soa7_kernel<<<grid, kPrepThreads, 0, (cudaStream_t)stream>>>(
-        pts, pts_lo, n, poses, pose_stride, centre_poses, centre_pose_stride, centroid, out_soa7, npad,
-        skip, skip_stride);
+        pts, pts_lo, perm, n, poses, pose_stride, centre_poses, centre_pose_stride, centroid, out_soa7,
+        npad, skip, skip_stride);
     return launched("prepare_soa7_kernel");
 }
 

@@ -79,7 +79,7 @@ static int verify_chunk(int64_t nq, int64_t nt, int64_t b) {
 }
 
 struct VerifyLayout {
-    size_t xs, ys, d2a, d2b, means, centroid, nnws, total;
+    size_t xs, ys, d2a, d2b, means, centroid, perm_q, perm_t, stage_x, stage_y, sortws, nnws, total;
     int chunk;
 };
 
@@ -106,6 +106,11 @@ static VerifyLayout verify_layout(int64_t nq, int64_t nt, int64_t b, int bidirec
     L.d2b = off;  off += bidirectional ? align256((size_t)L.chunk * nt * 4) : 0;
     L.means = off; off += align256((size_t)2 * L.chunk * 8);
     L.centroid = off; off += 256;
+    L.perm_q = off; off += align256((size_t)nq * 4);
+    L.perm_t = off; off += align256((size_t)nt * 4);
+    L.stage_x = off; off += align256((size_t)L.chunk * (nqp / ISR_SOA_TILE) * 16);
+    L.stage_y = off; off += align256((size_t)L.chunk * (ntp / ISR_SOA_TILE) * 16);
+    L.sortws = off; off += isr_spatial_order_workspace_bytes(big);
     const size_t w1 = isr_nn_workspace_bytes(big, big, L.chunk);
     const size_t w2 = isr_nn2_workspace_bytes(nq < nt ? nq : nt, big, L.chunk);
     L.nnws = off; off += w1 > w2 ? w1 : w2;
@@ -150,7 +155,20 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
 
     const bool direct = nn_mode_direct();
     double *centroid = reinterpret_cast<double *>(ws + L.centroid);
-    if (!direct) ISR_TRY(isr_centroid(cloud_t, nt, centroid, stream));
+    int32_t *perm_q = reinterpret_cast<int32_t *>(ws + L.perm_q);
+    int32_t *perm_t = reinterpret_cast<int32_t *>(ws + L.perm_t);
+    float *stage_x = reinterpret_cast<float *>(ws + L.stage_x);
+    float *stage_y = reinterpret_cast<float *>(ws + L.stage_y);
+    if (!direct) {
+        ISR_TRY(isr_centroid(cloud_t, nt, centroid, stream));
+        // Morton order once per cloud; every candidate's rigid copy inherits the coherence.
+        // The losses are means over all points, so nothing has to be permuted back.
+        ISR_TRY(isr_spatial_order(cloud_t, nt, perm_t, ws + L.sortws, L.nnws - L.sortws, stream));
+        if (cloud_q == cloud_t && nq == nt) perm_q = perm_t;
+        else ISR_TRY(isr_spatial_order(cloud_q, nq, perm_q, ws + L.sortws, L.nnws - L.sortws, stream));
+    }
+    const IsrCloud cx{xs, nq, nqp, 7 * nqp, stage_x, nullptr};
+    const IsrCloud cy{ys, nt, ntp, 7 * ntp, stage_y, nullptr};
     for (int64_t k0 = 0; k0 < b; k0 += L.chunk) {
         const int c = (int)((b - k0) < L.chunk ? (b - k0) : L.chunk);
         if (direct) {
@@ -162,12 +180,13 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
                                0, nnws, nnws_bytes, stream));
         } else {
             // both clouds of candidate k are centred on c_k = Pt_k . centroid(cloud_t)
-            ISR_TRY(isr_prepare_cloud(cloud_q, nullptr, nq, poses_q + k0 * 16, 16, poses_t + k0 * 16, 16,
-                                      centroid, c, xs, nqp, nullptr, 0, stream));
-            ISR_TRY(isr_prepare_cloud(cloud_t, nullptr, nt, poses_t + k0 * 16, 16, poses_t + k0 * 16, 16,
-                                      centroid, c, ys, ntp, nullptr, 0, stream));
-            ISR_TRY(isr_nn2(xs, nq, nqp, 7 * nqp, ys, nt, ntp, 7 * ntp, c, 0, d2a, nullptr, nullptr,
-                            0, nnws, nnws_bytes, stream));
+            ISR_TRY(isr_prepare_cloud(cloud_q, nullptr, perm_q, nq, poses_q + k0 * 16, 16,
+                                      poses_t + k0 * 16, 16, centroid, c, xs, nqp, nullptr, 0, stream));
+            ISR_TRY(isr_prepare_cloud(cloud_t, nullptr, perm_t, nt, poses_t + k0 * 16, 16,
+                                      poses_t + k0 * 16, 16, centroid, c, ys, ntp, nullptr, 0, stream));
+            ISR_TRY(isr_stage_centroids(xs, nq, nqp, 7 * nqp, c, stage_x, stream));
+            ISR_TRY(isr_stage_centroids(ys, nt, ntp, 7 * ntp, c, stage_y, stream));
+            ISR_TRY(isr_nn2(&cx, &cy, c, 0, d2a, nullptr, nullptr, 0, nnws, nnws_bytes, stream));
         }
         ISR_TRY(isr_mean_sqrt(d2a, nq, c, means, stream));
         if (bidirectional) {
@@ -175,8 +194,7 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
                 ISR_TRY(isr_nn_soa(ys, nt, ntp, 3 * ntp, xs, nq, nqp, 3 * nqp, c, d2b, nullptr,
                                    nullptr, 0, nnws, nnws_bytes, stream));
             else
-                ISR_TRY(isr_nn2(ys, nt, ntp, 7 * ntp, xs, nq, nqp, 7 * nqp, c, 0, d2b, nullptr,
-                                nullptr, 0, nnws, nnws_bytes, stream));
+                ISR_TRY(isr_nn2(&cy, &cx, c, 0, d2b, nullptr, nullptr, 0, nnws, nnws_bytes, stream));
             ISR_TRY(isr_mean_sqrt(d2b, nt, c, means + L.chunk, stream));
         }
         verify_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(means, means + L.chunk, valid, k0, c,

@@ -98,33 +98,56 @@ int isr_nn_soa(const float *q_soa, int64_t nq, int64_t nq_pad, int64_t q_bstride
                int64_t batch, float *out_d2, int32_t *out_idx, const int32_t *skip,
                int64_t skip_stride, void *workspace, size_t workspace_bytes, void *stream);
 
-/* ---- K1' + K2 (production): centred hi/lo planes and the filtered exact search --------- */
+/* ---- K1' + K2 (production): ordered, centred hi/lo planes and the filtered exact search -- */
 /* out3[0..2] = FP64 centroid of pts (single CTA, fixed summation order). */
 int isr_centroid(const float *pts, int64_t n, double *out3, void *stream);
+
+/* perm[i] = original index of the i-th point in Morton (Z-curve) order.  NeRF surface clouds
+ * arrive in farthest-point-sampling order (genFeat.py:199-202), i.e. spatially random; the
+ * scan kernel is fastest when consecutive stored points are neighbours.  Deterministic. */
+size_t isr_spatial_order_workspace_bytes(int64_t n);
+int isr_spatial_order(const float *pts, int64_t n, int32_t *perm, void *workspace,
+                      size_t workspace_bytes, void *stream);
 
 /* K1 with centring and FP64-accurate output, "SoA7" planes out[b][7][npad]:
  *   0-2 hi = float32(R_b p + t_b - c_b), 3 = fl32 |hi|^2, 4-6 lo = float32(exact - hi).
  * c_b = C_b . centroid (centre_poses NULL: c_b = centroid; centroid NULL: c_b = 0).
  * Both clouds of a pair must be prepared with the same c_b.  poses NULL = identity (b == 1).
  * pts_lo (float32 [n][3], may be NULL): low part of a float64 input cloud, p = pts + pts_lo
- * (icp.py:68 hands Open3D a float64 camera-frame source).
- * Strides are in doubles.  Replaces the same reference lines as isr_transform_points_soa. */
-int isr_prepare_cloud(const float *pts, const float *pts_lo, int64_t n, const double *poses,
-                      int64_t pose_stride,
-                      const double *centre_poses, int64_t centre_pose_stride,
-                      const double *centroid, int64_t b, float *out_soa7, int64_t npad,
-                      const int32_t *skip, int64_t skip_stride, void *stream);
+ * (icp.py:68 hands Open3D a float64 camera-frame source).  perm (may be NULL): stored
+ * position i holds original point perm[i].  Strides are in doubles.
+ * Replaces the same reference lines as isr_transform_points_soa. */
+int isr_prepare_cloud(const float *pts, const float *pts_lo, const int32_t *perm, int64_t n,
+                      const double *poses, int64_t pose_stride, const double *centre_poses,
+                      int64_t centre_pose_stride, const double *centroid, int64_t b,
+                      float *out_soa7, int64_t npad, const int32_t *skip, int64_t skip_stride,
+                      void *stream);
 
-/* Brute-force exact 1-NN on SoA7 clouds: FP32 3-FMA filter over every pair, FP64 resolve of
- * the few targets inside the proven error window (nn2.cu).  out_idx equals the float64
- * brute-force argmin of the prepared coordinates (lowest index on exact ties); out_d2 is
- * that FP64 squared distance rounded to float32.  use_lo == 0 ignores the lo planes
- * (distances between the float32 hi coordinates).  Same reference call sites as isr_nn_soa. */
+/* out[b][npad/1024][4] = (x, y, z, count) centroid of every 1024-point tile of a SoA7 cloud. */
+int isr_stage_centroids(const float *soa7, int64_t n, int64_t npad, int64_t bstride,
+                        int64_t batch, float *out, void *stream);
+
+/* A prepared cloud (or batch of clouds) as the search kernel sees it. */
+typedef struct IsrCloud {
+    const float *soa7;    /* [batch][7][npad] from isr_prepare_cloud                          */
+    int64_t n;            /* real points                                                      */
+    int64_t npad;         /* padded plane length (multiple of ISR_SOA_TILE)                   */
+    int64_t bstride;      /* floats between batch items; 0 = one cloud shared by the batch    */
+    const float *stage_c; /* isr_stage_centroids output, or NULL (scan in storage order)      */
+    const int32_t *perm;  /* the perm it was prepared with, or NULL; results are reported in
+                             original indices either way                                      */
+} IsrCloud;
+
+/* Brute-force exact 1-NN of every query in its target: FP32 3-FMA filter over every pair,
+ * FP64 resolve of the few targets inside the proven error window (nn2.cu).  out_idx
+ * [batch][nq] equals the float64 brute-force argmin of the prepared coordinates (lowest
+ * original index on exact ties); out_d2 is that FP64 squared distance rounded to float32.
+ * use_lo == 0 ignores the lo planes (distances between the float32 hi coordinates).
+ * Same reference call sites as isr_nn_soa. */
 size_t isr_nn2_workspace_bytes(int64_t nq, int64_t nt, int64_t batch);
-int isr_nn2(const float *q_soa7, int64_t nq, int64_t nq_pad, int64_t q_bstride,
-            const float *t_soa7, int64_t nt, int64_t nt_pad, int64_t t_bstride, int64_t batch,
-            int use_lo, float *out_d2, int32_t *out_idx, const int32_t *skip, int64_t skip_stride,
-            void *workspace, size_t workspace_bytes, void *stream);
+int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, float *out_d2,
+            int32_t *out_idx, const int32_t *skip, int64_t skip_stride, void *workspace,
+            size_t workspace_bytes, void *stream);
 
 /* out_mean[b] = mean_i sqrt(d2[b][i]) in FP64, fixed summation order (deterministic).
  * np.mean(np.asarray(compute_point_cloud_distance(..))) -- verfication.py:98,100. */
@@ -165,15 +188,16 @@ typedef struct IsrIcpState {
  * target, and reduce the 17 FP64 sums over correspondences with d2 < max_dist^2 (strict)
  * into sums[starts][17].  corr_idx int32 [starts][ns] receives the NN index of every
  * source point, inlier uint8 [starts][ns] its correspondence flag.  States whose `done`
- * is set are skipped.  tgt_soa7 = isr_prepare_cloud(tgt, identity, centroid) and `centroid`
- * (device double[3], normally isr_centroid(tgt)) are prepared once per target.  src_lo (may
- * be NULL) is the float32 low part of a float64 source, as in isr_prepare_cloud.  This is GetRegistrationResultAndCorrespondences of Open3D's
+ * is set are skipped.  Prepared once per problem: `centroid` (device double[3], normally
+ * isr_centroid(tgt)), tgt_cloud = the target through isr_spatial_order / isr_prepare_cloud
+ * (identity pose, that centroid) / isr_stage_centroids, src_perm = isr_spatial_order(src)
+ * (may be NULL).  src_lo (may be NULL) is the float32 low part of a float64 source.  This is GetRegistrationResultAndCorrespondences of Open3D's
  * RegistrationICP (icp.py:97-103, upstream). */
 size_t isr_icp_workspace_bytes(int64_t ns, int64_t nt, int64_t starts);
 int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src,
-                       const float *src_lo, int64_t ns, const float *tgt, const float *tgt_soa7, const double *centroid,
-                       int64_t nt, int64_t nt_pad, double max_dist, double *sums,
-                       int32_t *corr_idx, uint8_t *inlier, void *workspace,
+                       const float *src_lo, const int32_t *src_perm, int64_t ns, const float *tgt,
+                       const IsrCloud *tgt_cloud, const double *centroid, double max_dist,
+                       double *sums, int32_t *corr_idx, uint8_t *inlier, void *workspace,
                        size_t workspace_bytes, void *stream);
 
 /* Consume sums[starts][17] (already reduced over all source shards): set fitness / rmse
@@ -189,8 +213,8 @@ int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64
  * o3d.pipelines.registration.registration_icp, icp.py:101-103; with max_iteration == 0
  * it is evaluate_registration, icp.py:97-98. */
 int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
-                int64_t ns, const float *tgt, const float *tgt_soa7, const double *centroid, int64_t nt,
-                int64_t nt_pad, double max_dist, int max_iteration, double rel_fitness,
+                const int32_t *src_perm, int64_t ns, const float *tgt, const IsrCloud *tgt_cloud,
+                const double *centroid, double max_dist, int max_iteration, double rel_fitness,
                 double rel_rmse, double *sums, int32_t *corr_idx, uint8_t *inlier,
                 void *workspace, size_t workspace_bytes, void *stream);
 

@@ -39,8 +39,10 @@ if "nn" in which:
         rng = np.random.default_rng(0)
         for k in range(B): P[k, :3, :3] = synth.random_rotation(rng)
         cen = api.centroid_of(cloud)
+        perm = api.spatial_order(cloud) if os.environ.get("PROBE_LIBSORT", "1") == "1" else None
         for name, q, t in (("direct", api.pack_soa(cloud, P), api.pack_soa(cloud)),
-                           ("exact", api.prepare_cloud(cloud, P, centroid=cen), api.prepare_cloud(cloud, centroid=cen))):
+                           ("exact", api.prepare_cloud(cloud, P, centroid=cen, perm=perm),
+                            api.prepare_cloud(cloud, centroid=cen, perm=perm, stage_centroids=True))):
             for idx in (False, True):
                 best, med = timeit(lambda: api.nearest_neighbors_soa(q, t, return_index=idx))
                 fl = 8.0 * N * N * B

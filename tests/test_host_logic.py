@@ -67,10 +67,16 @@ def test_argument_validation_needs_no_gpu():
     assert lib.isr_nn_soa(None, 5, 1000, 0, None, 0, 1024, 0, 1, None, None, None, 0, None, 0, None) == -2
     assert lib.isr_transform_points(None, -1, None, 1, None, None) == -2
     assert lib.isr_verify_poses(None, 0, None, 5, None, None, None, 1, 1, None, None, None, 0, None) == -2
-    assert lib.isr_icp_run(None, 1, None, None, 1, None, None, None, 1, 1024, 20.0, -1, 0.0, 0.0, None,
-                           None, None, None, 0, None) == -1
-    assert lib.isr_nn2(None, 5, 1024, 0, None, 5, 1024, 0, 1, 1, None, None, None, 0, None, 0, None) == -1
-    assert lib.isr_prepare_cloud(None, None, 5, None, 16, None, 16, None, 2, None, 1024, None, 0, None) == -1
+    assert lib.isr_icp_run(None, 1, None, None, None, 1, None, None, None, 20.0, -1, 0.0, 0.0, None, None,
+                           None, None, 0, None) == -1
+    assert lib.isr_nn2(None, None, 1, 1, None, None, None, 0, None, 0, None) == -1
+    empty = _lib.IsrCloud(None, 5, 1024, 0, None, None)
+    assert lib.isr_nn2(ctypes.byref(empty), ctypes.byref(empty), 1, 1, None, None, None, 0, None, 0,
+                       None) == -1
+    assert lib.isr_prepare_cloud(None, None, None, 5, None, 16, None, 16, None, 2, None, 1024, None, 0,
+                                 None) == -1
+    assert lib.isr_spatial_order(None, 5, None, None, 0, None) == -1
+    assert lib.isr_spatial_order_workspace_bytes(100000) >= 131072 * 8
     with pytest.raises(_lib.IsrError):
         _lib.check(-3)
 
