@@ -27,7 +27,9 @@ if mode == "direct":
     q = api.pack_soa(cloud, P); t = api.pack_soa(cloud)
 else:
     cen = api.centroid_of(cloud)
-    q = api.prepare_cloud(cloud, P, centroid=cen); t = api.prepare_cloud(cloud, centroid=cen)
+    perm = api.spatial_order(cloud)
+    q = api.prepare_cloud(cloud, P, centroid=cen, perm=perm)
+    t = api.prepare_cloud(cloud, centroid=cen, perm=perm, stage_centroids=True)
 for _ in range(3):
     r = api.nearest_neighbors_soa(q, t, return_index=idx)
 torch.cuda.synchronize()

@@ -1,0 +1,78 @@
+"""Multi-GPU parity (NCCL, one process per GPU).  Needs >= 2 visible GPUs; skipped otherwise
+(the single-GPU round-end box).  Run with `gpurun --gpus 2 -- python -m pytest tests -m gpu`."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as td
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import dist, synth
+    dist.init_from_env()
+    out = {}
+    try:
+        cloud = synth.make_cloud(6000, seed=1)
+        R_true, _ = synth.true_pose(3)
+        Rs, _, k0 = synth.make_candidates(21, seed=10, R_true=R_true, t_true=np.zeros(3))
+        Mq, Mt = synth.verification_matrices(Rs, R_true)
+        bi, bl, losses = dist.verify_poses_sharded(cloud, Mq, Mt, gather_losses=True)
+        out["verify"] = (int(bi.item()), float(bl.item()), losses.cpu().numpy(), k0)
+        src, tgt, _ = synth.icp_pair(9001, 9500, 6, 7)
+        res = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=12)
+        out["icp"] = (res[0].transformation, res[0].fitness, res[0].inlier_rmse, res[0].iterations)
+        torch.cuda.synchronize()
+    finally:
+        td.destroy_process_group()
+    q.put((rank, out))
+
+
+def test_two_gpu_sharding_matches_oracle():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    cloud = synth.make_cloud(6000, seed=1)
+    R_true, _ = synth.true_pose(3)
+    Rs, _, k0 = synth.make_candidates(21, seed=10, R_true=R_true, t_true=np.zeros(3))
+    Mq, Mt = synth.verification_matrices(Rs, R_true)
+    ref, ref_best = oracle.verify_matrices(cloud, cloud, Mq, Mt)
+    src, tgt, _ = synth.icp_pair(9001, 9500, 6, 7)
+    o = oracle.registration_icp(src, tgt, 20.0, np.eye(4), max_iteration=12)
+    for r in (0, 1):
+        bi, bl, losses, kk = got[r]["verify"]
+        assert bi == ref_best == k0
+        np.testing.assert_allclose(losses, ref, rtol=1e-5)
+        np.testing.assert_allclose(bl, ref[ref_best], rtol=1e-5)
+        T, fit, rmse, it = got[r]["icp"]
+        np.testing.assert_allclose(T, o.transformation, rtol=1e-7, atol=1e-7)
+        assert it == o.iterations and abs(fit - o.fitness) < 1e-12
+        np.testing.assert_allclose(rmse, o.inlier_rmse, rtol=1e-7)
+    np.testing.assert_array_equal(got[0]["icp"][0], got[1]["icp"][0])   # bit-identical ranks
+    np.testing.assert_array_equal(got[0]["verify"][2], got[1]["verify"][2])
