@@ -46,17 +46,19 @@ centroid_kernel(const float *__restrict__ pts, int64_t n, double *__restrict__ o
     }
 }
 
-// grid: (npad / 256, b)
+// grid: (npad / 256, ceil(b / kPosesPerCta)).  A CTA keeps its 256 points in registers and
+// walks kPosesPerCta poses, so the (gathered) point read and the CTA start-up are paid once
+// per 16 x 7 KB of coalesced plane writes.
+constexpr int kPosesPerCta = 16;
+
 __global__ void __launch_bounds__(kPrepThreads)
 prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts_lo,
                     const int32_t *__restrict__ perm, int64_t n, const double *__restrict__ poses,
                     int64_t pose_stride, const double *__restrict__ centre_poses,
-                    int64_t centre_pose_stride, const double *__restrict__ centroid,
+                    int64_t centre_pose_stride, const double *__restrict__ centroid, int64_t b,
                     float *__restrict__ out, int64_t npad, const int32_t *__restrict__ skip,
                     int64_t skip_stride) {
     __shared__ float stage[kPrepThreads * 3];
-    const int b = blockIdx.y;
-    if (skip != nullptr && skip[(int64_t)b * skip_stride] != 0) return;
     const int64_t p0 = (int64_t)blockIdx.x * kPrepThreads;
     const int cnt = (int)max((int64_t)0, min((int64_t)kPrepThreads, n - p0));
     const int tid = threadIdx.x;
@@ -68,47 +70,55 @@ prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts
         stage[tid * 3] = src[0]; stage[tid * 3 + 1] = src[1]; stage[tid * 3 + 2] = src[2];
     }
     __syncthreads();
-
-    float hx = ISR_PAD_COORD, hy = ISR_PAD_COORD, hz = ISR_PAD_COORD;
-    float lx = 0.f, ly = 0.f, lz = 0.f;
-    if (tid < cnt) {
-        // centre of this batch item
-        double cx = 0, cy = 0, cz = 0;
-        if (centroid != nullptr) {
-            cx = centroid[0]; cy = centroid[1]; cz = centroid[2];
-            if (centre_poses != nullptr) {
-                const double *C = centre_poses + (int64_t)b * centre_pose_stride;
-                const double mx = cx, my = cy, mz = cz;
-                cx = ((C[0] * mx + C[1] * my) + C[2] * mz) + C[3];
-                cy = ((C[4] * mx + C[5] * my) + C[6] * mz) + C[7];
-                cz = ((C[8] * mx + C[9] * my) + C[10] * mz) + C[11];
-            }
-        }
-        double px = stage[tid * 3], py = stage[tid * 3 + 1], pz = stage[tid * 3 + 2];
+    const bool live = tid < cnt;
+    double px = 0, py = 0, pz = 0;
+    if (live) {
+        px = stage[tid * 3]; py = stage[tid * 3 + 1]; pz = stage[tid * 3 + 2];
         if (pts_lo != nullptr) {  // float64 input carried as a float32 hi/lo pair
             const float *l = pts_lo + (perm != nullptr ? (int64_t)perm[p0 + tid] : p0 + tid) * 3;
             px += (double)l[0]; py += (double)l[1]; pz += (double)l[2];
         }
-        double x = px, y = py, z = pz;
-        if (poses != nullptr) {
-            const double *P = poses + (int64_t)b * pose_stride;
-            x = ((P[0] * px + P[1] * py) + P[2] * pz) + P[3];
-            y = ((P[4] * px + P[5] * py) + P[6] * pz) + P[7];
-            z = ((P[8] * px + P[9] * py) + P[10] * pz) + P[11];
-        }
-        x -= cx; y -= cy; z -= cz;
-        hx = (float)x; hy = (float)y; hz = (float)z;
-        lx = (float)(x - (double)hx); ly = (float)(y - (double)hy); lz = (float)(z - (double)hz);
     }
-    const float nrm = __fmaf_rn(hz, hz, __fmaf_rn(hy, hy, __fmul_rn(hx, hx)));
-    float *o = out + (int64_t)b * 7 * npad + p0 + tid;
-    o[0] = hx;
-    o[npad] = hy;
-    o[2 * npad] = hz;
-    o[3 * npad] = nrm;
-    o[4 * npad] = lx;
-    o[5 * npad] = ly;
-    o[6 * npad] = lz;
+    const int64_t b_begin = (int64_t)blockIdx.y * kPosesPerCta;
+    const int64_t b_end = min(b, b_begin + kPosesPerCta);
+    for (int64_t bb = b_begin; bb < b_end; ++bb) {
+        if (skip != nullptr && skip[bb * skip_stride] != 0) continue;
+        float hx = ISR_PAD_COORD, hy = ISR_PAD_COORD, hz = ISR_PAD_COORD;
+        float lx = 0.f, ly = 0.f, lz = 0.f;
+        if (live) {
+            // centre of this batch item
+            double cx = 0, cy = 0, cz = 0;
+            if (centroid != nullptr) {
+                cx = centroid[0]; cy = centroid[1]; cz = centroid[2];
+                if (centre_poses != nullptr) {
+                    const double *C = centre_poses + bb * centre_pose_stride;
+                    const double mx = cx, my = cy, mz = cz;
+                    cx = ((C[0] * mx + C[1] * my) + C[2] * mz) + C[3];
+                    cy = ((C[4] * mx + C[5] * my) + C[6] * mz) + C[7];
+                    cz = ((C[8] * mx + C[9] * my) + C[10] * mz) + C[11];
+                }
+            }
+            double x = px, y = py, z = pz;
+            if (poses != nullptr) {
+                const double *P = poses + bb * pose_stride;
+                x = ((P[0] * px + P[1] * py) + P[2] * pz) + P[3];
+                y = ((P[4] * px + P[5] * py) + P[6] * pz) + P[7];
+                z = ((P[8] * px + P[9] * py) + P[10] * pz) + P[11];
+            }
+            x -= cx; y -= cy; z -= cz;
+            hx = (float)x; hy = (float)y; hz = (float)z;
+            lx = (float)(x - (double)hx); ly = (float)(y - (double)hy); lz = (float)(z - (double)hz);
+        }
+        const float nrm = __fmaf_rn(hz, hz, __fmaf_rn(hy, hy, __fmul_rn(hx, hx)));
+        float *o = out + bb * 7 * npad + p0 + tid;
+        o[0] = hx;
+        o[npad] = hy;
+        o[2 * npad] = hz;
+        o[3 * npad] = nrm;
+        o[4 * npad] = lx;
+        o[5 * npad] = ly;
+        o[6 * npad] = lz;
+    }
 }
 
 // centroid of the real points of every 1024-point SoA tile ("stage"): grid (stages, batch)
@@ -188,11 +198,11 @@ int isr_prepare_cloud(const float *pts, const float *pts_lo, const int32_t *perm
                 "prepare_cloud: repack (poses NULL) needs b == 1");
     ISR_REQUIRE(b <= 65535, ISR_E_SHAPE, "prepare_cloud: batch %lld > 65535", (long long)b);
     ISR_REQUIRE(aligned16(out_soa7), ISR_E_ALIGN, "prepare_cloud: out not 16-byte aligned");
-    dim3 grid((unsigned)(npad / kPrepThreads), (unsigned)b);
+    dim3 grid((unsigned)(npad / kPrepThreads), (unsigned)((b + kPosesPerCta - 1) / kPosesPerCta));
     ProfScope prof(kProfTransform, (cudaStream_t)stream);
     prepare_soa7_kernel<<<grid, kPrepThreads, 0, (cudaStream_t)stream>>>(
-        pts, pts_lo, perm, n, poses, pose_stride, centre_poses, centre_pose_stride, centroid, out_soa7,
-        npad, skip, skip_stride);
+        pts, pts_lo, perm, n, poses, pose_stride, centre_poses, centre_pose_stride, centroid, b,
+        out_soa7, npad, skip, skip_stride);
     return launched("prepare_soa7_kernel");
 }
 

@@ -38,37 +38,45 @@ __device__ __forceinline__ void apply_pose(const Pose12 &P, float x, float y, fl
     oz = (float)(((P.r[6] * dx + P.r[7] * dy) + P.r[8] * dz) + P.t[2]);
 }
 
-// grid: (ceil(n / 256), b)
+// grid: (ceil(n / 256), ceil(b / kTfPosesPerCta)): the CTA's 256 points stay in registers
+// while it walks 16 poses; every pose's 3 KB go out as float4 through shared memory.
+constexpr int kTfPosesPerCta = 16;
+
 __global__ void __launch_bounds__(kTfThreads)
 transform_aos_kernel(const float *__restrict__ pts, int64_t n, const double *__restrict__ poses,
-                     float *__restrict__ out, int vec_ok) {
+                     int64_t b, float *__restrict__ out, int vec_ok) {
     __shared__ float stage[kTfThreads * 3];
-    const int b = blockIdx.y;
     const int64_t p0 = (int64_t)blockIdx.x * kTfThreads;
     const int cnt = (int)min((int64_t)kTfThreads, n - p0);
-    const Pose12 P = load_pose(poses + (int64_t)b * 16);
     const int tid = threadIdx.x;
 
     // coalesced read of this block's 256 x 3 floats through shared memory
     const float *src = pts + p0 * 3;
     for (int k = tid; k < cnt * 3; k += kTfThreads) stage[k] = src[k];
     __syncthreads();
-    float ox = 0.f, oy = 0.f, oz = 0.f;
-    if (tid < cnt) apply_pose(P, stage[tid * 3], stage[tid * 3 + 1], stage[tid * 3 + 2], ox, oy, oz);
-    __syncthreads();
-    if (tid < cnt) {
-        stage[tid * 3] = ox;
-        stage[tid * 3 + 1] = oy;
-        stage[tid * 3 + 2] = oz;
-    }
-    __syncthreads();
-    float *dst = out + ((int64_t)b * n + p0) * 3;
-    if (vec_ok && cnt == kTfThreads) {
-        // 768 floats = 192 float4, 16-byte aligned because n % 4 == 0 and p0 % 256 == 0
-        if (tid < kTfThreads * 3 / 4)
-            reinterpret_cast<float4 *>(dst)[tid] = reinterpret_cast<const float4 *>(stage)[tid];
-    } else {
-        for (int k = tid; k < cnt * 3; k += kTfThreads) dst[k] = stage[k];
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (tid < cnt) { x = stage[tid * 3]; y = stage[tid * 3 + 1]; z = stage[tid * 3 + 2]; }
+    const int64_t b_begin = (int64_t)blockIdx.y * kTfPosesPerCta;
+    const int64_t b_end = min(b, b_begin + kTfPosesPerCta);
+    for (int64_t bb = b_begin; bb < b_end; ++bb) {
+        const Pose12 P = load_pose(poses + bb * 16);
+        float ox = 0.f, oy = 0.f, oz = 0.f;
+        if (tid < cnt) apply_pose(P, x, y, z, ox, oy, oz);
+        __syncthreads();  // previous pose's stores have been read out of `stage`
+        if (tid < cnt) {
+            stage[tid * 3] = ox;
+            stage[tid * 3 + 1] = oy;
+            stage[tid * 3 + 2] = oz;
+        }
+        __syncthreads();
+        float *dst = out + (bb * n + p0) * 3;
+        if (vec_ok && cnt == kTfThreads) {
+            // 768 floats = 192 float4, 16-byte aligned because n % 4 == 0 and p0 % 256 == 0
+            if (tid < kTfThreads * 3 / 4)
+                reinterpret_cast<float4 *>(dst)[tid] = reinterpret_cast<const float4 *>(stage)[tid];
+        } else {
+            for (int k = tid; k < cnt * 3; k += kTfThreads) dst[k] = stage[k];
+        }
     }
 }
 
@@ -116,11 +124,12 @@ int isr_transform_points(const float *pts, int64_t n, const double *poses, int64
     ISR_REQUIRE(n >= 0 && b >= 0, ISR_E_SHAPE, "transform_points: negative size");
     if (n == 0 || b == 0) return ISR_OK;
     ISR_REQUIRE(pts && poses && out, ISR_E_INVALID_ARG, "transform_points: null pointer");
-    ISR_REQUIRE(b <= 65535, ISR_E_SHAPE, "transform_points: batch %lld > 65535", (long long)b);
+    ISR_REQUIRE(b <= 65535 * 16, ISR_E_SHAPE, "transform_points: batch %lld too large", (long long)b);
     const int vec_ok = (n % 4 == 0) && aligned16(out);
-    dim3 grid((unsigned)((n + kTfThreads - 1) / kTfThreads), (unsigned)b);
+    dim3 grid((unsigned)((n + kTfThreads - 1) / kTfThreads),
+              (unsigned)((b + kTfPosesPerCta - 1) / kTfPosesPerCta));
     ProfScope prof(kProfTransform, (cudaStream_t)stream);
-    transform_aos_kernel<<<grid, kTfThreads, 0, (cudaStream_t)stream>>>(pts, n, poses, out, vec_ok);
+    transform_aos_kernel<<<grid, kTfThreads, 0, (cudaStream_t)stream>>>(pts, n, poses, b, out, vec_ok);
     return launched("transform_aos_kernel");
 }
 
