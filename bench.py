@@ -181,7 +181,7 @@ def run_reference(args):
     value = s * len(times) / tot
     sample = (f"{s} of the {args.candidates} candidates per step (float64 KD-tree Chamfer, both "
               f"directions, {args.points} pts), scipy cKDTree workers=-1 as the Open3D stand-in")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -189,11 +189,27 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+def emit(obj):
+    """Print the ONE JSON line on the real stdout (see main: fd 1 is parked on stderr while
+    the run is in flight so that library chatter -- NCCL's version banner -- cannot mix in)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
+
+
+_REAL_STDOUT = None
 
 
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -431,7 +447,7 @@ def main():
         "cpu_baseline": cpu,
         "secondary": secondary,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":
