@@ -94,6 +94,10 @@ __global__ void __launch_bounds__(256) ffma2_pattern_kernel(int iters, float *si
                 m0 = __int_as_float(__float_as_int(m0) | __float_as_int(lo) | __float_as_int(hi));
             }
         }
+        if (MODE == 9) {  // 8 extra scalar FFMA next to 16 FFMA2: does fmalite add capacity?
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sc[k] = __fmaf_rn(sc[k], 1.0000001f, 1e-9f);
+        }
         if (MODE == 8) {  // one FMNMX3 per FOUR values... (half the mins) reference point
 #pragma unroll
             for (int k = 0; k < 16; k += 2) {
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(256) ffma2_pattern_kernel(int iters, float *si
     }
     float s = m0 + m1;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { float lo, hi; unpack2(a[k], lo, hi); s += lo + hi; }
+    for (int k = 0; k < 16; ++k) { float lo, hi; unpack2(a[k], lo, hi); s += lo + hi + sc[k]; }
     if (s == 123.456f) sink[0] = s;
 }
 
@@ -121,6 +125,7 @@ extern "C" int isr_bench_ffma2_pattern(int blocks, int iters, int mode, float *s
     else if (mode == 6) ffma2_pattern_kernel<6><<<blocks, 256, 0, st>>>(iters, sink, src);
     else if (mode == 7) ffma2_pattern_kernel<7><<<blocks, 256, 0, st>>>(iters, sink, src);
     else if (mode == 8) ffma2_pattern_kernel<8><<<blocks, 256, 0, st>>>(iters, sink, src);
+    else if (mode == 9) ffma2_pattern_kernel<9><<<blocks, 256, 0, st>>>(iters, sink, src);
     else ffma2_pattern_kernel<4><<<blocks, 256, 0, st>>>(iters, sink, src);
     if (flops_out_host) *flops_out_host = (double)blocks * 256.0 * (double)iters * 16.0 * 4.0;
     return launched("ffma2_pattern_kernel");

@@ -6,7 +6,7 @@ lib = ctypes.CDLL(_lib.LIB_PATH)
 torch.cuda.set_device(0)
 sink = torch.zeros(4, device="cuda"); src = torch.full((32,), 1.0000001, device="cuda")
 fl = ctypes.c_double(0)
-for mode in (2, 3, 4, 5, 6, 7, 8):
+for mode in (2, 9, 8):
     best = 0
     for _ in range(4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
