@@ -255,11 +255,12 @@ icp_solve_kernel(IsrIcpState *__restrict__ states, const double *__restrict__ su
     st.T[12] = 0.0; st.T[13] = 0.0; st.T[14] = 0.0; st.T[15] = 1.0;
 }
 
-static int acc_blocks(int64_t ns, int64_t starts) {
+// The grid (and with it the grouping of the partial sums) depends on the source size only,
+// never on the batch of starts or the device: a start gives bit-identical sums whether it
+// runs alone or next to 63 others.
+static int acc_blocks(int64_t ns) {
     int64_t want = (ns + kAccThreads * 8 - 1) / (kAccThreads * 8);
-    int64_t cap = (int64_t)sm_count() * 8 / (starts > 0 ? starts : 1);
-    if (cap < 8) cap = 8;
-    if (want > cap) want = cap;
+    if (want > 1024) want = 1024;
     if (want < 1) want = 1;
     return (int)want;
 }
@@ -272,12 +273,10 @@ struct IcpLayout {
 static IcpLayout icp_layout(int64_t ns, int64_t nt, int64_t starts) {
     IcpLayout L;
     const int64_t nsp = isr_soa_padded_len(ns);
-    // nblk must not depend on the device so that workspace sizing works without a GPU
-    // context: size for the largest grid acc_blocks() can pick (cap >= want).
     size_t off = 0;
     L.xs = off;       off += align256((size_t)starts * 7 * nsp * 4);
     L.d2 = off;       off += align256((size_t)starts * ns * 4);
-    const int64_t max_blk = (ns + kAccThreads * 8 - 1) / (kAccThreads * 8) + 1;
+    const int64_t max_blk = acc_blocks(ns);
     L.partials = off; off += align256((size_t)starts * max_blk * kNS * 8);
     L.tickets = off;  off += align256((size_t)starts * 4);
     const size_t w1 = isr_nn_workspace_bytes(ns, nt, starts), w2 = isr_nn2_workspace_bytes(ns, nt, starts);
@@ -336,7 +335,7 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, co
     ISR_TRY(isr_nn2(&src_cloud, tgt_cloud, starts, 1, d2, corr_idx, done, kStateInts, ws + L.nnws,
                     L.total - L.nnws, stream));
     ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
-    const int nblk = acc_blocks(ns, starts);
+    const int nblk = acc_blocks(ns);
     dim3 grid((unsigned)nblk, (unsigned)starts);
     ProfScope prof(kProfIcpAcc, st);
     icp_accumulate_kernel<<<grid, kAccThreads, 0, st>>>(states, src, src_lo, ns, tgt, corr_idx,
