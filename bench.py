@@ -357,19 +357,26 @@ def main():
         Pb = api._poses(Mq[lo:lo + min(256, b_local)], dev)
         nb = Pb.shape[0]
 
-        def timed(fn, reps=3):
-            fn(); torch.cuda.synchronize()
+        def kernel_seconds(fn, kind, reps=3):
+            """Device time of the kernel(s) of one profile kind inside fn (CUDA events recorded
+            by libisr around the launch), best of `reps`."""
+            fn()
+            torch.cuda.synchronize()
             best = 1e30
+            mk, nk = (ctypes.c_double * 5)(), (ctypes.c_uint64 * 5)()
             for _ in range(reps):
-                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); fn(); b_.record(); b_.synchronize()
-                best = min(best, a.elapsed_time(b_) * 1e-3)
+                lib.isr_profile_enable(1)
+                lib.isr_profile_collect(None, None)
+                fn()
+                _lib.check(lib.isr_profile_collect(mk, nk))
+                lib.isr_profile_enable(0)
+                best = min(best, float(mk[kind]) * 1e-3)
             return best
 
-        t_k1 = timed(lambda: api.transform_points(cloud_d, Pb))
+        t_k1 = kernel_seconds(lambda: api.transform_points(cloud_d, Pb), 0)
         k1_bytes = args.points * 12 + nb * args.points * 12
         cen = api.centroid_of(cloud_d)
-        t_k1p = timed(lambda: api.prepare_cloud(cloud_d, Pb, centroid=cen, centre_poses=Pb))
+        t_k1p = kernel_seconds(lambda: api.prepare_cloud(cloud_d, Pb, centroid=cen, centre_poses=Pb), 0)
         k1p_bytes = args.points * 12 + nb * 7 * _lib.soa_padded_len(args.points) * 4
         secondary = {
             "icp_iters_per_s": args.icp_iters / t_icp,

@@ -52,29 +52,53 @@ icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__res
 
     const int32_t *ids = idx + (int64_t)s * ns;
     uint8_t *inl = inlier != nullptr ? inlier + (int64_t)s * ns : nullptr;
-    for (int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i < ns;
-         i += (int64_t)gridDim.x * kAccThreads) {
-        double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
-        if (src_lo != nullptr) {
-            px += (double)src_lo[3 * i]; py += (double)src_lo[3 * i + 1]; pz += (double)src_lo[3 * i + 2];
+    // 4 points per thread and trip, all loads of a trip issued before the first use: the
+    // dependent gather (index -> target row) is what bounds this kernel, so keep 4 in flight.
+    constexpr int U = 4;
+    const int64_t stride = (int64_t)gridDim.x * kAccThreads;
+    for (int64_t i0 = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i0 < ns; i0 += U * stride) {
+        float fx[U], fy[U], fz[U], lx[U], ly[U], lz[U];
+        int j[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            ok[u] = i < ns;
+            const int64_t ii = ok[u] ? i : i0;
+            fx[u] = src[3 * ii]; fy[u] = src[3 * ii + 1]; fz[u] = src[3 * ii + 2];
+            lx[u] = ly[u] = lz[u] = 0.f;
+            if (src_lo != nullptr) {
+                lx[u] = src_lo[3 * ii]; ly[u] = src_lo[3 * ii + 1]; lz[u] = src_lo[3 * ii + 2];
+            }
+            j[u] = ids[ii];
         }
-        const double sx = ((T[0] * px + T[1] * py) + T[2] * pz) + T[3];
-        const double sy = ((T[4] * px + T[5] * py) + T[6] * pz) + T[7];
-        const double sz = ((T[8] * px + T[9] * py) + T[10] * pz) + T[11];
-        const int64_t j = ids[i];
-        const double tx = tgt[3 * j], ty = tgt[3 * j + 1], tz = tgt[3 * j + 2];
-        const double dx = sx - tx, dy = sy - ty, dz = sz - tz;
-        const double d2 = dx * dx + dy * dy + dz * dz;
-        const bool in = d2 < max_d2;
-        if (inl != nullptr) inl[i] = in ? 1 : 0;
-        if (in) {
-            acc[0] += sx; acc[1] += sy; acc[2] += sz;
-            acc[3] += tx; acc[4] += ty; acc[5] += tz;
-            acc[6] += tx * sx; acc[7] += tx * sy; acc[8] += tx * sz;
-            acc[9] += ty * sx; acc[10] += ty * sy; acc[11] += ty * sz;
-            acc[12] += tz * sx; acc[13] += tz * sy; acc[14] += tz * sz;
-            acc[15] += d2;
-            acc[16] += 1.0;
+        float gx[U], gy[U], gz[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t jj = j[u];
+            gx[u] = tgt[3 * jj]; gy[u] = tgt[3 * jj + 1]; gz[u] = tgt[3 * jj + 2];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double px = (double)fx[u] + (double)lx[u], py = (double)fy[u] + (double)ly[u],
+                         pz = (double)fz[u] + (double)lz[u];
+            const double sx = ((T[0] * px + T[1] * py) + T[2] * pz) + T[3];
+            const double sy = ((T[4] * px + T[5] * py) + T[6] * pz) + T[7];
+            const double sz = ((T[8] * px + T[9] * py) + T[10] * pz) + T[11];
+            const double tx = gx[u], ty = gy[u], tz = gz[u];
+            const double dx = sx - tx, dy = sy - ty, dz = sz - tz;
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            const bool in = ok[u] && d2 < max_d2;
+            if (inl != nullptr && ok[u]) inl[i0 + u * stride] = in ? 1 : 0;
+            if (in) {
+                acc[0] += sx; acc[1] += sy; acc[2] += sz;
+                acc[3] += tx; acc[4] += ty; acc[5] += tz;
+                acc[6] += tx * sx; acc[7] += tx * sy; acc[8] += tx * sz;
+                acc[9] += ty * sx; acc[10] += ty * sy; acc[11] += ty * sz;
+                acc[12] += tz * sx; acc[13] += tz * sy; acc[14] += tz * sz;
+                acc[15] += d2;
+                acc[16] += 1.0;
+            }
         }
     }
 #pragma unroll
@@ -100,12 +124,30 @@ icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__res
     }
     __syncthreads();
     if (is_last) {
+        // final reduction over the CTAs' partials by the whole block: thread t takes blocks
+        // t, t+256, ... (fixed mapping), then the same warp -> CTA tree as above
         __threadfence();
+        const double *base = partials + (int64_t)s * gridDim.x * kNS;
+        double v[kNS];
+#pragma unroll
+        for (int k = 0; k < kNS; ++k) v[k] = 0.0;
+        for (unsigned bk = threadIdx.x; bk < gridDim.x; bk += kAccThreads) {
+#pragma unroll
+            for (int k = 0; k < kNS; ++k) v[k] += base[(int64_t)bk * kNS + k];
+        }
+#pragma unroll
+        for (int k = 0; k < kNS; ++k) v[k] = warp_sum(v[k]);
+        __syncthreads();  // `red` is reused
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < kNS; ++k) red[warp][k] = v[k];
+        }
+        __syncthreads();
         if (threadIdx.x < kNS) {
-            const double *base = partials + (int64_t)s * gridDim.x * kNS;
-            double v = 0.0;
-            for (unsigned bk = 0; bk < gridDim.x; ++bk) v += base[(int64_t)bk * kNS + threadIdx.x];
-            sums[(int64_t)s * kNS + threadIdx.x] = v;
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kAccThreads / 32; ++w) t += red[w][threadIdx.x];
+            sums[(int64_t)s * kNS + threadIdx.x] = t;
         }
         if (threadIdx.x == 0) tickets[s] = 0;
     }
@@ -259,8 +301,8 @@ icp_solve_kernel(IsrIcpState *__restrict__ states, const double *__restrict__ su
 // never on the batch of starts or the device: a start gives bit-identical sums whether it
 // runs alone or next to 63 others.
 static int acc_blocks(int64_t ns) {
-    int64_t want = (ns + kAccThreads * 8 - 1) / (kAccThreads * 8);
-    if (want > 1024) want = 1024;
+    int64_t want = (ns + kAccThreads * 4 - 1) / (kAccThreads * 4);
+    if (want > 2048) want = 2048;
     if (want < 1) want = 1;
     return (int)want;
 }

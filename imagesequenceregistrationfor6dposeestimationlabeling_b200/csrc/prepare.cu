@@ -59,9 +59,31 @@ prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts
                     float *__restrict__ out, int64_t npad, const int32_t *__restrict__ skip,
                     int64_t skip_stride) {
     __shared__ float stage[kPrepThreads * 3];
+    __shared__ double spose[kPosesPerCta][12];    // pose rows of this CTA's batch items
+    __shared__ double scentre[kPosesPerCta][3];   // and their centres c_b
     const int64_t p0 = (int64_t)blockIdx.x * kPrepThreads;
     const int cnt = (int)max((int64_t)0, min((int64_t)kPrepThreads, n - p0));
     const int tid = threadIdx.x;
+    {
+        const int64_t b0 = (int64_t)blockIdx.y * kPosesPerCta;
+        const int nb = (int)min((int64_t)kPosesPerCta, b - b0);
+        if (poses != nullptr && tid < nb * 12)
+            spose[tid / 12][tid % 12] = poses[(b0 + tid / 12) * pose_stride + tid % 12];
+        if (tid < nb) {
+            double cx = 0, cy = 0, cz = 0;
+            if (centroid != nullptr) {
+                cx = centroid[0]; cy = centroid[1]; cz = centroid[2];
+                if (centre_poses != nullptr) {
+                    const double *C = centre_poses + (b0 + tid) * centre_pose_stride;
+                    const double mx = cx, my = cy, mz = cz;
+                    cx = ((C[0] * mx + C[1] * my) + C[2] * mz) + C[3];
+                    cy = ((C[4] * mx + C[5] * my) + C[6] * mz) + C[7];
+                    cz = ((C[8] * mx + C[9] * my) + C[10] * mz) + C[11];
+                }
+            }
+            scentre[tid][0] = cx; scentre[tid][1] = cy; scentre[tid][2] = cz;
+        }
+    }
     if (perm == nullptr) {
         const float *src = pts + p0 * 3;
         for (int k = tid; k < cnt * 3; k += kPrepThreads) stage[k] = src[k];
@@ -86,21 +108,11 @@ prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts
         float hx = ISR_PAD_COORD, hy = ISR_PAD_COORD, hz = ISR_PAD_COORD;
         float lx = 0.f, ly = 0.f, lz = 0.f;
         if (live) {
-            // centre of this batch item
-            double cx = 0, cy = 0, cz = 0;
-            if (centroid != nullptr) {
-                cx = centroid[0]; cy = centroid[1]; cz = centroid[2];
-                if (centre_poses != nullptr) {
-                    const double *C = centre_poses + bb * centre_pose_stride;
-                    const double mx = cx, my = cy, mz = cz;
-                    cx = ((C[0] * mx + C[1] * my) + C[2] * mz) + C[3];
-                    cy = ((C[4] * mx + C[5] * my) + C[6] * mz) + C[7];
-                    cz = ((C[8] * mx + C[9] * my) + C[10] * mz) + C[11];
-                }
-            }
+            const int bl = (int)(bb - b_begin);
+            const double cx = scentre[bl][0], cy = scentre[bl][1], cz = scentre[bl][2];
             double x = px, y = py, z = pz;
             if (poses != nullptr) {
-                const double *P = poses + bb * pose_stride;
+                const double *P = spose[bl];
                 x = ((P[0] * px + P[1] * py) + P[2] * pz) + P[3];
                 y = ((P[4] * px + P[5] * py) + P[6] * pz) + P[7];
                 z = ((P[8] * px + P[9] * py) + P[10] * pz) + P[11];
