@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libisr.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "isr.h")
 
 ISR_SOA_TILE = 1024
+ISR_SUB_TILE = 64
 ISR_PAD_COORD = np.float32(1.0e18)
 ISR_ICP_NSUMS = 17
 
@@ -38,7 +39,8 @@ assert ICP_STATE_DTYPE.itemsize == 184
 class IsrCloud(ctypes.Structure):
     """ctypes mirror of ``struct IsrCloud`` (include/isr.h)."""
     _fields_ = [("soa7", ctypes.c_void_p), ("n", ctypes.c_int64), ("npad", ctypes.c_int64),
-                ("bstride", ctypes.c_int64), ("stage_c", ctypes.c_void_p), ("perm", ctypes.c_void_p)]
+                ("bstride", ctypes.c_int64), ("stage_c", ctypes.c_void_p), ("perm", ctypes.c_void_p),
+                ("sub_c", ctypes.c_void_p)]
 
 
 class IsrError(RuntimeError):
@@ -74,7 +76,10 @@ SIGNATURES = {
     "isr_spatial_order_workspace_bytes": (_SZ, [_I64]),
     "isr_spatial_order": (_I, [_P, _I64, _P, _P, _SZ, _P]),
     "isr_prepare_cloud": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
-    "isr_stage_centroids": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P]),
+    "isr_tile_spheres": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P, _P]),
+    "isr_set_nn_pruning": (_I, [_I]),
+    "isr_get_nn_pruning": (_I, []),
+    "isr_profile_nn_pairs": (_I, [_P, _P]),
     "isr_nn2_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "isr_nn2": (_I, [_P, _P, _I64, _I, _P, _P, _P, _I64, _P, _SZ, _P]),
     "isr_mean_sqrt": (_I, [_P, _I64, _I64, _P, _P]),

@@ -98,6 +98,16 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+def set_nn_pruning(on: bool) -> None:
+    """Process-wide switch of the nearest-neighbour kernel's tile pruning (default on).
+    Off = exhaustive brute force over every (query, target) pair; results are identical."""
+    _lib.check(_lib.load().isr_set_nn_pruning(1 if on else 0))
+
+
+def get_nn_pruning() -> bool:
+    return bool(_lib.load().isr_get_nn_pruning())
+
+
 def pose_from_Rt(R, t) -> np.ndarray:
     """4x4 float64 pose (column-vector convention) from a 3x3 rotation and a translation."""
     T = np.eye(4)
@@ -137,7 +147,8 @@ class SoaCloud:
     n: int
     centroid: Optional[torch.Tensor] = None
     perm: Optional[torch.Tensor] = None      # int32 [n]: stored position -> original index
-    stage_c: Optional[torch.Tensor] = None   # float32 [B, npad/1024, 4] stage centroids
+    stage_c: Optional[torch.Tensor] = None   # float32 [B, npad/1024, 4] stage spheres (c, r)
+    sub_c: Optional[torch.Tensor] = None     # float32 [B, npad/64, 4] sub-tile spheres
 
     @property
     def planes(self) -> int:
@@ -146,7 +157,8 @@ class SoaCloud:
     def descriptor(self, batched: bool) -> "_lib.IsrCloud":
         """ctypes ``IsrCloud`` for this cloud (7-plane clouds only)."""
         return _lib.IsrCloud(self.data.data_ptr(), self.n, self.npad,
-                             7 * self.npad if batched else 0, _ptr(self.stage_c), _ptr(self.perm))
+                             7 * self.npad if batched else 0, _ptr(self.stage_c), _ptr(self.perm),
+                             _ptr(self.sub_c))
 
     @property
     def npad(self) -> int:
@@ -209,8 +221,9 @@ def prepare_cloud(points, poses=None, centroid=None, centre_poses=None, perm=Non
     """[N,3] (optionally transformed by poses [B,4,4]) -> centred hi/lo SoA7 planes [B,7,npad].
     The centre of batch item b is centre_poses[b] . centroid (centre_poses None: centroid).
     float64 input keeps its precision (hi/lo split).  `perm` (from spatial_order) stores the
-    points in Morton order; `stage_centroids` adds the per-tile centroids a target needs for
-    nearest-stage-first scanning."""
+    points in Morton order; `stage_centroids` adds the bounding spheres of the 1024-point
+    stages and 64-point sub-tiles that a target needs for nearest-stage-first scanning and
+    tile pruning."""
     device = _device(device)
     pts, pts_lo = _points_hilo(points, device)
     if pts.dim() != 2:
@@ -231,14 +244,15 @@ def prepare_cloud(points, poses=None, centroid=None, centre_poses=None, perm=Non
             _ptr(pts), _ptr(pts_lo), _ptr(perm), n, None if P is None else _ptr(P[b0:]), 16,
             None if C is None else _ptr(C[b0:]), 16, _ptr(cen), bc, _ptr(out[b0:]), npad, None, 0,
             _stream()))
-    sc = None
+    sc = sub = None
     if stage_centroids:
         sc = torch.empty((b, npad // _lib.ISR_SOA_TILE, 4), dtype=torch.float32, device=device)
+        sub = torch.empty((b, npad // _lib.ISR_SUB_TILE, 4), dtype=torch.float32, device=device)
         for b0 in range(0, b, 65535):
             bc = min(65535, b - b0)
-            _lib.check(lib.isr_stage_centroids(_ptr(out[b0:]), n, npad, 7 * npad, bc, _ptr(sc[b0:]),
-                                               _stream()))
-    return SoaCloud(out, n, cen, perm, sc)
+            _lib.check(lib.isr_tile_spheres(_ptr(out[b0:]), n, npad, 7 * npad, bc, _ptr(sc[b0:]),
+                                            _ptr(sub[b0:]), _stream()))
+    return SoaCloud(out, n, cen, perm, sc, sub)
 
 
 def _pack_batched(points, device) -> SoaCloud:
@@ -298,10 +312,11 @@ def nearest_neighbors_soa(q: SoaCloud, t: SoaCloud, return_index: bool = True,
         if pl == 7:
             ws = _workspace(lib.isr_nn2_workspace_bytes(q.n, t.n, bc), device)
             qdesc = _lib.IsrCloud(qd.data_ptr(), q.n, q.npad, pl * q.npad if qb > 1 else 0, None,
-                                  _ptr(q.perm))
+                                  _ptr(q.perm), None)
             tsc = None if t.stage_c is None else (t.stage_c[b0:] if tb > 1 else t.stage_c)
+            tsub = None if t.sub_c is None else (t.sub_c[b0:] if tb > 1 else t.sub_c)
             tdesc = _lib.IsrCloud(td.data_ptr(), t.n, t.npad, pl * t.npad if tb > 1 else 0,
-                                  _ptr(tsc), _ptr(t.perm))
+                                  _ptr(tsc), _ptr(t.perm), _ptr(tsub))
             _lib.check(lib.isr_nn2(
                 ctypes.byref(qdesc), ctypes.byref(tdesc), bc, 1 if use_lo else 0, _ptr(d2[b0:]),
                 _ptr(idx[b0:]) if idx is not None else None, None, 0, _ptr(ws), ws.numel(),

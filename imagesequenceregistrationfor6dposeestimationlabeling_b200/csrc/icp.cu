@@ -373,7 +373,7 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, co
     // source: FP64 pose from the device state, centred on the target's centroid, hi/lo planes
     ISR_TRY(isr_prepare_cloud(src, src_lo, src_perm, ns, &states[0].T[0], kStateDoubles, nullptr, 0,
                               centroid, starts, xs, nsp, done, kStateInts, stream));
-    const IsrCloud src_cloud{xs, ns, nsp, 7 * nsp, nullptr, src_perm};
+    const IsrCloud src_cloud{xs, ns, nsp, 7 * nsp, nullptr, src_perm, nullptr};
     ISR_TRY(isr_nn2(&src_cloud, tgt_cloud, starts, 1, d2, corr_idx, done, kStateInts, ws + L.nnws,
                     L.total - L.nnws, stream));
     ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));

@@ -1,8 +1,12 @@
 // K2 (production) -- brute-force nearest neighbour: FP32 filter scan + exact FP64 resolve.
 //
 // Replaces the KD-tree 1-NN of Open3D (verfication.py:97,99; icp.py:97-103,113,115) and
-// sklearn (choosePose.py:21-22).  Every (query, target) pair is still visited -- this is
-// brute force -- but the per-pair work is the cheapest FP32 form that can be made exact:
+// sklearn (choosePose.py:21-22).  Tiled brute force: a (256-query warp block, 64-target
+// sub-tile) pair is either scanned completely or -- when the target carries bounding spheres
+// and pruning is on -- skipped because the sphere proves that none of its points can beat
+// (or tie) the exact neighbour already found for any of the warp's queries.  With pruning
+// off every pair is visited.  The per-pair work is the cheapest FP32 form that can be made
+// exact:
 //
 //   scan    a_j = fma(-2qx, px, fma(-2qy, py, fma(-2qz, pz, |p_j|^2)))   ~ d_j^2 - |q|^2
 //           3 FFMA per pair (packed: 3 FFMA2 per target pair) + 1/2 FMNMX3, all on the
@@ -22,6 +26,21 @@
 // so j*'s sub-tile is flagged and j* is inside the window: it is always resolved exactly.
 // The returned index therefore equals the float64 brute-force argmin of the prepared
 // (hi+lo) coordinates; the returned d2 is that FP64 distance rounded once to float32.
+//
+// Pruning (PRUNE variant).  Clouds are stored in Morton order, so a warp's 256 queries, a
+// 1024-target stage and a 64-target sub-tile are all compact patches.  Every query carries
+// dq >= its exact best distance so far (FP64 Dbest from the resolve path, rounded up, plus
+// the size of its lo part); a tile with sphere (c, r) is skipped by a warp iff for every
+// query |q - c| > dq + r (evaluated in FP32 with a 1e-4 relative margin, the sphere radius
+// being inflated by prepare.cu for rounding and for the targets' lo parts): then every point
+// of the tile is strictly farther than the neighbour already held, so it can be neither the
+// minimum nor an equal-distance tie.  Order of work per CTA: (1) the stage nearest to the
+// query block, each warp starting with its nearest sub-tile, which gives every query a
+// near-final bound; (2) a list of the stages whose sphere comes within the CTA-wide bound
+// (all others are never even loaded); (3) those stages, each warp testing the stage sphere
+// and then the 16 sub-tile spheres, which ride along with the stage in shared memory.
+// The exactness argument above is untouched: the true neighbour's tile is never skipped
+// (its distance is <= every bound), so it is visited, flagged and resolved as before.
 //
 // Roofline: FP32 CUDA cores.  Algorithmic work stays 8 flop per pair;
 // executed FP32-pipe work is 3 lane-ops per pair, so the algorithmic rate can exceed the
@@ -58,7 +77,28 @@ struct NN2Params {
     const int *perm_q;       // stored position -> original index (NULL = identity)
     const int *perm_t;
     unsigned long long *dbg;  // tuning only: event counters
+    const float4 *sub_c;     // [batch][stages_total * STAGE/SUB] sub-tile spheres (PRUNE)
+    long long sub_c_bstride;
+    unsigned long long *evaluated;  // profiling: scanned (warp, sub-tile) units, or NULL
 };
+
+// Can this lane rule out every point of the tile with sphere S for all of its Q queries?
+// q2* = -2 * query (hi part); dmax >= best distance so far of each of the lane's live queries
+// (0 for a lane without live queries, whose padded coordinates are far from everything).
+template <int Q>
+__device__ __forceinline__ bool lane_rules_out(const float4 S, const float (&q2x)[Q],
+                                               const float (&q2y)[Q], const float (&q2z)[Q],
+                                               float dmax) {
+    float m = CUDART_INF_F;
+#pragma unroll
+    for (int r = 0; r < Q; ++r) {
+        const float dx = fmaf(q2x[r], -0.5f, -S.x), dy = fmaf(q2y[r], -0.5f, -S.y),
+                    dz = fmaf(q2z[r], -0.5f, -S.z);
+        m = fminf(m, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    }
+    const float rr = (dmax + S.w) * 1.0001f;
+    return S.w < 0.f || m > rr * rr;
+}
 
 // Upper threshold for "could still be the nearest neighbour": running minimum + window.
 // mt = running min of a (~ d^2 - |q|^2), nq2 = |q|^2, qn = |q| (float32, hi part).
@@ -73,16 +113,25 @@ __device__ __forceinline__ float filter_threshold(float mt, float nq2, float qn)
     return __fadd_ru(mt, W);
 }
 
-template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR>
+constexpr int kListCap = 512;  // stages a pruning CTA can list; more -> it walks all of them
+
+template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR, bool PRUNE>
 __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
     static_assert(STAGE % SUB == 0 && SUB % 8 == 0 && Q <= 16, "tile shapes");
+    static_assert(!PRUNE || (SUB == ISR_SUB_TILE && STAGE == ISR_SOA_TILE && STAGE / SUB <= 32),
+                  "pruning uses the spheres of prepare.cu");
+    constexpr int SUBS = STAGE / SUB;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int SLOT_F = 4 * STAGE + (PRUNE ? 4 * SUBS : 0);  // floats per pipeline slot
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *sbuf = reinterpret_cast<float *>(smem_raw);  // [NSTAGES][4][STAGE]
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSTAGES * 4 * STAGE * 4);
+    float *sbuf = reinterpret_cast<float *>(smem_raw);  // [NSTAGES][4][STAGE] (+ [SUBS] spheres)
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSTAGES * SLOT_F * 4);
+    int *slist = reinterpret_cast<int *>(full + NSTAGES);  // [kListCap], PRUNE only
 
     const int b = blockIdx.z;
     if (p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) return;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const float *__restrict__ gq = p.q + (long long)b * p.q_bstride;
     const float *__restrict__ gt = p.t + (long long)b * p.t_bstride;
     const int s_begin = blockIdx.y * p.stages_per_split;
@@ -102,37 +151,47 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
     float mt_l[Q], thr_l[Q], tm_l[Q];
     double Dbest_l[Q];
     int ibest_l[Q];
-    const int q0 = blockIdx.x * (THREADS * Q);
+    // a warp owns 32*Q consecutive stored queries (a compact patch under Morton order);
+    // lane l holds queries l, 32+l, ...: every load below is one coalesced 128-byte line
+    const int q0 = blockIdx.x * (THREADS * Q) + warp * (32 * Q) + lane;
+    float dq_l[Q];       // PRUNE: per-query upper bound of the best distance so far
+    float dmax = 0.f;    // PRUNE: max of dq_l over the lane's live queries
 #pragma unroll
     for (int r = 0; r < Q; ++r) {
-        const int i = min(q0 + r * THREADS + tid, p.nq_pad - 1);
+        const int i = min(q0 + r * 32, p.nq_pad - 1);
         q2x[r] = -2.0f * gq[i];
         q2y[r] = -2.0f * gq[p.nq_pad + i];
         q2z[r] = -2.0f * gq[2ll * p.nq_pad + i];
         // padded query slots (i >= nq) must never reach the resolve path: their 1e18
         // coordinates would put every target inside the error window
-        const bool live = (q0 + r * THREADS + tid < p.nq) && !p.debug_no_resolve;
+        const bool live = (q0 + r * 32 < p.nq) && !p.debug_no_resolve;
         thr[r] = live ? CUDART_INF_F : -CUDART_INF_F;
+        if (PRUNE && q0 + r * 32 < p.nq) dmax = CUDART_INF_F;
     }
     for (int r = 0; r < Q; ++r) {  // run-time loop on purpose
         mt_l[r] = CUDART_INF_F;
-        thr_l[r] = (q0 + r * THREADS + tid < p.nq) && !p.debug_no_resolve ? CUDART_INF_F : -CUDART_INF_F;
+        thr_l[r] = (q0 + r * 32 < p.nq) && !p.debug_no_resolve ? CUDART_INF_F : -CUDART_INF_F;
         Dbest_l[r] = CUDART_INF;
         ibest_l[r] = s_begin * STAGE;
+        if (PRUNE) dq_l[r] = (q0 + r * 32 < p.nq) ? CUDART_INF_F : 0.f;
     }
 
-    // Scan order: the target stage whose centroid is nearest to this CTA's query block goes
+    // Scan order: the target stage whose centre is nearest to this CTA's query block goes
     // first (clouds are stored in Morton order, so both are compact patches).  After that
     // one stage every query already holds a near-final bound and the remaining stages
-    // almost never reach the resolve path.  The rest follows in ascending order.
+    // almost never reach the resolve path.  The rest follows in ascending order, or -- when
+    // pruning -- only the listed stages follow.
     int s_first = 0;
-    if (p.stage_c != nullptr && nst > 1) {
-        __shared__ float cred[4][THREADS / 32];
-        __shared__ u64 sred[THREADS / 32];
+    float cQx = 0.f, cQy = 0.f, cQz = 0.f, rQ = 0.f;  // PRUNE: query-block sphere
+    float cWx = 0.f, cWy = 0.f, cWz = 0.f;            // PRUNE: this warp's query centroid
+    __shared__ float cred[4][WARPS];
+    __shared__ u64 sred[WARPS];
+    __shared__ int scount;
+    if (p.stage_c != nullptr && (nst > 1 || PRUNE)) {
         float cx = 0.f, cy = 0.f, cz = 0.f, cn = 0.f;
 #pragma unroll
         for (int r = 0; r < Q; ++r) {
-            if (q0 + r * THREADS + tid < p.nq) {
+            if (q0 + r * 32 < p.nq) {
                 cx += q2x[r]; cy += q2y[r]; cz += q2z[r]; cn += 1.f;
             }
         }
@@ -143,13 +202,17 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
             cz += __shfl_xor_sync(0xffffffffu, cz, o);
             cn += __shfl_xor_sync(0xffffffffu, cn, o);
         }
-        if ((tid & 31) == 0) {
-            cred[0][tid >> 5] = cx; cred[1][tid >> 5] = cy; cred[2][tid >> 5] = cz; cred[3][tid >> 5] = cn;
+        if (PRUNE) {
+            const float invw = cn > 0.f ? -0.5f / cn : 0.f;  // q2 = -2 * query
+            cWx = cx * invw; cWy = cy * invw; cWz = cz * invw;
+        }
+        if (lane == 0) {
+            cred[0][warp] = cx; cred[1][warp] = cy; cred[2][warp] = cz; cred[3][warp] = cn;
         }
         __syncthreads();
         cx = cy = cz = cn = 0.f;
 #pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) {
+        for (int w = 0; w < WARPS; ++w) {
             cx += cred[0][w]; cy += cred[1][w]; cz += cred[2][w]; cn += cred[3][w];
         }
         const float inv = cn > 0.f ? -0.5f / cn : 0.f;  // q2 = -2 * query
@@ -168,42 +231,110 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
             const u64 other = __shfl_xor_sync(0xffffffffu, best, o);
             best = other < best ? other : best;
         }
-        if ((tid & 31) == 0) sred[tid >> 5] = best;
+        if (lane == 0) sred[warp] = best;
+        if (PRUNE) {
+            // radius of the query block about (cx, cy, cz), live queries only
+            float m = 0.f;
+#pragma unroll
+            for (int r = 0; r < Q; ++r) {
+                if (q0 + r * 32 < p.nq) {
+                    const float dx = fmaf(q2x[r], -0.5f, -cx), dy = fmaf(q2y[r], -0.5f, -cy),
+                                dz = fmaf(q2z[r], -0.5f, -cz);
+                    m = fmaxf(m, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            __syncthreads();  // cred is reused
+            if (lane == 0) cred[0][warp] = m;
+            if (tid == 0) scount = 0;
+        }
         __syncthreads();
         best = sred[0];
 #pragma unroll
-        for (int w = 1; w < THREADS / 32; ++w) best = sred[w] < best ? sred[w] : best;
+        for (int w = 1; w < WARPS; ++w) best = sred[w] < best ? sred[w] : best;
         s_first = (int)(unsigned)(best & 0xffffffffull);
         if (s_first >= nst) s_first = 0;
+        if (PRUNE) {
+            float m = cred[0][0];
+#pragma unroll
+            for (int w = 1; w < WARPS; ++w) m = fmaxf(m, cred[0][w]);
+            cQx = cx; cQy = cy; cQz = cz;
+            rQ = __fsqrt_ru(m) * 1.00002f;
+        }
     }
-    auto stage_of = [&](int pos) { return pos == 0 ? s_first : (pos - 1 < s_first ? pos - 1 : pos); };
+    // pipeline position -> stage (relative to s_begin).  Position 0 is s_first; then either
+    // all other stages in ascending order or (PRUNE, after the list is built) the list.
+    bool use_list = false;
+    int npos = PRUNE ? 1 : nst;
+    auto stage_of = [&](int pos) {
+        if (pos == 0) return s_first;
+        if (PRUNE && use_list) return slist[pos - 1];
+        return pos - 1 < s_first ? pos - 1 : pos;
+    };
 
     auto issue = [&](int sl) {
         const int slot = sl % NSTAGES;
-        float *dst = sbuf + (size_t)slot * 4 * STAGE;
-        const float *src = gt + (long long)(s_begin + stage_of(sl)) * STAGE;
-        mbar_expect_tx(&full[slot], 4u * STAGE * 4u);
+        float *dst = sbuf + (size_t)slot * SLOT_F;
+        const int stg = s_begin + stage_of(sl);
+        const float *src = gt + (long long)stg * STAGE;
+        mbar_expect_tx(&full[slot], 4u * STAGE * 4u + (PRUNE ? SUBS * 16u : 0u));
 #pragma unroll
         for (int pl = 0; pl < 4; ++pl)
             bulk_g2s(dst + pl * STAGE, src + (long long)pl * p.nt_pad, STAGE * 4u, &full[slot]);
+        if (PRUNE)
+            bulk_g2s(dst + 4 * STAGE, p.sub_c + (long long)b * p.sub_c_bstride + (long long)stg * SUBS,
+                     SUBS * 16u, &full[slot]);
     };
     if (tid == 0) {
-        for (int i = 0; i < NSTAGES - 1 && i < nst; ++i) issue(i);
+        for (int i = 0; i < NSTAGES - 1 && i < npos; ++i) issue(i);
     }
-
+    unsigned nscanned = 0;  // (warp, sub-tile) units this warp evaluated
 
     // (A per-slot `empty` mbarrier instead of the CTA barrier below was measured 2 % slower:
     // the 5 % of samples parked at the barrier are warps that would otherwise only run ahead.)
-    for (int sl = 0; sl < nst; ++sl) {
-        if (tid == 0 && sl + NSTAGES - 1 < nst) issue(sl + NSTAGES - 1);
+    for (int sl = 0; sl < npos; ++sl) {
+        if (tid == 0 && sl + NSTAGES - 1 < npos) issue(sl + NSTAGES - 1);
         const int slot = sl % NSTAGES;
+        bool skip_stage = false;
+        if (PRUNE && sl > 0) {
+            // the whole stage first: one sphere test per warp (the sphere comes from L2
+            // while the stage's bulk copy is still in flight)
+            const float4 S = p.stage_c[(long long)b * p.stage_c_bstride + s_begin + stage_of(sl)];
+            skip_stage = __all_sync(0xffffffffu, lane_rules_out<Q>(S, q2x, q2y, q2z, dmax));
+        }
         mbar_wait(&full[slot], (sl / NSTAGES) & 1);
-        const float4 *sx = reinterpret_cast<const float4 *>(sbuf + (size_t)slot * 4 * STAGE);
+        const float4 *sx = reinterpret_cast<const float4 *>(sbuf + (size_t)slot * SLOT_F);
         const float4 *sy = sx + STAGE / 4;
         const float4 *sz = sy + STAGE / 4;
         const float4 *sn = sz + STAGE / 4;
+        const float4 *ssph = sn + STAGE / 4;  // PRUNE: the stage's SUBS sub-tile spheres
+        int sub_first = 0;
+        if (PRUNE && sl == 0) {
+            // no bound yet: start with the sub-tile nearest to this warp's queries
+            float d = CUDART_INF_F;
+            if (lane < SUBS) {
+                const float4 S = ssph[lane];
+                const float dx = S.x - cWx, dy = S.y - cWy, dz = S.z - cWz;
+                d = S.w < 0.f ? CUDART_INF_F : dx * dx + dy * dy + dz * dz;
+            }
+            u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(unsigned)lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const u64 other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other < key ? other : key;
+            }
+            sub_first = (int)(unsigned)(key & 31ull);
+            if (sub_first >= SUBS) sub_first = 0;
+        }
 #pragma unroll 1
-        for (int sub = 0; sub < STAGE / SUB; ++sub) {
+        for (int k = 0; k < (skip_stage ? 0 : SUBS); ++k) {
+            int sub = k;
+            if (PRUNE) {
+                if (sl == 0) sub = k == 0 ? sub_first : (k <= sub_first ? k - 1 : k);
+                if (__all_sync(0xffffffffu, lane_rules_out<Q>(ssph[sub], q2x, q2y, q2z, dmax))) continue;
+            }
+            ++nscanned;
             float tm[Q];
 #pragma unroll
             for (int r = 0; r < Q; ++r) tm[r] = CUDART_INF_F;
@@ -272,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
                         if ((int)(__ffs(am) - 1) == (tid & 31)) atomicAdd(p.dbg + 2, 1ull);  // warp-level resolve passes
                     }
 #endif
-                    const int qi = min(q0 + r * THREADS + tid, p.nq_pad - 1);
+                    const int qi = min(q0 + r * 32, p.nq_pad - 1);
                     const float qhx = gq[qi], qhy = gq[p.nq_pad + qi], qhz = gq[2ll * p.nq_pad + qi];
                     const float cx = -2.0f * qhx, cy = -2.0f * qhy, cz = -2.0f * qhz;
                     const float nq2 = __fmaf_rn(qhz, qhz, __fmaf_rn(qhy, qhy, qhx * qhx));
@@ -322,16 +453,61 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
                     }
                     Dbest_l[r] = Db;
                     ibest_l[r] = ib;
+                    // >= the exact best distance of the FP64 (hi + lo) query, rounded up
+                    if (PRUNE)
+                        dq_l[r] = __double2float_ru(sqrt(Db)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
                 }
 #pragma unroll
                 for (int r = 0; r < Q; ++r) thr[r] = thr_l[r];
+                if (PRUNE) {
+                    float m = 0.f;
+                    for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r]);  // run-time loop on purpose
+                    dmax = m;
+                }
             }
         }
         __syncthreads();  // every warp is done with this slot before it is refilled
+        if (PRUNE && sl == 0 && nst > 1) {
+            // every live query now holds a finite bound: list the stages that can still
+            // matter to any query of the block, |cQ - c| <= B + rQ + r.
+            float B = dmax;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) B = fmaxf(B, __shfl_xor_sync(0xffffffffu, B, o));
+            if (lane == 0) cred[1][warp] = B;
+            __syncthreads();
+            B = cred[1][0];
+#pragma unroll
+            for (int w = 1; w < WARPS; ++w) B = fmaxf(B, cred[1][w]);
+            const float4 *sc = p.stage_c + (long long)b * p.stage_c_bstride + s_begin;
+            for (int base = 0; base < nst; base += THREADS) {
+                const int sI = base + tid;
+                bool need = false;
+                if (sI < nst && sI != s_first) {
+                    const float4 c = sc[sI];
+                    const float dx = c.x - cQx, dy = c.y - cQy, dz = c.z - cQz;
+                    const float rr = (B + rQ + c.w) * 1.0001f;
+                    need = c.w >= 0.f && !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, need);
+                int at = 0;
+                if (lane == 0 && m != 0) at = atomicAdd(&scount, __popc(m));
+                at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+                if (need && at < kListCap) slist[at] = sI;
+            }
+            __syncthreads();
+            const int cnt = scount;
+            use_list = cnt <= kListCap;
+            npos = use_list ? 1 + cnt : nst;
+            if (tid == 0) {
+                for (int i = 1; i < NSTAGES - 1 + 1 && i < npos; ++i) issue(i);
+            }
+        }
     }
+    if (p.evaluated != nullptr && lane == 0 && nscanned != 0)
+        atomicAdd(p.evaluated, (unsigned long long)nscanned);
 
     for (int r = 0; r < Q; ++r) {
-        const int i = q0 + r * THREADS + tid;
+        const int i = q0 + r * 32;
         if (i < p.nq) {
             // report in the caller's original indexing
             const int io = p.perm_q != nullptr ? p.perm_q[i] : i;
@@ -371,14 +547,17 @@ __global__ void nn2_combine_kernel(const double *__restrict__ part_D, const int 
 }
 
 // ---- host-side launch ----------------------------------------------------------------
-template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR = 2>
+template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR = 2, bool PRUNE = false>
 struct NN2Variant {
     static constexpr int kQueriesPerCta = Q * THREADS;
     static constexpr int kStage = STAGE;
-    static constexpr size_t kSmem = (size_t)NSTAGES * 4 * STAGE * 4 + NSTAGES * 8;
+    static constexpr bool kPrune = PRUNE;
+    static constexpr size_t kSmem =
+        (size_t)NSTAGES * (4 * STAGE + (PRUNE ? 4 * (STAGE / SUB) : 0)) * 4 + NSTAGES * 8 +
+        (PRUNE ? kListCap * 4 : 0);
 
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
-        auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR>;
+        auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR, PRUNE>;
         static thread_local int configured_dev = -1;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -395,7 +574,7 @@ struct NN2Variant {
 
     static int ctas_per_sm() {
         int n = 0;
-        auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR>;
+        auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR, PRUNE>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS, kSmem) != cudaSuccess ||
             n < 1)
@@ -405,7 +584,35 @@ struct NN2Variant {
 };
 
 using NN2Main = NN2Variant<8, 128, 1024, 3, 64, 4, 1>;
+using NN2Pruned = NN2Variant<8, 128, 1024, 3, 64, 4, 1, true>;
 constexpr int kMaxSplits = 32;
+
+// process-wide pruning switch and profiling counters (isr.h)
+static std::atomic<int> g_prune{-1};
+static std::atomic<unsigned long long> g_answered{0};
+static unsigned long long *g_evaluated_dev[64] = {nullptr};  // per device, allocated on first use
+
+static bool pruning_on() {
+    int v = g_prune.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("ISR_NN_PRUNE");
+        v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+        g_prune.store(v);
+    }
+    return v != 0;
+}
+
+static unsigned long long *evaluated_counter() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (g_evaluated_dev[dev] == nullptr) {
+        unsigned long long *ptr = nullptr;
+        if (cudaMalloc(&ptr, 64) != cudaSuccess) return nullptr;
+        cudaMemset(ptr, 0, 64);
+        g_evaluated_dev[dev] = ptr;
+    }
+    return g_evaluated_dev[dev];
+}
 constexpr int kSlotsUpperBound = 148 * 8;  // for workspace sizing without a device
 
 static int choose_splits(long long ctas, int stages, int slots) {
@@ -438,7 +645,8 @@ static int nn2_dispatch(const NN2Call &c) {
     const int stages = (int)(c.t->npad / V::kStage);
     static thread_local int slots = 0;
     if (slots == 0) slots = sm_count() * V::ctas_per_sm();
-    int splits = choose_splits((long long)nqb * c.batch, stages, slots);
+    // a pruning CTA needs the whole target range: its bound comes from the nearest stage
+    int splits = V::kPrune ? 1 : choose_splits((long long)nqb * c.batch, stages, slots);
     const int per = (stages + splits - 1) / splits;
     splits = (stages + per - 1) / per;  // no empty split
 
@@ -451,6 +659,14 @@ static int nn2_dispatch(const NN2Call &c) {
     p.stage_c = (V::kStage == ISR_SOA_TILE) ? reinterpret_cast<const float4 *>(c.t->stage_c) : nullptr;
     p.stage_c_bstride = c.t->bstride == 0 ? 0 : c.t->npad / ISR_SOA_TILE;
     p.perm_q = c.q->perm; p.perm_t = c.t->perm;
+    p.sub_c = reinterpret_cast<const float4 *>(c.t->sub_c);
+    p.sub_c_bstride = c.t->bstride == 0 ? 0 : c.t->npad / ISR_SUB_TILE;
+    p.evaluated = nullptr;
+    if (prof_enabled()) {
+        p.evaluated = evaluated_counter();
+        g_answered.fetch_add((unsigned long long)nq * (unsigned long long)c.t->n *
+                             (unsigned long long)c.batch);
+    }
     p.dbg = nullptr;
 #ifdef ISR_NN_TUNING
     {
@@ -577,7 +793,33 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
         default: break;
     }
 #endif
+    if (t->sub_c != nullptr && t->stage_c != nullptr && pruning_on()) {
+        ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
+        return nn2_dispatch<NN2Pruned>(c);
+    }
     return nn2_dispatch<NN2Main>(c);
+}
+
+int isr_set_nn_pruning(int on) {
+    isr::g_prune.store(on != 0 ? 1 : 0);
+    return ISR_OK;
+}
+
+int isr_get_nn_pruning(void) { return isr::pruning_on() ? 1 : 0; }
+
+int isr_profile_nn_pairs(uint64_t *evaluated_host, uint64_t *answered_host) {
+    using namespace isr;
+    unsigned long long units = 0;
+    unsigned long long *ctr = evaluated_counter();
+    if (ctr != nullptr) {
+        ISR_TRY(check_cuda(cudaDeviceSynchronize(), "profile_nn_pairs sync"));
+        ISR_TRY(check_cuda(cudaMemcpy(&units, ctr, 8, cudaMemcpyDeviceToHost), "profile_nn_pairs read"));
+        ISR_TRY(check_cuda(cudaMemset(ctr, 0, 8), "profile_nn_pairs clear"));
+    }
+    // one unit = one warp block of 32 x 8 queries against one 64-target sub-tile
+    if (evaluated_host) *evaluated_host = (uint64_t)units * 256ull * (uint64_t)ISR_SUB_TILE;
+    if (answered_host) *answered_host = (uint64_t)g_answered.exchange(0);
+    return ISR_OK;
 }
 
 }  // extern "C"

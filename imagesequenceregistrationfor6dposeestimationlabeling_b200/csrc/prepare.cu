@@ -133,38 +133,107 @@ prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts
     }
 }
 
-// centroid of the real points of every 1024-point SoA tile ("stage"): grid (stages, batch)
+// Bounding spheres of the stored tiles, for the bound-pruned scan of nn2.cu: one sphere per
+// 1024-point stage and one per 64-point sub-tile (ISR_SUB_TILE), each (cx, cy, cz, r) with the
+// centre at the middle of the tile's bounding box and r >= max |p - c| over the tile's real
+// points -- inflated so that the bound also holds for the FP64 (hi + lo) coordinates and
+// survives the float32 evaluation here.  A tile without real points gets r = -1 and a far
+// centre (never scanned first, always pruned).  grid (stages, batch), 256 threads; thread t
+// owns points 4t..4t+3 of the stage, so a sub-tile is 16 consecutive lanes.
 __global__ void __launch_bounds__(256)
-stage_centroid_kernel(const float *__restrict__ soa7, int64_t n, int64_t npad, int64_t bstride,
-                      float4 *__restrict__ out) {
-    __shared__ float red[4][8];
-    const int s = blockIdx.x, b = blockIdx.y;
-    const float *base = soa7 + (int64_t)b * bstride + (int64_t)s * ISR_SOA_TILE;
-    float cx = 0.f, cy = 0.f, cz = 0.f, cn = 0.f;
-    for (int k = threadIdx.x; k < ISR_SOA_TILE; k += 256) {
-        if ((int64_t)s * ISR_SOA_TILE + k < n) {
-            cx += base[k]; cy += base[npad + k]; cz += base[2 * npad + k]; cn += 1.f;
+tile_spheres_kernel(const float *__restrict__ soa7, int64_t n, int64_t npad, int64_t bstride,
+                    float4 *__restrict__ out_stage, float4 *__restrict__ out_sub) {
+    constexpr int kSubs = ISR_SOA_TILE / ISR_SUB_TILE;  // 16
+    __shared__ float red[6][8];
+    __shared__ float rmax[8];
+    const int s = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+    const float *base = soa7 + (int64_t)b * bstride + (int64_t)s * ISR_SOA_TILE + 4 * t;
+    const float4 X = *reinterpret_cast<const float4 *>(base);
+    const float4 Y = *reinterpret_cast<const float4 *>(base + npad);
+    const float4 Z = *reinterpret_cast<const float4 *>(base + 2 * npad);
+    const float px[4] = {X.x, X.y, X.z, X.w}, py[4] = {Y.x, Y.y, Y.z, Y.w}, pz[4] = {Z.x, Z.y, Z.z, Z.w};
+    const int64_t g0 = (int64_t)s * ISR_SOA_TILE + 4 * t;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (g0 + k < n) {
+            lo[0] = fminf(lo[0], px[k]); hi[0] = fmaxf(hi[0], px[k]);
+            lo[1] = fminf(lo[1], py[k]); hi[1] = fmaxf(hi[1], py[k]);
+            lo[2] = fminf(lo[2], pz[k]); hi[2] = fmaxf(hi[2], pz[k]);
         }
     }
+    // ---- sub-tile: 16 lanes --------------------------------------------------------------
+    float slo[3], shi[3];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        cx += __shfl_xor_sync(0xffffffffu, cx, o);
-        cy += __shfl_xor_sync(0xffffffffu, cy, o);
-        cz += __shfl_xor_sync(0xffffffffu, cz, o);
-        cn += __shfl_xor_sync(0xffffffffu, cn, o);
+    for (int d = 0; d < 3; ++d) {
+        slo[d] = lo[d]; shi[d] = hi[d];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            slo[d] = fminf(slo[d], __shfl_xor_sync(0xffffffffu, slo[d], o));
+            shi[d] = fmaxf(shi[d], __shfl_xor_sync(0xffffffffu, shi[d], o));
+        }
     }
-    if ((threadIdx.x & 31) == 0) {
-        red[0][threadIdx.x >> 5] = cx; red[1][threadIdx.x >> 5] = cy;
-        red[2][threadIdx.x >> 5] = cz; red[3][threadIdx.x >> 5] = cn;
+    auto radius2 = [&](float cx, float cy, float cz) {
+        float m = -1.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (g0 + k < n) {
+                const float dx = px[k] - cx, dy = py[k] - cy, dz = pz[k] - cz;
+                m = fmaxf(m, dx * dx + dy * dy + dz * dz);
+            }
+        }
+        return m;
+    };
+    // r = sqrt(max d2) rounded up, + the lo parts of the points (|lo| <= 2^-24 |hi| per
+    // component) and of the evaluation, relative to the tile's distance from the origin
+    auto inflate = [](float m2, float cx, float cy, float cz) {
+        const float r = __fsqrt_ru(m2) * 1.00002f;
+        const float cn = __fsqrt_ru(cx * cx + cy * cy + cz * cz);
+        return r + 1e-6f * (cn + r) + 1e-37f;
+    };
+    {
+        const bool any = slo[0] <= shi[0];
+        const float cx = 0.5f * (slo[0] + shi[0]), cy = 0.5f * (slo[1] + shi[1]), cz = 0.5f * (slo[2] + shi[2]);
+        float m = any ? radius2(cx, cy, cz) : -1.f;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((t & 15) == 0) {
+            out_sub[((int64_t)b * gridDim.x + s) * kSubs + (t >> 4)] =
+                any ? make_float4(cx, cy, cz, inflate(m, cx, cy, cz))
+                    : make_float4(ISR_PAD_COORD, ISR_PAD_COORD, ISR_PAD_COORD, -1.f);
+        }
+    }
+    // ---- stage: whole CTA ----------------------------------------------------------------
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        slo[d] = fminf(slo[d], __shfl_xor_sync(0xffffffffu, slo[d], 16));
+        shi[d] = fmaxf(shi[d], __shfl_xor_sync(0xffffffffu, shi[d], 16));
+    }
+    if ((t & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { red[d][t >> 5] = slo[d]; red[3 + d][t >> 5] = shi[d]; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        cx = cy = cz = cn = 0.f;
-        for (int w = 0; w < 8; ++w) { cx += red[0][w]; cy += red[1][w]; cz += red[2][w]; cn += red[3][w]; }
-        const float inv = cn > 0.f ? 1.f / cn : 0.f;
-        // an all-padding tile gets a far-away centroid so it is never chosen first
-        out[(int64_t)b * gridDim.x + s] = cn > 0.f ? make_float4(cx * inv, cy * inv, cz * inv, cn)
-                                                   : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        slo[d] = red[d][0]; shi[d] = red[3 + d][0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { slo[d] = fminf(slo[d], red[d][w]); shi[d] = fmaxf(shi[d], red[3 + d][w]); }
+    }
+    const bool any = slo[0] <= shi[0];
+    const float cx = 0.5f * (slo[0] + shi[0]), cy = 0.5f * (slo[1] + shi[1]), cz = 0.5f * (slo[2] + shi[2]);
+    float m = any ? radius2(cx, cy, cz) : -1.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((t & 31) == 0) rmax[t >> 5] = m;
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, rmax[w]);
+        out_stage[(int64_t)b * gridDim.x + s] =
+            any ? make_float4(cx, cy, cz, inflate(m, cx, cy, cz))
+                : make_float4(ISR_PAD_COORD, ISR_PAD_COORD, ISR_PAD_COORD, -1.f);
     }
 }
 
@@ -181,18 +250,20 @@ int isr_centroid(const float *pts, int64_t n, double *out3, void *stream) {
     return launched("centroid_kernel");
 }
 
-int isr_stage_centroids(const float *soa7, int64_t n, int64_t npad, int64_t bstride, int64_t batch,
-                        float *out, void *stream) {
+int isr_tile_spheres(const float *soa7, int64_t n, int64_t npad, int64_t bstride, int64_t batch,
+                     float *out_stage, float *out_sub, void *stream) {
     using namespace isr;
-    ISR_REQUIRE(soa7 && out && n >= 0 && npad >= n && npad % ISR_SOA_TILE == 0 && npad > 0 && batch >= 1,
-                ISR_E_INVALID_ARG, "stage_centroids: bad argument");
-    ISR_REQUIRE(batch <= 65535, ISR_E_SHAPE, "stage_centroids: batch > 65535");
-    ISR_REQUIRE(aligned16(out), ISR_E_ALIGN, "stage_centroids: out not 16-byte aligned");
+    ISR_REQUIRE(soa7 && out_stage && out_sub && n >= 0 && npad >= n && npad % ISR_SOA_TILE == 0 &&
+                    npad > 0 && batch >= 1,
+                ISR_E_INVALID_ARG, "tile_spheres: bad argument");
+    ISR_REQUIRE(batch <= 65535, ISR_E_SHAPE, "tile_spheres: batch > 65535");
+    ISR_REQUIRE(aligned16(out_stage) && aligned16(out_sub) && aligned16(soa7) && bstride % 4 == 0,
+                ISR_E_ALIGN, "tile_spheres: pointers must be 16-byte aligned");
     dim3 grid((unsigned)(npad / ISR_SOA_TILE), (unsigned)batch);
     ProfScope prof(kProfTransform, (cudaStream_t)stream);
-    stage_centroid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(soa7, n, npad, bstride,
-                                                                   reinterpret_cast<float4 *>(out));
-    return launched("stage_centroid_kernel");
+    tile_spheres_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        soa7, n, npad, bstride, reinterpret_cast<float4 *>(out_stage), reinterpret_cast<float4 *>(out_sub));
+    return launched("tile_spheres_kernel");
 }
 
 int isr_prepare_cloud(const float *pts, const float *pts_lo, const int32_t *perm, int64_t n,

@@ -47,6 +47,7 @@ extern "C" {
 #define ISR_E_WORKSPACE (-5)
 
 #define ISR_SOA_TILE 1024      /* SoA planes are padded to a multiple of this        */
+#define ISR_SUB_TILE 64        /* pruning granularity inside a 1024-point stage      */
 #define ISR_PAD_COORD 1.0e18f  /* coordinate stored in padded slots (d2 ~ 3e36, finite) */
 
 /* ---- library / device --------------------------------------------------------------- */
@@ -123,9 +124,14 @@ int isr_prepare_cloud(const float *pts, const float *pts_lo, const int32_t *perm
                       float *out_soa7, int64_t npad, const int32_t *skip, int64_t skip_stride,
                       void *stream);
 
-/* out[b][npad/1024][4] = (x, y, z, count) centroid of every 1024-point tile of a SoA7 cloud. */
-int isr_stage_centroids(const float *soa7, int64_t n, int64_t npad, int64_t bstride,
-                        int64_t batch, float *out, void *stream);
+/* Bounding spheres of the stored tiles of a SoA7 cloud, (cx, cy, cz, r) float32 each:
+ * out_stage [batch][npad/1024] for the 1024-point stages, out_sub [batch][npad/64] for the
+ * 64-point sub-tiles.  r bounds |p - c| for every real point of the tile, inflated to hold
+ * for the FP64 (hi + lo) coordinates; r = -1 marks a tile of padding only.  The search uses
+ * them to scan the nearest stage first and to skip tiles that provably cannot hold a
+ * query's nearest neighbour (what the KD-tree of Open3D / sklearn does by construction). */
+int isr_tile_spheres(const float *soa7, int64_t n, int64_t npad, int64_t bstride, int64_t batch,
+                     float *out_stage, float *out_sub, void *stream);
 
 /* A prepared cloud (or batch of clouds) as the search kernel sees it. */
 typedef struct IsrCloud {
@@ -133,13 +139,28 @@ typedef struct IsrCloud {
     int64_t n;            /* real points                                                      */
     int64_t npad;         /* padded plane length (multiple of ISR_SOA_TILE)                   */
     int64_t bstride;      /* floats between batch items; 0 = one cloud shared by the batch    */
-    const float *stage_c; /* isr_stage_centroids output, or NULL (scan in storage order)      */
+    const float *stage_c; /* isr_tile_spheres out_stage, or NULL (scan in storage order)      */
     const int32_t *perm;  /* the perm it was prepared with, or NULL; results are reported in
                              original indices either way                                      */
+    const float *sub_c;   /* isr_tile_spheres out_sub, or NULL (no tile pruning: every pair is
+                             evaluated); only read when this cloud is the target             */
 } IsrCloud;
 
-/* Brute-force exact 1-NN of every query in its target: FP32 3-FMA filter over every pair,
- * FP64 resolve of the few targets inside the proven error window (nn2.cu).  out_idx
+/* Process-wide switch for the tile pruning of isr_nn2 (default on).  Off = exhaustive brute
+ * force: every (query, target) pair goes through the FP32 scan.  Results are identical either
+ * way; bench.py uses it to time the exhaustive kernel against its FP32 roofline. */
+int isr_set_nn_pruning(int on);
+int isr_get_nn_pruning(void);
+
+/* While isr_profile_enable(1): pairs the isr_nn2 launches actually evaluated (scanned
+ * sub-tiles x queries, padded lanes included) and the pairs they answered for (nq x nt x
+ * batch).  Synchronises the device, then clears both counters. */
+int isr_profile_nn_pairs(uint64_t *evaluated_host, uint64_t *answered_host);
+
+/* Exact 1-NN of every query in its target by tiled brute force: FP32 3-FMA filter over the
+ * pairs of every tile that can hold the neighbour (all tiles when pruning is off or the
+ * target has no sub_c), FP64 resolve of the few targets inside the proven error window
+ * (nn2.cu).  out_idx
  * [batch][nq] equals the float64 brute-force argmin of the prepared coordinates (lowest
  * original index on exact ties); out_d2 is that FP64 squared distance rounded to float32.
  * use_lo == 0 ignores the lo planes (distances between the float32 hi coordinates).
@@ -190,7 +211,7 @@ typedef struct IsrIcpState {
  * source point, inlier uint8 [starts][ns] its correspondence flag.  States whose `done`
  * is set are skipped.  Prepared once per problem: `centroid` (device double[3], normally
  * isr_centroid(tgt)), tgt_cloud = the target through isr_spatial_order / isr_prepare_cloud
- * (identity pose, that centroid) / isr_stage_centroids, src_perm = isr_spatial_order(src)
+ * (identity pose, that centroid) / isr_tile_spheres, src_perm = isr_spatial_order(src)
  * (may be NULL).  src_lo (may be NULL) is the float32 low part of a float64 source.  This is GetRegistrationResultAndCorrespondences of Open3D's
  * RegistrationICP (icp.py:97-103, upstream). */
 size_t isr_icp_workspace_bytes(int64_t ns, int64_t nt, int64_t starts);

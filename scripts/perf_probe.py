@@ -65,3 +65,39 @@ if "icp" in which:
         prob.accumulate(20.0); prob.solve(prob.ns, 0.0, 0.0, False)
     best, med = timeit(one, reps=2)
     print(f"icp 1Mx1M one iteration: {best:.3f}s -> {1/best:.2f} it/s; {8e12/best/1e12:.2f} TF/s")
+
+if "prune" in which:
+    import ctypes
+    lib = _lib.load()
+    def pairs():
+        ev, an = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _lib.check(lib.isr_profile_nn_pairs(ctypes.byref(ev), ctypes.byref(an)))
+        return ev.value, an.value
+    N = 100000; B = int(os.environ.get("PROBE_B", "256"))
+    cloud = synth.make_cloud(N, 1)
+    R_true, _ = synth.true_pose(3)
+    Rs, _, k0 = synth.make_candidates(B, 10, R_true=R_true, t_true=np.zeros(3))
+    Mq, Mt = synth.verification_matrices(Rs, R_true)
+    cd = api._points(cloud, api._device()); Mqd = api._poses(Mq, api._device()); Mtd = api._poses(Mt, api._device())
+    res = {}
+    for on in (True, False):
+        api.set_nn_pruning(on)
+        best, med = timeit(lambda: isr.verify_poses(cd, Mqd, Mtd), reps=2)
+        lib.isr_profile_enable(1); pairs()
+        r = isr.verify_poses(cd, Mqd, Mtd); torch.cuda.synchronize()
+        ev, an = pairs(); lib.isr_profile_enable(0)
+        lib.isr_profile_collect(None, None)
+        res[on] = r.losses.cpu().numpy()
+        print(f"verify B={B} prune={on}: {best:.4f}s -> {B/best:.1f} cand/s; evaluated {ev:.3e} of {an:.3e} pairs ({ev/max(an,1)*100:.2f}%), {8*ev/best/1e12:.2f} TF/s on evaluated pairs; best {r.best_index} (k0 {k0})")
+    print("verify losses identical:", np.array_equal(res[True], res[False]))
+    src, tgt, _ = synth.icp_pair(1000000, 1000000, 4, 5)
+    for on in (True, False):
+        api.set_nn_pruning(on)
+        prob = isr.IcpProblem(src, tgt, np.eye(4)[None])
+        def one():
+            prob.accumulate(20.0); prob.solve(prob.ns, 0.0, 0.0, False)
+        best, med = timeit(one, reps=3 if on else 1, warm=1)
+        lib.isr_profile_enable(1); pairs(); one(); torch.cuda.synchronize(); ev, an = pairs(); lib.isr_profile_enable(0)
+        lib.isr_profile_collect(None, None)
+        print(f"icp 1Mx1M prune={on}: {best*1e3:.2f} ms/it -> {1/best:.1f} it/s; evaluated {ev/max(an,1)*100:.3f}% of pairs; T[0,:]={prob.results(False)[0].transformation[0]}")
+    api.set_nn_pruning(True)

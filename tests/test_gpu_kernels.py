@@ -142,6 +142,94 @@ def test_nn_indices_match_float64_oracle_on_surface_cloud(gpu):
         np.testing.assert_allclose(res.dist.cpu().numpy(), dk, rtol=1e-5, atol=1e-6)
 
 
+def test_tile_spheres_bound_their_points(gpu):
+    """Every stored point lies inside the sphere of its 64-point sub-tile and of its
+    1024-point stage (prepare.cu); padding-only tiles are marked r = -1."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api, synth
+    for n, offset in ((100000, 0.0), (5000, 700.0), (64, 0.0), (1, 3.0)):
+        cloud = synth.make_cloud(max(n, 8), seed=3)[:n] + np.float32(offset)
+        P = _rand_poses(3, n, trans=50.0)
+        c = api.prepare_cloud(cloud, P, perm=api.spatial_order(cloud), stage_centroids=True)
+        data = c.data.cpu().numpy().astype(np.float64)
+        pts = np.moveaxis(data[:, 0:3] + data[:, 4:7], 1, 2)            # [B, npad, 3] hi + lo
+        for spheres, tile in ((c.sub_c.cpu().numpy(), 64), (c.stage_c.cpu().numpy(), 1024)):
+            nt = c.npad // tile
+            assert spheres.shape == (3, nt, 4)
+            for b in range(3):
+                for k in range(nt):
+                    lo, hi = k * tile, min((k + 1) * tile, n)
+                    if hi <= lo:
+                        assert spheres[b, k, 3] == -1.0
+                        continue
+                    d = np.linalg.norm(pts[b, lo:hi] - spheres[b, k, :3].astype(np.float64), axis=1)
+                    assert d.max() <= spheres[b, k, 3]
+                    assert spheres[b, k, 3] <= d.max() * 1.001 + 1e-4 * (1 + abs(offset))
+
+
+@pytest.mark.parametrize("case", ["aligned", "rotated", "far_apart", "clusters", "lattice_ties",
+                                  "tiny_target", "camera_frame"])
+def test_nn_pruned_equals_exhaustive(gpu, case):
+    """Tile pruning only skips work: indices and d2 are bit-identical to the exhaustive scan
+    (and to the float64 brute-force oracle)."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api, synth
+    rng = np.random.default_rng(5)
+    if case == "aligned":
+        q, t = synth.make_cloud(30000, seed=1), synth.make_cloud(40000, seed=2)
+    elif case == "rotated":
+        t = synth.make_cloud(40000, seed=2)
+        q = (synth.make_cloud(30000, seed=1).astype(np.float64) @ synth.random_rotation(rng).T).astype(np.float32)
+    elif case == "far_apart":
+        q, t = synth.make_cloud(5000, seed=1) + np.float32(900.0), synth.make_cloud(20000, seed=2)
+    elif case == "clusters":
+        cen = rng.normal(scale=200, size=(40, 3))
+        t = (cen[rng.integers(0, 40, 30000)] + rng.normal(scale=2.0, size=(30000, 3))).astype(np.float32)
+        q = (cen[rng.integers(0, 40, 9000)] + rng.normal(scale=30.0, size=(9000, 3))).astype(np.float32)
+    elif case == "lattice_ties":
+        g = np.stack(np.meshgrid(np.arange(20), np.arange(20), np.arange(20), indexing="ij"), -1)
+        t = g.reshape(-1, 3).astype(np.float32)
+        t = np.concatenate([t, t[::-1]], axis=0)
+        q = (g.reshape(-1, 3) + 0.5).astype(np.float32)
+    elif case == "tiny_target":
+        q, t = synth.make_cloud(9000, seed=1), synth.make_cloud(100, seed=2)[:37]
+    else:
+        off = np.array([30, -20, 700], np.float32)
+        q, t = synth.make_cloud(20000, seed=1) + off, synth.make_cloud(70000, seed=2) + off
+    assert api.get_nn_pruning()
+    try:
+        pr = gpu.nearest_neighbors(q, t)
+        api.set_nn_pruning(False)
+        ex = gpu.nearest_neighbors(q, t)
+    finally:
+        api.set_nn_pruning(True)
+    np.testing.assert_array_equal(pr.idx.cpu().numpy(), ex.idx.cpu().numpy())
+    np.testing.assert_array_equal(pr.d2.cpu().numpy().view(np.uint32), ex.d2.cpu().numpy().view(np.uint32))
+    sub = rng.choice(len(q), size=min(len(q), 3000), replace=False)
+    rd2, ridx = c_oracle.nn_f64(q[sub], t)
+    np.testing.assert_array_equal(pr.idx.cpu().numpy()[sub], ridx)
+
+
+def test_verify_and_icp_pruned_equal_exhaustive(gpu):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api, synth
+    cloud = synth.make_cloud(20000, seed=1)
+    R_true, _ = synth.true_pose(3)
+    Rs, _, k0 = synth.make_candidates(24, seed=5, R_true=R_true, t_true=np.zeros(3))
+    Mq, Mt = synth.verification_matrices(Rs, R_true)
+    src, tgt, _ = synth.icp_pair(15000, 18000, 6, 7)
+    out = {}
+    try:
+        for on in (True, False):
+            api.set_nn_pruning(on)
+            v = gpu.verify_poses(cloud, Mq, Mt, mode="chamfer")
+            r = gpu.icp(src, tgt, np.eye(4), 20.0, max_iteration=8)
+            out[on] = (v.losses.cpu().numpy(), v.best_index, r.transformation, r.fitness, r.inlier_rmse,
+                       r.correspondence_set)
+    finally:
+        api.set_nn_pruning(True)
+    for a, b in zip(out[True], out[False]):
+        np.testing.assert_array_equal(np.asarray(a), np.asarray(b))   # bit-identical
+    assert out[True][1] == k0
+
+
 def test_nn_lattice_ties_pick_lowest_index(gpu):
     g = np.stack(np.meshgrid(np.arange(6), np.arange(6), np.arange(6), indexing="ij"), -1)
     t = g.reshape(-1, 3).astype(np.float32)
