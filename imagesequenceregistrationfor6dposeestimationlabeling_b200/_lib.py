@@ -80,6 +80,7 @@ SIGNATURES = {
     "isr_set_nn_pruning": (_I, [_I]),
     "isr_get_nn_pruning": (_I, []),
     "isr_profile_nn_pairs": (_I, [_P, _P]),
+    "isr_profile_nn_counters": (_I, [_P]),
     "isr_nn2_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "isr_nn2": (_I, [_P, _P, _I64, _I, _P, _P, _P, _I64, _P, _SZ, _P]),
     "isr_mean_sqrt": (_I, [_P, _I64, _I64, _P, _P]),

@@ -27,18 +27,22 @@
 // The returned index therefore equals the float64 brute-force argmin of the prepared
 // (hi+lo) coordinates; the returned d2 is that FP64 distance rounded once to float32.
 //
-// Pruning (PRUNE variant).  Clouds are stored in Morton order, so a warp's 256 queries, a
+// Pruning (nn2_pruned_kernel).  Clouds are stored in Morton order, so a warp's 256 queries, a
 // 1024-target stage and a 64-target sub-tile are all compact patches.  Every query carries
 // dq >= its exact best distance so far (FP64 Dbest from the resolve path, rounded up, plus
 // the size of its lo part); a tile with sphere (c, r) is skipped by a warp iff for every
 // query |q - c| > dq + r (evaluated in FP32 with a 1e-4 relative margin, the sphere radius
 // being inflated by prepare.cu for rounding and for the targets' lo parts): then every point
 // of the tile is strictly farther than the neighbour already held, so it can be neither the
-// minimum nor an equal-distance tie.  Order of work per CTA: (1) the stage nearest to the
-// query block, each warp starting with its nearest sub-tile, which gives every query a
-// near-final bound; (2) a list of the stages whose sphere comes within the CTA-wide bound
-// (all others are never even loaded); (3) those stages, each warp testing the stage sphere
-// and then the 16 sub-tile spheres, which ride along with the stage in shared memory.
+// minimum nor an equal-distance tie.  Every warp works on its own (no CTA barrier, its own
+// shared-memory ring fed by 1-D bulk copies): (1) seeds -- for four anchor queries spread
+// over its block, the sub-tile whose centre is nearest (via the nearest stage), scanned
+// first so that every query holds a near-final bound even when the block straddles a jump
+// of the Z-curve; (2) one pass over the stage spheres, keeping the stages that come within
+// the warp-wide bound of the warp's query sphere; their sub-tile spheres pass the same
+// coarse test into a FIFO; (3) each FIFO entry gets the exact per-query test with the
+// bounds of that moment and is scanned only if it survives.  Loads are issued up to four
+// entries ahead.
 // The exactness argument above is untouched: the true neighbour's tile is never skipped
 // (its distance is <= every bound), so it is visited, flagged and resolved as before.
 //
@@ -113,20 +117,176 @@ __device__ __forceinline__ float filter_threshold(float mt, float nq2, float qn)
     return __fadd_ru(mt, W);
 }
 
-constexpr int kListCap = 512;  // stages a pruning CTA can list; more -> it walks all of them
+// One (warp, sub-tile) unit: the FP32 filter scan of SUB targets against the warp's 32 x Q
+// queries, and the FP64 resolve of the flagged ones.  sx..sn point at the sub-tile's x, y,
+// z, |p|^2 values in shared memory; gbase is the stored index of its first target.  The
+// scan state (q2*, thr) lives in registers; the resolve state (mt_l .. dq_l) is indexed at
+// run time, which places it in (L1-resident) local memory and keeps it out of the scan's
+// registers.
+template <int Q, int SUB, int UNR, bool PRUNE>
+__device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__restrict__ gq,
+                                             const float *__restrict__ gt, int q0, int lane,
+                                             const float4 *sx, const float4 *sy, const float4 *sz,
+                                             const float4 *sn, int gbase, const float (&q2x)[Q],
+                                             const float (&q2y)[Q], const float (&q2z)[Q],
+                                             float (&thr)[Q], float *mt_l, float *thr_l,
+                                             float *tm_l, double *Dbest_l, int *ibest_l,
+                                             float *dq_l, float &dmax, unsigned &nflag,
+                                             unsigned &npass) {
+    float tm[Q];
+#pragma unroll
+    for (int r = 0; r < Q; ++r) tm[r] = CUDART_INF_F;
+#pragma unroll UNR
+    for (int g = 0; g < SUB / 4; ++g) {
+        const float4 X = sx[g];
+        const float4 Y = sy[g];
+        const float4 Z = sz[g];
+        const float4 N = sn[g];
+        const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+        const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+        const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+        const u64 n01 = pack2(N.x, N.y), n23 = pack2(N.z, N.w);
+        // level-major over the Q queries: consecutive FFMA2 are independent and share
+        // the target-pair operand (operand-reuse cache); the query rides as a scalar
+        u64 acc[Q];
+#pragma unroll
+        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2z[r], q2z[r]), z01, n01);
+#pragma unroll
+        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2y[r], q2y[r]), y01, acc[r]);
+#pragma unroll
+        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2x[r], q2x[r]), x01, acc[r]);
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            float a0, a1;
+            unpack2(acc[r], a0, a1);
+            tm[r] = min3(tm[r], a0, a1);
+        }
+#pragma unroll
+        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2z[r], q2z[r]), z23, n23);
+#pragma unroll
+        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2y[r], q2y[r]), y23, acc[r]);
+#pragma unroll
+        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2x[r], q2x[r]), x23, acc[r]);
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            float a0, a1;
+            unpack2(acc[r], a0, a1);
+            tm[r] = min3(tm[r], a0, a1);
+        }
+    }
+    unsigned flags = 0;
+#pragma unroll
+    for (int r = 0; r < Q; ++r) flags |= (tm[r] <= thr[r]) ? (1u << r) : 0u;
+    if (PRUNE && p.evaluated != nullptr) {  // profiling only
+        const unsigned mx = __reduce_max_sync(0xffffffffu, (unsigned)__popc(flags));
+        nflag += mx != 0 ? 1u : 0u;
+        npass += mx;
+    }
+    if (flags != 0) {
+#ifdef ISR_NN_TUNING
+        if (p.dbg != nullptr) {
+            const unsigned am = __activemask();
+            if ((int)(__ffs(am) - 1) == lane) atomicAdd(p.dbg + 0, 1ull);  // warp-level flagged sub-tiles
+            atomicAdd(p.dbg + 1, (unsigned long long)__popc(flags));            // (query, sub-tile) events
+        }
+#endif
+        // ---- resolve: rare, divergent; one pass serves every flagged lane ----------
+#pragma unroll
+        for (int r = 0; r < Q; ++r) tm_l[r] = tm[r];
+        for (unsigned f = flags; f != 0; f &= f - 1) {
+            const int r = __ffs(f) - 1;
+#ifdef ISR_NN_TUNING
+            if (p.dbg != nullptr) {
+                const unsigned am = __activemask();
+                if ((int)(__ffs(am) - 1) == lane) atomicAdd(p.dbg + 2, 1ull);  // warp-level resolve passes
+            }
+#endif
+            const int qi = min(q0 + r * 32, p.nq_pad - 1);
+            const float qhx = gq[qi], qhy = gq[p.nq_pad + qi], qhz = gq[2ll * p.nq_pad + qi];
+            const float cx = -2.0f * qhx, cy = -2.0f * qhy, cz = -2.0f * qhz;
+            const float nq2 = __fmaf_rn(qhz, qhz, __fmaf_rn(qhy, qhy, qhx * qhx));
+            const float m = fminf(mt_l[r], tm_l[r]);
+            const float th = filter_threshold(m, nq2, sqrtf(nq2));
+            mt_l[r] = m;
+            thr_l[r] = th;
+            double qlx = 0.0, qly = 0.0, qlz = 0.0;
+            if (p.use_lo) {
+                qlx = gq[4ll * p.nq_pad + qi];
+                qly = gq[5ll * p.nq_pad + qi];
+                qlz = gq[6ll * p.nq_pad + qi];
+            }
+            double Db = Dbest_l[r];
+            int ib = ibest_l[r];
+            for (int g = 0; g < SUB / 4; ++g) {
+                const float4 X = sx[g], Y = sy[g], Z = sz[g], N = sn[g];
+                const float pxs[4] = {X.x, X.y, X.z, X.w}, pys[4] = {Y.x, Y.y, Y.z, Y.w},
+                            pzs[4] = {Z.x, Z.y, Z.z, Z.w}, pns[4] = {N.x, N.y, N.z, N.w};
+                float as[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    as[k] = __fmaf_rn(cx, pxs[k], __fmaf_rn(cy, pys[k], __fmaf_rn(cz, pzs[k], pns[k])));
+                if (fminf(fminf(as[0], as[1]), fminf(as[2], as[3])) <= th) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (as[k] <= th) {
+                            const int j = 4 * g + k;
+                            const float px = pxs[k], py = pys[k], pz = pzs[k];
+#ifdef ISR_NN_TUNING
+                            if (p.dbg != nullptr) atomicAdd(p.dbg + 3, 1ull);  // exact evaluations
+#endif
+                            double dx = (double)qhx - (double)px, dy = (double)qhy - (double)py,
+                                   dz = (double)qhz - (double)pz;
+                            if (p.use_lo) {
+                                const long long gj = gbase + j;
+                                dx += qlx - (double)gt[4ll * p.nt_pad + gj];
+                                dy += qly - (double)gt[5ll * p.nt_pad + gj];
+                                dz += qlz - (double)gt[6ll * p.nt_pad + gj];
+                            }
+                            const double D = fma(dz, dz, fma(dy, dy, dx * dx));
+                            // strict minimum; on an exact tie the lower ORIGINAL index wins
+                            // (tiles are not visited in index order and storage is permuted)
+                            bool take = D < Db;
+                            if (D == Db) {
+                                const int cand = gbase + j;
+                                const int oc = p.perm_t != nullptr ? p.perm_t[min(cand, p.nt - 1)] : cand;
+                                const int ob = p.perm_t != nullptr ? p.perm_t[min(ib, p.nt - 1)] : ib;
+                                take = oc < ob;
+                            }
+                            if (take) {
+                                Db = D;
+                                ib = gbase + j;
+                            }
+                        }
+                    }
+                }
+            }
+            Dbest_l[r] = Db;
+            ibest_l[r] = ib;
+            // >= the exact best distance of the FP64 (hi + lo) query, rounded up
+            if (PRUNE)
+                dq_l[r] = __double2float_ru(sqrt(Db)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
+        }
+#pragma unroll
+        for (int r = 0; r < Q; ++r) thr[r] = thr_l[r];
+        if (PRUNE) {
+            float m = 0.f;
+            for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r]);  // run-time loop on purpose
+            dmax = m;
+        }
+    }
+}
 
-template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR, bool PRUNE>
+// ---- exhaustive kernel: every stage, every sub-tile -----------------------------------------
+// 128 threads x 8 queries = 1024 queries per CTA; targets stream through shared memory in
+// 1024-point stages (4 planes, 16 KB), 3 in flight: four cp.async.bulk (UBLKCP, TMA engine)
+// per stage on an mbarrier.
+template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR>
 __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
     static_assert(STAGE % SUB == 0 && SUB % 8 == 0 && Q <= 16, "tile shapes");
-    static_assert(!PRUNE || (SUB == ISR_SUB_TILE && STAGE == ISR_SOA_TILE && STAGE / SUB <= 32),
-                  "pruning uses the spheres of prepare.cu");
-    constexpr int SUBS = STAGE / SUB;
     constexpr int WARPS = THREADS / 32;
-    constexpr int SLOT_F = 4 * STAGE + (PRUNE ? 4 * SUBS : 0);  // floats per pipeline slot
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *sbuf = reinterpret_cast<float *>(smem_raw);  // [NSTAGES][4][STAGE] (+ [SUBS] spheres)
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSTAGES * SLOT_F * 4);
-    int *slist = reinterpret_cast<int *>(full + NSTAGES);  // [kListCap], PRUNE only
+    float *sbuf = reinterpret_cast<float *>(smem_raw);  // [NSTAGES][4][STAGE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSTAGES * 4 * STAGE * 4);
 
     const int b = blockIdx.z;
     if (p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) return;
@@ -146,16 +306,15 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
 
     // Scan state, in registers: -2 * query (hi part) and the flag threshold.
     float q2x[Q], q2y[Q], q2z[Q], thr[Q];
-    // Resolve state, touched only on the rare path and indexed at run time there, which
-    // places it in (L1-resident) local memory and keeps it out of the scan's registers.
+    // Resolve state (see scan_subtile)
     float mt_l[Q], thr_l[Q], tm_l[Q];
     double Dbest_l[Q];
     int ibest_l[Q];
-    // a warp owns 32*Q consecutive stored queries (a compact patch under Morton order);
-    // lane l holds queries l, 32+l, ...: every load below is one coalesced 128-byte line
+    float dmax = 0.f;
+    unsigned nflag_unused = 0;
+    // a warp owns 32*Q consecutive stored queries; lane l holds queries l, 32+l, ...: every
+    // load below is one coalesced 128-byte line
     const int q0 = blockIdx.x * (THREADS * Q) + warp * (32 * Q) + lane;
-    float dq_l[Q];       // PRUNE: per-query upper bound of the best distance so far
-    float dmax = 0.f;    // PRUNE: max of dq_l over the lane's live queries
 #pragma unroll
     for (int r = 0; r < Q; ++r) {
         const int i = min(q0 + r * 32, p.nq_pad - 1);
@@ -166,28 +325,22 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
         // coordinates would put every target inside the error window
         const bool live = (q0 + r * 32 < p.nq) && !p.debug_no_resolve;
         thr[r] = live ? CUDART_INF_F : -CUDART_INF_F;
-        if (PRUNE && q0 + r * 32 < p.nq) dmax = CUDART_INF_F;
     }
     for (int r = 0; r < Q; ++r) {  // run-time loop on purpose
         mt_l[r] = CUDART_INF_F;
         thr_l[r] = (q0 + r * 32 < p.nq) && !p.debug_no_resolve ? CUDART_INF_F : -CUDART_INF_F;
         Dbest_l[r] = CUDART_INF;
         ibest_l[r] = s_begin * STAGE;
-        if (PRUNE) dq_l[r] = (q0 + r * 32 < p.nq) ? CUDART_INF_F : 0.f;
     }
 
     // Scan order: the target stage whose centre is nearest to this CTA's query block goes
     // first (clouds are stored in Morton order, so both are compact patches).  After that
     // one stage every query already holds a near-final bound and the remaining stages
-    // almost never reach the resolve path.  The rest follows in ascending order, or -- when
-    // pruning -- only the listed stages follow.
+    // almost never reach the resolve path.  The rest follows in ascending order.
     int s_first = 0;
-    float cQx = 0.f, cQy = 0.f, cQz = 0.f, rQ = 0.f;  // PRUNE: query-block sphere
-    float cWx = 0.f, cWy = 0.f, cWz = 0.f;            // PRUNE: this warp's query centroid
-    __shared__ float cred[4][WARPS];
-    __shared__ u64 sred[WARPS];
-    __shared__ int scount;
-    if (p.stage_c != nullptr && (nst > 1 || PRUNE)) {
+    if (p.stage_c != nullptr && nst > 1) {
+        __shared__ float cred[4][WARPS];
+        __shared__ u64 sred[WARPS];
         float cx = 0.f, cy = 0.f, cz = 0.f, cn = 0.f;
 #pragma unroll
         for (int r = 0; r < Q; ++r) {
@@ -201,10 +354,6 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
             cy += __shfl_xor_sync(0xffffffffu, cy, o);
             cz += __shfl_xor_sync(0xffffffffu, cz, o);
             cn += __shfl_xor_sync(0xffffffffu, cn, o);
-        }
-        if (PRUNE) {
-            const float invw = cn > 0.f ? -0.5f / cn : 0.f;  // q2 = -2 * query
-            cWx = cx * invw; cWy = cy * invw; cWz = cz * invw;
         }
         if (lane == 0) {
             cred[0][warp] = cx; cred[1][warp] = cy; cred[2][warp] = cz; cred[3][warp] = cn;
@@ -232,279 +381,54 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
             best = other < best ? other : best;
         }
         if (lane == 0) sred[warp] = best;
-        if (PRUNE) {
-            // radius of the query block about (cx, cy, cz), live queries only
-            float m = 0.f;
-#pragma unroll
-            for (int r = 0; r < Q; ++r) {
-                if (q0 + r * 32 < p.nq) {
-                    const float dx = fmaf(q2x[r], -0.5f, -cx), dy = fmaf(q2y[r], -0.5f, -cy),
-                                dz = fmaf(q2z[r], -0.5f, -cz);
-                    m = fmaxf(m, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            __syncthreads();  // cred is reused
-            if (lane == 0) cred[0][warp] = m;
-            if (tid == 0) scount = 0;
-        }
         __syncthreads();
         best = sred[0];
 #pragma unroll
         for (int w = 1; w < WARPS; ++w) best = sred[w] < best ? sred[w] : best;
         s_first = (int)(unsigned)(best & 0xffffffffull);
         if (s_first >= nst) s_first = 0;
-        if (PRUNE) {
-            float m = cred[0][0];
-#pragma unroll
-            for (int w = 1; w < WARPS; ++w) m = fmaxf(m, cred[0][w]);
-            cQx = cx; cQy = cy; cQz = cz;
-            rQ = __fsqrt_ru(m) * 1.00002f;
-        }
     }
-    // pipeline position -> stage (relative to s_begin).  Position 0 is s_first; then either
-    // all other stages in ascending order or (PRUNE, after the list is built) the list.
-    bool use_list = false;
-    int npos = PRUNE ? 1 : nst;
-    auto stage_of = [&](int pos) {
-        if (pos == 0) return s_first;
-        if (PRUNE && use_list) return slist[pos - 1];
-        return pos - 1 < s_first ? pos - 1 : pos;
-    };
+    auto stage_of = [&](int pos) { return pos == 0 ? s_first : (pos - 1 < s_first ? pos - 1 : pos); };
 
     auto issue = [&](int sl) {
         const int slot = sl % NSTAGES;
-        float *dst = sbuf + (size_t)slot * SLOT_F;
-        const int stg = s_begin + stage_of(sl);
-        const float *src = gt + (long long)stg * STAGE;
-        mbar_expect_tx(&full[slot], 4u * STAGE * 4u + (PRUNE ? SUBS * 16u : 0u));
+        float *dst = sbuf + (size_t)slot * 4 * STAGE;
+        const float *src = gt + (long long)(s_begin + stage_of(sl)) * STAGE;
+        mbar_expect_tx(&full[slot], 4u * STAGE * 4u);
 #pragma unroll
         for (int pl = 0; pl < 4; ++pl)
             bulk_g2s(dst + pl * STAGE, src + (long long)pl * p.nt_pad, STAGE * 4u, &full[slot]);
-        if (PRUNE)
-            bulk_g2s(dst + 4 * STAGE, p.sub_c + (long long)b * p.sub_c_bstride + (long long)stg * SUBS,
-                     SUBS * 16u, &full[slot]);
     };
     if (tid == 0) {
-        for (int i = 0; i < NSTAGES - 1 && i < npos; ++i) issue(i);
+        for (int i = 0; i < NSTAGES - 1 && i < nst; ++i) issue(i);
     }
-    unsigned nscanned = 0;  // (warp, sub-tile) units this warp evaluated
 
     // (A per-slot `empty` mbarrier instead of the CTA barrier below was measured 2 % slower:
     // the 5 % of samples parked at the barrier are warps that would otherwise only run ahead.)
-    for (int sl = 0; sl < npos; ++sl) {
-        if (tid == 0 && sl + NSTAGES - 1 < npos) issue(sl + NSTAGES - 1);
+    for (int sl = 0; sl < nst; ++sl) {
+        if (tid == 0 && sl + NSTAGES - 1 < nst) issue(sl + NSTAGES - 1);
         const int slot = sl % NSTAGES;
-        bool skip_stage = false;
-        if (PRUNE && sl > 0) {
-            // the whole stage first: one sphere test per warp (the sphere comes from L2
-            // while the stage's bulk copy is still in flight)
-            const float4 S = p.stage_c[(long long)b * p.stage_c_bstride + s_begin + stage_of(sl)];
-            skip_stage = __all_sync(0xffffffffu, lane_rules_out<Q>(S, q2x, q2y, q2z, dmax));
-        }
         mbar_wait(&full[slot], (sl / NSTAGES) & 1);
-        const float4 *sx = reinterpret_cast<const float4 *>(sbuf + (size_t)slot * SLOT_F);
+        const float4 *sx = reinterpret_cast<const float4 *>(sbuf + (size_t)slot * 4 * STAGE);
         const float4 *sy = sx + STAGE / 4;
         const float4 *sz = sy + STAGE / 4;
         const float4 *sn = sz + STAGE / 4;
-        const float4 *ssph = sn + STAGE / 4;  // PRUNE: the stage's SUBS sub-tile spheres
-        int sub_first = 0;
-        if (PRUNE && sl == 0) {
-            // no bound yet: start with the sub-tile nearest to this warp's queries
-            float d = CUDART_INF_F;
-            if (lane < SUBS) {
-                const float4 S = ssph[lane];
-                const float dx = S.x - cWx, dy = S.y - cWy, dz = S.z - cWz;
-                d = S.w < 0.f ? CUDART_INF_F : dx * dx + dy * dy + dz * dz;
-            }
-            u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(unsigned)lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const u64 other = __shfl_xor_sync(0xffffffffu, key, o);
-                key = other < key ? other : key;
-            }
-            sub_first = (int)(unsigned)(key & 31ull);
-            if (sub_first >= SUBS) sub_first = 0;
-        }
+        const int gstage = (s_begin + stage_of(sl)) * STAGE;
 #pragma unroll 1
-        for (int k = 0; k < (skip_stage ? 0 : SUBS); ++k) {
-            int sub = k;
-            if (PRUNE) {
-                if (sl == 0) sub = k == 0 ? sub_first : (k <= sub_first ? k - 1 : k);
-                if (__all_sync(0xffffffffu, lane_rules_out<Q>(ssph[sub], q2x, q2y, q2z, dmax))) continue;
-            }
-            ++nscanned;
-            float tm[Q];
-#pragma unroll
-            for (int r = 0; r < Q; ++r) tm[r] = CUDART_INF_F;
-#pragma unroll UNR
-            for (int g = 0; g < SUB / 4; ++g) {
-                const float4 X = sx[sub * (SUB / 4) + g];
-                const float4 Y = sy[sub * (SUB / 4) + g];
-                const float4 Z = sz[sub * (SUB / 4) + g];
-                const float4 N = sn[sub * (SUB / 4) + g];
-                const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
-                const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
-                const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
-                const u64 n01 = pack2(N.x, N.y), n23 = pack2(N.z, N.w);
-                // level-major over the Q queries: consecutive FFMA2 are independent and share
-                // the target-pair operand (operand-reuse cache); the query rides as a scalar
-                u64 acc[Q];
-#pragma unroll
-                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2z[r], q2z[r]), z01, n01);
-#pragma unroll
-                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2y[r], q2y[r]), y01, acc[r]);
-#pragma unroll
-                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2x[r], q2x[r]), x01, acc[r]);
-#pragma unroll
-                for (int r = 0; r < Q; ++r) {
-                    float a0, a1;
-                    unpack2(acc[r], a0, a1);
-                    tm[r] = min3(tm[r], a0, a1);
-                }
-#pragma unroll
-                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2z[r], q2z[r]), z23, n23);
-#pragma unroll
-                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2y[r], q2y[r]), y23, acc[r]);
-#pragma unroll
-                for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2x[r], q2x[r]), x23, acc[r]);
-#pragma unroll
-                for (int r = 0; r < Q; ++r) {
-                    float a0, a1;
-                    unpack2(acc[r], a0, a1);
-                    tm[r] = min3(tm[r], a0, a1);
-                }
-            }
-            unsigned flags = 0;
-#pragma unroll
-            for (int r = 0; r < Q; ++r) flags |= (tm[r] <= thr[r]) ? (1u << r) : 0u;
-            if (flags != 0) {
-#ifdef ISR_NN_TUNING
-                if (p.dbg != nullptr) {
-                    const unsigned am = __activemask();
-                    if ((int)(__ffs(am) - 1) == (tid & 31)) atomicAdd(p.dbg + 0, 1ull);  // warp-level flagged sub-tiles
-                    atomicAdd(p.dbg + 1, (unsigned long long)__popc(flags));            // (query, sub-tile) events
-                }
-#endif
-                // ---- resolve: rare, divergent; one pass serves every flagged lane ----------
-#pragma unroll
-                for (int r = 0; r < Q; ++r) tm_l[r] = tm[r];
-                const float *fx = reinterpret_cast<const float *>(sx) + sub * SUB;
-                const float *fy = reinterpret_cast<const float *>(sy) + sub * SUB;
-                const float *fz = reinterpret_cast<const float *>(sz) + sub * SUB;
-                const float *fn = reinterpret_cast<const float *>(sn) + sub * SUB;
-                const int gbase = (s_begin + stage_of(sl)) * STAGE + sub * SUB;
-                for (unsigned f = flags; f != 0; f &= f - 1) {
-                    const int r = __ffs(f) - 1;
-#ifdef ISR_NN_TUNING
-                    if (p.dbg != nullptr) {
-                        const unsigned am = __activemask();
-                        if ((int)(__ffs(am) - 1) == (tid & 31)) atomicAdd(p.dbg + 2, 1ull);  // warp-level resolve passes
-                    }
-#endif
-                    const int qi = min(q0 + r * 32, p.nq_pad - 1);
-                    const float qhx = gq[qi], qhy = gq[p.nq_pad + qi], qhz = gq[2ll * p.nq_pad + qi];
-                    const float cx = -2.0f * qhx, cy = -2.0f * qhy, cz = -2.0f * qhz;
-                    const float nq2 = __fmaf_rn(qhz, qhz, __fmaf_rn(qhy, qhy, qhx * qhx));
-                    const float m = fminf(mt_l[r], tm_l[r]);
-                    const float th = filter_threshold(m, nq2, sqrtf(nq2));
-                    mt_l[r] = m;
-                    thr_l[r] = th;
-                    double qlx = 0.0, qly = 0.0, qlz = 0.0;
-                    if (p.use_lo) {
-                        qlx = gq[4ll * p.nq_pad + qi];
-                        qly = gq[5ll * p.nq_pad + qi];
-                        qlz = gq[6ll * p.nq_pad + qi];
-                    }
-                    double Db = Dbest_l[r];
-                    int ib = ibest_l[r];
-#pragma unroll 4
-                    for (int j = 0; j < SUB; ++j) {
-                        const float px = fx[j], py = fy[j], pz = fz[j];
-                        const float a = __fmaf_rn(cx, px, __fmaf_rn(cy, py, __fmaf_rn(cz, pz, fn[j])));
-                        if (a <= th) {
-#ifdef ISR_NN_TUNING
-                            if (p.dbg != nullptr) atomicAdd(p.dbg + 3, 1ull);  // exact evaluations
-#endif
-                            double dx = (double)qhx - (double)px, dy = (double)qhy - (double)py,
-                                   dz = (double)qhz - (double)pz;
-                            if (p.use_lo) {
-                                const long long gj = gbase + j;
-                                dx += qlx - (double)gt[4ll * p.nt_pad + gj];
-                                dy += qly - (double)gt[5ll * p.nt_pad + gj];
-                                dz += qlz - (double)gt[6ll * p.nt_pad + gj];
-                            }
-                            const double D = fma(dz, dz, fma(dy, dy, dx * dx));
-                            // strict minimum; on an exact tie the lower ORIGINAL index wins
-                            // (stages are not visited in index order and storage is permuted)
-                            bool take = D < Db;
-                            if (D == Db) {
-                                const int cand = gbase + j;
-                                const int oc = p.perm_t != nullptr ? p.perm_t[min(cand, p.nt - 1)] : cand;
-                                const int ob = p.perm_t != nullptr ? p.perm_t[min(ib, p.nt - 1)] : ib;
-                                take = oc < ob;
-                            }
-                            if (take) {
-                                Db = D;
-                                ib = gbase + j;
-                            }
-                        }
-                    }
-                    Dbest_l[r] = Db;
-                    ibest_l[r] = ib;
-                    // >= the exact best distance of the FP64 (hi + lo) query, rounded up
-                    if (PRUNE)
-                        dq_l[r] = __double2float_ru(sqrt(Db)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
-                }
-#pragma unroll
-                for (int r = 0; r < Q; ++r) thr[r] = thr_l[r];
-                if (PRUNE) {
-                    float m = 0.f;
-                    for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r]);  // run-time loop on purpose
-                    dmax = m;
-                }
-            }
+        for (int sub = 0; sub < STAGE / SUB; ++sub) {
+            scan_subtile<Q, SUB, UNR, false>(p, gq, gt, q0, lane, sx + sub * (SUB / 4),
+                                             sy + sub * (SUB / 4), sz + sub * (SUB / 4),
+                                             sn + sub * (SUB / 4), gstage + sub * SUB, q2x, q2y, q2z,
+                                             thr, mt_l, thr_l, tm_l, Dbest_l, ibest_l, nullptr, dmax,
+                                             nflag_unused, nflag_unused);
         }
         __syncthreads();  // every warp is done with this slot before it is refilled
-        if (PRUNE && sl == 0 && nst > 1) {
-            // every live query now holds a finite bound: list the stages that can still
-            // matter to any query of the block, |cQ - c| <= B + rQ + r.
-            float B = dmax;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) B = fmaxf(B, __shfl_xor_sync(0xffffffffu, B, o));
-            if (lane == 0) cred[1][warp] = B;
-            __syncthreads();
-            B = cred[1][0];
-#pragma unroll
-            for (int w = 1; w < WARPS; ++w) B = fmaxf(B, cred[1][w]);
-            const float4 *sc = p.stage_c + (long long)b * p.stage_c_bstride + s_begin;
-            for (int base = 0; base < nst; base += THREADS) {
-                const int sI = base + tid;
-                bool need = false;
-                if (sI < nst && sI != s_first) {
-                    const float4 c = sc[sI];
-                    const float dx = c.x - cQx, dy = c.y - cQy, dz = c.z - cQz;
-                    const float rr = (B + rQ + c.w) * 1.0001f;
-                    need = c.w >= 0.f && !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, need);
-                int at = 0;
-                if (lane == 0 && m != 0) at = atomicAdd(&scount, __popc(m));
-                at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
-                if (need && at < kListCap) slist[at] = sI;
-            }
-            __syncthreads();
-            const int cnt = scount;
-            use_list = cnt <= kListCap;
-            npos = use_list ? 1 + cnt : nst;
-            if (tid == 0) {
-                for (int i = 1; i < NSTAGES - 1 + 1 && i < npos; ++i) issue(i);
-            }
-        }
     }
-    if (p.evaluated != nullptr && lane == 0 && nscanned != 0)
-        atomicAdd(p.evaluated, (unsigned long long)nscanned);
+    if (p.evaluated != nullptr && lane == 0) {
+        atomicAdd(p.evaluated + 0, (unsigned long long)nst * (STAGE / SUB));
+        atomicAdd(p.evaluated + 1, (unsigned long long)nst);
+        atomicAdd(p.evaluated + 4, 1ull);
+    }
 
     for (int r = 0; r < Q; ++r) {
         const int i = q0 + r * 32;
@@ -520,6 +444,334 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
                 p.out_d2[o] = (float)Dbest_l[r];
                 if (p.out_idx != nullptr) p.out_idx[o] = jo;
             }
+        }
+    }
+}
+
+// ---- pruned kernel: warp-autonomous, sub-tile granularity ------------------------------------
+constexpr int kRing = 4;    // sub-tile buffers in flight per warp
+constexpr int kFifo = 64;   // candidate sub-tiles queued per warp
+constexpr int kAnchors = 4; // seed queries per warp
+
+template <int SUB, int Q>
+struct alignas(128) PrunedWarpSmem {
+    float buf[kRing][4][SUB];  // x, y, z, |p|^2 of one sub-tile per slot
+    float4 sph[kFifo];         // queued candidates: sphere,
+    int id[kFifo];             //   sub-tile index in the target (-1: dropped by the exact test),
+    unsigned rows[kFifo];      //   query rows that the coarse test could not rule out
+    float4 row[Q];             // sphere (c, rho) of query row r = the 32 queries r*32 .. r*32+31
+    float rowB[Q];             // max of their bounds dq (refreshed between batches of work)
+    uint64_t full[kRing];
+};
+
+template <int Q, int WARPS, int SUB, int MINB, int UNR>
+__global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2Params p) {
+    static_assert(SUB == ISR_SUB_TILE && ISR_SOA_TILE / SUB <= 32 && Q == 8, "pruning uses the spheres of prepare.cu");
+    constexpr int SUBS = ISR_SOA_TILE / SUB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int b = blockIdx.z;
+    if (p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) return;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int q0 = blockIdx.x * (WARPS * 32 * Q) + warp * (32 * Q) + lane;
+    if (q0 - lane >= p.nq) return;  // this warp has no live query; warps never meet at a barrier
+    PrunedWarpSmem<SUB, Q> &ws = reinterpret_cast<PrunedWarpSmem<SUB, Q> *>(smem_raw)[warp];
+    const float *__restrict__ gq = p.q + (long long)b * p.q_bstride;
+    const float *__restrict__ gt = p.t + (long long)b * p.t_bstride;
+    const float4 *__restrict__ stage_c = p.stage_c + (long long)b * p.stage_c_bstride;
+    const float4 *__restrict__ sub_c = p.sub_c + (long long)b * p.sub_c_bstride;
+    const int stages = p.stages_total;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kRing; ++i) mbar_init(&ws.full[i], 1);
+        mbar_fence_init();
+    }
+
+    float q2x[Q], q2y[Q], q2z[Q], thr[Q];
+    float mt_l[Q], thr_l[Q], tm_l[Q], dq_l[Q];
+    double Dbest_l[Q];
+    int ibest_l[Q];
+    float dmax = 0.f;  // max over the lane's live queries of dq_l (0: no live query)
+#pragma unroll
+    for (int r = 0; r < Q; ++r) {
+        const int i = min(q0 + r * 32, p.nq_pad - 1);
+        q2x[r] = -2.0f * gq[i];
+        q2y[r] = -2.0f * gq[p.nq_pad + i];
+        q2z[r] = -2.0f * gq[2ll * p.nq_pad + i];
+        const bool live = q0 + r * 32 < p.nq;
+        thr[r] = live ? CUDART_INF_F : -CUDART_INF_F;
+        if (live) dmax = CUDART_INF_F;
+    }
+    for (int r = 0; r < Q; ++r) {  // run-time loop on purpose
+        const bool live = q0 + r * 32 < p.nq;
+        mt_l[r] = CUDART_INF_F;
+        thr_l[r] = live ? CUDART_INF_F : -CUDART_INF_F;
+        Dbest_l[r] = CUDART_INF;
+        ibest_l[r] = 0;
+        dq_l[r] = live ? CUDART_INF_F : 0.f;
+    }
+
+    // ---- query-row spheres: row r is 32 consecutive stored queries, a compact patch ----------
+#pragma unroll
+    for (int r = 0; r < Q; ++r) {
+        const bool live = q0 + r * 32 < p.nq;
+        float cx = live ? q2x[r] : 0.f, cy = live ? q2y[r] : 0.f, cz = live ? q2z[r] : 0.f,
+              cn = live ? 1.f : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cx += __shfl_xor_sync(0xffffffffu, cx, o);
+            cy += __shfl_xor_sync(0xffffffffu, cy, o);
+            cz += __shfl_xor_sync(0xffffffffu, cz, o);
+            cn += __shfl_xor_sync(0xffffffffu, cn, o);
+        }
+        const float inv = cn > 0.f ? -0.5f / cn : 0.f;  // q2 = -2 * query
+        cx *= inv; cy *= inv; cz *= inv;
+        const float dx = fmaf(q2x[r], -0.5f, -cx), dy = fmaf(q2y[r], -0.5f, -cy),
+                    dz = fmaf(q2z[r], -0.5f, -cz);
+        float m = live ? fmaf(dz, dz, fmaf(dy, dy, dx * dx)) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) {
+            ws.row[r] = make_float4(cx, cy, cz, cn > 0.f ? __fsqrt_ru(m) * 1.00002f : -1.f);
+            ws.rowB[r] = cn > 0.f ? CUDART_INF_F : 0.f;
+        }
+    }
+    __syncwarp();
+    // rowB[r] <- max over the row of the current bounds (they only ever shrink, so a stale
+    // value is merely conservative)
+    auto refresh_bounds = [&]() {
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            float m = dq_l[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) ws.rowB[r] = m;
+        }
+        __syncwarp();
+    };
+    // coarse test, one candidate sphere per lane: which query rows can it still matter to?
+    auto coarse_rows = [&](const float4 S) {
+        unsigned rows = 0;
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            const float4 R = ws.row[r];
+            const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
+            const float rr = (ws.rowB[r] + R.w + S.w) * 1.0001f;
+            if (R.w >= 0.f && !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr)) rows |= 1u << r;
+        }
+        return S.w >= 0.f ? rows : 0u;
+    };
+    // exact test, one query per lane and row: is any query of `rows` not ruled out?
+    auto exact_any = [&](const float4 S, unsigned rows) {
+        bool need = false;
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            if (rows & (1u << r)) {  // warp-uniform
+                const float dx = fmaf(q2x[r], -0.5f, -S.x), dy = fmaf(q2y[r], -0.5f, -S.y),
+                            dz = fmaf(q2z[r], -0.5f, -S.z);
+                const float rr = (dq_l[r] + S.w) * 1.0001f;
+                // a dead query slot (dq = 0, padded coordinates ~1e18) is always ruled out
+                need = need || !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr);
+            }
+        }
+        return __any_sync(0xffffffffu, need);
+    };
+
+    // ---- seeds: for kAnchors queries spread over the block, the nearest sub-tile centre ------
+    // anchors sit at stored positions 0, 85, 170, 255 of the warp's 256 queries
+    int head = 0, look = 0, tail = 0, nloads = 0, nconsumed = 0;  // FIFO / ring state, warp-uniform
+    int seed[kAnchors];
+    {
+        constexpr int ar[kAnchors] = {0, 2, 5, 7};
+        constexpr int al[kAnchors] = {0, 21, 10, 31};
+        float ax[kAnchors], ay[kAnchors], az[kAnchors];
+#pragma unroll
+        for (int a = 0; a < kAnchors; ++a) {
+            const bool live = __shfl_sync(0xffffffffu, q0 + ar[a] * 32 < p.nq ? 1 : 0, al[a]) != 0;
+            const int l = live ? al[a] : 0;  // position 0 is always live
+            const float x = live ? q2x[ar[a]] : q2x[0], y = live ? q2y[ar[a]] : q2y[0],
+                        z = live ? q2z[ar[a]] : q2z[0];
+            ax[a] = -0.5f * __shfl_sync(0xffffffffu, x, l);
+            ay[a] = -0.5f * __shfl_sync(0xffffffffu, y, l);
+            az[a] = -0.5f * __shfl_sync(0xffffffffu, z, l);
+        }
+        u64 bk[kAnchors];
+#pragma unroll
+        for (int a = 0; a < kAnchors; ++a) bk[a] = ~0ull;
+        for (int base = 0; base < stages; base += 32) {
+            const int s = base + lane;
+            if (s < stages) {
+                const float4 S = stage_c[s];
+                if (S.w >= 0.f) {
+#pragma unroll
+                    for (int a = 0; a < kAnchors; ++a) {
+                        const float dx = S.x - ax[a], dy = S.y - ay[a], dz = S.z - az[a];
+                        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        const u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(unsigned)s;
+                        bk[a] = key < bk[a] ? key : bk[a];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < kAnchors; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const u64 other = __shfl_xor_sync(0xffffffffu, bk[a], o);
+                bk[a] = other < bk[a] ? other : bk[a];
+            }
+            int st = (int)(unsigned)(bk[a] & 0xffffffffull);
+            if (st >= stages) st = 0;
+            // nearest sub-tile centre inside that stage
+            u64 key = ~0ull;
+            if (lane < SUBS) {
+                const float4 S = sub_c[(long long)st * SUBS + lane];
+                if (S.w >= 0.f) {
+                    const float dx = S.x - ax[a], dy = S.y - ay[a], dz = S.z - az[a];
+                    key = ((u64)__float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) << 32) | (u64)(unsigned)lane;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const u64 other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other < key ? other : key;
+            }
+            int sb = (int)(unsigned)(key & 31ull);
+            if (key == ~0ull) sb = 0;
+            seed[a] = st * SUBS + sb;
+            bool dup = false;
+#pragma unroll
+            for (int c = 0; c < a; ++c) dup = dup || seed[c] == seed[a];
+            if (!dup) {
+                if (lane == 0) {
+                    // +inf radius: never ruled out
+                    ws.sph[tail % kFifo] = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
+                    ws.id[tail % kFifo] = seed[a];
+                    ws.rows[tail % kFifo] = (1u << Q) - 1u;
+                }
+                ++tail;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- main loop: ONE code path that either consumes a queued sub-tile or produces more -------
+    // (a single scan site keeps the instruction footprint small: the warps of an SM sit in
+    // different phases, so every inlined copy of the scan would compete for the instruction cache)
+    //   consume: exact-test queued entries up to kRing loads ahead (survivors get their bulk
+    //            copy issued at once), then wait for the head entry's data and scan it;
+    //   produce: next chunk of 32 stage spheres -> coarse row test, one per lane; then per
+    //            candidate stage the exact test, and its 16 sub-tile spheres -> coarse row test
+    //            -> FIFO.
+    unsigned nscanned = 0, ntests = 0, ncand = 0, nflag = 0, npass = 0;
+    bool seeding = true;   // the seeds must be scanned before anything is produced
+    int base = 0;          // next chunk of stage spheres
+    int cbase = 0;         // base of the chunk whose candidates are in smask
+    unsigned smask = 0;    // candidate stages of the current chunk not yet expanded
+    float4 Sst = make_float4(0.f, 0.f, 0.f, -1.f);  // this lane's stage sphere of the chunk
+    unsigned rows_st = 0;                           // and its coarse row mask
+    for (;;) {
+        const int pending = tail - head;
+        const bool produced_all = smask == 0 && base >= stages;
+        if (pending > 0 && (seeding || produced_all || pending > kFifo - SUBS)) {
+            while (look < tail && nloads - nconsumed < kRing) {
+                const int e = look % kFifo;
+                ++ntests;
+                if (exact_any(ws.sph[e], ws.rows[e])) {
+                    if (lane == 0) {
+                        const int slot = nloads % kRing;
+                        const long long src = (long long)ws.id[e] * SUB;
+                        mbar_expect_tx(&ws.full[slot], 4u * SUB * 4u);
+#pragma unroll
+                        for (int pl = 0; pl < 4; ++pl)
+                            bulk_g2s(&ws.buf[slot][pl][0], gt + (long long)pl * p.nt_pad + src, SUB * 4u,
+                                     &ws.full[slot]);
+                    }
+                    ++nloads;
+                } else {
+                    if (lane == 0) ws.id[e] = -1;
+                }
+                ++look;
+            }
+            __syncwarp();
+            const int id = ws.id[head % kFifo];
+            if (id >= 0) {
+                const int slot = nconsumed % kRing;
+                mbar_wait(&ws.full[slot], (nconsumed / kRing) & 1);
+                ++nscanned;
+                const float4 *sx = reinterpret_cast<const float4 *>(&ws.buf[slot][0][0]);
+                scan_subtile<Q, SUB, UNR, true>(p, gq, gt, q0, lane, sx, sx + SUB / 4, sx + 2 * (SUB / 4),
+                                                sx + 3 * (SUB / 4), id * SUB, q2x, q2y, q2z, thr, mt_l,
+                                                thr_l, tm_l, Dbest_l, ibest_l, dq_l, dmax, nflag, npass);
+                ++nconsumed;
+                __syncwarp();  // every lane is done with the slot before lane 0 refills it
+            }
+            ++head;
+            continue;
+        }
+        seeding = false;
+        if (produced_all) break;
+        if (smask == 0) {
+            // next chunk: refresh the row bounds, coarse-test 32 stage spheres
+            refresh_bounds();
+            cbase = base;
+            base += 32;
+            const int s = cbase + lane;
+            Sst = stage_c[min(s, stages - 1)];
+            rows_st = s < stages ? coarse_rows(Sst) : 0u;
+            smask = __ballot_sync(0xffffffffu, rows_st != 0);
+            continue;
+        }
+        const int l = __ffs(smask) - 1;
+        smask &= smask - 1;
+        {
+            const float4 S = make_float4(__shfl_sync(0xffffffffu, Sst.x, l), __shfl_sync(0xffffffffu, Sst.y, l),
+                                         __shfl_sync(0xffffffffu, Sst.z, l), __shfl_sync(0xffffffffu, Sst.w, l));
+            if (!exact_any(S, __shfl_sync(0xffffffffu, rows_st, l))) continue;
+        }
+        ++ncand;
+        {
+            // the stage's sub-tile spheres, one per lane
+            float4 S = make_float4(0.f, 0.f, 0.f, -1.f);
+            unsigned rows = 0;
+            const int gid = (cbase + l) * SUBS + lane;
+            if (lane < SUBS) {
+                S = sub_c[gid];
+                rows = coarse_rows(S);
+#pragma unroll
+                for (int a = 0; a < kAnchors; ++a) rows = gid == seed[a] ? 0u : rows;  // already scanned
+            }
+            const unsigned m16 = __ballot_sync(0xffffffffu, rows != 0);
+            if (rows != 0) {
+                const int pos = (tail + __popc(m16 & ((1u << lane) - 1u))) % kFifo;
+                ws.sph[pos] = S;
+                ws.id[pos] = gid;
+                ws.rows[pos] = rows;
+            }
+            tail += __popc(m16);
+            __syncwarp();
+        }
+    }
+
+    if (p.evaluated != nullptr && lane == 0) {
+        atomicAdd(p.evaluated + 0, (unsigned long long)nscanned);
+        atomicAdd(p.evaluated + 1, (unsigned long long)stages);   // stage spheres tested
+        atomicAdd(p.evaluated + 2, (unsigned long long)ncand);    // stages that passed
+        atomicAdd(p.evaluated + 3, (unsigned long long)ntests);   // exact sub-tile tests
+        atomicAdd(p.evaluated + 4, 1ull);                         // warps
+        atomicAdd(p.evaluated + 5, (unsigned long long)nflag);    // scanned units that flagged
+        atomicAdd(p.evaluated + 6, (unsigned long long)npass);    // resolve passes (warp level)
+    }
+
+    for (int r = 0; r < Q; ++r) {
+        const int i = q0 + r * 32;
+        if (i < p.nq) {
+            const int io = p.perm_q != nullptr ? p.perm_q[i] : i;
+            const int jo = p.perm_t != nullptr ? p.perm_t[min(ibest_l[r], p.nt - 1)] : ibest_l[r];
+            const long long o = (long long)b * p.nq + io;
+            p.out_d2[o] = (float)Dbest_l[r];
+            if (p.out_idx != nullptr) p.out_idx[o] = jo;
         }
     }
 }
@@ -547,17 +799,15 @@ __global__ void nn2_combine_kernel(const double *__restrict__ part_D, const int 
 }
 
 // ---- host-side launch ----------------------------------------------------------------
-template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR = 2, bool PRUNE = false>
+template <int Q, int THREADS, int STAGE, int NSTAGES, int SUB, int MINB, int UNR = 2>
 struct NN2Variant {
     static constexpr int kQueriesPerCta = Q * THREADS;
     static constexpr int kStage = STAGE;
-    static constexpr bool kPrune = PRUNE;
-    static constexpr size_t kSmem =
-        (size_t)NSTAGES * (4 * STAGE + (PRUNE ? 4 * (STAGE / SUB) : 0)) * 4 + NSTAGES * 8 +
-        (PRUNE ? kListCap * 4 : 0);
+    static constexpr bool kPrune = false;
+    static constexpr size_t kSmem = (size_t)NSTAGES * 4 * STAGE * 4 + NSTAGES * 8;
 
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
-        auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR, PRUNE>;
+        auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR>;
         static thread_local int configured_dev = -1;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -574,7 +824,7 @@ struct NN2Variant {
 
     static int ctas_per_sm() {
         int n = 0;
-        auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR, PRUNE>;
+        auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS, kSmem) != cudaSuccess ||
             n < 1)
@@ -584,7 +834,25 @@ struct NN2Variant {
 };
 
 using NN2Main = NN2Variant<8, 128, 1024, 3, 64, 4, 1>;
-using NN2Pruned = NN2Variant<8, 128, 1024, 3, 64, 4, 1, true>;
+
+// the pruned kernel: WARPS independent warps of 32 x Q queries per CTA
+template <int Q, int WARPS, int SUB, int MINB, int UNR>
+struct NN2PrunedVariant {
+    static constexpr int kQueriesPerCta = Q * WARPS * 32;
+    static constexpr int kStage = ISR_SOA_TILE;
+    static constexpr bool kPrune = true;
+    static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q>);
+
+    static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
+        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR>;
+        ProfScope prof(kProfNN, st);
+        kern<<<grid, WARPS * 32, kSmem, st>>>(p);
+        return launched("nn2_pruned_kernel");
+    }
+    static int ctas_per_sm() { return MINB; }
+};
+using NN2Pruned = NN2PrunedVariant<8, 4, 64, 4, 1>;
+static_assert(NN2Pruned::kSmem <= 48 * 1024, "pruned kernel uses the default dynamic shared memory limit");
 constexpr int kMaxSplits = 32;
 
 // process-wide pruning switch and profiling counters (isr.h)
@@ -800,6 +1068,15 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
     return nn2_dispatch<NN2Main>(c);
 }
 
+int isr_profile_nn_counters(uint64_t *out8_host) {
+    using namespace isr;
+    ISR_REQUIRE(out8_host != nullptr, ISR_E_INVALID_ARG, "profile_nn_counters: null pointer");
+    unsigned long long *ctr = evaluated_counter();
+    ISR_REQUIRE(ctr != nullptr, ISR_E_CUDA, "profile_nn_counters: no counter buffer");
+    ISR_TRY(check_cuda(cudaDeviceSynchronize(), "profile_nn_counters sync"));
+    return check_cuda(cudaMemcpy(out8_host, ctr, 64, cudaMemcpyDeviceToHost), "profile_nn_counters read");
+}
+
 int isr_set_nn_pruning(int on) {
     isr::g_prune.store(on != 0 ? 1 : 0);
     return ISR_OK;
@@ -814,7 +1091,7 @@ int isr_profile_nn_pairs(uint64_t *evaluated_host, uint64_t *answered_host) {
     if (ctr != nullptr) {
         ISR_TRY(check_cuda(cudaDeviceSynchronize(), "profile_nn_pairs sync"));
         ISR_TRY(check_cuda(cudaMemcpy(&units, ctr, 8, cudaMemcpyDeviceToHost), "profile_nn_pairs read"));
-        ISR_TRY(check_cuda(cudaMemset(ctr, 0, 8), "profile_nn_pairs clear"));
+        ISR_TRY(check_cuda(cudaMemset(ctr, 0, 64), "profile_nn_pairs clear"));
     }
     // one unit = one warp block of 32 x 8 queries against one 64-target sub-tile
     if (evaluated_host) *evaluated_host = (uint64_t)units * 256ull * (uint64_t)ISR_SUB_TILE;

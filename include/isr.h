@@ -156,6 +156,10 @@ int isr_get_nn_pruning(void);
  * sub-tiles x queries, padded lanes included) and the pairs they answered for (nq x nt x
  * batch).  Synchronises the device, then clears both counters. */
 int isr_profile_nn_pairs(uint64_t *evaluated_host, uint64_t *answered_host);
+/* Raw per-warp event counters behind the figure above, uint64 [8], not cleared: scanned
+ * (warp, sub-tile) units, stages walked, stages skipped by their sphere, sub-tile sphere
+ * tests, warps, warps whose stage list overflowed, 2 reserved.  Synchronises the device. */
+int isr_profile_nn_counters(uint64_t *out8_host);
 
 /* Exact 1-NN of every query in its target by tiled brute force: FP32 3-FMA filter over the
  * pairs of every tile that can hold the neighbour (all tiles when pruning is off or the

@@ -70,6 +70,10 @@ if "prune" in which:
     import ctypes
     lib = _lib.load()
     def pairs():
+        c8 = (ctypes.c_uint64 * 8)()
+        _lib.check(lib.isr_profile_nn_counters(c8))
+        w = max(c8[4], 1)
+        print(f"   per warp: scanned sub-tiles {c8[0]/w:.1f}, stage spheres {c8[1]/w:.1f}, stage candidates {c8[2]/w:.1f}, exact sub tests {c8[3]/w:.1f}, flagged units {c8[5]/w:.1f}, resolve passes {c8[6]/w:.1f}; warps {c8[4]}")
         ev, an = ctypes.c_uint64(0), ctypes.c_uint64(0)
         _lib.check(lib.isr_profile_nn_pairs(ctypes.byref(ev), ctypes.byref(an)))
         return ev.value, an.value
@@ -86,7 +90,9 @@ if "prune" in which:
         lib.isr_profile_enable(1); pairs()
         r = isr.verify_poses(cd, Mqd, Mtd); torch.cuda.synchronize()
         ev, an = pairs(); lib.isr_profile_enable(0)
-        lib.isr_profile_collect(None, None)
+        ms = (ctypes.c_double * 5)(); ln = (ctypes.c_uint64 * 5)()
+        lib.isr_profile_collect(ms, ln)
+        print("   ms by kind (transform, nn, reduce, icp_acc, icp_solve):", [round(x, 3) for x in ms], list(ln))
         res[on] = r.losses.cpu().numpy()
         print(f"verify B={B} prune={on}: {best:.4f}s -> {B/best:.1f} cand/s; evaluated {ev:.3e} of {an:.3e} pairs ({ev/max(an,1)*100:.2f}%), {8*ev/best/1e12:.2f} TF/s on evaluated pairs; best {r.best_index} (k0 {k0})")
     print("verify losses identical:", np.array_equal(res[True], res[False]))
@@ -98,6 +104,8 @@ if "prune" in which:
             prob.accumulate(20.0); prob.solve(prob.ns, 0.0, 0.0, False)
         best, med = timeit(one, reps=3 if on else 1, warm=1)
         lib.isr_profile_enable(1); pairs(); one(); torch.cuda.synchronize(); ev, an = pairs(); lib.isr_profile_enable(0)
-        lib.isr_profile_collect(None, None)
+        ms = (ctypes.c_double * 5)(); ln = (ctypes.c_uint64 * 5)()
+        lib.isr_profile_collect(ms, ln)
+        print("   ms by kind (transform, nn, reduce, icp_acc, icp_solve):", [round(x, 3) for x in ms], list(ln))
         print(f"icp 1Mx1M prune={on}: {best*1e3:.2f} ms/it -> {1/best:.1f} it/s; evaluated {ev/max(an,1)*100:.3f}% of pairs; T[0,:]={prob.results(False)[0].transformation[0]}")
     api.set_nn_pruning(True)
