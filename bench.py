@@ -14,10 +14,15 @@ NCCL inside the timed region.  Rank 0 prints ONE JSON line.
   value      candidates/s with all inputs resident in HBM (device-timed, max over ranks)
   e2e        the same through the public API with pinned HOST inputs and the result read
              back to the host every step (copies inside the timed region)
-  roofline   the nearest-neighbour kernel (K2, nn2_kernel): algorithmic FP32 flops (8 per
-             point pair) / its live CUDA-event duration, against the FP32
-             CUDA-core peak.  The kernel EXECUTES 3 FMA (6 flop) per pair, so the algorithmic
-             rate may exceed the FMA peak (cap 8/6); `executed_frac` is the honest pipe load
+  roofline   the nearest-neighbour kernel of the timed region (K2, nn2_pruned_kernel): FP32
+             flops of the point pairs it EVALUATED (8 per pair; pairs counted
+             on the device) / its live CUDA-event duration, against the FP32 CUDA-core peak.
+             The kernel skips tiles that provably cannot hold a nearest neighbour (exact
+             results, like the KD-tree of the reference), so `brute_force_equivalent` -- 8 flop
+             x every pair it ANSWERED for -- is reported next to it and may exceed the peak.
+             The scan executes 3 FMA (6 flop) per pair; `executed_frac` is the honest pipe load
+  roofline_exhaustive  the same figures for the exhaustive kernel (nn2_kernel, every pair
+             evaluated, pruning switched off) on a bounded batch of the same candidates
   cpu_baseline  the float64 CPU oracle (scipy cKDTree stand-in for Open3D) on a bounded
              sample of the same candidates, on this box's host cores
   secondary  ICP iterations/s on a 1M x 1M pair (BASELINE configs[3], per rank source shard
@@ -258,8 +263,14 @@ def main():
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
+    def nn_pairs():
+        ev, an = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _lib.check(lib.isr_profile_nn_pairs(ctypes.byref(ev), ctypes.byref(an)))
+        return float(ev.value), float(an.value)
+
     lib.isr_profile_enable(1)
     lib.isr_profile_collect(None, None)
+    nn_pairs()
     _lib.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -273,6 +284,7 @@ def main():
     ms_kind = (ctypes.c_double * 5)()
     n_kind = (ctypes.c_uint64 * 5)()
     _lib.check(lib.isr_profile_collect(ms_kind, n_kind))
+    pairs_evaluated, pairs_answered = nn_pairs()
     lib.isr_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
     sel_idx, sel_loss = int(best_idx.item()), float(best_loss.item())
@@ -280,7 +292,30 @@ def main():
     value = args.candidates * world * args.steps / t_resident
     nn_ms, nn_launches = float(ms_kind[1]), int(n_kind[1])
     pairs_total = 2.0 * args.points * args.points * b_local * args.steps  # both directions
-    achieved = FLOP_PER_PAIR * pairs_total / (nn_ms * 1e-3) / 1e12 if nn_ms > 0 else None
+    assert abs(pairs_answered - pairs_total) <= 1e-9 * pairs_total, (pairs_answered, pairs_total)
+    achieved = FLOP_PER_PAIR * pairs_evaluated / (nn_ms * 1e-3) / 1e12 if nn_ms > 0 else None
+    bf_equiv = FLOP_PER_PAIR * pairs_total / (nn_ms * 1e-3) / 1e12 if nn_ms > 0 else None
+
+    # ---------------- the exhaustive kernel on a bounded batch (pruning off) ---------------
+    n_ex = min(b_local, 250)
+    api.set_nn_pruning(False)
+    try:
+        api.verify_poses(cloud_d, Mq_d[:min(n_ex, 16)], Mt_d[:min(n_ex, 16)], mode="chamfer")
+        torch.cuda.synchronize()
+        lib.isr_profile_enable(1)
+        lib.isr_profile_collect(None, None)
+        nn_pairs()
+        ex_res = api.verify_poses(cloud_d, Mq_d[:n_ex], Mt_d[:n_ex], mode="chamfer")
+        torch.cuda.synchronize()
+        ex_ms, ex_n = (ctypes.c_double * 5)(), (ctypes.c_uint64 * 5)()
+        _lib.check(lib.isr_profile_collect(ex_ms, ex_n))
+        ex_eval, ex_answered = nn_pairs()
+        lib.isr_profile_enable(0)
+    finally:
+        api.set_nn_pruning(True)
+    pr_res = api.verify_poses(cloud_d, Mq_d[:n_ex], Mt_d[:n_ex], mode="chamfer")
+    assert torch.equal(ex_res.losses, pr_res.losses), "pruned and exhaustive losses differ"
+    ex_tflops = FLOP_PER_PAIR * ex_answered / (float(ex_ms[1]) * 1e-3) / 1e12
 
     # ---------------- end-to-end arm: host buffers in, host result out -------------------
     cloud_h = torch.from_numpy(cloud).pin_memory()
@@ -341,6 +376,7 @@ def main():
         barrier()
         lib.isr_profile_enable(1)
         lib.isr_profile_collect(None, None)
+        nn_pairs()
         e0.record()
         for k in range(args.icp_iters):
             icp_iter()
@@ -348,7 +384,20 @@ def main():
         barrier()
         t_icp = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
         _lib.check(lib.isr_profile_collect(ms_kind, n_kind))
+        icp_eval, icp_answered = nn_pairs()
         lib.isr_profile_enable(0)
+        # the same loop with the exhaustive kernel (2 iterations)
+        api.set_nn_pruning(False)
+        try:
+            icp_iter()
+            barrier()
+            e0.record()
+            icp_iter()
+            e1.record()
+            barrier()
+            t_icp_ex = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        finally:
+            api.set_nn_pruning(True)
         r = prob.results(with_correspondences=False)[0]
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         ns_local = shi - slo
@@ -382,7 +431,12 @@ def main():
             "icp_iters_per_s": args.icp_iters / t_icp,
             "icp_config": f"dense ICP refine (BASELINE configs[3]): {args.icp_points} x {args.icp_points} "
                           f"points, {args.icp_iters} forced iterations, source sharded x{world}",
-            "icp_nn_tflops": FLOP_PER_PAIR * ns_local * args.icp_points * n_kind[1] / (ms_kind[1] * 1e-3) / 1e12,
+            "icp_nn_pairs_evaluated_frac": icp_eval / max(icp_answered, 1.0),
+            "icp_nn_tflops_evaluated": FLOP_PER_PAIR * icp_eval / (ms_kind[1] * 1e-3) / 1e12,
+            "icp_nn_tflops_brute_force_equivalent": FLOP_PER_PAIR * icp_answered / (ms_kind[1] * 1e-3) / 1e12,
+            "icp_nn_ms_per_iter": ms_kind[1] / max(n_kind[1], 1),
+            "icp_exhaustive_iters_per_s": 1.0 / t_icp_ex,
+            "icp_exhaustive_nn_tflops": FLOP_PER_PAIR * ns_local * args.icp_points / t_icp_ex / 1e12,
             "icp_fitness": r.fitness, "icp_inlier_rmse": r.inlier_rmse,
             "k1_transform_gbs": k1_bytes / t_k1 / 1e9,
             "k1_transform_frac_of_hbm": k1_bytes / t_k1 / 1e9 / hbm,
@@ -419,12 +473,12 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")) as f:
-            per_pair = json.load(f).get("dram_bytes_per_cloud_pair")
-        # ncu capture held 40 cloud pairs per launch; a bench launch holds this many
+            per_pair = json.load(f).get("pruned_dram_bytes_per_cloud_pair")
+        # ncu capture held 64 cloud pairs per launch; a bench launch holds this many
         traffic = per_pair * (2.0 * b_local * args.steps / max(nn_launches, 1))
     except Exception:
         pass
-    per_launch_flop = FLOP_PER_PAIR * pairs_total / max(nn_launches, 1)
+    per_launch_flop = FLOP_PER_PAIR * pairs_evaluated / max(nn_launches, 1)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_resident / args.steps,
@@ -435,10 +489,15 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {
-            "kernel": "nn2_kernel (K2 brute-force nearest neighbour: FP32 3-FMA filter scan over every "
-                      "pair + FP64 resolve inside the error window)",
+            "kernel": "nn2_pruned_kernel (K2 tiled brute-force nearest neighbour: FP32 3-FMA filter scan "
+                      "of every 256-query x 64-target tile pair that can hold a neighbour + FP64 resolve "
+                      "inside the error window; tiles ruled out by their bounding spheres are skipped)",
             "bound": "fp32", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
             "frac": achieved / peak_nominal if achieved else None,
+            "achieved_definition": "8 flop x point pairs evaluated (device counter) / kernel time",
+            "pairs_evaluated_frac": pairs_evaluated / pairs_total,
+            "brute_force_equivalent": bf_equiv,
+            "brute_force_equivalent_frac": bf_equiv / peak_nominal if bf_equiv else None,
             "peak_source": f"nominal {sm_count.value} SM x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz "
                            "(MEASURED_PEAKS.json holds no FP32 CUDA-core figure)",
             "peak_measured_ffma": ffma_measured,
@@ -450,6 +509,17 @@ def main():
             "avg_launch_ms": nn_ms / max(nn_launches, 1),
             "kernel_share_of_step": nn_ms * 1e-3 / t_resident,
             "traffic": traffic,
+        },
+        "roofline_exhaustive": {
+            "kernel": "nn2_kernel (pruning off: FP32 3-FMA filter scan over EVERY pair + FP64 resolve)",
+            "bound": "fp32", "achieved": ex_tflops, "peak": peak_nominal, "unit": "TFLOP/s",
+            "frac": ex_tflops / peak_nominal,
+            "frac_of_measured_ffma": ex_tflops / ffma_measured,
+            "executed_frac": ex_tflops * 6.0 / 8.0 / peak_nominal,
+            "candidates": n_ex, "candidates_per_s": n_ex / (float(ex_ms[1]) * 1e-3),
+            "launches": int(ex_n[1]), "avg_launch_ms": float(ex_ms[1]) / max(int(ex_n[1]), 1),
+            "pairs_evaluated_frac": ex_eval / max(ex_answered, 1.0),
+            "losses_identical_to_pruned": True,
         },
         "cpu_baseline": cpu,
         "secondary": secondary,

@@ -475,6 +475,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     const int lane = tid & 31, warp = tid >> 5;
     const int q0 = blockIdx.x * (WARPS * 32 * Q) + warp * (32 * Q) + lane;
     if (q0 - lane >= p.nq) return;  // this warp has no live query; warps never meet at a barrier
+    const long long t_start = clock64();
     PrunedWarpSmem<SUB, Q> &ws = reinterpret_cast<PrunedWarpSmem<SUB, Q> *>(smem_raw)[warp];
     const float *__restrict__ gq = p.q + (long long)b * p.q_bstride;
     const float *__restrict__ gt = p.t + (long long)b * p.t_bstride;
@@ -762,6 +763,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         atomicAdd(p.evaluated + 4, 1ull);                         // warps
         atomicAdd(p.evaluated + 5, (unsigned long long)nflag);    // scanned units that flagged
         atomicAdd(p.evaluated + 6, (unsigned long long)npass);    // resolve passes (warp level)
+        // slowest warp: cycles / 1024, with its scanned units and exact tests
+        const unsigned long long cyc = (unsigned long long)(clock64() - t_start) >> 10;
+        atomicMax(p.evaluated + 7, (cyc << 44) | ((unsigned long long)(nscanned & 0xFFFFFu) << 24) |
+                                       (unsigned long long)(ntests & 0xFFFFFFu));
     }
 
     for (int r = 0; r < Q; ++r) {
@@ -852,6 +857,8 @@ struct NN2PrunedVariant {
     static int ctas_per_sm() { return MINB; }
 };
 using NN2Pruned = NN2PrunedVariant<8, 4, 64, 4, 1>;
+using NN2Pruned2 = NN2PrunedVariant<8, 2, 64, 8, 1>;
+using NN2Pruned1 = NN2PrunedVariant<8, 1, 64, 16, 1>;
 static_assert(NN2Pruned::kSmem <= 48 * 1024, "pruned kernel uses the default dynamic shared memory limit");
 constexpr int kMaxSplits = 32;
 
@@ -1063,6 +1070,10 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
 #endif
     if (t->sub_c != nullptr && t->stage_c != nullptr && pruning_on()) {
         ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
+        static int pw = -1;
+        if (pw < 0) { const char *e = getenv("ISR_NN_PWARPS"); pw = e ? atoi(e) : 1; }
+        if (pw == 1) return nn2_dispatch<NN2Pruned1>(c);
+        if (pw == 2) return nn2_dispatch<NN2Pruned2>(c);
         return nn2_dispatch<NN2Pruned>(c);
     }
     return nn2_dispatch<NN2Main>(c);
