@@ -217,47 +217,52 @@ __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__
             }
             double Db = Dbest_l[r];
             int ib = ibest_l[r];
+            // pass 1, branch-free: which targets fall inside the window?  (Lanes hit in
+            // different places; a branch here would run the FP64 code once per hit position.)
+            static_assert(SUB <= 64, "window mask is 64 bits");
+            u64 wmask = 0;
+#pragma unroll 4
             for (int g = 0; g < SUB / 4; ++g) {
                 const float4 X = sx[g], Y = sy[g], Z = sz[g], N = sn[g];
-                const float pxs[4] = {X.x, X.y, X.z, X.w}, pys[4] = {Y.x, Y.y, Y.z, Y.w},
-                            pzs[4] = {Z.x, Z.y, Z.z, Z.w}, pns[4] = {N.x, N.y, N.z, N.w};
-                float as[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    as[k] = __fmaf_rn(cx, pxs[k], __fmaf_rn(cy, pys[k], __fmaf_rn(cz, pzs[k], pns[k])));
-                if (fminf(fminf(as[0], as[1]), fminf(as[2], as[3])) <= th) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (as[k] <= th) {
-                            const int j = 4 * g + k;
-                            const float px = pxs[k], py = pys[k], pz = pzs[k];
+                const float a0 = __fmaf_rn(cx, X.x, __fmaf_rn(cy, Y.x, __fmaf_rn(cz, Z.x, N.x)));
+                const float a1 = __fmaf_rn(cx, X.y, __fmaf_rn(cy, Y.y, __fmaf_rn(cz, Z.y, N.y)));
+                const float a2 = __fmaf_rn(cx, X.z, __fmaf_rn(cy, Y.z, __fmaf_rn(cz, Z.z, N.z)));
+                const float a3 = __fmaf_rn(cx, X.w, __fmaf_rn(cy, Y.w, __fmaf_rn(cz, Z.w, N.w)));
+                const unsigned bits = (a0 <= th ? 1u : 0u) | (a1 <= th ? 2u : 0u) | (a2 <= th ? 4u : 0u) |
+                                      (a3 <= th ? 8u : 0u);
+                wmask |= (u64)bits << (4 * g);
+            }
+            // pass 2: exact FP64 distance of those few (ascending stored position)
+            const float *fx = reinterpret_cast<const float *>(sx);
+            const float *fy = reinterpret_cast<const float *>(sy);
+            const float *fz = reinterpret_cast<const float *>(sz);
+            for (; wmask != 0; wmask &= wmask - 1) {
+                const int j = __ffsll((long long)wmask) - 1;
+                const float px = fx[j], py = fy[j], pz = fz[j];
 #ifdef ISR_NN_TUNING
-                            if (p.dbg != nullptr) atomicAdd(p.dbg + 3, 1ull);  // exact evaluations
+                if (p.dbg != nullptr) atomicAdd(p.dbg + 3, 1ull);  // exact evaluations
 #endif
-                            double dx = (double)qhx - (double)px, dy = (double)qhy - (double)py,
-                                   dz = (double)qhz - (double)pz;
-                            if (p.use_lo) {
-                                const long long gj = gbase + j;
-                                dx += qlx - (double)gt[4ll * p.nt_pad + gj];
-                                dy += qly - (double)gt[5ll * p.nt_pad + gj];
-                                dz += qlz - (double)gt[6ll * p.nt_pad + gj];
-                            }
-                            const double D = fma(dz, dz, fma(dy, dy, dx * dx));
-                            // strict minimum; on an exact tie the lower ORIGINAL index wins
-                            // (tiles are not visited in index order and storage is permuted)
-                            bool take = D < Db;
-                            if (D == Db) {
-                                const int cand = gbase + j;
-                                const int oc = p.perm_t != nullptr ? p.perm_t[min(cand, p.nt - 1)] : cand;
-                                const int ob = p.perm_t != nullptr ? p.perm_t[min(ib, p.nt - 1)] : ib;
-                                take = oc < ob;
-                            }
-                            if (take) {
-                                Db = D;
-                                ib = gbase + j;
-                            }
-                        }
-                    }
+                double dx = (double)qhx - (double)px, dy = (double)qhy - (double)py,
+                       dz = (double)qhz - (double)pz;
+                if (p.use_lo) {
+                    const long long gj = gbase + j;
+                    dx += qlx - (double)gt[4ll * p.nt_pad + gj];
+                    dy += qly - (double)gt[5ll * p.nt_pad + gj];
+                    dz += qlz - (double)gt[6ll * p.nt_pad + gj];
+                }
+                const double D = fma(dz, dz, fma(dy, dy, dx * dx));
+                // strict minimum; on an exact tie the lower ORIGINAL index wins
+                // (tiles are not visited in index order and storage is permuted)
+                bool take = D < Db;
+                if (D == Db) {
+                    const int cand = gbase + j;
+                    const int oc = p.perm_t != nullptr ? p.perm_t[min(cand, p.nt - 1)] : cand;
+                    const int ob = p.perm_t != nullptr ? p.perm_t[min(ib, p.nt - 1)] : ib;
+                    take = oc < ob;
+                }
+                if (take) {
+                    Db = D;
+                    ib = gbase + j;
                 }
             }
             Dbest_l[r] = Db;

@@ -1,4 +1,4 @@
-// Spatial ordering of a cloud (Morton / Z-order) -- preprocessing for the filtered
+// Spatial ordering of a cloud (Hilbert curve) -- preprocessing for the filtered
 // nearest-neighbour kernel (nn2.cu), once per cloud.
 //
 // The brute-force scan visits every pair whatever the order, but how often its rare
@@ -9,9 +9,9 @@
 // them itself.  Results are always reported in the caller's original indexing.
 //
 //   bbox_kernel        min/max of the cloud (single CTA)
-//   morton_keys_kernel key = (30-bit Morton code of the cubic-cell quantised point) << 32 | index
+//   morton_keys_kernel key = (30-bit Hilbert index of the cubic-cell quantised point) << 32 | index
 //   bitonic_*          sort of the 64-bit keys (unique => deterministic, stable in the index)
-//   extract_perm       perm[i] = original index of the i-th point in Morton order
+//   extract_perm       perm[i] = original index of the i-th point along the curve
 #include <math_constants.h>
 
 #include "isr_common.cuh"
@@ -85,7 +85,30 @@ __global__ void morton_keys_kernel(const float *__restrict__ pts, int64_t n, int
         const float v = (pts[3 * i + c] - bbox[c]) * sc;
         q[c] = (unsigned)fminf(fmaxf(v, 0.0f), 1023.0f);
     }
-    const unsigned code = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
+    // Hilbert index of the cell (Skilling's transpose form, 10 bits per axis): unlike the
+    // Z-curve it never jumps, so every run of consecutive points -- a query row, a sub-tile, a
+    // stage -- is one connected patch and its bounding sphere stays tight.
+    constexpr unsigned M = 1u << 9;
+    for (unsigned Q = M; Q > 1; Q >>= 1) {
+        const unsigned P = Q - 1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (q[c] & Q) {
+                q[0] ^= P;
+            } else {
+                const unsigned t = (q[0] ^ q[c]) & P;
+                q[0] ^= t;
+                q[c] ^= t;
+            }
+        }
+    }
+    q[1] ^= q[0];
+    q[2] ^= q[1];
+    unsigned t = 0;
+    for (unsigned Q = M; Q > 1; Q >>= 1)
+        if (q[2] & Q) t ^= Q - 1;
+    q[0] ^= t; q[1] ^= t; q[2] ^= t;
+    const unsigned code = (spread10(q[0]) << 2) | (spread10(q[1]) << 1) | spread10(q[2]);
     keys[i] = ((u64)code << 32) | (u64)(unsigned)i;
 }
 

@@ -53,8 +53,44 @@ def test_prepare_cloud_hi_lo_planes(gpu):
     np.testing.assert_allclose(cg, pts.astype(np.float64).mean(0), rtol=0, atol=1e-10)
 
 
+def _hilbert_code(q, bits=10):
+    """3-D Hilbert index (Skilling's transpose form), numpy restatement of sort.cu."""
+    X = [q[:, c].astype(np.uint32).copy() for c in range(3)]
+    M = 1 << (bits - 1)
+    Q = M
+    while Q > 1:
+        P = Q - 1
+        for c in range(3):
+            m = (X[c] & Q) != 0
+            X[0] = np.where(m, X[0] ^ P, X[0])
+            t = np.where(m, 0, (X[0] ^ X[c]) & P).astype(np.uint32)
+            X[0] ^= t
+            X[c] ^= t
+        Q >>= 1
+    X[1] ^= X[0]
+    X[2] ^= X[1]
+    t = np.zeros_like(X[0])
+    Q = M
+    while Q > 1:
+        t = np.where((X[2] & Q) != 0, t ^ (Q - 1), t).astype(np.uint32)
+        Q >>= 1
+    code = np.zeros(len(q), dtype=np.uint64)
+    for bit in range(bits - 1, -1, -1):
+        for c in range(3):
+            code = (code << np.uint64(1)) | (((X[c] ^ t) >> bit) & 1).astype(np.uint64)
+    return code
+
+
+def test_hilbert_restatement_is_a_continuous_curve():
+    g = np.stack(np.meshgrid(*[np.arange(16)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    code = _hilbert_code(g, bits=4)
+    assert len(np.unique(code)) == len(code)
+    steps = np.abs(np.diff(g[np.argsort(code)], axis=0)).sum(1)
+    assert steps.min() == 1 and steps.max() == 1
+
+
 @pytest.mark.parametrize("n", [1, 5, 2048, 2049, 70001])
-def test_spatial_order_is_a_morton_sorted_permutation(gpu, n):
+def test_spatial_order_is_a_hilbert_sorted_permutation(gpu, n):
     rng = np.random.default_rng(n)
     pts = rng.normal(scale=50, size=(n, 3)).astype(np.float32)
     perm = gpu.spatial_order(pts).cpu().numpy()
@@ -62,14 +98,7 @@ def test_spatial_order_is_a_morton_sorted_permutation(gpu, n):
     lo, hi = pts.min(0), pts.max(0)
     ext = max(float((hi - lo).max()), 1e-30)
     q = np.clip(((pts - lo) * np.float32(1023.0 / ext)), 0, 1023).astype(np.uint64)
-
-    def spread(v):
-        v = (v | (v << 16)) & 0x030000FF
-        v = (v | (v << 8)) & 0x0300F00F
-        v = (v | (v << 4)) & 0x030C30C3
-        v = (v | (v << 2)) & 0x09249249
-        return v
-    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    code = _hilbert_code(q)
     key = (code[perm].astype(np.uint64) << np.uint64(32)) | perm.astype(np.uint64)
     # allow for float rounding of the quantisation at cell borders: codes must be sorted in
     # all but a handful of places, and identical inputs always give the identical permutation
