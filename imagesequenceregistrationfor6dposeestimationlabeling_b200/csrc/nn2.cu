@@ -84,6 +84,7 @@ struct NN2Params {
     const float4 *sub_c;     // [batch][stages_total * STAGE/SUB] sub-tile spheres (PRUNE)
     long long sub_c_bstride;
     unsigned long long *evaluated;  // profiling: scanned (warp, sub-tile) units, or NULL
+    const int *order;        // [batch][gridDim.x] query block run by CTA x of batch item b, or NULL
 };
 
 // Can this lane rule out every point of the tile with sphere S for all of its Q queries?
@@ -132,7 +133,7 @@ __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__
                                              float (&thr)[Q], float *mt_l, float *thr_l,
                                              float *tm_l, double *Dbest_l, int *ibest_l,
                                              float *dq_l, float &dmax, unsigned &nflag,
-                                             unsigned &npass) {
+                                             unsigned &npass, const float *qsm = nullptr) {
     float tm[Q];
 #pragma unroll
     for (int r = 0; r < Q; ++r) tm[r] = CUDART_INF_F;
@@ -202,7 +203,11 @@ __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__
             }
 #endif
             const int qi = min(q0 + r * 32, p.nq_pad - 1);
-            const float qhx = gq[qi], qhy = gq[p.nq_pad + qi], qhz = gq[2ll * p.nq_pad + qi];
+            // the query's coordinates: from the warp's shared-memory copy when there is one
+            // (qsm: [6][32 * Q], hi xyz then lo xyz), else from global memory
+            const int qs = r * 32 + lane;
+            const float qhx = PRUNE ? qsm[qs] : gq[qi], qhy = PRUNE ? qsm[32 * Q + qs] : gq[p.nq_pad + qi],
+                        qhz = PRUNE ? qsm[2 * 32 * Q + qs] : gq[2ll * p.nq_pad + qi];
             const float cx = -2.0f * qhx, cy = -2.0f * qhy, cz = -2.0f * qhz;
             const float nq2 = __fmaf_rn(qhz, qhz, __fmaf_rn(qhy, qhy, qhx * qhx));
             const float m = fminf(mt_l[r], tm_l[r]);
@@ -211,9 +216,9 @@ __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__
             thr_l[r] = th;
             double qlx = 0.0, qly = 0.0, qlz = 0.0;
             if (p.use_lo) {
-                qlx = gq[4ll * p.nq_pad + qi];
-                qly = gq[5ll * p.nq_pad + qi];
-                qlz = gq[6ll * p.nq_pad + qi];
+                qlx = PRUNE ? qsm[3 * 32 * Q + qs] : gq[4ll * p.nq_pad + qi];
+                qly = PRUNE ? qsm[4 * 32 * Q + qs] : gq[5ll * p.nq_pad + qi];
+                qlz = PRUNE ? qsm[5 * 32 * Q + qs] : gq[6ll * p.nq_pad + qi];
             }
             double Db = Dbest_l[r];
             int ib = ibest_l[r];
@@ -455,7 +460,7 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
 
 // ---- pruned kernel: warp-autonomous, sub-tile granularity ------------------------------------
 constexpr int kRing = 4;    // sub-tile buffers in flight per warp
-constexpr int kFifo = 64;   // candidate sub-tiles queued per warp
+constexpr int kFifo = 96;   // candidate sub-tiles queued per warp
 constexpr int kAnchors = 4; // seed queries per warp
 
 template <int SUB, int Q>
@@ -467,18 +472,22 @@ struct alignas(128) PrunedWarpSmem {
     float4 row[Q];             // sphere (c, rho) of query row r = the 32 queries r*32 .. r*32+31
     float rowB[Q];             // max of their bounds dq (refreshed between batches of work)
     uint64_t full[kRing];
+    float qs[6][32 * Q];       // the warp's queries, hi xyz and lo xyz (read by the resolve path)
 };
 
-template <int Q, int WARPS, int SUB, int MINB, int UNR>
+template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG>
 __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2Params p) {
-    static_assert(SUB == ISR_SUB_TILE && ISR_SOA_TILE / SUB <= 32 && Q == 8, "pruning uses the spheres of prepare.cu");
+    static_assert(SUB == ISR_SUB_TILE && ISR_SOA_TILE / SUB == 16 && Q == 8, "pruning uses the spheres of prepare.cu");
     constexpr int SUBS = ISR_SOA_TILE / SUB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.z;
     if (p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) return;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int q0 = blockIdx.x * (WARPS * 32 * Q) + warp * (32 * Q) + lane;
+    // heaviest query blocks first (order from block_order_kernel): the grid is only a few
+    // waves deep for a single cloud pair, and a late-starting heavy block would be its tail
+    const int blk = p.order != nullptr ? p.order[(long long)b * gridDim.x + blockIdx.x] : (int)blockIdx.x;
+    const int q0 = blk * (WARPS * 32 * Q) + warp * (32 * Q) + lane;
     if (q0 - lane >= p.nq) return;  // this warp has no live query; warps never meet at a barrier
     const long long t_start = clock64();
     PrunedWarpSmem<SUB, Q> &ws = reinterpret_cast<PrunedWarpSmem<SUB, Q> *>(smem_raw)[warp];
@@ -508,6 +517,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         const bool live = q0 + r * 32 < p.nq;
         thr[r] = live ? CUDART_INF_F : -CUDART_INF_F;
         if (live) dmax = CUDART_INF_F;
+        ws.qs[0][r * 32 + lane] = -0.5f * q2x[r];
+        ws.qs[1][r * 32 + lane] = -0.5f * q2y[r];
+        ws.qs[2][r * 32 + lane] = -0.5f * q2z[r];
+        if (p.use_lo) {
+            ws.qs[3][r * 32 + lane] = gq[4ll * p.nq_pad + i];
+            ws.qs[4][r * 32 + lane] = gq[5ll * p.nq_pad + i];
+            ws.qs[5][r * 32 + lane] = gq[6ll * p.nq_pad + i];
+        }
     }
     for (int r = 0; r < Q; ++r) {  // run-time loop on purpose
         const bool live = q0 + r * 32 < p.nq;
@@ -671,6 +688,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     //            candidate stage the exact test, and its 16 sub-tile spheres -> coarse row test
     //            -> FIFO.
     unsigned nscanned = 0, ntests = 0, ncand = 0, nflag = 0, npass = 0;
+    unsigned refreshed_at = ~0u;
     bool seeding = true;   // the seeds must be scanned before anything is produced
     int base = 0;          // next chunk of stage spheres
     int cbase = 0;         // base of the chunk whose candidates are in smask
@@ -680,7 +698,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     for (;;) {
         const int pending = tail - head;
         const bool produced_all = smask == 0 && base >= stages;
-        if (pending > 0 && (seeding || produced_all || pending > kFifo - SUBS)) {
+        if (pending > 0 && (seeding || produced_all || pending > kFifo - 2 * SUBS)) {
             while (look < tail && nloads - nconsumed < kRing) {
                 const int e = look % kFifo;
                 ++ntests;
@@ -706,10 +724,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                 const int slot = nconsumed % kRing;
                 mbar_wait(&ws.full[slot], (nconsumed / kRing) & 1);
                 ++nscanned;
+                // scanned in FLAG-sized pieces (FLAG == SUB in the shipped variant)
                 const float4 *sx = reinterpret_cast<const float4 *>(&ws.buf[slot][0][0]);
-                scan_subtile<Q, SUB, UNR, true>(p, gq, gt, q0, lane, sx, sx + SUB / 4, sx + 2 * (SUB / 4),
-                                                sx + 3 * (SUB / 4), id * SUB, q2x, q2y, q2z, thr, mt_l,
-                                                thr_l, tm_l, Dbest_l, ibest_l, dq_l, dmax, nflag, npass);
+#pragma unroll 1
+                for (int h = 0; h < SUB / FLAG; ++h)
+                    scan_subtile<Q, FLAG, UNR, true>(p, gq, gt, q0, lane, sx + h * (FLAG / 4),
+                                                     sx + SUB / 4 + h * (FLAG / 4),
+                                                     sx + 2 * (SUB / 4) + h * (FLAG / 4),
+                                                     sx + 3 * (SUB / 4) + h * (FLAG / 4), id * SUB + h * FLAG,
+                                                     q2x, q2y, q2z, thr, mt_l, thr_l, tm_l, Dbest_l, ibest_l,
+                                                     dq_l, dmax, nflag, npass, &ws.qs[0][0]);
                 ++nconsumed;
                 __syncwarp();  // every lane is done with the slot before lane 0 refills it
             }
@@ -719,8 +743,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         seeding = false;
         if (produced_all) break;
         if (smask == 0) {
-            // next chunk: refresh the row bounds, coarse-test 32 stage spheres
-            refresh_bounds();
+            // next chunk: refresh the row bounds (if any scan ran since), coarse-test 32 stage spheres
+            if (nscanned != refreshed_at) {
+                refresh_bounds();
+                refreshed_at = nscanned;
+            }
             cbase = base;
             base += 32;
             const int s = cbase + lane;
@@ -729,33 +756,44 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
             smask = __ballot_sync(0xffffffffu, rows_st != 0);
             continue;
         }
-        const int l = __ffs(smask) - 1;
+        // two candidate stages per step: lanes 0-15 take the sub-tiles of the first, lanes
+        // 16-31 those of the second (one dependent global load serves both)
+        const int l1 = __ffs(smask) - 1;
         smask &= smask - 1;
+        const int l2 = smask != 0 ? __ffs(smask) - 1 : -1;
+        smask &= smask - 1;  // (0 & anything = 0)
+        bool pass1, pass2 = false;
         {
-            const float4 S = make_float4(__shfl_sync(0xffffffffu, Sst.x, l), __shfl_sync(0xffffffffu, Sst.y, l),
-                                         __shfl_sync(0xffffffffu, Sst.z, l), __shfl_sync(0xffffffffu, Sst.w, l));
-            if (!exact_any(S, __shfl_sync(0xffffffffu, rows_st, l))) continue;
+            const float4 S = make_float4(__shfl_sync(0xffffffffu, Sst.x, l1), __shfl_sync(0xffffffffu, Sst.y, l1),
+                                         __shfl_sync(0xffffffffu, Sst.z, l1), __shfl_sync(0xffffffffu, Sst.w, l1));
+            pass1 = exact_any(S, __shfl_sync(0xffffffffu, rows_st, l1));
         }
-        ++ncand;
+        if (l2 >= 0) {
+            const float4 S = make_float4(__shfl_sync(0xffffffffu, Sst.x, l2), __shfl_sync(0xffffffffu, Sst.y, l2),
+                                         __shfl_sync(0xffffffffu, Sst.z, l2), __shfl_sync(0xffffffffu, Sst.w, l2));
+            pass2 = exact_any(S, __shfl_sync(0xffffffffu, rows_st, l2));
+        }
+        if (!pass1 && !pass2) continue;
+        ncand += (pass1 ? 1u : 0u) + (pass2 ? 1u : 0u);
         {
-            // the stage's sub-tile spheres, one per lane
             float4 S = make_float4(0.f, 0.f, 0.f, -1.f);
             unsigned rows = 0;
-            const int gid = (cbase + l) * SUBS + lane;
-            if (lane < SUBS) {
+            const bool mine = lane < SUBS ? pass1 : pass2;
+            const int gid = (cbase + (lane < SUBS ? l1 : l2)) * SUBS + (lane & (SUBS - 1));
+            if (mine) {
                 S = sub_c[gid];
                 rows = coarse_rows(S);
 #pragma unroll
                 for (int a = 0; a < kAnchors; ++a) rows = gid == seed[a] ? 0u : rows;  // already scanned
             }
-            const unsigned m16 = __ballot_sync(0xffffffffu, rows != 0);
+            const unsigned m32 = __ballot_sync(0xffffffffu, rows != 0);
             if (rows != 0) {
-                const int pos = (tail + __popc(m16 & ((1u << lane) - 1u))) % kFifo;
+                const int pos = (tail + __popc(m32 & ((1u << lane) - 1u))) % kFifo;
                 ws.sph[pos] = S;
                 ws.id[pos] = gid;
                 ws.rows[pos] = rows;
             }
-            tail += __popc(m16);
+            tail += __popc(m32);
             __syncwarp();
         }
     }
@@ -784,6 +822,78 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
             if (p.out_idx != nullptr) p.out_idx[o] = jo;
         }
     }
+}
+
+// ---- launch order of the pruned kernel's query blocks -----------------------------------------
+// Work per block grows with the spread of its queries (a block that straddles a gap of the
+// curve needs the neighbourhoods of both sides).  weight = squared radius of the block about
+// its centroid; blocks are launched in descending weight (longest-processing-time first).
+constexpr int kOrderMax = 4096;  // blocks per batch item that the single-CTA sort handles
+
+// one warp per (batch item, block of QB queries)
+template <int QB>
+__global__ void __launch_bounds__(128)
+block_weight_kernel(const float *__restrict__ q, long long q_bstride, int nq, int nq_pad, int nqb,
+                    int batch, u64 *__restrict__ keys) {
+    const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= nqb * batch) return;
+    const int b = w / nqb, blk = w % nqb;
+    const float *gq = q + (long long)b * q_bstride;
+    float x[QB / 32], y[QB / 32], z[QB / 32];
+    float sx = 0.f, sy = 0.f, sz = 0.f, sn = 0.f;
+#pragma unroll
+    for (int r = 0; r < QB / 32; ++r) {
+        const int i = blk * QB + r * 32 + lane;
+        const bool live = i < nq;
+        const int ii = min(i, nq_pad - 1);
+        x[r] = gq[ii]; y[r] = gq[nq_pad + ii]; z[r] = gq[2ll * nq_pad + ii];
+        if (live) { sx += x[r]; sy += y[r]; sz += z[r]; sn += 1.f; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        sn += __shfl_xor_sync(0xffffffffu, sn, o);
+    }
+    const float inv = sn > 0.f ? 1.f / sn : 0.f;
+    sx *= inv; sy *= inv; sz *= inv;
+    float m = 0.f;
+#pragma unroll
+    for (int r = 0; r < QB / 32; ++r) {
+        if (blk * QB + r * 32 + lane < nq) {
+            const float dx = x[r] - sx, dy = y[r] - sy, dz = z[r] - sz;
+            m = fmaxf(m, dx * dx + dy * dy + dz * dz);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // ascending sort of ~bits(weight) = descending weight; ties by ascending block index
+    if (lane == 0) keys[w] = ((u64)(~__float_as_uint(m)) << 32) | (u64)(unsigned)blk;
+}
+
+// one CTA per batch item: bitonic sort of its <= kOrderMax keys, order[i] = block of rank i
+__global__ void __launch_bounds__(1024)
+block_order_kernel(const u64 *__restrict__ keys, int nqb, int *__restrict__ order) {
+    __shared__ u64 s[kOrderMax];
+    const int b = blockIdx.x;
+    int n2 = 1;
+    while (n2 < nqb) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += 1024) s[i] = i < nqb ? keys[(long long)b * nqb + i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < n2 / 2; t += 1024) {
+                const int i = 2 * t - (t & (j - 1));
+                const bool asc = (i & k) == 0;
+                const u64 a = s[i], c = s[i + j];
+                if ((a > c) == asc) { s[i] = c; s[i + j] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < nqb; i += 1024) order[(long long)b * nqb + i] = (int)(unsigned)(s[i] & 0xffffffffull);
 }
 
 // partial results carry original indices; exact ties go to the lower one
@@ -846,7 +956,7 @@ struct NN2Variant {
 using NN2Main = NN2Variant<8, 128, 1024, 3, 64, 4, 1>;
 
 // the pruned kernel: WARPS independent warps of 32 x Q queries per CTA
-template <int Q, int WARPS, int SUB, int MINB, int UNR>
+template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG>
 struct NN2PrunedVariant {
     static constexpr int kQueriesPerCta = Q * WARPS * 32;
     static constexpr int kStage = ISR_SOA_TILE;
@@ -854,16 +964,18 @@ struct NN2PrunedVariant {
     static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q>);
 
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
-        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR>;
+        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG>;
         ProfScope prof(kProfNN, st);
         kern<<<grid, WARPS * 32, kSmem, st>>>(p);
         return launched("nn2_pruned_kernel");
     }
     static int ctas_per_sm() { return MINB; }
 };
-using NN2Pruned = NN2PrunedVariant<8, 4, 64, 4, 1>;
-using NN2Pruned2 = NN2PrunedVariant<8, 2, 64, 8, 1>;
-using NN2Pruned1 = NN2PrunedVariant<8, 1, 64, 16, 1>;
+// one warp per CTA: a finished warp frees its slot at once (measured 5 % faster than 4-warp
+// CTAs, whose slowest warp holds the registers and shared memory of the other three)
+// (flag granularity FLAG = 32 / 16 targets inside the 64-target pruning unit was measured
+// 2 % / 19 % slower than 64: more, shorter resolve passes)
+using NN2Pruned = NN2PrunedVariant<8, 1, 64, 16, 1, 64>;
 static_assert(NN2Pruned::kSmem <= 48 * 1024, "pruned kernel uses the default dynamic shared memory limit");
 constexpr int kMaxSplits = 32;
 
@@ -907,6 +1019,10 @@ static int choose_splits(long long ctas, int stages, int slots) {
     return splits;
 }
 
+static size_t order_workspace_bytes(long long nqb, long long batch) {
+    return align256((size_t)nqb * batch * 8) + align256((size_t)nqb * batch * 4);
+}
+
 struct NN2Call {
     const IsrCloud *q;
     const IsrCloud *t;
@@ -946,6 +1062,20 @@ static int nn2_dispatch(const NN2Call &c) {
         p.evaluated = evaluated_counter();
         g_answered.fetch_add((unsigned long long)nq * (unsigned long long)c.t->n *
                              (unsigned long long)c.batch);
+    }
+    p.order = nullptr;
+    if (V::kPrune && nqb > 1 && nqb <= kOrderMax && c.workspace != nullptr &&
+        c.workspace_bytes >= order_workspace_bytes(nqb, c.batch)) {
+        u64 *keys = reinterpret_cast<u64 *>(c.workspace);
+        int *order = reinterpret_cast<int *>(reinterpret_cast<char *>(c.workspace) +
+                                             align256((size_t)nqb * c.batch * 8));
+        const long long warps = (long long)nqb * c.batch;
+        block_weight_kernel<V::kQueriesPerCta><<<(unsigned)((warps + 3) / 4), 128, 0, c.st>>>(
+            p.q, p.q_bstride, p.nq, p.nq_pad, nqb, (int)c.batch, keys);
+        ISR_TRY(launched("block_weight_kernel"));
+        block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, order);
+        ISR_TRY(launched("block_order_kernel"));
+        p.order = order;
     }
     p.dbg = nullptr;
 #ifdef ISR_NN_TUNING
@@ -1020,9 +1150,12 @@ size_t isr_nn2_workspace_bytes(int64_t nq, int64_t nt, int64_t batch) {
     const int64_t nt_pad = isr_soa_padded_len(nt);
     const int nqb = (int)((nq + 2047) / 2048);  // largest CTA tile of any variant
     const int splits = choose_splits((long long)nqb * batch, (int)(nt_pad / 512), kSlotsUpperBound);
-    if (splits <= 1) return 256;
+    // launch order of the pruned kernel's 256-query blocks
+    const size_t ord = order_workspace_bytes((nq + 255) / 256, batch);
+    if (splits <= 1) return ord;
     const size_t total = (size_t)nq * (size_t)batch;
-    return align256(total * splits * 8) + align256(total * splits * 4);
+    const size_t part = align256(total * splits * 8) + align256(total * splits * 4);
+    return part > ord ? part : ord;
 }
 
 int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, float *out_d2,
@@ -1075,10 +1208,6 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
 #endif
     if (t->sub_c != nullptr && t->stage_c != nullptr && pruning_on()) {
         ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
-        static int pw = -1;
-        if (pw < 0) { const char *e = getenv("ISR_NN_PWARPS"); pw = e ? atoi(e) : 1; }
-        if (pw == 1) return nn2_dispatch<NN2Pruned1>(c);
-        if (pw == 2) return nn2_dispatch<NN2Pruned2>(c);
         return nn2_dispatch<NN2Pruned>(c);
     }
     return nn2_dispatch<NN2Main>(c);

@@ -114,7 +114,7 @@ static VerifyLayout verify_layout(int64_t nq, int64_t nt, int64_t b, int bidirec
     L.sub_y = off; off += align256((size_t)L.chunk * (ntp / ISR_SUB_TILE) * 16);
     L.sortws = off; off += isr_spatial_order_workspace_bytes(big);
     const size_t w1 = isr_nn_workspace_bytes(big, big, L.chunk);
-    const size_t w2 = isr_nn2_workspace_bytes(nq < nt ? nq : nt, big, L.chunk);
+    const size_t w2 = isr_nn2_workspace_bytes(big, big, L.chunk);
     L.nnws = off; off += w1 > w2 ? w1 : w2;
     L.total = off;
     return L;
