@@ -40,7 +40,7 @@ class IsrCloud(ctypes.Structure):
     """ctypes mirror of ``struct IsrCloud`` (include/isr.h)."""
     _fields_ = [("soa7", ctypes.c_void_p), ("n", ctypes.c_int64), ("npad", ctypes.c_int64),
                 ("bstride", ctypes.c_int64), ("stage_c", ctypes.c_void_p), ("perm", ctypes.c_void_p),
-                ("sub_c", ctypes.c_void_p)]
+                ("sub_c", ctypes.c_void_p), ("hint", ctypes.c_void_p)]
 
 
 class IsrError(RuntimeError):

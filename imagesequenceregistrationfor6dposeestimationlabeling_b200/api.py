@@ -158,7 +158,7 @@ class SoaCloud:
         """ctypes ``IsrCloud`` for this cloud (7-plane clouds only)."""
         return _lib.IsrCloud(self.data.data_ptr(), self.n, self.npad,
                              7 * self.npad if batched else 0, _ptr(self.stage_c), _ptr(self.perm),
-                             _ptr(self.sub_c))
+                             _ptr(self.sub_c), None)
 
     @property
     def npad(self) -> int:
@@ -312,11 +312,11 @@ def nearest_neighbors_soa(q: SoaCloud, t: SoaCloud, return_index: bool = True,
         if pl == 7:
             ws = _workspace(lib.isr_nn2_workspace_bytes(q.n, t.n, bc), device)
             qdesc = _lib.IsrCloud(qd.data_ptr(), q.n, q.npad, pl * q.npad if qb > 1 else 0, None,
-                                  _ptr(q.perm), None)
+                                  _ptr(q.perm), None, None)
             tsc = None if t.stage_c is None else (t.stage_c[b0:] if tb > 1 else t.stage_c)
             tsub = None if t.sub_c is None else (t.sub_c[b0:] if tb > 1 else t.sub_c)
             tdesc = _lib.IsrCloud(td.data_ptr(), t.n, t.npad, pl * t.npad if tb > 1 else 0,
-                                  _ptr(tsc), _ptr(t.perm), _ptr(tsub))
+                                  _ptr(tsc), _ptr(t.perm), _ptr(tsub), None)
             _lib.check(lib.isr_nn2(
                 ctypes.byref(qdesc), ctypes.byref(tdesc), bc, 1 if use_lo else 0, _ptr(d2[b0:]),
                 _ptr(idx[b0:]) if idx is not None else None, None, 0, _ptr(ws), ws.numel(),

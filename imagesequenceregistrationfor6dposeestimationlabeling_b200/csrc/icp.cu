@@ -153,6 +153,18 @@ icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__res
     }
 }
 
+// hint[start][*] = -1 for the starts that have not been evaluated yet (their workspace may
+// hold anything); a no-op for every later iteration
+__global__ void __launch_bounds__(256)
+icp_hint_reset_kernel(const IsrIcpState *__restrict__ states, int64_t nsp, long long total,
+                      int32_t *__restrict__ hint) {
+    const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i0 >= total) return;
+    const IsrIcpState &st = states[i0 / nsp];  // nsp is a multiple of 1024: 4 slots, one start
+    if (st.evals != 0 || st.done != 0) return;
+    *reinterpret_cast<int4 *>(hint + i0) = make_int4(-1, -1, -1, -1);
+}
+
 // ---- 3x3 SVD (one-sided Jacobi, FP64) and Kabsch ---------------------------------------
 __device__ void svd3(const double M[3][3], double U[3][3], double D[3], double V[3][3]) {
     double A[3][3];
@@ -308,7 +320,7 @@ static int acc_blocks(int64_t ns) {
 }
 
 struct IcpLayout {
-    size_t xs, d2, partials, tickets, nnws, total;
+    size_t xs, d2, partials, tickets, hint, nnws, total;
     int nblk;
 };
 
@@ -321,6 +333,7 @@ static IcpLayout icp_layout(int64_t ns, int64_t nt, int64_t starts) {
     const int64_t max_blk = acc_blocks(ns);
     L.partials = off; off += align256((size_t)starts * max_blk * kNS * 8);
     L.tickets = off;  off += align256((size_t)starts * 4);
+    L.hint = off;     off += align256((size_t)starts * nsp * 4);
     const size_t w1 = isr_nn_workspace_bytes(ns, nt, starts), w2 = isr_nn2_workspace_bytes(ns, nt, starts);
     L.nnws = off;     off += w1 > w2 ? w1 : w2;
     L.total = off;
@@ -373,7 +386,15 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, co
     // source: FP64 pose from the device state, centred on the target's centroid, hi/lo planes
     ISR_TRY(isr_prepare_cloud(src, src_lo, src_perm, ns, &states[0].T[0], kStateDoubles, nullptr, 0,
                               centroid, starts, xs, nsp, done, kStateInts, stream));
-    const IsrCloud src_cloud{xs, ns, nsp, 7 * nsp, nullptr, src_perm, nullptr};
+    // every source point starts the search from its previous correspondence: between two ICP
+    // iterations the pose moves little, so that neighbour is already a near-final bound
+    int32_t *hint = reinterpret_cast<int32_t *>(ws + L.hint);
+    {
+        const long long total = (long long)starts * nsp;
+        icp_hint_reset_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(states, nsp, total, hint);
+        ISR_TRY(launched("icp_hint_reset_kernel"));
+    }
+    const IsrCloud src_cloud{xs, ns, nsp, 7 * nsp, nullptr, src_perm, nullptr, hint};
     ISR_TRY(isr_nn2(&src_cloud, tgt_cloud, starts, 1, d2, corr_idx, done, kStateInts, ws + L.nnws,
                     L.total - L.nnws, stream));
     ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));

@@ -85,6 +85,7 @@ struct NN2Params {
     long long sub_c_bstride;
     unsigned long long *evaluated;  // profiling: scanned (warp, sub-tile) units, or NULL
     const int *order;        // [batch][gridDim.x] query block run by CTA x of batch item b, or NULL
+    int *hint;               // [batch][nq_pad] in/out starting neighbours (stored positions), or NULL
 };
 
 // Can this lane rule out every point of the tile with sphere S for all of its Q queries?
@@ -535,6 +536,45 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         dq_l[r] = live ? CUDART_INF_F : 0.f;
     }
 
+    // ---- starting bounds from the caller's hints (the previous search's neighbours) ----------
+    // A hinted query starts as if its hint had already been scanned and resolved: running
+    // filter minimum = the hint's filter value, best = its exact FP64 distance.
+    bool all_hinted = false;
+    if (p.hint != nullptr) {
+        __syncwarp();  // ws.qs is complete
+        bool ok = true;
+        for (int r = 0; r < Q; ++r) {  // run-time loop: the resolve state lives in local memory
+            const int i = q0 + r * 32;
+            if (i >= p.nq) continue;
+            const int h = p.hint[(long long)b * p.nq_pad + i];
+            if (h < 0 || h >= p.nt) { ok = false; continue; }
+            const int qs = r * 32 + lane;
+            const float qhx = ws.qs[0][qs], qhy = ws.qs[1][qs], qhz = ws.qs[2][qs];
+            const float px = gt[h], py = gt[p.nt_pad + h], pz = gt[2ll * p.nt_pad + h];
+            const float a = __fmaf_rn(-2.0f * qhx, px, __fmaf_rn(-2.0f * qhy, py,
+                                      __fmaf_rn(-2.0f * qhz, pz, gt[3ll * p.nt_pad + h])));
+            double dx = (double)qhx - (double)px, dy = (double)qhy - (double)py, dz = (double)qhz - (double)pz;
+            if (p.use_lo) {
+                dx += (double)ws.qs[3][qs] - (double)gt[4ll * p.nt_pad + h];
+                dy += (double)ws.qs[4][qs] - (double)gt[5ll * p.nt_pad + h];
+                dz += (double)ws.qs[5][qs] - (double)gt[6ll * p.nt_pad + h];
+            }
+            const double D = fma(dz, dz, fma(dy, dy, dx * dx));
+            const float nq2 = __fmaf_rn(qhz, qhz, __fmaf_rn(qhy, qhy, qhx * qhx));
+            mt_l[r] = a;
+            thr_l[r] = filter_threshold(a, nq2, sqrtf(nq2));
+            Dbest_l[r] = D;
+            ibest_l[r] = h;
+            dq_l[r] = __double2float_ru(sqrt(D)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
+        }
+        all_hinted = __all_sync(0xffffffffu, ok);
+#pragma unroll
+        for (int r = 0; r < Q; ++r) thr[r] = thr_l[r];
+        float m = 0.f;
+        for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r]);  // run-time loop on purpose
+        dmax = m;
+    }
+
     // ---- query-row spheres: row r is 32 consecutive stored queries, a compact patch ----------
 #pragma unroll
     for (int r = 0; r < Q; ++r) {
@@ -605,7 +645,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     // anchors sit at stored positions 0, 85, 170, 255 of the warp's 256 queries
     int head = 0, look = 0, tail = 0, nloads = 0, nconsumed = 0;  // FIFO / ring state, warp-uniform
     int seed[kAnchors];
-    {
+#pragma unroll
+    for (int a = 0; a < kAnchors; ++a) seed[a] = -1;
+    if (!all_hinted) {  // (a fully hinted warp already holds near-final bounds)
         constexpr int ar[kAnchors] = {0, 2, 5, 7};
         constexpr int al[kAnchors] = {0, 21, 10, 31};
         float ax[kAnchors], ay[kAnchors], az[kAnchors];
@@ -820,6 +862,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
             const long long o = (long long)b * p.nq + io;
             p.out_d2[o] = (float)Dbest_l[r];
             if (p.out_idx != nullptr) p.out_idx[o] = jo;
+            if (p.hint != nullptr) p.hint[(long long)b * p.nq_pad + i] = ibest_l[r];
         }
     }
 }
@@ -1063,6 +1106,7 @@ static int nn2_dispatch(const NN2Call &c) {
         g_answered.fetch_add((unsigned long long)nq * (unsigned long long)c.t->n *
                              (unsigned long long)c.batch);
     }
+    p.hint = V::kPrune ? c.q->hint : nullptr;
     p.order = nullptr;
     if (V::kPrune && nqb > 1 && nqb <= kOrderMax && c.workspace != nullptr &&
         c.workspace_bytes >= order_workspace_bytes(nqb, c.batch)) {

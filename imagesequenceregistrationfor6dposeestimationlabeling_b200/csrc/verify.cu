@@ -171,8 +171,8 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
         if (cloud_q == cloud_t && nq == nt) perm_q = perm_t;
         else ISR_TRY(isr_spatial_order(cloud_q, nq, perm_q, ws + L.sortws, L.nnws - L.sortws, stream));
     }
-    const IsrCloud cx{xs, nq, nqp, 7 * nqp, stage_x, nullptr, sub_x};
-    const IsrCloud cy{ys, nt, ntp, 7 * ntp, stage_y, nullptr, sub_y};
+    const IsrCloud cx{xs, nq, nqp, 7 * nqp, stage_x, nullptr, sub_x, nullptr};
+    const IsrCloud cy{ys, nt, ntp, 7 * ntp, stage_y, nullptr, sub_y, nullptr};
     for (int64_t k0 = 0; k0 < b; k0 += L.chunk) {
         const int c = (int)((b - k0) < L.chunk ? (b - k0) : L.chunk);
         if (direct) {

@@ -144,6 +144,13 @@ typedef struct IsrCloud {
                              original indices either way                                      */
     const float *sub_c;   /* isr_tile_spheres out_sub, or NULL (no tile pruning: every pair is
                              evaluated); only read when this cloud is the target             */
+    int32_t *hint;        /* only read when this cloud is the QUERY of a pruned search; NULL or
+                             int32 [batch][npad], by stored query position: stored position in
+                             the target of a point near the query (-1 = none).  It seeds the
+                             query's bound -- any value gives the same result, a good one less
+                             work -- and is overwritten with the neighbour found, so that the
+                             next search of the same clouds (the next ICP iteration) starts
+                             from it                                                          */
 } IsrCloud;
 
 /* Process-wide switch for the tile pruning of isr_nn2 (default on).  Off = exhaustive brute

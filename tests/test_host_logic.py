@@ -70,7 +70,7 @@ def test_argument_validation_needs_no_gpu():
     assert lib.isr_icp_run(None, 1, None, None, None, 1, None, None, None, 20.0, -1, 0.0, 0.0, None, None,
                            None, None, 0, None) == -1
     assert lib.isr_nn2(None, None, 1, 1, None, None, None, 0, None, 0, None) == -1
-    empty = _lib.IsrCloud(None, 5, 1024, 0, None, None, None)
+    empty = _lib.IsrCloud(None, 5, 1024, 0, None, None, None, None)
     assert lib.isr_nn2(ctypes.byref(empty), ctypes.byref(empty), 1, 1, None, None, None, 0, None, 0,
                        None) == -1
     assert lib.isr_prepare_cloud(None, None, None, 5, None, 16, None, 16, None, 2, None, 1024, None, 0,
