@@ -86,6 +86,7 @@ struct NN2Params {
     unsigned long long *evaluated;  // profiling: scanned (warp, sub-tile) units, or NULL
     const int *order;        // [batch][gridDim.x] query block run by CTA x of batch item b, or NULL
     int *hint;               // [batch][nq_pad] in/out starting neighbours (stored positions), or NULL
+    int nanchors;            // tuning: seeds actually used (<= kAnchors)
 };
 
 // Can this lane rule out every point of the tile with sphere S for all of its Q queries?
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
 // ---- pruned kernel: warp-autonomous, sub-tile granularity ------------------------------------
 constexpr int kRing = 4;    // sub-tile buffers in flight per warp
 constexpr int kFifo = 96;   // candidate sub-tiles queued per warp
-constexpr int kAnchors = 4; // seed queries per warp
+constexpr int kAnchors = 8; // seeds per warp: one per query row
 
 template <int SUB, int Q>
 struct alignas(128) PrunedWarpSmem {
@@ -641,25 +642,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         return __any_sync(0xffffffffu, need);
     };
 
-    // ---- seeds: for kAnchors queries spread over the block, the nearest sub-tile centre ------
-    // anchors sit at stored positions 0, 85, 170, 255 of the warp's 256 queries
+    // ---- seeds: for every query row, the sub-tile whose centre is nearest to the row's --------
     int head = 0, look = 0, tail = 0, nloads = 0, nconsumed = 0;  // FIFO / ring state, warp-uniform
     int seed[kAnchors];
 #pragma unroll
     for (int a = 0; a < kAnchors; ++a) seed[a] = -1;
     if (!all_hinted) {  // (a fully hinted warp already holds near-final bounds)
-        constexpr int ar[kAnchors] = {0, 2, 5, 7};
-        constexpr int al[kAnchors] = {0, 21, 10, 31};
+        // anchors: the centres of the 8 query rows (a dead row falls back to row 0, which
+        // always holds a live query)
         float ax[kAnchors], ay[kAnchors], az[kAnchors];
 #pragma unroll
         for (int a = 0; a < kAnchors; ++a) {
-            const bool live = __shfl_sync(0xffffffffu, q0 + ar[a] * 32 < p.nq ? 1 : 0, al[a]) != 0;
-            const int l = live ? al[a] : 0;  // position 0 is always live
-            const float x = live ? q2x[ar[a]] : q2x[0], y = live ? q2y[ar[a]] : q2y[0],
-                        z = live ? q2z[ar[a]] : q2z[0];
-            ax[a] = -0.5f * __shfl_sync(0xffffffffu, x, l);
-            ay[a] = -0.5f * __shfl_sync(0xffffffffu, y, l);
-            az[a] = -0.5f * __shfl_sync(0xffffffffu, z, l);
+            const float4 R = ws.row[a].w >= 0.f ? ws.row[a] : ws.row[0];
+            ax[a] = R.x; ay[a] = R.y; az[a] = R.z;
         }
         u64 bk[kAnchors];
 #pragma unroll
@@ -705,7 +700,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
             int sb = (int)(unsigned)(key & 31ull);
             if (key == ~0ull) sb = 0;
             seed[a] = st * SUBS + sb;
-            bool dup = false;
+            bool dup = a >= p.nanchors;
+            if (dup) seed[a] = -1;
 #pragma unroll
             for (int c = 0; c < a; ++c) dup = dup || seed[c] == seed[a];
             if (!dup) {
@@ -1107,6 +1103,11 @@ static int nn2_dispatch(const NN2Call &c) {
                              (unsigned long long)c.batch);
     }
     p.hint = V::kPrune ? c.q->hint : nullptr;
+    {
+        static int na = -1;
+        if (na < 0) { const char *e = getenv("ISR_NN_ANCHORS"); na = e ? atoi(e) : kAnchors; }
+        p.nanchors = na;
+    }
     p.order = nullptr;
     if (V::kPrune && nqb > 1 && nqb <= kOrderMax && c.workspace != nullptr &&
         c.workspace_bytes >= order_workspace_bytes(nqb, c.batch)) {
