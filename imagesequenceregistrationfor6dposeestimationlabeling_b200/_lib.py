@@ -88,6 +88,9 @@ SIGNATURES = {
     "isr_verify_poses": (_I, [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I, _P, _P, _P, _SZ, _P]),
     "isr_icp_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "isr_icp_accumulate": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _D, _P, _P, _P, _P, _SZ, _P]),
+    "isr_icp_search": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "isr_icp_corr_dist": (_I, [_P, _I64, _P, _P, _I64, _P, _P, _P, _P]),
+    "isr_icp_accumulate_corr": (_I, [_P, _I64, _P, _P, _I64, _P, _I64, _P, _D, _P, _P, _P, _SZ, _P]),
     "isr_icp_solve": (_I, [_P, _I64, _P, _I64, _D, _D, _I, _P]),
     "isr_icp_run": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _D, _I, _D, _D, _P, _P, _P, _P, _SZ,
                          _P]),

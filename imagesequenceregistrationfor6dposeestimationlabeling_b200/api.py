@@ -559,6 +559,35 @@ class IcpProblem:
             _stream()))
         return self.sums
 
+    # -- the two halves of `accumulate`, for target-sharded ICP (dist.py) ---------------------
+    def search(self) -> torch.Tensor:
+        """Transform the source by every state's T and find each point's nearest neighbour in
+        THIS problem's target -> int32 [starts, ns] (also kept in self.corr_idx)."""
+        _lib.check(_lib.load().isr_icp_search(
+            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), _ptr(self.src_perm),
+            self.ns, ctypes.byref(self.tgt_desc), _ptr(self.centroid), _ptr(self.corr_idx),
+            _ptr(self.ws), self.ws.numel(), _stream()))
+        return self.corr_idx
+
+    def corr_dist(self, corr_idx: torch.Tensor) -> torch.Tensor:
+        """float64 [starts, ns]: exact squared distance of every given correspondence (+inf
+        where the index is negative), in the accumulate kernel's arithmetic."""
+        if not hasattr(self, "_D"):
+            self._D = torch.full((self.starts, max(self.ns, 1)), float("inf"), dtype=torch.float64,
+                                 device=self.device)
+        _lib.check(_lib.load().isr_icp_corr_dist(
+            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), self.ns, _ptr(self.tgt),
+            _ptr(corr_idx), _ptr(self._D), _stream()))
+        return self._D
+
+    def accumulate_corr(self, corr_idx: torch.Tensor, max_dist: float) -> torch.Tensor:
+        """The 17 sums over the given correspondences (index < 0: none on this rank)."""
+        _lib.check(_lib.load().isr_icp_accumulate_corr(
+            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), self.ns, _ptr(self.tgt),
+            self.nt, _ptr(corr_idx), float(max_dist), _ptr(self.sums), _ptr(self.inlier), _ptr(self.ws),
+            self.ws.numel(), _stream()))
+        return self.sums
+
     def solve(self, ns_total: int, rel_fitness: float, rel_rmse: float, final_eval: bool,
               sums: Optional[torch.Tensor] = None) -> None:
         sums = self.sums if sums is None else sums

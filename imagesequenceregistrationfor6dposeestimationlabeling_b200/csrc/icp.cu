@@ -71,11 +71,14 @@ icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__res
                 lx[u] = src_lo[3 * ii]; ly[u] = src_lo[3 * ii + 1]; lz[u] = src_lo[3 * ii + 2];
             }
             j[u] = ids[ii];
+            // a negative index: this source point has no correspondence here (target-sharded
+            // ICP: its neighbour lives on another rank)
+            ok[u] = ok[u] && j[u] >= 0;
         }
         float gx[U], gy[U], gz[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t jj = j[u];
+            const int64_t jj = j[u] >= 0 ? j[u] : 0;
             gx[u] = tgt[3 * jj]; gy[u] = tgt[3 * jj + 1]; gz[u] = tgt[3 * jj + 2];
         }
 #pragma unroll
@@ -89,7 +92,7 @@ icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__res
             const double dx = sx - tx, dy = sy - ty, dz = sz - tz;
             const double d2 = dx * dx + dy * dy + dz * dz;
             const bool in = ok[u] && d2 < max_d2;
-            if (inl != nullptr && ok[u]) inl[i0 + u * stride] = in ? 1 : 0;
+            if (inl != nullptr && i0 + u * stride < ns) inl[i0 + u * stride] = in ? 1 : 0;
             if (in) {
                 acc[0] += sx; acc[1] += sy; acc[2] += sz;
                 acc[3] += tx; acc[4] += ty; acc[5] += tz;
@@ -150,6 +153,35 @@ icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__res
             sums[(int64_t)s * kNS + threadIdx.x] = t;
         }
         if (threadIdx.x == 0) tickets[s] = 0;
+    }
+}
+
+// out_D[start][i] = FP64 squared distance between T.src[i] and tgt[idx[start][i]] (the same
+// arithmetic as the accumulate kernel); +inf where idx < 0.  grid (blocks, starts).
+__global__ void __launch_bounds__(256)
+icp_corr_dist_kernel(const IsrIcpState *__restrict__ states, const float *__restrict__ src,
+                     const float *__restrict__ src_lo, int64_t ns, const float *__restrict__ tgt,
+                     const int32_t *__restrict__ idx, double *__restrict__ out_D) {
+    const int s = blockIdx.y;
+    const IsrIcpState &stt = states[s];
+    if (stt.done != 0) return;
+    double T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = stt.T[k];
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < ns; i += (int64_t)gridDim.x * 256) {
+        const int j = idx[(int64_t)s * ns + i];
+        double D = CUDART_INF;
+        if (j >= 0) {
+            double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
+            if (src_lo != nullptr) { px += (double)src_lo[3 * i]; py += (double)src_lo[3 * i + 1]; pz += (double)src_lo[3 * i + 2]; }
+            const double sx = ((T[0] * px + T[1] * py) + T[2] * pz) + T[3];
+            const double sy = ((T[4] * px + T[5] * py) + T[6] * pz) + T[7];
+            const double sz = ((T[8] * px + T[9] * py) + T[10] * pz) + T[11];
+            const double dx = sx - (double)tgt[3ll * j], dy = sy - (double)tgt[3ll * j + 1],
+                         dz = sz - (double)tgt[3ll * j + 2];
+            D = dx * dx + dy * dy + dz * dz;
+        }
+        out_D[(int64_t)s * ns + i] = D;
     }
 }
 
@@ -350,19 +382,17 @@ size_t isr_icp_workspace_bytes(int64_t ns, int64_t nt, int64_t starts) {
     return isr::icp_layout(ns, nt, starts).total;
 }
 
-int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
-                       const int32_t *src_perm, int64_t ns, const float *tgt,
-                       const IsrCloud *tgt_cloud, const double *centroid, double max_dist,
-                       double *sums, int32_t *corr_idx, uint8_t *inlier, void *workspace,
-                       size_t workspace_bytes, void *stream) {
+int isr_icp_search(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                   const int32_t *src_perm, int64_t ns, const IsrCloud *tgt_cloud, const double *centroid,
+                   int32_t *corr_idx, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace isr;
     ISR_REQUIRE(tgt_cloud != nullptr, ISR_E_INVALID_ARG, "icp: null target descriptor");
     const int64_t nt = tgt_cloud->n;
     ISR_REQUIRE(starts >= 1 && ns >= 1 && nt >= 1, ISR_E_SHAPE,
                 "icp: need starts, ns, nt >= 1 (starts=%lld ns=%lld nt=%lld)", (long long)starts,
                 (long long)ns, (long long)nt);
-    ISR_REQUIRE(states && src && tgt && tgt_cloud->soa7 && centroid && sums && corr_idx,
-                ISR_E_INVALID_ARG, "icp: null pointer");
+    ISR_REQUIRE(states && src && tgt_cloud->soa7 && centroid && corr_idx, ISR_E_INVALID_ARG,
+                "icp: null pointer");
     ISR_REQUIRE(tgt_cloud->bstride == 0, ISR_E_SHAPE, "icp: the target cloud is shared by all starts");
     ISR_REQUIRE(starts <= 65535, ISR_E_SHAPE, "icp: starts %lld > 65535", (long long)starts);
     IcpLayout L = icp_layout(ns, nt, starts);
@@ -374,15 +404,8 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, co
     char *ws = reinterpret_cast<char *>(workspace);
     float *xs = reinterpret_cast<float *>(ws + L.xs);
     float *d2 = reinterpret_cast<float *>(ws + L.d2);
-    double *partials = reinterpret_cast<double *>(ws + L.partials);
-    unsigned *tickets = reinterpret_cast<unsigned *>(ws + L.tickets);
     const int64_t nsp = isr_soa_padded_len(ns);
     const int32_t *done = &states[0].done;  // device address arithmetic only
-
-    if (max_dist <= 0.0) {
-        // upstream: a non-positive distance yields an empty result
-        return check_cuda(cudaMemsetAsync(sums, 0, (size_t)starts * kNS * 8, st), "icp memset");
-    }
     // source: FP64 pose from the device state, centred on the target's centroid, hi/lo planes
     ISR_TRY(isr_prepare_cloud(src, src_lo, src_perm, ns, &states[0].T[0], kStateDoubles, nullptr, 0,
                               centroid, starts, xs, nsp, done, kStateInts, stream));
@@ -395,8 +418,43 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, co
         ISR_TRY(launched("icp_hint_reset_kernel"));
     }
     const IsrCloud src_cloud{xs, ns, nsp, 7 * nsp, nullptr, src_perm, nullptr, hint};
-    ISR_TRY(isr_nn2(&src_cloud, tgt_cloud, starts, 1, d2, corr_idx, done, kStateInts, ws + L.nnws,
-                    L.total - L.nnws, stream));
+    return isr_nn2(&src_cloud, tgt_cloud, starts, 1, d2, corr_idx, done, kStateInts, ws + L.nnws,
+                   L.total - L.nnws, stream);
+}
+
+int isr_icp_corr_dist(const IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                      int64_t ns, const float *tgt, const int32_t *corr_idx, double *out_D,
+                      void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(starts >= 1 && starts <= 65535 && ns >= 1, ISR_E_SHAPE, "icp_corr_dist: bad size");
+    ISR_REQUIRE(states && src && tgt && corr_idx && out_D, ISR_E_INVALID_ARG, "icp_corr_dist: null pointer");
+    dim3 grid((unsigned)acc_blocks(ns), (unsigned)starts);
+    icp_corr_dist_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(states, src, src_lo, ns, tgt, corr_idx, out_D);
+    return launched("icp_corr_dist_kernel");
+}
+
+int isr_icp_accumulate_corr(const IsrIcpState *states, int64_t starts, const float *src,
+                            const float *src_lo, int64_t ns, const float *tgt, int64_t nt,
+                            const int32_t *corr_idx, double max_dist, double *sums, uint8_t *inlier,
+                            void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(starts >= 1 && starts <= 65535 && ns >= 1 && nt >= 1, ISR_E_SHAPE,
+                "icp_accumulate_corr: bad size");
+    ISR_REQUIRE(states && src && tgt && corr_idx && sums, ISR_E_INVALID_ARG,
+                "icp_accumulate_corr: null pointer");
+    IcpLayout L = icp_layout(ns, nt, starts);
+    ISR_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, ISR_E_WORKSPACE,
+                "icp: workspace %zu < %zu bytes", workspace_bytes, L.total);
+    ISR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ISR_E_ALIGN,
+                "icp: workspace not 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = reinterpret_cast<char *>(workspace);
+    double *partials = reinterpret_cast<double *>(ws + L.partials);
+    unsigned *tickets = reinterpret_cast<unsigned *>(ws + L.tickets);
+    if (max_dist <= 0.0) {
+        // upstream: a non-positive distance yields an empty result
+        return check_cuda(cudaMemsetAsync(sums, 0, (size_t)starts * kNS * 8, st), "icp memset");
+    }
     ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
     const int nblk = acc_blocks(ns);
     dim3 grid((unsigned)nblk, (unsigned)starts);
@@ -405,6 +463,21 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, co
                                                         max_dist * max_dist, partials, tickets, sums,
                                                         inlier);
     return launched("icp_accumulate_kernel");
+}
+
+int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                       const int32_t *src_perm, int64_t ns, const float *tgt,
+                       const IsrCloud *tgt_cloud, const double *centroid, double max_dist,
+                       double *sums, int32_t *corr_idx, uint8_t *inlier, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(tgt_cloud != nullptr && tgt != nullptr && sums != nullptr, ISR_E_INVALID_ARG,
+                "icp: null pointer");
+    if (max_dist > 0.0)
+        ISR_TRY(isr_icp_search(states, starts, src, src_lo, src_perm, ns, tgt_cloud, centroid, corr_idx,
+                               workspace, workspace_bytes, stream));
+    return isr_icp_accumulate_corr(states, starts, src, src_lo, ns, tgt, tgt_cloud->n, corr_idx, max_dist,
+                                   sums, inlier, workspace, workspace_bytes, stream);
 }
 
 int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64_t ns_total,

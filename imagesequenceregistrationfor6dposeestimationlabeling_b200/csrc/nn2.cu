@@ -1005,7 +1005,10 @@ struct NN2PrunedVariant {
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
         auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG>;
         ProfScope prof(kProfNN, st);
-        kern<<<grid, WARPS * 32, kSmem, st>>>(p);
+        // the lo planes of the query copy (last 3 KB of the per-warp block) are only touched
+        // when the search uses the lo parts
+        const size_t smem = WARPS == 1 && !p.use_lo ? kSmem - 3 * 32 * Q * sizeof(float) : kSmem;
+        kern<<<grid, WARPS * 32, smem, st>>>(p);
         return launched("nn2_pruned_kernel");
     }
     static int ctas_per_sm() { return MINB; }
@@ -1015,6 +1018,7 @@ struct NN2PrunedVariant {
 // (flag granularity FLAG = 32 / 16 targets inside the 64-target pruning unit was measured
 // 2 % / 19 % slower than 64: more, shorter resolve passes)
 using NN2Pruned = NN2PrunedVariant<8, 1, 64, 16, 1, 64>;
+using NN2Pruned20 = NN2PrunedVariant<8, 1, 64, 20, 1, 64>;
 static_assert(NN2Pruned::kSmem <= 48 * 1024, "pruned kernel uses the default dynamic shared memory limit");
 constexpr int kMaxSplits = 32;
 
@@ -1253,6 +1257,9 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
 #endif
     if (t->sub_c != nullptr && t->stage_c != nullptr && pruning_on()) {
         ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
+        static int mb = -1;
+        if (mb < 0) { const char *e = getenv("ISR_NN_PMINB"); mb = e ? atoi(e) : 16; }
+        if (mb == 20) return nn2_dispatch<NN2Pruned20>(c);
         return nn2_dispatch<NN2Pruned>(c);
     }
     return nn2_dispatch<NN2Main>(c);

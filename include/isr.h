@@ -232,6 +232,27 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src,
                        double *sums, int32_t *corr_idx, uint8_t *inlier, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* The two halves of isr_icp_accumulate, for callers that exchange correspondences between
+ * them (target-sharded ICP: every rank searches its own slice of the target, the ranks
+ * agree on the nearest one with two MIN all-reduces, and each rank accumulates the
+ * correspondences that landed in its slice):
+ *   isr_icp_search          transform by state.T + 1-NN -> corr_idx [starts][ns] (target index)
+ *   isr_icp_corr_dist       out_D [starts][ns] float64 = |T src[i] - tgt[corr_idx]|^2, +inf where
+ *                           corr_idx < 0 (the accumulate kernel's arithmetic: what the ranks compare)
+ *   isr_icp_accumulate_corr the 17 sums over corr_idx; an index < 0 means "no correspondence
+ *                           on this rank".  nt = rows of tgt. */
+int isr_icp_search(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                   const int32_t *src_perm, int64_t ns, const IsrCloud *tgt_cloud,
+                   const double *centroid, int32_t *corr_idx, void *workspace,
+                   size_t workspace_bytes, void *stream);
+int isr_icp_corr_dist(const IsrIcpState *states, int64_t starts, const float *src,
+                      const float *src_lo, int64_t ns, const float *tgt, const int32_t *corr_idx,
+                      double *out_D, void *stream);
+int isr_icp_accumulate_corr(const IsrIcpState *states, int64_t starts, const float *src,
+                            const float *src_lo, int64_t ns, const float *tgt, int64_t nt,
+                            const int32_t *corr_idx, double max_dist, double *sums,
+                            uint8_t *inlier, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Consume sums[starts][17] (already reduced over all source shards): set fitness / rmse
  * (ns_total = global source count), apply Open3D's break test against the previous
  * evaluation, and otherwise solve Kabsch (Eigen::umeyama without scaling, 3x3 Jacobi SVD,

@@ -91,6 +91,40 @@ class _OracleIcpBackend:
         return [dict(T=self.T[k], **self.state[k]) for k in range(len(self.T))]
 
 
+class _OracleIcpTargetBackend(_OracleIcpBackend):
+    """Target-sharded counterpart: all source points against one target slice (tests only)."""
+
+    def search(self):
+        idx = np.zeros((len(self.T), len(self.src)), dtype=np.int32)
+        D = np.full((len(self.T), len(self.src)), np.inf)
+        self._s = [None] * len(self.T)
+        for k, T in enumerate(self.T):
+            if self.state[k]["done"]:
+                continue
+            s = oracle.transform(self.src, T)
+            _, j = self.tree.query(s, k=1)
+            idx[k] = j
+            D[k] = ((s - self.tgt[j]) ** 2).sum(1)
+            self._s[k] = s
+        return torch.from_numpy(idx), torch.from_numpy(D)
+
+    def accumulate(self, local_idx, max_dist):
+        sums = np.zeros((len(self.T), 17))
+        li = local_idx.numpy()
+        for k in range(len(self.T)):
+            if self.state[k]["done"]:
+                continue
+            own = li[k] >= 0
+            s, t = self._s[k][own], self.tgt[li[k][own]]
+            d2 = ((s - t) ** 2).sum(1)
+            keep = d2 < max_dist * max_dist
+            s, t, d2 = s[keep], t[keep], d2[keep]
+            sums[k, 0:3], sums[k, 3:6] = s.sum(0), t.sum(0)
+            sums[k, 6:15] = (t.T @ s).reshape(9)
+            sums[k, 15], sums[k, 16] = d2.sum(), keep.sum()
+        return torch.from_numpy(sums)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
@@ -128,6 +162,12 @@ def _worker(rank, world, port, q):
         res = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=12,
                                backend_factory=_OracleIcpBackend)
         out["icp"] = res[0]
+        # the north star's variant: target rows sharded, per-point MIN all-reduce; the target
+        # holds a duplicated block so that equal-distance neighbours sit on different ranks
+        tgt2 = np.concatenate([tgt, tgt[:700]])
+        res = dist.icp_sharded(src, tgt2, np.eye(4), 20.0, max_iteration=12, shard="target",
+                               backend_factory=_OracleIcpTargetBackend)
+        out["icp_target"] = res[0]
     finally:
         td.destroy_process_group()
     q.put((rank, out))
@@ -169,3 +209,11 @@ def test_world_size_2_gloo():
         np.testing.assert_allclose(res["fitness"], o.fitness, rtol=1e-12)
         np.testing.assert_allclose(res["rmse"], o.inlier_rmse, rtol=1e-9)
     np.testing.assert_array_equal(got[0]["icp"]["T"], got[1]["icp"]["T"])   # bit-identical ranks
+    o2 = oracle.registration_icp(src, np.concatenate([tgt, tgt[:700]]), 20.0, np.eye(4), max_iteration=12)
+    for r in (0, 1):
+        res = got[r]["icp_target"]
+        np.testing.assert_allclose(res["T"], o2.transformation, rtol=1e-9, atol=1e-9)
+        assert res["iters"] == o2.iterations
+        np.testing.assert_allclose(res["fitness"], o2.fitness, rtol=1e-12)
+        np.testing.assert_allclose(res["rmse"], o2.inlier_rmse, rtol=1e-9)
+    np.testing.assert_array_equal(got[0]["icp_target"]["T"], got[1]["icp_target"]["T"])

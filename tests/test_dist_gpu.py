@@ -38,6 +38,8 @@ def _worker(rank, world, port, q):
         src, tgt, _ = synth.icp_pair(9001, 9500, 6, 7)
         res = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=12)
         out["icp"] = (res[0].transformation, res[0].fitness, res[0].inlier_rmse, res[0].iterations)
+        res = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=12, shard="target")
+        out["icp_target"] = (res[0].transformation, res[0].fitness, res[0].inlier_rmse, res[0].iterations)
         torch.cuda.synchronize()
     finally:
         td.destroy_process_group()
@@ -70,9 +72,11 @@ def test_two_gpu_sharding_matches_oracle():
         assert bi == ref_best == k0
         np.testing.assert_allclose(losses, ref, rtol=1e-5)
         np.testing.assert_allclose(bl, ref[ref_best], rtol=1e-5)
-        T, fit, rmse, it = got[r]["icp"]
-        np.testing.assert_allclose(T, o.transformation, rtol=1e-7, atol=1e-7)
-        assert it == o.iterations and abs(fit - o.fitness) < 1e-12
-        np.testing.assert_allclose(rmse, o.inlier_rmse, rtol=1e-7)
+        for key in ("icp", "icp_target"):
+            T, fit, rmse, it = got[r][key]
+            np.testing.assert_allclose(T, o.transformation, rtol=1e-7, atol=1e-7)
+            assert it == o.iterations and abs(fit - o.fitness) < 1e-12
+            np.testing.assert_allclose(rmse, o.inlier_rmse, rtol=1e-7)
     np.testing.assert_array_equal(got[0]["icp"][0], got[1]["icp"][0])   # bit-identical ranks
+    np.testing.assert_array_equal(got[0]["icp_target"][0], got[1]["icp_target"][0])
     np.testing.assert_array_equal(got[0]["verify"][2], got[1]["verify"][2])

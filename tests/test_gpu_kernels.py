@@ -471,6 +471,35 @@ def test_icp_threshold_edge_and_empty_correspondences(gpu):
     assert r.iterations == o.iterations == 1
 
 
+def test_icp_search_accumulate_halves_equal_the_fused_call(gpu):
+    """isr_icp_search + isr_icp_corr_dist + isr_icp_accumulate_corr (the target-sharded ICP's
+    building blocks, here on one rank) reproduce isr_icp_run bit for bit; negative indices
+    drop correspondences."""
+    import torch
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api, dist, synth
+    src, tgt, _ = synth.icp_pair(7001, 8000, 6, 7)
+    a = gpu.icp(src, tgt, np.eye(4), 20.0, max_iteration=9)
+    b = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=9, shard="target")[0]
+    np.testing.assert_array_equal(a.transformation, b.transformation)
+    assert (a.fitness, a.inlier_rmse, a.iterations) == (b.fitness, b.inlier_rmse, b.iterations)
+    prob = api.IcpProblem(src, tgt, np.eye(4)[None])
+    idx = prob.search()
+    D = prob.corr_dist(idx).cpu().numpy()[0]
+    dk, ik = oracle.nearest(src, tgt)
+    np.testing.assert_array_equal(idx.cpu().numpy()[0], ik)
+    np.testing.assert_allclose(D, dk * dk, rtol=1e-12, atol=1e-18)
+    full = prob.accumulate_corr(idx, 20.0).cpu().numpy().copy()
+    half = idx.clone()
+    half[0, ::2] = -1
+    part = prob.accumulate_corr(half, 20.0).cpu().numpy().copy()
+    other = idx.clone()
+    other[0, 1::2] = -1
+    rest = prob.accumulate_corr(other, 20.0).cpu().numpy().copy()
+    assert part[0, 16] + rest[0, 16] == full[0, 16] == len(src)
+    np.testing.assert_allclose(part + rest, full, rtol=1e-12)
+    assert np.isinf(prob.corr_dist(half).cpu().numpy()[0, ::2]).all()
+
+
 def test_multistart_icp_matches_individual_runs(gpu):
     from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
     src, tgt, _ = synth.icp_pair(8000, 9000, 6, 7)
