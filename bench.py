@@ -399,6 +399,40 @@ def main():
         finally:
             api.set_nn_pruning(True)
         r = prob.results(with_correspondences=False)[0]
+        # the north star's target-sharded form of the same loop (N > 1 only): every rank
+        # searches its slice of the target for ALL source points, two per-point MIN
+        # all-reduces pick the neighbour, then the same 17-double SUM all-reduce
+        t_icp_tgt = None
+        if world > 1:
+            tlo, thi = dist.shard_bounds(len(tgt), rank, world)
+            tbe = dist.CudaIcpTargetShardBackend(src, tgt[tlo:thi], np.eye(4)[None])
+
+            def icp_iter_target(final=False):
+                idx, D = tbe.search()
+                gidx = idx.to(torch.int64) + tlo
+                Dmin = D.clone()
+                td.all_reduce(Dmin, op=td.ReduceOp.MIN)
+                gidx = torch.where(D == Dmin, gidx, torch.full_like(gidx, np.iinfo(np.int64).max))
+                td.all_reduce(gidx, op=td.ReduceOp.MIN)
+                mine = (gidx >= tlo) & (gidx < thi)
+                local = torch.where(mine, gidx - tlo, torch.full_like(gidx, -1)).to(torch.int32).contiguous()
+                sums = tbe.accumulate(local, 20.0)
+                td.all_reduce(sums, op=td.ReduceOp.SUM)
+                tbe.solve(sums, len(src), 0.0, 0.0, final)
+
+            icp_iter_target()
+            barrier()
+            e0.record()
+            for k in range(args.icp_iters):
+                icp_iter_target()
+            e1.record()
+            barrier()
+            t_icp_tgt = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+            rt = tbe.results()[0]
+            # (the two loops ran a different number of iterations: same basin, not the same rmse)
+            assert abs(rt.fitness - r.fitness) < 1e-6 and abs(rt.inlier_rmse - r.inlier_rmse) < 0.2 * r.inlier_rmse, \
+                (rt.fitness, r.fitness, rt.inlier_rmse, r.inlier_rmse)
+            del tbe
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         ns_local = shi - slo
         k3_bytes = ns_local * 32                            # 12 src + 4 idx + 4 d2 + 12 tgt
@@ -435,6 +469,7 @@ def main():
             "icp_nn_tflops_evaluated": FLOP_PER_PAIR * icp_eval / (ms_kind[1] * 1e-3) / 1e12,
             "icp_nn_tflops_brute_force_equivalent": FLOP_PER_PAIR * icp_answered / (ms_kind[1] * 1e-3) / 1e12,
             "icp_nn_ms_per_iter": ms_kind[1] / max(n_kind[1], 1),
+            "icp_target_sharded_iters_per_s": (args.icp_iters / t_icp_tgt) if t_icp_tgt else None,
             "icp_exhaustive_iters_per_s": 1.0 / t_icp_ex,
             "icp_exhaustive_nn_tflops": FLOP_PER_PAIR * ns_local * args.icp_points / t_icp_ex / 1e12,
             "icp_fitness": r.fitness, "icp_inlier_rmse": r.inlier_rmse,

@@ -94,6 +94,7 @@ SIGNATURES = {
     "isr_icp_solve": (_I, [_P, _I64, _P, _I64, _D, _D, _I, _P]),
     "isr_icp_run": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _D, _I, _D, _D, _P, _P, _P, _P, _SZ,
                          _P]),
+    "isr_radius_count": (_I, [_P, _P, _D, _P, _P]),
     "isr_bench_ffma": (_I, [_I, _I, _I, _P, _P, _P]),
 }
 

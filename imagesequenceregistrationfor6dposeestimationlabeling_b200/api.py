@@ -369,6 +369,37 @@ def nearest_neighbors(query, target, return_index: bool = True, mode: str = "exa
     return res
 
 
+def radius_neighbor_count(points, radius: float, target=None, device=None) -> torch.Tensor:
+    """int32 [N]: for every point, the number of `target` points (default: the cloud itself,
+    the point included) with d^2 < radius^2 -- strict, decided in float64.  The count behind
+    Open3D's remove_radius_outlier (generateCors.py:254-258, trainPose.py:343-347)."""
+    device = _device(device)
+    if not radius > 0:
+        raise ValueError("radius must be positive")
+    qp, qlo = _points_hilo(points, device)
+    if qp.dim() != 2:
+        raise ValueError("radius_neighbor_count expects points of shape [N, 3]")
+    out = torch.zeros((qp.shape[0],), dtype=torch.int32, device=device)
+    if qp.shape[0] == 0:
+        return out
+    if target is None:
+        cen = centroid_of(qp, device)
+        q7 = t7 = prepare_cloud(points, centroid=cen, perm=spatial_order(qp, device), stage_centroids=True,
+                                device=device)
+    else:
+        tp = _points(target, device)
+        if tp.shape[0] == 0:
+            return out
+        cen = centroid_of(tp, device)
+        t7 = prepare_cloud(target, centroid=cen, perm=spatial_order(tp, device), stage_centroids=True,
+                           device=device)
+        q7 = prepare_cloud(points, centroid=cen, perm=spatial_order(qp, device), device=device)
+    qd, tdesc = q7.descriptor(batched=False), t7.descriptor(batched=False)
+    _lib.check(_lib.load().isr_radius_count(ctypes.byref(qd), ctypes.byref(tdesc), float(radius),
+                                            _ptr(out), _stream()))
+    return out
+
+
 def _mean_sqrt(d2: torch.Tensor) -> torch.Tensor:
     """FP64 mean of sqrt(d2) per row, deterministic order."""
     b, n = d2.shape

@@ -78,5 +78,25 @@ class PointCloud:
         d = api.point_cloud_distance(self._np(), target._np())
         return d.cpu().numpy().view(_Distances)
 
+    # -- generateCors.py:254-258, trainPose.py:343-347 ------------------------------------
+    def remove_radius_outlier(self, nb_points, radius, print_progress=False):
+        """(filtered cloud, list of kept indices): a point stays iff more than `nb_points`
+        points (itself included) lie within `radius` of it (strict, float64 decision)."""
+        if len(self) == 0:
+            return PointCloud(), []
+        cnt = api.radius_neighbor_count(self._np(), float(radius)).cpu().numpy()
+        ind = np.nonzero(cnt > int(nb_points))[0]
+        return self.select_by_index(ind), [int(i) for i in ind]
+
+    def select_by_index(self, indices, invert=False):
+        idx = np.asarray(indices, dtype=np.int64)
+        if invert:
+            keep = np.ones(len(self), dtype=bool)
+            keep[idx] = False
+            idx = np.nonzero(keep)[0]
+        out = PointCloud()
+        out._points = Vector3dVector(self._np()[idx])
+        return out
+
     def __repr__(self):
         return f"PointCloud with {len(self)} points."

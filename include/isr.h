@@ -271,6 +271,16 @@ int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const flo
                 double rel_rmse, double *sums, int32_t *corr_idx, uint8_t *inlier,
                 void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- radius neighbour count ----------------------------------- */
+/* out_count[i] (int32 [nq], original query indexing) = number of target points with
+ * d^2 < radius^2 (strict, float64 decision, a point coinciding with the query included):
+ * the count behind Open3D's PointCloud.remove_radius_outlier(nb_points, radius), which keeps
+ * point i iff count > nb_points (generateCors.py:254-258, trainPose.py:343-347).  q and t are
+ * prepared clouds (isr_prepare_cloud with a common centre; single clouds, bstride 0); t needs
+ * its tile spheres.  Pass the same cloud twice for the self-count of the reference. */
+int isr_radius_count(const IsrCloud *q, const IsrCloud *t, double radius, int32_t *out_count,
+                     void *stream);
+
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* FFMA-chain microbenchmark: launches `blocks` x 256 threads, each running `iters`
  * rounds of 16 independent FMAs (packed != 0: fma.rn.f32x2).  flops_out_host receives the

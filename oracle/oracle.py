@@ -170,6 +170,29 @@ def verify_matrices(pc_q, pc_t, Mq, Mt, bidirectional=True, workers=-1):
 # --------------------------------------------------------------------------------------
 # ICP  (icp.py:88-117; Open3D RegistrationICP / Eigen::umeyama upstream)
 # --------------------------------------------------------------------------------------
+def radius_count(points, radius, target=None, chunk=512):
+    """Neighbours with d^2 < radius^2 (strict, float64; the point itself included when the
+    target is the cloud) -- what Open3D's remove_radius_outlier counts (upstream: KDTreeFlann
+    SearchRadius -> nanoflann RadiusResultSet keeps `dist < radius`, both squared;
+    generateCors.py:254-258, trainPose.py:343-347).  Brute force in chunks: the definition."""
+    q = np.asarray(points, dtype=np.float64)
+    t = q if target is None else np.asarray(target, dtype=np.float64)
+    r2 = float(radius) * float(radius)
+    out = np.zeros(len(q), dtype=np.int32)
+    for lo in range(0, len(q), chunk):
+        d = q[lo:lo + chunk, None, :] - t[None, :, :]
+        out[lo:lo + chunk] = ((d * d).sum(-1) < r2).sum(1)
+    return out
+
+
+def remove_radius_outlier(points, nb_points, radius):
+    """-> (kept points, kept indices): keep point i iff its radius count > nb_points
+    (upstream PointCloud::RemoveRadiusOutliers)."""
+    cnt = radius_count(points, radius)
+    ind = np.nonzero(cnt > nb_points)[0]
+    return np.asarray(points)[ind], ind
+
+
 def transform(points, T):
     """PointCloud.transform: p <- T[:3,:3] p + T[:3,3] (float64).  icp.py:22,110."""
     T = np.asarray(T, dtype=np.float64)

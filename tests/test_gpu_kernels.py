@@ -500,6 +500,48 @@ def test_icp_search_accumulate_halves_equal_the_fused_call(gpu):
     assert np.isinf(prob.corr_dist(half).cpu().numpy()[0, ::2]).all()
 
 
+@pytest.mark.parametrize("n,radius,scale,offset", [
+    (1, 1.0, 1.0, 0.0), (300, 3.0, 1.0, 0.0), (6000, 4.0, 1.0, 0.0), (6000, 0.05 * 60 / 1.8, 1.0, 0.0),
+    (5000, 0.002, 1.0 / 2000, 0.0), (4000, 4.0, 1.0, 700.0), (3000, 1e-3, 1.0, 900.0)])
+def test_radius_count_equals_float64_bruteforce(gpu, n, radius, scale, offset):
+    """the counts behind remove_radius_outlier equal the float64 brute
+    force (strict <, self included) for object-frame, tiny-scale, camera-frame clouds and for
+    a radius far below the coordinate magnitude (all-FP64 fallback)."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    pts = (synth.make_cloud(max(n, 8), seed=4)[:n].astype(np.float64) * scale + offset).astype(np.float32)
+    got = gpu.radius_neighbor_count(pts, radius).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.radius_count(pts, radius))
+    assert got.min() >= 1
+
+
+def test_radius_count_lattice_boundary_and_target(gpu):
+    """Neighbours at exactly the radius are excluded (strict <); separate query/target clouds."""
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(12), indexing="ij"), -1)
+    pts = g.reshape(-1, 3).astype(np.float32)
+    for radius in (1.0, np.sqrt(2.0), 2.0, 2.0000001):
+        got = gpu.radius_neighbor_count(pts, radius).cpu().numpy()
+        np.testing.assert_array_equal(got, oracle.radius_count(pts, radius))
+    q = (pts[::7] + np.float32(0.25))
+    got = gpu.radius_neighbor_count(q, 1.3, target=pts).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.radius_count(q, 1.3, target=pts))
+
+
+def test_remove_radius_outlier_shim(gpu):
+    """o3d.geometry.PointCloud.remove_radius_outlier as generateCors.py:254-258 calls it."""
+    import imagesequenceregistrationfor6dposeestimationlabeling_b200.o3d_compat as o3d
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    rng = np.random.default_rng(8)
+    mverts = np.concatenate([synth.make_cloud(5000, seed=2) / 66.0,            # unit-cube-sized surface
+                             rng.uniform(-1.2, 1.2, size=(300, 3))]).astype(np.float32)  # stray points
+    pcd = o3d.geometry.PointCloud()
+    pcd.points = o3d.utility.Vector3dVector(mverts)
+    cl, ind = pcd.remove_radius_outlier(nb_points=20, radius=0.05)
+    ref_pts, ref_ind = oracle.remove_radius_outlier(mverts, 20, 0.05)
+    assert list(ind) == list(ref_ind) and len(cl) == len(ref_ind)
+    np.testing.assert_array_equal(np.asarray(cl.points), ref_pts.astype(np.float64))
+    assert 0 < len(ind) < len(mverts)
+
+
 def test_multistart_icp_matches_individual_runs(gpu):
     from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
     src, tgt, _ = synth.icp_pair(8000, 9000, 6, 7)

@@ -208,3 +208,19 @@ def test_choose_image_vote():
     err, image_id, top = oracle.choose_image(pred, gt, verts, surface, diameter=120.0)
     assert err.shape == (n, n) and err[0, 1] == 1 and err[0, 2] == 0
     assert image_id in (0, 1, 3) and top[0] == image_id and top[-1] == 2
+
+
+def test_radius_count_restatement_against_kdtree():
+    """The brute-force definition agrees with scipy's ball query away from the boundary, is
+    strict at the boundary, and counts the point itself."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(3)
+    pts = rng.normal(size=(1500, 3)).astype(np.float32)
+    cnt = oracle.radius_count(pts, 0.3)
+    ref = cKDTree(pts.astype(np.float64)).query_ball_point(pts.astype(np.float64), 0.3, return_length=True)
+    np.testing.assert_array_equal(cnt, ref)          # no pair sits exactly on the boundary here
+    line = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [4, 0, 0]], dtype=np.float32)
+    np.testing.assert_array_equal(oracle.radius_count(line, 1.0), [1, 1, 1, 1])       # strict <
+    np.testing.assert_array_equal(oracle.radius_count(line, 1.0000001), [2, 3, 2, 1])
+    kept, ind = oracle.remove_radius_outlier(line, 1, 1.5)
+    assert list(ind) == [0, 1, 2] and len(kept) == 3
