@@ -353,10 +353,15 @@ def nearest_neighbors(query, target, return_index: bool = True, mode: str = "exa
                            device=device)
         if qp.dim() == 2:
             q7 = prepare_cloud(qp, centroid=cen, perm=spatial_order(qp, device), device=device)
-        else:  # a batch of query clouds against one target: stored unordered
-            q7 = SoaCloud(torch.cat([prepare_cloud(qp[k], centroid=cen, device=device).data
-                                     for k in range(qp.shape[0])]), qp.shape[1], cen)
-        res = nearest_neighbors_soa(q7, t7, return_index)
+            res = nearest_neighbors_soa(q7, t7, return_index)
+        else:
+            # a batch of different query clouds against one target: each gets its own curve
+            # order (the pruned search relies on it), so they are searched one by one
+            outs = [nearest_neighbors_soa(
+                prepare_cloud(qp[k], centroid=cen, perm=spatial_order(qp[k], device), device=device),
+                t7, return_index) for k in range(qp.shape[0])]
+            res = NNResult(torch.cat([o.d2 for o in outs]),
+                           torch.cat([o.idx for o in outs]) if return_index else None)
     else:
         outs = []
         for k in range(tp.shape[0]):

@@ -86,7 +86,7 @@ struct NN2Params {
     unsigned long long *evaluated;  // profiling: scanned (warp, sub-tile) units, or NULL
     const int *order;        // [batch][gridDim.x] query block run by CTA x of batch item b, or NULL
     int *hint;               // [batch][nq_pad] in/out starting neighbours (stored positions), or NULL
-    int nanchors;            // tuning: seeds actually used (<= kAnchors)
+    int nanchors;            // seeds used (<= kAnchors; fewer only for tuning runs)
 };
 
 // Can this lane rule out every point of the tile with sphere S for all of its Q queries?
@@ -1017,8 +1017,9 @@ struct NN2PrunedVariant {
 // CTAs, whose slowest warp holds the registers and shared memory of the other three)
 // (flag granularity FLAG = 32 / 16 targets inside the 64-target pruning unit was measured
 // 2 % / 19 % slower than 64: more, shorter resolve passes)
+// (20 warps per SM -- a 102-register cap, 224 B of spills -- was measured 2 % slower on the
+// verification workload and 8 % slower on the ICP search)
 using NN2Pruned = NN2PrunedVariant<8, 1, 64, 16, 1, 64>;
-using NN2Pruned20 = NN2PrunedVariant<8, 1, 64, 20, 1, 64>;
 static_assert(NN2Pruned::kSmem <= 48 * 1024, "pruned kernel uses the default dynamic shared memory limit");
 constexpr int kMaxSplits = 32;
 
@@ -1107,11 +1108,10 @@ static int nn2_dispatch(const NN2Call &c) {
                              (unsigned long long)c.batch);
     }
     p.hint = V::kPrune ? c.q->hint : nullptr;
-    {
-        static int na = -1;
-        if (na < 0) { const char *e = getenv("ISR_NN_ANCHORS"); na = e ? atoi(e) : kAnchors; }
-        p.nanchors = na;
-    }
+    p.nanchors = kAnchors;  // measured on the verification workload: 1 seed 6.4k, 2 7.6k, 4 8.8k, 8 9.0k candidates/s
+#ifdef ISR_NN_TUNING
+    if (const char *e = getenv("ISR_NN_ANCHORS")) p.nanchors = atoi(e);
+#endif
     p.order = nullptr;
     if (V::kPrune && nqb > 1 && nqb <= kOrderMax && c.workspace != nullptr &&
         c.workspace_bytes >= order_workspace_bytes(nqb, c.batch)) {
@@ -1257,9 +1257,6 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
 #endif
     if (t->sub_c != nullptr && t->stage_c != nullptr && pruning_on()) {
         ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
-        static int mb = -1;
-        if (mb < 0) { const char *e = getenv("ISR_NN_PMINB"); mb = e ? atoi(e) : 16; }
-        if (mb == 20) return nn2_dispatch<NN2Pruned20>(c);
         return nn2_dispatch<NN2Pruned>(c);
     }
     return nn2_dispatch<NN2Main>(c);
