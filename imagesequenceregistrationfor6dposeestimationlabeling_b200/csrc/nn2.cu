@@ -84,7 +84,8 @@ struct NN2Params {
     const float4 *sub_c;     // [batch][stages_total * STAGE/SUB] sub-tile spheres (PRUNE)
     long long sub_c_bstride;
     unsigned long long *evaluated;  // profiling: scanned (warp, sub-tile) units, or NULL
-    const int *order;        // [batch][gridDim.x] query block run by CTA x of batch item b, or NULL
+    const int *order;        // [batch][gridDim.x] (query block | (row + 1) << 24) run by CTA x, or NULL
+    const int *order_count;  // [batch] entries of `order` in use
     int *hint;               // [batch][nq_pad] in/out starting neighbours (stored positions), or NULL
     int nanchors;            // seeds used (<= kAnchors; fewer only for tuning runs)
 };
@@ -487,10 +488,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     // heaviest query blocks first (order from block_order_kernel): the grid is only a few
-    // waves deep for a single cloud pair, and a late-starting heavy block would be its tail
-    const int blk = p.order != nullptr ? p.order[(long long)b * gridDim.x + blockIdx.x] : (int)blockIdx.x;
+    // waves deep for a single cloud pair, and a late-starting heavy block would be its tail.
+    // The very widest blocks are split over 8 CTAs that own one query row each (rowsel).
+    int blk = (int)blockIdx.x, rowsel = 0;
+    if (p.order != nullptr) {
+        if ((int)blockIdx.x >= p.order_count[b]) return;
+        const int entry = p.order[(long long)b * gridDim.x + blockIdx.x];
+        blk = entry & 0xFFFFFF;
+        rowsel = entry >> 24;  // 0: all rows; r + 1: only row r
+    }
     const int q0 = blk * (WARPS * 32 * Q) + warp * (32 * Q) + lane;
     if (q0 - lane >= p.nq) return;  // this warp has no live query; warps never meet at a barrier
+    unsigned livemask = 0;  // bit r: query r * 32 + lane exists and belongs to this CTA
+#pragma unroll
+    for (int r = 0; r < Q; ++r)
+        if (q0 + r * 32 < p.nq && (rowsel == 0 || rowsel - 1 == r)) livemask |= 1u << r;
+    if (__ballot_sync(0xffffffffu, livemask != 0) == 0) return;
     const long long t_start = clock64();
     PrunedWarpSmem<SUB, Q> &ws = reinterpret_cast<PrunedWarpSmem<SUB, Q> *>(smem_raw)[warp];
     const float *__restrict__ gq = p.q + (long long)b * p.q_bstride;
@@ -516,7 +529,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         q2x[r] = -2.0f * gq[i];
         q2y[r] = -2.0f * gq[p.nq_pad + i];
         q2z[r] = -2.0f * gq[2ll * p.nq_pad + i];
-        const bool live = q0 + r * 32 < p.nq;
+        const bool live = (livemask >> r) & 1u;
         thr[r] = live ? CUDART_INF_F : -CUDART_INF_F;
         if (live) dmax = CUDART_INF_F;
         ws.qs[0][r * 32 + lane] = -0.5f * q2x[r];
@@ -529,7 +542,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         }
     }
     for (int r = 0; r < Q; ++r) {  // run-time loop on purpose
-        const bool live = q0 + r * 32 < p.nq;
+        const bool live = (livemask >> r) & 1u;
         mt_l[r] = CUDART_INF_F;
         thr_l[r] = live ? CUDART_INF_F : -CUDART_INF_F;
         Dbest_l[r] = CUDART_INF;
@@ -546,7 +559,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         bool ok = true;
         for (int r = 0; r < Q; ++r) {  // run-time loop: the resolve state lives in local memory
             const int i = q0 + r * 32;
-            if (i >= p.nq) continue;
+            if (!((livemask >> r) & 1u)) continue;
             const int h = p.hint[(long long)b * p.nq_pad + i];
             if (h < 0 || h >= p.nt) { ok = false; continue; }
             const int qs = r * 32 + lane;
@@ -579,7 +592,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     // ---- query-row spheres: row r is 32 consecutive stored queries, a compact patch ----------
 #pragma unroll
     for (int r = 0; r < Q; ++r) {
-        const bool live = q0 + r * 32 < p.nq;
+        const bool live = (livemask >> r) & 1u;
         float cx = live ? q2x[r] : 0.f, cy = live ? q2y[r] : 0.f, cz = live ? q2z[r] : 0.f,
               cn = live ? 1.f : 0.f;
 #pragma unroll
@@ -852,7 +865,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
 
     for (int r = 0; r < Q; ++r) {
         const int i = q0 + r * 32;
-        if (i < p.nq) {
+        if ((livemask >> r) & 1u) {
             const int io = p.perm_q != nullptr ? p.perm_q[i] : i;
             const int jo = p.perm_t != nullptr ? p.perm_t[min(ibest_l[r], p.nt - 1)] : ibest_l[r];
             const long long o = (long long)b * p.nq + io;
@@ -912,10 +925,17 @@ block_weight_kernel(const float *__restrict__ q, long long q_bstride, int nq, in
     if (lane == 0) keys[w] = ((u64)(~__float_as_uint(m)) << 32) | (u64)(unsigned)blk;
 }
 
-// one CTA per batch item: bitonic sort of its <= kOrderMax keys, order[i] = block of rank i
+// one CTA per batch item: bitonic sort of its <= kOrderMax keys; then the launch list:
+// the (at most kSplitMax) blocks whose radius exceeds twice the median radius -- blocks that
+// straddle a gap of the curve and need the neighbourhoods of several patches -- are split
+// into Q single-row entries, everything else follows as whole blocks in descending weight.
+constexpr int kSplitMax = 128;  // (512 was measured slower: 25 % more total work, tail no longer the limit)
 __global__ void __launch_bounds__(1024)
-block_order_kernel(const u64 *__restrict__ keys, int nqb, int *__restrict__ order) {
+block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, int split_max,
+                   int *__restrict__ order, int *__restrict__ order_count) {
     __shared__ u64 s[kOrderMax];
+    __shared__ int nsplit;
+    static_assert(kSplitMax == 128, "order_workspace_bytes sizes the launch list for 128 split blocks");
     const int b = blockIdx.x;
     int n2 = 1;
     while (n2 < nqb) n2 <<= 1;
@@ -932,7 +952,24 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int *__restrict__ orde
             __syncthreads();
         }
     }
-    for (int i = threadIdx.x; i < nqb; i += 1024) order[(long long)b * nqb + i] = (int)(unsigned)(s[i] & 0xffffffffull);
+    if (threadIdx.x == 0) {
+        const float wmed = __uint_as_float(~(unsigned)(s[nqb / 2] >> 32));
+        int h = 0;
+        while (h < split_max && h < nqb && __uint_as_float(~(unsigned)(s[h] >> 32)) > 4.0f * wmed) ++h;
+        nsplit = h;
+        order_count[b] = nqb + (rows - 1) * h;
+    }
+    __syncthreads();
+    const int h = nsplit;
+    int *out = order + (long long)b * stride;
+    for (int i = threadIdx.x; i < nqb; i += 1024) {
+        const int blk = (int)(unsigned)(s[i] & 0xffffffffull);
+        if (i < h) {
+            for (int r = 0; r < rows; ++r) out[i * rows + r] = blk | ((r + 1) << 24);
+        } else {
+            out[h * rows + (i - h)] = blk;
+        }
+    }
 }
 
 // partial results carry original indices; exact ties go to the lower one
@@ -1064,7 +1101,9 @@ static int choose_splits(long long ctas, int stages, int slots) {
 }
 
 static size_t order_workspace_bytes(long long nqb, long long batch) {
-    return align256((size_t)nqb * batch * 8) + align256((size_t)nqb * batch * 4);
+    // keys, launch list (room for kSplitMax = 128 blocks split into 8 rows), entry counts
+    return align256((size_t)nqb * batch * 8) + align256((size_t)(nqb + 7 * 128) * batch * 4) +
+           align256((size_t)batch * 4);
 }
 
 struct NN2Call {
@@ -1113,18 +1152,30 @@ static int nn2_dispatch(const NN2Call &c) {
     if (const char *e = getenv("ISR_NN_ANCHORS")) p.nanchors = atoi(e);
 #endif
     p.order = nullptr;
+    p.order_count = nullptr;
+    int grid_x = nqb;
     if (V::kPrune && nqb > 1 && nqb <= kOrderMax && c.workspace != nullptr &&
         c.workspace_bytes >= order_workspace_bytes(nqb, c.batch)) {
-        u64 *keys = reinterpret_cast<u64 *>(c.workspace);
-        int *order = reinterpret_cast<int *>(reinterpret_cast<char *>(c.workspace) +
-                                             align256((size_t)nqb * c.batch * 8));
+        constexpr int kRows = V::kQueriesPerCta / 32;
+        // splitting only pays when the grid is a few waves deep (a single cloud pair, a few
+        // ICP starts); a big batch hides its wide blocks behind the others
+        const int split_max = (long long)nqb * c.batch <= 16384 ? kSplitMax : 0;
+        const int stride = nqb + (kRows - 1) * split_max;
+        char *w = reinterpret_cast<char *>(c.workspace);
+        u64 *keys = reinterpret_cast<u64 *>(w);
+        int *order = reinterpret_cast<int *>(w + align256((size_t)nqb * c.batch * 8));
+        int *count = reinterpret_cast<int *>(w + align256((size_t)nqb * c.batch * 8) +
+                                             align256((size_t)stride * c.batch * 4));
         const long long warps = (long long)nqb * c.batch;
         block_weight_kernel<V::kQueriesPerCta><<<(unsigned)((warps + 3) / 4), 128, 0, c.st>>>(
             p.q, p.q_bstride, p.nq, p.nq_pad, nqb, (int)c.batch, keys);
         ISR_TRY(launched("block_weight_kernel"));
-        block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, order);
+        block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, kRows, stride, split_max, order,
+                                                                 count);
         ISR_TRY(launched("block_order_kernel"));
         p.order = order;
+        p.order_count = count;
+        grid_x = stride;
     }
     p.dbg = nullptr;
 #ifdef ISR_NN_TUNING
@@ -1152,7 +1203,7 @@ static int nn2_dispatch(const NN2Call &c) {
         if (nores < 0) { const char *e = getenv("ISR_NN2_NORESOLVE"); nores = (e && atoi(e)) ? 1 : 0; }
         p.debug_no_resolve = nores;
     }
-    dim3 grid((unsigned)nqb, (unsigned)splits, (unsigned)c.batch);
+    dim3 grid((unsigned)grid_x, (unsigned)splits, (unsigned)c.batch);
     if (splits == 1) return V::launch(p, grid, c.st);
 
     const long long total = (long long)nq * c.batch;
