@@ -399,6 +399,23 @@ def main():
         finally:
             api.set_nn_pruning(True)
         r = prob.results(with_correspondences=False)[0]
+        # the same source-sharded loop as ONE C call with the exchange of the 17 sums fused into
+        # the accumulate / solve kernels (peer-memory stores + flag wait; no NCCL call, no host
+        # work per iteration) -- the default of dist.icp_sharded under N > 1
+        pprob = api.IcpProblem(src[slo:shi], tgt, np.eye(4)[None])
+        peer = dist.peer_exchange()
+        pprob.run_sharded(peer, len(src), 20.0, 0, 0.0, 0.0)       # warm-up: one evaluation
+        pprob.reopen()
+        barrier()
+        e0.record()
+        pprob.run_sharded(peer, len(src), 20.0, args.icp_iters - 1, 0.0, 0.0)
+        e1.record()
+        barrier()
+        t_icp_peer = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        rp = pprob.results(with_correspondences=False)[0]
+        assert abs(rp.fitness - r.fitness) < 1e-6 and abs(rp.inlier_rmse - r.inlier_rmse) < 0.2 * r.inlier_rmse, \
+            (rp.fitness, r.fitness, rp.inlier_rmse, r.inlier_rmse)
+        del pprob
         # the north star's target-sharded form of the same loop (N > 1 only): every rank
         # searches its slice of the target for ALL source points, two per-point MIN
         # all-reduces pick the neighbour, then the same 17-double SUM all-reduce
@@ -464,11 +481,15 @@ def main():
         secondary = {
             "icp_iters_per_s": args.icp_iters / t_icp,
             "icp_config": f"dense ICP refine (BASELINE configs[3]): {args.icp_points} x {args.icp_points} "
-                          f"points, {args.icp_iters} forced iterations, source sharded x{world}",
+                          f"points, {args.icp_iters} forced iterations, source sharded x{world}, one accumulate + "
+                          f"{'NCCL all-reduce + ' if world > 1 else ''}solve enqueued per iteration",
             "icp_nn_pairs_evaluated_frac": icp_eval / max(icp_answered, 1.0),
             "icp_nn_tflops_evaluated": FLOP_PER_PAIR * icp_eval / (ms_kind[1] * 1e-3) / 1e12,
             "icp_nn_tflops_brute_force_equivalent": FLOP_PER_PAIR * icp_answered / (ms_kind[1] * 1e-3) / 1e12,
             "icp_nn_ms_per_iter": ms_kind[1] / max(n_kind[1], 1),
+            "icp_peer_exchange_iters_per_s": args.icp_iters / t_icp_peer,
+            "icp_peer_exchange_config": "same loop as one isr_icp_run_sharded call: sums exchanged inside the "
+                                        "accumulate/solve kernels through peer memory (NVLink), no NCCL call",
             "icp_target_sharded_iters_per_s": (args.icp_iters / t_icp_tgt) if t_icp_tgt else None,
             "icp_exhaustive_iters_per_s": 1.0 / t_icp_ex,
             "icp_exhaustive_nn_tflops": FLOP_PER_PAIR * ns_local * args.icp_points / t_icp_ex / 1e12,

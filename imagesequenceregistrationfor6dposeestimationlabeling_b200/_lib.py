@@ -19,6 +19,9 @@ ISR_SOA_TILE = 1024
 ISR_SUB_TILE = 64
 ISR_PAD_COORD = np.float32(1.0e18)
 ISR_ICP_NSUMS = 17
+ISR_PEER_MAX_RANKS = 8
+ISR_PEER_MAX_STARTS = 64
+ISR_PEER_HANDLE_BYTES = 64
 
 #: numpy mirror of ``struct IsrIcpState`` (include/isr.h)
 ICP_STATE_DTYPE = np.dtype([
@@ -94,6 +97,11 @@ SIGNATURES = {
     "isr_icp_solve": (_I, [_P, _I64, _P, _I64, _D, _D, _I, _P]),
     "isr_icp_run": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _D, _I, _D, _D, _P, _P, _P, _P, _SZ,
                          _P]),
+    "isr_peer_create": (_I, [_I, _I, _P, _P]),
+    "isr_peer_connect": (_I, [_P, _P]),
+    "isr_peer_destroy": (_I, [_P]),
+    "isr_icp_run_sharded": (_I, [_P, _I64, _P, _P, _P, _I64, _I64, _P, _P, _P, _D, _I, _D, _D, _P, _P, _P,
+                                 _P, _SZ, _P, _P]),
     "isr_radius_count": (_I, [_P, _P, _D, _P, _P]),
     "isr_bench_ffma": (_I, [_I, _I, _I, _P, _P, _P]),
 }

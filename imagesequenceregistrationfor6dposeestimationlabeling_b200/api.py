@@ -644,11 +644,30 @@ class IcpProblem:
             float(rel_fitness), float(rel_rmse), _ptr(self.sums), _ptr(self.corr_idx),
             _ptr(self.inlier), _ptr(self.ws), self.ws.numel(), _stream()))
 
+    def reopen(self) -> None:
+        """Clear `done` of every start (offset 176 of IsrIcpState) so that another run continues
+        from the current poses and correspondences."""
+        self.states.view(torch.int32)[:, 44] = 0
+
+    def run_sharded(self, peer, ns_total: int, max_dist: float, max_iteration: int, rel_fitness: float,
+                    rel_rmse: float) -> None:
+        """`run` for one source shard: the 17 sums are exchanged between the ranks of `peer`
+        (dist.PeerExchange) inside the accumulate / solve kernels (isr_icp_run_sharded)."""
+        _lib.check(_lib.load().isr_icp_run_sharded(
+            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), _ptr(self.src_perm),
+            self.ns, int(ns_total), _ptr(self.tgt), ctypes.byref(self.tgt_desc), _ptr(self.centroid),
+            float(max_dist), int(max_iteration), float(rel_fitness), float(rel_rmse), _ptr(self.sums),
+            _ptr(self.corr_idx), _ptr(self.inlier), _ptr(self.ws), self.ws.numel(), peer.handle,
+            _stream()))
+
     def results(self, with_correspondences: bool = True) -> list:
         st = self.states.cpu().numpy().view(_lib.ICP_STATE_DTYPE).reshape(self.starts)
         out = []
         for k in range(self.starts):
             s = st[k]
+            if int(s["reserved"]) == 1:
+                raise RuntimeError("sharded ICP: a peer rank never delivered its sums (exchange timed "
+                                   "out inside icp_solve_kernel); results are invalid")
             out.append(IcpResult(
                 transformation=s["T"].reshape(4, 4).copy(), fitness=float(s["fitness"]),
                 inlier_rmse=float(s["inlier_rmse"]), n_corr=int(s["n_corr"]),

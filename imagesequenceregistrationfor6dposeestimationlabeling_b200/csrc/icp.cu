@@ -20,6 +20,7 @@
 // T <- U T.  A finished start sets `done`; all later kernels for it exit at once, so the
 // host enqueues max_iteration + 1 passes without ever reading the device.
 #include <math_constants.h>
+#include <string.h>
 
 #include "isr_common.cuh"
 
@@ -31,12 +32,40 @@ constexpr int kStateInts = (int)(sizeof(IsrIcpState) / sizeof(int32_t));
 constexpr int kStateDoubles = (int)(sizeof(IsrIcpState) / sizeof(double));
 static_assert(sizeof(IsrIcpState) % 8 == 0, "IsrIcpState must be a whole number of doubles");
 
+// ---- exchange of the 17 sums between the GPUs of one box, fused into the two ICP kernels ----
+// Every rank owns one small buffer that all peers map through CUDA IPC (NVLink / NVSwitch
+// peer memory):  data[2][world][kPeerStarts][17] doubles and flag[2][world][kPeerStarts].
+// The last-arriving CTA of the accumulate kernel stores this rank's sums for start s into
+// slot [seq & 1][rank][s] of EVERY rank's buffer, fences, and then stores the message number
+// seq into the matching flags; the solve kernel of every rank waits until its own buffer
+// holds seq from all ranks and adds the `world` vectors in rank order -- the same order
+// everywhere, so all ranks solve bit-identical problems.  No collective library call, no
+// extra launch, nothing read by the host.  Two slots suffice: a rank can only start message
+// seq + 1 after it has received every peer's seq, i.e. after every peer has finished reading
+// message seq - 1 from the slot that seq + 1 overwrites.
+constexpr int kPeerRanks = ISR_PEER_MAX_RANKS;
+constexpr int kPeerStarts = ISR_PEER_MAX_STARTS;
+struct PeerView {
+    double *data[kPeerRanks];
+    unsigned long long *flag[kPeerRanks];
+    int rank, world;  // world == 0: no exchange
+    unsigned long long seq;
+};
+__host__ __device__ inline size_t peer_data_index(const PeerView &v, int from_rank, int start) {
+    return (((size_t)(v.seq & 1) * kPeerRanks + from_rank) * kPeerStarts + start) * kNS;
+}
+__host__ __device__ inline size_t peer_flag_index(const PeerView &v, int from_rank, int start) {
+    return ((size_t)(v.seq & 1) * kPeerRanks + from_rank) * kPeerStarts + start;
+}
+constexpr size_t kPeerDataBytes = (size_t)2 * kPeerRanks * kPeerStarts * kNS * sizeof(double);
+constexpr size_t kPeerFlagBytes = (size_t)2 * kPeerRanks * kPeerStarts * sizeof(unsigned long long);
+
 // grid: (nblk, starts)
 __global__ void __launch_bounds__(kAccThreads)
 icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__restrict__ src,
                       const float *__restrict__ src_lo, int64_t ns, const float *__restrict__ tgt, const int32_t *__restrict__ idx,
                       double max_d2, double *__restrict__ partials, unsigned *__restrict__ tickets,
-                      double *__restrict__ sums, uint8_t *__restrict__ inlier) {
+                      double *__restrict__ sums, uint8_t *__restrict__ inlier, const PeerView px) {
     const int s = blockIdx.y;
     const IsrIcpState &stt = states[s];
     if (stt.done != 0) return;
@@ -151,6 +180,16 @@ icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__res
 #pragma unroll
             for (int w = 0; w < kAccThreads / 32; ++w) t += red[w][threadIdx.x];
             sums[(int64_t)s * kNS + threadIdx.x] = t;
+            // push this rank's sums into every rank's exchange buffer (peer stores over NVLink)
+            for (int r = 0; r < px.world; ++r) px.data[r][peer_data_index(px, px.rank, s) + threadIdx.x] = t;
+        }
+        if (px.world > 0) {
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x < px.world) {
+                volatile unsigned long long *f = px.flag[threadIdx.x] + peer_flag_index(px, px.rank, s);
+                *f = px.seq;
+            }
         }
         if (threadIdx.x == 0) tickets[s] = 0;
     }
@@ -286,11 +325,44 @@ __device__ __forceinline__ double det3(const double M[3][3]) {
 // one warp per start; lane 0 carries the (tiny, serial) FP64 solve.
 __global__ void __launch_bounds__(32)
 icp_solve_kernel(IsrIcpState *__restrict__ states, const double *__restrict__ sums,
-                 int64_t ns_total, double rel_fitness, double rel_rmse, int final_eval) {
-    if (threadIdx.x != 0) return;
+                 int64_t ns_total, double rel_fitness, double rel_rmse, int final_eval, const PeerView px) {
     IsrIcpState &st = states[blockIdx.x];
     if (st.done != 0) return;
-    const double *S = sums + (int64_t)blockIdx.x * kNS;
+    __shared__ double Sx[kNS];
+    if (px.world > 0) {
+        // wait for message seq of every rank in THIS rank's buffer, then add in rank order
+        const int s = blockIdx.x;
+        bool ok = true;
+        if ((int)threadIdx.x < px.world) {
+            volatile unsigned long long *f = px.flag[px.rank] + peer_flag_index(px, threadIdx.x, s);
+            const long long t0 = clock64();
+            while (*f != px.seq) {
+                if (clock64() - t0 > 20000000000ll) { ok = false; break; }  // ~10 s: a peer died
+            }
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        __threadfence_system();
+        if (!ok) {
+            if (threadIdx.x == 0) {
+                st.done = 1;
+                st.reserved = 1;  // exchange timed out
+                st.fitness = CUDART_NAN;
+                st.inlier_rmse = CUDART_NAN;
+            }
+            return;
+        }
+        if (threadIdx.x < kNS) {
+            double t = 0.0;
+            for (int r = 0; r < px.world; ++r) {
+                const volatile double *d = px.data[px.rank] + peer_data_index(px, r, s);
+                t += d[threadIdx.x];
+            }
+            Sx[threadIdx.x] = t;
+        }
+        __syncwarp();
+    }
+    if (threadIdx.x != 0) return;
+    const double *S = px.world > 0 ? Sx : sums + (int64_t)blockIdx.x * kNS;
     const double cnt = S[16];
     const double fitness = ns_total > 0 ? cnt / (double)ns_total : 0.0;
     const double rmse = cnt > 0.0 ? sqrt(S[15] / cnt) : 0.0;
@@ -375,7 +447,125 @@ static IcpLayout icp_layout(int64_t ns, int64_t nt, int64_t starts) {
 
 }  // namespace isr
 
+// Host side of the exchange: this rank's buffer, the peers' mappings, the message counter.
+struct IsrPeer {
+    int rank = 0, world = 0;
+    void *own = nullptr;                       // data (kPeerDataBytes) followed by the flags
+    void *mapped[ISR_PEER_MAX_RANKS] = {};     // mapped[rank] == own
+    bool connected = false;
+    unsigned long long seq = 0;                // number of exchanges enqueued so far
+};
+
+namespace isr {
+
+static PeerView peer_view(const IsrPeer *p, bool next_message) {
+    PeerView v{};
+    if (p == nullptr) return v;  // world == 0
+    for (int r = 0; r < p->world; ++r) {
+        char *base = reinterpret_cast<char *>(p->mapped[r]);
+        v.data[r] = reinterpret_cast<double *>(base);
+        v.flag[r] = reinterpret_cast<unsigned long long *>(base + kPeerDataBytes);
+    }
+    v.rank = p->rank;
+    v.world = p->world;
+    v.seq = p->seq + (next_message ? 1 : 0);
+    return v;
+}
+
+static int accumulate_corr_px(const IsrIcpState *states, int64_t starts, const float *src,
+                              const float *src_lo, int64_t ns, const float *tgt, int64_t nt,
+                              const int32_t *corr_idx, double max_dist, double *sums, uint8_t *inlier,
+                              void *workspace, size_t workspace_bytes, const PeerView &px, void *stream) {
+    ISR_REQUIRE(starts >= 1 && starts <= 65535 && ns >= 1 && nt >= 1, ISR_E_SHAPE,
+                "icp_accumulate_corr: bad size");
+    ISR_REQUIRE(states && src && tgt && corr_idx && sums, ISR_E_INVALID_ARG,
+                "icp_accumulate_corr: null pointer");
+    IcpLayout L = icp_layout(ns, nt, starts);
+    ISR_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, ISR_E_WORKSPACE,
+                "icp: workspace %zu < %zu bytes", workspace_bytes, L.total);
+    ISR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ISR_E_ALIGN,
+                "icp: workspace not 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = reinterpret_cast<char *>(workspace);
+    double *partials = reinterpret_cast<double *>(ws + L.partials);
+    unsigned *tickets = reinterpret_cast<unsigned *>(ws + L.tickets);
+    ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
+    const int nblk = acc_blocks(ns);
+    dim3 grid((unsigned)nblk, (unsigned)starts);
+    ProfScope prof(kProfIcpAcc, st);
+    icp_accumulate_kernel<<<grid, kAccThreads, 0, st>>>(states, src, src_lo, ns, tgt, corr_idx,
+                                                        max_dist * max_dist, partials, tickets, sums,
+                                                        inlier, px);
+    return launched("icp_accumulate_kernel");
+}
+
+static int solve_px(IsrIcpState *states, int64_t starts, const double *sums, int64_t ns_total,
+                    double rel_fitness, double rel_rmse, int final_eval, const PeerView &px, void *stream) {
+    ISR_REQUIRE(starts >= 1 && states && sums, ISR_E_INVALID_ARG, "icp_solve: bad argument");
+    ProfScope prof(kProfIcpSolve, (cudaStream_t)stream);
+    icp_solve_kernel<<<(unsigned)starts, 32, 0, (cudaStream_t)stream>>>(
+        states, sums, ns_total, rel_fitness, rel_rmse, final_eval, px);
+    return launched("icp_solve_kernel");
+}
+
+}  // namespace isr
+
 extern "C" {
+
+int isr_peer_create(int rank, int world, IsrPeer **out, unsigned char *handle_out) {
+    using namespace isr;
+    static_assert(sizeof(cudaIpcMemHandle_t) <= ISR_PEER_HANDLE_BYTES, "IPC handle size");
+    ISR_REQUIRE(out != nullptr && handle_out != nullptr, ISR_E_INVALID_ARG, "peer_create: null pointer");
+    ISR_REQUIRE(world >= 1 && world <= ISR_PEER_MAX_RANKS && rank >= 0 && rank < world, ISR_E_INVALID_ARG,
+                "peer_create: rank %d of %d (at most %d ranks)", rank, world, ISR_PEER_MAX_RANKS);
+    IsrPeer *p = new IsrPeer();
+    p->rank = rank;
+    p->world = world;
+    int s = check_cuda(cudaMalloc(&p->own, kPeerDataBytes + kPeerFlagBytes), "peer_create: cudaMalloc");
+    if (s == ISR_OK) s = check_cuda(cudaMemset(p->own, 0, kPeerDataBytes + kPeerFlagBytes), "peer_create: memset");
+    if (s == ISR_OK) s = check_cuda(cudaDeviceSynchronize(), "peer_create: sync");
+    memset(handle_out, 0, ISR_PEER_HANDLE_BYTES);
+    if (s == ISR_OK && world > 1) {
+        cudaIpcMemHandle_t h;
+        s = check_cuda(cudaIpcGetMemHandle(&h, p->own), "peer_create: cudaIpcGetMemHandle");
+        if (s == ISR_OK) memcpy(handle_out, &h, sizeof(h));
+    }
+    if (s != ISR_OK) {
+        if (p->own) cudaFree(p->own);
+        delete p;
+        return s;
+    }
+    p->mapped[rank] = p->own;
+    *out = p;
+    return ISR_OK;
+}
+
+int isr_peer_connect(IsrPeer *p, const unsigned char *handles) {
+    using namespace isr;
+    ISR_REQUIRE(p != nullptr && (handles != nullptr || p->world == 1), ISR_E_INVALID_ARG,
+                "peer_connect: null pointer");
+    ISR_REQUIRE(!p->connected, ISR_E_INVALID_ARG, "peer_connect: already connected");
+    for (int r = 0; r < p->world; ++r) {
+        if (r == p->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * ISR_PEER_HANDLE_BYTES, sizeof(h));
+        ISR_TRY(check_cuda(cudaIpcOpenMemHandle(&p->mapped[r], h, cudaIpcMemLazyEnablePeerAccess),
+                           "peer_connect: cudaIpcOpenMemHandle"));
+    }
+    p->connected = true;
+    return ISR_OK;
+}
+
+int isr_peer_destroy(IsrPeer *p) {
+    using namespace isr;
+    if (p == nullptr) return ISR_OK;
+    int s = check_cuda(cudaDeviceSynchronize(), "peer_destroy: sync");
+    for (int r = 0; r < p->world; ++r)
+        if (r != p->rank && p->mapped[r] != nullptr) cudaIpcCloseMemHandle(p->mapped[r]);
+    if (p->own) cudaFree(p->own);
+    delete p;
+    return s;
+}
 
 size_t isr_icp_workspace_bytes(int64_t ns, int64_t nt, int64_t starts) {
     if (ns < 1 || nt < 1 || starts < 1) return 256;
@@ -438,31 +628,14 @@ int isr_icp_accumulate_corr(const IsrIcpState *states, int64_t starts, const flo
                             const int32_t *corr_idx, double max_dist, double *sums, uint8_t *inlier,
                             void *workspace, size_t workspace_bytes, void *stream) {
     using namespace isr;
-    ISR_REQUIRE(starts >= 1 && starts <= 65535 && ns >= 1 && nt >= 1, ISR_E_SHAPE,
-                "icp_accumulate_corr: bad size");
-    ISR_REQUIRE(states && src && tgt && corr_idx && sums, ISR_E_INVALID_ARG,
-                "icp_accumulate_corr: null pointer");
-    IcpLayout L = icp_layout(ns, nt, starts);
-    ISR_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, ISR_E_WORKSPACE,
-                "icp: workspace %zu < %zu bytes", workspace_bytes, L.total);
-    ISR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ISR_E_ALIGN,
-                "icp: workspace not 256-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-    char *ws = reinterpret_cast<char *>(workspace);
-    double *partials = reinterpret_cast<double *>(ws + L.partials);
-    unsigned *tickets = reinterpret_cast<unsigned *>(ws + L.tickets);
     if (max_dist <= 0.0) {
         // upstream: a non-positive distance yields an empty result
-        return check_cuda(cudaMemsetAsync(sums, 0, (size_t)starts * kNS * 8, st), "icp memset");
+        ISR_REQUIRE(starts >= 1 && sums, ISR_E_INVALID_ARG, "icp_accumulate_corr: bad argument");
+        return check_cuda(cudaMemsetAsync(sums, 0, (size_t)starts * kNS * 8, (cudaStream_t)stream),
+                          "icp memset");
     }
-    ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
-    const int nblk = acc_blocks(ns);
-    dim3 grid((unsigned)nblk, (unsigned)starts);
-    ProfScope prof(kProfIcpAcc, st);
-    icp_accumulate_kernel<<<grid, kAccThreads, 0, st>>>(states, src, src_lo, ns, tgt, corr_idx,
-                                                        max_dist * max_dist, partials, tickets, sums,
-                                                        inlier);
-    return launched("icp_accumulate_kernel");
+    return accumulate_corr_px(states, starts, src, src_lo, ns, tgt, nt, corr_idx, max_dist, sums, inlier,
+                              workspace, workspace_bytes, PeerView{}, stream);
 }
 
 int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
@@ -482,12 +655,8 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, co
 
 int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64_t ns_total,
                   double rel_fitness, double rel_rmse, int final_eval, void *stream) {
-    using namespace isr;
-    ISR_REQUIRE(starts >= 1 && states && sums, ISR_E_INVALID_ARG, "icp_solve: bad argument");
-    ProfScope prof(kProfIcpSolve, (cudaStream_t)stream);
-    icp_solve_kernel<<<(unsigned)starts, 32, 0, (cudaStream_t)stream>>>(
-        states, sums, ns_total, rel_fitness, rel_rmse, final_eval);
-    return launched("icp_solve_kernel");
+    return isr::solve_px(states, starts, sums, ns_total, rel_fitness, rel_rmse, final_eval,
+                         isr::PeerView{}, stream);
 }
 
 int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
@@ -503,6 +672,45 @@ int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const flo
                                    stream));
         ISR_TRY(isr_icp_solve(states, starts, sums, ns, rel_fitness, rel_rmse,
                               k == max_iteration ? 1 : 0, stream));
+    }
+    return ISR_OK;
+}
+
+int isr_icp_run_sharded(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                        const int32_t *src_perm, int64_t ns, int64_t ns_total, const float *tgt,
+                        const IsrCloud *tgt_cloud, const double *centroid, double max_dist,
+                        int max_iteration, double rel_fitness, double rel_rmse, double *sums,
+                        int32_t *corr_idx, uint8_t *inlier, void *workspace, size_t workspace_bytes,
+                        IsrPeer *peer, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(max_iteration >= 0, ISR_E_INVALID_ARG, "icp_run_sharded: max_iteration < 0");
+    ISR_REQUIRE(peer != nullptr && peer->connected, ISR_E_INVALID_ARG,
+                "icp_run_sharded: the peer exchange is not connected");
+    ISR_REQUIRE(starts >= 1 && starts <= ISR_PEER_MAX_STARTS, ISR_E_SHAPE,
+                "icp_run_sharded: starts %lld outside 1..%d", (long long)starts, ISR_PEER_MAX_STARTS);
+    ISR_REQUIRE(tgt_cloud != nullptr && tgt != nullptr && sums != nullptr, ISR_E_INVALID_ARG,
+                "icp_run_sharded: null pointer");
+    ISR_REQUIRE(ns >= 1 && ns_total >= ns, ISR_E_SHAPE, "icp_run_sharded: ns %lld, ns_total %lld",
+                (long long)ns, (long long)ns_total);
+    for (int k = 0; k <= max_iteration; ++k) {
+        if (max_dist > 0.0) {
+            ISR_TRY(isr_icp_search(states, starts, src, src_lo, src_perm, ns, tgt_cloud, centroid, corr_idx,
+                                   workspace, workspace_bytes, stream));
+            // the message number advances only once both kernels of the pair are enqueued
+            const PeerView px = peer_view(peer, true);
+            ISR_TRY(accumulate_corr_px(states, starts, src, src_lo, ns, tgt, tgt_cloud->n, corr_idx, max_dist,
+                                       sums, inlier, workspace, workspace_bytes, px, stream));
+            const int s = solve_px(states, starts, sums, ns_total, rel_fitness, rel_rmse,
+                                   k == max_iteration ? 1 : 0, px, stream);
+            peer->seq += 1;  // the accumulate kernel has been launched: its message exists
+            ISR_TRY(s);
+        } else {
+            // no correspondences anywhere: every rank's sums are zero, nothing to exchange
+            ISR_TRY(check_cuda(cudaMemsetAsync(sums, 0, (size_t)starts * kNS * 8, (cudaStream_t)stream),
+                               "icp memset"));
+            ISR_TRY(solve_px(states, starts, sums, ns_total, rel_fitness, rel_rmse,
+                             k == max_iteration ? 1 : 0, PeerView{}, stream));
+        }
     }
     return ISR_OK;
 }

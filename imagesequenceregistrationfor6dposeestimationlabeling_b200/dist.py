@@ -8,9 +8,12 @@ the selection: an exact first-minimum argmin built from two 8-byte MIN all-reduc
 ``list.index(min(list))`` of verfication.py:105-106 across ranks.
 
 Single-pair ICP shards the SOURCE points by default; the target is replicated (12 MB at
-1 M points, L2-resident).  Per iteration one 17-double SUM all-reduce of the partial Kabsch
-sums sits between the accumulate and solve kernels; every rank then solves the same 3x3
-problem, so no broadcast is needed and all ranks hold bit-identical poses.  Nothing is read
+1 M points, L2-resident).  Per iteration the 17 partial Kabsch sums per start are exchanged
+between the accumulate and solve kernels; every rank then solves the same 3x3 problem, so no
+broadcast is needed and all ranks hold bit-identical poses.  The exchange is fused into the
+two kernels (`PeerExchange`: stores into the peers' HBM over NVLink, flag wait in the solve
+kernel, fixed rank-order sum) -- no collective call, no extra launch, the loop is one C call;
+an NCCL all-reduce per iteration is the alternative (`exchange="nccl"`).  Nothing is read
 back to the host inside the loop.  
 
 `shard="target"` is the north star's variant: every rank holds a contiguous slice of the
@@ -125,6 +128,69 @@ def verify_poses_sharded(cloud_q, poses_q, poses_t, cloud_t=None, mode: str = "c
     return best_idx, best_loss, losses
 
 
+class PeerExchange:
+    """This rank's end of the kernel-fused exchange of isr_icp_run_sharded (include/isr.h):
+    a small buffer in this GPU's HBM that every peer maps through CUDA IPC and writes over
+    NVLink.  The IPC handles travel once through torch.distributed (all_gather, any backend);
+    the loop itself contains no collective call.  Collective: every rank of `group` must
+    construct it, and `close()` it, at the same point."""
+
+    def __init__(self, group=None):
+        import ctypes
+
+        from . import _lib
+
+        self.group = group
+        if td.is_initialized():
+            self.rank, self.world = td.get_rank(group), td.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        if self.world > _lib.ISR_PEER_MAX_RANKS:
+            raise ValueError(f"PeerExchange: {self.world} ranks > {_lib.ISR_PEER_MAX_RANKS}")
+        lib = _lib.load()
+        self.handle = ctypes.c_void_p()
+        mine = (ctypes.c_ubyte * _lib.ISR_PEER_HANDLE_BYTES)()
+        _lib.check(lib.isr_peer_create(self.rank, self.world, ctypes.byref(self.handle), mine))
+        handles = bytes(mine)
+        if self.world > 1:
+            # rides on whatever backend the group has; a byte tensor on the group's device
+            dev = (torch.device("cuda", torch.cuda.current_device())
+                   if td.get_backend(group) == "nccl" else torch.device("cpu"))
+            t = torch.frombuffer(bytearray(handles), dtype=torch.uint8).to(dev)
+            out = torch.empty((self.world * len(handles),), dtype=torch.uint8, device=dev)
+            td.all_gather_into_tensor(out, t, group=group)
+            handles = bytes(out.cpu().numpy().tobytes())
+        buf = (ctypes.c_ubyte * len(handles)).from_buffer_copy(handles)
+        _lib.check(lib.isr_peer_connect(self.handle, buf))
+
+    def close(self) -> None:
+        from . import _lib
+
+        if self.handle is not None and self.handle.value:
+            if self.world > 1:
+                torch.cuda.synchronize()
+                td.barrier(group=self.group)  # no peer may still be writing into this buffer
+            _lib.check(_lib.load().isr_peer_destroy(self.handle))
+            self.handle = None
+
+
+_peer_cache: dict = {}
+
+
+def peer_exchange(group=None) -> PeerExchange:
+    """The process-wide PeerExchange of `group` (created on first use; collective)."""
+    key = id(group) if group is not None else None
+    if key not in _peer_cache:
+        _peer_cache[key] = PeerExchange(group)
+    return _peer_cache[key]
+
+
+def close_peer_exchanges() -> None:
+    """Collective: release every cached PeerExchange (before destroy_process_group)."""
+    for key in sorted(_peer_cache, key=lambda k: (k is not None, k)):
+        _peer_cache.pop(key).close()
+
+
 class CudaIcpBackend:
     """accumulate / solve of one source shard on this rank's GPU (api.IcpProblem)."""
 
@@ -194,15 +260,20 @@ def _icp_target_sharded(source, target, inits, max_dist, max_iteration, rel_fitn
 def icp_sharded(source, target, init=None, max_correspondence_distance: float = 20.0,
                 max_iteration: int = 30, relative_fitness: float = 1e-6,
                 relative_rmse: float = 1e-6, group=None, backend_factory: Optional[Callable] = None,
-                shard: str = "source"):
+                shard: str = "source", exchange: str = "auto"):
     """Every rank passes the FULL source and target.  shard="source": rank r registers source
-    rows shard_bounds(ns, r, world) against the whole target; the loop enqueues accumulate ->
-    all-reduce(17 doubles per start) -> solve per iteration.  shard="target": rank r holds
-    target rows shard_bounds(nt, r, world) (module docstring).  Neither form synchronises with
-    the host inside the loop.  Returns this rank's list of results (identical on all ranks);
-    `init` may be [4,4] or [S,4,4]."""
+    rows shard_bounds(ns, r, world) against the whole target; per iteration the 17 sums per
+    start are exchanged between accumulate and solve -- exchange="peer": inside those two
+    kernels through peer memory (PeerExchange / isr_icp_run_sharded; the whole loop is one C
+    call), exchange="nccl": one all-reduce per iteration, "auto": peer whenever it applies
+    (CUDA back end, every shard non-empty, at most 64 starts, at most 8 ranks).
+    shard="target": rank r holds target rows shard_bounds(nt, r, world) (module docstring).
+    No form synchronises with the host inside the loop.  Returns this rank's list of results
+    (identical on all ranks); `init` may be [4,4] or [S,4,4]."""
     if shard not in ("source", "target"):
         raise ValueError("shard must be 'source' or 'target'")
+    if exchange not in ("auto", "peer", "nccl"):
+        raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
     if td.is_initialized():
         rank, world = td.get_rank(group), td.get_world_size(group)
     else:
@@ -213,6 +284,22 @@ def icp_sharded(source, target, init=None, max_correspondence_distance: float = 
                                    relative_fitness, relative_rmse, group, backend_factory, rank, world)
     ns = len(source)
     lo, hi = shard_bounds(ns, rank, world)
+    from . import _lib
+
+    # decided from (ns, world, starts) alone, hence identically on every rank
+    peer_ok = (backend_factory is None and world <= _lib.ISR_PEER_MAX_RANKS
+               and len(inits) <= _lib.ISR_PEER_MAX_STARTS
+               and all(shard_bounds(ns, r, world)[0] < shard_bounds(ns, r, world)[1] for r in range(world)))
+    if exchange == "peer" and not peer_ok:
+        raise ValueError("exchange='peer' needs the CUDA back end, a non-empty shard on every rank, "
+                         f"<= {_lib.ISR_PEER_MAX_STARTS} starts and <= {_lib.ISR_PEER_MAX_RANKS} ranks")
+    if peer_ok and (exchange == "peer" or (exchange == "auto" and world > 1)):
+        from . import api
+
+        prob = api.IcpProblem(source[lo:hi], target, inits)
+        prob.run_sharded(peer_exchange(group), ns, max_correspondence_distance, max_iteration,
+                         relative_fitness, relative_rmse)
+        return prob.results(with_correspondences=False)
     factory = backend_factory or CudaIcpBackend
     be = factory(source[lo:hi], target, inits)
     for k in range(max_iteration + 1):

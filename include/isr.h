@@ -271,6 +271,41 @@ int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const flo
                 double rel_rmse, double *sums, int32_t *corr_idx, uint8_t *inlier,
                 void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- source-sharded ICP over the GPUs of one box (collective C2) ------ */
+/* One process per GPU.  Instead of a collective-library call between the accumulate and
+ * solve kernels, the exchange of the 17 sums is FUSED into them: the last CTA of
+ * icp_accumulate_kernel stores this rank's sums straight into every peer's exchange buffer
+ * (CUDA IPC mapping of peer HBM, carried by NVLink / NVSwitch), and icp_solve_kernel waits
+ * on flags in its own buffer and adds the ranks' vectors in rank order, so that all ranks
+ * solve bit-identical 3x3 problems.  No extra launch, no host synchronisation.
+ *   isr_peer_create   allocates this rank's buffer; handle_out receives ISR_PEER_HANDLE_BYTES
+ *                     bytes that the caller passes to all other ranks by any means
+ *                     (torch.distributed all_gather in dist.py)
+ *   isr_peer_connect  handles = world x ISR_PEER_HANDLE_BYTES bytes, in rank order (the own
+ *                     entry is ignored); maps every peer's buffer
+ *   isr_peer_destroy  unmaps and frees; all ranks must have finished their loops (barrier)
+ * world == 1 is allowed (the rank exchanges with itself; used by single-GPU tests). */
+#define ISR_PEER_MAX_RANKS 8
+#define ISR_PEER_MAX_STARTS 64
+#define ISR_PEER_HANDLE_BYTES 64
+typedef struct IsrPeer IsrPeer;
+int isr_peer_create(int rank, int world, IsrPeer **out, unsigned char *handle_out);
+int isr_peer_connect(IsrPeer *peer, const unsigned char *handles);
+int isr_peer_destroy(IsrPeer *peer);
+
+/* isr_icp_run for one SOURCE shard: src / src_lo / src_perm / corr_idx / inlier describe this
+ * rank's ns rows, ns_total is the global source count, the target is replicated.  Every
+ * rank of `peer` must make the same sequence of calls with the same starts, criteria and
+ * max_iteration.  starts <= ISR_PEER_MAX_STARTS.  A peer that never arrives makes the solve
+ * kernel give up after ~10 s: the state gets done = 1, reserved = 1 and NaN fitness.
+ * registration_icp, icp.py:101-103. */
+int isr_icp_run_sharded(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                        const int32_t *src_perm, int64_t ns, int64_t ns_total, const float *tgt,
+                        const IsrCloud *tgt_cloud, const double *centroid, double max_dist,
+                        int max_iteration, double rel_fitness, double rel_rmse, double *sums,
+                        int32_t *corr_idx, uint8_t *inlier, void *workspace, size_t workspace_bytes,
+                        IsrPeer *peer, void *stream);
+
 /* ---- radius neighbour count ----------------------------------- */
 /* out_count[i] (int32 [nq], original query indexing) = number of target points with
  * d^2 < radius^2 (strict, float64 decision, a point coinciding with the query included):

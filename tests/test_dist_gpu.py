@@ -38,10 +38,21 @@ def _worker(rank, world, port, q):
         src, tgt, _ = synth.icp_pair(9001, 9500, 6, 7)
         res = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=12)
         out["icp"] = (res[0].transformation, res[0].fitness, res[0].inlier_rmse, res[0].iterations)
+        res = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=12, exchange="nccl")
+        out["icp_nccl"] = (res[0].transformation, res[0].fitness, res[0].inlier_rmse, res[0].iterations)
+        inits = np.stack([synth.pose_matrix(synth.rotvec_to_matrix([0, 0, 2 * np.pi * k / 5]), [0, 0, 0])
+                          for k in range(5)])
+        res = dist.icp_sharded(src, tgt, inits, 20.0, max_iteration=30, relative_fitness=1e-4,
+                               relative_rmse=1e-3)
+        out["icp_multi"] = [(r.transformation, r.fitness, r.inlier_rmse, r.iterations) for r in res]
+        res = dist.icp_sharded(src, tgt, inits, 20.0, max_iteration=30, relative_fitness=1e-4,
+                               relative_rmse=1e-3, exchange="nccl")
+        out["icp_multi_nccl"] = [(r.transformation, r.fitness, r.inlier_rmse, r.iterations) for r in res]
         res = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=12, shard="target")
         out["icp_target"] = (res[0].transformation, res[0].fitness, res[0].inlier_rmse, res[0].iterations)
         torch.cuda.synchronize()
     finally:
+        dist.close_peer_exchanges()
         td.destroy_process_group()
     q.put((rank, out))
 
@@ -72,11 +83,20 @@ def test_two_gpu_sharding_matches_oracle():
         assert bi == ref_best == k0
         np.testing.assert_allclose(losses, ref, rtol=1e-5)
         np.testing.assert_allclose(bl, ref[ref_best], rtol=1e-5)
-        for key in ("icp", "icp_target"):
+        for key in ("icp", "icp_nccl", "icp_target"):
             T, fit, rmse, it = got[r][key]
             np.testing.assert_allclose(T, o.transformation, rtol=1e-7, atol=1e-7)
             assert it == o.iterations and abs(fit - o.fitness) < 1e-12
             np.testing.assert_allclose(rmse, o.inlier_rmse, rtol=1e-7)
     np.testing.assert_array_equal(got[0]["icp"][0], got[1]["icp"][0])   # bit-identical ranks
+    # the kernel-fused peer exchange (default) adds the two ranks' sums in rank order, as the
+    # 2-rank all-reduce does: same bits
+    np.testing.assert_array_equal(got[0]["icp"][0], got[0]["icp_nccl"][0])
+    for r in (0, 1):
+        assert len(got[r]["icp_multi"]) == 5
+        for a, b, c in zip(got[r]["icp_multi"], got[r]["icp_multi_nccl"], got[0]["icp_multi"]):
+            np.testing.assert_array_equal(a[0], c[0])
+            np.testing.assert_allclose(a[0], b[0], rtol=1e-9, atol=1e-9)
+            assert a[3] == b[3] and a[1] == b[1]
     np.testing.assert_array_equal(got[0]["icp_target"][0], got[1]["icp_target"][0])
     np.testing.assert_array_equal(got[0]["verify"][2], got[1]["verify"][2])

@@ -500,6 +500,35 @@ def test_icp_search_accumulate_halves_equal_the_fused_call(gpu):
     assert np.isinf(prob.corr_dist(half).cpu().numpy()[0, ::2]).all()
 
 
+def test_icp_kernel_fused_exchange_single_rank_equals_icp_run(gpu):
+    """isr_icp_run_sharded with a one-rank PeerExchange (the rank stores its sums into its own
+    exchange buffer and the solve kernel waits on the flag and reads them back) reproduces
+    isr_icp_run bit for bit -- single start, multi-start with starts finishing at different
+    iterations, reuse of the exchange across problems, and max_dist <= 0."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api, dist, synth
+    src, tgt, _ = synth.icp_pair(7001, 8000, 6, 7)
+    a = gpu.icp(src, tgt, np.eye(4), 20.0, max_iteration=9)
+    b = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=9, exchange="peer")[0]
+    np.testing.assert_array_equal(a.transformation, b.transformation)
+    assert (a.fitness, a.inlier_rmse, a.iterations) == (b.fitness, b.inlier_rmse, b.iterations)
+    inits = np.stack([synth.pose_matrix(synth.rotvec_to_matrix([0, 0, 2 * np.pi * k / 5]), [0, 0, 0])
+                          for k in range(5)])
+    ref = api.IcpProblem(src, tgt, inits)
+    ref.run(20.0, 30, 1e-4, 1e-3)
+    got = dist.icp_sharded(src, tgt, inits, 20.0, max_iteration=30, relative_fitness=1e-4,
+                           relative_rmse=1e-3, exchange="peer")
+    want = ref.results(with_correspondences=False)
+    assert min(w.iterations for w in want) < 30   # some start stops by the criteria, on the device
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g.transformation, w.transformation)
+        assert (g.fitness, g.inlier_rmse, g.iterations) == (w.fitness, w.inlier_rmse, w.iterations)
+    z = dist.icp_sharded(src, tgt, np.eye(4), 0.0, max_iteration=3, exchange="peer")[0]
+    assert z.fitness == 0.0 and z.inlier_rmse == 0.0
+    np.testing.assert_array_equal(z.transformation, np.eye(4))
+    with pytest.raises(ValueError):
+        dist.icp_sharded(src, tgt, np.tile(np.eye(4), (65, 1, 1)), 20.0, max_iteration=1, exchange="peer")
+
+
 @pytest.mark.parametrize("n,radius,scale,offset", [
     (1, 1.0, 1.0, 0.0), (300, 3.0, 1.0, 0.0), (6000, 4.0, 1.0, 0.0), (6000, 0.05 * 60 / 1.8, 1.0, 0.0),
     (5000, 0.002, 1.0 / 2000, 0.0), (4000, 4.0, 1.0, 700.0), (3000, 1e-3, 1.0, 900.0)])
