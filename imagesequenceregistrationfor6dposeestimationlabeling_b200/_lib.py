@@ -43,7 +43,7 @@ class IsrCloud(ctypes.Structure):
     """ctypes mirror of ``struct IsrCloud`` (include/isr.h)."""
     _fields_ = [("soa7", ctypes.c_void_p), ("n", ctypes.c_int64), ("npad", ctypes.c_int64),
                 ("bstride", ctypes.c_int64), ("stage_c", ctypes.c_void_p), ("perm", ctypes.c_void_p),
-                ("sub_c", ctypes.c_void_p), ("hint", ctypes.c_void_p)]
+                ("sub_c", ctypes.c_void_p), ("hint", ctypes.c_void_p), ("sub_box", ctypes.c_void_p)]
 
 
 class IsrError(RuntimeError):
@@ -79,7 +79,7 @@ SIGNATURES = {
     "isr_spatial_order_workspace_bytes": (_SZ, [_I64]),
     "isr_spatial_order": (_I, [_P, _I64, _P, _P, _SZ, _P]),
     "isr_prepare_cloud": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
-    "isr_tile_spheres": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P, _P]),
+    "isr_tile_spheres": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),
     "isr_set_nn_pruning": (_I, [_I]),
     "isr_get_nn_pruning": (_I, []),
     "isr_profile_nn_pairs": (_I, [_P, _P]),

@@ -149,6 +149,7 @@ class SoaCloud:
     perm: Optional[torch.Tensor] = None      # int32 [n]: stored position -> original index
     stage_c: Optional[torch.Tensor] = None   # float32 [B, npad/1024, 4] stage spheres (c, r)
     sub_c: Optional[torch.Tensor] = None     # float32 [B, npad/64, 4] sub-tile spheres
+    sub_box: Optional[torch.Tensor] = None   # int32 [B, npad/64] packed half-extents of the sub-tile boxes
 
     @property
     def planes(self) -> int:
@@ -158,7 +159,7 @@ class SoaCloud:
         """ctypes ``IsrCloud`` for this cloud (7-plane clouds only)."""
         return _lib.IsrCloud(self.data.data_ptr(), self.n, self.npad,
                              7 * self.npad if batched else 0, _ptr(self.stage_c), _ptr(self.perm),
-                             _ptr(self.sub_c), None)
+                             _ptr(self.sub_c), None, _ptr(self.sub_box))
 
     @property
     def npad(self) -> int:
@@ -244,15 +245,16 @@ def prepare_cloud(points, poses=None, centroid=None, centre_poses=None, perm=Non
             _ptr(pts), _ptr(pts_lo), _ptr(perm), n, None if P is None else _ptr(P[b0:]), 16,
             None if C is None else _ptr(C[b0:]), 16, _ptr(cen), bc, _ptr(out[b0:]), npad, None, 0,
             _stream()))
-    sc = sub = None
+    sc = sub = box = None
     if stage_centroids:
         sc = torch.empty((b, npad // _lib.ISR_SOA_TILE, 4), dtype=torch.float32, device=device)
         sub = torch.empty((b, npad // _lib.ISR_SUB_TILE, 4), dtype=torch.float32, device=device)
+        box = torch.empty((b, npad // _lib.ISR_SUB_TILE), dtype=torch.int32, device=device)
         for b0 in range(0, b, 65535):
             bc = min(65535, b - b0)
             _lib.check(lib.isr_tile_spheres(_ptr(out[b0:]), n, npad, 7 * npad, bc, _ptr(sc[b0:]),
-                                            _ptr(sub[b0:]), _stream()))
-    return SoaCloud(out, n, cen, perm, sc, sub)
+                                            _ptr(sub[b0:]), _ptr(box[b0:]), _stream()))
+    return SoaCloud(out, n, cen, perm, sc, sub, box)
 
 
 def _pack_batched(points, device) -> SoaCloud:
@@ -312,11 +314,12 @@ def nearest_neighbors_soa(q: SoaCloud, t: SoaCloud, return_index: bool = True,
         if pl == 7:
             ws = _workspace(lib.isr_nn2_workspace_bytes(q.n, t.n, bc), device)
             qdesc = _lib.IsrCloud(qd.data_ptr(), q.n, q.npad, pl * q.npad if qb > 1 else 0, None,
-                                  _ptr(q.perm), None, None)
+                                  _ptr(q.perm), None, None, None)
             tsc = None if t.stage_c is None else (t.stage_c[b0:] if tb > 1 else t.stage_c)
             tsub = None if t.sub_c is None else (t.sub_c[b0:] if tb > 1 else t.sub_c)
+            tbox = None if t.sub_box is None else (t.sub_box[b0:] if tb > 1 else t.sub_box)
             tdesc = _lib.IsrCloud(td.data_ptr(), t.n, t.npad, pl * t.npad if tb > 1 else 0,
-                                  _ptr(tsc), _ptr(t.perm), _ptr(tsub), None)
+                                  _ptr(tsc), _ptr(t.perm), _ptr(tsub), None, _ptr(tbox))
             _lib.check(lib.isr_nn2(
                 ctypes.byref(qdesc), ctypes.byref(tdesc), bc, 1 if use_lo else 0, _ptr(d2[b0:]),
                 _ptr(idx[b0:]) if idx is not None else None, None, 0, _ptr(ws), ws.numel(),

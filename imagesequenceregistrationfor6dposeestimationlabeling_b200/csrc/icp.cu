@@ -607,7 +607,7 @@ int isr_icp_search(IsrIcpState *states, int64_t starts, const float *src, const 
         icp_hint_reset_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(states, nsp, total, hint);
         ISR_TRY(launched("icp_hint_reset_kernel"));
     }
-    const IsrCloud src_cloud{xs, ns, nsp, 7 * nsp, nullptr, src_perm, nullptr, hint};
+    const IsrCloud src_cloud{xs, ns, nsp, 7 * nsp, nullptr, src_perm, nullptr, hint, nullptr};
     return isr_nn2(&src_cloud, tgt_cloud, starts, 1, d2, corr_idx, done, kStateInts, ws + L.nnws,
                    L.total - L.nnws, stream);
 }

@@ -88,7 +88,11 @@ struct NN2Params {
     const int *order_count;  // [batch] entries of `order` in use
     int *hint;               // [batch][nq_pad] in/out starting neighbours (stored positions), or NULL
     int nanchors;            // seeds used (<= kAnchors; fewer only for tuning runs)
+    int sort_fifo;           // scan the queued sub-tiles nearest-first (0: in stage order)
+    const unsigned *sub_h;   // [batch][stages_total * STAGE/SUB] packed half-extents of the sub-tile
+    long long sub_h_bstride; //   boxes (isr_tile_spheres), or NULL: sphere tests only
 };
+constexpr unsigned kNoBox = 0x3FFFFFFFu;  // three 10-bit fractions of the radius, all ones
 
 // Can this lane rule out every point of the tile with sphere S for all of its Q queries?
 // q2* = -2 * query (hi part); dmax >= best distance so far of each of the lane's live queries
@@ -472,6 +476,7 @@ struct alignas(128) PrunedWarpSmem {
     float4 sph[kFifo];         // queued candidates: sphere,
     int id[kFifo];             //   sub-tile index in the target (-1: dropped by the exact test),
     unsigned rows[kFifo];      //   query rows that the coarse test could not rule out
+    unsigned box[kFifo];       //   packed half-extents of its bounding box about the sphere's centre
     float4 row[Q];             // sphere (c, rho) of query row r = the 32 queries r*32 .. r*32+31
     float rowB[Q];             // max of their bounds dq (refreshed between batches of work)
     uint64_t full[kRing];
@@ -510,6 +515,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     const float *__restrict__ gt = p.t + (long long)b * p.t_bstride;
     const float4 *__restrict__ stage_c = p.stage_c + (long long)b * p.stage_c_bstride;
     const float4 *__restrict__ sub_c = p.sub_c + (long long)b * p.sub_c_bstride;
+    const unsigned *__restrict__ sub_h = p.sub_h != nullptr ? p.sub_h + (long long)b * p.sub_h_bstride : nullptr;
     const int stages = p.stages_total;
 
     if (lane == 0) {
@@ -639,6 +645,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         }
         return S.w >= 0.f ? rows : 0u;
     };
+    // the same for a sub-tile with its box (see exact_any_box): the row's sphere must reach both
+    auto coarse_rows_box = [&](const float4 S, unsigned hb) {
+        const float sc = S.w * (1.00001f / 1023.f);
+        const float hx = (float)(hb & 1023u) * sc, hy = (float)((hb >> 10) & 1023u) * sc,
+                    hz = (float)((hb >> 20) & 1023u) * sc;
+        unsigned rows = 0;
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            const float4 R = ws.row[r];
+            const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
+            const float rb = (ws.rowB[r] + R.w) * 1.0001f, rr = rb + S.w * 1.0001f;
+            const float ex = fmaxf(fabsf(dx) - hx, 0.f), ey = fmaxf(fabsf(dy) - hy, 0.f),
+                        ez = fmaxf(fabsf(dz) - hz, 0.f);
+            const bool out = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr ||
+                             fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > rb * rb;
+            if (R.w >= 0.f && !out) rows |= 1u << r;
+        }
+        return S.w >= 0.f ? rows : 0u;
+    };
     // exact test, one query per lane and row: is any query of `rows` not ruled out?
     auto exact_any = [&](const float4 S, unsigned rows) {
         bool need = false;
@@ -650,6 +675,31 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                 const float rr = (dq_l[r] + S.w) * 1.0001f;
                 // a dead query slot (dq = 0, padded coordinates ~1e18) is always ruled out
                 need = need || !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr);
+            }
+        }
+        return __any_sync(0xffffffffu, need);
+    };
+    // the same for a sub-tile that also carries its axis-aligned box (centre = the sphere's,
+    // half-extents = hb's three 10-bit fractions of the radius, rounded up): a query is ruled
+    // out when EITHER volume is farther than its bound.  The patches are thin sheets of the
+    // surface; the box follows them where the sphere is mostly empty.
+    auto exact_any_box = [&](const float4 S, unsigned rows, unsigned hb) {
+        const float sc = S.w * (1.00001f / 1023.f);
+        const float hx = (float)(hb & 1023u) * sc, hy = (float)((hb >> 10) & 1023u) * sc,
+                    hz = (float)((hb >> 20) & 1023u) * sc;
+        bool need = false;
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            if (rows & (1u << r)) {  // warp-uniform
+                const float dx = fmaf(q2x[r], -0.5f, -S.x), dy = fmaf(q2y[r], -0.5f, -S.y),
+                            dz = fmaf(q2z[r], -0.5f, -S.z);
+                const float rr = (dq_l[r] + S.w) * 1.0001f;
+                const float ex = fmaxf(fabsf(dx) - hx, 0.f), ey = fmaxf(fabsf(dy) - hy, 0.f),
+                            ez = fmaxf(fabsf(dz) - hz, 0.f);
+                const float rb = dq_l[r] * 1.0001f;
+                const bool out = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr ||
+                                 fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > rb * rb;
+                need = need || !out;
             }
         }
         return __any_sync(0xffffffffu, need);
@@ -723,6 +773,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                     ws.sph[tail % kFifo] = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
                     ws.id[tail % kFifo] = seed[a];
                     ws.rows[tail % kFifo] = (1u << Q) - 1u;
+                    ws.box[tail % kFifo] = kNoBox;
                 }
                 ++tail;
             }
@@ -740,6 +791,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     //            -> FIFO.
     unsigned nscanned = 0, ntests = 0, ncand = 0, nflag = 0, npass = 0;
     unsigned refreshed_at = ~0u;
+    bool sorted = p.sort_fifo == 0;
     bool seeding = true;   // the seeds must be scanned before anything is produced
     int base = 0;          // next chunk of stage spheres
     int cbase = 0;         // base of the chunk whose candidates are in smask
@@ -749,11 +801,62 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     for (;;) {
         const int pending = tail - head;
         const bool produced_all = smask == 0 && base >= stages;
+        if (produced_all && !sorted) {
+            // Everything is queued: put the untested entries in nearest-first order (squared
+            // distance between the sub-tile's centre and the nearest of the query rows it may
+            // matter to).  Near tiles tighten the bounds first, so that more of the far ones fail
+            // their exact test and fewer scans improve a neighbour that a later scan improves
+            // again.  Rank sort of at most 64 keys, two per lane, through the idle ring buffer.
+            sorted = true;
+            const int cnt = tail - look;
+            if (cnt > 2 && cnt <= 64 && look == head) {
+                u64 *keys = reinterpret_cast<u64 *>(&ws.buf[0][0][0]);
+                float4 S2[2];
+                int id2[2];
+                unsigned rows2[2], box2[2];
+                u64 key2[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int j = k * 32 + lane;
+                    key2[k] = ~0ull;
+                    if (j < cnt) {
+                        const int e = (look + j) % kFifo;
+                        S2[k] = ws.sph[e]; id2[k] = ws.id[e]; rows2[k] = ws.rows[e]; box2[k] = ws.box[e];
+                        float d = CUDART_INF_F;
+#pragma unroll
+                        for (int r = 0; r < Q; ++r) {
+                            const float4 R = ws.row[r];
+                            const float dx = S2[k].x - R.x, dy = S2[k].y - R.y, dz = S2[k].z - R.z;
+                            const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            d = (rows2[k] >> r) & 1u ? fminf(d, dd) : d;
+                        }
+                        key2[k] = ((u64)__float_as_uint(d) << 32) | (u64)(unsigned)j;
+                    }
+                    keys[j] = key2[k];
+                }
+                __syncwarp();
+                int rank0 = 0, rank1 = 0;
+                for (int j = 0; j < cnt; ++j) {
+                    const u64 kj = keys[j];
+                    rank0 += kj < key2[0] ? 1 : 0;
+                    rank1 += kj < key2[1] ? 1 : 0;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (k * 32 + lane < cnt) {
+                        const int e = (look + (k == 0 ? rank0 : rank1)) % kFifo;
+                        ws.sph[e] = S2[k]; ws.id[e] = id2[k]; ws.rows[e] = rows2[k]; ws.box[e] = box2[k];
+                    }
+                }
+                __syncwarp();
+            }
+        }
         if (pending > 0 && (seeding || produced_all || pending > kFifo - 2 * SUBS)) {
             while (look < tail && nloads - nconsumed < kRing) {
                 const int e = look % kFifo;
                 ++ntests;
-                if (exact_any(ws.sph[e], ws.rows[e])) {
+                if (exact_any_box(ws.sph[e], ws.rows[e], ws.box[e])) {
                     if (lane == 0) {
                         const int slot = nloads % kRing;
                         const long long src = (long long)ws.id[e] * SUB;
@@ -831,9 +934,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
             unsigned rows = 0;
             const bool mine = lane < SUBS ? pass1 : pass2;
             const int gid = (cbase + (lane < SUBS ? l1 : l2)) * SUBS + (lane & (SUBS - 1));
+            unsigned hb = kNoBox;
             if (mine) {
                 S = sub_c[gid];
-                rows = coarse_rows(S);
+                if (sub_h != nullptr) hb = sub_h[gid];
+                rows = coarse_rows_box(S, hb);
 #pragma unroll
                 for (int a = 0; a < kAnchors; ++a) rows = gid == seed[a] ? 0u : rows;  // already scanned
             }
@@ -843,6 +948,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                 ws.sph[pos] = S;
                 ws.id[pos] = gid;
                 ws.rows[pos] = rows;
+                ws.box[pos] = hb;
             }
             tail += __popc(m32);
             __syncwarp();
@@ -1140,6 +1246,13 @@ static int nn2_dispatch(const NN2Call &c) {
     p.perm_q = c.q->perm; p.perm_t = c.t->perm;
     p.sub_c = reinterpret_cast<const float4 *>(c.t->sub_c);
     p.sub_c_bstride = c.t->bstride == 0 ? 0 : c.t->npad / ISR_SUB_TILE;
+    p.sub_h = reinterpret_cast<const unsigned *>(c.t->sub_box);
+    p.sub_h_bstride = p.sub_c_bstride;
+    {
+        static int use_box = -1;
+        if (use_box < 0) { const char *e = getenv("ISR_NN_BOX"); use_box = (e && atoi(e) == 0) ? 0 : 1; }
+        if (!use_box) p.sub_h = nullptr;
+    }
     p.evaluated = nullptr;
     if (prof_enabled()) {
         p.evaluated = evaluated_counter();
@@ -1151,6 +1264,11 @@ static int nn2_dispatch(const NN2Call &c) {
 #ifdef ISR_NN_TUNING
     if (const char *e = getenv("ISR_NN_ANCHORS")) p.nanchors = atoi(e);
 #endif
+    {
+        static int sort_fifo = -1;
+        if (sort_fifo < 0) { const char *e = getenv("ISR_NN_SORT"); sort_fifo = (e && atoi(e) == 0) ? 0 : 1; }
+        p.sort_fifo = sort_fifo;
+    }
     p.order = nullptr;
     p.order_count = nullptr;
     int grid_x = nqb;

@@ -142,7 +142,8 @@ prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts
 // owns points 4t..4t+3 of the stage, so a sub-tile is 16 consecutive lanes.
 __global__ void __launch_bounds__(256)
 tile_spheres_kernel(const float *__restrict__ soa7, int64_t n, int64_t npad, int64_t bstride,
-                    float4 *__restrict__ out_stage, float4 *__restrict__ out_sub) {
+                    float4 *__restrict__ out_stage, float4 *__restrict__ out_sub,
+                    uint32_t *__restrict__ out_box) {
     constexpr int kSubs = ISR_SOA_TILE / ISR_SUB_TILE;  // 16
     __shared__ float red[6][8];
     __shared__ float rmax[8];
@@ -199,9 +200,27 @@ tile_spheres_kernel(const float *__restrict__ soa7, int64_t n, int64_t npad, int
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if ((t & 15) == 0) {
+            const float r = any ? inflate(m, cx, cy, cz) : -1.f;
             out_sub[((int64_t)b * gridDim.x + s) * kSubs + (t >> 4)] =
-                any ? make_float4(cx, cy, cz, inflate(m, cx, cy, cz))
+                any ? make_float4(cx, cy, cz, r)
                     : make_float4(ISR_PAD_COORD, ISR_PAD_COORD, ISR_PAD_COORD, -1.f);
+            if (out_box != nullptr) {
+                // half-extents of the bounding box about the same centre, inflated like the radius,
+                // as 10-bit fractions of it, rounded up (decoded as r * k / 1023, again rounded up)
+                unsigned packed = 0x3FFFFFFFu;
+                if (any && r > 0.f) {
+                    const float slack = r - __fsqrt_rd(fmaxf(m, 0.f));  // what `inflate` added
+                    packed = 0;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const float h = 0.5f * (shi[d] - slo[d]) * 1.00002f + slack;
+                        int k = (int)ceilf(h / r * 1023.f * 1.00001f);
+                        k = k < 1 ? 1 : (k > 1023 ? 1023 : k);
+                        packed |= (unsigned)k << (10 * d);
+                    }
+                }
+                out_box[((int64_t)b * gridDim.x + s) * kSubs + (t >> 4)] = packed;
+            }
         }
     }
     // ---- stage: whole CTA ----------------------------------------------------------------
@@ -251,7 +270,7 @@ int isr_centroid(const float *pts, int64_t n, double *out3, void *stream) {
 }
 
 int isr_tile_spheres(const float *soa7, int64_t n, int64_t npad, int64_t bstride, int64_t batch,
-                     float *out_stage, float *out_sub, void *stream) {
+                     float *out_stage, float *out_sub, uint32_t *out_box, void *stream) {
     using namespace isr;
     ISR_REQUIRE(soa7 && out_stage && out_sub && n >= 0 && npad >= n && npad % ISR_SOA_TILE == 0 &&
                     npad > 0 && batch >= 1,
@@ -262,7 +281,8 @@ int isr_tile_spheres(const float *soa7, int64_t n, int64_t npad, int64_t bstride
     dim3 grid((unsigned)(npad / ISR_SOA_TILE), (unsigned)batch);
     ProfScope prof(kProfTransform, (cudaStream_t)stream);
     tile_spheres_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        soa7, n, npad, bstride, reinterpret_cast<float4 *>(out_stage), reinterpret_cast<float4 *>(out_sub));
+        soa7, n, npad, bstride, reinterpret_cast<float4 *>(out_stage), reinterpret_cast<float4 *>(out_sub),
+        out_box);
     return launched("tile_spheres_kernel");
 }
 

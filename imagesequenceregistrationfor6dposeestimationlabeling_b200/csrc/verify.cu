@@ -79,7 +79,7 @@ static int verify_chunk(int64_t nq, int64_t nt, int64_t b) {
 }
 
 struct VerifyLayout {
-    size_t xs, ys, d2a, d2b, means, centroid, perm_q, perm_t, stage_x, stage_y, sub_x, sub_y, sortws, nnws, total;
+    size_t xs, ys, d2a, d2b, means, centroid, perm_q, perm_t, stage_x, stage_y, sub_x, sub_y, box_x, box_y, sortws, nnws, total;
     int chunk;
 };
 
@@ -112,6 +112,8 @@ static VerifyLayout verify_layout(int64_t nq, int64_t nt, int64_t b, int bidirec
     L.stage_y = off; off += align256((size_t)L.chunk * (ntp / ISR_SOA_TILE) * 16);
     L.sub_x = off; off += align256((size_t)L.chunk * (nqp / ISR_SUB_TILE) * 16);
     L.sub_y = off; off += align256((size_t)L.chunk * (ntp / ISR_SUB_TILE) * 16);
+    L.box_x = off; off += align256((size_t)L.chunk * (nqp / ISR_SUB_TILE) * 4);
+    L.box_y = off; off += align256((size_t)L.chunk * (ntp / ISR_SUB_TILE) * 4);
     L.sortws = off; off += isr_spatial_order_workspace_bytes(big);
     const size_t w1 = isr_nn_workspace_bytes(big, big, L.chunk);
     const size_t w2 = isr_nn2_workspace_bytes(big, big, L.chunk);
@@ -163,6 +165,8 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
     float *stage_y = reinterpret_cast<float *>(ws + L.stage_y);
     float *sub_x = reinterpret_cast<float *>(ws + L.sub_x);
     float *sub_y = reinterpret_cast<float *>(ws + L.sub_y);
+    uint32_t *box_x = reinterpret_cast<uint32_t *>(ws + L.box_x);
+    uint32_t *box_y = reinterpret_cast<uint32_t *>(ws + L.box_y);
     if (!direct) {
         ISR_TRY(isr_centroid(cloud_t, nt, centroid, stream));
         // Morton order once per cloud; every candidate's rigid copy inherits the coherence.
@@ -171,8 +175,8 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
         if (cloud_q == cloud_t && nq == nt) perm_q = perm_t;
         else ISR_TRY(isr_spatial_order(cloud_q, nq, perm_q, ws + L.sortws, L.nnws - L.sortws, stream));
     }
-    const IsrCloud cx{xs, nq, nqp, 7 * nqp, stage_x, nullptr, sub_x, nullptr};
-    const IsrCloud cy{ys, nt, ntp, 7 * ntp, stage_y, nullptr, sub_y, nullptr};
+    const IsrCloud cx{xs, nq, nqp, 7 * nqp, stage_x, nullptr, sub_x, nullptr, box_x};
+    const IsrCloud cy{ys, nt, ntp, 7 * ntp, stage_y, nullptr, sub_y, nullptr, box_y};
     for (int64_t k0 = 0; k0 < b; k0 += L.chunk) {
         const int c = (int)((b - k0) < L.chunk ? (b - k0) : L.chunk);
         if (direct) {
@@ -188,8 +192,8 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
                                       poses_t + k0 * 16, 16, centroid, c, xs, nqp, nullptr, 0, stream));
             ISR_TRY(isr_prepare_cloud(cloud_t, nullptr, perm_t, nt, poses_t + k0 * 16, 16,
                                       poses_t + k0 * 16, 16, centroid, c, ys, ntp, nullptr, 0, stream));
-            ISR_TRY(isr_tile_spheres(xs, nq, nqp, 7 * nqp, c, stage_x, sub_x, stream));
-            ISR_TRY(isr_tile_spheres(ys, nt, ntp, 7 * ntp, c, stage_y, sub_y, stream));
+            ISR_TRY(isr_tile_spheres(xs, nq, nqp, 7 * nqp, c, stage_x, sub_x, box_x, stream));
+            ISR_TRY(isr_tile_spheres(ys, nt, ntp, 7 * ntp, c, stage_y, sub_y, box_y, stream));
             ISR_TRY(isr_nn2(&cx, &cy, c, 0, d2a, nullptr, nullptr, 0, nnws, nnws_bytes, stream));
         }
         ISR_TRY(isr_mean_sqrt(d2a, nq, c, means, stream));

@@ -129,9 +129,14 @@ int isr_prepare_cloud(const float *pts, const float *pts_lo, const int32_t *perm
  * 64-point sub-tiles.  r bounds |p - c| for every real point of the tile, inflated to hold
  * for the FP64 (hi + lo) coordinates; r = -1 marks a tile of padding only.  The search uses
  * them to scan the nearest stage first and to skip tiles that provably cannot hold a
- * query's nearest neighbour (what the KD-tree of Open3D / sklearn does by construction). */
+ * query's nearest neighbour (what the KD-tree of Open3D / sklearn does by construction).
+ * out_box (uint32 [batch][npad/64], may be NULL) receives each sub-tile's axis-aligned bounding
+ * box about the same centre: three 10-bit fields k_x | k_y << 10 | k_z << 20, half-extent
+ * h = r * k / 1023 (rounded up, inflated like r); 0x3FFFFFFF for a tile of padding only.  The
+ * patches of a surface cloud are thin sheets: the box follows them where the sphere is mostly
+ * empty, and a tile is skipped when either volume is out of reach. */
 int isr_tile_spheres(const float *soa7, int64_t n, int64_t npad, int64_t bstride, int64_t batch,
-                     float *out_stage, float *out_sub, void *stream);
+                     float *out_stage, float *out_sub, uint32_t *out_box, void *stream);
 
 /* A prepared cloud (or batch of clouds) as the search kernel sees it. */
 typedef struct IsrCloud {
@@ -151,6 +156,8 @@ typedef struct IsrCloud {
                              work -- and is overwritten with the neighbour found, so that the
                              next search of the same clouds (the next ICP iteration) starts
                              from it                                                          */
+    const uint32_t *sub_box; /* isr_tile_spheres out_box, or NULL (sphere tests only); only read
+                             when this cloud is the target                                    */
 } IsrCloud;
 
 /* Process-wide switch for the tile pruning of isr_nn2 (default on).  Off = exhaustive brute

@@ -193,6 +193,18 @@ def test_tile_spheres_bound_their_points(gpu):
                     d = np.linalg.norm(pts[b, lo:hi] - spheres[b, k, :3].astype(np.float64), axis=1)
                     assert d.max() <= spheres[b, k, 3]
                     assert spheres[b, k, 3] <= d.max() * 1.001 + 1e-4 * (1 + abs(offset))
+        # the sub-tile boxes: centre = the sphere's, half-extents r * k / 1023 per axis
+        sub, box = c.sub_c.cpu().numpy().astype(np.float64), c.sub_box.cpu().numpy().astype(np.int64)
+        for b in range(3):
+            for k in range(c.npad // 64):
+                lo, hi = k * 64, min((k + 1) * 64, n)
+                if hi <= lo:
+                    assert box[b, k] == 0x3FFFFFFF
+                    continue
+                h = sub[b, k, 3] * np.array([box[b, k] & 1023, (box[b, k] >> 10) & 1023, (box[b, k] >> 20) & 1023]) / 1023.0
+                ext = np.abs(pts[b, lo:hi] - sub[b, k, :3]).max(axis=0)
+                assert (ext <= h).all()
+                assert (h <= ext * 1.001 + sub[b, k, 3] * 2e-3 + 1e-4 * (1 + abs(offset))).all()
 
 
 @pytest.mark.parametrize("case", ["aligned", "rotated", "far_apart", "clusters", "lattice_ties",
