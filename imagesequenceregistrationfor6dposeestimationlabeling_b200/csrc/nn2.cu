@@ -131,7 +131,71 @@ __device__ __forceinline__ float filter_threshold(float mt, float nq2, float qn)
 // scan state (q2*, thr) lives in registers; the resolve state (mt_l .. dq_l) is indexed at
 // run time, which places it in (L1-resident) local memory and keeps it out of the scan's
 // registers.
-template <int Q, int SUB, int UNR, bool PRUNE>
+// The filter scan of SUB targets for query rows R0 .. R0 + QN - 1 of the lane.  The sub-tile is
+// walked in PARTS equal pieces; after each piece the rows whose minimum over the piece comes
+// within their threshold get bit (piece * 8 + row) of `flags` (the resolve then re-derives only
+// those pieces); tm[R0 ..] receives the minimum over the whole sub-tile.  Level-major over the
+// rows: consecutive FFMA2 are independent and share the target-pair operand (operand-reuse
+// cache); the query rides as a scalar.
+template <int Q, int R0, int QN, int SUB, int UNR, int PARTS>
+__device__ __forceinline__ void scan_rows(const float4 *sx, const float4 *sy, const float4 *sz,
+                                          const float4 *sn, const float (&q2x)[Q], const float (&q2y)[Q],
+                                          const float (&q2z)[Q], const float (&thr)[Q], float (&tm)[Q],
+                                          unsigned &flags) {
+    constexpr int G = SUB / 4 / PARTS;  // groups of 4 targets per piece
+    static_assert(G * PARTS * 4 == SUB && PARTS <= 4, "pieces");
+#pragma unroll 1
+    for (int part = 0; part < PARTS; ++part) {
+        float tp[QN];
+#pragma unroll
+        for (int r = 0; r < QN; ++r) tp[r] = CUDART_INF_F;
+#pragma unroll UNR
+        for (int g = part * G; g < (part + 1) * G; ++g) {
+            const float4 X = sx[g];
+            const float4 Y = sy[g];
+            const float4 Z = sz[g];
+            const float4 N = sn[g];
+            const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+            const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+            const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+            const u64 n01 = pack2(N.x, N.y), n23 = pack2(N.z, N.w);
+            u64 acc[QN];
+#pragma unroll
+            for (int r = 0; r < QN; ++r) acc[r] = fma2(pack2(q2z[R0 + r], q2z[R0 + r]), z01, n01);
+#pragma unroll
+            for (int r = 0; r < QN; ++r) acc[r] = fma2(pack2(q2y[R0 + r], q2y[R0 + r]), y01, acc[r]);
+#pragma unroll
+            for (int r = 0; r < QN; ++r) acc[r] = fma2(pack2(q2x[R0 + r], q2x[R0 + r]), x01, acc[r]);
+#pragma unroll
+            for (int r = 0; r < QN; ++r) {
+                float a0, a1;
+                unpack2(acc[r], a0, a1);
+                tp[r] = min3(tp[r], a0, a1);
+            }
+#pragma unroll
+            for (int r = 0; r < QN; ++r) acc[r] = fma2(pack2(q2z[R0 + r], q2z[R0 + r]), z23, n23);
+#pragma unroll
+            for (int r = 0; r < QN; ++r) acc[r] = fma2(pack2(q2y[R0 + r], q2y[R0 + r]), y23, acc[r]);
+#pragma unroll
+            for (int r = 0; r < QN; ++r) acc[r] = fma2(pack2(q2x[R0 + r], q2x[R0 + r]), x23, acc[r]);
+#pragma unroll
+            for (int r = 0; r < QN; ++r) {
+                float a0, a1;
+                unpack2(acc[r], a0, a1);
+                tp[r] = min3(tp[r], a0, a1);
+            }
+        }
+        unsigned f = 0;
+#pragma unroll
+        for (int r = 0; r < QN; ++r) {
+            f |= (tp[r] <= thr[R0 + r]) ? (1u << (R0 + r)) : 0u;
+            tm[R0 + r] = PARTS == 1 ? tp[r] : fminf(tm[R0 + r], tp[r]);
+        }
+        flags |= f << (8 * part);
+    }
+}
+
+template <int Q, int SUB, int UNR, bool PRUNE, int PARTS = 1>
 __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__restrict__ gq,
                                              const float *__restrict__ gt, int q0, int lane,
                                              const float4 *sx, const float4 *sy, const float4 *sz,
@@ -140,51 +204,25 @@ __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__
                                              float (&thr)[Q], float *mt_l, float *thr_l,
                                              float *tm_l, double *Dbest_l, int *ibest_l,
                                              float *dq_l, float &dmax, unsigned &nflag,
-                                             unsigned &npass, const float *qsm = nullptr) {
+                                             unsigned &npass, const float *qsm = nullptr,
+                                             unsigned rows = ~0u) {
     float tm[Q];
 #pragma unroll
     for (int r = 0; r < Q; ++r) tm[r] = CUDART_INF_F;
-#pragma unroll UNR
-    for (int g = 0; g < SUB / 4; ++g) {
-        const float4 X = sx[g];
-        const float4 Y = sy[g];
-        const float4 Z = sz[g];
-        const float4 N = sn[g];
-        const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
-        const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
-        const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
-        const u64 n01 = pack2(N.x, N.y), n23 = pack2(N.z, N.w);
-        // level-major over the Q queries: consecutive FFMA2 are independent and share
-        // the target-pair operand (operand-reuse cache); the query rides as a scalar
-        u64 acc[Q];
-#pragma unroll
-        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2z[r], q2z[r]), z01, n01);
-#pragma unroll
-        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2y[r], q2y[r]), y01, acc[r]);
-#pragma unroll
-        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2x[r], q2x[r]), x01, acc[r]);
-#pragma unroll
-        for (int r = 0; r < Q; ++r) {
-            float a0, a1;
-            unpack2(acc[r], a0, a1);
-            tm[r] = min3(tm[r], a0, a1);
-        }
-#pragma unroll
-        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2z[r], q2z[r]), z23, n23);
-#pragma unroll
-        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2y[r], q2y[r]), y23, acc[r]);
-#pragma unroll
-        for (int r = 0; r < Q; ++r) acc[r] = fma2(pack2(q2x[r], q2x[r]), x23, acc[r]);
-#pragma unroll
-        for (int r = 0; r < Q; ++r) {
-            float a0, a1;
-            unpack2(acc[r], a0, a1);
-            tm[r] = min3(tm[r], a0, a1);
-        }
+    unsigned pflags = 0;  // bit (piece * 8 + row)
+    if (PRUNE && Q == 8) {
+        // the pruned search scans only the half of the warp's query rows (0-3, 4-7) that the
+        // exact test could not rule out: an unscanned row keeps tm = +inf and never flags
+        if (rows & 0x0Fu)
+            scan_rows<Q, 0, Q / 2, SUB, UNR, PARTS>(sx, sy, sz, sn, q2x, q2y, q2z, thr, tm, pflags);
+        if (rows & 0xF0u)
+            scan_rows<Q, Q / 2, Q - Q / 2, SUB, UNR, PARTS>(sx, sy, sz, sn, q2x, q2y, q2z, thr, tm, pflags);
+    } else {
+        static_assert(PRUNE || PARTS == 1, "the exhaustive kernel flags whole sub-tiles");
+        scan_rows<Q, 0, Q, SUB, UNR, PARTS>(sx, sy, sz, sn, q2x, q2y, q2z, thr, tm, pflags);
     }
-    unsigned flags = 0;
-#pragma unroll
-    for (int r = 0; r < Q; ++r) flags |= (tm[r] <= thr[r]) ? (1u << r) : 0u;
+    // bit r: row r has a flagged piece
+    const unsigned flags = (pflags | (pflags >> 8) | (pflags >> 16) | (pflags >> 24)) & 0xFFu;
     if (PRUNE && p.evaluated != nullptr) {  // profiling only
         const unsigned mx = __reduce_max_sync(0xffffffffu, (unsigned)__popc(flags));
         nflag += mx != 0 ? 1u : 0u;
@@ -233,16 +271,21 @@ __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__
             // different places; a branch here would run the FP64 code once per hit position.)
             static_assert(SUB <= 64, "window mask is 64 bits");
             u64 wmask = 0;
+            // (lanes walk their own flagged pieces side by side: same code, different offsets)
+            for (unsigned pf = (pflags >> r) & 0x01010101u; pf != 0; pf &= pf - 1) {
+                constexpr int G = SUB / 4 / PARTS;
+                const int g0 = ((__ffs(pf) - 1) >> 3) * G;
 #pragma unroll 4
-            for (int g = 0; g < SUB / 4; ++g) {
-                const float4 X = sx[g], Y = sy[g], Z = sz[g], N = sn[g];
-                const float a0 = __fmaf_rn(cx, X.x, __fmaf_rn(cy, Y.x, __fmaf_rn(cz, Z.x, N.x)));
-                const float a1 = __fmaf_rn(cx, X.y, __fmaf_rn(cy, Y.y, __fmaf_rn(cz, Z.y, N.y)));
-                const float a2 = __fmaf_rn(cx, X.z, __fmaf_rn(cy, Y.z, __fmaf_rn(cz, Z.z, N.z)));
-                const float a3 = __fmaf_rn(cx, X.w, __fmaf_rn(cy, Y.w, __fmaf_rn(cz, Z.w, N.w)));
-                const unsigned bits = (a0 <= th ? 1u : 0u) | (a1 <= th ? 2u : 0u) | (a2 <= th ? 4u : 0u) |
-                                      (a3 <= th ? 8u : 0u);
-                wmask |= (u64)bits << (4 * g);
+                for (int g = g0; g < g0 + G; ++g) {
+                    const float4 X = sx[g], Y = sy[g], Z = sz[g], N = sn[g];
+                    const float a0 = __fmaf_rn(cx, X.x, __fmaf_rn(cy, Y.x, __fmaf_rn(cz, Z.x, N.x)));
+                    const float a1 = __fmaf_rn(cx, X.y, __fmaf_rn(cy, Y.y, __fmaf_rn(cz, Z.y, N.y)));
+                    const float a2 = __fmaf_rn(cx, X.z, __fmaf_rn(cy, Y.z, __fmaf_rn(cz, Z.z, N.z)));
+                    const float a3 = __fmaf_rn(cx, X.w, __fmaf_rn(cy, Y.w, __fmaf_rn(cz, Z.w, N.w)));
+                    const unsigned bits = (a0 <= th ? 1u : 0u) | (a1 <= th ? 2u : 0u) | (a2 <= th ? 4u : 0u) |
+                                          (a3 <= th ? 8u : 0u);
+                    wmask |= (u64)bits << (4 * g);
+                }
             }
             // pass 2: exact FP64 distance of those few (ascending stored position)
             const float *fx = reinterpret_cast<const float *>(sx);
@@ -442,7 +485,7 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
         __syncthreads();  // every warp is done with this slot before it is refilled
     }
     if (p.evaluated != nullptr && lane == 0) {
-        atomicAdd(p.evaluated + 0, (unsigned long long)nst * (STAGE / SUB));
+        atomicAdd(p.evaluated + 0, 2ull * nst * (STAGE / SUB));  // in half units (128 queries x SUB targets)
         atomicAdd(p.evaluated + 1, (unsigned long long)nst);
         atomicAdd(p.evaluated + 4, 1ull);
     }
@@ -483,7 +526,7 @@ struct alignas(128) PrunedWarpSmem {
     float qs[6][32 * Q];       // the warp's queries, hi xyz and lo xyz (read by the resolve path)
 };
 
-template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG>
+template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS>
 __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2Params p) {
     static_assert(SUB == ISR_SUB_TILE && ISR_SOA_TILE / SUB == 16 && Q == 8, "pruning uses the spheres of prepare.cu");
     constexpr int SUBS = ISR_SOA_TILE / SUB;
@@ -683,11 +726,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     // half-extents = hb's three 10-bit fractions of the radius, rounded up): a query is ruled
     // out when EITHER volume is farther than its bound.  The patches are thin sheets of the
     // surface; the box follows them where the sphere is mostly empty.
-    auto exact_any_box = [&](const float4 S, unsigned rows, unsigned hb) {
+    auto exact_rows_box = [&](const float4 S, unsigned rows, unsigned hb) {
         const float sc = S.w * (1.00001f / 1023.f);
         const float hx = (float)(hb & 1023u) * sc, hy = (float)((hb >> 10) & 1023u) * sc,
                     hz = (float)((hb >> 20) & 1023u) * sc;
-        bool need = false;
+        unsigned need = 0;
 #pragma unroll
         for (int r = 0; r < Q; ++r) {
             if (rows & (1u << r)) {  // warp-uniform
@@ -699,10 +742,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                 const float rb = dq_l[r] * 1.0001f;
                 const bool out = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr ||
                                  fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > rb * rb;
-                need = need || !out;
+                if (__any_sync(0xffffffffu, !out)) need |= 1u << r;
             }
         }
-        return __any_sync(0xffffffffu, need);
+        return need;
     };
 
     // ---- seeds: for every query row, the sub-tile whose centre is nearest to the row's --------
@@ -789,7 +832,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     //   produce: next chunk of 32 stage spheres -> coarse row test, one per lane; then per
     //            candidate stage the exact test, and its 16 sub-tile spheres -> coarse row test
     //            -> FIFO.
-    unsigned nscanned = 0, ntests = 0, ncand = 0, nflag = 0, npass = 0;
+    unsigned nscanned = 0, nhalves = 0, ntests = 0, ncand = 0, nflag = 0, npass = 0;
     unsigned refreshed_at = ~0u;
     bool sorted = p.sort_fifo == 0;
     bool seeding = true;   // the seeds must be scanned before anything is produced
@@ -856,8 +899,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
             while (look < tail && nloads - nconsumed < kRing) {
                 const int e = look % kFifo;
                 ++ntests;
-                if (exact_any_box(ws.sph[e], ws.rows[e], ws.box[e])) {
+                const unsigned need = exact_rows_box(ws.sph[e], ws.rows[e], ws.box[e]);
+                if (need != 0) {
                     if (lane == 0) {
+                        ws.rows[e] = need;
                         const int slot = nloads % kRing;
                         const long long src = (long long)ws.id[e] * SUB;
                         mbar_expect_tx(&ws.full[slot], 4u * SUB * 4u);
@@ -877,17 +922,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
             if (id >= 0) {
                 const int slot = nconsumed % kRing;
                 mbar_wait(&ws.full[slot], (nconsumed / kRing) & 1);
+                const unsigned rows_e = ws.rows[head % kFifo];
                 ++nscanned;
+                nhalves += ((rows_e & 0x0Fu) ? 1u : 0u) + ((rows_e & 0xF0u) ? 1u : 0u);
                 // scanned in FLAG-sized pieces (FLAG == SUB in the shipped variant)
                 const float4 *sx = reinterpret_cast<const float4 *>(&ws.buf[slot][0][0]);
 #pragma unroll 1
                 for (int h = 0; h < SUB / FLAG; ++h)
-                    scan_subtile<Q, FLAG, UNR, true>(p, gq, gt, q0, lane, sx + h * (FLAG / 4),
+                    scan_subtile<Q, FLAG, UNR, true, PARTS>(p, gq, gt, q0, lane, sx + h * (FLAG / 4),
                                                      sx + SUB / 4 + h * (FLAG / 4),
                                                      sx + 2 * (SUB / 4) + h * (FLAG / 4),
                                                      sx + 3 * (SUB / 4) + h * (FLAG / 4), id * SUB + h * FLAG,
                                                      q2x, q2y, q2z, thr, mt_l, thr_l, tm_l, Dbest_l, ibest_l,
-                                                     dq_l, dmax, nflag, npass, &ws.qs[0][0]);
+                                                     dq_l, dmax, nflag, npass, &ws.qs[0][0], rows_e);
                 ++nconsumed;
                 __syncwarp();  // every lane is done with the slot before lane 0 refills it
             }
@@ -956,7 +1003,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     }
 
     if (p.evaluated != nullptr && lane == 0) {
-        atomicAdd(p.evaluated + 0, (unsigned long long)nscanned);
+        atomicAdd(p.evaluated + 0, (unsigned long long)nhalves);  // scanned half units (4 query rows x SUB targets)
         atomicAdd(p.evaluated + 1, (unsigned long long)stages);   // stage spheres tested
         atomicAdd(p.evaluated + 2, (unsigned long long)ncand);    // stages that passed
         atomicAdd(p.evaluated + 3, (unsigned long long)ntests);   // exact sub-tile tests
@@ -1138,7 +1185,7 @@ struct NN2Variant {
 using NN2Main = NN2Variant<8, 128, 1024, 3, 64, 4, 1>;
 
 // the pruned kernel: WARPS independent warps of 32 x Q queries per CTA
-template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG>
+template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS>
 struct NN2PrunedVariant {
     static constexpr int kQueriesPerCta = Q * WARPS * 32;
     static constexpr int kStage = ISR_SOA_TILE;
@@ -1146,7 +1193,7 @@ struct NN2PrunedVariant {
     static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q>);
 
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
-        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG>;
+        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS>;
         ProfScope prof(kProfNN, st);
         // the lo planes of the query copy (last 3 KB of the per-warp block) are only touched
         // when the search uses the lo parts
@@ -1162,7 +1209,15 @@ struct NN2PrunedVariant {
 // 2 % / 19 % slower than 64: more, shorter resolve passes)
 // (20 warps per SM -- a 102-register cap, 224 B of spills -- was measured 2 % slower on the
 // verification workload and 8 % slower on the ICP search)
-using NN2Pruned = NN2PrunedVariant<8, 1, 64, 16, 1, 64>;
+// (PARTS = 2 / 4 -- flagging halves / quarters of the sub-tile so that the resolve re-derives
+// only those -- removes 3/4 of the resolve's pass-1 instructions but was measured 2 % slower
+// on the verification workload and equal on the ICP search: the kernel is bound by the
+// latency of its serial phases at 4 warps per scheduler, not by instruction count)
+using NN2Pruned = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 1>;
+#ifdef ISR_NN_TUNING
+using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 2>;
+using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 4>;
+#endif
 static_assert(NN2Pruned::kSmem <= 48 * 1024, "pruned kernel uses the default dynamic shared memory limit");
 constexpr int kMaxSplits = 32;
 
@@ -1248,11 +1303,9 @@ static int nn2_dispatch(const NN2Call &c) {
     p.sub_c_bstride = c.t->bstride == 0 ? 0 : c.t->npad / ISR_SUB_TILE;
     p.sub_h = reinterpret_cast<const unsigned *>(c.t->sub_box);
     p.sub_h_bstride = p.sub_c_bstride;
-    {
-        static int use_box = -1;
-        if (use_box < 0) { const char *e = getenv("ISR_NN_BOX"); use_box = (e && atoi(e) == 0) ? 0 : 1; }
-        if (!use_box) p.sub_h = nullptr;
-    }
+#ifdef ISR_NN_TUNING
+    if (const char *e = getenv("ISR_NN_BOX")) { if (atoi(e) == 0) p.sub_h = nullptr; }
+#endif
     p.evaluated = nullptr;
     if (prof_enabled()) {
         p.evaluated = evaluated_counter();
@@ -1264,11 +1317,10 @@ static int nn2_dispatch(const NN2Call &c) {
 #ifdef ISR_NN_TUNING
     if (const char *e = getenv("ISR_NN_ANCHORS")) p.nanchors = atoi(e);
 #endif
-    {
-        static int sort_fifo = -1;
-        if (sort_fifo < 0) { const char *e = getenv("ISR_NN_SORT"); sort_fifo = (e && atoi(e) == 0) ? 0 : 1; }
-        p.sort_fifo = sort_fifo;
-    }
+    p.sort_fifo = 1;  // measured on the verification workload: +3 %
+#ifdef ISR_NN_TUNING
+    if (const char *e = getenv("ISR_NN_SORT")) p.sort_fifo = atoi(e);
+#endif
     p.order = nullptr;
     p.order_count = nullptr;
     int grid_x = nqb;
@@ -1426,6 +1478,12 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
 #endif
     if (t->sub_c != nullptr && t->stage_c != nullptr && pruning_on()) {
         ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
+#ifdef ISR_NN_TUNING
+        static int parts = -1;
+        if (parts < 0) { const char *e = getenv("ISR_NN_PARTS"); parts = e ? atoi(e) : 1; }
+        if (parts == 2) return nn2_dispatch<NN2PrunedP2>(c);
+        if (parts == 4) return nn2_dispatch<NN2PrunedP4>(c);
+#endif
         return nn2_dispatch<NN2Pruned>(c);
     }
     return nn2_dispatch<NN2Main>(c);
@@ -1456,8 +1514,8 @@ int isr_profile_nn_pairs(uint64_t *evaluated_host, uint64_t *answered_host) {
         ISR_TRY(check_cuda(cudaMemcpy(&units, ctr, 8, cudaMemcpyDeviceToHost), "profile_nn_pairs read"));
         ISR_TRY(check_cuda(cudaMemset(ctr, 0, 64), "profile_nn_pairs clear"));
     }
-    // one unit = one warp block of 32 x 8 queries against one 64-target sub-tile
-    if (evaluated_host) *evaluated_host = (uint64_t)units * 256ull * (uint64_t)ISR_SUB_TILE;
+    // counted in half units: 32 x 4 queries against one 64-target sub-tile
+    if (evaluated_host) *evaluated_host = (uint64_t)units * 128ull * (uint64_t)ISR_SUB_TILE;
     if (answered_host) *answered_host = (uint64_t)g_answered.exchange(0);
     return ISR_OK;
 }
