@@ -543,14 +543,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         if ((int)blockIdx.x >= p.order_count[b]) return;
         const int entry = p.order[(long long)b * gridDim.x + blockIdx.x];
         blk = entry & 0xFFFFFF;
-        rowsel = entry >> 24;  // 0: all rows; r + 1: only row r
+        rowsel = entry >> 24;  // 0: all rows; r + 1: only row r; 9 / 10: rows 0-3 / 4-7
     }
     const int q0 = blk * (WARPS * 32 * Q) + warp * (32 * Q) + lane;
     if (q0 - lane >= p.nq) return;  // this warp has no live query; warps never meet at a barrier
     unsigned livemask = 0;  // bit r: query r * 32 + lane exists and belongs to this CTA
 #pragma unroll
     for (int r = 0; r < Q; ++r)
-        if (q0 + r * 32 < p.nq && (rowsel == 0 || rowsel - 1 == r)) livemask |= 1u << r;
+        if (q0 + r * 32 < p.nq && (rowsel == 0 || rowsel - 1 == r || (rowsel > Q && rowsel - 1 - Q == r / (Q / 2))))
+            livemask |= 1u << r;
     if (__ballot_sync(0xffffffffu, livemask != 0) == 0) return;
     const long long t_start = clock64();
     PrunedWarpSmem<SUB, Q> &ws = reinterpret_cast<PrunedWarpSmem<SUB, Q> *>(smem_raw)[warp];
@@ -1084,7 +1085,7 @@ block_weight_kernel(const float *__restrict__ q, long long q_bstride, int nq, in
 // into Q single-row entries, everything else follows as whole blocks in descending weight.
 constexpr int kSplitMax = 128;  // (512 was measured slower: 25 % more total work, tail no longer the limit)
 __global__ void __launch_bounds__(1024)
-block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, int split_max,
+block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, int split_max, int halve,
                    int *__restrict__ order, int *__restrict__ order_count) {
     __shared__ u64 s[kOrderMax];
     __shared__ int nsplit;
@@ -1110,7 +1111,7 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
         int h = 0;
         while (h < split_max && h < nqb && __uint_as_float(~(unsigned)(s[h] >> 32)) > 4.0f * wmed) ++h;
         nsplit = h;
-        order_count[b] = nqb + (rows - 1) * h;
+        order_count[b] = (halve ? 2 : 1) * (nqb - h) + rows * h;
     }
     __syncthreads();
     const int h = nsplit;
@@ -1119,6 +1120,11 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
         const int blk = (int)(unsigned)(s[i] & 0xffffffffull);
         if (i < h) {
             for (int r = 0; r < rows; ++r) out[i * rows + r] = blk | ((r + 1) << 24);
+        } else if (halve) {
+            // a grid less than a few waves deep: every block runs as two CTAs of 4 query rows
+            // (the scan skips the dead half, so the split costs little and halves the tail)
+            out[h * rows + 2 * (i - h)] = blk | ((rows + 1) << 24);
+            out[h * rows + 2 * (i - h) + 1] = blk | ((rows + 2) << 24);
         } else {
             out[h * rows + (i - h)] = blk;
         }
@@ -1262,8 +1268,9 @@ static int choose_splits(long long ctas, int stages, int slots) {
 }
 
 static size_t order_workspace_bytes(long long nqb, long long batch) {
-    // keys, launch list (room for kSplitMax = 128 blocks split into 8 rows), entry counts
-    return align256((size_t)nqb * batch * 8) + align256((size_t)(nqb + 7 * 128) * batch * 4) +
+    // keys, launch list (room for every block as two halves and kSplitMax = 128 blocks split into
+    // 8 rows), entry counts
+    return align256((size_t)nqb * batch * 8) + align256((size_t)(2 * nqb + 7 * 128) * batch * 4) +
            align256((size_t)batch * 4);
 }
 
@@ -1330,7 +1337,15 @@ static int nn2_dispatch(const NN2Call &c) {
         // splitting only pays when the grid is a few waves deep (a single cloud pair, a few
         // ICP starts); a big batch hides its wide blocks behind the others
         const int split_max = (long long)nqb * c.batch <= 16384 ? kSplitMax : 0;
-        const int stride = nqb + (kRows - 1) * split_max;
+        // a grid that fills less than half of the machine runs every block as two CTAs of 4
+        // query rows (measured, ICP search: 100k points 0.203 -> 0.163 ms, 250k 0.248 -> 0.206 ms;
+        // from one full wave on -- 500k, 1M points -- the repeated per-CTA tests cost more than
+        // the shorter tail gains: 0.350 -> 0.381 ms, 0.63 -> 0.81 ms)
+        int halve = 2ll * nqb * c.batch <= slots ? 1 : 0;
+#ifdef ISR_NN_TUNING
+        if (const char *e = getenv("ISR_NN_HALVE")) halve = (long long)nqb * c.batch <= (long long)atoi(e) * slots ? 1 : 0;
+#endif
+        const int stride = halve ? 2 * nqb + (kRows - 2) * split_max : nqb + (kRows - 1) * split_max;
         char *w = reinterpret_cast<char *>(c.workspace);
         u64 *keys = reinterpret_cast<u64 *>(w);
         int *order = reinterpret_cast<int *>(w + align256((size_t)nqb * c.batch * 8));
@@ -1340,7 +1355,7 @@ static int nn2_dispatch(const NN2Call &c) {
         block_weight_kernel<V::kQueriesPerCta><<<(unsigned)((warps + 3) / 4), 128, 0, c.st>>>(
             p.q, p.q_bstride, p.nq, p.nq_pad, nqb, (int)c.batch, keys);
         ISR_TRY(launched("block_weight_kernel"));
-        block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, kRows, stride, split_max, order,
+        block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, kRows, stride, split_max, halve, order,
                                                                  count);
         ISR_TRY(launched("block_order_kernel"));
         p.order = order;
@@ -1391,24 +1406,6 @@ static int nn2_dispatch(const NN2Call &c) {
     return launched("nn2_combine_kernel");
 }
 
-#ifdef ISR_NN_TUNING
-using NN2T13 = NN2Variant<8, 128, 1024, 3, 64, 4, 1>;
-using NN2T14 = NN2Variant<8, 128, 1024, 3, 64, 4, 4>;
-using NN2T15 = NN2Variant<8, 128, 1024, 3, 128, 4, 1>;
-using NN2T16 = NN2Variant<8, 128, 1024, 4, 64, 4, 1>;
-using NN2T1 = NN2Variant<8, 128, 1024, 3, 16, 4>;
-using NN2T2 = NN2Variant<8, 128, 1024, 3, 64, 4>;
-using NN2T3 = NN2Variant<8, 128, 1024, 3, 32, 4, 4>;
-using NN2T4 = NN2Variant<8, 128, 1024, 3, 32, 4, 1>;
-using NN2T5 = NN2Variant<4, 128, 1024, 3, 32, 6>;
-using NN2T6 = NN2Variant<8, 256, 1024, 3, 32, 2>;
-using NN2T7 = NN2Variant<12, 128, 1024, 3, 32, 3>;
-using NN2T8 = NN2Variant<16, 64, 1024, 3, 32, 4>;
-using NN2T9 = NN2Variant<8, 128, 512, 4, 32, 4>;
-using NN2T10 = NN2Variant<8, 128, 1024, 3, 32, 3, 4>;
-using NN2T11 = NN2Variant<6, 128, 1024, 3, 32, 5>;
-using NN2T12 = NN2Variant<8, 128, 1024, 3, 128, 4>;
-#endif
 
 }  // namespace isr
 
@@ -1450,32 +1447,6 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
                 "nn: stage centroids must be 16-byte aligned");
     const NN2Call c{q, t, batch, use_lo, out_d2, out_idx, skip, skip_stride, workspace,
                     workspace_bytes, (cudaStream_t)stream};
-#ifdef ISR_NN_TUNING
-    static int variant = -1;
-    if (variant < 0) {
-        const char *e = getenv("ISR_NN_VARIANT");
-        variant = e ? atoi(e) : 0;
-    }
-    switch (variant) {
-        case 1: return nn2_dispatch<NN2T1>(c);
-        case 2: return nn2_dispatch<NN2T2>(c);
-        case 3: return nn2_dispatch<NN2T3>(c);
-        case 4: return nn2_dispatch<NN2T4>(c);
-        case 5: return nn2_dispatch<NN2T5>(c);
-        case 6: return nn2_dispatch<NN2T6>(c);
-        case 7: return nn2_dispatch<NN2T7>(c);
-        case 8: return nn2_dispatch<NN2T8>(c);
-        case 9: return nn2_dispatch<NN2T9>(c);
-        case 10: return nn2_dispatch<NN2T10>(c);
-        case 11: return nn2_dispatch<NN2T11>(c);
-        case 12: return nn2_dispatch<NN2T12>(c);
-        case 13: return nn2_dispatch<NN2T13>(c);
-        case 14: return nn2_dispatch<NN2T14>(c);
-        case 15: return nn2_dispatch<NN2T15>(c);
-        case 16: return nn2_dispatch<NN2T16>(c);
-        default: break;
-    }
-#endif
     if (t->sub_c != nullptr && t->stage_c != nullptr && pruning_on()) {
         ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
 #ifdef ISR_NN_TUNING
