@@ -1223,6 +1223,8 @@ using NN2Pruned = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 1>;
 #ifdef ISR_NN_TUNING
 using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 2>;
 using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 4>;
+using NN2PrunedU2 = NN2PrunedVariant<8, 1, 64, 16, 2, 64, 1>;
+using NN2PrunedU4 = NN2PrunedVariant<8, 1, 64, 16, 4, 64, 1>;
 #endif
 static_assert(NN2Pruned::kSmem <= 48 * 1024, "pruned kernel uses the default dynamic shared memory limit");
 constexpr int kMaxSplits = 32;
@@ -1454,6 +1456,8 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
         if (parts < 0) { const char *e = getenv("ISR_NN_PARTS"); parts = e ? atoi(e) : 1; }
         if (parts == 2) return nn2_dispatch<NN2PrunedP2>(c);
         if (parts == 4) return nn2_dispatch<NN2PrunedP4>(c);
+        if (parts == 12) return nn2_dispatch<NN2PrunedU2>(c);
+        if (parts == 14) return nn2_dispatch<NN2PrunedU4>(c);
 #endif
         return nn2_dispatch<NN2Pruned>(c);
     }
