@@ -65,6 +65,7 @@ def parse_args():
     ap.add_argument("--icp-points", type=int, default=1_000_000)
     ap.add_argument("--icp-iters", type=int, default=10)
     ap.add_argument("--skip-icp", action="store_true")
+    ap.add_argument("--skip-extra", action="store_true", help="skip the config-5 / ADD-S timings")
     ap.add_argument("--skip-cpu", action="store_true")
     return ap.parse_args()
 
@@ -399,16 +400,25 @@ def main():
         finally:
             api.set_nn_pruning(True)
         r = prob.results(with_correspondences=False)[0]
-        # the same source-sharded loop as ONE C call with the exchange of the 17 sums fused into
-        # the accumulate / solve kernels (peer-memory stores + flag wait; no NCCL call, no host
-        # work per iteration) -- the default of dist.icp_sharded under N > 1
+        # The product's loop (api.icp / dist.icp_sharded): ONE C call for all iterations.  At
+        # N = 1 isr_icp_run; at N > 1 isr_icp_run_sharded, the same source-sharded loop with the
+        # exchange of the 17 sums fused into the accumulate / solve kernels (peer-memory stores +
+        # flag wait; no NCCL call, no host work per iteration).  After the first evaluation a
+        # run keeps the launch order of the search and skips the per-iteration set-up launches.
         pprob = api.IcpProblem(src[slo:shi], tgt, np.eye(4)[None])
-        peer = dist.peer_exchange()
-        pprob.run_sharded(peer, len(src), 20.0, 0, 0.0, 0.0)       # warm-up: one evaluation
+        peer = dist.peer_exchange() if world > 1 else None
+
+        def icp_run(iters):
+            if world > 1:
+                pprob.run_sharded(peer, len(src), 20.0, iters - 1, 0.0, 0.0)
+            else:
+                pprob.run(20.0, iters - 1, 0.0, 0.0)
+
+        icp_run(1)       # warm-up: one evaluation
         pprob.reopen()
         barrier()
         e0.record()
-        pprob.run_sharded(peer, len(src), 20.0, args.icp_iters - 1, 0.0, 0.0)
+        icp_run(args.icp_iters)
         e1.record()
         barrier()
         t_icp_peer = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
@@ -479,17 +489,19 @@ def main():
         t_k1p = kernel_seconds(lambda: api.prepare_cloud(cloud_d, Pb, centroid=cen, centre_poses=Pb), 0)
         k1p_bytes = args.points * 12 + nb * 7 * _lib.soa_padded_len(args.points) * 4
         secondary = {
-            "icp_iters_per_s": args.icp_iters / t_icp,
+            "icp_iters_per_s": args.icp_iters / t_icp_peer,
             "icp_config": f"dense ICP refine (BASELINE configs[3]): {args.icp_points} x {args.icp_points} "
-                          f"points, {args.icp_iters} forced iterations, source sharded x{world}, one accumulate + "
-                          f"{'NCCL all-reduce + ' if world > 1 else ''}solve enqueued per iteration",
+                          f"points, {args.icp_iters} forced iterations, source sharded x{world}, one C call "
+                          + ("(isr_icp_run_sharded: sums exchanged inside the accumulate/solve kernels through "
+                             "peer memory over NVLink, no NCCL call)" if world > 1 else "(isr_icp_run)"),
+            "icp_stepwise_iters_per_s": args.icp_iters / t_icp,
+            "icp_stepwise_config": "the same loop driven from Python, one accumulate + "
+                                   f"{'NCCL all-reduce + ' if world > 1 else ''}solve call per iteration "
+                                   "(the kernel timings below come from this leg)",
             "icp_nn_pairs_evaluated_frac": icp_eval / max(icp_answered, 1.0),
             "icp_nn_tflops_evaluated": FLOP_PER_PAIR * icp_eval / (ms_kind[1] * 1e-3) / 1e12,
             "icp_nn_tflops_brute_force_equivalent": FLOP_PER_PAIR * icp_answered / (ms_kind[1] * 1e-3) / 1e12,
             "icp_nn_ms_per_iter": ms_kind[1] / max(n_kind[1], 1),
-            "icp_peer_exchange_iters_per_s": args.icp_iters / t_icp_peer,
-            "icp_peer_exchange_config": "same loop as one isr_icp_run_sharded call: sums exchanged inside the "
-                                        "accumulate/solve kernels through peer memory (NVLink), no NCCL call",
             "icp_target_sharded_iters_per_s": (args.icp_iters / t_icp_tgt) if t_icp_tgt else None,
             "icp_exhaustive_iters_per_s": 1.0 / t_icp_ex,
             "icp_exhaustive_nn_tflops": FLOP_PER_PAIR * ns_local * args.icp_points / t_icp_ex / 1e12,
@@ -505,6 +517,42 @@ def main():
             "hbm_peak_gbs": hbm,
         }
         del prob
+        if world == 1 and not args.skip_extra:
+            # BASELINE configs[4]: 64 symmetry-seeded starts x 250k points, 30-iteration ICP each
+            # (default criteria), Chamfer-ranked -- end to end through api.multistart_icp from host arrays
+            s5, t5, _ = synth.icp_pair(250000, 250000, 6, 7)
+            inits5 = np.stack([synth.pose_matrix(synth.rotvec_to_matrix([0, 0, 2 * np.pi * k / 64]), [0, 0, 0])
+                               for k in range(64)])
+            api.multistart_icp(s5, t5, inits5[:2], 20.0, max_iteration=2)   # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ms5 = api.multistart_icp(s5, t5, inits5, 20.0, max_iteration=30)
+            torch.cuda.synchronize()
+            dt5 = time.perf_counter() - t0
+            it5 = int(sum(r_.iterations + 1 for r_ in ms5.results))
+            secondary.update({
+                "config5_multistart_seconds": dt5,
+                "config5_multistart_evaluations_per_s": it5 / dt5,
+                "config5_config": "64 starts x 250000 x 250000 points, <= 30 iterations each (default criteria), then "
+                                  f"Chamfer ranking; {it5} ICP evaluations in total; wall clock incl. host prep and H2D",
+                "config5_best_start": int(ms5.order[0]),
+            })
+            # ADD-S scoring as choosePose.py:20-22,124-134 calls it: 20k CAD vertices against the
+            # 100k-point surface cloud, one pose pair per call, batched
+            verts = synth.make_cloud(20000, seed=3)
+            R_t, t_t = synth.true_pose(3)
+            Rs_a, ts_a, _ = synth.make_candidates(1000, seed=10, R_true=R_t, t_true=t_t)
+            gR, gT = np.tile(R_t, (1000, 1, 1)), np.tile(t_t, (1000, 1))
+            api.adds(verts, gR[:64], gT[:64], Rs_a[:64], ts_a[:64], cloud)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            api.adds(verts, gR, gT, Rs_a, ts_a, cloud).cpu()
+            dta = time.perf_counter() - t0
+            secondary.update({
+                "adds_pose_pairs_per_s": 1000 / dta,
+                "adds_config": "ADD-S (one-directional): 1000 pose pairs x 20000 vertices vs 100000 surface points, "
+                               "host arrays in, host losses out",
+            })
 
     # ---------------- CPU baseline (rank 0, N == 1 only) ---------------------------------
     cpu = None

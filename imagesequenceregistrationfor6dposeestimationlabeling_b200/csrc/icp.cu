@@ -423,6 +423,10 @@ static int acc_blocks(int64_t ns) {
     return (int)want;
 }
 
+int icp_search_impl(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                    const int32_t *src_perm, int64_t ns, const IsrCloud *tgt_cloud, const double *centroid,
+                    int32_t *corr_idx, void *workspace, size_t workspace_bytes, void *stream, int repeat);
+
 struct IcpLayout {
     size_t xs, d2, partials, tickets, hint, nnws, total;
     int nblk;
@@ -475,7 +479,8 @@ static PeerView peer_view(const IsrPeer *p, bool next_message) {
 static int accumulate_corr_px(const IsrIcpState *states, int64_t starts, const float *src,
                               const float *src_lo, int64_t ns, const float *tgt, int64_t nt,
                               const int32_t *corr_idx, double max_dist, double *sums, uint8_t *inlier,
-                              void *workspace, size_t workspace_bytes, const PeerView &px, void *stream) {
+                              void *workspace, size_t workspace_bytes, const PeerView &px, void *stream,
+                              int repeat = 0) {
     ISR_REQUIRE(starts >= 1 && starts <= 65535 && ns >= 1 && nt >= 1, ISR_E_SHAPE,
                 "icp_accumulate_corr: bad size");
     ISR_REQUIRE(states && src && tgt && corr_idx && sums, ISR_E_INVALID_ARG,
@@ -489,7 +494,8 @@ static int accumulate_corr_px(const IsrIcpState *states, int64_t starts, const f
     char *ws = reinterpret_cast<char *>(workspace);
     double *partials = reinterpret_cast<double *>(ws + L.partials);
     unsigned *tickets = reinterpret_cast<unsigned *>(ws + L.tickets);
-    ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
+    // (the kernel's last CTA leaves the tickets at zero for the next launch)
+    if (!repeat) ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
     const int nblk = acc_blocks(ns);
     dim3 grid((unsigned)nblk, (unsigned)starts);
     ProfScope prof(kProfIcpAcc, st);
@@ -575,7 +581,20 @@ size_t isr_icp_workspace_bytes(int64_t ns, int64_t nt, int64_t starts) {
 int isr_icp_search(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
                    const int32_t *src_perm, int64_t ns, const IsrCloud *tgt_cloud, const double *centroid,
                    int32_t *corr_idx, void *workspace, size_t workspace_bytes, void *stream) {
-    using namespace isr;
+    return isr::icp_search_impl(states, starts, src, src_lo, src_perm, ns, tgt_cloud, centroid, corr_idx,
+                                workspace, workspace_bytes, stream, 0);
+}
+
+}  // extern "C"
+
+namespace isr {
+
+// `repeat` != 0: this is not the first evaluation of a loop that this library drives
+// (isr_icp_run*): the hints hold the previous correspondences (no reset needed) and the
+// launch order of the search is still in the workspace.
+int icp_search_impl(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                    const int32_t *src_perm, int64_t ns, const IsrCloud *tgt_cloud, const double *centroid,
+                    int32_t *corr_idx, void *workspace, size_t workspace_bytes, void *stream, int repeat) {
     ISR_REQUIRE(tgt_cloud != nullptr, ISR_E_INVALID_ARG, "icp: null target descriptor");
     const int64_t nt = tgt_cloud->n;
     ISR_REQUIRE(starts >= 1 && ns >= 1 && nt >= 1, ISR_E_SHAPE,
@@ -602,15 +621,19 @@ int isr_icp_search(IsrIcpState *states, int64_t starts, const float *src, const 
     // every source point starts the search from its previous correspondence: between two ICP
     // iterations the pose moves little, so that neighbour is already a near-final bound
     int32_t *hint = reinterpret_cast<int32_t *>(ws + L.hint);
-    {
+    if (!repeat) {
         const long long total = (long long)starts * nsp;
         icp_hint_reset_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(states, nsp, total, hint);
         ISR_TRY(launched("icp_hint_reset_kernel"));
     }
     const IsrCloud src_cloud{xs, ns, nsp, 7 * nsp, nullptr, src_perm, nullptr, hint, nullptr};
-    return isr_nn2(&src_cloud, tgt_cloud, starts, 1, d2, corr_idx, done, kStateInts, ws + L.nnws,
-                   L.total - L.nnws, stream);
+    return nn2_search(&src_cloud, tgt_cloud, starts, 1, d2, corr_idx, done, kStateInts, ws + L.nnws,
+                      L.total - L.nnws, stream, repeat);
 }
+
+}  // namespace isr
+
+extern "C" {
 
 int isr_icp_corr_dist(const IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
                       int64_t ns, const float *tgt, const int32_t *corr_idx, double *out_D,
@@ -666,10 +689,18 @@ int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const flo
                 size_t workspace_bytes, void *stream) {
     using namespace isr;
     ISR_REQUIRE(max_iteration >= 0, ISR_E_INVALID_ARG, "icp_run: max_iteration < 0");
+    ISR_REQUIRE(tgt_cloud != nullptr && tgt != nullptr && sums != nullptr, ISR_E_INVALID_ARG,
+                "icp_run: null pointer");
     for (int k = 0; k <= max_iteration; ++k) {
-        ISR_TRY(isr_icp_accumulate(states, starts, src, src_lo, src_perm, ns, tgt, tgt_cloud, centroid,
-                                   max_dist, sums, corr_idx, inlier, workspace, workspace_bytes,
-                                   stream));
+        if (max_dist > 0.0) {
+            ISR_TRY(icp_search_impl(states, starts, src, src_lo, src_perm, ns, tgt_cloud, centroid, corr_idx,
+                                    workspace, workspace_bytes, stream, k > 0));
+            ISR_TRY(accumulate_corr_px(states, starts, src, src_lo, ns, tgt, tgt_cloud->n, corr_idx, max_dist,
+                                       sums, inlier, workspace, workspace_bytes, PeerView{}, stream, k > 0));
+        } else {
+            ISR_TRY(isr_icp_accumulate_corr(states, starts, src, src_lo, ns, tgt, tgt_cloud->n, corr_idx,
+                                            max_dist, sums, inlier, workspace, workspace_bytes, stream));
+        }
         ISR_TRY(isr_icp_solve(states, starts, sums, ns, rel_fitness, rel_rmse,
                               k == max_iteration ? 1 : 0, stream));
     }
@@ -694,12 +725,12 @@ int isr_icp_run_sharded(IsrIcpState *states, int64_t starts, const float *src, c
                 (long long)ns, (long long)ns_total);
     for (int k = 0; k <= max_iteration; ++k) {
         if (max_dist > 0.0) {
-            ISR_TRY(isr_icp_search(states, starts, src, src_lo, src_perm, ns, tgt_cloud, centroid, corr_idx,
-                                   workspace, workspace_bytes, stream));
+            ISR_TRY(icp_search_impl(states, starts, src, src_lo, src_perm, ns, tgt_cloud, centroid, corr_idx,
+                                    workspace, workspace_bytes, stream, k > 0));
             // the message number advances only once both kernels of the pair are enqueued
             const PeerView px = peer_view(peer, true);
             ISR_TRY(accumulate_corr_px(states, starts, src, src_lo, ns, tgt, tgt_cloud->n, corr_idx, max_dist,
-                                       sums, inlier, workspace, workspace_bytes, px, stream));
+                                       sums, inlier, workspace, workspace_bytes, px, stream, k > 0));
             const int s = solve_px(states, starts, sums, ns_total, rel_fitness, rel_rmse,
                                    k == max_iteration ? 1 : 0, px, stream);
             peer->seq += 1;  // the accumulate kernel has been launched: its message exists

@@ -60,6 +60,14 @@ struct ProfScope {
         }                             \
     } while (0)
 
+// isr_nn2 with one more knob for callers that repeat the same search on slowly moving clouds
+// (the ICP loop): reuse_order != 0 keeps the launch order of the pruned kernel's query blocks
+// that the previous call left in `workspace` (block weights are invariant under the rigid
+// motion between two iterations) instead of recomputing it.
+int nn2_search(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, float *out_d2,
+               int32_t *out_idx, const int32_t *skip, int64_t skip_stride, void *workspace,
+               size_t workspace_bytes, void *stream, int reuse_order);
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -1285,6 +1285,7 @@ struct NN2Call {
     const int32_t *skip; int64_t skip_stride;
     void *workspace; size_t workspace_bytes;
     cudaStream_t st;
+    int reuse_order;
 };
 
 template <class V>
@@ -1354,12 +1355,14 @@ static int nn2_dispatch(const NN2Call &c) {
         int *count = reinterpret_cast<int *>(w + align256((size_t)nqb * c.batch * 8) +
                                              align256((size_t)stride * c.batch * 4));
         const long long warps = (long long)nqb * c.batch;
-        block_weight_kernel<V::kQueriesPerCta><<<(unsigned)((warps + 3) / 4), 128, 0, c.st>>>(
-            p.q, p.q_bstride, p.nq, p.nq_pad, nqb, (int)c.batch, keys);
-        ISR_TRY(launched("block_weight_kernel"));
-        block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, kRows, stride, split_max, halve, order,
-                                                                 count);
-        ISR_TRY(launched("block_order_kernel"));
+        if (!c.reuse_order) {
+            block_weight_kernel<V::kQueriesPerCta><<<(unsigned)((warps + 3) / 4), 128, 0, c.st>>>(
+                p.q, p.q_bstride, p.nq, p.nq_pad, nqb, (int)c.batch, keys);
+            ISR_TRY(launched("block_weight_kernel"));
+            block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, kRows, stride, split_max, halve,
+                                                                     order, count);
+            ISR_TRY(launched("block_order_kernel"));
+        }
         p.order = order;
         p.order_count = count;
         grid_x = stride;
@@ -1430,7 +1433,17 @@ size_t isr_nn2_workspace_bytes(int64_t nq, int64_t nt, int64_t batch) {
 int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, float *out_d2,
             int32_t *out_idx, const int32_t *skip, int64_t skip_stride, void *workspace,
             size_t workspace_bytes, void *stream) {
-    using namespace isr;
+    return isr::nn2_search(q, t, batch, use_lo, out_d2, out_idx, skip, skip_stride, workspace, workspace_bytes,
+                           stream, 0);
+}
+
+}  // extern "C"
+
+namespace isr {
+
+int nn2_search(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, float *out_d2,
+               int32_t *out_idx, const int32_t *skip, int64_t skip_stride, void *workspace,
+               size_t workspace_bytes, void *stream, int reuse_order) {
     ISR_REQUIRE(q != nullptr && t != nullptr, ISR_E_INVALID_ARG, "nn: null cloud descriptor");
     ISR_REQUIRE(q->n >= 0 && t->n >= 1 && batch >= 0, ISR_E_SHAPE,
                 "nn: need nq >= 0, nt >= 1, batch >= 0 (nq=%lld nt=%lld batch=%lld)",
@@ -1448,7 +1461,7 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
     ISR_REQUIRE(t->stage_c == nullptr || aligned16(t->stage_c), ISR_E_ALIGN,
                 "nn: stage centroids must be 16-byte aligned");
     const NN2Call c{q, t, batch, use_lo, out_d2, out_idx, skip, skip_stride, workspace,
-                    workspace_bytes, (cudaStream_t)stream};
+                    workspace_bytes, (cudaStream_t)stream, reuse_order};
     if (t->sub_c != nullptr && t->stage_c != nullptr && pruning_on()) {
         ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
 #ifdef ISR_NN_TUNING
@@ -1463,6 +1476,10 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
     }
     return nn2_dispatch<NN2Main>(c);
 }
+
+}  // namespace isr
+
+extern "C" {
 
 int isr_profile_nn_counters(uint64_t *out8_host) {
     using namespace isr;
