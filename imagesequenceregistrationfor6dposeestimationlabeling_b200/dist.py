@@ -128,6 +128,65 @@ def verify_poses_sharded(cloud_q, poses_q, poses_t, cloud_t=None, mode: str = "c
     return best_idx, best_loss, losses
 
 
+def _cuda_multistart(source, target, inits, max_dist, max_iteration, rel_fitness, rel_rmse):
+    from . import api
+
+    ms = api.multistart_icp(source, target, inits, max_dist, max_iteration, rel_fitness, rel_rmse)
+    return ([r.transformation for r in ms.results], [r.fitness for r in ms.results],
+            [r.inlier_rmse for r in ms.results], [r.iterations for r in ms.results], ms.chamfer)
+
+
+def multistart_icp_sharded(source, target, inits, max_correspondence_distance: float = 20.0,
+                           max_iteration: int = 30, relative_fitness: float = 1e-6,
+                           relative_rmse: float = 1e-6, group=None, runner: Optional[Callable] = None):
+    """BASELINE configs[4] over the GPUs of one box: the
+    symmetry-seeded starts are independent, so rank r runs the contiguous block
+    shard_bounds(S, r, world) of `inits` (batched ICP + Chamfer score of each registered
+    source, api.multistart_icp) -- no data-path collective.  The ranks then exchange one
+    fixed-size record per start (4x4 pose, fitness, rmse, iterations, Chamfer: 20 doubles) with
+    one all-gather, and rank by ascending Chamfer, first minimum first (icp.py:113-117 applied
+    per start).  Every rank passes the full arrays and gets the same dict:
+    transformations [S,4,4], fitness [S], inlier_rmse [S], iterations [S], chamfer [S], order [S],
+    best (index of the first minimum; also agreed through global_first_argmin)."""
+    runner = runner or _cuda_multistart
+    if td.is_initialized():
+        rank, world = td.get_rank(group), td.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    inits = np.asarray(inits, dtype=np.float64).reshape(-1, 4, 4)
+    s = len(inits)
+    lo, hi = shard_bounds(s, rank, world)
+    per = (s + world - 1) // world
+    rec = np.full((per, 20), np.inf)
+    if hi > lo:
+        Ts, fit, rmse, iters, ch = runner(source, target, inits[lo:hi], max_correspondence_distance,
+                                          max_iteration, relative_fitness, relative_rmse)
+        rec[: hi - lo, :16] = np.asarray(Ts, dtype=np.float64).reshape(hi - lo, 16)
+        rec[: hi - lo, 16], rec[: hi - lo, 17] = fit, rmse
+        rec[: hi - lo, 18], rec[: hi - lo, 19] = iters, ch
+    if world > 1:
+        dev = (torch.device("cuda", torch.cuda.current_device())
+               if td.get_backend(group) == "nccl" else torch.device("cpu"))
+        mine = torch.from_numpy(rec).to(dev)
+        out = torch.empty((world * per, 20), dtype=torch.float64, device=dev)
+        td.all_gather_into_tensor(out, mine, group=group)
+        rec = out.cpu().numpy()
+    rec = rec[:s]
+    ch = rec[:, 19].copy()
+    # C1 on the per-rank minima: the same first-minimum rule as the candidate selection
+    lbest = int(np.argmin(ch[lo:hi])) + lo if hi > lo else 0
+    lloss = torch.tensor([ch[lbest] if hi > lo else float("inf")], dtype=torch.float64)
+    lidx = torch.tensor([lbest if hi > lo else _I64_MAX], dtype=torch.int64)
+    if world > 1 and td.get_backend(group) == "nccl":
+        lloss, lidx = lloss.cuda(), lidx.cuda()
+    _, best = global_first_argmin(lloss, lidx, group)
+    order = np.argsort(ch, kind="stable")
+    assert int(best.item()) == int(order[0])
+    return {"transformations": rec[:, :16].reshape(s, 4, 4).copy(), "fitness": rec[:, 16].copy(),
+            "inlier_rmse": rec[:, 17].copy(), "iterations": rec[:, 18].astype(np.int64), "chamfer": ch,
+            "order": order, "best": int(order[0])}
+
+
 class PeerExchange:
     """This rank's end of the kernel-fused exchange of isr_icp_run_sharded (include/isr.h):
     a small buffer in this GPU's HBM that every peer maps through CUDA IPC and writes over

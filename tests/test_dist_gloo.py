@@ -125,6 +125,17 @@ class _OracleIcpTargetBackend(_OracleIcpBackend):
         return torch.from_numpy(sums)
 
 
+def _oracle_multistart(source, target, inits, max_dist, max_iteration, rf, rr):
+    Ts, fit, rmse, iters, ch = [], [], [], [], []
+    for T0 in inits:
+        o = oracle.registration_icp(source, target, max_dist, T0, max_iteration=max_iteration,
+                                    relative_fitness=rf, relative_rmse=rr)
+        Ts.append(o.transformation); fit.append(o.fitness); rmse.append(o.inlier_rmse)
+        iters.append(o.iterations)
+        ch.append(oracle.chamfer(oracle.transform(source, o.transformation), target))
+    return Ts, fit, rmse, iters, np.array(ch)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
@@ -168,6 +179,13 @@ def _worker(rank, world, port, q):
         res = dist.icp_sharded(src, tgt2, np.eye(4), 20.0, max_iteration=12, shard="target",
                                backend_factory=_OracleIcpTargetBackend)
         out["icp_target"] = res[0]
+        # config 5: starts split across ranks (3 starts over 2 ranks: 2 + 1), one duplicated
+        # start so that the best Chamfer value exists on both ranks (lowest index must win)
+        s5, t5, _ = synth.icp_pair(1201, 1500, 6, 7)
+        inits = np.stack([synth.pose_matrix(synth.rotvec_to_matrix([0, 0, a]), [0, 0, 0])
+                          for a in (0.0, 2.0, 0.0)])
+        out["multistart"] = dist.multistart_icp_sharded(s5, t5, inits, 20.0, max_iteration=6,
+                                                        runner=_oracle_multistart)
     finally:
         td.destroy_process_group()
     q.put((rank, out))
@@ -217,3 +235,13 @@ def test_world_size_2_gloo():
         np.testing.assert_allclose(res["fitness"], o2.fitness, rtol=1e-12)
         np.testing.assert_allclose(res["rmse"], o2.inlier_rmse, rtol=1e-9)
     np.testing.assert_array_equal(got[0]["icp_target"]["T"], got[1]["icp_target"]["T"])
+    s5, t5, _ = synth.icp_pair(1201, 1500, 6, 7)
+    inits = np.stack([synth.pose_matrix(synth.rotvec_to_matrix([0, 0, a]), [0, 0, 0]) for a in (0.0, 2.0, 0.0)])
+    Ts, fit, rmse, iters, ch = _oracle_multistart(s5, t5, inits, 20.0, 6, 1e-6, 1e-6)
+    for r in (0, 1):
+        m = got[r]["multistart"]
+        np.testing.assert_array_equal(m["transformations"], np.stack(Ts))
+        np.testing.assert_array_equal(m["chamfer"], ch)
+        np.testing.assert_array_equal(m["iterations"], iters)
+        assert ch[0] == ch[2] and m["best"] == int(np.argmin(ch)) == m["order"][0]
+        assert list(m["order"]) == list(np.argsort(ch, kind="stable"))

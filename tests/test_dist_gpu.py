@@ -48,6 +48,7 @@ def _worker(rank, world, port, q):
         res = dist.icp_sharded(src, tgt, inits, 20.0, max_iteration=30, relative_fitness=1e-4,
                                relative_rmse=1e-3, exchange="nccl")
         out["icp_multi_nccl"] = [(r.transformation, r.fitness, r.inlier_rmse, r.iterations) for r in res]
+        out["multistart"] = dist.multistart_icp_sharded(src, tgt, inits, 20.0, max_iteration=15)
         res = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=12, shard="target")
         out["icp_target"] = (res[0].transformation, res[0].fitness, res[0].inlier_rmse, res[0].iterations)
         torch.cuda.synchronize()
@@ -99,4 +100,14 @@ def test_two_gpu_sharding_matches_oracle():
             np.testing.assert_allclose(a[0], b[0], rtol=1e-9, atol=1e-9)
             assert a[3] == b[3] and a[1] == b[1]
     np.testing.assert_array_equal(got[0]["icp_target"][0], got[1]["icp_target"][0])
+    # config 5 split by starts (3 + 2): equals the single-GPU batched run, on both ranks
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api
+    inits = np.stack([synth.pose_matrix(synth.rotvec_to_matrix([0, 0, 2 * np.pi * k / 5]), [0, 0, 0])
+                      for k in range(5)])
+    ms = api.multistart_icp(src, tgt, inits, 20.0, max_iteration=15)
+    for r in (0, 1):
+        m = got[r]["multistart"]
+        np.testing.assert_array_equal(m["transformations"], np.stack([x.transformation for x in ms.results]))
+        np.testing.assert_array_equal(m["chamfer"], ms.chamfer)
+        assert list(m["order"]) == list(ms.order) and m["best"] == int(ms.order[0])
     np.testing.assert_array_equal(got[0]["verify"][2], got[1]["verify"][2])
