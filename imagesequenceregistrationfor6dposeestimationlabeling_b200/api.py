@@ -741,6 +741,35 @@ def refine_pose(R, t, source, target, max_correspondence_distance: float = 20.0,
 
 
 # --------------------------------------------------------------------------------------
+# PnP hypothesis scoring
+# --------------------------------------------------------------------------------------
+def score_pnp_hypotheses(points3d, points2d, camera_matrix, poses, reprojection_error: float = 2.0,
+                         return_inliers: bool = False, device=None):
+    """Consensus of every hypothesis in `poses` [B,4,4] (object -> camera) over the 2-D/3-D
+    correspondences (points3d [n,3], points2d [n,2] pixels): the test inside
+    cv2.solvePnPRansac as choosePose.py:23-33,280-300 uses it.  Returns int32 counts [B] on the
+    device (and the uint8 flags [B, n] when asked)."""
+    device = _device(device)
+    p3 = _points(points3d, device)
+    p2 = _to_dev(points2d, torch.float32, device)
+    if p3.dim() != 2 or p2.dim() != 2 or p2.shape != (p3.shape[0], 2):
+        raise ValueError("score_pnp_hypotheses: points3d [n,3] and points2d [n,2] expected")
+    K = _to_dev(np.asarray(camera_matrix, dtype=np.float64).reshape(3, 3), torch.float64, device)
+    P = _poses(poses, device)
+    n, b = p3.shape[0], P.shape[0]
+    counts = torch.empty((b,), dtype=torch.int32, device=device)
+    flags = torch.empty((b, n), dtype=torch.uint8, device=device) if return_inliers else None
+    lib = _lib.load()
+    step = 65535 * 16
+    for b0 in range(0, max(b, 1), step):
+        bc = min(step, b - b0)
+        _lib.check(lib.isr_pnp_score(_ptr(p3), _ptr(p2), n, _ptr(K), _ptr(P[b0:]), bc,
+                                     float(reprojection_error), _ptr(counts[b0:]),
+                                     _ptr(flags[b0:]) if flags is not None else None, _stream()))
+    return (counts, flags) if return_inliers else counts
+
+
+# --------------------------------------------------------------------------------------
 # measurement helper
 # --------------------------------------------------------------------------------------
 def measure_fp32_peak(packed: bool = False, iters: int = 4096, reps: int = 5) -> float:

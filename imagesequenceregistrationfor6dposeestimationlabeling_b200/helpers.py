@@ -89,6 +89,25 @@ def choose_image(pred_rel_poses, gt_rel_poses, modelVerts, diameter, surface_poi
     return error, int(np.argmax(votes)), np.argsort(-votes)[:50]
 
 
+def select_pnp_hypothesis(h3d, h2d, cam, Rs, ts, reperr: float = 2.0):
+    """Score PnP hypotheses (Rs [B,3,3], ts [B,3]) on the device and return the reference's
+    `pnp` triple for the winner (choosePose.py:23-33): (R, t, inlier indices) of the first
+    hypothesis with the largest consensus, or the failure sentinel (1, 1, 1) -- which
+    `verify_poses(valid_mask=...)` maps to +inf -- when no hypothesis has an inlier.  The
+    hypothesis GENERATION (cv2's P3P + RNG) stays with the caller; this replaces the consensus
+    loop, so that candidates go to the verification without a host round trip per pose."""
+    Rs = np.asarray(Rs, dtype=np.float64).reshape(-1, 3, 3)
+    ts = np.asarray(ts, dtype=np.float64).reshape(-1, 3)
+    P = np.tile(np.eye(4), (len(Rs), 1, 1))
+    P[:, :3, :3], P[:, :3, 3] = Rs, ts
+    counts, flags = api.score_pnp_hypotheses(h3d, h2d, cam, P, reperr, return_inliers=True)
+    counts = counts.cpu().numpy()
+    if len(counts) == 0 or counts.max() == 0:
+        return 1, 1, 1
+    k = int(np.argmax(counts))  # first maximum
+    return Rs[k].copy(), ts[k].copy(), np.nonzero(flags[k].cpu().numpy())[0]
+
+
 def draw_registration_result(source, target, transformation):
     """Open3D GUI in the reference (blocking); a no-op here."""
     return None

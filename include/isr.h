@@ -323,6 +323,18 @@ int isr_icp_run_sharded(IsrIcpState *states, int64_t starts, const float *src, c
 int isr_radius_count(const IsrCloud *q, const IsrCloud *t, double radius, int32_t *out_count,
                      void *stream);
 
+/* ---- PnP hypothesis scoring ------------------------------------ */
+/* out_count[j] (int32 [b]) = number of the n 2-D/3-D correspondences that hypothesis j
+ * (poses float64 [b][16], object -> camera) reprojects within `reperr` pixels: the consensus
+ * test of cv2.solvePnPRansac as choosePose.py:23-33,280-300 calls it (camera matrix `cam`,
+ * device double[9] row-major, no distortion; error = float32(du^2 + dv^2) <= reperr^2; a point
+ * with z == 0 is projected with z = 1, as OpenCV's projectPoints does).  p3d float32 [n][3],
+ * p2d float32 [n][2] (u, v).  out_inlier (uint8 [b][n], may be NULL) receives the flags
+ * (the `in1` array of choosePose.py:24,31 for the winning hypothesis). */
+int isr_pnp_score(const float *p3d, const float *p2d, int64_t n, const double *cam,
+                  const double *poses, int64_t b, double reperr, int32_t *out_count,
+                  uint8_t *out_inlier, void *stream);
+
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* FFMA-chain microbenchmark: launches `blocks` x 256 threads, each running `iters`
  * rounds of 16 independent FMAs (packed != 0: fma.rn.f32x2).  flops_out_host receives the

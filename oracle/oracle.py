@@ -193,6 +193,32 @@ def remove_radius_outlier(points, nb_points, radius):
     return np.asarray(points)[ind], ind
 
 
+def pnp_inliers(p3d, p2d, cam, R, t, reperr=2.0):
+    """Consensus set of ONE PnP hypothesis as cv2.solvePnPRansac scores it (choosePose.py:23-33
+    calls it with reprojectionError=2, distCoeffs=None).  OpenCV (calib3d: PnPRansacCallback::
+    computeError, RANSACPointSetRegistrator::findInliers; not installable here -> parity
+    unpinned, restated from the published source): points and image points are float32, the
+    pinhole projection is evaluated in float64 and stored as float32 (z == 0 -> 1),
+    err = float32(double(du)^2 + double(dv)^2), inlier iff err <= reperr^2 (double).
+    Returns the boolean mask [n]."""
+    P = np.asarray(p3d, dtype=np.float32).astype(np.float64)
+    uv = np.asarray(p2d, dtype=np.float32)
+    K = np.asarray(cam, dtype=np.float64).reshape(3, 3)
+    R = np.asarray(R, dtype=np.float64).reshape(3, 3)
+    t = np.asarray(t, dtype=np.float64).reshape(3)
+    x = ((R[0, 0] * P[:, 0] + R[0, 1] * P[:, 1]) + R[0, 2] * P[:, 2]) + t[0]
+    y = ((R[1, 0] * P[:, 0] + R[1, 1] * P[:, 1]) + R[1, 2] * P[:, 2]) + t[1]
+    z = ((R[2, 0] * P[:, 0] + R[2, 1] * P[:, 1]) + R[2, 2] * P[:, 2]) + t[2]
+    with np.errstate(divide="ignore"):
+        iz = np.where(z != 0.0, 1.0 / z, 1.0)
+    xn, yn = x * iz, y * iz
+    pu = (K[0, 0] * xn + K[0, 1] * yn + K[0, 2]).astype(np.float32)
+    pv = (K[1, 1] * yn + K[1, 2]).astype(np.float32)
+    du, dv = (uv[:, 0] - pu).astype(np.float64), (uv[:, 1] - pv).astype(np.float64)
+    err = (du * du + dv * dv).astype(np.float32)
+    return err.astype(np.float64) <= float(reperr) * float(reperr)
+
+
 def transform(points, T):
     """PointCloud.transform: p <- T[:3,:3] p + T[:3,3] (float64).  icp.py:22,110."""
     T = np.asarray(T, dtype=np.float64)

@@ -567,6 +567,56 @@ def test_radius_count_lattice_boundary_and_target(gpu):
     np.testing.assert_array_equal(got, oracle.radius_count(q, 1.3, target=pts))
 
 
+def _pnp_scene(n=5000, seed=0):
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    rng = np.random.default_rng(seed)
+    p3d = synth.make_cloud(n, seed=5)
+    R, t = synth.true_pose(3)
+    cam = np.array([[1075.0, 0.0, 360.0], [0.0, 1073.0, 270.0], [0.0, 0.0, 1.0]])
+    pc = p3d.astype(np.float64) @ R.T + t
+    uv = (pc[:, :2] / pc[:, 2:3]) * [cam[0, 0], cam[1, 1]] + [cam[0, 2], cam[1, 2]]
+    uv += rng.normal(scale=0.7, size=uv.shape)
+    bad = rng.random(n) < 0.3                      # wrong correspondences
+    uv[bad] = rng.uniform([0, 0], [720, 540], size=(int(bad.sum()), 2))
+    return p3d, uv.astype(np.float32), cam, R, t
+
+
+def test_pnp_hypothesis_scoring_equals_oracle(gpu):
+    """inlier counts and flags of a batch of PnP hypotheses equal the
+    restated OpenCV consensus test, including hypotheses at the 2-pixel edge, behind the
+    camera and with z == 0; the helper returns the reference's (R, t, inliers) triple of the
+    first best hypothesis and the (1, 1, 1) sentinel when nothing reprojects."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import helpers, synth
+    p3d, uv, cam, R, t = _pnp_scene()
+    rng = np.random.default_rng(1)
+    Rs = [R] + [R @ synth.rotvec_to_matrix(rng.normal(scale=s, size=3)) for s in
+                (1e-4, 1e-3, 3e-3, 1e-2, 0.1, 1.0)] + [synth.random_rotation(rng) for _ in range(30)] + [R]
+    ts = [t] + [t + rng.normal(scale=s, size=3) for s in (0.01, 0.1, 0.5, 2.0, 10.0, 50.0)] + \
+         [t * np.array([1, 1, -1.0])] * 15 + [np.zeros(3)] * 15 + [t]
+    P = np.stack([synth.pose_matrix(a, b) for a, b in zip(Rs, ts)])
+    counts, flags = gpu.score_pnp_hypotheses(p3d, uv, cam, P, 2.0, return_inliers=True)
+    counts, flags = counts.cpu().numpy(), flags.cpu().numpy().astype(bool)
+    for k in range(len(P)):
+        ref = oracle.pnp_inliers(p3d, uv, cam, Rs[k], ts[k], 2.0)
+        np.testing.assert_array_equal(flags[k], ref)
+        assert counts[k] == ref.sum()
+    assert counts[0] == counts[-1] > 0.5 * len(p3d)
+    # every hypothesis twice: the winner must be the FIRST of the two equal maxima
+    Rb, tb, inl = helpers.select_pnp_hypothesis(p3d, uv, cam, np.stack(Rs + Rs), np.stack(ts + ts))
+    ks = int(np.argmax(counts))
+    np.testing.assert_array_equal(Rb, Rs[ks])
+    np.testing.assert_array_equal(tb, ts[ks])
+    np.testing.assert_array_equal(inl, np.nonzero(oracle.pnp_inliers(p3d, uv, cam, Rs[ks], ts[ks]))[0])
+    far = helpers.select_pnp_hypothesis(p3d, uv + 1e4, cam, np.stack(Rs[:3]), np.stack(ts[:3]))
+    assert far == (1, 1, 1)
+    # sizes that are not multiples of the tile, an empty batch, a zero threshold
+    c = gpu.score_pnp_hypotheses(p3d[:1001], uv[:1001], cam, P[:17], 0.0).cpu().numpy()
+    assert c.shape == (17,) and c.max() == 0
+    c = gpu.score_pnp_hypotheses(p3d[:3], uv[:3], cam, P[:1], 1e9).cpu().numpy()
+    assert c.tolist() == [3]
+    assert gpu.score_pnp_hypotheses(p3d, uv, cam, np.zeros((0, 4, 4))).shape == (0,)
+
+
 def test_remove_radius_outlier_shim(gpu):
     """o3d.geometry.PointCloud.remove_radius_outlier as generateCors.py:254-258 calls it."""
     import imagesequenceregistrationfor6dposeestimationlabeling_b200.o3d_compat as o3d

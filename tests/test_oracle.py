@@ -224,3 +224,26 @@ def test_radius_count_restatement_against_kdtree():
     np.testing.assert_array_equal(oracle.radius_count(line, 1.0000001), [2, 3, 2, 1])
     kept, ind = oracle.remove_radius_outlier(line, 1, 1.5)
     assert list(ind) == [0, 1, 2] and len(kept) == 3
+
+
+def test_pnp_inliers_known_answers():
+    """oracle.pnp_inliers: exact projection -> all inliers; a 3-pixel shift -> none at the
+    2-pixel threshold, all at 3.5; the squared-error edge is inclusive; z == 0 projects with z = 1."""
+    rng = np.random.default_rng(0)
+    P = rng.uniform(-50, 50, size=(200, 3)).astype(np.float32)
+    R, t = np.eye(3), np.array([0.0, 0.0, 700.0])
+    cam = np.array([[1000.0, 0.0, 320.0], [0.0, 1000.0, 240.0], [0.0, 0.0, 1.0]])
+    pc = P.astype(np.float64) + t
+    uv = (pc[:, :2] / pc[:, 2:3]) * 1000.0 + [320.0, 240.0]
+    assert oracle.pnp_inliers(P, uv, cam, R, t, 2.0).all()
+    shifted = uv + [3.0, 0.0]
+    assert not oracle.pnp_inliers(P, shifted, cam, R, t, 2.0).any()
+    assert oracle.pnp_inliers(P, shifted, cam, R, t, 3.5).all()
+    # inclusive edge on an exactly representable case: point on the axis, 2-pixel offset
+    P0 = np.array([[0.0, 0.0, 0.0]], dtype=np.float32)
+    assert oracle.pnp_inliers(P0, np.array([[322.0, 240.0]]), cam, R, t, 2.0)[0]
+    assert not oracle.pnp_inliers(P0, np.array([[322.0, 240.0]]), cam, R, t, 1.999)[0]
+    # z == 0: OpenCV divides by 1 instead
+    m = oracle.pnp_inliers(np.array([[0.001, 0.0, 0.0]], dtype=np.float32), np.array([[321.0, 240.0]]), cam, R,
+                           np.zeros(3), 0.5)
+    assert m[0]
