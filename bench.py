@@ -406,13 +406,18 @@ def main():
         # flag wait; no NCCL call, no host work per iteration).  After the first evaluation a
         # run keeps the launch order of the search and skips the per-iteration set-up launches.
         pprob = api.IcpProblem(src[slo:shi], tgt, np.eye(4)[None])
-        peer = dist.peer_exchange() if world > 1 else None
+        peer = dist.peer_exchange(required=False) if world > 1 else None
 
         def icp_run(iters):
-            if world > 1:
+            if peer is not None:
                 pprob.run_sharded(peer, len(src), 20.0, iters - 1, 0.0, 0.0)
-            else:
+            elif world == 1:
                 pprob.run(20.0, iters - 1, 0.0, 0.0)
+            else:  # peer memory unavailable on this box: the NCCL form of dist.icp_sharded
+                for k in range(iters):
+                    sums_k = pprob.accumulate(20.0)
+                    td.all_reduce(sums_k, op=td.ReduceOp.SUM)
+                    pprob.solve(len(src), 0.0, 0.0, k == iters - 1, sums_k)
 
         icp_run(1)       # warm-up: one evaluation
         pprob.reopen()
@@ -493,7 +498,8 @@ def main():
             "icp_config": f"dense ICP refine (BASELINE configs[3]): {args.icp_points} x {args.icp_points} "
                           f"points, {args.icp_iters} forced iterations, source sharded x{world}, one C call "
                           + ("(isr_icp_run_sharded: sums exchanged inside the accumulate/solve kernels through "
-                             "peer memory over NVLink, no NCCL call)" if world > 1 else "(isr_icp_run)"),
+                             "peer memory over NVLink, no NCCL call)" if peer is not None else
+                             "(isr_icp_run)" if world == 1 else "(peer memory unavailable: NCCL all-reduce per iteration)"),
             "icp_stepwise_iters_per_s": args.icp_iters / t_icp,
             "icp_stepwise_config": "the same loop driven from Python, one accumulate + "
                                    f"{'NCCL all-reduce + ' if world > 1 else ''}solve call per iteration "
@@ -570,6 +576,7 @@ def main():
 
     if world > 1:
         barrier()
+        dist.close_peer_exchanges()
         td.destroy_process_group()
     if rank != 0:
         return

@@ -236,18 +236,39 @@ class PeerExchange:
 _peer_cache: dict = {}
 
 
-def peer_exchange(group=None) -> PeerExchange:
-    """The process-wide PeerExchange of `group` (created on first use; collective)."""
+def peer_exchange(group=None, required: bool = True) -> Optional[PeerExchange]:
+    """The process-wide PeerExchange of `group` (created on first use; collective).  The ranks
+    agree on the outcome: if mapping the peers' buffers fails on ANY rank (GPUs without
+    peer access, IPC disabled in the container), every rank drops its end and gets None --
+    or the error, when `required`."""
     key = id(group) if group is not None else None
     if key not in _peer_cache:
-        _peer_cache[key] = PeerExchange(group)
-    return _peer_cache[key]
+        px, err = None, None
+        try:
+            px = PeerExchange(group)
+        except Exception as e:  # noqa: BLE001 -- reported below, after the ranks have agreed
+            err = e
+        if td.is_initialized() and td.get_world_size(group) > 1:
+            dev = (torch.device("cuda", torch.cuda.current_device())
+                   if td.get_backend(group) == "nccl" else torch.device("cpu"))
+            ok = torch.tensor([0 if px is None else 1], dtype=torch.int32, device=dev)
+            td.all_reduce(ok, op=td.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0 and px is not None:
+                px.close()
+                px, err = None, RuntimeError("a peer rank could not map the exchange buffers")
+        _peer_cache[key] = (px, err)
+    px, err = _peer_cache[key]
+    if px is None and required:
+        raise RuntimeError(f"kernel-fused peer exchange unavailable: {err}")
+    return px
 
 
 def close_peer_exchanges() -> None:
     """Collective: release every cached PeerExchange (before destroy_process_group)."""
     for key in sorted(_peer_cache, key=lambda k: (k is not None, k)):
-        _peer_cache.pop(key).close()
+        px, _ = _peer_cache.pop(key)
+        if px is not None:
+            px.close()
 
 
 class CudaIcpBackend:
@@ -355,10 +376,12 @@ def icp_sharded(source, target, init=None, max_correspondence_distance: float = 
     if peer_ok and (exchange == "peer" or (exchange == "auto" and world > 1)):
         from . import api
 
-        prob = api.IcpProblem(source[lo:hi], target, inits)
-        prob.run_sharded(peer_exchange(group), ns, max_correspondence_distance, max_iteration,
-                         relative_fitness, relative_rmse)
-        return prob.results(with_correspondences=False)
+        px = peer_exchange(group, required=(exchange == "peer"))
+        if px is not None:
+            prob = api.IcpProblem(source[lo:hi], target, inits)
+            prob.run_sharded(px, ns, max_correspondence_distance, max_iteration, relative_fitness,
+                             relative_rmse)
+            return prob.results(with_correspondences=False)
     factory = backend_factory or CudaIcpBackend
     be = factory(source[lo:hi], target, inits)
     for k in range(max_iteration + 1):
