@@ -1086,7 +1086,7 @@ block_weight_kernel(const float *__restrict__ q, long long q_bstride, int nq, in
 constexpr int kSplitMax = 128;  // (512 was measured slower: 25 % more total work, tail no longer the limit)
 __global__ void __launch_bounds__(1024)
 block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, int split_max, int halve,
-                   int *__restrict__ order, int *__restrict__ order_count) {
+                   float split_factor, int *__restrict__ order, int *__restrict__ order_count) {
     __shared__ u64 s[kOrderMax];
     __shared__ int nsplit;
     static_assert(kSplitMax == 128, "order_workspace_bytes sizes the launch list for 128 split blocks");
@@ -1109,7 +1109,7 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
     if (threadIdx.x == 0) {
         const float wmed = __uint_as_float(~(unsigned)(s[nqb / 2] >> 32));
         int h = 0;
-        while (h < split_max && h < nqb && __uint_as_float(~(unsigned)(s[h] >> 32)) > 4.0f * wmed) ++h;
+        while (h < split_max && h < nqb && __uint_as_float(~(unsigned)(s[h] >> 32)) > split_factor * wmed) ++h;
         nsplit = h;
         order_count[b] = (halve ? 2 : 1) * (nqb - h) + rows * h;
     }
@@ -1339,7 +1339,12 @@ static int nn2_dispatch(const NN2Call &c) {
         constexpr int kRows = V::kQueriesPerCta / 32;
         // splitting only pays when the grid is a few waves deep (a single cloud pair, a few
         // ICP starts); a big batch hides its wide blocks behind the others
-        const int split_max = (long long)nqb * c.batch <= 16384 ? kSplitMax : 0;
+        int split_max = (long long)nqb * c.batch <= 16384 ? kSplitMax : 0;
+        float split_factor = 4.0f;  // squared radius > 4 x the median's: radius > twice the median
+#ifdef ISR_NN_TUNING
+        if (const char *e = getenv("ISR_NN_SPLIT_MAX")) { if (split_max) split_max = atoi(e); }
+        if (const char *e = getenv("ISR_NN_SPLIT_THR")) split_factor = (float)atof(e);
+#endif
         // a grid that fills less than half of the machine runs every block as two CTAs of 4
         // query rows (measured, ICP search: 100k points 0.203 -> 0.163 ms, 250k 0.248 -> 0.206 ms;
         // from one full wave on -- 500k, 1M points -- the repeated per-CTA tests cost more than
@@ -1360,7 +1365,7 @@ static int nn2_dispatch(const NN2Call &c) {
                 p.q, p.q_bstride, p.nq, p.nq_pad, nqb, (int)c.batch, keys);
             ISR_TRY(launched("block_weight_kernel"));
             block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, kRows, stride, split_max, halve,
-                                                                     order, count);
+                                                                     split_factor, order, count);
             ISR_TRY(launched("block_order_kernel"));
         }
         p.order = order;
