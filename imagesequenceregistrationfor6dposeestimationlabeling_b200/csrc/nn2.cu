@@ -125,12 +125,6 @@ __device__ __forceinline__ float filter_threshold(float mt, float nq2, float qn)
     return __fadd_ru(mt, W);
 }
 
-// One (warp, sub-tile) unit: the FP32 filter scan of SUB targets against the warp's 32 x Q
-// queries, and the FP64 resolve of the flagged ones.  sx..sn point at the sub-tile's x, y,
-// z, |p|^2 values in shared memory; gbase is the stored index of its first target.  The
-// scan state (q2*, thr) lives in registers; the resolve state (mt_l .. dq_l) is indexed at
-// run time, which places it in (L1-resident) local memory and keeps it out of the scan's
-// registers.
 // The filter scan of SUB targets for query rows R0 .. R0 + QN - 1 of the lane.  The sub-tile is
 // walked in PARTS equal pieces; after each piece the rows whose minimum over the piece comes
 // within their threshold get bit (piece * 8 + row) of `flags` (the resolve then re-derives only
@@ -195,32 +189,21 @@ __device__ __forceinline__ void scan_rows(const float4 *sx, const float4 *sy, co
     }
 }
 
-template <int Q, int SUB, int UNR, bool PRUNE, int PARTS = 1>
-__device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__restrict__ gq,
-                                             const float *__restrict__ gt, int q0, int lane,
-                                             const float4 *sx, const float4 *sy, const float4 *sz,
-                                             const float4 *sn, int gbase, const float (&q2x)[Q],
-                                             const float (&q2y)[Q], const float (&q2z)[Q],
-                                             float (&thr)[Q], float *mt_l, float *thr_l,
-                                             float *tm_l, double *Dbest_l, int *ibest_l,
-                                             float *dq_l, float &dmax, unsigned &nflag,
-                                             unsigned &npass, const float *qsm = nullptr,
-                                             unsigned rows = ~0u) {
-    float tm[Q];
-#pragma unroll
-    for (int r = 0; r < Q; ++r) tm[r] = CUDART_INF_F;
-    unsigned pflags = 0;  // bit (piece * 8 + row)
-    if (PRUNE && Q == 8) {
-        // the pruned search scans only the half of the warp's query rows (0-3, 4-7) that the
-        // exact test could not rule out: an unscanned row keeps tm = +inf and never flags
-        if (rows & 0x0Fu)
-            scan_rows<Q, 0, Q / 2, SUB, UNR, PARTS>(sx, sy, sz, sn, q2x, q2y, q2z, thr, tm, pflags);
-        if (rows & 0xF0u)
-            scan_rows<Q, Q / 2, Q - Q / 2, SUB, UNR, PARTS>(sx, sy, sz, sn, q2x, q2y, q2z, thr, tm, pflags);
-    } else {
-        static_assert(PRUNE || PARTS == 1, "the exhaustive kernel flags whole sub-tiles");
-        scan_rows<Q, 0, Q, SUB, UNR, PARTS>(sx, sy, sz, sn, q2x, q2y, q2z, thr, tm, pflags);
-    }
+// The FP64 resolve of one scanned (warp, sub-tile) unit.  pflags: bit (piece * 8 + row) set
+// where the filter minimum of that piece came within the row's threshold; tm: the filter
+// minima over the whole sub-tile.  sx..sn point at the sub-tile's x, y, z, |p|^2 values in
+// shared memory; gbase is the stored index of its first target.  The resolve state (mt_l ..
+// dq_l) is indexed at run time, which places it in (L1-resident) local memory and keeps it
+// out of the scan's registers.  Returns whether anything was flagged.
+template <int Q, int SUB, bool PRUNE, int PARTS>
+__device__ __forceinline__ bool resolve_flagged(const NN2Params &p, const float *__restrict__ gq,
+                                                const float *__restrict__ gt, int q0, int lane,
+                                                const float4 *sx, const float4 *sy, const float4 *sz,
+                                                const float4 *sn, int gbase, unsigned pflags,
+                                                const float (&tm)[Q], float *mt_l, float *thr_l,
+                                                float *tm_l, double *Dbest_l, int *ibest_l,
+                                                float *dq_l, float &dmax, unsigned &nflag,
+                                                unsigned &npass, const float *qsm) {
     // bit r: row r has a flagged piece
     const unsigned flags = (pflags | (pflags >> 8) | (pflags >> 16) | (pflags >> 24)) & 0xFFu;
     if (PRUNE && p.evaluated != nullptr) {  // profiling only
@@ -324,16 +307,82 @@ __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__
             ibest_l[r] = ib;
             // >= the exact best distance of the FP64 (hi + lo) query, rounded up
             if (PRUNE)
-                dq_l[r] = __double2float_ru(sqrt(Db)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
+                dq_l[r] = __fsqrt_ru(__double2float_ru(Db)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
         }
-#pragma unroll
-        for (int r = 0; r < Q; ++r) thr[r] = thr_l[r];
         if (PRUNE) {
             float m = 0.f;
             for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r]);  // run-time loop on purpose
             dmax = m;
         }
     }
+    return flags != 0;
+}
+
+// One (warp, sub-tile) unit of the exhaustive kernel: the FP32 filter scan of SUB targets
+// against the warp's 32 x Q queries (operands and thresholds in registers), then the resolve.
+template <int Q, int SUB, int UNR>
+__device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__restrict__ gq,
+                                             const float *__restrict__ gt, int q0, int lane,
+                                             const float4 *sx, const float4 *sy, const float4 *sz,
+                                             const float4 *sn, int gbase, const float (&q2x)[Q],
+                                             const float (&q2y)[Q], const float (&q2z)[Q],
+                                             float (&thr)[Q], float *mt_l, float *thr_l,
+                                             float *tm_l, double *Dbest_l, int *ibest_l,
+                                             float *dq_l, float &dmax, unsigned &nflag,
+                                             unsigned &npass) {
+    float tm[Q];
+#pragma unroll
+    for (int r = 0; r < Q; ++r) tm[r] = CUDART_INF_F;
+    unsigned pflags = 0;
+    scan_rows<Q, 0, Q, SUB, UNR, 1>(sx, sy, sz, sn, q2x, q2y, q2z, thr, tm, pflags);
+    if (resolve_flagged<Q, SUB, false, 1>(p, gq, gt, q0, lane, sx, sy, sz, sn, gbase, pflags, tm, mt_l, thr_l,
+                                          tm_l, Dbest_l, ibest_l, dq_l, dmax, nflag, npass, nullptr)) {
+#pragma unroll
+        for (int r = 0; r < Q; ++r) thr[r] = thr_l[r];
+    }
+}
+
+// The same unit in the pruned search, which scans only the half of the warp's query rows
+// (0-3, 4-7) that the exact test could not rule out (`rows`): an unscanned row keeps tm = +inf
+// and never flags.  The half's operands (-2 q and the thresholds) are fetched for the scan
+// from the warp's shared-memory copy of its queries (qsm: [6][32 * Q], hi xyz then lo xyz)
+// and from the resolve state, so that they occupy registers only while a scan runs.
+template <int Q, int SUB, int UNR, int PARTS>
+__device__ __forceinline__ void scan_subtile_pruned(const NN2Params &p, const float *__restrict__ gq,
+                                                    const float *__restrict__ gt, int q0, int lane,
+                                                    const float4 *sx, const float4 *sy, const float4 *sz,
+                                                    const float4 *sn, int gbase, float *mt_l, float *thr_l,
+                                                    float *tm_l, double *Dbest_l, int *ibest_l, float *dq_l,
+                                                    float &dmax, unsigned &nflag, unsigned &npass,
+                                                    const float *qsm, unsigned rows) {
+    static_assert(Q == 8, "two halves of four rows");
+    constexpr int H = Q / 2;
+    float tm[Q];
+#pragma unroll
+    for (int r = 0; r < Q; ++r) tm[r] = CUDART_INF_F;
+    unsigned pflags = 0;  // bit (piece * 8 + row)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if ((rows >> (half * H)) & ((1u << H) - 1u)) {
+            float hx[H], hy[H], hz[H], ht[H], tmh[H];
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+                const int qs = (half * H + r) * 32 + lane;
+                hx[r] = -2.0f * qsm[qs];
+                hy[r] = -2.0f * qsm[32 * Q + qs];
+                hz[r] = -2.0f * qsm[2 * 32 * Q + qs];
+                ht[r] = thr_l[half * H + r];
+                tmh[r] = CUDART_INF_F;
+            }
+            unsigned pf = 0;
+            scan_rows<H, 0, H, SUB, UNR, PARTS>(sx, sy, sz, sn, hx, hy, hz, ht, tmh, pf);
+            pflags |= pf << (half * H);  // rows 0..3 of every piece's byte -> rows half * 4 ..
+#pragma unroll
+            for (int r = 0; r < H; ++r) tm[half * H + r] = tmh[r];
+        }
+    }
+    resolve_flagged<Q, SUB, true, PARTS>(p, gq, gt, q0, lane, sx, sy, sz, sn, gbase, pflags, tm, mt_l, thr_l, tm_l,
+                                         Dbest_l, ibest_l, dq_l, dmax, nflag, npass, qsm);
 }
 
 // ---- exhaustive kernel: every stage, every sub-tile -----------------------------------------
@@ -476,7 +525,7 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
         const int gstage = (s_begin + stage_of(sl)) * STAGE;
 #pragma unroll 1
         for (int sub = 0; sub < STAGE / SUB; ++sub) {
-            scan_subtile<Q, SUB, UNR, false>(p, gq, gt, q0, lane, sx + sub * (SUB / 4),
+            scan_subtile<Q, SUB, UNR>(p, gq, gt, q0, lane, sx + sub * (SUB / 4),
                                              sy + sub * (SUB / 4), sz + sub * (SUB / 4),
                                              sn + sub * (SUB / 4), gstage + sub * SUB, q2x, q2y, q2z,
                                              thr, mt_l, thr_l, tm_l, Dbest_l, ibest_l, nullptr, dmax,
@@ -523,7 +572,8 @@ struct alignas(128) PrunedWarpSmem {
     float4 row[Q];             // sphere (c, rho) of query row r = the 32 queries r*32 .. r*32+31
     float rowB[Q];             // max of their bounds dq (refreshed between batches of work)
     uint64_t full[kRing];
-    float qs[6][32 * Q];       // the warp's queries, hi xyz and lo xyz (read by the resolve path)
+    int seed[kAnchors];        // sub-tiles scanned first (-1: none)
+    float qs[6][32 * Q];       // the warp's queries, hi xyz and lo xyz (read by the scan and the resolve path)
 };
 
 template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS>
@@ -568,31 +618,28 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         mbar_fence_init();
     }
 
-    float q2x[Q], q2y[Q], q2z[Q], thr[Q];
+    // Everything per query row is a RUN-TIME loop over r from here on (the queries live in
+    // shared memory, the resolve state in local memory): the kernel's code is what competes
+    // for the instruction cache when the warps of an SM sit in different phases, and every
+    // loop unrolled over the 8 rows multiplies it (124 KB of SASS before, no_instruction the
+    // fastest-growing stall when more warps were made resident).
     float mt_l[Q], thr_l[Q], tm_l[Q], dq_l[Q];
     double Dbest_l[Q];
     int ibest_l[Q];
     float dmax = 0.f;  // max over the lane's live queries of dq_l (0: no live query)
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < Q; ++r) {
         const int i = min(q0 + r * 32, p.nq_pad - 1);
-        q2x[r] = -2.0f * gq[i];
-        q2y[r] = -2.0f * gq[p.nq_pad + i];
-        q2z[r] = -2.0f * gq[2ll * p.nq_pad + i];
-        const bool live = (livemask >> r) & 1u;
-        thr[r] = live ? CUDART_INF_F : -CUDART_INF_F;
-        if (live) dmax = CUDART_INF_F;
-        ws.qs[0][r * 32 + lane] = -0.5f * q2x[r];
-        ws.qs[1][r * 32 + lane] = -0.5f * q2y[r];
-        ws.qs[2][r * 32 + lane] = -0.5f * q2z[r];
+        ws.qs[0][r * 32 + lane] = gq[i];
+        ws.qs[1][r * 32 + lane] = gq[p.nq_pad + i];
+        ws.qs[2][r * 32 + lane] = gq[2ll * p.nq_pad + i];
         if (p.use_lo) {
             ws.qs[3][r * 32 + lane] = gq[4ll * p.nq_pad + i];
             ws.qs[4][r * 32 + lane] = gq[5ll * p.nq_pad + i];
             ws.qs[5][r * 32 + lane] = gq[6ll * p.nq_pad + i];
         }
-    }
-    for (int r = 0; r < Q; ++r) {  // run-time loop on purpose
         const bool live = (livemask >> r) & 1u;
+        if (live) dmax = CUDART_INF_F;
         mt_l[r] = CUDART_INF_F;
         thr_l[r] = live ? CUDART_INF_F : -CUDART_INF_F;
         Dbest_l[r] = CUDART_INF;
@@ -607,6 +654,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     if (p.hint != nullptr) {
         __syncwarp();  // ws.qs is complete
         bool ok = true;
+#pragma unroll 1
         for (int r = 0; r < Q; ++r) {  // run-time loop: the resolve state lives in local memory
             const int i = q0 + r * 32;
             if (!((livemask >> r) & 1u)) continue;
@@ -629,22 +677,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
             thr_l[r] = filter_threshold(a, nq2, sqrtf(nq2));
             Dbest_l[r] = D;
             ibest_l[r] = h;
-            dq_l[r] = __double2float_ru(sqrt(D)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
+            dq_l[r] = __fsqrt_ru(__double2float_ru(D)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
         }
         all_hinted = __all_sync(0xffffffffu, ok);
-#pragma unroll
-        for (int r = 0; r < Q; ++r) thr[r] = thr_l[r];
         float m = 0.f;
-        for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r]);  // run-time loop on purpose
+#pragma unroll 1
+        for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r]);
         dmax = m;
     }
 
     // ---- query-row spheres: row r is 32 consecutive stored queries, a compact patch ----------
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < Q; ++r) {
         const bool live = (livemask >> r) & 1u;
-        float cx = live ? q2x[r] : 0.f, cy = live ? q2y[r] : 0.f, cz = live ? q2z[r] : 0.f,
-              cn = live ? 1.f : 0.f;
+        const float qx = ws.qs[0][r * 32 + lane], qy = ws.qs[1][r * 32 + lane], qz = ws.qs[2][r * 32 + lane];
+        float cx = live ? qx : 0.f, cy = live ? qy : 0.f, cz = live ? qz : 0.f, cn = live ? 1.f : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             cx += __shfl_xor_sync(0xffffffffu, cx, o);
@@ -652,10 +699,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
             cz += __shfl_xor_sync(0xffffffffu, cz, o);
             cn += __shfl_xor_sync(0xffffffffu, cn, o);
         }
-        const float inv = cn > 0.f ? -0.5f / cn : 0.f;  // q2 = -2 * query
+        const float inv = cn > 0.f ? 1.0f / cn : 0.f;
         cx *= inv; cy *= inv; cz *= inv;
-        const float dx = fmaf(q2x[r], -0.5f, -cx), dy = fmaf(q2y[r], -0.5f, -cy),
-                    dz = fmaf(q2z[r], -0.5f, -cz);
+        const float dx = qx - cx, dy = qy - cy, dz = qz - cz;
         float m = live ? fmaf(dz, dz, fmaf(dy, dy, dx * dx)) : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -668,7 +714,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     // rowB[r] <- max over the row of the current bounds (they only ever shrink, so a stale
     // value is merely conservative)
     auto refresh_bounds = [&]() {
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < Q; ++r) {
             float m = dq_l[r];
 #pragma unroll
@@ -680,7 +726,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     // coarse test, one candidate sphere per lane: which query rows can it still matter to?
     auto coarse_rows = [&](const float4 S) {
         unsigned rows = 0;
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < Q; ++r) {
             const float4 R = ws.row[r];
             const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
@@ -695,7 +741,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         const float hx = (float)(hb & 1023u) * sc, hy = (float)((hb >> 10) & 1023u) * sc,
                     hz = (float)((hb >> 20) & 1023u) * sc;
         unsigned rows = 0;
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < Q; ++r) {
             const float4 R = ws.row[r];
             const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
@@ -711,15 +757,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     // exact test, one query per lane and row: is any query of `rows` not ruled out?
     auto exact_any = [&](const float4 S, unsigned rows) {
         bool need = false;
-#pragma unroll
-        for (int r = 0; r < Q; ++r) {
-            if (rows & (1u << r)) {  // warp-uniform
-                const float dx = fmaf(q2x[r], -0.5f, -S.x), dy = fmaf(q2y[r], -0.5f, -S.y),
-                            dz = fmaf(q2z[r], -0.5f, -S.z);
-                const float rr = (dq_l[r] + S.w) * 1.0001f;
-                // a dead query slot (dq = 0, padded coordinates ~1e18) is always ruled out
-                need = need || !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr);
-            }
+        for (unsigned m = rows & ((1u << Q) - 1u); m != 0; m &= m - 1) {  // warp-uniform
+            const int r = __ffs(m) - 1;
+            const float dx = ws.qs[0][r * 32 + lane] - S.x, dy = ws.qs[1][r * 32 + lane] - S.y,
+                        dz = ws.qs[2][r * 32 + lane] - S.z;
+            const float rr = (dq_l[r] + S.w) * 1.0001f;
+            // a dead query slot (dq = 0, padded coordinates ~1e18) is always ruled out
+            need = need || !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr);
         }
         return __any_sync(0xffffffffu, need);
     };
@@ -732,70 +776,57 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         const float hx = (float)(hb & 1023u) * sc, hy = (float)((hb >> 10) & 1023u) * sc,
                     hz = (float)((hb >> 20) & 1023u) * sc;
         unsigned need = 0;
-#pragma unroll
-        for (int r = 0; r < Q; ++r) {
-            if (rows & (1u << r)) {  // warp-uniform
-                const float dx = fmaf(q2x[r], -0.5f, -S.x), dy = fmaf(q2y[r], -0.5f, -S.y),
-                            dz = fmaf(q2z[r], -0.5f, -S.z);
-                const float rr = (dq_l[r] + S.w) * 1.0001f;
-                const float ex = fmaxf(fabsf(dx) - hx, 0.f), ey = fmaxf(fabsf(dy) - hy, 0.f),
-                            ez = fmaxf(fabsf(dz) - hz, 0.f);
-                const float rb = dq_l[r] * 1.0001f;
-                const bool out = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr ||
-                                 fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > rb * rb;
-                if (__any_sync(0xffffffffu, !out)) need |= 1u << r;
-            }
+        for (unsigned m = rows & ((1u << Q) - 1u); m != 0; m &= m - 1) {  // warp-uniform
+            const int r = __ffs(m) - 1;
+            const float dx = ws.qs[0][r * 32 + lane] - S.x, dy = ws.qs[1][r * 32 + lane] - S.y,
+                        dz = ws.qs[2][r * 32 + lane] - S.z;
+            const float rr = (dq_l[r] + S.w) * 1.0001f;
+            const float ex = fmaxf(fabsf(dx) - hx, 0.f), ey = fmaxf(fabsf(dy) - hy, 0.f),
+                        ez = fmaxf(fabsf(dz) - hz, 0.f);
+            const float rb = dq_l[r] * 1.0001f;
+            const bool out = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr ||
+                             fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > rb * rb;
+            if (__any_sync(0xffffffffu, !out)) need |= 1u << r;
         }
         return need;
     };
 
     // ---- seeds: for every query row, the sub-tile whose centre is nearest to the row's --------
     int head = 0, look = 0, tail = 0, nloads = 0, nconsumed = 0;  // FIFO / ring state, warp-uniform
-    int seed[kAnchors];
-#pragma unroll
-    for (int a = 0; a < kAnchors; ++a) seed[a] = -1;
+    if (lane < kAnchors) ws.seed[lane] = -1;
+    __syncwarp();
     if (!all_hinted) {  // (a fully hinted warp already holds near-final bounds)
-        // anchors: the centres of the 8 query rows (a dead row falls back to row 0, which
-        // always holds a live query)
-        float ax[kAnchors], ay[kAnchors], az[kAnchors];
-#pragma unroll
-        for (int a = 0; a < kAnchors; ++a) {
+        // anchors: the centres of the query rows (a dead row falls back to row 0, which always
+        // holds a live query); a run-time loop over the anchors, like everything per row
+#pragma unroll 1
+        for (int a = 0; a < kAnchors && a < p.nanchors; ++a) {
             const float4 R = ws.row[a].w >= 0.f ? ws.row[a] : ws.row[0];
-            ax[a] = R.x; ay[a] = R.y; az[a] = R.z;
-        }
-        u64 bk[kAnchors];
-#pragma unroll
-        for (int a = 0; a < kAnchors; ++a) bk[a] = ~0ull;
-        for (int base = 0; base < stages; base += 32) {
-            const int s = base + lane;
-            if (s < stages) {
-                const float4 S = stage_c[s];
-                if (S.w >= 0.f) {
-#pragma unroll
-                    for (int a = 0; a < kAnchors; ++a) {
-                        const float dx = S.x - ax[a], dy = S.y - ay[a], dz = S.z - az[a];
+            u64 bk = ~0ull;
+            for (int base = 0; base < stages; base += 32) {
+                const int s = base + lane;
+                if (s < stages) {
+                    const float4 S = stage_c[s];
+                    if (S.w >= 0.f) {
+                        const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
                         const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                         const u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(unsigned)s;
-                        bk[a] = key < bk[a] ? key : bk[a];
+                        bk = key < bk ? key : bk;
                     }
                 }
             }
-        }
-#pragma unroll
-        for (int a = 0; a < kAnchors; ++a) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                const u64 other = __shfl_xor_sync(0xffffffffu, bk[a], o);
-                bk[a] = other < bk[a] ? other : bk[a];
+                const u64 other = __shfl_xor_sync(0xffffffffu, bk, o);
+                bk = other < bk ? other : bk;
             }
-            int st = (int)(unsigned)(bk[a] & 0xffffffffull);
+            int st = (int)(unsigned)(bk & 0xffffffffull);
             if (st >= stages) st = 0;
             // nearest sub-tile centre inside that stage
             u64 key = ~0ull;
             if (lane < SUBS) {
                 const float4 S = sub_c[(long long)st * SUBS + lane];
                 if (S.w >= 0.f) {
-                    const float dx = S.x - ax[a], dy = S.y - ay[a], dz = S.z - az[a];
+                    const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
                     key = ((u64)__float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) << 32) | (u64)(unsigned)lane;
                 }
             }
@@ -806,23 +837,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
             }
             int sb = (int)(unsigned)(key & 31ull);
             if (key == ~0ull) sb = 0;
-            seed[a] = st * SUBS + sb;
-            bool dup = a >= p.nanchors;
-            if (dup) seed[a] = -1;
-#pragma unroll
-            for (int c = 0; c < a; ++c) dup = dup || seed[c] == seed[a];
+            const int sd = st * SUBS + sb;
+            bool dup = false;
+            for (int c = 0; c < a; ++c) dup = dup || ws.seed[c] == sd;
             if (!dup) {
                 if (lane == 0) {
                     // +inf radius: never ruled out
                     ws.sph[tail % kFifo] = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
-                    ws.id[tail % kFifo] = seed[a];
+                    ws.id[tail % kFifo] = sd;
                     ws.rows[tail % kFifo] = (1u << Q) - 1u;
                     ws.box[tail % kFifo] = kNoBox;
+                    ws.seed[a] = sd;
                 }
                 ++tail;
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
 
     // ---- main loop: ONE code path that either consumes a queued sub-tile or produces more -------
@@ -867,7 +897,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                         const int e = (look + j) % kFifo;
                         S2[k] = ws.sph[e]; id2[k] = ws.id[e]; rows2[k] = ws.rows[e]; box2[k] = ws.box[e];
                         float d = CUDART_INF_F;
-#pragma unroll
+#pragma unroll 1
                         for (int r = 0; r < Q; ++r) {
                             const float4 R = ws.row[r];
                             const float dx = S2[k].x - R.x, dy = S2[k].y - R.y, dz = S2[k].z - R.z;
@@ -930,12 +960,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                 const float4 *sx = reinterpret_cast<const float4 *>(&ws.buf[slot][0][0]);
 #pragma unroll 1
                 for (int h = 0; h < SUB / FLAG; ++h)
-                    scan_subtile<Q, FLAG, UNR, true, PARTS>(p, gq, gt, q0, lane, sx + h * (FLAG / 4),
+                    scan_subtile_pruned<Q, FLAG, UNR, PARTS>(p, gq, gt, q0, lane, sx + h * (FLAG / 4),
                                                      sx + SUB / 4 + h * (FLAG / 4),
                                                      sx + 2 * (SUB / 4) + h * (FLAG / 4),
                                                      sx + 3 * (SUB / 4) + h * (FLAG / 4), id * SUB + h * FLAG,
-                                                     q2x, q2y, q2z, thr, mt_l, thr_l, tm_l, Dbest_l, ibest_l,
-                                                     dq_l, dmax, nflag, npass, &ws.qs[0][0], rows_e);
+                                                     mt_l, thr_l, tm_l, Dbest_l, ibest_l, dq_l, dmax, nflag,
+                                                     npass, &ws.qs[0][0], rows_e);
                 ++nconsumed;
                 __syncwarp();  // every lane is done with the slot before lane 0 refills it
             }
@@ -988,7 +1018,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                 if (sub_h != nullptr) hb = sub_h[gid];
                 rows = coarse_rows_box(S, hb);
 #pragma unroll
-                for (int a = 0; a < kAnchors; ++a) rows = gid == seed[a] ? 0u : rows;  // already scanned
+                for (int a = 0; a < kAnchors; ++a) rows = gid == ws.seed[a] ? 0u : rows;  // already scanned
             }
             const unsigned m32 = __ballot_sync(0xffffffffu, rows != 0);
             if (rows != 0) {
@@ -1017,6 +1047,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                                        (unsigned long long)(ntests & 0xFFFFFFu));
     }
 
+#pragma unroll 1
     for (int r = 0; r < Q; ++r) {
         const int i = q0 + r * 32;
         if ((livemask >> r) & 1u) {
@@ -1200,6 +1231,16 @@ struct NN2PrunedVariant {
 
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
         auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS>;
+        static thread_local int configured_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (configured_dev != dev) {
+            // MINB single-warp CTAs of ~10 KB each only fit with the largest shared-memory carve-out
+            ISR_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                    (int)cudaSharedmemCarveoutMaxShared),
+                               "nn2 pruned carve-out"));
+            configured_dev = dev;
+        }
         ProfScope prof(kProfNN, st);
         // the lo planes of the query copy (last 3 KB of the per-warp block) are only touched
         // when the search uses the lo parts
@@ -1219,7 +1260,7 @@ struct NN2PrunedVariant {
 // only those -- removes 3/4 of the resolve's pass-1 instructions but was measured 2 % slower
 // on the verification workload and equal on the ICP search: the kernel is bound by the
 // latency of its serial phases at 4 warps per scheduler, not by instruction count)
-using NN2Pruned = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 1>;
+using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1>;
 #ifdef ISR_NN_TUNING
 using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 2>;
 using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 4>;
