@@ -756,14 +756,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     };
     // exact test, one query per lane and row: is any query of `rows` not ruled out?
     auto exact_any = [&](const float4 S, unsigned rows) {
+        float dq[Q];  // (unrolled with the bounds loaded together, like exact_rows_box below)
+#pragma unroll
+        for (int r = 0; r < Q; ++r) dq[r] = dq_l[r];
         bool need = false;
-        for (unsigned m = rows & ((1u << Q) - 1u); m != 0; m &= m - 1) {  // warp-uniform
-            const int r = __ffs(m) - 1;
-            const float dx = ws.qs[0][r * 32 + lane] - S.x, dy = ws.qs[1][r * 32 + lane] - S.y,
-                        dz = ws.qs[2][r * 32 + lane] - S.z;
-            const float rr = (dq_l[r] + S.w) * 1.0001f;
-            // a dead query slot (dq = 0, padded coordinates ~1e18) is always ruled out
-            need = need || !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr);
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            if (rows & (1u << r)) {  // warp-uniform
+                const float dx = ws.qs[0][r * 32 + lane] - S.x, dy = ws.qs[1][r * 32 + lane] - S.y,
+                            dz = ws.qs[2][r * 32 + lane] - S.z;
+                const float rr = (dq[r] + S.w) * 1.0001f;
+                // a dead query slot (dq = 0, padded coordinates ~1e18) is always ruled out
+                need = need || !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr);
+            }
         }
         return __any_sync(0xffffffffu, need);
     };
@@ -775,18 +780,26 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         const float sc = S.w * (1.00001f / 1023.f);
         const float hx = (float)(hb & 1023u) * sc, hy = (float)((hb >> 10) & 1023u) * sc,
                     hz = (float)((hb >> 20) & 1023u) * sc;
+        // (the one per-row loop that stays unrolled: it runs ~60 times per warp, and with a
+        // run-time row index every row waited for its own bound from local memory -- 7.5 % of
+        // all samples on that one load; here the eight loads go out together)
+        float dq[Q];
+#pragma unroll
+        for (int r = 0; r < Q; ++r) dq[r] = dq_l[r];
         unsigned need = 0;
-        for (unsigned m = rows & ((1u << Q) - 1u); m != 0; m &= m - 1) {  // warp-uniform
-            const int r = __ffs(m) - 1;
-            const float dx = ws.qs[0][r * 32 + lane] - S.x, dy = ws.qs[1][r * 32 + lane] - S.y,
-                        dz = ws.qs[2][r * 32 + lane] - S.z;
-            const float rr = (dq_l[r] + S.w) * 1.0001f;
-            const float ex = fmaxf(fabsf(dx) - hx, 0.f), ey = fmaxf(fabsf(dy) - hy, 0.f),
-                        ez = fmaxf(fabsf(dz) - hz, 0.f);
-            const float rb = dq_l[r] * 1.0001f;
-            const bool out = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr ||
-                             fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > rb * rb;
-            if (__any_sync(0xffffffffu, !out)) need |= 1u << r;
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            if (rows & (1u << r)) {  // warp-uniform
+                const float dx = ws.qs[0][r * 32 + lane] - S.x, dy = ws.qs[1][r * 32 + lane] - S.y,
+                            dz = ws.qs[2][r * 32 + lane] - S.z;
+                const float rr = (dq[r] + S.w) * 1.0001f;
+                const float ex = fmaxf(fabsf(dx) - hx, 0.f), ey = fmaxf(fabsf(dy) - hy, 0.f),
+                            ez = fmaxf(fabsf(dz) - hz, 0.f);
+                const float rb = dq[r] * 1.0001f;
+                const bool out = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr ||
+                                 fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > rb * rb;
+                if (__any_sync(0xffffffffu, !out)) need |= 1u << r;
+            }
         }
         return need;
     };
