@@ -1275,8 +1275,8 @@ struct NN2PrunedVariant {
 // latency of its serial phases at 4 warps per scheduler, not by instruction count)
 using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1>;
 #ifdef ISR_NN_TUNING
-using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 2>;
-using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 16, 1, 64, 4>;
+using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 2>;
+using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 4>;
 using NN2PrunedU2 = NN2PrunedVariant<8, 1, 64, 16, 2, 64, 1>;
 using NN2PrunedU4 = NN2PrunedVariant<8, 1, 64, 16, 4, 64, 1>;
 #endif
