@@ -79,6 +79,7 @@ SIGNATURES = {
     "isr_spatial_order_workspace_bytes": (_SZ, [_I64]),
     "isr_spatial_order": (_I, [_P, _I64, _P, _P, _SZ, _P]),
     "isr_prepare_cloud": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
+    "isr_stage_sphere_count": (_I64, [_I64]),
     "isr_tile_spheres": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),
     "isr_set_nn_pruning": (_I, [_I]),
     "isr_get_nn_pruning": (_I, []),

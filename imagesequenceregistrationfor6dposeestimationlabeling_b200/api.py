@@ -147,7 +147,7 @@ class SoaCloud:
     n: int
     centroid: Optional[torch.Tensor] = None
     perm: Optional[torch.Tensor] = None      # int32 [n]: stored position -> original index
-    stage_c: Optional[torch.Tensor] = None   # float32 [B, npad/1024, 4] stage spheres (c, r)
+    stage_c: Optional[torch.Tensor] = None   # float32 [B, npad/1024 + chunks, 4] stage, then chunk spheres (c, r)
     sub_c: Optional[torch.Tensor] = None     # float32 [B, npad/64, 4] sub-tile spheres
     sub_box: Optional[torch.Tensor] = None   # int32 [B, npad/64] packed half-extents of the sub-tile boxes
 
@@ -247,7 +247,7 @@ def prepare_cloud(points, poses=None, centroid=None, centre_poses=None, perm=Non
             _stream()))
     sc = sub = box = None
     if stage_centroids:
-        sc = torch.empty((b, npad // _lib.ISR_SOA_TILE, 4), dtype=torch.float32, device=device)
+        sc = torch.empty((b, lib.isr_stage_sphere_count(npad), 4), dtype=torch.float32, device=device)
         sub = torch.empty((b, npad // _lib.ISR_SUB_TILE, 4), dtype=torch.float32, device=device)
         box = torch.empty((b, npad // _lib.ISR_SUB_TILE), dtype=torch.int32, device=device)
         for b0 in range(0, b, 65535):

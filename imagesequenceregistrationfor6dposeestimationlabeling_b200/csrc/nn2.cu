@@ -880,14 +880,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     unsigned refreshed_at = ~0u;
     bool sorted = p.sort_fifo == 0;
     bool seeding = true;   // the seeds must be scanned before anything is produced
-    int base = 0;          // next chunk of stage spheres
-    int cbase = 0;         // base of the chunk whose candidates are in smask
+    const int nchunks = (stages + 31) / 32;
+    int gchunk = 0;        // next group of 32 chunk spheres (a chunk = 32 stages)
+    int cgroup = 0;        // first chunk of the group whose candidates are in cmask
+    unsigned cmask = 0;    // candidate chunks of the current group not yet expanded
+    int cbase = 0;         // first stage of the chunk whose candidates are in smask
     unsigned smask = 0;    // candidate stages of the current chunk not yet expanded
     float4 Sst = make_float4(0.f, 0.f, 0.f, -1.f);  // this lane's stage sphere of the chunk
     unsigned rows_st = 0;                           // and its coarse row mask
     for (;;) {
         const int pending = tail - head;
-        const bool produced_all = smask == 0 && base >= stages;
+        const bool produced_all = smask == 0 && cmask == 0 && gchunk >= nchunks;
         if (produced_all && !sorted) {
             // Everything is queued: put the untested entries in nearest-first order (squared
             // distance between the sub-tile's centre and the nearest of the query rows it may
@@ -988,13 +991,28 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         seeding = false;
         if (produced_all) break;
         if (smask == 0) {
-            // next chunk: refresh the row bounds (if any scan ran since), coarse-test 32 stage spheres
+            // refresh the row bounds (if any scan ran since)
             if (nscanned != refreshed_at) {
                 refresh_bounds();
                 refreshed_at = nscanned;
             }
-            cbase = base;
-            base += 32;
+            if (cmask == 0) {
+                // next group: coarse-test 32 chunk spheres, one per lane (a chunk sphere bounds
+                // the spheres of 32 consecutive stages)
+                cgroup = gchunk;
+                gchunk += 32;
+                if (nchunks <= 8) {  // a small target (<= 256 k points): its few chunks are all walked
+                    cmask = (1u << nchunks) - 1u;
+                    continue;
+                }
+                const int c = cgroup + lane;
+                const float4 C = stage_c[stages + min(c, nchunks - 1)];
+                cmask = __ballot_sync(0xffffffffu, c < nchunks && coarse_rows(C) != 0);
+                continue;
+            }
+            // next candidate chunk: coarse-test its 32 stage spheres
+            cbase = (cgroup + __ffs(cmask) - 1) * 32;
+            cmask &= cmask - 1;
             const int s = cbase + lane;
             Sst = stage_c[min(s, stages - 1)];
             rows_st = s < stages ? coarse_rows(Sst) : 0u;
@@ -1361,7 +1379,7 @@ static int nn2_dispatch(const NN2Call &c) {
     // stage centroids are laid out per 1024-point SoA tile; only usable when the kernel's
     // stage is that tile
     p.stage_c = (V::kStage == ISR_SOA_TILE) ? reinterpret_cast<const float4 *>(c.t->stage_c) : nullptr;
-    p.stage_c_bstride = c.t->bstride == 0 ? 0 : c.t->npad / ISR_SOA_TILE;
+    p.stage_c_bstride = c.t->bstride == 0 ? 0 : isr_stage_sphere_count(c.t->npad);
     p.perm_q = c.q->perm; p.perm_t = c.t->perm;
     p.sub_c = reinterpret_cast<const float4 *>(c.t->sub_c);
     p.sub_c_bstride = c.t->bstride == 0 ? 0 : c.t->npad / ISR_SUB_TILE;

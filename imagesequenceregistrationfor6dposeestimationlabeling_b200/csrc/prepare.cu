@@ -142,7 +142,7 @@ prepare_soa7_kernel(const float *__restrict__ pts, const float *__restrict__ pts
 // owns points 4t..4t+3 of the stage, so a sub-tile is 16 consecutive lanes.
 __global__ void __launch_bounds__(256)
 tile_spheres_kernel(const float *__restrict__ soa7, int64_t n, int64_t npad, int64_t bstride,
-                    float4 *__restrict__ out_stage, float4 *__restrict__ out_sub,
+                    float4 *__restrict__ out_stage, int stage_total, float4 *__restrict__ out_sub,
                     uint32_t *__restrict__ out_box) {
     constexpr int kSubs = ISR_SOA_TILE / ISR_SUB_TILE;  // 16
     __shared__ float red[6][8];
@@ -250,15 +250,52 @@ tile_spheres_kernel(const float *__restrict__ soa7, int64_t n, int64_t npad, int
     if (t == 0) {
 #pragma unroll
         for (int w = 1; w < 8; ++w) m = fmaxf(m, rmax[w]);
-        out_stage[(int64_t)b * gridDim.x + s] =
+        out_stage[(int64_t)b * stage_total + s] =
             any ? make_float4(cx, cy, cz, inflate(m, cx, cy, cz))
                 : make_float4(ISR_PAD_COORD, ISR_PAD_COORD, ISR_PAD_COORD, -1.f);
     }
 }
 
+// one warp per (chunk of 32 stages, batch item): the sphere that bounds the chunk's stage
+// spheres -- centre of the box around them, radius max(|c_i - c| + r_i), rounded up
+__global__ void __launch_bounds__(32)
+chunk_spheres_kernel(float4 *__restrict__ stage, int stages, int total) {
+    const int c = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+    float4 *st = stage + (int64_t)b * total;
+    const int s = c * 32 + lane;
+    float4 S = make_float4(0.f, 0.f, 0.f, -1.f);
+    if (s < stages) S = st[s];
+    const bool ok = S.w >= 0.f;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {ok ? S.x - S.w : inf, ok ? S.y - S.w : inf, ok ? S.z - S.w : inf};
+    float hi[3] = {ok ? S.x + S.w : -inf, ok ? S.y + S.w : -inf, ok ? S.z + S.w : -inf};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+    }
+    const bool any = lo[0] <= hi[0];
+    const float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
+    const float dx = S.x - cx, dy = S.y - cy, dz = S.z - cz;
+    float r = ok ? __fsqrt_ru(dx * dx + dy * dy + dz * dz) * 1.00001f + S.w : -1.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if (lane == 0)
+        st[stages + c] = any ? make_float4(cx, cy, cz, r * 1.00001f + 1e-37f)
+                             : make_float4(ISR_PAD_COORD, ISR_PAD_COORD, ISR_PAD_COORD, -1.f);
+}
+
 }  // namespace isr
 
 extern "C" {
+
+int64_t isr_stage_sphere_count(int64_t npad) {
+    const int64_t stages = npad / ISR_SOA_TILE;
+    return stages + (stages + 31) / 32;
+}
 
 int isr_centroid(const float *pts, int64_t n, double *out3, void *stream) {
     using namespace isr;
@@ -280,10 +317,16 @@ int isr_tile_spheres(const float *soa7, int64_t n, int64_t npad, int64_t bstride
                 ISR_E_ALIGN, "tile_spheres: pointers must be 16-byte aligned");
     dim3 grid((unsigned)(npad / ISR_SOA_TILE), (unsigned)batch);
     ProfScope prof(kProfTransform, (cudaStream_t)stream);
+    const int stages = (int)(npad / ISR_SOA_TILE);
+    const int total = (int)isr_stage_sphere_count(npad);
     tile_spheres_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        soa7, n, npad, bstride, reinterpret_cast<float4 *>(out_stage), reinterpret_cast<float4 *>(out_sub),
+        soa7, n, npad, bstride, reinterpret_cast<float4 *>(out_stage), total, reinterpret_cast<float4 *>(out_sub),
         out_box);
-    return launched("tile_spheres_kernel");
+    ISR_TRY(launched("tile_spheres_kernel"));
+    dim3 cgrid((unsigned)(total - stages), (unsigned)batch);
+    chunk_spheres_kernel<<<cgrid, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4 *>(out_stage), stages,
+                                                                total);
+    return launched("chunk_spheres_kernel");
 }
 
 int isr_prepare_cloud(const float *pts, const float *pts_lo, const int32_t *perm, int64_t n,

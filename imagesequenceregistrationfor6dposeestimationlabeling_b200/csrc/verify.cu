@@ -108,8 +108,8 @@ static VerifyLayout verify_layout(int64_t nq, int64_t nt, int64_t b, int bidirec
     L.centroid = off; off += 256;
     L.perm_q = off; off += align256((size_t)nq * 4);
     L.perm_t = off; off += align256((size_t)nt * 4);
-    L.stage_x = off; off += align256((size_t)L.chunk * (nqp / ISR_SOA_TILE) * 16);
-    L.stage_y = off; off += align256((size_t)L.chunk * (ntp / ISR_SOA_TILE) * 16);
+    L.stage_x = off; off += align256((size_t)L.chunk * isr_stage_sphere_count(nqp) * 16);
+    L.stage_y = off; off += align256((size_t)L.chunk * isr_stage_sphere_count(ntp) * 16);
     L.sub_x = off; off += align256((size_t)L.chunk * (nqp / ISR_SUB_TILE) * 16);
     L.sub_y = off; off += align256((size_t)L.chunk * (ntp / ISR_SUB_TILE) * 16);
     L.box_x = off; off += align256((size_t)L.chunk * (nqp / ISR_SUB_TILE) * 4);

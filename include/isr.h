@@ -125,7 +125,10 @@ int isr_prepare_cloud(const float *pts, const float *pts_lo, const int32_t *perm
                       void *stream);
 
 /* Bounding spheres of the stored tiles of a SoA7 cloud, (cx, cy, cz, r) float32 each:
- * out_stage [batch][npad/1024] for the 1024-point stages, out_sub [batch][npad/64] for the
+ * out_stage [batch][isr_stage_sphere_count(npad)]: first the npad/1024 spheres of the
+ * 1024-point stages, then one sphere per chunk of 32 consecutive stages (it bounds the 32
+ * stage spheres; the search tests a chunk before it looks at its stages -- 977 stage spheres
+ * per query block at 1 M target points otherwise); out_sub [batch][npad/64] for the
  * 64-point sub-tiles.  r bounds |p - c| for every real point of the tile, inflated to hold
  * for the FP64 (hi + lo) coordinates; r = -1 marks a tile of padding only.  The search uses
  * them to scan the nearest stage first and to skip tiles that provably cannot hold a
@@ -135,6 +138,7 @@ int isr_prepare_cloud(const float *pts, const float *pts_lo, const int32_t *perm
  * h = r * k / 1023 (rounded up, inflated like r); 0x3FFFFFFF for a tile of padding only.  The
  * patches of a surface cloud are thin sheets: the box follows them where the sphere is mostly
  * empty, and a tile is skipped when either volume is out of reach. */
+int64_t isr_stage_sphere_count(int64_t npad);
 int isr_tile_spheres(const float *soa7, int64_t n, int64_t npad, int64_t bstride, int64_t batch,
                      float *out_stage, float *out_sub, uint32_t *out_box, void *stream);
 
@@ -144,7 +148,8 @@ typedef struct IsrCloud {
     int64_t n;            /* real points                                                      */
     int64_t npad;         /* padded plane length (multiple of ISR_SOA_TILE)                   */
     int64_t bstride;      /* floats between batch items; 0 = one cloud shared by the batch    */
-    const float *stage_c; /* isr_tile_spheres out_stage, or NULL (scan in storage order)      */
+    const float *stage_c; /* isr_tile_spheres out_stage (stage + chunk spheres, batch stride
+                             isr_stage_sphere_count(npad)), or NULL (scan in storage order)   */
     const int32_t *perm;  /* the perm it was prepared with, or NULL; results are reported in
                              original indices either way                                      */
     const float *sub_c;   /* isr_tile_spheres out_sub, or NULL (no tile pruning: every pair is

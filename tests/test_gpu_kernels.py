@@ -181,7 +181,10 @@ def test_tile_spheres_bound_their_points(gpu):
         c = api.prepare_cloud(cloud, P, perm=api.spatial_order(cloud), stage_centroids=True)
         data = c.data.cpu().numpy().astype(np.float64)
         pts = np.moveaxis(data[:, 0:3] + data[:, 4:7], 1, 2)            # [B, npad, 3] hi + lo
-        for spheres, tile in ((c.sub_c.cpu().numpy(), 64), (c.stage_c.cpu().numpy(), 1024)):
+        nst = c.npad // 1024
+        assert c.stage_c.shape == (3, nst + (nst + 31) // 32, 4)
+        chunk = c.stage_c.cpu().numpy().astype(np.float64)[:, nst:]
+        for spheres, tile in ((c.sub_c.cpu().numpy(), 64), (c.stage_c.cpu().numpy()[:, :nst], 1024)):
             nt = c.npad // tile
             assert spheres.shape == (3, nt, 4)
             for b in range(3):
@@ -193,6 +196,14 @@ def test_tile_spheres_bound_their_points(gpu):
                     d = np.linalg.norm(pts[b, lo:hi] - spheres[b, k, :3].astype(np.float64), axis=1)
                     assert d.max() <= spheres[b, k, 3]
                     assert spheres[b, k, 3] <= d.max() * 1.001 + 1e-4 * (1 + abs(offset))
+        # the chunk spheres (32 stages each) bound their points as well
+        for b in range(3):
+            for k in range(chunk.shape[1]):
+                lo, hi = k * 32768, min((k + 1) * 32768, n)
+                if hi <= lo:
+                    assert chunk[b, k, 3] == -1.0
+                    continue
+                assert np.linalg.norm(pts[b, lo:hi] - chunk[b, k, :3], axis=1).max() <= chunk[b, k, 3]
         # the sub-tile boxes: centre = the sphere's, half-extents r * k / 1023 per axis
         sub, box = c.sub_c.cpu().numpy().astype(np.float64), c.sub_box.cpu().numpy().astype(np.int64)
         for b in range(3):
