@@ -14,8 +14,8 @@
 //           |a_j - A_j| <= 13 u R^2 (u = 2^-24, R = |q| + d), proven from the three fma
 //           roundings and the rounding of |p|^2 (clouds are centred by prepare.cu so R is
 //           the object radius, not the camera distance).
-//   flag    per 32-target sub-tile one compare per query: does the sub-tile minimum come
-//           within the window W of the running minimum?  (one FSETP per query per 32 targets)
+//   flag    per 64-target sub-tile one compare per query: does the sub-tile minimum come
+//           within the window W of the running minimum?
 //   resolve only then: re-derive the sub-tile's a_j, and for the targets inside the window
 //           compute the distance EXACTLY in FP64 from the hi/lo coordinates; keep the
 //           smallest (strict <, ascending index => lowest index on exact ties).
@@ -27,22 +27,28 @@
 // The returned index therefore equals the float64 brute-force argmin of the prepared
 // (hi+lo) coordinates; the returned d2 is that FP64 distance rounded once to float32.
 //
-// Pruning (nn2_pruned_kernel).  Clouds are stored in Morton order, so a warp's 256 queries, a
-// 1024-target stage and a 64-target sub-tile are all compact patches.  Every query carries
-// dq >= its exact best distance so far (FP64 Dbest from the resolve path, rounded up, plus
-// the size of its lo part); a tile with sphere (c, r) is skipped by a warp iff for every
-// query |q - c| > dq + r (evaluated in FP32 with a 1e-4 relative margin, the sphere radius
-// being inflated by prepare.cu for rounding and for the targets' lo parts): then every point
-// of the tile is strictly farther than the neighbour already held, so it can be neither the
-// minimum nor an equal-distance tie.  Every warp works on its own (no CTA barrier, its own
-// shared-memory ring fed by 1-D bulk copies): (1) seeds -- for four anchor queries spread
-// over its block, the sub-tile whose centre is nearest (via the nearest stage), scanned
-// first so that every query holds a near-final bound even when the block straddles a jump
-// of the Z-curve; (2) one pass over the stage spheres, keeping the stages that come within
-// the warp-wide bound of the warp's query sphere; their sub-tile spheres pass the same
-// coarse test into a FIFO; (3) each FIFO entry gets the exact per-query test with the
-// bounds of that moment and is scanned only if it survives.  Loads are issued up to four
-// entries ahead.
+// Pruning (nn2_pruned_kernel).  Clouds are stored along a Hilbert curve (sort.cu), so a warp's
+// 256 queries, a 1024-target stage and a 64-target sub-tile are all compact patches.  Every
+// query carries dq >= its exact best distance so far (FP64 Dbest from the resolve path, rounded
+// up, plus the size of its lo part).  A tile with sphere (c, r) is skipped for a query iff
+// |q - c| > dq + r, a sub-tile also iff dist(q, box) > dq for its axis-aligned box (both in
+// FP32 with a 1e-4 relative margin; radius and half-extents are inflated by prepare.cu for
+// rounding and for the targets' lo parts): every point of the tile is then strictly farther
+// than the neighbour already held, so it can be neither the minimum nor an equal-distance
+// tie.  Every warp works on its own (one warp per CTA, no barrier, its own shared-memory ring
+// fed by 1-D bulk copies):
+//   (1) starting bounds: the caller's hints (ICP: the previous iteration's neighbours), else
+//       seeds -- for the centre of each of its 8 query rows the sub-tile whose centre is
+//       nearest (via the nearest stage), scanned first;
+//   (2) a three-level walk over the target's spheres, coarse tests against the 8 query-ROW
+//       spheres first (one sphere per lane): chunk spheres (32 stages each) -> stage spheres
+//       -> per candidate stage the exact per-query test, then its 16 sub-tile spheres / boxes
+//       -> FIFO entries with the mask of rows they may matter to;
+//   (3) when everything is queued, the entries are put in nearest-first order;
+//   (4) each entry gets the exact per-query test with the bounds of that moment (which also
+//       yields the rows that still need it); a survivor's 1 KB bulk copy is issued at once, up
+//       to four entries ahead of the scan, and it is scanned for the halves (rows 0-3, 4-7)
+//       that need it.
 // The exactness argument above is untouched: the true neighbour's tile is never skipped
 // (its distance is <= every bound), so it is visited, flagged and resolved as before.
 //
