@@ -192,7 +192,10 @@ class PeerExchange:
     a small buffer in this GPU's HBM that every peer maps through CUDA IPC and writes over
     NVLink.  The IPC handles travel once through torch.distributed (all_gather, any backend);
     the loop itself contains no collective call.  Collective: every rank of `group` must
-    construct it, and `close()` it, at the same point."""
+    construct it, and `close()` it, at the same point.  Construction never raises half-way
+    through its collectives: every rank takes part in all of them and the ranks agree on the
+    outcome -- `ok` is the same everywhere, `error` says what went wrong on this rank (or that
+    a peer failed)."""
 
     def __init__(self, group=None):
         import ctypes
@@ -204,33 +207,63 @@ class PeerExchange:
             self.rank, self.world = td.get_rank(group), td.get_world_size(group)
         else:
             self.rank, self.world = 0, 1
-        if self.world > _lib.ISR_PEER_MAX_RANKS:
-            raise ValueError(f"PeerExchange: {self.world} ranks > {_lib.ISR_PEER_MAX_RANKS}")
-        lib = _lib.load()
-        self.handle = ctypes.c_void_p()
-        mine = (ctypes.c_ubyte * _lib.ISR_PEER_HANDLE_BYTES)()
-        _lib.check(lib.isr_peer_create(self.rank, self.world, ctypes.byref(self.handle), mine))
+        self.handle, self.ok, self.error = None, False, None
+        nbytes = _lib.ISR_PEER_HANDLE_BYTES
+        mine = (ctypes.c_ubyte * nbytes)()
+        try:
+            if self.world > _lib.ISR_PEER_MAX_RANKS:
+                raise ValueError(f"{self.world} ranks > {_lib.ISR_PEER_MAX_RANKS}")
+            h = ctypes.c_void_p()
+            _lib.check(_lib.load().isr_peer_create(self.rank, self.world, ctypes.byref(h), mine))
+            self.handle = h
+        except Exception as e:  # noqa: BLE001 -- agreed with the peers below
+            self.error = e
         handles = bytes(mine)
         if self.world > 1:
             # rides on whatever backend the group has; a byte tensor on the group's device
             dev = (torch.device("cuda", torch.cuda.current_device())
                    if td.get_backend(group) == "nccl" else torch.device("cpu"))
             t = torch.frombuffer(bytearray(handles), dtype=torch.uint8).to(dev)
-            out = torch.empty((self.world * len(handles),), dtype=torch.uint8, device=dev)
+            out = torch.empty((self.world * nbytes,), dtype=torch.uint8, device=dev)
             td.all_gather_into_tensor(out, t, group=group)
             handles = bytes(out.cpu().numpy().tobytes())
-        buf = (ctypes.c_ubyte * len(handles)).from_buffer_copy(handles)
-        _lib.check(lib.isr_peer_connect(self.handle, buf))
+        if self._agree(self.handle is not None):
+            try:
+                buf = (ctypes.c_ubyte * len(handles)).from_buffer_copy(handles)
+                _lib.check(_lib.load().isr_peer_connect(self.handle, buf))
+                connected = True
+            except Exception as e:  # noqa: BLE001
+                self.error, connected = e, False
+            self.ok = self._agree(connected)
+        if not self.ok:
+            if self.error is None:
+                self.error = RuntimeError("a peer rank could not create or map the exchange buffers")
+            self._release()
 
-    def close(self) -> None:
+    def _agree(self, flag: bool) -> bool:
+        """MIN over the ranks of a local success flag."""
+        if self.world == 1:
+            return bool(flag)
+        dev = (torch.device("cuda", torch.cuda.current_device())
+               if td.get_backend(self.group) == "nccl" else torch.device("cpu"))
+        ok = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        td.all_reduce(ok, op=td.ReduceOp.MIN, group=self.group)
+        return bool(int(ok.item()))
+
+    def _release(self) -> None:
         from . import _lib
 
+        if self.handle is not None and self.handle.value:
+            _lib.check(_lib.load().isr_peer_destroy(self.handle))
+        self.handle = None
+
+    def close(self) -> None:
         if self.handle is not None and self.handle.value:
             if self.world > 1:
                 torch.cuda.synchronize()
                 td.barrier(group=self.group)  # no peer may still be writing into this buffer
-            _lib.check(_lib.load().isr_peer_destroy(self.handle))
-            self.handle = None
+            self._release()
+        self.ok = False
 
 
 _peer_cache: dict = {}
@@ -238,37 +271,24 @@ _peer_cache: dict = {}
 
 def peer_exchange(group=None, required: bool = True) -> Optional[PeerExchange]:
     """The process-wide PeerExchange of `group` (created on first use; collective).  The ranks
-    agree on the outcome: if mapping the peers' buffers fails on ANY rank (GPUs without
+    agree on the outcome: if creating or mapping the buffers fails on ANY rank (GPUs without
     peer access, IPC disabled in the container), every rank drops its end and gets None --
     or the error, when `required`."""
     key = id(group) if group is not None else None
     if key not in _peer_cache:
-        px, err = None, None
-        try:
-            px = PeerExchange(group)
-        except Exception as e:  # noqa: BLE001 -- reported below, after the ranks have agreed
-            err = e
-        if td.is_initialized() and td.get_world_size(group) > 1:
-            dev = (torch.device("cuda", torch.cuda.current_device())
-                   if td.get_backend(group) == "nccl" else torch.device("cpu"))
-            ok = torch.tensor([0 if px is None else 1], dtype=torch.int32, device=dev)
-            td.all_reduce(ok, op=td.ReduceOp.MIN, group=group)
-            if int(ok.item()) == 0 and px is not None:
-                px.close()
-                px, err = None, RuntimeError("a peer rank could not map the exchange buffers")
-        _peer_cache[key] = (px, err)
-    px, err = _peer_cache[key]
-    if px is None and required:
-        raise RuntimeError(f"kernel-fused peer exchange unavailable: {err}")
+        _peer_cache[key] = PeerExchange(group)
+    px = _peer_cache[key]
+    if not px.ok:
+        if required:
+            raise RuntimeError(f"kernel-fused peer exchange unavailable: {px.error}")
+        return None
     return px
 
 
 def close_peer_exchanges() -> None:
     """Collective: release every cached PeerExchange (before destroy_process_group)."""
     for key in sorted(_peer_cache, key=lambda k: (k is not None, k)):
-        px, _ = _peer_cache.pop(key)
-        if px is not None:
-            px.close()
+        _peer_cache.pop(key).close()
 
 
 class CudaIcpBackend:

@@ -186,6 +186,9 @@ def _worker(rank, world, port, q):
                           for a in (0.0, 2.0, 0.0)])
         out["multistart"] = dist.multistart_icp_sharded(s5, t5, inits, 20.0, max_iteration=6,
                                                         runner=_oracle_multistart)
+        # no GPU here: creating the peer-memory exchange fails on every rank; the ranks must
+        # walk through its collectives together and agree on "unavailable" (no hang, no raise)
+        out["peer_unavailable"] = dist.peer_exchange(required=False) is None
     finally:
         td.destroy_process_group()
     q.put((rank, out))
@@ -203,6 +206,7 @@ def test_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     for r in (0, 1):
+        assert got[r]["peer_unavailable"] is True
         assert got[r]["tie"] == (2.5, 3)
         assert got[r]["inf"] == (1.25, 9)
     cloud = synth.make_cloud(1500, seed=1)
