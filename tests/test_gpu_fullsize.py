@@ -58,6 +58,31 @@ def test_config2_verification_1k_candidates_100k_points(gpu):
     np.testing.assert_array_equal(res2.losses.cpu().numpy(), losses[perm])   # bit-identical
 
 
+def test_config3_sweep_10k_candidates_100k_points(gpu):
+    """Config 3 on one GPU (the multi-GPU form shards the same call by candidate,
+    tests/test_dist_gpu.py): 10 000 candidates x 100k points.  Planted candidate selected;
+    the oracle checks a seeded subset plus the GPU's top 8; a block of the sweep scored on its
+    own gives bit-identical losses (chunking and launch order do not leak into results)."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    cloud = synth.make_cloud(100000, seed=1)
+    R_true, _ = synth.true_pose(3)
+    Rs, _, k0 = synth.make_candidates(10000, seed=11, R_true=R_true, t_true=np.zeros(3))
+    Mq, Mt = synth.verification_matrices(Rs, R_true)
+    res = gpu.verify_poses(cloud, Mq, Mt, mode="chamfer")
+    losses = res.losses.cpu().numpy()
+    assert losses.shape == (10000,) and np.isfinite(losses).all()
+    assert res.best_index == k0 == int(np.argmin(losses))
+    rng = np.random.default_rng(3)
+    top8 = np.argsort(losses, kind="stable")[:8]
+    sub = np.unique(np.concatenate([[k0], top8, rng.choice(10000, size=6, replace=False)]))
+    ref, _ = oracle.verify_matrices(cloud, cloud, Mq[sub], Mt[sub])
+    np.testing.assert_allclose(losses[sub], ref, rtol=1e-5)
+    assert int(sub[np.argmin(ref)]) == k0
+    blk = slice(4100, 4100 + 300)
+    res2 = gpu.verify_poses(cloud, Mq[blk], Mt[blk], mode="chamfer")
+    np.testing.assert_array_equal(res2.losses.cpu().numpy(), losses[blk])
+
+
 def test_config2_adds_mode_100k_surface(gpu):
     from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
     surface = synth.make_cloud(100000, seed=1)
