@@ -47,7 +47,7 @@
 //   (3) when everything is queued, the entries are put in nearest-first order;
 //   (4) each entry gets the exact per-query test with the bounds of that moment (which also
 //       yields the rows that still need it); a survivor's 1 KB bulk copy is issued at once, up
-//       to four entries ahead of the scan, and it is scanned for the halves (rows 0-3, 4-7)
+//       to four entries ahead of the scan, and it is scanned for the quarters (two rows each)
 //       that need it.
 // The exactness argument above is untouched: the true neighbour's tile is never skipped
 // (its distance is <= every bound), so it is visited, flagged and resolved as before.
@@ -348,12 +348,13 @@ __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__
     }
 }
 
-// The same unit in the pruned search, which scans only the half of the warp's query rows
-// (0-3, 4-7) that the exact test could not rule out (`rows`): an unscanned row keeps tm = +inf
-// and never flags.  The half's operands (-2 q and the thresholds) are fetched for the scan
+// The same unit in the pruned search, which scans only those groups of the warp's query rows
+// (GROUPS = 4: quarters of two rows) in which the exact test could not rule out every row
+// (`rows`): an unscanned row keeps tm = +inf and never flags.  A group's operands (-2 q and the
+// thresholds) are fetched for the scan
 // from the warp's shared-memory copy of its queries (qsm: [6][32 * Q], hi xyz then lo xyz)
 // and from the resolve state, so that they occupy registers only while a scan runs.
-template <int Q, int SUB, int UNR, int PARTS>
+template <int Q, int SUB, int UNR, int PARTS, int GROUPS>
 __device__ __forceinline__ void scan_subtile_pruned(const NN2Params &p, const float *__restrict__ gq,
                                                     const float *__restrict__ gt, int q0, int lane,
                                                     const float4 *sx, const float4 *sy, const float4 *sz,
@@ -361,14 +362,14 @@ __device__ __forceinline__ void scan_subtile_pruned(const NN2Params &p, const fl
                                                     float *tm_l, double *Dbest_l, int *ibest_l, float *dq_l,
                                                     float &dmax, unsigned &nflag, unsigned &npass,
                                                     const float *qsm, unsigned rows) {
-    static_assert(Q == 8, "two halves of four rows");
-    constexpr int H = Q / 2;
+    static_assert(Q == 8 && (GROUPS == 2 || GROUPS == 4 || GROUPS == 8), "halves, quarters or single rows");
+    constexpr int H = Q / GROUPS;
     float tm[Q];
 #pragma unroll
     for (int r = 0; r < Q; ++r) tm[r] = CUDART_INF_F;
     unsigned pflags = 0;  // bit (piece * 8 + row)
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < GROUPS; ++half) {
         if ((rows >> (half * H)) & ((1u << H) - 1u)) {
             float hx[H], hy[H], hz[H], ht[H], tmh[H];
 #pragma unroll
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
         __syncthreads();  // every warp is done with this slot before it is refilled
     }
     if (p.evaluated != nullptr && lane == 0) {
-        atomicAdd(p.evaluated + 0, 2ull * nst * (STAGE / SUB));  // in half units (128 queries x SUB targets)
+        atomicAdd(p.evaluated + 0, 4ull * nst * (STAGE / SUB));  // in quarter units (64 queries x SUB targets)
         atomicAdd(p.evaluated + 1, (unsigned long long)nst);
         atomicAdd(p.evaluated + 4, 1ull);
     }
@@ -582,7 +583,7 @@ struct alignas(128) PrunedWarpSmem {
     float qs[6][32 * Q];       // the warp's queries, hi xyz and lo xyz (read by the scan and the resolve path)
 };
 
-template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS>
+template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS, int GROUPS = 2>
 __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2Params p) {
     static_assert(SUB == ISR_SUB_TILE && ISR_SOA_TILE / SUB == 16 && Q == 8, "pruning uses the spheres of prepare.cu");
     constexpr int SUBS = ISR_SOA_TILE / SUB;
@@ -977,12 +978,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                 mbar_wait(&ws.full[slot], (nconsumed / kRing) & 1);
                 const unsigned rows_e = ws.rows[head % kFifo];
                 ++nscanned;
-                nhalves += ((rows_e & 0x0Fu) ? 1u : 0u) + ((rows_e & 0xF0u) ? 1u : 0u);
+                // counted in half units (4 rows x SUB targets): a quarter (2 rows) is half of one
+                if (GROUPS == 2) {
+                    nhalves += ((rows_e & 0x0Fu) ? 2u : 0u) + ((rows_e & 0xF0u) ? 2u : 0u);
+                } else if (GROUPS == 8) {
+                    nhalves += (unsigned)(__popc(rows_e & 0xFFu) + 1) / 2u;  // (rounded: a row is half a quarter)
+                } else {
+                    nhalves += ((rows_e & 0x03u) ? 1u : 0u) + ((rows_e & 0x0Cu) ? 1u : 0u) +
+                               ((rows_e & 0x30u) ? 1u : 0u) + ((rows_e & 0xC0u) ? 1u : 0u);
+                }
                 // scanned in FLAG-sized pieces (FLAG == SUB in the shipped variant)
                 const float4 *sx = reinterpret_cast<const float4 *>(&ws.buf[slot][0][0]);
 #pragma unroll 1
                 for (int h = 0; h < SUB / FLAG; ++h)
-                    scan_subtile_pruned<Q, FLAG, UNR, PARTS>(p, gq, gt, q0, lane, sx + h * (FLAG / 4),
+                    scan_subtile_pruned<Q, FLAG, UNR, PARTS, GROUPS>(p, gq, gt, q0, lane, sx + h * (FLAG / 4),
                                                      sx + SUB / 4 + h * (FLAG / 4),
                                                      sx + 2 * (SUB / 4) + h * (FLAG / 4),
                                                      sx + 3 * (SUB / 4) + h * (FLAG / 4), id * SUB + h * FLAG,
@@ -1071,7 +1080,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     }
 
     if (p.evaluated != nullptr && lane == 0) {
-        atomicAdd(p.evaluated + 0, (unsigned long long)nhalves);  // scanned half units (4 query rows x SUB targets)
+        atomicAdd(p.evaluated + 0, (unsigned long long)nhalves);  // scanned quarter units (2 query rows x SUB targets)
         atomicAdd(p.evaluated + 1, (unsigned long long)stages);   // stage spheres tested
         atomicAdd(p.evaluated + 2, (unsigned long long)ncand);    // stages that passed
         atomicAdd(p.evaluated + 3, (unsigned long long)ntests);   // exact sub-tile tests
@@ -1259,7 +1268,7 @@ struct NN2Variant {
 using NN2Main = NN2Variant<8, 128, 1024, 3, 64, 4, 1>;
 
 // the pruned kernel: WARPS independent warps of 32 x Q queries per CTA
-template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS>
+template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS, int GROUPS = 2>
 struct NN2PrunedVariant {
     static constexpr int kQueriesPerCta = Q * WARPS * 32;
     static constexpr int kStage = ISR_SOA_TILE;
@@ -1267,7 +1276,7 @@ struct NN2PrunedVariant {
     static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q>);
 
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
-        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS>;
+        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS, GROUPS>;
         static thread_local int configured_dev = -1;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -1297,10 +1306,15 @@ struct NN2PrunedVariant {
 // only those -- removes 3/4 of the resolve's pass-1 instructions but was measured 2 % slower
 // on the verification workload and equal on the ICP search: the kernel is bound by the
 // latency of its serial phases at 4 warps per scheduler, not by instruction count)
-using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1>;
+// (GROUPS: the scan runs per quarter of the query rows (2 rows); halves (4 rows) evaluate 25 %
+// more pairs and were 2 % slower on verification and ICP, 9 % on ADD-S with its sparse queries;
+// single rows evaluate 6 % fewer pairs still but leave one dependent FFMA2 chain per lane: -7 %)
+using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4>;
 #ifdef ISR_NN_TUNING
 using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 2>;
 using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 4>;
+using NN2PrunedG4 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2>;
+using NN2PrunedG8 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 8>;
 using NN2PrunedU2 = NN2PrunedVariant<8, 1, 64, 16, 2, 64, 1>;
 using NN2PrunedU4 = NN2PrunedVariant<8, 1, 64, 16, 4, 64, 1>;
 #endif
@@ -1552,6 +1566,8 @@ int nn2_search(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, 
         if (parts < 0) { const char *e = getenv("ISR_NN_PARTS"); parts = e ? atoi(e) : 1; }
         if (parts == 2) return nn2_dispatch<NN2PrunedP2>(c);
         if (parts == 4) return nn2_dispatch<NN2PrunedP4>(c);
+        if (parts == 24) return nn2_dispatch<NN2PrunedG4>(c);
+        if (parts == 28) return nn2_dispatch<NN2PrunedG8>(c);
         if (parts == 12) return nn2_dispatch<NN2PrunedU2>(c);
         if (parts == 14) return nn2_dispatch<NN2PrunedU4>(c);
 #endif
@@ -1589,8 +1605,8 @@ int isr_profile_nn_pairs(uint64_t *evaluated_host, uint64_t *answered_host) {
         ISR_TRY(check_cuda(cudaMemcpy(&units, ctr, 8, cudaMemcpyDeviceToHost), "profile_nn_pairs read"));
         ISR_TRY(check_cuda(cudaMemset(ctr, 0, 64), "profile_nn_pairs clear"));
     }
-    // counted in half units: 32 x 4 queries against one 64-target sub-tile
-    if (evaluated_host) *evaluated_host = (uint64_t)units * 128ull * (uint64_t)ISR_SUB_TILE;
+    // counted in quarter units: 32 x 2 queries against one 64-target sub-tile
+    if (evaluated_host) *evaluated_host = (uint64_t)units * 64ull * (uint64_t)ISR_SUB_TILE;
     if (answered_host) *answered_host = (uint64_t)g_answered.exchange(0);
     return ISR_OK;
 }

@@ -74,7 +74,7 @@ if "prune" in which:
         _lib.check(lib.isr_profile_nn_counters(c8))
         w = max(c8[4], 1)
         if c8[7]: print(f"   slowest warp: {(c8[7] >> 44) * 1024 / 1e6:.2f} Mcycles, scanned {(c8[7] >> 24) & 0xFFFFF}, exact tests {c8[7] & 0xFFFFFF}")
-        print(f"   per warp: scanned sub-tiles {c8[0]/w/2:.1f}, stage spheres {c8[1]/w:.1f}, stage candidates {c8[2]/w:.1f}, exact sub tests {c8[3]/w:.1f}, flagged units {c8[5]/w:.1f}, resolve passes {c8[6]/w:.1f}; warps {c8[4]}")
+        print(f"   per warp: scanned sub-tiles {c8[0]/w/4:.1f}, stage spheres {c8[1]/w:.1f}, stage candidates {c8[2]/w:.1f}, exact sub tests {c8[3]/w:.1f}, flagged units {c8[5]/w:.1f}, resolve passes {c8[6]/w:.1f}; warps {c8[4]}")
         ev, an = ctypes.c_uint64(0), ctypes.c_uint64(0)
         _lib.check(lib.isr_profile_nn_pairs(ctypes.byref(ev), ctypes.byref(an)))
         return ev.value, an.value

@@ -24,7 +24,7 @@ def counters():
     c8 = (ctypes.c_uint64 * 8)()
     _lib.check(lib.isr_profile_nn_counters(c8))
     w = max(c8[4], 1)
-    s = (f"per warp: scanned {c8[0]/w/2:.1f} (unit equivalents), stage cand {c8[2]/w:.1f}, exact tests {c8[3]/w:.1f}, "
+    s = (f"per warp: scanned {c8[0]/w/4:.1f} (unit equivalents), stage cand {c8[2]/w:.1f}, exact tests {c8[3]/w:.1f}, "
          f"flagged {c8[5]/w:.1f}, resolve passes {c8[6]/w:.1f}; slowest warp {(c8[7] >> 44) * 1024 / 1e6:.2f} Mcyc "
          f"scanned {(c8[7] >> 24) & 0xFFFFF}")
     ev, an = ctypes.c_uint64(0), ctypes.c_uint64(0)

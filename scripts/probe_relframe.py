@@ -21,7 +21,7 @@ def counters():
     c8 = (ctypes.c_uint64 * 8)()
     _lib.check(lib.isr_profile_nn_counters(c8))
     w = max(c8[4], 1)
-    s = f"scanned {c8[0]/w/2:.1f} unit-eq, exact tests {c8[3]/w:.1f}, flagged {c8[5]/w:.1f}, passes {c8[6]/w:.1f}"
+    s = f"scanned {c8[0]/w/4:.1f} unit-eq, exact tests {c8[3]/w:.1f}, flagged {c8[5]/w:.1f}, passes {c8[6]/w:.1f}"
     ev, an = ctypes.c_uint64(0), ctypes.c_uint64(0)
     _lib.check(lib.isr_profile_nn_pairs(ctypes.byref(ev), ctypes.byref(an)))
     return s
