@@ -362,7 +362,7 @@ __device__ __forceinline__ void scan_subtile_pruned(const NN2Params &p, const fl
                                                     float *tm_l, double *Dbest_l, int *ibest_l, float *dq_l,
                                                     float &dmax, unsigned &nflag, unsigned &npass,
                                                     const float *qsm, unsigned rows) {
-    static_assert(Q == 8 && (GROUPS == 2 || GROUPS == 4 || GROUPS == 8), "halves, quarters or single rows");
+    static_assert(Q == 8 && (GROUPS == 2 || GROUPS == 4), "halves of four rows or quarters of two");
     constexpr int H = Q / GROUPS;
     float tm[Q];
 #pragma unroll
@@ -981,8 +981,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                 // counted in half units (4 rows x SUB targets): a quarter (2 rows) is half of one
                 if (GROUPS == 2) {
                     nhalves += ((rows_e & 0x0Fu) ? 2u : 0u) + ((rows_e & 0xF0u) ? 2u : 0u);
-                } else if (GROUPS == 8) {
-                    nhalves += (unsigned)(__popc(rows_e & 0xFFu) + 1) / 2u;  // (rounded: a row is half a quarter)
                 } else {
                     nhalves += ((rows_e & 0x03u) ? 1u : 0u) + ((rows_e & 0x0Cu) ? 1u : 0u) +
                                ((rows_e & 0x30u) ? 1u : 0u) + ((rows_e & 0xC0u) ? 1u : 0u);
@@ -1309,12 +1307,16 @@ struct NN2PrunedVariant {
 // (GROUPS: the scan runs per quarter of the query rows (2 rows); halves (4 rows) evaluate 25 %
 // more pairs and were 2 % slower on verification and ICP, 9 % on ADD-S with its sparse queries;
 // single rows evaluate 6 % fewer pairs still but leave one dependent FFMA2 chain per lane: -7 %)
+// (but a scan that needs most rows costs ~40 % more in two-row pieces -- twice the shared-memory
+// reads per FFMA2, two dependent chains per lane instead of four: the multi-start ICP batch,
+// whose starts are mostly far from aligned, took 0.40 s with quarters against 0.27 s with
+// halves, so a batched ICP search uses the halves; choosing per half at run time -- 4-row scan
+// when both quarters are needed -- kept config 5 at 0.30 s but gave the 4 % on verification back)
 using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4>;
+using NN2PrunedHalves = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2>;
 #ifdef ISR_NN_TUNING
 using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 2>;
 using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 4>;
-using NN2PrunedG4 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2>;
-using NN2PrunedG8 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 8>;
 using NN2PrunedU2 = NN2PrunedVariant<8, 1, 64, 16, 2, 64, 1>;
 using NN2PrunedU4 = NN2PrunedVariant<8, 1, 64, 16, 4, 64, 1>;
 #endif
@@ -1566,11 +1568,12 @@ int nn2_search(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, 
         if (parts < 0) { const char *e = getenv("ISR_NN_PARTS"); parts = e ? atoi(e) : 1; }
         if (parts == 2) return nn2_dispatch<NN2PrunedP2>(c);
         if (parts == 4) return nn2_dispatch<NN2PrunedP4>(c);
-        if (parts == 24) return nn2_dispatch<NN2PrunedG4>(c);
-        if (parts == 28) return nn2_dispatch<NN2PrunedG8>(c);
+        if (parts == 24) return nn2_dispatch<NN2PrunedHalves>(c);
         if (parts == 12) return nn2_dispatch<NN2PrunedU2>(c);
         if (parts == 14) return nn2_dispatch<NN2PrunedU4>(c);
 #endif
+        // a batch of hinted searches = multi-start ICP: scan-heavy, see NN2PrunedHalves
+        if (q->hint != nullptr && batch > 1) return nn2_dispatch<NN2PrunedHalves>(c);
         return nn2_dispatch<NN2Pruned>(c);
     }
     return nn2_dispatch<NN2Main>(c);
