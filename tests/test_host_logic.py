@@ -77,6 +77,13 @@ def test_argument_validation_needs_no_gpu():
                                  None) == -1
     assert lib.isr_spatial_order(None, 5, None, None, 0, None) == -1
     assert lib.isr_spatial_order_workspace_bytes(100000) >= 131072 * 8
+    # stage spheres + one chunk sphere per 32 stages
+    assert [lib.isr_stage_sphere_count(1024 * k) for k in (1, 32, 33, 977)] == [2, 33, 35, 977 + 31]
+    assert lib.isr_pnp_score(None, None, 5, None, None, 3, 2.0, None, None, None) == -1
+    assert lib.isr_pnp_score(None, None, -1, None, None, 3, 2.0, None, None, None) == -2
+    assert lib.isr_peer_create(3, 2, None, None) == -1
+    assert lib.isr_icp_run_sharded(None, 1, None, None, None, 1, 1, None, None, None, 20.0, 1, 0.0, 0.0, None,
+                                   None, None, None, 0, None, None) == -1
     with pytest.raises(_lib.IsrError):
         _lib.check(-3)
 

@@ -121,6 +121,41 @@ def test_umeyama_recovers_exact_motion_and_fixes_reflection():
     np.testing.assert_allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-12)
 
 
+def test_umeyama_equals_an_independent_kabsch():
+    """The Open3D half of the oracle has no golden vectors (Open3D is not installable here), so
+    its rigid estimation is also checked against an implementation that shares no code with
+    it: scipy's Rotation.align_vectors (Kabsch on centred vectors) on noisy correspondences."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(11)
+    for n, noise in ((50, 0.0), (400, 0.5), (3000, 3.0)):
+        src = rng.normal(scale=40, size=(n, 3))
+        R = synth.random_rotation(rng)
+        dst = src @ R.T + np.array([5.0, -2.0, 700.0]) + rng.normal(scale=noise, size=(n, 3))
+        T = oracle.umeyama(src, dst)
+        rot, _ = Rotation.align_vectors(dst - dst.mean(0), src - src.mean(0))
+        np.testing.assert_allclose(T[:3, :3], rot.as_matrix(), atol=1e-9)
+        np.testing.assert_allclose(T[:3, 3], dst.mean(0) - rot.as_matrix() @ src.mean(0), atol=1e-7)
+
+
+def test_evaluate_registration_equals_bruteforce_definition():
+    """fitness / inlier_rmse / correspondence set straight from their definitions with the C
+    brute-force nearest neighbour (no tree): strict d < threshold, one row per inlier."""
+    src, tgt, _ = synth.icp_pair(700, 900, 6, 7, angle_deg=4.0, shift_mm=6.0)
+    T = synth.pose_matrix(synth.rotvec_to_matrix([0.02, -0.01, 0.03]), [0.5, -0.3, 0.2])
+    thr = 2.0
+    r = oracle.evaluate_registration(src, tgt, thr, T)
+    moved = (src.astype(np.float64) @ T[:3, :3].T + T[:3, 3])
+    d2 = ((moved[:, None, :] - tgt.astype(np.float64)[None, :, :]) ** 2).sum(-1)
+    j = d2.argmin(1)
+    dmin = np.sqrt(d2[np.arange(len(src)), j])
+    keep = dmin < thr
+    assert 0 < keep.sum() < len(src)
+    assert r.fitness == keep.sum() / len(src)
+    np.testing.assert_allclose(r.inlier_rmse, np.sqrt((dmin[keep] ** 2).mean()), rtol=1e-12)
+    np.testing.assert_array_equal(np.asarray(r.correspondence_set),
+                                  np.stack([np.nonzero(keep)[0], j[keep]], axis=1))
+
+
 # ---- KAT 5-7: ICP -------------------------------------------------------------------------
 def test_icp_recovers_small_motion():
     tgt = synth.make_cloud(8000, seed=8)
