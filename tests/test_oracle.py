@@ -282,3 +282,53 @@ def test_pnp_inliers_known_answers():
     m = oracle.pnp_inliers(np.array([[0.001, 0.0, 0.0]], dtype=np.float32), np.array([[321.0, 240.0]]), cam, R,
                            np.zeros(3), 0.5)
     assert m[0]
+
+
+# ---- size-independent properties of the restated path (seeded, small) ----------------------
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_chamfer_is_symmetric_and_rigid_invariant(seed):
+    """Chamfer(a, b) = Chamfer(b, a); moving BOTH clouds by the same rigid motion changes
+    nothing (to rounding) -- what lets verification work in any frame."""
+    rng = np.random.default_rng(seed)
+    a = synth.make_cloud(900, seed=20 + seed).astype(np.float64)
+    b = synth.make_cloud(1100, seed=30 + seed).astype(np.float64) + rng.normal(scale=0.5, size=3)
+    c0 = oracle.chamfer(a, b)
+    assert c0 == oracle.chamfer(b, a)
+    R, t = synth.random_rotation(rng), rng.normal(scale=300, size=3)
+    np.testing.assert_allclose(oracle.chamfer(a @ R.T + t, b @ R.T + t), c0, rtol=1e-10)
+    assert oracle.chamfer(a, a) == 0.0
+
+
+def test_icp_result_is_a_fixed_point_of_evaluation():
+    """The registration result is the evaluation AFTER the last update (upstream's loop):
+    evaluating its transformation again reproduces fitness, rmse and the correspondence set,
+    and restarting ICP from it converges at once without moving."""
+    src, tgt, _ = synth.icp_pair(1500, 1800, 6, 7)
+    r = oracle.registration_icp(src, tgt, 20.0, np.eye(4), max_iteration=40)
+    e = oracle.evaluate_registration(src, tgt, 20.0, r.transformation)
+    # (upstream moves the cloud by each update in turn; one transform by the composed matrix
+    # differs in the last bits)
+    assert e.fitness == r.fitness
+    np.testing.assert_allclose(e.inlier_rmse, r.inlier_rmse, rtol=1e-12)
+    np.testing.assert_array_equal(np.asarray(e.correspondence_set), np.asarray(r.correspondence_set))
+    if r.iterations < 40:  # stopped by the criteria: one more run stops after its first update
+        r2 = oracle.registration_icp(src, tgt, 20.0, r.transformation, max_iteration=40)
+        assert r2.iterations <= 1
+        np.testing.assert_allclose(r2.transformation, r.transformation, atol=1e-5)
+
+
+def test_verify_is_permutation_equivariant_and_first_min():
+    """Shuffling the candidates permutes the losses; with the best candidate duplicated the
+    FIRST occurrence is selected (list.index(min(list)), verfication.py:105-106)."""
+    cloud = synth.make_cloud(1200, seed=1)
+    R_true, _ = synth.true_pose(3)
+    Rs, _, k0 = synth.make_candidates(7, seed=10, R_true=R_true, t_true=np.zeros(3))
+    Mq, Mt = synth.verification_matrices(Rs, R_true)
+    losses, best = oracle.verify_matrices(cloud, cloud, Mq, Mt)
+    perm = np.random.default_rng(0).permutation(7)
+    lp, bp = oracle.verify_matrices(cloud, cloud, Mq[perm], Mt[perm])
+    np.testing.assert_array_equal(lp, losses[perm])
+    assert perm[bp] == best == k0
+    Mq2, Mt2 = np.concatenate([Mq, Mq[k0:k0 + 1]]), np.concatenate([Mt, Mt[k0:k0 + 1]])
+    _, b2 = oracle.verify_matrices(cloud, cloud, Mq2, Mt2)
+    assert b2 == k0
