@@ -3,7 +3,7 @@ and point-to-point ICP) behind the reference's call surface.
 
 Public surface
   api        batched device API: transform_points, nearest_neighbors, chamfer_distance,
-             adds, verify_poses, evaluate_registration, icp, multistart_icp, refine_pose
+             adds, verify_poses, evaluate_registration, icp, multistart_icp, icp_refine_pose
   helpers    the reference scripts' helper names (calculate_relative_pose, ADD, ADDS, ...)
   o3d_compat Open3D-shaped shim (``import ...o3d_compat as o3d``)
   compat     sklearn-shaped KDTree shim
@@ -18,7 +18,7 @@ from .api import (IcpProblem, IcpResult, MultiStartResult, NNResult, SoaCloud,  
                   VerifyResult, adds, chamfer_distance, evaluate_registration, icp,
                   centroid_of, measure_fp32_peak, multistart_icp, nearest_neighbors, pack_soa,
                   prepare_cloud, spatial_order, set_nn_pruning, get_nn_pruning, radius_neighbor_count,
-                  point_cloud_distance, pose_from_Rt, refine_pose, score_pnp_hypotheses, transform_points,
+                  point_cloud_distance, pose_from_Rt, icp_refine_pose, refine_pose, score_pnp_hypotheses, transform_points,
                   verify_poses)
 from .helpers import (ADD, ADDS, calculate_relative_pose, choose_image,  # noqa: F401
                       compute_rel_poses, draw_registration_result, relative_pose_table,

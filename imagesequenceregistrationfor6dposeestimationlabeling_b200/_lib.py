@@ -94,12 +94,13 @@ SIGNATURES = {
     "isr_icp_accumulate": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _D, _P, _P, _P, _P, _SZ, _P]),
     "isr_icp_search": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "isr_icp_corr_dist": (_I, [_P, _I64, _P, _P, _I64, _P, _P, _P, _P]),
-    "isr_icp_accumulate_corr": (_I, [_P, _I64, _P, _P, _I64, _P, _I64, _P, _D, _P, _P, _P, _SZ, _P]),
+    "isr_icp_accumulate_corr": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _D, _P, _P, _P, _SZ, _P]),
     "isr_icp_solve": (_I, [_P, _I64, _P, _I64, _D, _D, _I, _P]),
     "isr_icp_run": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _D, _I, _D, _D, _P, _P, _P, _P, _SZ,
                          _P]),
     "isr_peer_create": (_I, [_I, _I, _P, _P]),
     "isr_peer_connect": (_I, [_P, _P]),
+    "isr_peer_set_timeout": (_I, [_P, _D]),
     "isr_peer_destroy": (_I, [_P]),
     "isr_icp_run_sharded": (_I, [_P, _I64, _P, _P, _P, _I64, _I64, _P, _P, _P, _D, _I, _D, _D, _P, _P, _P,
                                  _P, _SZ, _P, _P]),

@@ -12,12 +12,14 @@ Reference mapping (file:line into the reference repository):
   verify_poses        candidate loop + argmin  verfication.py:61-108; choosePose.py:124-138
   evaluate_registration / icp                  icp.py:96-103
   multistart_icp      symmetry-seeded starts   README.md:42-46 (config 5 of BASELINE.json)
-  refine_pose         (R, t, loss) convention  pose_refine.py:21-22,101-104
+  icp_refine_pose     (R, t, loss) convention  pose_refine.py:21-22,101-104 (alias: refine_pose)
 """
 from __future__ import annotations
 
 import ctypes
 import dataclasses
+import functools
+import inspect
 from typing import Optional, Sequence
 
 import numpy as np
@@ -39,6 +41,33 @@ def _device(device=None) -> torch.device:
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device(fn):
+    """libisr launches on the device that is CURRENT in the calling thread, on torch's current
+    stream of that device.  A public function that is handed `device=` (or tensors living on
+    another GPU) therefore runs its whole body under ``torch.cuda.device(...)``: allocations,
+    stream and kernels all belong to the same GPU."""
+    sig = inspect.signature(fn)
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = sig.bind(*args, **kwargs).arguments.get("device")
+        if dev is None:
+            for a in list(args) + list(kwargs.values()):
+                t = a.data if isinstance(a, SoaCloud) else a
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    dev = t.device
+                    break
+        if dev is None or not torch.cuda.is_available():
+            return fn(*args, **kwargs)
+        dev = torch.device(dev)
+        if dev.type != "cuda":
+            raise ValueError(f"device must be a CUDA device, got {dev}")
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
 
 
 _NP_OF = {torch.float32: np.float32, torch.float64: np.float64, torch.uint8: np.uint8,
@@ -119,6 +148,7 @@ def pose_from_Rt(R, t) -> np.ndarray:
 # --------------------------------------------------------------------------------------
 # K1 -- transform
 # --------------------------------------------------------------------------------------
+@_on_device
 def transform_points(points, poses, device=None) -> torch.Tensor:
     """out[b] = points @ poses[b,:3,:3].T + poses[b,:3,3]  ->  float32 [B, N, 3] (FP64 math)."""
     device = _device(device)
@@ -170,6 +200,7 @@ class SoaCloud:
         return self.data.shape[0]
 
 
+@_on_device
 def pack_soa(points, poses=None, device=None) -> SoaCloud:
     """Repack [N,3] (optionally transformed by each of poses [B,4,4]) into SoA planes."""
     device = _device(device)
@@ -194,6 +225,7 @@ def pack_soa(points, poses=None, device=None) -> SoaCloud:
     return SoaCloud(out, n)
 
 
+@_on_device
 def centroid_of(points, device=None) -> torch.Tensor:
     """FP64 centroid [3] of an [N,3] cloud, on the device (deterministic order)."""
     device = _device(device)
@@ -204,8 +236,9 @@ def centroid_of(points, device=None) -> torch.Tensor:
     return out
 
 
+@_on_device
 def spatial_order(points, device=None) -> torch.Tensor:
-    """int32 [N] Morton-order permutation of an [N,3] cloud (perm[i] = original index)."""
+    """int32 [N] Hilbert-curve order of an [N,3] cloud (perm[i] = original index of the i-th stored point)."""
     device = _device(device)
     pts = _points(points, device)
     n = pts.shape[0]
@@ -217,12 +250,13 @@ def spatial_order(points, device=None) -> torch.Tensor:
     return perm
 
 
+@_on_device
 def prepare_cloud(points, poses=None, centroid=None, centre_poses=None, perm=None,
                   stage_centroids: bool = False, device=None) -> SoaCloud:
     """[N,3] (optionally transformed by poses [B,4,4]) -> centred hi/lo SoA7 planes [B,7,npad].
     The centre of batch item b is centre_poses[b] . centroid (centre_poses None: centroid).
     float64 input keeps its precision (hi/lo split).  `perm` (from spatial_order) stores the
-    points in Morton order; `stage_centroids` adds the bounding spheres of the 1024-point
+    points in that (Hilbert-curve) order; `stage_centroids` adds the bounding spheres of the 1024-point
     stages and 64-point sub-tiles that a target needs for nearest-stage-first scanning and
     tile pruning."""
     device = _device(device)
@@ -288,6 +322,7 @@ class NNResult:
         return torch.sqrt(self.d2.to(torch.float64))
 
 
+@_on_device
 def nearest_neighbors_soa(q: SoaCloud, t: SoaCloud, return_index: bool = True,
                           use_lo: bool = True) -> NNResult:
     """K2 on prepared clouds.  7-plane clouds run the production filtered-exact kernel
@@ -334,6 +369,7 @@ def nearest_neighbors_soa(q: SoaCloud, t: SoaCloud, return_index: bool = True,
     return NNResult(d2, idx)
 
 
+@_on_device
 def nearest_neighbors(query, target, return_index: bool = True, mode: str = "exact",
                       device=None) -> NNResult:
     """Brute-force 1-NN of query [Nq,3] / [B,Nq,3] in target [Nt,3] / [B,Nt,3].
@@ -352,24 +388,25 @@ def nearest_neighbors(query, target, return_index: bool = True, mode: str = "exa
         if tp.shape[0] < 1:
             raise ValueError("nearest_neighbors: empty target cloud")
         cen = centroid_of(tp, device)
-        t7 = prepare_cloud(tp, centroid=cen, perm=spatial_order(tp, device), stage_centroids=True,
+        # (prepare_cloud gets the ORIGINAL arrays: float64 clouds are split into hi/lo pairs)
+        t7 = prepare_cloud(target, centroid=cen, perm=spatial_order(tp, device), stage_centroids=True,
                            device=device)
         if qp.dim() == 2:
-            q7 = prepare_cloud(qp, centroid=cen, perm=spatial_order(qp, device), device=device)
+            q7 = prepare_cloud(query, centroid=cen, perm=spatial_order(qp, device), device=device)
             res = nearest_neighbors_soa(q7, t7, return_index)
         else:
             # a batch of different query clouds against one target: each gets its own curve
             # order (the pruned search relies on it), so they are searched one by one
             outs = [nearest_neighbors_soa(
-                prepare_cloud(qp[k], centroid=cen, perm=spatial_order(qp[k], device), device=device),
+                prepare_cloud(query[k], centroid=cen, perm=spatial_order(qp[k], device), device=device),
                 t7, return_index) for k in range(qp.shape[0])]
             res = NNResult(torch.cat([o.d2 for o in outs]),
                            torch.cat([o.idx for o in outs]) if return_index else None)
     else:
         outs = []
         for k in range(tp.shape[0]):
-            qk = qp if qp.dim() == 2 else qp[k]
-            outs.append(nearest_neighbors(qk, tp[k], return_index, mode, device))
+            qk = query if qp.dim() == 2 else query[k]
+            outs.append(nearest_neighbors(qk, target[k], return_index, mode, device))
         return NNResult(torch.stack([o.d2 for o in outs]),
                         torch.stack([o.idx for o in outs]) if return_index else None)
     if single:
@@ -377,6 +414,7 @@ def nearest_neighbors(query, target, return_index: bool = True, mode: str = "exa
     return res
 
 
+@_on_device
 def radius_neighbor_count(points, radius: float, target=None, device=None) -> torch.Tensor:
     """int32 [N]: for every point, the number of `target` points (default: the cloud itself,
     the point included) with d^2 < radius^2 -- strict, decided in float64.  The count behind
@@ -416,6 +454,7 @@ def _mean_sqrt(d2: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def point_cloud_distance(source, target, device=None) -> torch.Tensor:
     """Open3D compute_point_cloud_distance: float64 [N] distances; empty target -> zeros."""
     device = _device(device)
@@ -425,9 +464,11 @@ def point_cloud_distance(source, target, device=None) -> torch.Tensor:
         return torch.zeros((src.shape[0],), dtype=torch.float64, device=device)
     if src.shape[0] == 0:
         return torch.zeros((0,), dtype=torch.float64, device=device)
-    return nearest_neighbors(src, tgt, return_index=False, device=device).dist
+    # (the ORIGINAL arrays go to the search: float64 clouds keep their precision as hi/lo pairs)
+    return nearest_neighbors(source, target, return_index=False, device=device).dist
 
 
+@_on_device
 def chamfer_distance(a, b, device=None) -> torch.Tensor:
     """(mean d(a->b) + mean d(b->a)) / 2, unsquared, float64 scalar tensor
     (verfication.py:97-101).  Accepts [N,3] or batched [B,N,3]."""
@@ -437,13 +478,14 @@ def chamfer_distance(a, b, device=None) -> torch.Tensor:
     if not single:
         if pa.dim() != 3 or pb.dim() != 3 or pa.shape[0] != pb.shape[0]:
             raise ValueError("batched chamfer_distance expects [B,N,3] and [B,M,3]")
-        return torch.stack([chamfer_distance(pa[k], pb[k], device) for k in range(pa.shape[0])])
+        return torch.stack([chamfer_distance(a[k], b[k], device) for k in range(pa.shape[0])])
     if pa.shape[0] == 0 or pb.shape[0] == 0:
         raise ValueError("chamfer_distance: empty cloud")
     cen = centroid_of(pb, device)
-    A = prepare_cloud(pa, centroid=cen, perm=spatial_order(pa, device), stage_centroids=True,
+    # (float64 inputs -- icp.py:110-113 builds a float64 merged cloud -- keep their precision)
+    A = prepare_cloud(a, centroid=cen, perm=spatial_order(pa, device), stage_centroids=True,
                       device=device)
-    B = prepare_cloud(pb, centroid=cen, perm=spatial_order(pb, device), stage_centroids=True,
+    B = prepare_cloud(b, centroid=cen, perm=spatial_order(pb, device), stage_centroids=True,
                       device=device)
     ab = _mean_sqrt(nearest_neighbors_soa(A, B, return_index=False).d2)
     ba = _mean_sqrt(nearest_neighbors_soa(B, A, return_index=False).d2)
@@ -464,6 +506,7 @@ class VerifyResult:
         return float(self.best[1:2].view(torch.float64).item())
 
 
+@_on_device
 def verify_poses(cloud_q, poses_q, poses_t, cloud_t=None, mode: str = "chamfer",
                  valid_mask=None, device=None) -> VerifyResult:
     """Score B candidate poses and select the first minimum, entirely on the device.
@@ -504,6 +547,7 @@ def verify_poses(cloud_q, poses_q, poses_t, cloud_t=None, mode: str = "chamfer",
     return VerifyResult(losses, best)
 
 
+@_on_device
 def adds(verts, gtR, gtT, R, T, surface_points, device=None) -> torch.Tensor:
     """Batched ADDS (choosePose.py:20-22): mean 1-NN distance from verts.gtR^T+gtT to
     surface.R^T+T.  gtR/R may be [3,3] or [B,3,3]; returns float64 [B] (or scalar)."""
@@ -552,6 +596,16 @@ class IcpResult:
                 "Access transformation to get result.")
 
 
+def _on_self_device(fn):
+    """Method form of _on_device: run on the device the object's buffers live on."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 class IcpProblem:
     """Device-side buffers of one (source, target) pair for `starts` simultaneous ICP starts.
 
@@ -561,6 +615,10 @@ class IcpProblem:
 
     def __init__(self, source, target, inits, device=None):
         self.device = _device(device)
+        with torch.cuda.device(self.device):
+            self._init(source, target, inits)
+
+    def _init(self, source, target, inits):
         self.src, self.src_lo = _points_hilo(source, self.device)
         self.tgt = _points(target, self.device)
         if self.src.dim() != 2 or self.tgt.dim() != 2:
@@ -587,6 +645,7 @@ class IcpProblem:
         self.corr_idx = torch.zeros((self.starts, ns1), dtype=torch.int32, device=self.device)
         self.inlier = torch.zeros((self.starts, ns1), dtype=torch.uint8, device=self.device)
 
+    @_on_self_device
     def accumulate(self, max_dist: float) -> torch.Tensor:
         if self.ns == 0:
             self.sums.zero_()
@@ -599,6 +658,7 @@ class IcpProblem:
         return self.sums
 
     # -- the two halves of `accumulate`, for target-sharded ICP (dist.py) ---------------------
+    @_on_self_device
     def search(self) -> torch.Tensor:
         """Transform the source by every state's T and find each point's nearest neighbour in
         THIS problem's target -> int32 [starts, ns] (also kept in self.corr_idx)."""
@@ -608,6 +668,7 @@ class IcpProblem:
             _ptr(self.ws), self.ws.numel(), _stream()))
         return self.corr_idx
 
+    @_on_self_device
     def corr_dist(self, corr_idx: torch.Tensor) -> torch.Tensor:
         """float64 [starts, ns]: exact squared distance of every given correspondence (+inf
         where the index is negative), in the accumulate kernel's arithmetic."""
@@ -619,14 +680,16 @@ class IcpProblem:
             _ptr(corr_idx), _ptr(self._D), _stream()))
         return self._D
 
+    @_on_self_device
     def accumulate_corr(self, corr_idx: torch.Tensor, max_dist: float) -> torch.Tensor:
         """The 17 sums over the given correspondences (index < 0: none on this rank)."""
         _lib.check(_lib.load().isr_icp_accumulate_corr(
-            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), self.ns, _ptr(self.tgt),
-            self.nt, _ptr(corr_idx), float(max_dist), _ptr(self.sums), _ptr(self.inlier), _ptr(self.ws),
-            self.ws.numel(), _stream()))
+            _ptr(self.states), self.starts, _ptr(self.src), _ptr(self.src_lo), _ptr(self.src_perm), self.ns,
+            _ptr(self.tgt), self.nt, _ptr(corr_idx), float(max_dist), _ptr(self.sums), _ptr(self.inlier),
+            _ptr(self.ws), self.ws.numel(), _stream()))
         return self.sums
 
+    @_on_self_device
     def solve(self, ns_total: int, rel_fitness: float, rel_rmse: float, final_eval: bool,
               sums: Optional[torch.Tensor] = None) -> None:
         sums = self.sums if sums is None else sums
@@ -634,6 +697,7 @@ class IcpProblem:
                                              float(rel_fitness), float(rel_rmse),
                                              1 if final_eval else 0, _stream()))
 
+    @_on_self_device
     def run(self, max_dist: float, max_iteration: int, rel_fitness: float, rel_rmse: float) -> None:
         if self.ns == 0:
             for k in range(max_iteration + 1):
@@ -652,6 +716,7 @@ class IcpProblem:
         from the current poses and correspondences."""
         self.states.view(torch.int32)[:, 44] = 0
 
+    @_on_self_device
     def run_sharded(self, peer, ns_total: int, max_dist: float, max_iteration: int, rel_fitness: float,
                     rel_rmse: float) -> None:
         """`run` for one source shard: the 17 sums are exchanged between the ranks of `peer`
@@ -663,6 +728,7 @@ class IcpProblem:
             _ptr(self.corr_idx), _ptr(self.inlier), _ptr(self.ws), self.ws.numel(), peer.handle,
             _stream()))
 
+    @_on_self_device
     def results(self, with_correspondences: bool = True) -> list:
         st = self.states.cpu().numpy().view(_lib.ICP_STATE_DTYPE).reshape(self.starts)
         out = []
@@ -680,6 +746,7 @@ class IcpProblem:
         return out
 
 
+@_on_device
 def evaluate_registration(source, target, max_correspondence_distance: float,
                           transformation=None, device=None) -> IcpResult:
     """o3d.pipelines.registration.evaluate_registration (icp.py:97-98)."""
@@ -689,6 +756,7 @@ def evaluate_registration(source, target, max_correspondence_distance: float,
     return prob.results()[0]
 
 
+@_on_device
 def icp(source, target, init=None, max_correspondence_distance: float = 20.0,
         max_iteration: int = 30, relative_fitness: float = 1e-6, relative_rmse: float = 1e-6,
         device=None) -> IcpResult:
@@ -710,6 +778,7 @@ class MultiStartResult:
         return self.results[int(self.order[0])]
 
 
+@_on_device
 def multistart_icp(source, target, inits, max_correspondence_distance: float = 20.0,
                    max_iteration: int = 30, relative_fitness: float = 1e-6,
                    relative_rmse: float = 1e-6, device=None) -> MultiStartResult:
@@ -728,21 +797,39 @@ def multistart_icp(source, target, inits, max_correspondence_distance: float = 2
     return MultiStartResult(res, ch, np.argsort(ch, kind="stable"))
 
 
-def refine_pose(R, t, source, target, max_correspondence_distance: float = 20.0,
-                max_iteration: int = 30, device=None):
-    """ICP refinement with the return convention of pose_refine.py:21-22,101-104:
-    ``(R, t, loss)``.  (R, t) maps `source` into the frame of `target`; the loss is the
-    inlier RMSE of the final evaluation.  The reference's own objective (NeRF keys + GL
-    renderer, rotation frozen) is out of scope; only its call/return shape is kept."""
+@_on_device
+def icp_refine_pose(R, t, source, target, max_correspondence_distance: float = 20.0,
+                    max_iteration: int = 30, relative_fitness: float = 1e-6,
+                    relative_rmse: float = 1e-6, device=None):
+    """Point-to-point ICP refinement of the pose (R, t) that maps `source` into the frame of
+    `target`, returned in the convention of pose_refine.py:21-22,101-104: ``(R 3x3 float64,
+    t (3,) float64, loss)`` with loss = the inlier RMSE of the final evaluation.
+
+    This is NOT the reference's ``refine_pose`` objective: that one keeps R frozen and runs BFGS
+    on the translation against a NeRF-key / GL-renderer likelihood (pose_refine.py:74-98), is
+    reachable only behind a hard-coded ``useSurfEval=False`` (inference.py:27) and needs modules
+    the reference does not ship; it is out of scope.  Only the
+    ``(R, t, loss)`` return shape is carried over, so that a caller that unpacks the
+    reference's triple keeps working when it refines with ICP instead."""
+    src = np.asarray(source) if not isinstance(source, torch.Tensor) else source
+    tg = np.asarray(target) if not isinstance(target, torch.Tensor) else target
+    if src.ndim != 2 or src.shape[-1] != 3 or tg.ndim != 2 or tg.shape[-1] != 3:
+        raise TypeError("icp_refine_pose(R, t, source[N,3], target[M,3], ...): this is the ICP "
+                        "refinement, not pose_refine.refine_pose(R, t, query_img, renderer, ...)")
     res = icp(source, target, pose_from_Rt(R, t), max_correspondence_distance, max_iteration,
-              device=device)
+              relative_fitness, relative_rmse, device=device)
     T = res.transformation
-    return T[:3, :3].copy(), T[:3, 3].copy(), res.inlier_rmse
+    return T[:3, :3].copy(), T[:3, 3].copy(), float(res.inlier_rmse)
+
+
+#: name used by SURVEY.md section 8(b) / round 1; same function
+refine_pose = icp_refine_pose
 
 
 # --------------------------------------------------------------------------------------
 # PnP hypothesis scoring (SURVEY.md 8(f) row 3)
 # --------------------------------------------------------------------------------------
+@_on_device
 def score_pnp_hypotheses(points3d, points2d, camera_matrix, poses, reprojection_error: float = 2.0,
                          return_inliers: bool = False, device=None):
     """Consensus of every hypothesis in `poses` [B,4,4] (object -> camera) over the 2-D/3-D

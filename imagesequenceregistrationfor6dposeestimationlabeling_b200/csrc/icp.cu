@@ -9,194 +9,92 @@
 //                  |drmse| < rr } at most max_iteration times; the result is the last
 //                  evaluation; an empty correspondence set gives U = I.
 //
-// One evaluation = K1 (FP64 transform -> FP32 SoA) + K2 (FP32 brute-force 1-NN, indices)
-// + icp_accumulate_kernel (HBM-bound gather: 12 B source + 4 B index + 12 B gathered
-// target (+ 1 B flag written) per source point).  The gather re-derives every
-// correspondence distance in FP64 from the original source point and the FP64 pose, so
-// the inlier test, fitness, rmse and the 17 Kabsch sums carry no FP32 error; only the
-// choice of neighbour is made in FP32.  Sums are reduced warp -> CTA -> last-arriving CTA
-// in a fixed order (no floating-point atomics).  icp_solve_kernel (one warp per start)
-// applies the break test, solves the 3x3 SVD by one-sided Jacobi in FP64 and composes
-// T <- U T.  A finished start sets `done`; all later kernels for it exit at once, so the
-// host enqueues max_iteration + 1 passes without ever reading the device.
+// Two forms of one evaluation + update:
+//   FUSED (isr_icp_run, isr_icp_run_sharded; the product path): ONE kernel per iteration --
+//     nn2_pruned_kernel<FUSED> transforms the source itself, searches, gathers every
+//     neighbour's original coordinates (16-byte rows in stored order), forms the 17 sums in a
+//     launch-independent fixed order, exchanges them with the peer GPUs and solves Kabsch in
+//     the last warp to arrive (icp_device.cuh).  Per iteration nothing but that one launch is
+//     enqueued; nothing is read by the host.
+//   STEPWISE (isr_icp_search / _corr_dist / _accumulate_corr / _solve; target-sharded ICP, the
+//     NCCL exchange, the exhaustive search): K1' (FP64 transform -> hi/lo planes) + K2 +
+//     icp_accumulate_kernel (gather: 12 B source + 4 B index + 12 B gathered target + 1 B
+//     flag per source point) + icp_solve_kernel.
+// Both re-derive every correspondence distance in FP64 from the original source point and the
+// FP64 pose, so the inlier test, fitness, rmse and the 17 Kabsch sums carry no FP32 error; only
+// the choice of neighbour is made in FP32.  No floating-point atomics.  A finished start sets
+// `done`; all later kernels for it exit at once, so the host enqueues max_iteration + 1 passes
+// without ever reading the device.
 #include <math_constants.h>
 #include <string.h>
 
+#include "icp_device.cuh"
 #include "isr_common.cuh"
 
 namespace isr {
 
-constexpr int kAccThreads = 256;
-constexpr int kNS = ISR_ICP_NSUMS;
+constexpr int kAccThreads = 128;
 constexpr int kStateInts = (int)(sizeof(IsrIcpState) / sizeof(int32_t));
 constexpr int kStateDoubles = (int)(sizeof(IsrIcpState) / sizeof(double));
 static_assert(sizeof(IsrIcpState) % 8 == 0, "IsrIcpState must be a whole number of doubles");
 
-// ---- exchange of the 17 sums between the GPUs of one box, fused into the two ICP kernels ----
-// Every rank owns one small buffer that all peers map through CUDA IPC (NVLink / NVSwitch
-// peer memory):  data[2][world][kPeerStarts][17] doubles and flag[2][world][kPeerStarts].
-// The last-arriving CTA of the accumulate kernel stores this rank's sums for start s into
-// slot [seq & 1][rank][s] of EVERY rank's buffer, fences, and then stores the message number
-// seq into the matching flags; the solve kernel of every rank waits until its own buffer
-// holds seq from all ranks and adds the `world` vectors in rank order -- the same order
-// everywhere, so all ranks solve bit-identical problems.  No collective library call, no
-// extra launch, nothing read by the host.  Two slots suffice: a rank can only start message
-// seq + 1 after it has received every peer's seq, i.e. after every peer has finished reading
-// message seq - 1 from the slot that seq + 1 overwrites.
-constexpr int kPeerRanks = ISR_PEER_MAX_RANKS;
-constexpr int kPeerStarts = ISR_PEER_MAX_STARTS;
-struct PeerView {
-    double *data[kPeerRanks];
-    unsigned long long *flag[kPeerRanks];
-    int rank, world;  // world == 0: no exchange
-    unsigned long long seq;
-};
-__host__ __device__ inline size_t peer_data_index(const PeerView &v, int from_rank, int start) {
-    return (((size_t)(v.seq & 1) * kPeerRanks + from_rank) * kPeerStarts + start) * kNS;
-}
-__host__ __device__ inline size_t peer_flag_index(const PeerView &v, int from_rank, int start) {
-    return ((size_t)(v.seq & 1) * kPeerRanks + from_rank) * kPeerStarts + start;
-}
-constexpr size_t kPeerDataBytes = (size_t)2 * kPeerRanks * kPeerStarts * kNS * sizeof(double);
-constexpr size_t kPeerFlagBytes = (size_t)2 * kPeerRanks * kPeerStarts * sizeof(unsigned long long);
-
-// grid: (nblk, starts)
+// ---- stepwise accumulate: the same sums, in the same order, as the fused search's epilogue ----
+// One warp per block of 256 STORED source points (perm_q: stored position -> original index),
+// grid (ceil(nqb / 4), starts) x 128 threads.  Per point: original source row (12 B + 12 B lo),
+// its correspondence (4 B, original target index; < 0 = none on this rank), the gathered target
+// row (12 B), one flag written.  Row sums, then icp_fused_tail with do_solve = 0: rows -> block ->
+// group -> start in index order, so that the 17 sums equal the fused iteration's bit for bit.
 __global__ void __launch_bounds__(kAccThreads)
-icp_accumulate_kernel(const IsrIcpState *__restrict__ states, const float *__restrict__ src,
-                      const float *__restrict__ src_lo, int64_t ns, const float *__restrict__ tgt, const int32_t *__restrict__ idx,
-                      double max_d2, double *__restrict__ partials, unsigned *__restrict__ tickets,
-                      double *__restrict__ sums, uint8_t *__restrict__ inlier, const PeerView px) {
-    const int s = blockIdx.y;
-    const IsrIcpState &stt = states[s];
-    if (stt.done != 0) return;
-    __shared__ double red[kAccThreads / 32][kNS];
-    __shared__ bool is_last;
-
+icp_accumulate_rows_kernel(const __grid_constant__ IcpFuse f, const float *__restrict__ src,
+                           const float *__restrict__ src_lo, const int32_t *__restrict__ perm_q, int64_t ns,
+                           const float *__restrict__ tgt, const int32_t *__restrict__ idx,
+                           uint8_t *__restrict__ inlier) {
+    __shared__ double scratch_all[kAccThreads / 32][32 * kNS];
+    const int b = blockIdx.y;
+    if (f.states[b].done != 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int blk = blockIdx.x * (kAccThreads / 32) + warp;
+    if (blk >= f.nqb) return;
+    double *scratch = scratch_all[warp];
     double T[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) T[k] = stt.T[k];
-    double acc[kNS];
+    for (int k = 0; k < 12; ++k) T[k] = f.states[b].T[k];
+    double rs[8];
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) {
+        const int64_t i = (int64_t)blk * 256 + r * 32 + lane;
+        double c[kNS];
 #pragma unroll
-    for (int k = 0; k < kNS; ++k) acc[k] = 0.0;
-
-    const int32_t *ids = idx + (int64_t)s * ns;
-    uint8_t *inl = inlier != nullptr ? inlier + (int64_t)s * ns : nullptr;
-    // 4 points per thread and trip, all loads of a trip issued before the first use: the
-    // dependent gather (index -> target row) is what bounds this kernel, so keep 4 in flight.
-    constexpr int U = 4;
-    const int64_t stride = (int64_t)gridDim.x * kAccThreads;
-    for (int64_t i0 = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i0 < ns; i0 += U * stride) {
-        float fx[U], fy[U], fz[U], lx[U], ly[U], lz[U];
-        int j[U];
-        bool ok[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t i = i0 + u * stride;
-            ok[u] = i < ns;
-            const int64_t ii = ok[u] ? i : i0;
-            fx[u] = src[3 * ii]; fy[u] = src[3 * ii + 1]; fz[u] = src[3 * ii + 2];
-            lx[u] = ly[u] = lz[u] = 0.f;
-            if (src_lo != nullptr) {
-                lx[u] = src_lo[3 * ii]; ly[u] = src_lo[3 * ii + 1]; lz[u] = src_lo[3 * ii + 2];
+        for (int k = 0; k < kNS; ++k) c[k] = 0.0;
+        if (i < ns) {
+            const int64_t io = perm_q != nullptr ? perm_q[i] : i;
+            const int j = idx[(int64_t)b * ns + io];
+            bool in = false;
+            if (j >= 0) {
+                double px = src[3 * io], py = src[3 * io + 1], pz = src[3 * io + 2];
+                if (src_lo != nullptr) {
+                    px += (double)src_lo[3 * io]; py += (double)src_lo[3 * io + 1]; pz += (double)src_lo[3 * io + 2];
+                }
+                double sx, sy, sz;
+                icp_apply_pose(T, px, py, pz, sx, sy, sz);
+                const double tx = tgt[3ll * j], ty = tgt[3ll * j + 1], tz = tgt[3ll * j + 2];
+                const double d2 = icp_dist2(sx, sy, sz, tx, ty, tz);
+                in = d2 < f.max_d2;
+                if (in) icp_contrib(sx, sy, sz, tx, ty, tz, d2, c);
             }
-            j[u] = ids[ii];
-            // a negative index: this source point has no correspondence here (target-sharded
-            // ICP: its neighbour lives on another rank)
-            ok[u] = ok[u] && j[u] >= 0;
-        }
-        float gx[U], gy[U], gz[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t jj = j[u] >= 0 ? j[u] : 0;
-            gx[u] = tgt[3 * jj]; gy[u] = tgt[3 * jj + 1]; gz[u] = tgt[3 * jj + 2];
+            if (inlier != nullptr) inlier[(int64_t)b * ns + io] = in ? 1 : 0;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const double px = (double)fx[u] + (double)lx[u], py = (double)fy[u] + (double)ly[u],
-                         pz = (double)fz[u] + (double)lz[u];
-            const double sx = ((T[0] * px + T[1] * py) + T[2] * pz) + T[3];
-            const double sy = ((T[4] * px + T[5] * py) + T[6] * pz) + T[7];
-            const double sz = ((T[8] * px + T[9] * py) + T[10] * pz) + T[11];
-            const double tx = gx[u], ty = gy[u], tz = gz[u];
-            const double dx = sx - tx, dy = sy - ty, dz = sz - tz;
-            const double d2 = dx * dx + dy * dy + dz * dz;
-            const bool in = ok[u] && d2 < max_d2;
-            if (inl != nullptr && i0 + u * stride < ns) inl[i0 + u * stride] = in ? 1 : 0;
-            if (in) {
-                acc[0] += sx; acc[1] += sy; acc[2] += sz;
-                acc[3] += tx; acc[4] += ty; acc[5] += tz;
-                acc[6] += tx * sx; acc[7] += tx * sy; acc[8] += tx * sz;
-                acc[9] += ty * sx; acc[10] += ty * sy; acc[11] += ty * sz;
-                acc[12] += tz * sx; acc[13] += tz * sy; acc[14] += tz * sz;
-                acc[15] += d2;
-                acc[16] += 1.0;
-            }
-        }
+        for (int k = 0; k < kNS; ++k) scratch[lane * kNS + k] = c[k];
+        __syncwarp();
+        rs[r] = icp_row_sum(scratch, lane);
+        __syncwarp();
     }
-#pragma unroll
-    for (int k = 0; k < kNS; ++k) acc[k] = warp_sum(acc[k]);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < kNS; ++k) red[warp][k] = acc[k];
-    }
-    __syncthreads();
-    double *my = partials + ((int64_t)s * gridDim.x + blockIdx.x) * kNS;
-    if (threadIdx.x < kNS) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < kAccThreads / 32; ++w) v += red[w][threadIdx.x];
-        my[threadIdx.x] = v;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(&tickets[s], 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-        // final reduction over the CTAs' partials by the whole block: thread t takes blocks
-        // t, t+256, ... (fixed mapping), then the same warp -> CTA tree as above
-        __threadfence();
-        const double *base = partials + (int64_t)s * gridDim.x * kNS;
-        double v[kNS];
-#pragma unroll
-        for (int k = 0; k < kNS; ++k) v[k] = 0.0;
-        for (unsigned bk = threadIdx.x; bk < gridDim.x; bk += kAccThreads) {
-#pragma unroll
-            for (int k = 0; k < kNS; ++k) v[k] += base[(int64_t)bk * kNS + k];
-        }
-#pragma unroll
-        for (int k = 0; k < kNS; ++k) v[k] = warp_sum(v[k]);
-        __syncthreads();  // `red` is reused
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < kNS; ++k) red[warp][k] = v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x < kNS) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < kAccThreads / 32; ++w) t += red[w][threadIdx.x];
-            sums[(int64_t)s * kNS + threadIdx.x] = t;
-            // push this rank's sums into every rank's exchange buffer (peer stores over NVLink)
-            for (int r = 0; r < px.world; ++r) px.data[r][peer_data_index(px, px.rank, s) + threadIdx.x] = t;
-        }
-        if (px.world > 0) {
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x < px.world) {
-                volatile unsigned long long *f = px.flag[threadIdx.x] + peer_flag_index(px, px.rank, s);
-                *f = px.seq;
-            }
-        }
-        if (threadIdx.x == 0) tickets[s] = 0;
-    }
+    icp_fused_tail(f, b, blk, 0xFFu, lane, rs);
 }
 
 // out_D[start][i] = FP64 squared distance between T.src[i] and tgt[idx[start][i]] (the same
-// arithmetic as the accumulate kernel); +inf where idx < 0.  grid (blocks, starts).
+// arithmetic as the accumulate kernels); +inf where idx < 0.  grid (blocks, starts).
 __global__ void __launch_bounds__(256)
 icp_corr_dist_kernel(const IsrIcpState *__restrict__ states, const float *__restrict__ src,
                      const float *__restrict__ src_lo, int64_t ns, const float *__restrict__ tgt,
@@ -213,12 +111,9 @@ icp_corr_dist_kernel(const IsrIcpState *__restrict__ states, const float *__rest
         if (j >= 0) {
             double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
             if (src_lo != nullptr) { px += (double)src_lo[3 * i]; py += (double)src_lo[3 * i + 1]; pz += (double)src_lo[3 * i + 2]; }
-            const double sx = ((T[0] * px + T[1] * py) + T[2] * pz) + T[3];
-            const double sy = ((T[4] * px + T[5] * py) + T[6] * pz) + T[7];
-            const double sz = ((T[8] * px + T[9] * py) + T[10] * pz) + T[11];
-            const double dx = sx - (double)tgt[3ll * j], dy = sy - (double)tgt[3ll * j + 1],
-                         dz = sz - (double)tgt[3ll * j + 2];
-            D = dx * dx + dy * dy + dz * dz;
+            double sx, sy, sz;
+            icp_apply_pose(T, px, py, pz, sx, sy, sz);
+            D = icp_dist2(sx, sy, sz, (double)tgt[3ll * j], (double)tgt[3ll * j + 1], (double)tgt[3ll * j + 2]);
         }
         out_D[(int64_t)s * ns + i] = D;
     }
@@ -236,188 +131,48 @@ icp_hint_reset_kernel(const IsrIcpState *__restrict__ states, int64_t nsp, long 
     *reinterpret_cast<int4 *>(hint + i0) = make_int4(-1, -1, -1, -1);
 }
 
-// ---- 3x3 SVD (one-sided Jacobi, FP64) and Kabsch ---------------------------------------
-__device__ void svd3(const double M[3][3], double U[3][3], double D[3], double V[3][3]) {
-    double A[3][3];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            A[i][j] = M[i][j];
-            V[i][j] = (i == j) ? 1.0 : 0.0;
-        }
-    const int P[3] = {0, 0, 1}, Qc[3] = {1, 2, 2};
-    for (int sweep = 0; sweep < 64; ++sweep) {
-        bool rotated = false;
-        for (int pr = 0; pr < 3; ++pr) {
-            const int p = P[pr], q = Qc[pr];
-            double alpha = 0, beta = 0, gamma = 0;
-            for (int k = 0; k < 3; ++k) {
-                alpha += A[k][p] * A[k][p];
-                beta += A[k][q] * A[k][q];
-                gamma += A[k][p] * A[k][q];
-            }
-            if (gamma == 0.0 || fabs(gamma) <= 2.3e-16 * sqrt(alpha * beta)) continue;
-            rotated = true;
-            const double zeta = (beta - alpha) / (2.0 * gamma);
-            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
-            for (int k = 0; k < 3; ++k) {
-                const double ap = A[k][p], aq = A[k][q];
-                A[k][p] = c * ap - sn * aq;
-                A[k][q] = sn * ap + c * aq;
-                const double vp = V[k][p], vq = V[k][q];
-                V[k][p] = c * vp - sn * vq;
-                V[k][q] = sn * vp + c * vq;
-            }
-        }
-        if (!rotated) break;
-    }
-    for (int j = 0; j < 3; ++j)
-        D[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
-    // sort singular values descending (column permutation of A and V)
-    for (int a = 0; a < 2; ++a)
-        for (int b = a + 1; b < 3; ++b)
-            if (D[b] > D[a]) {
-                const double td = D[a]; D[a] = D[b]; D[b] = td;
-                for (int k = 0; k < 3; ++k) {
-                    const double ta = A[k][a]; A[k][a] = A[k][b]; A[k][b] = ta;
-                    const double tv = V[k][a]; V[k][a] = V[k][b]; V[k][b] = tv;
-                }
-            }
-    const double tiny = D[0] * 1e-14;
-    int rank = 0;
-    for (int j = 0; j < 3; ++j) {
-        if (D[j] > tiny && D[j] > 0.0) {
-            for (int k = 0; k < 3; ++k) U[k][j] = A[k][j] / D[j];
-            ++rank;
-        }
-    }
-    if (rank == 0) {
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) U[i][j] = (i == j) ? 1.0 : 0.0;
-    } else {
-        if (rank == 1) {
-            // any unit vector orthogonal to U[:,0]
-            int m = 0;
-            if (fabs(U[1][0]) < fabs(U[m][0])) m = 1;
-            if (fabs(U[2][0]) < fabs(U[m][0])) m = 2;
-            double e[3] = {0, 0, 0};
-            e[m] = 1.0;
-            const double dp = U[m][0];
-            double w[3], nn = 0;
-            for (int k = 0; k < 3; ++k) { w[k] = e[k] - dp * U[k][0]; nn += w[k] * w[k]; }
-            nn = sqrt(nn);
-            for (int k = 0; k < 3; ++k) U[k][1] = w[k] / nn;
-        }
-        if (rank <= 2) {
-            U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
-            U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
-            U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
-        }
-    }
-}
-
-__device__ __forceinline__ double det3(const double M[3][3]) {
-    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) -
-           M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
-           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
-}
-
-// one warp per start; lane 0 carries the (tiny, serial) FP64 solve.
+// one warp per start; lane 0 carries the (tiny, serial) FP64 solve (icp_device.cuh).
 __global__ void __launch_bounds__(32)
 icp_solve_kernel(IsrIcpState *__restrict__ states, const double *__restrict__ sums,
-                 int64_t ns_total, double rel_fitness, double rel_rmse, int final_eval, const PeerView px) {
+                 int64_t ns_total, double rel_fitness, double rel_rmse, int final_eval) {
     IsrIcpState &st = states[blockIdx.x];
-    if (st.done != 0) return;
-    __shared__ double Sx[kNS];
-    if (px.world > 0) {
-        // wait for message seq of every rank in THIS rank's buffer, then add in rank order
-        const int s = blockIdx.x;
-        bool ok = true;
-        if ((int)threadIdx.x < px.world) {
-            volatile unsigned long long *f = px.flag[px.rank] + peer_flag_index(px, threadIdx.x, s);
-            const long long t0 = clock64();
-            while (*f != px.seq) {
-                if (clock64() - t0 > 20000000000ll) { ok = false; break; }  // ~10 s: a peer died
-            }
-        }
-        ok = __all_sync(0xffffffffu, ok);
-        __threadfence_system();
-        if (!ok) {
-            if (threadIdx.x == 0) {
-                st.done = 1;
-                st.reserved = 1;  // exchange timed out
-                st.fitness = CUDART_NAN;
-                st.inlier_rmse = CUDART_NAN;
-            }
-            return;
-        }
-        if (threadIdx.x < kNS) {
-            double t = 0.0;
-            for (int r = 0; r < px.world; ++r) {
-                const volatile double *d = px.data[px.rank] + peer_data_index(px, r, s);
-                t += d[threadIdx.x];
-            }
-            Sx[threadIdx.x] = t;
-        }
-        __syncwarp();
-    }
-    if (threadIdx.x != 0) return;
-    const double *S = px.world > 0 ? Sx : sums + (int64_t)blockIdx.x * kNS;
-    const double cnt = S[16];
-    const double fitness = ns_total > 0 ? cnt / (double)ns_total : 0.0;
-    const double rmse = cnt > 0.0 ? sqrt(S[15] / cnt) : 0.0;
-    const bool had_prev = st.evals > 0;
-    const double pf = st.fitness, pr = st.inlier_rmse;
-    st.prev_fitness = pf;
-    st.prev_rmse = pr;
-    st.fitness = fitness;
-    st.inlier_rmse = rmse;
-    st.n_corr = (int64_t)cnt;
-    st.evals += 1;
-    if (had_prev && fabs(pf - fitness) < rel_fitness && fabs(pr - rmse) < rel_rmse) {
-        st.done = 1;
-        return;
-    }
-    if (final_eval) {
-        st.done = 1;
-        return;
-    }
-    st.iters += 1;
-    if (!(cnt > 0.0)) return;  // empty correspondence set: U = I
-
-    // Eigen::umeyama without scaling: Sigma = (1/n) sum (t - mu_t)(s - mu_s)^T
-    const double inv = 1.0 / cnt;
-    const double ms[3] = {S[0] * inv, S[1] * inv, S[2] * inv};
-    const double mt[3] = {S[3] * inv, S[4] * inv, S[5] * inv};
-    double Sig[3][3], U[3][3], V[3][3], D[3];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) Sig[i][j] = S[6 + 3 * i + j] * inv - mt[i] * ms[j];
-    svd3(Sig, U, D, V);
-    const double sgn = (det3(U) * det3(V) < 0.0) ? -1.0 : 1.0;
-    double R[3][3];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j)
-            R[i][j] = U[i][0] * V[j][0] + U[i][1] * V[j][1] + sgn * U[i][2] * V[j][2];
-    double tr[3];
-    for (int i = 0; i < 3; ++i)
-        tr[i] = mt[i] - (R[i][0] * ms[0] + R[i][1] * ms[1] + R[i][2] * ms[2]);
-    // T <- [R tr; 0 1] . T
-    double Tn[12];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 4; ++j) {
-            double v = R[i][0] * st.T[0 + j] + R[i][1] * st.T[4 + j] + R[i][2] * st.T[8 + j];
-            if (j == 3) v += tr[i];
-            Tn[4 * i + j] = v;
-        }
-    for (int k = 0; k < 12; ++k) st.T[k] = Tn[k];
-    st.T[12] = 0.0; st.T[13] = 0.0; st.T[14] = 0.0; st.T[15] = 1.0;
+    if (st.done != 0 || threadIdx.x != 0) return;
+    icp_solve_state(st, sums + (int64_t)blockIdx.x * kNS, ns_total, rel_fitness, rel_rmse, final_eval);
 }
 
-// The grid (and with it the grouping of the partial sums) depends on the source size only,
-// never on the batch of starts or the device: a start gives bit-identical sums whether it
-// runs alone or next to 63 others.
+// tgt4[i] = original coordinates of the target point stored at position i (perm NULL: i itself);
+// padded slots hold zeros (never referenced: the search reports real points only)
+__global__ void __launch_bounds__(256)
+icp_gather_tgt4_kernel(const float *__restrict__ tgt, const int32_t *__restrict__ perm, int64_t nt,
+                       int64_t ntp, float4 *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= ntp) return;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nt) {
+        const int64_t j = perm != nullptr ? perm[i] : i;
+        v = make_float4(tgt[3 * j], tgt[3 * j + 1], tgt[3 * j + 2], 0.f);
+    }
+    out[i] = v;
+}
+
+// after the fused loop: correspondences and flags from stored order back to the caller's indexing
+__global__ void __launch_bounds__(256)
+icp_unpermute_kernel(const int32_t *__restrict__ hint, const uint8_t *__restrict__ inl_stored,
+                     const int32_t *__restrict__ perm_q, const int32_t *__restrict__ perm_t, int64_t ns,
+                     int64_t nsp, int64_t nt, int32_t *__restrict__ corr_idx, uint8_t *__restrict__ inlier) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t s = blockIdx.y;
+    if (i >= ns) return;
+    const int64_t io = perm_q != nullptr ? perm_q[i] : i;
+    int j = hint[s * nsp + i];
+    j = j < 0 ? 0 : (j >= nt ? (int)(nt - 1) : j);
+    corr_idx[s * ns + io] = perm_t != nullptr ? perm_t[j] : j;
+    if (inlier != nullptr) inlier[s * ns + io] = inl_stored[s * nsp + i];
+}
+
+// grid of the exact-distance kernel
 static int acc_blocks(int64_t ns) {
-    int64_t want = (ns + kAccThreads * 4 - 1) / (kAccThreads * 4);
+    int64_t want = (ns + 256 * 4 - 1) / (256 * 4);
     if (want > 2048) want = 2048;
     if (want < 1) want = 1;
     return (int)want;
@@ -428,24 +183,32 @@ int icp_search_impl(IsrIcpState *states, int64_t starts, const float *src, const
                     int32_t *corr_idx, void *workspace, size_t workspace_bytes, void *stream, int repeat);
 
 struct IcpLayout {
-    size_t xs, d2, partials, tickets, hint, nnws, total;
-    int nblk;
+    size_t xs, d2, hint, nnws;                    // stepwise search (hint, nnws: both forms)
+    size_t blocksum, groupsum, ftick;             // the fixed-order reduction of the 17 sums (both)
+    size_t src7, tgt4, inl, rowsum;               // fused iteration
+    size_t total;
+    int nqb, ngroups;
 };
 
 static IcpLayout icp_layout(int64_t ns, int64_t nt, int64_t starts) {
     IcpLayout L;
-    const int64_t nsp = isr_soa_padded_len(ns);
+    const int64_t nsp = isr_soa_padded_len(ns), ntp = isr_soa_padded_len(nt);
     size_t off = 0;
     L.xs = off;       off += align256((size_t)starts * 7 * nsp * 4);
     L.d2 = off;       off += align256((size_t)starts * ns * 4);
-    const int64_t max_blk = acc_blocks(ns);
-    L.partials = off; off += align256((size_t)starts * max_blk * kNS * 8);
-    L.tickets = off;  off += align256((size_t)starts * 4);
     L.hint = off;     off += align256((size_t)starts * nsp * 4);
+    L.nqb = nn2_query_blocks(ns);
+    L.ngroups = (L.nqb + kFuseGroup - 1) / kFuseGroup;
+    L.blocksum = off; off += align256((size_t)starts * L.nqb * kNS * 8);
+    L.groupsum = off; off += align256((size_t)starts * L.ngroups * kNS * 8);
+    L.ftick = off;    off += align256((size_t)starts * (L.nqb + L.ngroups + 1) * 4);
+    L.src7 = off;     off += align256((size_t)7 * nsp * 4);
+    L.tgt4 = off;     off += align256((size_t)ntp * 16);
+    L.inl = off;      off += align256((size_t)starts * nsp);
+    L.rowsum = off;   off += align256((size_t)starts * L.nqb * 8 * kNS * 8);
     const size_t w1 = isr_nn_workspace_bytes(ns, nt, starts), w2 = isr_nn2_workspace_bytes(ns, nt, starts);
     L.nnws = off;     off += w1 > w2 ? w1 : w2;
     L.total = off;
-    L.nblk = 0;
     return L;
 }
 
@@ -458,6 +221,7 @@ struct IsrPeer {
     void *mapped[ISR_PEER_MAX_RANKS] = {};     // mapped[rank] == own
     bool connected = false;
     unsigned long long seq = 0;                // number of exchanges enqueued so far
+    long long timeout_cycles = 20000000000ll;  // ~10 s of SM clock
 };
 
 namespace isr {
@@ -473,45 +237,118 @@ static PeerView peer_view(const IsrPeer *p, bool next_message) {
     v.rank = p->rank;
     v.world = p->world;
     v.seq = p->seq + (next_message ? 1 : 0);
+    v.timeout_cycles = p->timeout_cycles;
     return v;
 }
 
-static int accumulate_corr_px(const IsrIcpState *states, int64_t starts, const float *src,
-                              const float *src_lo, int64_t ns, const float *tgt, int64_t nt,
-                              const int32_t *corr_idx, double max_dist, double *sums, uint8_t *inlier,
-                              void *workspace, size_t workspace_bytes, const PeerView &px, void *stream,
-                              int repeat = 0) {
+static int check_workspace(const IcpLayout &L, const void *workspace, size_t workspace_bytes) {
+    ISR_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, ISR_E_WORKSPACE,
+                "icp: workspace %zu < %zu bytes", workspace_bytes, L.total);
+    ISR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ISR_E_ALIGN,
+                "icp: workspace not 256-byte aligned");
+    return ISR_OK;
+}
+
+static int accumulate_corr(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                           const int32_t *src_perm, int64_t ns, const float *tgt, int64_t nt,
+                           const int32_t *corr_idx, double max_dist, double *sums, uint8_t *inlier,
+                           void *workspace, size_t workspace_bytes, void *stream, int repeat = 0) {
     ISR_REQUIRE(starts >= 1 && starts <= 65535 && ns >= 1 && nt >= 1, ISR_E_SHAPE,
                 "icp_accumulate_corr: bad size");
     ISR_REQUIRE(states && src && tgt && corr_idx && sums, ISR_E_INVALID_ARG,
                 "icp_accumulate_corr: null pointer");
     IcpLayout L = icp_layout(ns, nt, starts);
-    ISR_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, ISR_E_WORKSPACE,
-                "icp: workspace %zu < %zu bytes", workspace_bytes, L.total);
-    ISR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ISR_E_ALIGN,
-                "icp: workspace not 256-byte aligned");
+    ISR_TRY(check_workspace(L, workspace, workspace_bytes));
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = reinterpret_cast<char *>(workspace);
-    double *partials = reinterpret_cast<double *>(ws + L.partials);
-    unsigned *tickets = reinterpret_cast<unsigned *>(ws + L.tickets);
-    // (the kernel's last CTA leaves the tickets at zero for the next launch)
-    if (!repeat) ISR_TRY(check_cuda(cudaMemsetAsync(tickets, 0, (size_t)starts * 4, st), "icp memset"));
-    const int nblk = acc_blocks(ns);
-    dim3 grid((unsigned)nblk, (unsigned)starts);
+    IcpFuse f{};
+    f.states = states;
+    f.max_d2 = max_dist * max_dist;
+    f.blocksum = reinterpret_cast<double *>(ws + L.blocksum);
+    f.groupsum = reinterpret_cast<double *>(ws + L.groupsum);
+    f.tickets = reinterpret_cast<unsigned *>(ws + L.ftick);
+    f.sums = sums;
+    f.nqb = L.nqb;
+    f.ngroups = L.ngroups;
+    f.do_solve = 0;
+    // (the last warp of every reduction level leaves its ticket at zero for the next launch)
+    if (!repeat)
+        ISR_TRY(check_cuda(cudaMemsetAsync(f.tickets, 0, (size_t)starts * (L.nqb + L.ngroups + 1) * 4, st),
+                           "icp memset"));
+    constexpr int kWarps = kAccThreads / 32;
+    dim3 grid((unsigned)((L.nqb + kWarps - 1) / kWarps), (unsigned)starts);
     ProfScope prof(kProfIcpAcc, st);
-    icp_accumulate_kernel<<<grid, kAccThreads, 0, st>>>(states, src, src_lo, ns, tgt, corr_idx,
-                                                        max_dist * max_dist, partials, tickets, sums,
-                                                        inlier, px);
-    return launched("icp_accumulate_kernel");
+    icp_accumulate_rows_kernel<<<grid, kAccThreads, 0, st>>>(f, src, src_lo, src_perm, ns, tgt, corr_idx, inlier);
+    return launched("icp_accumulate_rows_kernel");
 }
 
-static int solve_px(IsrIcpState *states, int64_t starts, const double *sums, int64_t ns_total,
-                    double rel_fitness, double rel_rmse, int final_eval, const PeerView &px, void *stream) {
-    ISR_REQUIRE(starts >= 1 && states && sums, ISR_E_INVALID_ARG, "icp_solve: bad argument");
-    ProfScope prof(kProfIcpSolve, (cudaStream_t)stream);
-    icp_solve_kernel<<<(unsigned)starts, 32, 0, (cudaStream_t)stream>>>(
-        states, sums, ns_total, rel_fitness, rel_rmse, final_eval, px);
-    return launched("icp_solve_kernel");
+// The loop of isr_icp_run / isr_icp_run_sharded, one fused launch per evaluation.  `peer` NULL:
+// no exchange (single GPU).
+static int run_fused(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                     const int32_t *src_perm, int64_t ns, int64_t ns_total, const float *tgt,
+                     const IsrCloud *tgt_cloud, const double *centroid, double max_dist, int max_iteration,
+                     double rel_fitness, double rel_rmse, double *sums, int32_t *corr_idx, uint8_t *inlier,
+                     void *workspace, size_t workspace_bytes, IsrPeer *peer, void *stream) {
+    const int64_t nt = tgt_cloud->n;
+    ISR_REQUIRE(starts >= 1 && starts <= 65535 && ns >= 1 && nt >= 1, ISR_E_SHAPE, "icp_run: bad size");
+    ISR_REQUIRE(states && src && centroid && corr_idx, ISR_E_INVALID_ARG, "icp_run: null pointer");
+    ISR_REQUIRE(tgt_cloud->bstride == 0, ISR_E_SHAPE, "icp: the target cloud is shared by all starts");
+    const IcpLayout L = icp_layout(ns, nt, starts);
+    ISR_TRY(check_workspace(L, workspace, workspace_bytes));
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = reinterpret_cast<char *>(workspace);
+    const int64_t nsp = isr_soa_padded_len(ns), ntp = tgt_cloud->npad;
+    float *src7 = reinterpret_cast<float *>(ws + L.src7);
+    float4 *tgt4 = reinterpret_cast<float4 *>(ws + L.tgt4);
+    int32_t *hint = reinterpret_cast<int32_t *>(ws + L.hint);
+    uint8_t *inl = reinterpret_cast<uint8_t *>(ws + L.inl);
+    unsigned *ftick = reinterpret_cast<unsigned *>(ws + L.ftick);
+
+    // once per run: the source as stored-order hi/lo planes (identity pose, no centring), the
+    // target's original coordinates as 16-byte rows in stored order, empty hints, zero tickets
+    ISR_TRY(isr_prepare_cloud(src, src_lo, src_perm, ns, nullptr, 16, nullptr, 16, nullptr, 1, src7, nsp,
+                              nullptr, 0, stream));
+    icp_gather_tgt4_kernel<<<(unsigned)((ntp + 255) / 256), 256, 0, st>>>(tgt, tgt_cloud->perm, nt, ntp, tgt4);
+    ISR_TRY(launched("icp_gather_tgt4_kernel"));
+    {
+        const long long total = (long long)starts * nsp;
+        icp_hint_reset_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(states, nsp, total, hint);
+        ISR_TRY(launched("icp_hint_reset_kernel"));
+    }
+    ISR_TRY(check_cuda(cudaMemsetAsync(ftick, 0, (size_t)starts * (L.nqb + L.ngroups + 1) * 4, st), "icp memset"));
+
+    IcpFuse f{};
+    f.states = states;
+    f.src7 = src7;
+    f.tgt4 = tgt4;
+    f.centroid = centroid;
+    f.max_d2 = max_dist * max_dist;
+    f.rowsum = reinterpret_cast<double *>(ws + L.rowsum);
+    f.blocksum = reinterpret_cast<double *>(ws + L.blocksum);
+    f.groupsum = reinterpret_cast<double *>(ws + L.groupsum);
+    f.tickets = ftick;
+    f.sums = sums;
+    f.inlier = inl;
+    f.nqb = L.nqb;
+    f.ngroups = L.ngroups;
+    f.ns_total = ns_total;
+    f.rel_fitness = rel_fitness;
+    f.rel_rmse = rel_rmse;
+    f.do_solve = 1;
+    // the query "cloud" of the fused search: the original source planes, shared by all starts
+    const IsrCloud src_cloud{src7, ns, nsp, 0, nullptr, src_perm, nullptr, hint, nullptr};
+    const int32_t *done = &states[0].done;  // device address arithmetic only
+    for (int k = 0; k <= max_iteration; ++k) {
+        f.final_eval = k == max_iteration ? 1 : 0;
+        f.px = peer_view(peer, true);  // world == 0 without a peer
+        const int s = nn2_search(&src_cloud, tgt_cloud, starts, 1, nullptr, nullptr, done, kStateInts,
+                                 ws + L.nnws, L.total - L.nnws, stream, k > 0, &f);
+        if (peer != nullptr && s == ISR_OK) peer->seq += 1;  // the launch exists: so does its message
+        ISR_TRY(s);
+    }
+    dim3 grid((unsigned)((ns + 255) / 256), (unsigned)starts);
+    icp_unpermute_kernel<<<grid, 256, 0, st>>>(hint, inl, src_perm, tgt_cloud->perm, ns, nsp, nt, corr_idx, inlier);
+    return launched("icp_unpermute_kernel");
 }
 
 }  // namespace isr
@@ -562,6 +399,16 @@ int isr_peer_connect(IsrPeer *p, const unsigned char *handles) {
     return ISR_OK;
 }
 
+int isr_peer_set_timeout(IsrPeer *p, double seconds) {
+    using namespace isr;
+    ISR_REQUIRE(p != nullptr && seconds > 0.0, ISR_E_INVALID_ARG, "peer_set_timeout: bad argument");
+    int khz = 0;
+    ISR_TRY(isr_device_info(nullptr, &khz, nullptr));
+    const double cycles = seconds * (double)khz * 1e3;
+    p->timeout_cycles = cycles > 9e18 ? (long long)9e18 : (long long)cycles;
+    return ISR_OK;
+}
+
 int isr_peer_destroy(IsrPeer *p) {
     using namespace isr;
     if (p == nullptr) return ISR_OK;
@@ -589,9 +436,9 @@ int isr_icp_search(IsrIcpState *states, int64_t starts, const float *src, const 
 
 namespace isr {
 
-// `repeat` != 0: this is not the first evaluation of a loop that this library drives
-// (isr_icp_run*): the hints hold the previous correspondences (no reset needed) and the
-// launch order of the search is still in the workspace.
+// `repeat` != 0: this is not the first evaluation of a loop that this library drives: the hints
+// hold the previous correspondences (no reset needed) and the launch order of the search is
+// still in the workspace.
 int icp_search_impl(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
                     const int32_t *src_perm, int64_t ns, const IsrCloud *tgt_cloud, const double *centroid,
                     int32_t *corr_idx, void *workspace, size_t workspace_bytes, void *stream, int repeat) {
@@ -605,10 +452,7 @@ int icp_search_impl(IsrIcpState *states, int64_t starts, const float *src, const
     ISR_REQUIRE(tgt_cloud->bstride == 0, ISR_E_SHAPE, "icp: the target cloud is shared by all starts");
     ISR_REQUIRE(starts <= 65535, ISR_E_SHAPE, "icp: starts %lld > 65535", (long long)starts);
     IcpLayout L = icp_layout(ns, nt, starts);
-    ISR_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, ISR_E_WORKSPACE,
-                "icp: workspace %zu < %zu bytes", workspace_bytes, L.total);
-    ISR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ISR_E_ALIGN,
-                "icp: workspace not 256-byte aligned");
+    ISR_TRY(check_workspace(L, workspace, workspace_bytes));
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = reinterpret_cast<char *>(workspace);
     float *xs = reinterpret_cast<float *>(ws + L.xs);
@@ -628,7 +472,25 @@ int icp_search_impl(IsrIcpState *states, int64_t starts, const float *src, const
     }
     const IsrCloud src_cloud{xs, ns, nsp, 7 * nsp, nullptr, src_perm, nullptr, hint, nullptr};
     return nn2_search(&src_cloud, tgt_cloud, starts, 1, d2, corr_idx, done, kStateInts, ws + L.nnws,
-                      L.total - L.nnws, stream, repeat);
+                      L.total - L.nnws, stream, repeat, nullptr);
+}
+
+// The stepwise loop (exhaustive search, or a target without tile spheres): K1' + K2 + accumulate
+// + solve per evaluation.
+static int run_stepwise(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                        const int32_t *src_perm, int64_t ns, const float *tgt, const IsrCloud *tgt_cloud,
+                        const double *centroid, double max_dist, int max_iteration, double rel_fitness,
+                        double rel_rmse, double *sums, int32_t *corr_idx, uint8_t *inlier, void *workspace,
+                        size_t workspace_bytes, void *stream) {
+    for (int k = 0; k <= max_iteration; ++k) {
+        ISR_TRY(icp_search_impl(states, starts, src, src_lo, src_perm, ns, tgt_cloud, centroid, corr_idx,
+                                workspace, workspace_bytes, stream, k > 0));
+        ISR_TRY(accumulate_corr(states, starts, src, src_lo, src_perm, ns, tgt, tgt_cloud->n, corr_idx, max_dist,
+                                sums, inlier, workspace, workspace_bytes, stream, k > 0));
+        ISR_TRY(isr_icp_solve(states, starts, sums, ns, rel_fitness, rel_rmse, k == max_iteration ? 1 : 0,
+                              stream));
+    }
+    return ISR_OK;
 }
 
 }  // namespace isr
@@ -646,8 +508,8 @@ int isr_icp_corr_dist(const IsrIcpState *states, int64_t starts, const float *sr
     return launched("icp_corr_dist_kernel");
 }
 
-int isr_icp_accumulate_corr(const IsrIcpState *states, int64_t starts, const float *src,
-                            const float *src_lo, int64_t ns, const float *tgt, int64_t nt,
+int isr_icp_accumulate_corr(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
+                            const int32_t *src_perm, int64_t ns, const float *tgt, int64_t nt,
                             const int32_t *corr_idx, double max_dist, double *sums, uint8_t *inlier,
                             void *workspace, size_t workspace_bytes, void *stream) {
     using namespace isr;
@@ -657,8 +519,8 @@ int isr_icp_accumulate_corr(const IsrIcpState *states, int64_t starts, const flo
         return check_cuda(cudaMemsetAsync(sums, 0, (size_t)starts * kNS * 8, (cudaStream_t)stream),
                           "icp memset");
     }
-    return accumulate_corr_px(states, starts, src, src_lo, ns, tgt, nt, corr_idx, max_dist, sums, inlier,
-                              workspace, workspace_bytes, PeerView{}, stream);
+    return accumulate_corr(states, starts, src, src_lo, src_perm, ns, tgt, nt, corr_idx, max_dist, sums, inlier,
+                           workspace, workspace_bytes, stream);
 }
 
 int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
@@ -672,14 +534,18 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src, co
     if (max_dist > 0.0)
         ISR_TRY(isr_icp_search(states, starts, src, src_lo, src_perm, ns, tgt_cloud, centroid, corr_idx,
                                workspace, workspace_bytes, stream));
-    return isr_icp_accumulate_corr(states, starts, src, src_lo, ns, tgt, tgt_cloud->n, corr_idx, max_dist,
-                                   sums, inlier, workspace, workspace_bytes, stream);
+    return isr_icp_accumulate_corr(states, starts, src, src_lo, src_perm, ns, tgt, tgt_cloud->n, corr_idx,
+                                   max_dist, sums, inlier, workspace, workspace_bytes, stream);
 }
 
 int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64_t ns_total,
                   double rel_fitness, double rel_rmse, int final_eval, void *stream) {
-    return isr::solve_px(states, starts, sums, ns_total, rel_fitness, rel_rmse, final_eval,
-                         isr::PeerView{}, stream);
+    using namespace isr;
+    ISR_REQUIRE(starts >= 1 && states && sums, ISR_E_INVALID_ARG, "icp_solve: bad argument");
+    ProfScope prof(kProfIcpSolve, (cudaStream_t)stream);
+    icp_solve_kernel<<<(unsigned)starts, 32, 0, (cudaStream_t)stream>>>(states, sums, ns_total, rel_fitness,
+                                                                        rel_rmse, final_eval);
+    return launched("icp_solve_kernel");
 }
 
 int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
@@ -691,20 +557,24 @@ int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const flo
     ISR_REQUIRE(max_iteration >= 0, ISR_E_INVALID_ARG, "icp_run: max_iteration < 0");
     ISR_REQUIRE(tgt_cloud != nullptr && tgt != nullptr && sums != nullptr, ISR_E_INVALID_ARG,
                 "icp_run: null pointer");
-    for (int k = 0; k <= max_iteration; ++k) {
-        if (max_dist > 0.0) {
-            ISR_TRY(icp_search_impl(states, starts, src, src_lo, src_perm, ns, tgt_cloud, centroid, corr_idx,
-                                    workspace, workspace_bytes, stream, k > 0));
-            ISR_TRY(accumulate_corr_px(states, starts, src, src_lo, ns, tgt, tgt_cloud->n, corr_idx, max_dist,
-                                       sums, inlier, workspace, workspace_bytes, PeerView{}, stream, k > 0));
-        } else {
-            ISR_TRY(isr_icp_accumulate_corr(states, starts, src, src_lo, ns, tgt, tgt_cloud->n, corr_idx,
-                                            max_dist, sums, inlier, workspace, workspace_bytes, stream));
+    if (max_dist <= 0.0) {
+        // upstream: a non-positive distance yields an empty correspondence set in every evaluation
+        for (int k = 0; k <= max_iteration; ++k) {
+            ISR_TRY(isr_icp_accumulate_corr(states, starts, src, src_lo, src_perm, ns, tgt, tgt_cloud->n,
+                                            corr_idx, max_dist, sums, inlier, workspace, workspace_bytes,
+                                            stream));
+            ISR_TRY(isr_icp_solve(states, starts, sums, ns, rel_fitness, rel_rmse,
+                                  k == max_iteration ? 1 : 0, stream));
         }
-        ISR_TRY(isr_icp_solve(states, starts, sums, ns, rel_fitness, rel_rmse,
-                              k == max_iteration ? 1 : 0, stream));
+        return ISR_OK;
     }
-    return ISR_OK;
+    if (nn2_fusable(tgt_cloud))
+        return run_fused(states, starts, src, src_lo, src_perm, ns, ns, tgt, tgt_cloud, centroid, max_dist,
+                         max_iteration, rel_fitness, rel_rmse, sums, corr_idx, inlier, workspace,
+                         workspace_bytes, nullptr, stream);
+    return run_stepwise(states, starts, src, src_lo, src_perm, ns, tgt, tgt_cloud, centroid, max_dist,
+                        max_iteration, rel_fitness, rel_rmse, sums, corr_idx, inlier, workspace,
+                        workspace_bytes, stream);
 }
 
 int isr_icp_run_sharded(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
@@ -723,27 +593,21 @@ int isr_icp_run_sharded(IsrIcpState *states, int64_t starts, const float *src, c
                 "icp_run_sharded: null pointer");
     ISR_REQUIRE(ns >= 1 && ns_total >= ns, ISR_E_SHAPE, "icp_run_sharded: ns %lld, ns_total %lld",
                 (long long)ns, (long long)ns_total);
-    for (int k = 0; k <= max_iteration; ++k) {
-        if (max_dist > 0.0) {
-            ISR_TRY(icp_search_impl(states, starts, src, src_lo, src_perm, ns, tgt_cloud, centroid, corr_idx,
-                                    workspace, workspace_bytes, stream, k > 0));
-            // the message number advances only once both kernels of the pair are enqueued
-            const PeerView px = peer_view(peer, true);
-            ISR_TRY(accumulate_corr_px(states, starts, src, src_lo, ns, tgt, tgt_cloud->n, corr_idx, max_dist,
-                                       sums, inlier, workspace, workspace_bytes, px, stream, k > 0));
-            const int s = solve_px(states, starts, sums, ns_total, rel_fitness, rel_rmse,
-                                   k == max_iteration ? 1 : 0, px, stream);
-            peer->seq += 1;  // the accumulate kernel has been launched: its message exists
-            ISR_TRY(s);
-        } else {
-            // no correspondences anywhere: every rank's sums are zero, nothing to exchange
+    if (max_dist <= 0.0) {
+        // no correspondences anywhere: every rank's sums are zero, nothing to exchange
+        for (int k = 0; k <= max_iteration; ++k) {
             ISR_TRY(check_cuda(cudaMemsetAsync(sums, 0, (size_t)starts * kNS * 8, (cudaStream_t)stream),
                                "icp memset"));
-            ISR_TRY(solve_px(states, starts, sums, ns_total, rel_fitness, rel_rmse,
-                             k == max_iteration ? 1 : 0, PeerView{}, stream));
+            ISR_TRY(isr_icp_solve(states, starts, sums, ns_total, rel_fitness, rel_rmse,
+                                  k == max_iteration ? 1 : 0, stream));
         }
+        return ISR_OK;
     }
-    return ISR_OK;
+    ISR_REQUIRE(nn2_fusable(tgt_cloud), ISR_E_INVALID_ARG,
+                "icp_run_sharded: needs the pruned search (target tile spheres, isr_set_nn_pruning(1))");
+    return run_fused(states, starts, src, src_lo, src_perm, ns, ns_total, tgt, tgt_cloud, centroid, max_dist,
+                     max_iteration, rel_fitness, rel_rmse, sums, corr_idx, inlier, workspace, workspace_bytes,
+                     peer, stream);
 }
 
 }  // extern "C"

@@ -64,9 +64,15 @@ struct ProfScope {
 // (the ICP loop): reuse_order != 0 keeps the launch order of the pruned kernel's query blocks
 // that the previous call left in `workspace` (block weights are invariant under the rigid
 // motion between two iterations) instead of recomputing it.
+// `fuse` (icp_device.cuh), when not NULL, turns the search into one whole ICP evaluation + update:
+// q->soa7 then holds the ORIGINAL source planes (the kernel applies the pose itself) and nothing
+// is written to out_d2 / out_idx.  nn2_fusable: the pruned search would be used for this target.
+struct IcpFuse;
 int nn2_search(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, float *out_d2,
                int32_t *out_idx, const int32_t *skip, int64_t skip_stride, void *workspace,
-               size_t workspace_bytes, void *stream, int reuse_order);
+               size_t workspace_bytes, void *stream, int reuse_order, const IcpFuse *fuse);
+bool nn2_fusable(const IsrCloud *t);
+int nn2_query_blocks(int64_t nq);  // 256-query blocks of the pruned search
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }

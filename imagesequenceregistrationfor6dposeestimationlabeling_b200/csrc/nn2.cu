@@ -58,6 +58,7 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#include "icp_device.cuh"
 #include "isr_common.cuh"
 
 namespace isr {
@@ -583,9 +584,27 @@ struct alignas(128) PrunedWarpSmem {
     float qs[6][32 * Q];       // the warp's queries, hi xyz and lo xyz (read by the scan and the resolve path)
 };
 
-template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS, int GROUPS = 2>
-__global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2Params p) {
+// rows of a query block that launch-list code `rowsel` stands for: 0 all eight, 1..8 one row,
+// 9 / 10 a half (rows 0-3 / 4-7), 11..14 a quarter (rows 2k, 2k + 1)
+__host__ __device__ inline unsigned rows_of_code(int rowsel) {
+    if (rowsel == 0) return 0xFFu;
+    if (rowsel <= 8) return 1u << (rowsel - 1);
+    if (rowsel <= 10) return 0x0Fu << (4 * (rowsel - 9));
+    return 0x03u << (2 * (rowsel - 11));
+}
+// launch-list code of part c of a block that runs as `parts` CTAs
+__host__ __device__ inline int code_of_part(int parts, int c) {
+    return parts == 1 ? 0 : parts == 2 ? 9 + c : parts == 4 ? 11 + c : 1 + c;
+}
+
+// FUSED: the kernel is one whole ICP evaluation + update (IcpFuse, icp_device.cuh): the queries
+// are made from the original source and the start's pose in the prologue, and the epilogue turns
+// the neighbours into the 17 correspondence sums, reduces them across the grid and solves.
+template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS, int GROUPS = 2, bool FUSED = false>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     static_assert(SUB == ISR_SUB_TILE && ISR_SOA_TILE / SUB == 16 && Q == 8, "pruning uses the spheres of prepare.cu");
+    static_assert(!FUSED || WARPS == 1, "the fused tail is per one-warp CTA");
     constexpr int SUBS = ISR_SOA_TILE / SUB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.z;
@@ -600,16 +619,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
         if ((int)blockIdx.x >= p.order_count[b]) return;
         const int entry = p.order[(long long)b * gridDim.x + blockIdx.x];
         blk = entry & 0xFFFFFF;
-        rowsel = entry >> 24;  // 0: all rows; r + 1: only row r; 9 / 10: rows 0-3 / 4-7
+        rowsel = entry >> 24;  // rows_of_code
     }
+    const unsigned own = rows_of_code(rowsel);  // rows this CTA is responsible for
     const int q0 = blk * (WARPS * 32 * Q) + warp * (32 * Q) + lane;
-    if (q0 - lane >= p.nq) return;  // this warp has no live query; warps never meet at a barrier
+    if (!FUSED && q0 - lane >= p.nq) return;  // this warp has no live query; warps never meet at a barrier
     unsigned livemask = 0;  // bit r: query r * 32 + lane exists and belongs to this CTA
 #pragma unroll
     for (int r = 0; r < Q; ++r)
-        if (q0 + r * 32 < p.nq && (rowsel == 0 || rowsel - 1 == r || (rowsel > Q && rowsel - 1 - Q == r / (Q / 2))))
-            livemask |= 1u << r;
-    if (__ballot_sync(0xffffffffu, livemask != 0) == 0) return;
+        if (q0 + r * 32 < p.nq && ((own >> r) & 1u)) livemask |= 1u << r;
+    const unsigned liverows = __reduce_or_sync(0xffffffffu, livemask);  // rows with a live query
+    if (liverows == 0) {
+        if (FUSED) {  // nothing to search, but the reduction counts on every CTA of the launch list
+            double rs0[Q];
+#pragma unroll 1
+            for (int r = 0; r < Q; ++r) rs0[r] = 0.0;
+            icp_fused_tail(f, b, blk, own, lane, rs0);
+        }
+        return;
+    }
     const long long t_start = clock64();
     PrunedWarpSmem<SUB, Q> &ws = reinterpret_cast<PrunedWarpSmem<SUB, Q> *>(smem_raw)[warp];
     const float *__restrict__ gq = p.q + (long long)b * p.q_bstride;
@@ -634,16 +662,41 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     double Dbest_l[Q];
     int ibest_l[Q];
     float dmax = 0.f;  // max over the lane's live queries of dq_l (0: no live query)
+    double Tf[12], cf[3];  // FUSED: the start's pose and the centre of the prepared target
+    if (FUSED) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) Tf[k] = f.states[b].T[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cf[k] = f.centroid[k];
+    }
 #pragma unroll 1
     for (int r = 0; r < Q; ++r) {
         const int i = min(q0 + r * 32, p.nq_pad - 1);
-        ws.qs[0][r * 32 + lane] = gq[i];
-        ws.qs[1][r * 32 + lane] = gq[p.nq_pad + i];
-        ws.qs[2][r * 32 + lane] = gq[2ll * p.nq_pad + i];
-        if (p.use_lo) {
-            ws.qs[3][r * 32 + lane] = gq[4ll * p.nq_pad + i];
-            ws.qs[4][r * 32 + lane] = gq[5ll * p.nq_pad + i];
-            ws.qs[5][r * 32 + lane] = gq[6ll * p.nq_pad + i];
+        if (FUSED) {
+            // the arithmetic of prepare_soa7_kernel: FP64 R p + t - c, split into a float32 hi/lo pair
+            float hx = ISR_PAD_COORD, hy = ISR_PAD_COORD, hz = ISR_PAD_COORD, lx = 0.f, ly = 0.f, lz = 0.f;
+            if (q0 + r * 32 < p.nq) {
+                const float *s7 = f.src7;
+                const double px = (double)s7[i] + (double)s7[4ll * p.nq_pad + i];
+                const double py = (double)s7[p.nq_pad + i] + (double)s7[5ll * p.nq_pad + i];
+                const double pz = (double)s7[2ll * p.nq_pad + i] + (double)s7[6ll * p.nq_pad + i];
+                double x, y, z;
+                icp_apply_pose(Tf, px, py, pz, x, y, z);
+                x -= cf[0]; y -= cf[1]; z -= cf[2];
+                hx = (float)x; hy = (float)y; hz = (float)z;
+                lx = (float)(x - (double)hx); ly = (float)(y - (double)hy); lz = (float)(z - (double)hz);
+            }
+            ws.qs[0][r * 32 + lane] = hx; ws.qs[1][r * 32 + lane] = hy; ws.qs[2][r * 32 + lane] = hz;
+            ws.qs[3][r * 32 + lane] = lx; ws.qs[4][r * 32 + lane] = ly; ws.qs[5][r * 32 + lane] = lz;
+        } else {
+            ws.qs[0][r * 32 + lane] = gq[i];
+            ws.qs[1][r * 32 + lane] = gq[p.nq_pad + i];
+            ws.qs[2][r * 32 + lane] = gq[2ll * p.nq_pad + i];
+            if (p.use_lo) {
+                ws.qs[3][r * 32 + lane] = gq[4ll * p.nq_pad + i];
+                ws.qs[4][r * 32 + lane] = gq[5ll * p.nq_pad + i];
+                ws.qs[5][r * 32 + lane] = gq[6ll * p.nq_pad + i];
+            }
         }
         const bool live = (livemask >> r) & 1u;
         if (live) dmax = CUDART_INF_F;
@@ -816,11 +869,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
     if (lane < kAnchors) ws.seed[lane] = -1;
     __syncwarp();
     if (!all_hinted) {  // (a fully hinted warp already holds near-final bounds)
-        // anchors: the centres of the query rows (a dead row falls back to row 0, which always
-        // holds a live query); a run-time loop over the anchors, like everything per row
+        // anchors: the centres of the query rows (a dead row falls back to the first live one);
+        // a run-time loop over the anchors, like everything per row
 #pragma unroll 1
         for (int a = 0; a < kAnchors && a < p.nanchors; ++a) {
-            const float4 R = ws.row[a].w >= 0.f ? ws.row[a] : ws.row[0];
+            const float4 R = ws.row[a].w >= 0.f ? ws.row[a] : ws.row[__ffs(liverows) - 1];
             u64 bk = ~0ull;
             for (int base = 0; base < stages; base += 32) {
                 const int s = base + lane;
@@ -1091,16 +1144,65 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nn2_pruned_kernel(const NN2P
                                        (unsigned long long)(ntests & 0xFFFFFFu));
     }
 
+    if (FUSED) {
+        // ---- correspondences -> per-row sums (icp_device.cuh) --------------------------------------
+        // Distances are re-derived in FP64 from the ORIGINAL source point, the FP64 pose and the
+        // neighbour's original float32 coordinates (one 16-byte gather; neighbours of consecutive
+        // stored queries are stored close together): the strict d2 < max_d2 test, fitness, rmse
+        // and the Kabsch sums carry no FP32 error, only the choice of neighbour was made in FP32.
+        using WS = PrunedWarpSmem<SUB, Q>;
+        static_assert(offsetof(WS, sph) == sizeof(WS::buf) &&
+                          sizeof(WS::buf) + sizeof(WS::sph) >= 32 * kNS * sizeof(double),
+                      "the row reduction borrows the (idle) ring buffer and FIFO");
+        double *scratch = reinterpret_cast<double *>(&ws.buf[0][0][0]);  // [32 lanes][17]
+        __syncwarp();
+        double Te[12];  // (re-read: the pose must not sit in registers across the search)
+#pragma unroll
+        for (int k = 0; k < 12; ++k) Te[k] = __ldcg(&f.states[b].T[k]);
+        double rs[Q];
 #pragma unroll 1
-    for (int r = 0; r < Q; ++r) {
-        const int i = q0 + r * 32;
-        if ((livemask >> r) & 1u) {
-            const int io = p.perm_q != nullptr ? p.perm_q[i] : i;
-            const int jo = p.perm_t != nullptr ? p.perm_t[min(ibest_l[r], p.nt - 1)] : ibest_l[r];
-            const long long o = (long long)b * p.nq + io;
-            p.out_d2[o] = (float)Dbest_l[r];
-            if (p.out_idx != nullptr) p.out_idx[o] = jo;
-            if (p.hint != nullptr) p.hint[(long long)b * p.nq_pad + i] = ibest_l[r];
+        for (int r = 0; r < Q; ++r) rs[r] = 0.0;
+#pragma unroll 1
+        for (int r = 0; r < Q; ++r) {
+            if (!((own >> r) & 1u)) continue;  // warp-uniform
+            double c[kNS];
+#pragma unroll
+            for (int k = 0; k < kNS; ++k) c[k] = 0.0;
+            if ((livemask >> r) & 1u) {
+                const int i = q0 + r * 32;
+                const int j = ibest_l[r];
+                p.hint[(long long)b * p.nq_pad + i] = j;
+                const float4 t4 = f.tgt4[j];
+                const float *s7 = f.src7;
+                const double px = (double)s7[i] + (double)s7[4ll * p.nq_pad + i];
+                const double py = (double)s7[p.nq_pad + i] + (double)s7[5ll * p.nq_pad + i];
+                const double pz = (double)s7[2ll * p.nq_pad + i] + (double)s7[6ll * p.nq_pad + i];
+                double sx, sy, sz;
+                icp_apply_pose(Te, px, py, pz, sx, sy, sz);
+                const double d2 = icp_dist2(sx, sy, sz, (double)t4.x, (double)t4.y, (double)t4.z);
+                const bool in = d2 < f.max_d2;
+                f.inlier[(long long)b * p.nq_pad + i] = in ? 1 : 0;
+                if (in) icp_contrib(sx, sy, sz, (double)t4.x, (double)t4.y, (double)t4.z, d2, c);
+            }
+#pragma unroll
+            for (int k = 0; k < kNS; ++k) scratch[lane * kNS + k] = c[k];
+            __syncwarp();
+            rs[r] = icp_row_sum(scratch, lane);  // lane k: component k over the row's 32 queries
+            __syncwarp();
+        }
+        icp_fused_tail(f, b, blk, own, lane, rs);
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < Q; ++r) {
+            const int i = q0 + r * 32;
+            if ((livemask >> r) & 1u) {
+                const int io = p.perm_q != nullptr ? p.perm_q[i] : i;
+                const int jo = p.perm_t != nullptr ? p.perm_t[min(ibest_l[r], p.nt - 1)] : ibest_l[r];
+                const long long o = (long long)b * p.nq + io;
+                p.out_d2[o] = (float)Dbest_l[r];
+                if (p.out_idx != nullptr) p.out_idx[o] = jo;
+                if (p.hint != nullptr) p.hint[(long long)b * p.nq_pad + i] = ibest_l[r];
+            }
         }
     }
 }
@@ -1160,7 +1262,7 @@ block_weight_kernel(const float *__restrict__ q, long long q_bstride, int nq, in
 // into Q single-row entries, everything else follows as whole blocks in descending weight.
 constexpr int kSplitMax = 128;  // (512 was measured slower: 25 % more total work, tail no longer the limit)
 __global__ void __launch_bounds__(1024)
-block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, int split_max, int halve,
+block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, int split_max, int parts,
                    float split_factor, int *__restrict__ order, int *__restrict__ order_count) {
     __shared__ u64 s[kOrderMax];
     __shared__ int nsplit;
@@ -1186,7 +1288,7 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
         int h = 0;
         while (h < split_max && h < nqb && __uint_as_float(~(unsigned)(s[h] >> 32)) > split_factor * wmed) ++h;
         nsplit = h;
-        order_count[b] = (halve ? 2 : 1) * (nqb - h) + rows * h;
+        order_count[b] = parts * (nqb - h) + rows * h;
     }
     __syncthreads();
     const int h = nsplit;
@@ -1195,13 +1297,11 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
         const int blk = (int)(unsigned)(s[i] & 0xffffffffull);
         if (i < h) {
             for (int r = 0; r < rows; ++r) out[i * rows + r] = blk | ((r + 1) << 24);
-        } else if (halve) {
-            // a grid less than a few waves deep: every block runs as two CTAs of 4 query rows
-            // (the scan skips the dead half, so the split costs little and halves the tail)
-            out[h * rows + 2 * (i - h)] = blk | ((rows + 1) << 24);
-            out[h * rows + 2 * (i - h) + 1] = blk | ((rows + 2) << 24);
         } else {
-            out[h * rows + (i - h)] = blk;
+            // a grid that does not fill the machine: every block runs as `parts` CTAs of 8 / parts
+            // query rows (the scan skips the rows a CTA does not own, so the split costs little
+            // and shortens the tail)
+            for (int c = 0; c < parts; ++c) out[h * rows + parts * (i - h) + c] = blk | (code_of_part(parts, c) << 24);
         }
     }
 }
@@ -1236,7 +1336,8 @@ struct NN2Variant {
     static constexpr bool kPrune = false;
     static constexpr size_t kSmem = (size_t)NSTAGES * 4 * STAGE * 4 + NSTAGES * 8;
 
-    static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
+    static constexpr bool kFused = false;
+    static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &) {
         auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR>;
         static thread_local int configured_dev = -1;
         int dev = 0;
@@ -1252,7 +1353,7 @@ struct NN2Variant {
         return launched("nn2_kernel");
     }
 
-    static int ctas_per_sm() {
+    static int ctas_per_sm(bool) {
         int n = 0;
         auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
@@ -1266,15 +1367,16 @@ struct NN2Variant {
 using NN2Main = NN2Variant<8, 128, 1024, 3, 64, 4, 1>;
 
 // the pruned kernel: WARPS independent warps of 32 x Q queries per CTA
-template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS, int GROUPS = 2>
+template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS, int GROUPS = 2, bool FUSED = false>
 struct NN2PrunedVariant {
     static constexpr int kQueriesPerCta = Q * WARPS * 32;
     static constexpr int kStage = ISR_SOA_TILE;
     static constexpr bool kPrune = true;
+    static constexpr bool kFused = FUSED;
     static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q>);
 
-    static int launch(const NN2Params &p, dim3 grid, cudaStream_t st) {
-        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS, GROUPS>;
+    static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &fuse) {
+        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS, GROUPS, FUSED>;
         static thread_local int configured_dev = -1;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -1289,10 +1391,15 @@ struct NN2PrunedVariant {
         // the lo planes of the query copy (last 3 KB of the per-warp block) are only touched
         // when the search uses the lo parts
         const size_t smem = WARPS == 1 && !p.use_lo ? kSmem - 3 * 32 * Q * sizeof(float) : kSmem;
-        kern<<<grid, WARPS * 32, smem, st>>>(p);
-        return launched("nn2_pruned_kernel");
+        kern<<<grid, WARPS * 32, smem, st>>>(p, fuse);
+        return launched(FUSED ? "nn2_pruned_kernel<fused icp>" : "nn2_pruned_kernel");
     }
-    static int ctas_per_sm() { return MINB; }
+    // resident CTAs per SM: MINB by registers; by shared memory fewer when the lo planes are kept
+    static int ctas_per_sm(bool use_lo) {
+        const size_t smem = (WARPS == 1 && !use_lo ? kSmem - 3 * 32 * Q * sizeof(float) : kSmem) + 1024;
+        const int by_smem = (int)((size_t)233472 / smem);
+        return by_smem < MINB ? by_smem : MINB;
+    }
 };
 // one warp per CTA: a finished warp frees its slot at once (measured 5 % faster than 4-warp
 // CTAs, whose slowest warp holds the registers and shared memory of the other three)
@@ -1314,6 +1421,8 @@ struct NN2PrunedVariant {
 // when both quarters are needed -- kept config 5 at 0.30 s but gave the 4 % on verification back)
 using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4>;
 using NN2PrunedHalves = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2>;
+using NN2PrunedFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4, true>;
+using NN2PrunedHalvesFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2, true>;
 #ifdef ISR_NN_TUNING
 using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 2>;
 using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 4>;
@@ -1364,10 +1473,15 @@ static int choose_splits(long long ctas, int stages, int slots) {
 }
 
 static size_t order_workspace_bytes(long long nqb, long long batch) {
-    // keys, launch list (room for every block as two halves and kSplitMax = 128 blocks split into
-    // 8 rows), entry counts
-    return align256((size_t)nqb * batch * 8) + align256((size_t)(2 * nqb + 7 * 128) * batch * 4) +
+    // keys, launch list (room for every block as 8 single-row entries), entry counts
+    return align256((size_t)nqb * batch * 8) + align256((size_t)(8 * nqb) * batch * 4) +
            align256((size_t)batch * 4);
+}
+
+// run-time tuning knob, read once: ISR_<name> in the environment, else the default
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e != nullptr && *e != 0 ? atoi(e) : dflt;
 }
 
 struct NN2Call {
@@ -1380,6 +1494,7 @@ struct NN2Call {
     void *workspace; size_t workspace_bytes;
     cudaStream_t st;
     int reuse_order;
+    const IcpFuse *fuse;  // the fused ICP iteration (icp_device.cuh), or NULL
 };
 
 template <class V>
@@ -1387,8 +1502,7 @@ static int nn2_dispatch(const NN2Call &c) {
     const int64_t nq = c.q->n;
     const int nqb = (int)((nq + V::kQueriesPerCta - 1) / V::kQueriesPerCta);
     const int stages = (int)(c.t->npad / V::kStage);
-    static thread_local int slots = 0;
-    if (slots == 0) slots = sm_count() * V::ctas_per_sm();
+    const int slots = sm_count() * V::ctas_per_sm(c.use_lo != 0);  // (per call: the device may differ)
     // a pruning CTA needs the whole target range: its bound comes from the nearest stage
     int splits = V::kPrune ? 1 : choose_splits((long long)nqb * c.batch, stages, slots);
     const int per = (stages + splits - 1) / splits;
@@ -1439,15 +1553,16 @@ static int nn2_dispatch(const NN2Call &c) {
         if (const char *e = getenv("ISR_NN_SPLIT_MAX")) { if (split_max) split_max = atoi(e); }
         if (const char *e = getenv("ISR_NN_SPLIT_THR")) split_factor = (float)atof(e);
 #endif
-        // a grid that fills less than half of the machine runs every block as two CTAs of 4
-        // query rows (measured, ICP search: 100k points 0.203 -> 0.163 ms, 250k 0.248 -> 0.206 ms;
-        // from one full wave on -- 500k, 1M points -- the repeated per-CTA tests cost more than
-        // the shorter tail gains: 0.350 -> 0.381 ms, 0.63 -> 0.81 ms)
-        int halve = 2ll * nqb * c.batch <= slots ? 1 : 0;
-#ifdef ISR_NN_TUNING
-        if (const char *e = getenv("ISR_NN_HALVE")) halve = (long long)nqb * c.batch <= (long long)atoi(e) * slots ? 1 : 0;
-#endif
-        const int stride = halve ? 2 * nqb + (kRows - 2) * split_max : nqb + (kRows - 1) * split_max;
+        // a grid that does not fill the machine runs every block as 2 / 4 / 8 CTAs of 4 / 2 / 1
+        // query rows, as long as all of them are resident at once (round 1, halves only, ICP
+        // search: 100k points 0.203 -> 0.163 ms, 250k 0.248 -> 0.206 ms; from one full wave on --
+        // 500k, 1M points -- the repeated per-CTA tests cost more than the shorter tail gains:
+        // 0.350 -> 0.381 ms, 0.63 -> 0.81 ms)
+        static const int parts_max = env_int("ISR_NN_PARTS_MAX", 8);
+        int parts = 1;
+        while (parts < parts_max && 2ll * parts * nqb * c.batch <= slots) parts *= 2;
+        if (split_max > nqb) split_max = nqb;
+        const int stride = parts * nqb + (kRows - parts) * split_max;
         char *w = reinterpret_cast<char *>(c.workspace);
         u64 *keys = reinterpret_cast<u64 *>(w);
         int *order = reinterpret_cast<int *>(w + align256((size_t)nqb * c.batch * 8));
@@ -1458,7 +1573,7 @@ static int nn2_dispatch(const NN2Call &c) {
             block_weight_kernel<V::kQueriesPerCta><<<(unsigned)((warps + 3) / 4), 128, 0, c.st>>>(
                 p.q, p.q_bstride, p.nq, p.nq_pad, nqb, (int)c.batch, keys);
             ISR_TRY(launched("block_weight_kernel"));
-            block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, kRows, stride, split_max, halve,
+            block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, kRows, stride, split_max, parts,
                                                                      split_factor, order, count);
             ISR_TRY(launched("block_order_kernel"));
         }
@@ -1493,7 +1608,14 @@ static int nn2_dispatch(const NN2Call &c) {
         p.debug_no_resolve = nores;
     }
     dim3 grid((unsigned)grid_x, (unsigned)splits, (unsigned)c.batch);
-    if (splits == 1) return V::launch(p, grid, c.st);
+    IcpFuse fuse{};
+    if (V::kFused) {
+        ISR_REQUIRE(c.fuse != nullptr && splits == 1, ISR_E_INVALID_ARG, "nn: fused search without its descriptor");
+        fuse = *c.fuse;
+        ISR_REQUIRE(fuse.nqb == nqb && fuse.ngroups == (nqb + kFuseGroup - 1) / kFuseGroup, ISR_E_SHAPE,
+                    "nn: fused search: reduction layout for %d blocks, launch has %d", fuse.nqb, nqb);
+    }
+    if (splits == 1) return V::launch(p, grid, c.st, fuse);
 
     const long long total = (long long)nq * c.batch;
     const size_t need = align256((size_t)total * splits * 8) + (size_t)total * splits * 4;
@@ -1503,7 +1625,7 @@ static int nn2_dispatch(const NN2Call &c) {
     p.part_idx = reinterpret_cast<int *>(reinterpret_cast<char *>(c.workspace) +
                                          align256((size_t)total * splits * 8));
     p.part_stride = total;
-    ISR_TRY(V::launch(p, grid, c.st));
+    ISR_TRY(V::launch(p, grid, c.st, fuse));
     nn2_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.st>>>(
         p.part_D, p.part_idx, total, splits, c.out_d2, c.out_idx, c.skip, c.skip_stride,
         (long long)nq);
@@ -1533,22 +1655,28 @@ int isr_nn2(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, flo
             int32_t *out_idx, const int32_t *skip, int64_t skip_stride, void *workspace,
             size_t workspace_bytes, void *stream) {
     return isr::nn2_search(q, t, batch, use_lo, out_d2, out_idx, skip, skip_stride, workspace, workspace_bytes,
-                           stream, 0);
+                           stream, 0, nullptr);
 }
 
 }  // extern "C"
 
 namespace isr {
 
+bool nn2_fusable(const IsrCloud *t) {
+    return t != nullptr && t->sub_c != nullptr && t->stage_c != nullptr && pruning_on();
+}
+
+int nn2_query_blocks(int64_t nq) { return (int)((nq + NN2Pruned::kQueriesPerCta - 1) / NN2Pruned::kQueriesPerCta); }
+
 int nn2_search(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, float *out_d2,
                int32_t *out_idx, const int32_t *skip, int64_t skip_stride, void *workspace,
-               size_t workspace_bytes, void *stream, int reuse_order) {
+               size_t workspace_bytes, void *stream, int reuse_order, const IcpFuse *fuse) {
     ISR_REQUIRE(q != nullptr && t != nullptr, ISR_E_INVALID_ARG, "nn: null cloud descriptor");
     ISR_REQUIRE(q->n >= 0 && t->n >= 1 && batch >= 0, ISR_E_SHAPE,
                 "nn: need nq >= 0, nt >= 1, batch >= 0 (nq=%lld nt=%lld batch=%lld)",
                 (long long)q->n, (long long)t->n, (long long)batch);
     if (q->n == 0 || batch == 0) return ISR_OK;
-    ISR_REQUIRE(q->soa7 && t->soa7 && out_d2, ISR_E_INVALID_ARG, "nn: null pointer");
+    ISR_REQUIRE(q->soa7 && t->soa7 && (out_d2 || fuse), ISR_E_INVALID_ARG, "nn: null pointer");
     ISR_REQUIRE(q->npad >= q->n && q->npad % ISR_SOA_TILE == 0 && t->npad >= t->n &&
                     t->npad % ISR_SOA_TILE == 0,
                 ISR_E_SHAPE, "nn: padded lengths must be multiples of %d covering n", ISR_SOA_TILE);
@@ -1560,7 +1688,15 @@ int nn2_search(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, 
     ISR_REQUIRE(t->stage_c == nullptr || aligned16(t->stage_c), ISR_E_ALIGN,
                 "nn: stage centroids must be 16-byte aligned");
     const NN2Call c{q, t, batch, use_lo, out_d2, out_idx, skip, skip_stride, workspace,
-                    workspace_bytes, (cudaStream_t)stream, reuse_order};
+                    workspace_bytes, (cudaStream_t)stream, reuse_order, fuse};
+    if (fuse != nullptr) {
+        ISR_REQUIRE(nn2_fusable(t) && q->hint != nullptr && use_lo, ISR_E_INVALID_ARG,
+                    "nn: the fused ICP iteration needs the pruned search, hints and the lo planes");
+        ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
+        // (a batch of starts = multi-start ICP: scan-heavy, see NN2PrunedHalves)
+        if (batch > 1) return nn2_dispatch<NN2PrunedHalvesFused>(c);
+        return nn2_dispatch<NN2PrunedFused>(c);
+    }
     if (t->sub_c != nullptr && t->stage_c != nullptr && pruning_on()) {
         ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
 #ifdef ISR_NN_TUNING

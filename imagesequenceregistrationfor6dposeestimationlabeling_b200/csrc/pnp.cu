@@ -5,7 +5,7 @@
 // the 2-D/3-D correspondence set with a hypothesis (R, t) and the camera matrix, and count the
 // correspondences whose squared reprojection error is <= reperr^2.  OpenCV's restated
 // arithmetic (calib3d, PnPRansacCallback::computeError + RANSACPointSetRegistrator::findInliers;
-// cv2 is not installable here, so this restatement is unpinned): pinhole
+// pinned against cv2 4.13's own projectPoints output, tests/golden/reference_pnp_cv2.npz): pinhole
 // projection in FP64 stored as float32, z == 0 replaced by 1, float32 differences against the
 // float32 image points, error = float32(double(du)^2 + double(dv)^2), inlier iff
 // double(error) <= reperr * reperr.

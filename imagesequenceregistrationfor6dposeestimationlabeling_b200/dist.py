@@ -70,6 +70,21 @@ def _world(group) -> int:
     return td.get_world_size(group) if td.is_initialized() else 1
 
 
+def _is_nccl(group) -> bool:
+    return td.is_initialized() and td.get_backend(group) == "nccl"
+
+
+def _all_reduce(t: torch.Tensor, op, group=None) -> None:
+    """In-place all-reduce that also works for a CUDA tensor on a gloo group (two ranks sharing
+    one GPU in the tests, or a box without NCCL): staged through the host."""
+    if t.is_cuda and not _is_nccl(group):
+        c = t.cpu()
+        td.all_reduce(c, op=op, group=group)
+        t.copy_(c)
+    else:
+        td.all_reduce(t, op=op, group=group)
+
+
 def global_first_argmin(local_loss: torch.Tensor, local_index: torch.Tensor, group=None) -> tuple:
     """Exact cross-rank first-minimum.  local_loss: float64 [1] (use +inf when the rank has no
     candidate), local_index: int64 [1] GLOBAL index of the local first minimum.
@@ -77,9 +92,9 @@ def global_first_argmin(local_loss: torch.Tensor, local_index: torch.Tensor, gro
     if _world(group) == 1:
         return local_loss, local_index
     m = local_loss.clone()
-    td.all_reduce(m, op=td.ReduceOp.MIN, group=group)
+    _all_reduce(m, td.ReduceOp.MIN, group)
     cand = torch.where(local_loss == m, local_index, torch.full_like(local_index, _I64_MAX))
-    td.all_reduce(cand, op=td.ReduceOp.MIN, group=group)
+    _all_reduce(cand, td.ReduceOp.MIN, group)
     return m, cand
 
 
@@ -112,8 +127,7 @@ def verify_poses_sharded(cloud_q, poses_q, poses_t, cloud_t=None, mode: str = "c
         lidx = lidx.to(torch.int64) + lo
         lbest = lbest.to(torch.float64)
     else:  # more ranks than candidates
-        dev = torch.device("cuda", torch.cuda.current_device()) if (
-            td.is_initialized() and td.get_backend(group) == "nccl") else torch.device("cpu")
+        dev = torch.device("cuda", torch.cuda.current_device()) if _is_nccl(group) else torch.device("cpu")
         losses = torch.zeros((0,), dtype=torch.float64, device=dev)
         lidx = torch.full((1,), _I64_MAX, dtype=torch.int64, device=dev)
         lbest = torch.full((1,), float("inf"), dtype=torch.float64, device=dev)
@@ -197,7 +211,7 @@ class PeerExchange:
     outcome -- `ok` is the same everywhere, `error` says what went wrong on this rank (or that
     a peer failed)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, timeout_s: Optional[float] = None):
         import ctypes
 
         from . import _lib
@@ -216,6 +230,9 @@ class PeerExchange:
             h = ctypes.c_void_p()
             _lib.check(_lib.load().isr_peer_create(self.rank, self.world, ctypes.byref(h), mine))
             self.handle = h
+            timeout_s = timeout_s or float(os.environ.get("ISR_PEER_TIMEOUT_S", "0") or 0)
+            if timeout_s:  # how long the kernel waits for a peer's sums (default ~10 s)
+                _lib.check(_lib.load().isr_peer_set_timeout(h, float(timeout_s)))
         except Exception as e:  # noqa: BLE001 -- agreed with the peers below
             self.error = e
         handles = bytes(mine)
@@ -344,15 +361,15 @@ def _icp_target_sharded(source, target, inits, max_dist, max_iteration, rel_fitn
         gidx = idx.to(torch.int64) + lo
         if world > 1:
             Dmin = D.clone()
-            td.all_reduce(Dmin, op=td.ReduceOp.MIN, group=group)
+            _all_reduce(Dmin, td.ReduceOp.MIN, group)
             # lowest global target index among the ranks that hold the minimum
             gidx = torch.where(D == Dmin, gidx, torch.full_like(gidx, _I64_MAX))
-            td.all_reduce(gidx, op=td.ReduceOp.MIN, group=group)
+            _all_reduce(gidx, td.ReduceOp.MIN, group)
         mine = (gidx >= lo) & (gidx < hi)
         local = torch.where(mine, gidx - lo, torch.full_like(gidx, -1)).to(torch.int32).contiguous()
         sums = be.accumulate(local, max_dist)
         if world > 1:
-            td.all_reduce(sums, op=td.ReduceOp.SUM, group=group)
+            _all_reduce(sums, td.ReduceOp.SUM, group)
         be.solve(sums, ns, rel_fitness, rel_rmse, k == max_iteration)
     return be.results()
 
@@ -360,9 +377,11 @@ def _icp_target_sharded(source, target, inits, max_dist, max_iteration, rel_fitn
 def icp_sharded(source, target, init=None, max_correspondence_distance: float = 20.0,
                 max_iteration: int = 30, relative_fitness: float = 1e-6,
                 relative_rmse: float = 1e-6, group=None, backend_factory: Optional[Callable] = None,
-                shard: str = "source", exchange: str = "auto"):
-    """Every rank passes the FULL source and target.  shard="source": rank r registers source
-    rows shard_bounds(ns, r, world) against the whole target; per iteration the 17 sums per
+                shard: str = "source", exchange: str = "auto", spatial: bool = True):
+    """Every rank passes the FULL source and target.  shard="source": rank r registers block
+    shard_bounds(ns, r, world) of the source -- of its Hilbert-curve order when `spatial` (the
+    default on the CUDA back end: a compact patch per rank), else of its rows -- against the
+    whole target; per iteration the 17 sums per
     start are exchanged between accumulate and solve -- exchange="peer": inside those two
     kernels through peer memory (PeerExchange / isr_icp_run_sharded; the whole loop is one C
     call), exchange="nccl": one all-reduce per iteration, "auto": peer whenever it applies
@@ -386,6 +405,23 @@ def icp_sharded(source, target, init=None, max_correspondence_distance: float = 
     lo, hi = shard_bounds(ns, rank, world)
     from . import _lib
 
+    if backend_factory is None and spatial and world > 1:
+        # Shard along the Hilbert curve, not by row number: rank r gets the r-th contiguous run
+        # of the curve-ordered source, i.e. one compact patch of the surface at full density.
+        # Rows [lo, hi) of a cloud in file order (farthest-point-sampling order, genFeat.py:199-202)
+        # are a `world`-times sparser sample of the WHOLE surface: every rank would then walk all
+        # of the target's tiles and the search would not get faster with more ranks.  The order
+        # is an integer sort of the same keys on every rank (deterministic), so the ranks agree.
+        from . import api
+
+        perm = api.spatial_order(source)[lo:hi].to(torch.int64)
+        if isinstance(source, torch.Tensor):
+            source_shard = source[perm.to(source.device)]
+        else:
+            source_shard = np.asarray(source)[perm.cpu().numpy()]
+    else:
+        source_shard = source[lo:hi]
+
     # decided from (ns, world, starts) alone, hence identically on every rank
     peer_ok = (backend_factory is None and world <= _lib.ISR_PEER_MAX_RANKS
                and len(inits) <= _lib.ISR_PEER_MAX_STARTS
@@ -398,15 +434,18 @@ def icp_sharded(source, target, init=None, max_correspondence_distance: float = 
 
         px = peer_exchange(group, required=(exchange == "peer"))
         if px is not None:
-            prob = api.IcpProblem(source[lo:hi], target, inits)
+            prob = api.IcpProblem(source_shard, target, inits)
+            # the solve side waits for its peers inside a kernel (bounded spin): start together
+            torch.cuda.synchronize()
+            td.barrier(group=group)
             prob.run_sharded(px, ns, max_correspondence_distance, max_iteration, relative_fitness,
                              relative_rmse)
             return prob.results(with_correspondences=False)
     factory = backend_factory or CudaIcpBackend
-    be = factory(source[lo:hi], target, inits)
+    be = factory(source_shard, target, inits)
     for k in range(max_iteration + 1):
         sums = be.accumulate(max_correspondence_distance)
         if world > 1:
-            td.all_reduce(sums, op=td.ReduceOp.SUM, group=group)
+            _all_reduce(sums, td.ReduceOp.SUM, group)
         be.solve(sums, ns, relative_fitness, relative_rmse, k == max_iteration)
     return be.results()

@@ -11,9 +11,12 @@
  *    No C++ exception crosses the boundary.  isr_last_error() returns a thread-local
  *    message for the most recent failure on the calling thread.
  *  - All data pointers are DEVICE pointers owned by the caller (PyTorch's allocator in
- *    this repo) unless the parameter name ends in _host.  The library allocates no
- *    persistent memory; scratch is passed in as `workspace` (size from the matching
- *    *_workspace_bytes function, 256-byte aligned).
+ *    this repo) unless the parameter name ends in _host.  Scratch is passed in as
+ *    `workspace` (size from the matching *_workspace_bytes function, 256-byte aligned).
+ *    The library itself allocates only two small persistent objects: a 64-byte profiling
+ *    counter per device (first profiled search) and the exchange buffer of isr_peer_create.
+ *  - Every call works on the CUDA device that is current in the calling thread; all
+ *    pointers of a call must belong to it.
  *  - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work; none
  *    synchronises unless documented.
  *  - Points: row-major float32 [n][3] ("AoS", the reference's numpy N x 3 layout,
@@ -23,9 +26,13 @@
  *    (Open3D PointCloud.transform, icp.py:22,110).  The reference's right-multiplication
  *    `pc.dot(M)` (verfication.py:83-85) is the pose with rotation M^T.
  *  - Indices int32 (n < 2^31 - 1024), counts int64.
- *  - Arithmetic: nearest-neighbour search in FP32 direct-difference form
- *    d2 = fma(dz,dz, fma(dy,dy, dx*dx)), dx = q.x - p.x; lowest target index on exact
- *    ties.  Transforms, distances fed to ICP, all reductions, Kabsch: FP64.
+ *  - Arithmetic of the nearest-neighbour search (isr_nn2, nn2.cu): clouds are centred and
+ *    kept as float32 hi/lo pairs of their FP64 coordinates (isr_prepare_cloud); an FP32
+ *    3-FMA filter a_j = |p_j|^2 - 2 q.p_j over the tiles that can hold the neighbour, then an
+ *    exact FP64 distance for the few targets inside the filter's proven error window; the
+ *    index is the float64 argmin, lowest ORIGINAL target index on exact ties.  (isr_nn_soa is
+ *    the round-1 direct-difference FP32 kernel, kept for bit-exact A/B.)  Transforms,
+ *    distances fed to ICP, all reductions, Kabsch: FP64, fixed summation order.
  */
 #ifndef ISR_H_
 #define ISR_H_
@@ -103,7 +110,8 @@ int isr_nn_soa(const float *q_soa, int64_t nq, int64_t nq_pad, int64_t q_bstride
 /* out3[0..2] = FP64 centroid of pts (single CTA, fixed summation order). */
 int isr_centroid(const float *pts, int64_t n, double *out3, void *stream);
 
-/* perm[i] = original index of the i-th point in Morton (Z-curve) order.  NeRF surface clouds
+/* perm[i] = original index of the i-th point along a 30-bit Hilbert curve through the cloud's
+ * bounding box (the curve never jumps: any run of consecutive points is one connected patch).  NeRF surface clouds
  * arrive in farthest-point-sampling order (genFeat.py:199-202), i.e. spatially random; the
  * scan kernel is fastest when consecutive stored points are neighbours.  Deterministic. */
 size_t isr_spatial_order_workspace_bytes(int64_t n);
@@ -252,7 +260,11 @@ int isr_icp_accumulate(IsrIcpState *states, int64_t starts, const float *src,
  *   isr_icp_corr_dist       out_D [starts][ns] float64 = |T src[i] - tgt[corr_idx]|^2, +inf where
  *                           corr_idx < 0 (the accumulate kernel's arithmetic: what the ranks compare)
  *   isr_icp_accumulate_corr the 17 sums over corr_idx; an index < 0 means "no correspondence
- *                           on this rank".  nt = rows of tgt. */
+ *                           on this rank".  nt = rows of tgt.  The sums are formed in a fixed
+ *                           order over the STORED source order (src_perm, as in isr_icp_search;
+ *                           NULL = file order): 32-point rows, 256-point blocks, groups of 64
+ *                           blocks -- the order of the fused iteration of isr_icp_run, so both
+ *                           give the same bits. */
 int isr_icp_search(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
                    const int32_t *src_perm, int64_t ns, const IsrCloud *tgt_cloud,
                    const double *centroid, int32_t *corr_idx, void *workspace,
@@ -260,10 +272,11 @@ int isr_icp_search(IsrIcpState *states, int64_t starts, const float *src, const 
 int isr_icp_corr_dist(const IsrIcpState *states, int64_t starts, const float *src,
                       const float *src_lo, int64_t ns, const float *tgt, const int32_t *corr_idx,
                       double *out_D, void *stream);
-int isr_icp_accumulate_corr(const IsrIcpState *states, int64_t starts, const float *src,
-                            const float *src_lo, int64_t ns, const float *tgt, int64_t nt,
-                            const int32_t *corr_idx, double max_dist, double *sums,
-                            uint8_t *inlier, void *workspace, size_t workspace_bytes, void *stream);
+int isr_icp_accumulate_corr(IsrIcpState *states, int64_t starts, const float *src,
+                            const float *src_lo, const int32_t *src_perm, int64_t ns,
+                            const float *tgt, int64_t nt, const int32_t *corr_idx, double max_dist,
+                            double *sums, uint8_t *inlier, void *workspace, size_t workspace_bytes,
+                            void *stream);
 
 /* Consume sums[starts][17] (already reduced over all source shards): set fitness / rmse
  * (ns_total = global source count), apply Open3D's break test against the previous
@@ -275,6 +288,11 @@ int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64
 
 /* Full loop: states[i].T must hold init_i (other fields zero).  Enqueues
  * max_iteration + 1 evaluation passes; converged starts skip the rest on the device.
+ * With the pruned search (the default) one pass is ONE kernel launch: the search kernel
+ * transforms the source itself, gathers each neighbour's original coordinates, reduces the
+ * 17 sums in a fixed order across the grid and solves Kabsch in the last warp to arrive
+ * (nn2.cu / icp_device.cuh); otherwise K1' + K2 + accumulate + solve per pass.  corr_idx and
+ * inlier describe the LAST evaluation of every start.
  * o3d.pipelines.registration.registration_icp, icp.py:101-103; with max_iteration == 0
  * it is evaluate_registration, icp.py:97-98. */
 int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
@@ -284,12 +302,12 @@ int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const flo
                 void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- source-sharded ICP over the GPUs of one box (collective C2) ------ */
-/* One process per GPU.  Instead of a collective-library call between the accumulate and
- * solve kernels, the exchange of the 17 sums is FUSED into them: the last CTA of
- * icp_accumulate_kernel stores this rank's sums straight into every peer's exchange buffer
- * (CUDA IPC mapping of peer HBM, carried by NVLink / NVSwitch), and icp_solve_kernel waits
- * on flags in its own buffer and adds the ranks' vectors in rank order, so that all ranks
- * solve bit-identical 3x3 problems.  No extra launch, no host synchronisation.
+/* One process per GPU.  Instead of a collective-library call, the exchange of the 17 sums is
+ * FUSED into the iteration's one kernel: the warp that finishes this rank's reduction stores
+ * the rank's sums straight into every peer's exchange buffer (CUDA IPC mapping of peer HBM,
+ * carried by NVLink / NVSwitch), waits on the flags in its own buffer and adds the ranks'
+ * vectors in rank order, so that all ranks solve bit-identical 3x3 problems.  No extra
+ * launch, no host synchronisation.
  *   isr_peer_create   allocates this rank's buffer; handle_out receives ISR_PEER_HANDLE_BYTES
  *                     bytes that the caller passes to all other ranks by any means
  *                     (torch.distributed all_gather in dist.py)
@@ -303,13 +321,16 @@ int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const flo
 typedef struct IsrPeer IsrPeer;
 int isr_peer_create(int rank, int world, IsrPeer **out, unsigned char *handle_out);
 int isr_peer_connect(IsrPeer *peer, const unsigned char *handles);
+/* How long a rank waits (inside the kernel) for a peer's message before it gives up;
+ * default about 10 s of SM clock. */
+int isr_peer_set_timeout(IsrPeer *peer, double seconds);
 int isr_peer_destroy(IsrPeer *peer);
 
 /* isr_icp_run for one SOURCE shard: src / src_lo / src_perm / corr_idx / inlier describe this
  * rank's ns rows, ns_total is the global source count, the target is replicated.  Every
  * rank of `peer` must make the same sequence of calls with the same starts, criteria and
- * max_iteration.  starts <= ISR_PEER_MAX_STARTS.  A peer that never arrives makes the solve
- * kernel give up after ~10 s: the state gets done = 1, reserved = 1 and NaN fitness.
+ * max_iteration.  starts <= ISR_PEER_MAX_STARTS.  A peer that never arrives makes the waiting
+ * warp give up after the time-out: the state gets done = 1, reserved = 1 and NaN fitness.
  * registration_icp, icp.py:101-103. */
 int isr_icp_run_sharded(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
                         const int32_t *src_perm, int64_t ns, int64_t ns_total, const float *tgt,

@@ -196,8 +196,9 @@ def remove_radius_outlier(points, nb_points, radius):
 def pnp_inliers(p3d, p2d, cam, R, t, reperr=2.0):
     """Consensus set of ONE PnP hypothesis as cv2.solvePnPRansac scores it (choosePose.py:23-33
     calls it with reprojectionError=2, distCoeffs=None).  OpenCV (calib3d: PnPRansacCallback::
-    computeError, RANSACPointSetRegistrator::findInliers; not installable here -> parity
-    unpinned, restated from the published source): points and image points are float32, the
+    computeError, RANSACPointSetRegistrator::findInliers), restated from the published source
+    and PINNED against cv2 4.13 itself (tests/golden/reference_pnp_cv2.npz, made by
+    tests/golden/make_golden_cv2.py; test_pnp_inliers_match_cv2_golden): points and image points are float32, the
     pinhole projection is evaluated in float64 and stored as float32 (z == 0 -> 1),
     err = float32(double(du)^2 + double(dv)^2), inlier iff err <= reperr^2 (double).
     Returns the boolean mask [n]."""

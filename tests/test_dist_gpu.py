@@ -1,5 +1,12 @@
-"""Multi-GPU parity (NCCL, one process per GPU).  Needs >= 2 visible GPUs; skipped otherwise
-(the single-GPU round-end box).  Run with `gpurun --gpus 2 -- python -m pytest tests -m gpu`."""
+"""Multi-rank parity of the sharded paths against the oracle and the single-GPU results.
+
+  test_two_ranks_on_one_gpu   world 2 on ONE device: two processes share cuda:0, gloo carries the
+                              host-side collectives, and the kernel-fused exchange of the sharded
+                              ICP runs through CUDA IPC between the two processes -- so
+                              isr_icp_run_sharded, target-sharded ICP, the candidate split and the
+                              multi-start split are parity-checked on the driver's 1-GPU box
+  test_two_gpu_sharding...    the same with NCCL, one process per GPU (needs >= 2 GPUs:
+                              `gpurun --gpus 2 -- python -m pytest tests -m gpu`)"""
 import os
 import socket
 
@@ -21,12 +28,12 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, backend):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
-                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank if backend == "nccl" else 0))
     import torch.distributed as td
     from imagesequenceregistrationfor6dposeestimationlabeling_b200 import dist, synth
-    dist.init_from_env()
+    dist.init_from_env(backend)
     out = {}
     try:
         cloud = synth.make_cloud(6000, seed=1)
@@ -60,12 +67,20 @@ def _worker(rank, world, port, q):
 
 def test_two_gpu_sharding_matches_oracle():
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+        pytest.skip("needs 2 GPUs (the one-GPU form of this test runs everywhere)")
+    _run_two_ranks("nccl")
+
+
+def test_two_ranks_on_one_gpu_match_oracle():
+    _run_two_ranks("gloo")
+
+
+def _run_two_ranks(backend):
     from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, backend)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=600) for _ in procs)

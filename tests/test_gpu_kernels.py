@@ -1,4 +1,6 @@
 """GPU parity tests proper: every call goes through the C ABI (csrc/libisr.so)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -432,6 +434,40 @@ def test_icp_matches_oracle(gpu):
     np.testing.assert_allclose(r.inlier_rmse, o.inlier_rmse, rtol=1e-5)
 
 
+def test_icp_refine_pose_returns_the_reference_triple(gpu):
+    """``(R, t, loss)`` as pose_refine.py:21-22,101-104 returns it -- R 3x3
+    float64, t of shape (3,), a scalar loss -- equal to the ICP result started from (R, t)
+    (oracle.registration_icp) and to api.icp; float64 sources keep their precision; the
+    reference's own argument list (images, renderer objects) is rejected loudly."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api, synth
+    src, tgt, _ = synth.icp_pair(12000, 14000, 4, 5)
+    R0 = synth.rotvec_to_matrix([0.01, -0.008, 0.012])
+    t0 = np.array([0.4, -0.3, 0.2])
+    R, t, loss = gpu.icp_refine_pose(R0, t0, src, tgt)
+    assert isinstance(R, np.ndarray) and R.shape == (3, 3) and R.dtype == np.float64
+    assert isinstance(t, np.ndarray) and t.shape == (3,) and t.dtype == np.float64
+    assert isinstance(loss, float)
+    o = oracle.registration_icp(src, tgt, 20.0, api.pose_from_Rt(R0, t0))
+    T = api.pose_from_Rt(R, t)
+    _close_T(T, o.transformation)
+    np.testing.assert_allclose(loss, o.inlier_rmse, rtol=1e-5)
+    r = gpu.icp(src, tgt, api.pose_from_Rt(R0, t0), 20.0)
+    np.testing.assert_array_equal(T, r.transformation)
+    assert loss == r.inlier_rmse
+    np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-12)
+    assert gpu.refine_pose is gpu.icp_refine_pose
+    # a float64 camera-frame source (icp.py:68) and a capped iteration count
+    Rg, tg_ = synth.true_pose(3)
+    src64 = src.astype(np.float64) @ Rg.T + tg_
+    Minv = np.linalg.inv(api.pose_from_Rt(Rg, tg_))
+    R2, t2, loss2 = gpu.icp_refine_pose(Minv[:3, :3], Minv[:3, 3], src64, tgt, max_iteration=5)
+    o2 = oracle.registration_icp(src64, tgt, 20.0, Minv, max_iteration=5)
+    _close_T(api.pose_from_Rt(R2, t2), o2.transformation)
+    np.testing.assert_allclose(loss2, o2.inlier_rmse, rtol=1e-5)
+    with pytest.raises(TypeError):
+        gpu.icp_refine_pose(R0, t0, np.zeros((64, 64, 3, 2)), object())
+
+
 def test_icp_recovers_known_motion_and_converges(gpu):
     from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
     tgt = synth.make_cloud(20000, seed=8)
@@ -626,6 +662,17 @@ def test_pnp_hypothesis_scoring_equals_oracle(gpu):
     c = gpu.score_pnp_hypotheses(p3d[:3], uv[:3], cam, P[:1], 1e9).cpu().numpy()
     assert c.tolist() == [3]
     assert gpu.score_pnp_hypotheses(p3d, uv, cam, np.zeros((0, 4, 4))).shape == (0,)
+
+
+def test_pnp_scoring_equals_cv2_golden(gpu):
+    """isr_pnp_score against OpenCV's own numbers (tests/golden/reference_pnp_cv2.npz): flags and
+    counts equal the masks derived from cv2.projectPoints for every committed hypothesis."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_pnp_cv2.npz"))
+    P = np.tile(np.eye(4), (len(g["Rs"]), 1, 1))
+    P[:, :3, :3], P[:, :3, 3] = g["Rs"], g["tvecs"]
+    counts, flags = gpu.score_pnp_hypotheses(g["p3d"], g["p2d"], g["cam"], P, 2.0, return_inliers=True)
+    np.testing.assert_array_equal(flags.cpu().numpy().astype(bool), g["mask"])
+    np.testing.assert_array_equal(counts.cpu().numpy(), g["mask"].sum(1))
 
 
 def test_remove_radius_outlier_shim(gpu):

@@ -284,6 +284,32 @@ def test_pnp_inliers_known_answers():
     assert m[0]
 
 
+def test_pnp_inliers_match_cv2_golden():
+    """The PnP half is PINNED by OpenCV itself (tests/golden/make_golden_cv2.py, cv2 4.13): for 8
+    hypotheses x 3000 correspondences the consensus masks equal those derived from
+    cv2.projectPoints' float32 output -- the array PnPRansacCallback::computeError compares
+    against -- whether the squared error is accumulated in float32 (OpenCV's Matx21f norm) or
+    rounded once from float64 (the restatement); and the pose cv2.solvePnPRansac returned for
+    the reference's own call (choosePose.py:23-33: P3P, 500 iterations, 2 px) is scored
+    consistently with the inlier list it returned."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_pnp_cv2.npz"))
+    d = g["p2d"][None] - g["proj"]
+    err32 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]).astype(np.float32)
+    d64 = d.astype(np.float64)
+    err64 = (d64[..., 0] ** 2 + d64[..., 1] ** 2).astype(np.float32)
+    np.testing.assert_array_equal(err32 <= np.float32(4.0), g["mask"])
+    np.testing.assert_array_equal(err64.astype(np.float64) <= 4.0, g["mask"])
+    for k in range(len(g["Rs"])):
+        m = oracle.pnp_inliers(g["p3d"], g["p2d"], g["cam"], g["Rs"][k], g["tvecs"][k], 2.0)
+        np.testing.assert_array_equal(m, g["mask"][k])
+    assert g["mask"][0].sum() > 2000 and g["mask"][5].sum() == 0
+    # cv2's RANSAC result: its inlier list belongs to the best MINIMAL model, the returned pose is
+    # the EPnP refit on those inliers -- so the refit's consensus contains nearly all of them
+    m = oracle.pnp_inliers(g["p3d"], g["p2d"], g["cam"], g["ransac_R"], g["ransac_t"], 2.0)
+    inl = g["ransac_inliers"]
+    assert m[inl].mean() > 0.99 and m.sum() >= len(inl)
+
+
 # ---- size-independent properties of the restated path (seeded, small) ----------------------
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_chamfer_is_symmetric_and_rigid_invariant(seed):
