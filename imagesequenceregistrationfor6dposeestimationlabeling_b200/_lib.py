@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libisr.so")
+#: (ISR_LIBISR_PATH: developer A/B runs against another build of the same ABI)
+LIB_PATH = os.environ.get("ISR_LIBISR_PATH") or os.path.join(_HERE, "csrc", "libisr.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "isr.h")
 
 ISR_SOA_TILE = 1024
@@ -107,6 +108,7 @@ SIGNATURES = {
     "isr_radius_count": (_I, [_P, _P, _D, _P, _P]),
     "isr_pnp_score": (_I, [_P, _P, _I64, _P, _P, _I64, _D, _P, _P, _P]),
     "isr_bench_ffma": (_I, [_I, _I, _I, _P, _P, _P]),
+    "isr_debug_cta_log": (_I, [_P, _I64]),
 }
 
 _lib = None
@@ -123,6 +125,8 @@ def load() -> ctypes.CDLL:
                 "This package has no CPU fallback.")
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if os.environ.get("ISR_LIBISR_PATH") and not hasattr(lib, name):
+                continue  # (an older build in a developer A/B run)
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args

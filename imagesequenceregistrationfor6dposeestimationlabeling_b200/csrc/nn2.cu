@@ -98,7 +98,10 @@ struct NN2Params {
     int sort_fifo;           // scan the queued sub-tiles nearest-first (0: in stage order)
     const unsigned *sub_h;   // [batch][stages_total * STAGE/SUB] packed half-extents of the sub-tile
     long long sub_h_bstride; //   boxes (isr_tile_spheres), or NULL: sphere tests only
+    unsigned long long *cta_log;  // developer probe (isr_debug_cta_log): 4 words per CTA, or NULL
+    long long cta_log_cap;        //   records that fit
 };
+
 constexpr unsigned kNoBox = 0x3FFFFFFFu;  // three 10-bit fractions of the radius, all ones
 
 // Can this lane rule out every point of the tile with sphere S for all of its Q queries?
@@ -213,7 +216,7 @@ __device__ __forceinline__ bool resolve_flagged(const NN2Params &p, const float 
                                                 unsigned &npass, const float *qsm) {
     // bit r: row r has a flagged piece
     const unsigned flags = (pflags | (pflags >> 8) | (pflags >> 16) | (pflags >> 24)) & 0xFFu;
-    if (PRUNE && p.evaluated != nullptr) {  // profiling only
+    if (PRUNE && (p.evaluated != nullptr || p.cta_log != nullptr)) {  // profiling only
         const unsigned mx = __reduce_max_sync(0xffffffffu, (unsigned)__popc(flags));
         nflag += mx != 0 ? 1u : 0u;
         npass += mx;
@@ -299,7 +302,9 @@ __device__ __forceinline__ bool resolve_flagged(const NN2Params &p, const float 
                 // strict minimum; on an exact tie the lower ORIGINAL index wins
                 // (tiles are not visited in index order and storage is permuted)
                 bool take = D < Db;
-                if (D == Db) {
+                // (a hinted search meets its own hint again -- the same point, not a tie to break:
+                // the two dependent perm loads below would be paid by every query of every iteration)
+                if (D == Db && gbase + j != ib) {
                     const int cand = gbase + j;
                     const int oc = p.perm_t != nullptr ? p.perm_t[min(cand, p.nt - 1)] : cand;
                     const int ob = p.perm_t != nullptr ? p.perm_t[min(ib, p.nt - 1)] : ib;
@@ -580,8 +585,9 @@ struct alignas(128) PrunedWarpSmem {
     float4 row[Q];             // sphere (c, rho) of query row r = the 32 queries r*32 .. r*32+31
     float rowB[Q];             // max of their bounds dq (refreshed between batches of work)
     uint64_t full[kRing];
+    uint64_t qbar;             // mbarrier of the prologue's bulk copies of the warp's queries
     int seed[kAnchors];        // sub-tiles scanned first (-1: none)
-    float qs[6][32 * Q];       // the warp's queries, hi xyz and lo xyz (read by the scan and the resolve path)
+    alignas(16) float qs[6][32 * Q];  // the warp's queries, hi xyz and lo xyz (read by the scan and the resolve path)
 };
 
 // rows of a query block that launch-list code `rowsel` stands for: 0 all eight, 1..8 one row,
@@ -650,7 +656,26 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < kRing; ++i) mbar_init(&ws.full[i], 1);
+        mbar_init(&ws.qbar, 1);
         mbar_fence_init();
+    }
+    __syncwarp();
+    // The warp's 256 queries are 1 KB runs of the stored planes: one bulk copy per plane (TMA
+    // engine) straight into the shared-memory copy -- one round trip to L2 instead of one per
+    // query row.  FUSED: the planes are the ORIGINAL source; the pose is applied below, in place.
+    if (lane == 0) {
+        const float *base = FUSED ? f.src7 : gq;
+        const bool lo = FUSED || p.use_lo;
+        const long long qbase = (long long)(q0 - lane);
+        mbar_expect_tx(&ws.qbar, (lo ? 6u : 3u) * 32u * Q * 4u);
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl)
+            bulk_g2s(&ws.qs[pl][0], base + (long long)pl * p.nq_pad + qbase, 32u * Q * 4u, &ws.qbar);
+        if (lo) {
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+                bulk_g2s(&ws.qs[3 + pl][0], base + (long long)(4 + pl) * p.nq_pad + qbase, 32u * Q * 4u, &ws.qbar);
+        }
     }
 
     // Everything per query row is a RUN-TIME loop over r from here on (the queries live in
@@ -662,42 +687,8 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     double Dbest_l[Q];
     int ibest_l[Q];
     float dmax = 0.f;  // max over the lane's live queries of dq_l (0: no live query)
-    double Tf[12], cf[3];  // FUSED: the start's pose and the centre of the prepared target
-    if (FUSED) {
-#pragma unroll
-        for (int k = 0; k < 12; ++k) Tf[k] = f.states[b].T[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) cf[k] = f.centroid[k];
-    }
 #pragma unroll 1
     for (int r = 0; r < Q; ++r) {
-        const int i = min(q0 + r * 32, p.nq_pad - 1);
-        if (FUSED) {
-            // the arithmetic of prepare_soa7_kernel: FP64 R p + t - c, split into a float32 hi/lo pair
-            float hx = ISR_PAD_COORD, hy = ISR_PAD_COORD, hz = ISR_PAD_COORD, lx = 0.f, ly = 0.f, lz = 0.f;
-            if (q0 + r * 32 < p.nq) {
-                const float *s7 = f.src7;
-                const double px = (double)s7[i] + (double)s7[4ll * p.nq_pad + i];
-                const double py = (double)s7[p.nq_pad + i] + (double)s7[5ll * p.nq_pad + i];
-                const double pz = (double)s7[2ll * p.nq_pad + i] + (double)s7[6ll * p.nq_pad + i];
-                double x, y, z;
-                icp_apply_pose(Tf, px, py, pz, x, y, z);
-                x -= cf[0]; y -= cf[1]; z -= cf[2];
-                hx = (float)x; hy = (float)y; hz = (float)z;
-                lx = (float)(x - (double)hx); ly = (float)(y - (double)hy); lz = (float)(z - (double)hz);
-            }
-            ws.qs[0][r * 32 + lane] = hx; ws.qs[1][r * 32 + lane] = hy; ws.qs[2][r * 32 + lane] = hz;
-            ws.qs[3][r * 32 + lane] = lx; ws.qs[4][r * 32 + lane] = ly; ws.qs[5][r * 32 + lane] = lz;
-        } else {
-            ws.qs[0][r * 32 + lane] = gq[i];
-            ws.qs[1][r * 32 + lane] = gq[p.nq_pad + i];
-            ws.qs[2][r * 32 + lane] = gq[2ll * p.nq_pad + i];
-            if (p.use_lo) {
-                ws.qs[3][r * 32 + lane] = gq[4ll * p.nq_pad + i];
-                ws.qs[4][r * 32 + lane] = gq[5ll * p.nq_pad + i];
-                ws.qs[5][r * 32 + lane] = gq[6ll * p.nq_pad + i];
-            }
-        }
         const bool live = (livemask >> r) & 1u;
         if (live) dmax = CUDART_INF_F;
         mt_l[r] = CUDART_INF_F;
@@ -705,6 +696,33 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         Dbest_l[r] = CUDART_INF;
         ibest_l[r] = 0;
         dq_l[r] = live ? CUDART_INF_F : 0.f;
+    }
+    mbar_wait(&ws.qbar, 0);
+    if (FUSED) {
+        // the arithmetic of prepare_soa7_kernel: FP64 R p + t - c, split into a float32 hi/lo pair
+        double Tf[12], cf[3];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) Tf[k] = f.states[b].T[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cf[k] = f.centroid[k];
+#pragma unroll 1
+        for (int r = 0; r < Q; ++r) {
+            if (!((own >> r) & 1u)) continue;  // (rows of other CTAs keep the raw copy; never read)
+            const int qs = r * 32 + lane;
+            float hx = ISR_PAD_COORD, hy = ISR_PAD_COORD, hz = ISR_PAD_COORD, lx = 0.f, ly = 0.f, lz = 0.f;
+            if (q0 + r * 32 < p.nq) {
+                const double px = (double)ws.qs[0][qs] + (double)ws.qs[3][qs];
+                const double py = (double)ws.qs[1][qs] + (double)ws.qs[4][qs];
+                const double pz = (double)ws.qs[2][qs] + (double)ws.qs[5][qs];
+                double x, y, z;
+                icp_apply_pose(Tf, px, py, pz, x, y, z);
+                x -= cf[0]; y -= cf[1]; z -= cf[2];
+                hx = (float)x; hy = (float)y; hz = (float)z;
+                lx = (float)(x - (double)hx); ly = (float)(y - (double)hy); lz = (float)(z - (double)hz);
+            }
+            ws.qs[0][qs] = hx; ws.qs[1][qs] = hy; ws.qs[2][qs] = hz;
+            ws.qs[3][qs] = lx; ws.qs[4][qs] = ly; ws.qs[5][qs] = lz;
+        }
     }
 
     // ---- starting bounds from the caller's hints (the previous search's neighbours) ----------
@@ -1130,6 +1148,16 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         }
     }
 
+    if (p.cta_log != nullptr && lane == 0) {
+        const long long rec = ((long long)b * gridDim.x + blockIdx.x);
+        if (rec < p.cta_log_cap) {
+            unsigned long long *o = p.cta_log + 4 * rec;
+            o[0] = (unsigned long long)(clock64() - t_start);
+            o[1] = ((unsigned long long)nscanned << 32) | ntests;
+            o[2] = ((unsigned long long)nhalves << 32) | ncand;
+            o[3] = ((unsigned long long)(unsigned)blk << 32) | ((unsigned long long)rowsel << 24) | (npass & 0xFFFFFFu);
+        }
+    }
     if (p.evaluated != nullptr && lane == 0) {
         atomicAdd(p.evaluated + 0, (unsigned long long)nhalves);  // scanned quarter units (2 query rows x SUB targets)
         atomicAdd(p.evaluated + 1, (unsigned long long)stages);   // stage spheres tested
@@ -1435,6 +1463,8 @@ constexpr int kMaxSplits = 32;
 // process-wide pruning switch and profiling counters (isr.h)
 static std::atomic<int> g_prune{-1};
 static std::atomic<unsigned long long> g_answered{0};
+static unsigned long long *g_cta_log = nullptr;  // isr_debug_cta_log
+static long long g_cta_log_cap = 0;
 static unsigned long long *g_evaluated_dev[64] = {nullptr};  // per device, allocated on first use
 
 static bool pruning_on() {
@@ -1524,6 +1554,8 @@ static int nn2_dispatch(const NN2Call &c) {
 #ifdef ISR_NN_TUNING
     if (const char *e = getenv("ISR_NN_BOX")) { if (atoi(e) == 0) p.sub_h = nullptr; }
 #endif
+    p.cta_log = g_cta_log;
+    p.cta_log_cap = g_cta_log_cap;
     p.evaluated = nullptr;
     if (prof_enabled()) {
         p.evaluated = evaluated_counter();
@@ -1726,6 +1758,12 @@ int isr_profile_nn_counters(uint64_t *out8_host) {
     ISR_REQUIRE(ctr != nullptr, ISR_E_CUDA, "profile_nn_counters: no counter buffer");
     ISR_TRY(check_cuda(cudaDeviceSynchronize(), "profile_nn_counters sync"));
     return check_cuda(cudaMemcpy(out8_host, ctr, 64, cudaMemcpyDeviceToHost), "profile_nn_counters read");
+}
+
+int isr_debug_cta_log(uint64_t *dev_buf, int64_t capacity_records) {
+    isr::g_cta_log = reinterpret_cast<unsigned long long *>(dev_buf);
+    isr::g_cta_log_cap = dev_buf != nullptr ? capacity_records : 0;
+    return ISR_OK;
 }
 
 int isr_set_nn_pruning(int on) {

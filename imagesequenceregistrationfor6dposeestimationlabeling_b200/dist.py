@@ -436,8 +436,9 @@ def icp_sharded(source, target, init=None, max_correspondence_distance: float = 
         if px is not None:
             prob = api.IcpProblem(source_shard, target, inits)
             # the solve side waits for its peers inside a kernel (bounded spin): start together
-            torch.cuda.synchronize()
-            td.barrier(group=group)
+            if world > 1:
+                torch.cuda.synchronize()
+                td.barrier(group=group)
             prob.run_sharded(px, ns, max_correspondence_distance, max_iteration, relative_fitness,
                              relative_rmse)
             return prob.results(with_correspondences=False)

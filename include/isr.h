@@ -362,6 +362,12 @@ int isr_pnp_score(const float *p3d, const float *p2d, int64_t n, const double *c
                   uint8_t *out_inlier, void *stream);
 
 /* ---- measurement helpers ------------------------------------------------------------ */
+/* Developer probe of the pruned search: while dev_buf (device, 4 x uint64 per record) is set,
+ * every CTA of every isr_nn2 / ICP launch writes record [batch * gridDim.x + blockIdx.x] =
+ * {SM cycles it ran, scanned sub-tiles << 32 | exact sub-tile tests, scanned quarter units << 32
+ * | candidate stages, query block << 32 | row code << 24 | resolve passes}.  NULL switches it off. */
+int isr_debug_cta_log(uint64_t *dev_buf, int64_t capacity_records);
+
 /* FFMA-chain microbenchmark: launches `blocks` x 256 threads, each running `iters`
  * rounds of 16 independent FMAs (packed != 0: fma.rn.f32x2).  flops_out_host receives the
  * number of FP32 flops executed.  Used by bench.py to report the measured FP32 peak. */

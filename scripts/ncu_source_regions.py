@@ -42,7 +42,9 @@ marks = [(1, "header"), (find("inline bool lane_rules_out"), "lane_rules_out"),
          (find("void scan_subtile("), "scan: flags"), (find("// ---- resolve: rare"), "resolve: setup + threshold"),
          (find("u64 wmask = 0;"), "resolve: pass 1 (window mask)"), (find("// pass 2: exact FP64"), "resolve: pass 2 (FP64)"),
          (find("Dbest_l[r] = Db;"), "resolve: write-back + bound"), (find("// ---- exhaustive kernel"), "exhaustive"),
-         (find("nn2_pruned_kernel(const NN2Params p)"), "set-up (query load, state init)"),
+         (find("nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f)"), "set-up (query load, state init)"),
+         (find("// ---- correspondences -> per-row sums"), "fused ICP epilogue (gather, sums)"),
+         (find("report in the caller's original indexing") or find("const int io = p.perm_q != nullptr ? p.perm_q[i] : i;"), "result write-back"),
          (find("// ---- starting bounds from"), "hints"), (find("// ---- query-row spheres"), "query-row spheres"),
          (find("auto refresh_bounds"), "refresh row bounds"), (find("auto coarse_rows ="), "coarse test (stage spheres)"),
          (find("auto coarse_rows_box"), "coarse test (sub-tile box)"), (find("auto exact_any ="), "exact test (stage)"),
