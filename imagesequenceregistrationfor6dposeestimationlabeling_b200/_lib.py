@@ -91,6 +91,11 @@ SIGNATURES = {
     "isr_mean_sqrt": (_I, [_P, _I64, _I64, _P, _P]),
     "isr_verify_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I]),
     "isr_verify_poses": (_I, [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I, _P, _P, _P, _SZ, _P]),
+    "isr_rel_pose_table": (_I, [_P, _P, _I64, _I64, _I64, _P, _P]),
+    "isr_rigid_relative": (_I, [_P, _P, _I64, _P, _P]),
+    "isr_adds_fixed_target_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "isr_adds_fixed_target": (_I, [_P, _I64, _P, _I64, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
+    "isr_vote": (_I, [_P, _I64, _I64, _D, _P, _P, _P, _P]),
     "isr_icp_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "isr_icp_accumulate": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _D, _P, _P, _P, _P, _SZ, _P]),
     "isr_icp_search": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P]),

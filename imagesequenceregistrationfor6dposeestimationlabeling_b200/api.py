@@ -567,6 +567,73 @@ def adds(verts, gtR, gtT, R, T, surface_points, device=None) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------
+# the callers of the batched ADD-S in choosePose.py, on the device
+# --------------------------------------------------------------------------------------
+@_on_device
+def relative_pose_table(RList, TList, pair0: int = 0, count: Optional[int] = None, device=None) -> torch.Tensor:
+    """float64 [count, 4, 4] on the device: relative_poses[i][j] of choosePose.py:98-107 for the
+    flat pair indices k = i * n + j in [pair0, pair0 + count) (default: the whole n x n table)."""
+    device = _device(device)
+    R = _to_dev(np.asarray(RList, dtype=np.float64).reshape(-1, 9) if not isinstance(RList, torch.Tensor)
+                else RList.reshape(-1, 9), torch.float64, device)
+    t = _to_dev(np.asarray(TList, dtype=np.float64).reshape(-1, 3) if not isinstance(TList, torch.Tensor)
+                else TList.reshape(-1, 3), torch.float64, device)
+    n = R.shape[0]
+    if t.shape[0] != n:
+        raise ValueError("RList and TList must have the same length")
+    count = n * n - pair0 if count is None else int(count)
+    out = torch.empty((count, 4, 4), dtype=torch.float64, device=device)
+    _lib.check(_lib.load().isr_rel_pose_table(_ptr(R), _ptr(t), n, int(pair0), count, _ptr(out), _stream()))
+    return out
+
+
+@_on_device
+def adds_rigid(verts, poses_gt, poses_pred, surface_points, valid_mask=None, device=None) -> VerifyResult:
+    """ADDS(verts, gtR, gtT, R, T) of choosePose.py:20-22 for B pose pairs (poses_gt, poses_pred:
+    [B,4,4], host or device) with the SURFACE PREPARED ONCE: candidate k scores
+    (poses_pred[k]^-1 poses_gt[k]) . verts against the surface cloud itself, which is the same
+    distance whenever poses_pred[k] is a rigid motion.  No host synchronisation."""
+    device = _device(device)
+    V, S = _points(verts, device), _points(surface_points, device)
+    Pq, Pt = _poses(poses_gt, device), _poses(poses_pred, device)
+    if Pq.shape[0] != Pt.shape[0]:
+        raise ValueError("poses_gt and poses_pred must have the same batch size")
+    b = Pq.shape[0]
+    if b == 0 or V.shape[0] == 0 or S.shape[0] == 0:
+        raise ValueError("adds_rigid: empty input")
+    valid = None
+    if valid_mask is not None:
+        valid = _to_dev(np.asarray(valid_mask).astype(np.uint8) if not isinstance(
+            valid_mask, torch.Tensor) else valid_mask.to(torch.uint8), torch.uint8, device)
+    lib = _lib.load()
+    M = torch.empty_like(Pq)
+    _lib.check(lib.isr_rigid_relative(_ptr(Pq), _ptr(Pt), b, _ptr(M), _stream()))
+    ws = _workspace(lib.isr_adds_fixed_target_workspace_bytes(V.shape[0], S.shape[0], b), device)
+    losses = torch.empty((b,), dtype=torch.float64, device=device)
+    best = torch.empty((2,), dtype=torch.int64, device=device)
+    _lib.check(lib.isr_adds_fixed_target(_ptr(V), V.shape[0], _ptr(S), S.shape[0], _ptr(M), _ptr(valid), b,
+                                         _ptr(losses), _ptr(best), _ptr(ws), ws.numel(), _stream()))
+    return VerifyResult(losses, best)
+
+
+@_on_device
+def vote(losses, threshold: float, device=None):
+    """choosePose.py:135-151 on a loss table [rows, cols] (device float64): returns
+    (error uint8 [rows, cols], votes int32 [rows], best int64 [2] = {first argmax, its votes})."""
+    device = _device(device)
+    L = _to_dev(losses, torch.float64, device)
+    if L.dim() != 2:
+        raise ValueError("vote expects a [rows, cols] loss table")
+    rows, cols = L.shape
+    error = torch.empty((rows, cols), dtype=torch.uint8, device=device)
+    votes = torch.empty((rows,), dtype=torch.int32, device=device)
+    best = torch.empty((2,), dtype=torch.int64, device=device)
+    _lib.check(_lib.load().isr_vote(_ptr(L), rows, cols, float(threshold), _ptr(error), _ptr(votes), _ptr(best),
+                                    _stream()))
+    return error, votes, best
+
+
+# --------------------------------------------------------------------------------------
 # K3 -- ICP
 # --------------------------------------------------------------------------------------
 @dataclasses.dataclass

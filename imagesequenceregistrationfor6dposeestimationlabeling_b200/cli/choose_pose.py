@@ -18,6 +18,16 @@ from .. import helpers
 from ..o3d_compat.io import read_ply_vertices
 
 
+def _table(RList, TList):
+    """The n x n x 4 x 4 table of choosePose.py:98-107, built on the device (isr_rel_pose_table)
+    and brought back for np.save."""
+    from .. import api
+
+    n = len(TList)
+    return api.relative_pose_table(np.asarray(RList, dtype=np.float64), np.asarray(TList, dtype=np.float64)
+                                   ).cpu().numpy().reshape(n, n, 4, 4)
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description="Train a Linemod")
     ap.add_argument("--objid", dest="objid", default="2")
@@ -40,13 +50,13 @@ def main(argv=None):
             keys = sorted(gt.keys(), key=lambda x: int(x))[:args.limit]
             RList = [np.asarray(gt[k][0]["cam_R_m2c"]).reshape(3, 3) for k in keys]
             TList = [np.asarray(gt[k][0]["cam_t_m2c"]) for k in keys]
-            rel = helpers.relative_pose_table(RList, TList)                    # :98-107
+            rel = _table(RList, TList)                                         # :98-107
             np.save(os.path.join(exp, oid + "gt_relative_poses.npy"), rel)
             out["gt_relative_poses"] = rel
         if int(args.cal_pred):
             RList = np.load(os.path.join(exp, oid + "pred_R.npy"), allow_pickle=True)
             TList = np.load(os.path.join(exp, oid + "pred_t.npy"), allow_pickle=True)
-            rel = helpers.relative_pose_table(np.stack(list(RList)), np.stack(list(TList)))
+            rel = _table(np.stack(list(RList)), np.stack(list(TList)))
             np.save(os.path.join(exp, oid + "pred_relative_poses.npy"), rel)
             out["pred_relative_poses"] = rel
     if int(args.choose_image):

@@ -216,4 +216,69 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
     return ISR_OK;
 }
 
+
+// ---- ADD-S with the target prepared once (choosePose.py:124-138 for a whole table of pairs) ----
+// Candidate k scores M_k . cloud_q against cloud_t ITSELF (one-directional mean 1-NN distance).
+// With M_k = Pt_k^-1 Pq_k (isr_rigid_relative) this equals ADDS(verts, gtR, gtT, R, T) of
+// choosePose.py:20-22 whenever (R, T) is a rigid motion -- distances do not change when both
+// clouds are moved by Pt^-1 -- but the 100k-point surface is sorted, centred, split into hi/lo
+// planes and given its tile spheres ONCE instead of once per pose pair; per pair only the (small)
+// vertex cloud is transformed.  The target planes and spheres stay L2-resident across the batch.
+size_t isr_adds_fixed_target_workspace_bytes(int64_t nq, int64_t nt, int64_t b) {
+    if (nq < 1 || nt < 1 || b < 1) return 256;
+    return isr::verify_layout(nq, nt, b, 0).total;
+}
+
+int isr_adds_fixed_target(const float *cloud_q, int64_t nq, const float *cloud_t, int64_t nt,
+                          const double *poses_q, const uint8_t *valid, int64_t b, double *out_loss,
+                          int64_t *out_best, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(nq >= 1 && nt >= 1 && b >= 1, ISR_E_SHAPE,
+                "adds_fixed_target: need nq, nt, b >= 1 (nq=%lld nt=%lld b=%lld)", (long long)nq,
+                (long long)nt, (long long)b);
+    ISR_REQUIRE(cloud_q && cloud_t && poses_q && out_loss, ISR_E_INVALID_ARG, "adds_fixed_target: null pointer");
+    const VerifyLayout L = verify_layout(nq, nt, b, 0);
+    ISR_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, ISR_E_WORKSPACE,
+                "adds_fixed_target: workspace %zu < %zu bytes", workspace_bytes, L.total);
+    ISR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ISR_E_ALIGN,
+                "adds_fixed_target: workspace not 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = reinterpret_cast<char *>(workspace);
+    float *xs = reinterpret_cast<float *>(ws + L.xs);
+    float *ys = reinterpret_cast<float *>(ws + L.ys);
+    float *d2a = reinterpret_cast<float *>(ws + L.d2a);
+    double *means = reinterpret_cast<double *>(ws + L.means);
+    double *centroid = reinterpret_cast<double *>(ws + L.centroid);
+    int32_t *perm_q = reinterpret_cast<int32_t *>(ws + L.perm_q);
+    int32_t *perm_t = reinterpret_cast<int32_t *>(ws + L.perm_t);
+    float *stage_y = reinterpret_cast<float *>(ws + L.stage_y);
+    float *sub_y = reinterpret_cast<float *>(ws + L.sub_y);
+    uint32_t *box_y = reinterpret_cast<uint32_t *>(ws + L.box_y);
+    const int64_t nqp = isr_soa_padded_len(nq), ntp = isr_soa_padded_len(nt);
+    // the target, once: centroid, curve order, centred hi/lo planes (identity pose), tile spheres
+    ISR_TRY(isr_centroid(cloud_t, nt, centroid, stream));
+    ISR_TRY(isr_spatial_order(cloud_t, nt, perm_t, ws + L.sortws, L.nnws - L.sortws, stream));
+    ISR_TRY(isr_spatial_order(cloud_q, nq, perm_q, ws + L.sortws, L.nnws - L.sortws, stream));
+    ISR_TRY(isr_prepare_cloud(cloud_t, nullptr, perm_t, nt, nullptr, 16, nullptr, 16, centroid, 1, ys, ntp,
+                              nullptr, 0, stream));
+    ISR_TRY(isr_tile_spheres(ys, nt, ntp, 0, 1, stage_y, sub_y, box_y, stream));
+    const IsrCloud cx{xs, nq, nqp, 7 * nqp, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const IsrCloud cy{ys, nt, ntp, 0, stage_y, nullptr, sub_y, nullptr, box_y};
+    for (int64_t k0 = 0; k0 < b; k0 += L.chunk) {
+        const int c = (int)((b - k0) < L.chunk ? (b - k0) : L.chunk);
+        // queries: M_k . cloud_q, centred on the (fixed) target centroid
+        ISR_TRY(isr_prepare_cloud(cloud_q, nullptr, perm_q, nq, poses_q + k0 * 16, 16, nullptr, 16, centroid, c,
+                                  xs, nqp, nullptr, 0, stream));
+        ISR_TRY(isr_nn2(&cx, &cy, c, 0, d2a, nullptr, nullptr, 0, ws + L.nnws, L.total - L.nnws, stream));
+        ISR_TRY(isr_mean_sqrt(d2a, nq, c, means, stream));
+        verify_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(means, means, valid, k0, c, 0, out_loss);
+        ISR_TRY(launched("verify_finalize_kernel"));
+    }
+    if (out_best != nullptr) {
+        argmin_first_kernel<<<1, 1024, 0, st>>>(out_loss, b, out_best);
+        ISR_TRY(launched("argmin_first_kernel"));
+    }
+    return ISR_OK;
+}
+
 }  // extern "C"

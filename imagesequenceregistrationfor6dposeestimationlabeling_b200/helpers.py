@@ -4,7 +4,8 @@
   compute_rel_poses         choosePose.py:43-51
   relative_pose_table       choosePose.py:98-107   (the n x n x 4 x 4 table)
   ADD, ADDS                 choosePose.py:18-22, inference.py:116-120
-  choose_image              choosePose.py:121-151  (ADD-S vote, argmax, top-50)
+  choose_image              choosePose.py:121-151  (ADD-S vote, argmax, top-50; device-resident)
+  choose_image_from_poses   choosePose.py:98-107 + 121-151 in one pass (tables built on the device)
   draw_registration_result, vp   verfication.py:21-31, icp.py:8-27  (GUI; no-ops here)
 
 Pose algebra is host-side float64 numpy (3x3 / 4x4, negligible work); everything that
@@ -66,27 +67,71 @@ def ADDS(verts, gtR1, gtT1, R1, T1, surface_points=None):
     return float(api.adds(verts, gtR1, gtT1, R1, T1, S).item())
 
 
+def _vote_result(losses_dev, n0, n1, diameter):
+    """Vote + selection of choosePose.py:135-151.  error / votes / first-argmax come from the
+    device (isr_vote); the top-50 list is numpy's own ``argsort(-votes)[:50]`` on the n vote
+    counts, so that ties are ordered exactly as the reference's (unstable) sort orders them."""
+    error, votes, best = api.vote(losses_dev.view(n0, n1), 0.1 * float(diameter))
+    votes_h = votes.cpu().numpy().astype(np.float64)   # (np.sum of a float64 0/1 matrix)
+    image_id = int(best[0].item())
+    assert image_id == int(np.argmax(votes_h))
+    return error.cpu().numpy().astype(np.float64), image_id, np.argsort(-votes_h)[:50]
+
+
 def choose_image(pred_rel_poses, gt_rel_poses, modelVerts, diameter, surface_points=None,
-                 chunk: int = 4096):
-    """ADD-S vote over all pose pairs -> (error n x n, image_id, top-50 indices)."""
+                 chunk: int = 65536):
+    """ADD-S vote over all pose pairs -> (error n x n, image_id, top-50 indices), from the two
+    n x n x 4 x 4 tables that ``--rel_poses`` saves (choosePose.py:121-151).  The tables are
+    uploaded once; scoring (surface prepared once, isr_adds_fixed_target), the 0.1 x diameter
+    test, the row sums and the argmax run on the device without a host synchronisation in
+    between."""
+    import torch
+
     S = surfacePointsScaled if surface_points is None else surface_points
     if S is None:
         raise NameError("surfacePointsScaled is not set")
-    pred = np.asarray(pred_rel_poses, dtype=np.float64)
-    gt = np.asarray(gt_rel_poses, dtype=np.float64)
-    n0, n1 = pred.shape[:2]
-    P = pred.reshape(-1, 4, 4)
-    G = gt.reshape(-1, 4, 4)
     dev = api._device()
+    pred = pred_rel_poses if isinstance(pred_rel_poses, torch.Tensor) else np.asarray(pred_rel_poses, dtype=np.float64)
+    gt = gt_rel_poses if isinstance(gt_rel_poses, torch.Tensor) else np.asarray(gt_rel_poses, dtype=np.float64)
+    n0, n1 = pred.shape[:2]
+    P = api._poses(pred.reshape(-1, 4, 4), dev)
+    G = api._poses(gt.reshape(-1, 4, 4), dev)
     V = api._points(modelVerts, dev)
     Sd = api._points(S, dev)
-    losses = np.empty(len(P))
-    for k0 in range(0, len(P), chunk):
-        r = api.verify_poses(V, G[k0:k0 + chunk], P[k0:k0 + chunk], cloud_t=Sd, mode="adds")
-        losses[k0:k0 + chunk] = r.losses.cpu().numpy()
-    error = (losses.reshape(n0, n1) < 0.1 * diameter).astype(np.float64)
-    votes = np.sum(error, axis=1)
-    return error, int(np.argmax(votes)), np.argsort(-votes)[:50]
+    losses = torch.empty((n0 * n1,), dtype=torch.float64, device=dev)
+    for k0 in range(0, n0 * n1, chunk):
+        losses[k0:k0 + chunk] = api.adds_rigid(V, G[k0:k0 + chunk], P[k0:k0 + chunk], Sd).losses
+    return _vote_result(losses, n0, n1, diameter)
+
+
+def choose_image_from_poses(pred_R, pred_t, gt_R, gt_t, modelVerts, diameter, surface_points=None,
+                            rows_per_chunk: int = 64):
+    """``--rel_poses`` and ``--choose_image`` in one pass (choosePose.py:98-107, 121-151): the two
+    relative-pose tables are never materialised -- each chunk of table rows is built on the
+    device (isr_rel_pose_table) and scored at once.  Same return as `choose_image`."""
+    import torch
+
+    S = surfacePointsScaled if surface_points is None else surface_points
+    if S is None:
+        raise NameError("surfacePointsScaled is not set")
+    dev = api._device()
+    Rp = api._to_dev(np.asarray(pred_R, dtype=np.float64).reshape(-1, 9), torch.float64, dev)
+    tp = api._to_dev(np.asarray(pred_t, dtype=np.float64).reshape(-1, 3), torch.float64, dev)
+    Rg = api._to_dev(np.asarray(gt_R, dtype=np.float64).reshape(-1, 9), torch.float64, dev)
+    tg = api._to_dev(np.asarray(gt_t, dtype=np.float64).reshape(-1, 3), torch.float64, dev)
+    n = Rp.shape[0]
+    if not (tp.shape[0] == Rg.shape[0] == tg.shape[0] == n):
+        raise ValueError("predicted and ground-truth pose lists must have the same length")
+    V = api._points(modelVerts, dev)
+    Sd = api._points(S, dev)
+    losses = torch.empty((n * n,), dtype=torch.float64, device=dev)
+    step = max(1, int(rows_per_chunk)) * n
+    for k0 in range(0, n * n, step):
+        c = min(step, n * n - k0)
+        P = api.relative_pose_table(Rp, tp, k0, c)
+        G = api.relative_pose_table(Rg, tg, k0, c)
+        losses[k0:k0 + c] = api.adds_rigid(V, G, P, Sd).losses
+    return _vote_result(losses, n, n, diameter)
 
 
 def select_pnp_hypothesis(h3d, h2d, cam, Rs, ts, reperr: float = 2.0):

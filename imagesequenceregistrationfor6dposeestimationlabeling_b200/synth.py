@@ -78,13 +78,16 @@ def true_pose(seed: int):
     return R, t
 
 
-def make_candidates(b: int, seed: int, R_true=None, t_true=None):
+def make_candidates(b: int, seed: int, R_true=None, t_true=None, mix: str = "default"):
     """PnP+RANSAC-like candidate set around a true pose.
 
     90% are R* . Exp(w), |w| ~ U(0, 30 deg); 10% are Haar-random (RANSAC failures);
     t_k = t* + N(0, 5^2 mm); exactly one index k0 has |w| <= 0.1 deg.
+    mix="aligned" / "haar" makes every candidate (but k0) of the first / second kind -- the
+    pruned search's work depends on how well the two clouds of a candidate are aligned.
     Returns (R [b,3,3], t [b,3], k0).
     """
+    frac_haar = {"default": 0.1, "aligned": 0.0, "haar": 1.0}[mix]
     rng = np.random.default_rng(seed)
     if R_true is None:
         R_true, t_true = true_pose(seed + 7919)
@@ -97,7 +100,7 @@ def make_candidates(b: int, seed: int, R_true=None, t_true=None):
         if k == k0:
             ang = np.deg2rad(rng.uniform(0.0, 0.1))
             Rs[k] = R_true @ rotvec_to_matrix(axis * ang)
-        elif rng.uniform() < 0.1:
+        elif rng.uniform() < frac_haar:
             Rs[k] = random_rotation(rng)
         else:
             ang = np.deg2rad(rng.uniform(0.5, 30.0))

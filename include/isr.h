@@ -219,6 +219,32 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
                      int64_t b, int bidirectional, double *out_loss, int64_t *out_best,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- the callers of the batched ADD-S in choosePose.py, on the device --- */
+/* out[k - pair0] (float64 [count][16]) = relative_poses[i][j] for the flat pair index
+ * k = i * n + j in [pair0, pair0 + count): the 4x4 of compute_rel_poses(R_i, t_i, R_j, t_j) =
+ * (R_i^T R_j, t_j - t_i) -- NOT an SE(3) composition, kept as the reference has it
+ * (choosePose.py:43-51, 98-107).  R float64 [n][9] row-major, t float64 [n][3]. */
+int isr_rel_pose_table(const double *R, const double *t, int64_t n, int64_t pair0, int64_t count,
+                       double *out, void *stream);
+/* out[k] = poses_t[k]^-1 . poses_q[k] for RIGID poses_t (rotation inverse = transpose). */
+int isr_rigid_relative(const double *poses_q, const double *poses_t, int64_t b, double *out,
+                       void *stream);
+/* ADD-S of candidate k = mean 1-NN distance from poses_q[k] . cloud_q into cloud_t ITSELF
+ * (the target is sorted / prepared / given its tile spheres once for the whole batch).  With
+ * poses_q = isr_rigid_relative(Pq, Pt) this is ADDS(verts, gtR, gtT, R, T) of choosePose.py:20-22
+ * for rotation matrices R (the error is |R^T R - I| x the cloud diameter otherwise).
+ * valid / out_loss / out_best as in isr_verify_poses. */
+size_t isr_adds_fixed_target_workspace_bytes(int64_t nq, int64_t nt, int64_t b);
+int isr_adds_fixed_target(const float *cloud_q, int64_t nq, const float *cloud_t, int64_t nt,
+                          const double *poses_q, const uint8_t *valid, int64_t b, double *out_loss,
+                          int64_t *out_best, void *workspace, size_t workspace_bytes, void *stream);
+/* The vote of choosePose.py:135-151 over a loss table float64 [rows][cols]:
+ * out_error[i][j] (uint8, may be NULL) = loss[i][j] < threshold (NaN / inf: 0),
+ * out_votes[i] (int32) = sum_j error[i][j], out_best (int64 [2], may be NULL) = {index of the
+ * FIRST maximum of the votes (np.argmax), its vote count}. */
+int isr_vote(const double *loss, int64_t rows, int64_t cols, double threshold, uint8_t *out_error,
+             int32_t *out_votes, int64_t *out_best, void *stream);
+
 /* ---- K3: point-to-point ICP --------------------------------------------------------- */
 /* Device-resident state of one ICP start (one per symmetry-seeded start when batched). */
 typedef struct IsrIcpState {

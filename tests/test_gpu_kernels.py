@@ -708,6 +708,53 @@ def test_multistart_icp_matches_individual_runs(gpu):
     np.testing.assert_allclose(ms.chamfer[0], ch0, rtol=1e-5)
 
 
+def test_choose_image_on_device_n64(gpu):
+    """SURVEY 8(f) row 1 at n = 64 (4096 pose pairs): the relative-pose table built on the device
+    equals the reference's loop (choosePose.py:43-51,98-107); ADD-S with the surface prepared
+    once equals the general two-cloud form; error matrix, chosen image and top-50 equal
+    oracle.choose_image (sklearn KD-tree per pair, choosePose.py:121-151) -- from the saved
+    tables and from the pose lists directly."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api, helpers, synth
+    rng = np.random.default_rng(5)
+    n = 64
+    surface = synth.make_cloud(4000, seed=1).astype(np.float64)
+    verts = synth.make_cloud(700, seed=3).astype(np.float64)
+    gR = np.stack([synth.random_rotation(rng) for _ in range(n)])
+    gt_ = rng.normal(scale=20.0, size=(n, 3)) + [0, 0, 700.0]
+    # predictions: most within a few degrees / mm of the truth, a quarter badly off, some near the
+    # 0.1 x diameter decision
+    ang = np.where(rng.random(n) < 0.25, rng.uniform(0.5, 3.0, n), rng.uniform(0.0, 0.12, n))
+    pR = np.stack([gR[k] @ synth.rotvec_to_matrix(ang[k] * synth.random_rotation(rng)[0]) for k in range(n)])
+    pt = gt_ + rng.normal(scale=1.5, size=(n, 3))
+    tab_p, tab_g = oracle.rel_pose_table(pR, pt), oracle.rel_pose_table(gR, gt_)
+    dev_p = api.relative_pose_table(pR, pt).cpu().numpy().reshape(n, n, 4, 4)
+    np.testing.assert_allclose(dev_p, tab_p, rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(dev_p[:, :, 3], np.tile([0, 0, 0, 1.0], (n, n, 1)))
+    part = api.relative_pose_table(gR, gt_, pair0=n * 7 + 3, count=150).cpu().numpy()
+    np.testing.assert_allclose(part, tab_g.reshape(-1, 4, 4)[n * 7 + 3:n * 7 + 153], rtol=0, atol=1e-12)
+    # rigid form == general form
+    P, G = tab_p.reshape(-1, 4, 4)[:300], tab_g.reshape(-1, 4, 4)[:300]
+    a = api.adds_rigid(verts, G, P, surface).losses.cpu().numpy()
+    b = api.verify_poses(verts, G, P, cloud_t=surface, mode="adds").losses.cpu().numpy()
+    np.testing.assert_allclose(a, b, rtol=1e-6)
+    diameter = 120.0
+    err_o, img_o, top_o = oracle.choose_image(tab_p, tab_g, verts, surface, diameter)
+    assert 0 < err_o.sum() < n * n                       # both outcomes occur
+    for err, img, top in (helpers.choose_image(tab_p, tab_g, verts, diameter, surface_points=surface, chunk=1000),
+                          helpers.choose_image_from_poses(pR, pt, gR, gt_, verts, diameter, surface_points=surface,
+                                                          rows_per_chunk=5)):
+        np.testing.assert_array_equal(err, err_o)
+        assert img == img_o
+        np.testing.assert_array_equal(top, top_o)
+    # the vote kernel on its own: ties -> first maximum, NaN / inf never vote
+    L = np.full((5, 7), 1.0)
+    L[1, :3] = 0.0; L[3, :3] = 0.0; L[4, 0] = np.nan; L[4, 1] = np.inf; L[2, :] = 0.5
+    e, v, best = api.vote(L, 0.5)
+    np.testing.assert_array_equal(v.cpu().numpy(), [0, 3, 0, 3, 0])
+    assert best.cpu().numpy().tolist() == [1, 3]
+    np.testing.assert_array_equal(e.cpu().numpy(), (L < 0.5).astype(np.uint8))
+
+
 def test_kdtree_shim_and_helpers(gpu):
     from imagesequenceregistrationfor6dposeestimationlabeling_b200 import helpers, synth
     from imagesequenceregistrationfor6dposeestimationlabeling_b200.compat import KDTree
