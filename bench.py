@@ -688,13 +688,20 @@ def main():
             rngv = np.random.default_rng(4)
             gRv = np.stack([synth.random_rotation(rngv) for _ in range(nv)])
             gtv = rngv.normal(scale=20.0, size=(nv, 3)) + [0, 0, 700.0]
-            pRv = np.stack([gRv[k] @ synth.rotvec_to_matrix(rngv.normal(scale=0.05, size=3)) for k in range(nv)])
+            # predictions: 80 % within a few degrees of the truth, 20 % failed (Haar-random)
+            pRv = np.stack([gRv[k] @ synth.rotvec_to_matrix(rngv.normal(scale=0.05, size=3)) if rngv.random() < 0.8
+                            else synth.random_rotation(rngv) for k in range(nv)])
             ptv = gtv + rngv.normal(scale=1.5, size=(nv, 3))
             helpers.choose_image_from_poses(pRv[:16], ptv[:16], gRv[:16], gtv[:16], verts, 120.0, surface_points=cloud)
             torch.cuda.synchronize()
+            vst = {}
             t0 = time.perf_counter()
-            _, img, _ = helpers.choose_image_from_poses(pRv, ptv, gRv, gtv, verts, 120.0, surface_points=cloud)
+            _, img, _ = helpers.choose_image_from_poses(pRv, ptv, gRv, gtv, verts, 120.0, surface_points=cloud, stats=vst)
             dtv = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            _, img2, _ = helpers.choose_image_from_poses(pRv[:96], ptv[:96], gRv[:96], gtv[:96], verts, 120.0,
+                                                         surface_points=cloud, use_bounds=False)
+            dtx = time.perf_counter() - t0
             secondary.update({
                 "adds_pose_pairs_per_s": nb / dtr,
                 "adds_config": f"ADD-S (one-directional): {nb} pose pairs x 20000 vertices vs 100000 surface points, host arrays "
@@ -702,9 +709,13 @@ def main():
                 "adds_two_cloud_pose_pairs_per_s": nb / dta,
                 "adds_two_cloud_config": "the same pairs through api.adds (both clouds transformed per pair; any 4x4)",
                 "vote_pose_pairs_per_s": nv * nv / dtv,
-                "vote_config": f"choosePose.py:98-151 for {nv} images = {nv * nv} pose pairs: relative-pose tables, ADD-S, "
-                               "0.1 x diameter test, row sums and argmax on the device; pose lists in, chosen image out "
+                "vote_config": f"choosePose.py:98-151 for {nv} images = {nv * nv} pose pairs: relative-pose tables, "
+                               "sphere bounds on every pair's ADD-S (isr_adds_bounds), exact ADD-S for the "
+                               f"{vst.get('exact')} pairs the bounds leave undecided, 0.1 x diameter test, row sums and "
+                               "argmax on the device; pose lists in, chosen image out "
                                f"(wall clock; 1280 images = 1.64 M pairs would take {1280 * 1280 / (nv * nv / dtv):.1f} s)",
+                "vote_exact_only_pose_pairs_per_s": 96 * 96 / dtx,
+                "vote_exact_only_config": "the same vote for 96 images with every pair scored exactly (use_bounds=False)",
             })
 
     # ---------------- CPU baseline (rank 0, N == 1 only) ---------------------------------

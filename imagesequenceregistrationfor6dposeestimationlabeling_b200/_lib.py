@@ -95,6 +95,7 @@ SIGNATURES = {
     "isr_rigid_relative": (_I, [_P, _P, _I64, _P, _P]),
     "isr_adds_fixed_target_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "isr_adds_fixed_target": (_I, [_P, _I64, _P, _I64, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
+    "isr_adds_bounds": (_I, [_P, _I64, _P, _I64, _P, _P, _I64, _P, _P, _P, _P]),
     "isr_vote": (_I, [_P, _I64, _I64, _D, _P, _P, _P, _P]),
     "isr_icp_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "isr_icp_accumulate": (_I, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _D, _P, _P, _P, _P, _SZ, _P]),

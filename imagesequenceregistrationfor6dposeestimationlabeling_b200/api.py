@@ -617,6 +617,56 @@ def adds_rigid(verts, poses_gt, poses_pred, surface_points, valid_mask=None, dev
 
 
 @_on_device
+def rigid_relative(poses_q, poses_t, device=None) -> torch.Tensor:
+    """M[k] = poses_t[k]^-1 . poses_q[k] for rigid poses_t (float64 [B,4,4] on the device)."""
+    device = _device(device)
+    Pq, Pt = _poses(poses_q, device), _poses(poses_t, device)
+    if Pq.shape[0] != Pt.shape[0]:
+        raise ValueError("poses_q and poses_t must have the same batch size")
+    M = torch.empty_like(Pq)
+    _lib.check(_lib.load().isr_rigid_relative(_ptr(Pq), _ptr(Pt), Pq.shape[0], _ptr(M), _stream()))
+    return M
+
+
+@_on_device
+def adds_fixed(verts, poses, surface_points, device=None) -> VerifyResult:
+    """Mean 1-NN distance from poses[k] . verts into the surface cloud ITSELF (prepared once)."""
+    device = _device(device)
+    V, S, M = _points(verts, device), _points(surface_points, device), _poses(poses, device)
+    b = M.shape[0]
+    if b == 0 or V.shape[0] == 0 or S.shape[0] == 0:
+        raise ValueError("adds_fixed: empty input")
+    lib = _lib.load()
+    ws = _workspace(lib.isr_adds_fixed_target_workspace_bytes(V.shape[0], S.shape[0], b), device)
+    losses = torch.empty((b,), dtype=torch.float64, device=device)
+    best = torch.empty((2,), dtype=torch.int64, device=device)
+    _lib.check(lib.isr_adds_fixed_target(_ptr(V), V.shape[0], _ptr(S), S.shape[0], _ptr(M), None, b,
+                                         _ptr(losses), _ptr(best), _ptr(ws), ws.numel(), _stream()))
+    return VerifyResult(losses, best)
+
+
+@_on_device
+def adds_bounds(verts, poses, target: SoaCloud, device=None):
+    """(lower, upper) float64 [B] with lower <= ADD-S(poses[k] . verts -> target) <= upper, from
+    the tile spheres of a target prepared with ``prepare_cloud(..., stage_centroids=True)``
+    alone (isr_adds_bounds).  Returns None when the target's spheres do not fit shared memory."""
+    device = _device(device)
+    V, M = _points(verts, device), _poses(poses, device)
+    stages = target.npad // _lib.ISR_SOA_TILE
+    if target.batch != 1 or target.stage_c is None or target.sub_c is None or target.centroid is None:
+        raise ValueError("adds_bounds: the target must be one prepared cloud with its tile spheres")
+    if stages * 17 * 16 > 200 * 1024:
+        return None
+    b = M.shape[0]
+    lo = torch.empty((b,), dtype=torch.float64, device=device)
+    hi = torch.empty((b,), dtype=torch.float64, device=device)
+    _lib.check(_lib.load().isr_adds_bounds(_ptr(V), V.shape[0], _ptr(M), b, _ptr(target.centroid),
+                                           _ptr(target.stage_c), stages, _ptr(target.sub_c), _ptr(lo), _ptr(hi),
+                                           _stream()))
+    return lo, hi
+
+
+@_on_device
 def vote(losses, threshold: float, device=None):
     """choosePose.py:135-151 on a loss table [rows, cols] (device float64): returns
     (error uint8 [rows, cols], votes int32 [rows], best int64 [2] = {first argmax, its votes})."""

@@ -78,13 +78,67 @@ def _vote_result(losses_dev, n0, n1, diameter):
     return error.cpu().numpy().astype(np.float64), image_id, np.argsort(-votes_h)[:50]
 
 
+class _PairScorer:
+    """ADD-S of pose pairs against ONE surface cloud, for the vote: the surface is prepared once;
+    every chunk of pairs first gets rigorous bounds from the surface's tile spheres
+    (isr_adds_bounds: lower <= ADDS <= upper); pairs that the bounds already place on one side of
+    the threshold keep that bound as their "loss", the others are scored exactly at the end
+    (isr_adds_fixed_target) -- one host synchronisation in total, to count them."""
+
+    def __init__(self, modelVerts, surface, n_pairs, threshold, use_bounds=True):
+        import torch
+
+        self.dev = api._device()
+        self.V = api._points(modelVerts, self.dev)
+        if use_bounds and self.V.shape[0] > 0:
+            # curve order: 32 consecutive vertices are one small patch (isr_adds_bounds tests the
+            # target's stage spheres once per warp); a mean over the vertices does not depend on it
+            self.V = self.V[api.spatial_order(self.V).to(torch.int64)].contiguous()
+        self.S = api._points(surface, self.dev)
+        self.thr = float(threshold)
+        self.losses = torch.empty((n_pairs,), dtype=torch.float64, device=self.dev)
+        self.M = torch.empty((n_pairs, 4, 4), dtype=torch.float64, device=self.dev) if use_bounds else None
+        self.target = None
+        if use_bounds:
+            cen = api.centroid_of(self.S)
+            self.target = api.prepare_cloud(self.S, centroid=cen, perm=api.spatial_order(self.S),
+                                            stage_centroids=True)
+        self.undecided = 0
+
+    def add(self, k0, poses_gt, poses_pred):
+        """pairs k0 .. k0 + len: ADDS(verts, gt, pred) (choosePose.py:131-134)."""
+        import torch
+
+        c = poses_gt.shape[0]
+        M = api.rigid_relative(poses_gt, poses_pred)
+        bounds = api.adds_bounds(self.V, M, self.target) if self.target is not None else None
+        if bounds is None:
+            self.losses[k0:k0 + c] = api.adds_fixed(self.V, M, self.S).losses
+            return
+        lo, hi = bounds
+        self.M[k0:k0 + c] = M
+        # decided pairs: upper < thr (votes) keeps upper, lower >= thr (no vote) keeps lower; NaN marks the rest
+        nan = torch.full_like(lo, float("nan"))
+        self.losses[k0:k0 + c] = torch.where(hi < self.thr, hi, torch.where(lo >= self.thr, lo, nan))
+
+    def finish(self):
+        import torch
+
+        if self.target is not None:
+            idx = torch.nonzero(torch.isnan(self.losses), as_tuple=False)[:, 0]   # the one host sync
+            self.undecided = int(idx.numel())
+            for i0 in range(0, self.undecided, 65536):
+                sel = idx[i0:i0 + 65536]
+                self.losses[sel] = api.adds_fixed(self.V, self.M[sel], self.S).losses
+        return self.losses
+
+
 def choose_image(pred_rel_poses, gt_rel_poses, modelVerts, diameter, surface_points=None,
-                 chunk: int = 65536):
+                 chunk: int = 65536, use_bounds: bool = True, stats=None):
     """ADD-S vote over all pose pairs -> (error n x n, image_id, top-50 indices), from the two
     n x n x 4 x 4 tables that ``--rel_poses`` saves (choosePose.py:121-151).  The tables are
-    uploaded once; scoring (surface prepared once, isr_adds_fixed_target), the 0.1 x diameter
-    test, the row sums and the argmax run on the device without a host synchronisation in
-    between."""
+    uploaded once; scoring (_PairScorer), the 0.1 x diameter test, the row sums and the argmax
+    run on the device.  `stats` (a dict) receives the number of pairs that needed the exact search."""
     import torch
 
     S = surfacePointsScaled if surface_points is None else surface_points
@@ -96,16 +150,17 @@ def choose_image(pred_rel_poses, gt_rel_poses, modelVerts, diameter, surface_poi
     n0, n1 = pred.shape[:2]
     P = api._poses(pred.reshape(-1, 4, 4), dev)
     G = api._poses(gt.reshape(-1, 4, 4), dev)
-    V = api._points(modelVerts, dev)
-    Sd = api._points(S, dev)
-    losses = torch.empty((n0 * n1,), dtype=torch.float64, device=dev)
+    sc = _PairScorer(modelVerts, S, n0 * n1, 0.1 * float(diameter), use_bounds)
     for k0 in range(0, n0 * n1, chunk):
-        losses[k0:k0 + chunk] = api.adds_rigid(V, G[k0:k0 + chunk], P[k0:k0 + chunk], Sd).losses
+        sc.add(k0, G[k0:k0 + chunk], P[k0:k0 + chunk])
+    losses = sc.finish()
+    if stats is not None:
+        stats.update(pairs=n0 * n1, exact=sc.undecided if use_bounds and sc.target is not None else n0 * n1)
     return _vote_result(losses, n0, n1, diameter)
 
 
 def choose_image_from_poses(pred_R, pred_t, gt_R, gt_t, modelVerts, diameter, surface_points=None,
-                            rows_per_chunk: int = 64):
+                            rows_per_chunk: int = 64, use_bounds: bool = True, stats=None):
     """``--rel_poses`` and ``--choose_image`` in one pass (choosePose.py:98-107, 121-151): the two
     relative-pose tables are never materialised -- each chunk of table rows is built on the
     device (isr_rel_pose_table) and scored at once.  Same return as `choose_image`."""
@@ -122,15 +177,14 @@ def choose_image_from_poses(pred_R, pred_t, gt_R, gt_t, modelVerts, diameter, su
     n = Rp.shape[0]
     if not (tp.shape[0] == Rg.shape[0] == tg.shape[0] == n):
         raise ValueError("predicted and ground-truth pose lists must have the same length")
-    V = api._points(modelVerts, dev)
-    Sd = api._points(S, dev)
-    losses = torch.empty((n * n,), dtype=torch.float64, device=dev)
+    sc = _PairScorer(modelVerts, S, n * n, 0.1 * float(diameter), use_bounds)
     step = max(1, int(rows_per_chunk)) * n
     for k0 in range(0, n * n, step):
         c = min(step, n * n - k0)
-        P = api.relative_pose_table(Rp, tp, k0, c)
-        G = api.relative_pose_table(Rg, tg, k0, c)
-        losses[k0:k0 + c] = api.adds_rigid(V, G, P, Sd).losses
+        sc.add(k0, api.relative_pose_table(Rg, tg, k0, c), api.relative_pose_table(Rp, tp, k0, c))
+    losses = sc.finish()
+    if stats is not None:
+        stats.update(pairs=n * n, exact=sc.undecided if use_bounds and sc.target is not None else n * n)
     return _vote_result(losses, n, n, diameter)
 
 

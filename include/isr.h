@@ -238,6 +238,16 @@ size_t isr_adds_fixed_target_workspace_bytes(int64_t nq, int64_t nt, int64_t b);
 int isr_adds_fixed_target(const float *cloud_q, int64_t nq, const float *cloud_t, int64_t nt,
                           const double *poses_q, const uint8_t *valid, int64_t b, double *out_loss,
                           int64_t *out_best, void *workspace, size_t workspace_bytes, void *stream);
+/* Rigorous bounds on the ADD-S of candidate k (poses_q[k] . cloud_q against a prepared, FIXED
+ * target) from the target's tile spheres alone: out_lower[k] <= ADDS_k <= out_upper[k].
+ * centroid / stage_c / sub_c: the centre the target was prepared with and its isr_tile_spheres
+ * outputs (single cloud; `stages` = npad / 1024 stage spheres are read, then 16 sub-tile spheres per
+ * stage).  The vote of choosePose.py:135 only asks whether ADDS < 0.1 x diameter: pairs with
+ * upper < threshold or lower >= threshold are decided without touching a point, the rest go
+ * through isr_adds_fixed_target.  One CTA per pose pair, spheres in shared memory. */
+int isr_adds_bounds(const float *cloud_q, int64_t nq, const double *poses_q, int64_t b,
+                    const double *centroid, const float *stage_c, int64_t stages, const float *sub_c,
+                    double *out_lower, double *out_upper, void *stream);
 /* The vote of choosePose.py:135-151 over a loss table float64 [rows][cols]:
  * out_error[i][j] (uint8, may be NULL) = loss[i][j] < threshold (NaN / inf: 0),
  * out_votes[i] (int32) = sum_j error[i][j], out_best (int64 [2], may be NULL) = {index of the

@@ -102,6 +102,18 @@ def test_config2_adds_mode_100k_surface(gpu):
         ref = oracle.ADDS(verts.astype(np.float64), R_true, t_true, Rs[k], ts[k], surface.astype(np.float64))
         np.testing.assert_allclose(got[k], ref, rtol=1e-5)
     assert np.all(np.isfinite(got)) and got.shape == (48,)
+    # the same pairs with the surface prepared once (the vote's path) and their sphere bounds
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api
+    Pg = np.stack([synth.pose_matrix(R_true, t_true)] * 48)
+    Pp = np.stack([synth.pose_matrix(Rs[k], ts[k]) for k in range(48)])
+    rig = api.adds_rigid(verts, Pg, Pp, surface).losses.cpu().numpy()
+    np.testing.assert_allclose(rig, got, rtol=1e-6)
+    cen = api.centroid_of(surface)
+    tgt = api.prepare_cloud(surface, centroid=cen, perm=api.spatial_order(surface), stage_centroids=True)
+    lo, hi = api.adds_bounds(verts, api.rigid_relative(Pg, Pp), tgt)
+    lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+    assert np.all(lo <= got) and np.all(got <= hi)
+    assert np.mean((hi < 12.0) | (lo >= 12.0)) > 0.5      # most pairs are decided at 0.1 x 120 mm
 
 
 def test_nn_100k_x_100k_exact_indices_sampled(gpu):

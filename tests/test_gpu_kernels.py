@@ -737,15 +737,28 @@ def test_choose_image_on_device_n64(gpu):
     a = api.adds_rigid(verts, G, P, surface).losses.cpu().numpy()
     b = api.verify_poses(verts, G, P, cloud_t=surface, mode="adds").losses.cpu().numpy()
     np.testing.assert_allclose(a, b, rtol=1e-6)
+    # sphere bounds bracket the exact ADD-S (isr_adds_bounds), for aligned and for failed poses
+    cen = api.centroid_of(surface.astype(np.float32))
+    tgt = api.prepare_cloud(surface.astype(np.float32), centroid=cen, perm=api.spatial_order(surface.astype(np.float32)),
+                            stage_centroids=True)
+    lo, hi = api.adds_bounds(verts, api.rigid_relative(G, P), tgt)
+    lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+    assert np.all(lo <= a) and np.all(a <= hi) and np.all(lo >= 0)
     diameter = 120.0
     err_o, img_o, top_o = oracle.choose_image(tab_p, tab_g, verts, surface, diameter)
     assert 0 < err_o.sum() < n * n                       # both outcomes occur
-    for err, img, top in (helpers.choose_image(tab_p, tab_g, verts, diameter, surface_points=surface, chunk=1000),
+    st1, st2 = {}, {}
+    for err, img, top in (helpers.choose_image(tab_p, tab_g, verts, diameter, surface_points=surface, chunk=1000,
+                                               stats=st1),
+                          helpers.choose_image(tab_p, tab_g, verts, diameter, surface_points=surface, use_bounds=False),
                           helpers.choose_image_from_poses(pR, pt, gR, gt_, verts, diameter, surface_points=surface,
-                                                          rows_per_chunk=5)):
+                                                          rows_per_chunk=5, stats=st2)):
         np.testing.assert_array_equal(err, err_o)
         assert img == img_o
         np.testing.assert_array_equal(top, top_o)
+    # (with this 4000-point surface a sub-tile is a 13 mm patch and the bounds decide little; at 100k
+    # points they decide most pairs: tests/test_gpu_fullsize.py::test_config2_adds_mode_100k_surface)
+    assert st1["pairs"] == st2["pairs"] == n * n and st1["exact"] == st2["exact"] <= n * n
     # the vote kernel on its own: ties -> first maximum, NaN / inf never vote
     L = np.full((5, 7), 1.0)
     L[1, :3] = 0.0; L[3, :3] = 0.0; L[4, 0] = np.nan; L[4, 1] = np.inf; L[2, :] = 0.5
