@@ -113,6 +113,10 @@ SIGNATURES = {
                                  _P, _SZ, _P, _P]),
     "isr_radius_count": (_I, [_P, _P, _D, _P, _P]),
     "isr_pnp_score": (_I, [_P, _P, _I64, _P, _P, _I64, _D, _P, _P, _P]),
+    "isr_first_max": (_I, [_P, _I64, _P, _P]),
+    "isr_p3p_solve": (_I, [_P, _P, _P, _I64, _P, _P, _P]),
+    "isr_pnp_ransac_workspace_bytes": (_SZ, [_I64, _I64]),
+    "isr_pnp_ransac": (_I, [_P, _P, _I64, _P, _I64, ctypes.c_uint64, _D, _I, _P, _P, _P, _P, _SZ, _P]),
     "isr_bench_ffma": (_I, [_I, _I, _I, _P, _P, _P]),
     "isr_debug_cta_log": (_I, [_P, _I64]),
 }

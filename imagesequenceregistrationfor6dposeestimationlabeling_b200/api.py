@@ -646,12 +646,16 @@ def adds_fixed(verts, poses, surface_points, device=None) -> VerifyResult:
 
 
 @_on_device
-def adds_bounds(verts, poses, target: SoaCloud, device=None):
+def adds_bounds(verts, poses, target: SoaCloud, presorted: bool = False, device=None):
     """(lower, upper) float64 [B] with lower <= ADD-S(poses[k] . verts -> target) <= upper, from
     the tile spheres of a target prepared with ``prepare_cloud(..., stage_centroids=True)``
-    alone (isr_adds_bounds).  Returns None when the target's spheres do not fit shared memory."""
+    alone (isr_adds_bounds).  The kernel tests the stage spheres once per 32 consecutive
+    vertices, so the vertices are put in curve order first unless `presorted`.  Returns None
+    when the target's spheres do not fit shared memory."""
     device = _device(device)
     V, M = _points(verts, device), _poses(poses, device)
+    if not presorted and V.shape[0] > 32:
+        V = V[spatial_order(V, device).to(torch.int64)].contiguous()
     stages = target.npad // _lib.ISR_SOA_TILE
     if target.batch != 1 or target.stage_c is None or target.sub_c is None or target.centroid is None:
         raise ValueError("adds_bounds: the target must be one prepared cloud with its tile spheres")
@@ -971,6 +975,61 @@ def score_pnp_hypotheses(points3d, points2d, camera_matrix, poses, reprojection_
                                      float(reprojection_error), _ptr(counts[b0:]),
                                      _ptr(flags[b0:]) if flags is not None else None, _stream()))
     return (counts, flags) if return_inliers else counts
+
+
+@_on_device
+def p3p_solve(points3, pixels3, camera_matrix, device=None):
+    """All P3P solutions (Grunert, FP64) of B explicit samples: points3 [B,3,3] object points,
+    pixels3 [B,3,2].  Returns (poses float64 [B,4,4,4] with NaN beyond the real solutions,
+    counts int32 [B]) on the device -- the minimal solver behind SOLVEPNP_P3P."""
+    device = _device(device)
+    P = _to_dev(np.asarray(points3, dtype=np.float64).reshape(-1, 9), torch.float64, device)
+    uv = _to_dev(np.asarray(pixels3, dtype=np.float64).reshape(-1, 6), torch.float64, device)
+    K = _to_dev(np.asarray(camera_matrix, dtype=np.float64).reshape(9), torch.float64, device)
+    b = P.shape[0]
+    poses = torch.empty((b, 4, 4, 4), dtype=torch.float64, device=device)
+    cnt = torch.empty((b,), dtype=torch.int32, device=device)
+    _lib.check(_lib.load().isr_p3p_solve(_ptr(P), _ptr(uv), _ptr(K), b, _ptr(poses), _ptr(cnt), _stream()))
+    return poses, cnt
+
+
+@dataclasses.dataclass
+class PnpResult:
+    ok: bool                    # a pose was found (the winning hypothesis has at least one inlier)
+    R: np.ndarray               # 3x3 float64
+    t: np.ndarray               # (3,) float64
+    inliers: np.ndarray         # int indices: consensus set of the winning hypothesis (cv2's `inliers`)
+    consensus: int              # inliers of the returned (refitted) pose
+
+
+@_on_device
+def pnp_ransac(points3d, points2d, camera_matrix, iterations: int = 100, reprojection_error: float = 2.0,
+               seed: int = 0, refine_rounds: int = 3, device=None) -> PnpResult:
+    """cv2.solvePnPRansac(points3d, points2d, cam, None, iterationsCount=iterations,
+    reprojectionError=reprojection_error, flags=cv2.SOLVEPNP_P3P) on the device
+    (choosePose.py:23-33): P3P hypotheses, consensus, first best hypothesis, Gauss-Newton refit on
+    its inliers (isr_pnp_ransac).  One host synchronisation, to read the result."""
+    device = _device(device)
+    p3 = _points(points3d, device)
+    p2 = _to_dev(points2d, torch.float32, device)
+    if p3.dim() != 2 or p2.dim() != 2 or p2.shape != (p3.shape[0], 2):
+        raise ValueError("pnp_ransac: points3d [n,3] and points2d [n,2] expected")
+    n = p3.shape[0]
+    if n < 4:
+        return PnpResult(False, np.eye(3), np.zeros(3), np.zeros((0,), dtype=np.int64), 0)
+    K = _to_dev(np.asarray(camera_matrix, dtype=np.float64).reshape(9), torch.float64, device)
+    lib = _lib.load()
+    ws = _workspace(lib.isr_pnp_ransac_workspace_bytes(n, int(iterations)), device)
+    pose = torch.empty((16,), dtype=torch.float64, device=device)
+    counts = torch.empty((2,), dtype=torch.int32, device=device)
+    flags = torch.empty((n,), dtype=torch.uint8, device=device)
+    _lib.check(lib.isr_pnp_ransac(_ptr(p3), _ptr(p2), n, _ptr(K), int(iterations), int(seed) & (2 ** 64 - 1),
+                                  float(reprojection_error), int(refine_rounds), _ptr(pose), _ptr(counts),
+                                  _ptr(flags), _ptr(ws), ws.numel(), _stream()))
+    c = counts.cpu().numpy()
+    T = pose.cpu().numpy().reshape(4, 4)
+    ok = bool(c[0] > 0 and np.isfinite(T).all())
+    return PnpResult(ok, T[:3, :3].copy(), T[:3, 3].copy(), np.nonzero(flags.cpu().numpy())[0], int(c[1]))
 
 
 # --------------------------------------------------------------------------------------

@@ -123,6 +123,13 @@ int isr_rigid_relative(const double *poses_q, const double *poses_t, int64_t b, 
     return launched("rigid_relative_kernel");
 }
 
+int isr_first_max(const int32_t *v, int64_t n, int64_t *out2, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(n >= 1 && n <= 0x7FFFFFFF && v && out2, ISR_E_INVALID_ARG, "first_max: bad argument");
+    first_max_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(v, n, out2);
+    return launched("first_max_kernel");
+}
+
 int isr_vote(const double *loss, int64_t rows, int64_t cols, double threshold, uint8_t *out_error,
              int32_t *out_votes, int64_t *out_best, void *stream) {
     using namespace isr;

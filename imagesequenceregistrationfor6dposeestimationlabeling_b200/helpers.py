@@ -6,6 +6,7 @@
   ADD, ADDS                 choosePose.py:18-22, inference.py:116-120
   choose_image              choosePose.py:121-151  (ADD-S vote, argmax, top-50; device-resident)
   choose_image_from_poses   choosePose.py:98-107 + 121-151 in one pass (tables built on the device)
+  pnp                       choosePose.py:23-33    (cv2.solvePnPRansac with P3P, on the device)
   draw_registration_result, vp   verfication.py:21-31, icp.py:8-27  (GUI; no-ops here)
 
 Pose algebra is host-side float64 numpy (3x3 / 4x4, negligible work); everything that
@@ -111,7 +112,7 @@ class _PairScorer:
 
         c = poses_gt.shape[0]
         M = api.rigid_relative(poses_gt, poses_pred)
-        bounds = api.adds_bounds(self.V, M, self.target) if self.target is not None else None
+        bounds = api.adds_bounds(self.V, M, self.target, presorted=True) if self.target is not None else None
         if bounds is None:
             self.losses[k0:k0 + c] = api.adds_fixed(self.V, M, self.S).losses
             return
@@ -205,6 +206,19 @@ def select_pnp_hypothesis(h3d, h2d, cam, Rs, ts, reperr: float = 2.0):
         return 1, 1, 1
     k = int(np.argmax(counts))  # first maximum
     return Rs[k].copy(), ts[k].copy(), np.nonzero(flags[k].cpu().numpy())[0]
+
+
+def pnp(h3d, h2d, cam, itr=100, reperr=2, flag=None, gtR=None, gtT=None, spts=None, ret=None, seed=0):
+    """choosePose.py:23-33 with the same signature and returns: ``(rotmat 3x3, tvec (3,), inlier
+    indices)`` or the failure sentinel ``(1, 1, 1)``.  The RANSAC loop (P3P hypotheses, consensus,
+    refit) runs on the device (api.pnp_ransac); `flag` is accepted for compatibility -- the
+    reference only ever passes cv2.SOLVEPNP_P3P -- and gtR / gtT / spts / ret are unused, as in
+    the reference."""
+    r = api.pnp_ransac(h3d, h2d, cam, iterations=int(itr), reprojection_error=float(reperr), seed=seed)
+    if not r.ok:
+        print("pose could not be estimated with these correspondences")
+        return 1, 1, 1
+    return r.R, r.t, r.inliers
 
 
 def draw_registration_result(source, target, transformation):

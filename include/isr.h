@@ -397,6 +397,32 @@ int isr_pnp_score(const float *p3d, const float *p2d, int64_t n, const double *c
                   const double *poses, int64_t b, double reperr, int32_t *out_count,
                   uint8_t *out_inlier, void *stream);
 
+/* out2 (int64 [2]) = {index of the FIRST maximum of v[0..n) (np.argmax), that maximum}. */
+int isr_first_max(const int32_t *v, int64_t n, int64_t *out2, void *stream);
+
+/* ---- PnP-RANSAC hypothesis generation (second half) ---------------- */
+/* All solutions of the perspective three-point problem for b explicit samples (Grunert's quartic,
+ * FP64): pts float64 [b][3][3] object points, uv float64 [b][3][2] pixels, cam double[9].
+ * out_poses float64 [b][4][16] (NaN-filled beyond the out_n[b] real solutions), camera = R object
+ * + t.  The minimal solver behind cv2.solveP3P / SOLVEPNP_P3P (choosePose.py:23). */
+int isr_p3p_solve(const double *pts, const double *uv, const double *cam, int64_t b, double *out_poses,
+                  int32_t *out_n, void *stream);
+/* cv2.solvePnPRansac(p3d, p2d, cam, None, iterationsCount=iterations, reprojectionError=reperr,
+ * flags=SOLVEPNP_P3P) as choosePose.py:23-33 calls it, on the device: `iterations` hypotheses
+ * (4 correspondences each from a counter-based generator seeded with `seed`; P3P on three, the
+ * fourth picks the solution), the consensus test of isr_pnp_score for all of them, the first
+ * hypothesis with the largest consensus, and `refine_rounds` rounds of a Gauss-Newton refit on
+ * the inliers (consensus re-evaluated between rounds; OpenCV refits with EPnP).  All
+ * `iterations` are evaluated (no early exit: they run in parallel).
+ * out_pose float64 [16]; out_counts int32 [2] = {consensus of the winning hypothesis, consensus
+ * of out_pose}; out_inlier uint8 [n] = the winning hypothesis' consensus set (cv2's `inliers`).
+ * out_counts[0] == 0: no pose (the reference's `pnp` then returns (1, 1, 1)). */
+size_t isr_pnp_ransac_workspace_bytes(int64_t n, int64_t iterations);
+int isr_pnp_ransac(const float *p3d, const float *p2d, int64_t n, const double *cam, int64_t iterations,
+                   uint64_t seed, double reperr, int refine_rounds, double *out_pose,
+                   int32_t *out_counts, uint8_t *out_inlier, void *workspace, size_t workspace_bytes,
+                   void *stream);
+
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* Developer probe of the pruned search: while dev_buf (device, 4 x uint64 per record) is set,
  * every CTA of every isr_nn2 / ICP launch writes record [batch * gridDim.x + blockIdx.x] =

@@ -337,3 +337,48 @@ def icp_script(upper, lower, R_GT, t_GT, R_pred, t_pred, cad, threshold=20.0, wo
     merged = np.concatenate([transform(actual_upper, reg.transformation),
                              np.asarray(lower, dtype=np.float64)], axis=0)  # :110-111
     return ev, reg, chamfer(merged, cad, workers)
+
+
+def p3p(P, uv, cam):
+    """All solutions of the perspective three-point problem for object points P [3,3] seen at
+    pixels uv [3,2] (Grunert's quartic as in Haralick et al. 1994): the minimal solver behind
+    ``cv2.solvePnPRansac(..., flags=cv2.SOLVEPNP_P3P)`` (choosePose.py:23).  Pinned against
+    cv2.solveP3P on the committed 3-point sets of tests/golden/reference_pnp_cv2.npz.
+    Returns a list of (R, t) with camera = R object + t."""
+    P = np.asarray(P, dtype=np.float64)
+    K = np.asarray(cam, dtype=np.float64).reshape(3, 3)
+    f = (np.linalg.inv(K) @ np.concatenate([np.asarray(uv, dtype=np.float64), np.ones((3, 1))], 1).T).T
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    a2 = np.sum((P[1] - P[2]) ** 2); b2 = np.sum((P[0] - P[2]) ** 2); c2 = np.sum((P[0] - P[1]) ** 2)
+    ca, cb, cg = f[1] @ f[2], f[0] @ f[2], f[0] @ f[1]
+    q1, q2, q3, q4 = (a2 - c2) / b2, (a2 + c2) / b2, (b2 - c2) / b2, (b2 - a2) / b2
+    coef = [(q1 - 1) ** 2 - 4 * c2 / b2 * ca * ca,
+            4 * (q1 * (1 - q1) * cb - (1 - q2) * ca * cg + 2 * c2 / b2 * ca * ca * cb),
+            2 * (q1 * q1 - 1 + 2 * q1 * q1 * cb * cb + 2 * q3 * ca * ca - 4 * q2 * ca * cb * cg + 2 * q4 * cg * cg),
+            4 * (-q1 * (1 + q1) * cb + 2 * a2 / b2 * cg * cg * cb - (1 - q2) * ca * cg),
+            (1 + q1) ** 2 - 4 * a2 / b2 * cg * cg]
+
+    def frame(X):
+        e1 = X[1] - X[0]
+        e1 = e1 / np.linalg.norm(e1)
+        e3 = np.cross(e1, X[2] - X[0])
+        e3 = e3 / np.linalg.norm(e3)
+        return np.stack([e1, np.cross(e3, e1), e3], 1)
+
+    out = []
+    for v in np.roots(coef):
+        if abs(v.imag) > 1e-6 * max(1.0, abs(v.real)) or v.real <= 0:
+            continue
+        v = v.real
+        den = 2 * (cg - v * ca)
+        if abs(den) < 1e-12:
+            continue
+        u = ((q1 - 1) * v * v - 2 * q1 * cb * v + 1 + q1) / den
+        s1sq = b2 / (1 + v * v - 2 * v * cb)
+        if u <= 0 or s1sq <= 0:
+            continue
+        s1 = np.sqrt(s1sq)
+        Q = np.stack([s1 * f[0], u * s1 * f[1], v * s1 * f[2]])
+        R = frame(Q) @ frame(P).T
+        out.append((R, Q[0] - R @ P[0]))
+    return out

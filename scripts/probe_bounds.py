@@ -15,9 +15,9 @@ for name, scale in (("aligned 3deg", 0.05), ("aligned 10deg", 0.17), ("failed", 
     M = np.stack([synth.pose_matrix(synth.rotvec_to_matrix(rng.normal(scale=scale, size=3)) if scale else synth.random_rotation(rng),
                                     rng.normal(scale=1.5, size=3)) for _ in range(B)])
     Md = api._poses(M, torch.device("cuda", 0))
-    api.adds_bounds(verts, Md, tgt); torch.cuda.synchronize()
+    api.adds_bounds(verts, Md, tgt, presorted=True); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); lo, hi = api.adds_bounds(verts, Md, tgt); e1.record(); e1.synchronize()
+    e0.record(); lo, hi = api.adds_bounds(verts, Md, tgt, presorted=True); e1.record(); e1.synchronize()
     t = e0.elapsed_time(e1) * 1e-3
     ex = api.adds_fixed(verts, Md[:256], surface).losses.cpu().numpy()
     lo, hi = lo.cpu().numpy(), hi.cpu().numpy()

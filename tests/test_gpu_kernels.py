@@ -675,6 +675,48 @@ def test_pnp_scoring_equals_cv2_golden(gpu):
     np.testing.assert_array_equal(counts.cpu().numpy(), g["mask"].sum(1))
 
 
+def test_p3p_and_pnp_ransac_against_cv2_golden(gpu):
+    """SURVEY 8(f) row 3, generation side.  (1) isr_p3p_solve reproduces every cv2.solveP3P solution
+    of the committed 3-point sets and agrees with oracle.p3p.  (2) api.pnp_ransac on the committed
+    scene (3000 correspondences, 25 % gross outliers, 0.7 px noise), called as choosePose.py:300
+    calls cv2 (500 iterations, 2 px): the consensus of the returned pose -- counted with the
+    cv2-pinned oracle -- is at least that of the pose cv2.solvePnPRansac returned, the pose is
+    close to the truth, the inlier list is the winning hypothesis' consensus set, and the run
+    is reproducible for a seed.  (3) helpers.pnp keeps the reference's call and return shape."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api, helpers
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_pnp_cv2.npz"))
+    K = g["cam"]
+    P3 = np.stack([g["p3d"][ids].astype(np.float64) for ids in g["p3p_sets"]])
+    UV = np.stack([g["uv_true"][ids] for ids in g["p3p_sets"]])
+    poses, cnt = api.p3p_solve(P3, UV, K)
+    poses, cnt = poses.cpu().numpy(), cnt.cpu().numpy()
+    for b, (S, k) in enumerate(zip(g["p3p_solutions"], g["p3p_nsol"])):
+        ours = [(poses[b, s, :3, :3], poses[b, s, :3, 3]) for s in range(cnt[b])]
+        assert cnt[b] == len(oracle.p3p(P3[b], UV[b], K)) >= k
+        assert np.isnan(poses[b, cnt[b]:]).all()
+        for j in range(k):
+            Rc, tc = S[j, :9].reshape(3, 3), S[j, 9:]
+            assert min(np.abs(R - Rc).max() + np.abs(t - tc).max() / 100.0 for R, t in ours) < 1e-6
+    cv_count = int(oracle.pnp_inliers(g["p3d"], g["p2d"], K, g["ransac_R"], g["ransac_t"], 2.0).sum())
+    r = api.pnp_ransac(g["p3d"], g["p2d"], K, iterations=500, reprojection_error=2.0, seed=1)
+    assert r.ok
+    ours = oracle.pnp_inliers(g["p3d"], g["p2d"], K, r.R, r.t, 2.0)
+    assert int(ours.sum()) == r.consensus >= cv_count          # at least cv2's consensus
+    np.testing.assert_allclose(r.R @ r.R.T, np.eye(3), atol=1e-9)
+    assert np.linalg.norm(r.R - g["R_true"]) < 2e-3 and np.linalg.norm(r.t - g["t_true"]) < 1.0
+    assert len(r.inliers) <= r.consensus and len(r.inliers) > 0.6 * len(g["p3d"])
+    assert ours[r.inliers].mean() > 0.97                       # the refit keeps the winner's inliers
+    r2 = api.pnp_ransac(g["p3d"], g["p2d"], K, iterations=500, reprojection_error=2.0, seed=1)
+    np.testing.assert_array_equal(r.R, r2.R)
+    np.testing.assert_array_equal(r.inliers, r2.inliers)
+    R, t, inl = helpers.pnp(g["p3d"], g["p2d"], K, itr=500, reperr=2)
+    assert R.shape == (3, 3) and t.shape == (3,) and inl.ndim == 1
+    # degenerate correspondences (every 3-D point the same: no P3P sample has a solution): the
+    # reference's failure sentinel
+    bad = helpers.pnp(g["p3d"][:50] * 0 + 1.0, g["p2d"][:50], K, itr=64, reperr=2)
+    assert isinstance(bad, tuple) and bad == (1, 1, 1)
+
+
 def test_remove_radius_outlier_shim(gpu):
     """o3d.geometry.PointCloud.remove_radius_outlier as generateCors.py:254-258 calls it."""
     import imagesequenceregistrationfor6dposeestimationlabeling_b200.o3d_compat as o3d

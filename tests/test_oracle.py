@@ -310,6 +310,28 @@ def test_pnp_inliers_match_cv2_golden():
     assert m[inl].mean() > 0.99 and m.sum() >= len(inl)
 
 
+def test_p3p_restatement_matches_cv2_solveP3P():
+    """oracle.p3p (Grunert) returns every solution cv2.solveP3P returned for the 24 committed
+    3-point sets (tests/golden/make_golden_cv2.py), and each of its solutions reprojects the
+    three points exactly."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_pnp_cv2.npz"))
+    K = g["cam"]
+    for ids, S, k in zip(g["p3p_sets"], g["p3p_solutions"], g["p3p_nsol"]):
+        P = g["p3d"][ids].astype(np.float64)
+        uv = g["uv_true"][ids]
+        sols = oracle.p3p(P, uv, K)
+        assert len(sols) >= k >= 1
+        for j in range(k):
+            Rc, tc = S[j, :9].reshape(3, 3), S[j, 9:]
+            d = min(np.abs(R - Rc).max() + np.abs(t - tc).max() / 100.0 for R, t in sols)
+            assert d < 1e-6
+        for R, t in sols:
+            pc = P @ R.T + t
+            pr = (pc / pc[:, 2:3]) @ K.T
+            np.testing.assert_allclose(pr[:, :2], uv, atol=1e-6)
+            np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-9)
+
+
 # ---- size-independent properties of the restated path (seeded, small) ----------------------
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_chamfer_is_symmetric_and_rigid_invariant(seed):
