@@ -18,7 +18,7 @@ from .api import (IcpProblem, IcpResult, MultiStartResult, NNResult, SoaCloud,  
                   VerifyResult, adds, chamfer_distance, evaluate_registration, icp,
                   centroid_of, measure_fp32_peak, multistart_icp, nearest_neighbors, pack_soa,
                   prepare_cloud, spatial_order, set_nn_pruning, get_nn_pruning, radius_neighbor_count,
-                  point_cloud_distance, pose_from_Rt, icp_refine_pose, refine_pose, score_pnp_hypotheses, adds_rigid, vote, pnp_ransac, p3p_solve, transform_points,
+                  point_cloud_distance, pose_from_Rt, icp_refine_pose, refine_pose, score_pnp_hypotheses, adds_rigid, vote, pnp_ransac, p3p_solve, estimate_normals, transform_points,
                   verify_poses)
 from .helpers import (ADD, ADDS, calculate_relative_pose, choose_image, choose_image_from_poses,  # noqa: F401
                       compute_rel_poses, draw_registration_result, relative_pose_table,

@@ -112,6 +112,7 @@ SIGNATURES = {
     "isr_icp_run_sharded": (_I, [_P, _I64, _P, _P, _P, _I64, _I64, _P, _P, _P, _D, _I, _D, _D, _P, _P, _P,
                                  _P, _SZ, _P, _P]),
     "isr_radius_count": (_I, [_P, _P, _D, _P, _P]),
+    "isr_knn_normals": (_I, [_P, _I64, _I64, _I, _P, _P]),
     "isr_pnp_score": (_I, [_P, _P, _I64, _P, _P, _I64, _D, _P, _P, _P]),
     "isr_first_max": (_I, [_P, _I64, _P, _P]),
     "isr_p3p_solve": (_I, [_P, _P, _P, _I64, _P, _P, _P]),

@@ -446,6 +446,27 @@ def radius_neighbor_count(points, radius: float, target=None, device=None) -> to
     return out
 
 
+@_on_device
+def estimate_normals(points, neighborhood_size: int = 50, disambiguate_directions: bool = True,
+                     device=None) -> torch.Tensor:
+    """float32 [N,3]: pytorch3d.ops.estimate_pointcloud_normals(points[None], neighborhood_size,
+    disambiguate_directions)[0] (generateCors.py:200-215 calls it with 400 neighbours on 1000
+    points and negates the result): k-nearest-neighbour PCA, smallest-eigenvalue eigenvector,
+    majority-side direction (isr_knn_normals)."""
+    device = _device(device)
+    pts = _points(points, device)
+    if pts.dim() != 2:
+        raise ValueError("estimate_normals expects points of shape [N, 3]")
+    n = pts.shape[0]
+    k = int(neighborhood_size)
+    if not 1 <= k <= n:
+        raise ValueError(f"neighborhood_size {k} outside 1..{n}")
+    out = torch.empty((n, 3), dtype=torch.float32, device=device)
+    _lib.check(_lib.load().isr_knn_normals(_ptr(pts), n, k, 1 if disambiguate_directions else 0, _ptr(out),
+                                           _stream()))
+    return out
+
+
 def _mean_sqrt(d2: torch.Tensor) -> torch.Tensor:
     """FP64 mean of sqrt(d2) per row, deterministic order."""
     b, n = d2.shape

@@ -385,6 +385,16 @@ int isr_icp_run_sharded(IsrIcpState *states, int64_t starts, const float *src, c
 int isr_radius_count(const IsrCloud *q, const IsrCloud *t, double radius, int32_t *out_count,
                      void *stream);
 
+/* out_normals float32 [n][3]: pytorch3d.ops.estimate_pointcloud_normals(points,
+ * neighborhood_size=k, disambiguate_directions=disambiguate) as generateCors.py:200-215 calls it
+ * (k = 400 on the 1000 farthest-point samples of the NeRF cloud; the reference negates the
+ * result): the k nearest points of the same cloud (the point itself included; exact distance
+ * ties go to the lower index), covariance about their mean, eigenvector of the smallest
+ * eigenvalue, flipped when fewer than k / 2 neighbours lie on its positive side.  One CTA per
+ * point, all n distances in shared memory: n <= 49152. */
+int isr_knn_normals(const float *pts, int64_t n, int64_t k, int disambiguate, float *out_normals,
+                    void *stream);
+
 /* ---- PnP hypothesis scoring ------------------------------------ */
 /* out_count[j] (int32 [b]) = number of the n 2-D/3-D correspondences that hypothesis j
  * (poses float64 [b][16], object -> camera) reprojects within `reperr` pixels: the consensus

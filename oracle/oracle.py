@@ -382,3 +382,28 @@ def p3p(P, uv, cam):
         R = frame(Q) @ frame(P).T
         out.append((R, Q[0] - R @ P[0]))
     return out
+
+
+def estimate_normals(points, neighborhood_size=50, disambiguate_directions=True):
+    """pytorch3d.ops.estimate_pointcloud_normals(points[None], neighborhood_size,
+    disambiguate_directions)[0] restated (generateCors.py:200-215 calls it with 400 neighbours on
+    1000 farthest-point samples and negates the result).  pytorch3d is not installable here ->
+    parity unpinned for this function; it follows upstream's published algorithm
+    (points_normals.py): k nearest neighbours of the same cloud (self included), covariance about
+    the neighbourhood mean (mean of outer products), eigenvector of the smallest eigenvalue of
+    eigh, flipped when fewer than k / 2 neighbours have a positive projection on it.
+    Returns float64 [n, 3]."""
+    P = np.asarray(points, dtype=np.float64)
+    k = int(neighborhood_size)
+    _, idx = cKDTree(P).query(P, k=k)
+    idx = idx.reshape(len(P), k)
+    nb = P[idx]                                   # [n, k, 3]
+    cen = nb - nb.mean(axis=1, keepdims=True)
+    cov = np.einsum("nki,nkj->nij", cen, cen) / k
+    w, v = np.linalg.eigh(cov)
+    nrm = v[:, :, 0].copy()
+    if disambiguate_directions:
+        proj = np.einsum("nki,ni->nk", nb - P[:, None, :], nrm)
+        flip = (proj > 0).sum(axis=1) < 0.5 * k
+        nrm[flip] *= -1.0
+    return nrm

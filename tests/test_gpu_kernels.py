@@ -717,6 +717,38 @@ def test_p3p_and_pnp_ransac_against_cv2_golden(gpu):
     assert isinstance(bad, tuple) and bad == (1, 1, 1)
 
 
+@pytest.mark.parametrize("n,k", [(1000, 400), (700, 16), (3000, 64), (40, 40)])
+def test_knn_normals_equal_the_pytorch3d_restatement(gpu, n, k):
+    """SURVEY 8(f) row 4, second half: isr_knn_normals against oracle.estimate_normals (the
+    restated pytorch3d estimator) at the reference's size (1000 points, 400 neighbours,
+    generateCors.py:200-215) and others: same direction to 1e-4 rad wherever the two smallest
+    eigenvalues are separated, same sign, unit length; without disambiguation equal up to sign."""
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    pts = synth.make_cloud(n, seed=7)
+    got = gpu.estimate_normals(pts, k).cpu().numpy().astype(np.float64)
+    ref = oracle.estimate_normals(pts, k)
+    np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    # eigen-gap of the reference neighbourhood covariances: directions are only comparable where it is open
+    from scipy.spatial import cKDTree
+    P = pts.astype(np.float64)
+    _, idx = cKDTree(P).query(P, k=k)
+    nb = P[idx.reshape(n, k)]
+    cen = nb - nb.mean(1, keepdims=True)
+    w = np.linalg.eigvalsh(np.einsum("nki,nkj->nij", cen, cen) / k)
+    open_gap = (w[:, 1] - w[:, 0]) > 1e-3 * w[:, 2]
+    assert open_gap.mean() > 0.9
+    dots = (got * ref).sum(1)
+    assert np.all(np.abs(dots[open_gap]) > 1 - 1e-6)
+    # the majority-side rule decides the sign; only points whose vote is within one neighbour of k / 2 may differ
+    proj = np.einsum("nki,ni->nk", nb - P[:, None, :], ref)
+    margin = np.abs((proj > 0).sum(1) - 0.5 * k)
+    assert np.all(dots[open_gap & (margin > 1.5)] > 0)
+    got2 = gpu.estimate_normals(pts, k, disambiguate_directions=False).cpu().numpy().astype(np.float64)
+    assert np.all(np.abs((got2 * ref).sum(1))[open_gap] > 1 - 1e-6)
+    if k == n:   # every neighbourhood is the whole cloud: one normal for all
+        assert np.all(np.abs(got2 @ got2[0]) > 1 - 1e-6)
+
+
 def test_remove_radius_outlier_shim(gpu):
     """o3d.geometry.PointCloud.remove_radius_outlier as generateCors.py:254-258 calls it."""
     import imagesequenceregistrationfor6dposeestimationlabeling_b200.o3d_compat as o3d

@@ -332,6 +332,20 @@ def test_p3p_restatement_matches_cv2_solveP3P():
             np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-9)
 
 
+def test_estimate_normals_restatement_on_a_sphere():
+    """oracle.estimate_normals: on a noiseless sphere the k-NN PCA normal is radial; the
+    majority-side rule points it INWARDS (the neighbours of a convex patch lie below the tangent
+    plane), which is why generateCors.py:208 negates it."""
+    rng = np.random.default_rng(0)
+    u = rng.normal(size=(1500, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    n = oracle.estimate_normals(50.0 * u, 40)
+    np.testing.assert_allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-12)
+    assert np.all((n * u).sum(1) < -0.99)
+    n2 = oracle.estimate_normals(50.0 * u, 40, disambiguate_directions=False)
+    assert np.all(np.abs((n2 * u).sum(1)) > 0.99)
+
+
 # ---- size-independent properties of the restated path (seeded, small) ----------------------
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_chamfer_is_symmetric_and_rigid_invariant(seed):
