@@ -72,6 +72,7 @@ SIGNATURES = {
     "isr_profile_collect": (_I, [_P, _P]),
     "isr_soa_padded_len": (_I64, [_I64]),
     "isr_transform_points": (_I, [_P, _I64, _P, _I64, _P, _P]),
+    "isr_transform_points_f64": (_I, [_P, _I64, _P, _P, _P]),
     "isr_transform_points_soa": (_I, [_P, _I64, _P, _I64, _I64, _P, _I64, _P, _I64, _P]),
     "isr_nn_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "isr_nn_soa": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P,

@@ -166,6 +166,20 @@ def transform_points(points, poses, device=None) -> torch.Tensor:
     return out
 
 
+@_on_device
+def transform_points_f64(points: torch.Tensor, pose, out: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
+    """float64 [N,3] device tensor -> pose . points in float64 (in place when out is points):
+    Open3D's PointCloud.transform (icp.py:22,110) for a cloud that lives on the device."""
+    device = _device(device)
+    pts = _to_dev(points, torch.float64, device)
+    if pts.dim() != 2 or pts.shape[1] != 3:
+        raise ValueError("transform_points_f64 expects points of shape [N, 3]")
+    P = _poses(pose, device)
+    out = torch.empty_like(pts) if out is None else out
+    _lib.check(_lib.load().isr_transform_points_f64(_ptr(pts), pts.shape[0], _ptr(P), _ptr(out), _stream()))
+    return out
+
+
 @dataclasses.dataclass
 class SoaCloud:
     """A cloud (or batch of clouds) in the padded plane layout K2 streams.

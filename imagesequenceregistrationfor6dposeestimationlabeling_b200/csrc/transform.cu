@@ -29,14 +29,6 @@ __device__ __forceinline__ Pose12 load_pose(const double *p) {
     return P;
 }
 
-__device__ __forceinline__ Pose12 load_pose12(const double *p) {  // 3 x 4 rows, packed
-    Pose12 P;
-    P.r[0] = p[0]; P.r[1] = p[1]; P.r[2] = p[2];  P.t[0] = p[3];
-    P.r[3] = p[4]; P.r[4] = p[5]; P.r[5] = p[6];  P.t[1] = p[7];
-    P.r[6] = p[8]; P.r[7] = p[9]; P.r[8] = p[10]; P.t[2] = p[11];
-    return P;
-}
-
 __device__ __forceinline__ void apply_pose(const Pose12 &P, float x, float y, float z, float &ox,
                                            float &oy, float &oz) {
     const double dx = x, dy = y, dz = z;
@@ -85,7 +77,7 @@ transform_aos_kernel(const float *__restrict__ pts, int64_t n, const double *__r
         for (int k = 0; k < 12; ++k) in[k] = (k < cnt * 3) ? pts[i0 * 3 + k] : 0.f;
     }
     for (int64_t bb = b_begin; bb < b_end; ++bb) {
-        const Pose12 P = load_pose12(spose[bb - b_begin]);
+        const Pose12 P = load_pose(spose[bb - b_begin]);
         float o[12];
 #pragma unroll
         for (int k = 0; k < kTfPointsPerThread; ++k)
@@ -144,9 +136,37 @@ transform_soa_kernel(const float *__restrict__ pts, int64_t n, const double *__r
     o[2 * npad] = oz;
 }
 
+// float64 in / float64 out, one pose, in place allowed: Open3D's PointCloud.transform keeps
+// double coordinates (icp.py:22,110).  24 B read + 24 B written per point.
+__global__ void __launch_bounds__(kTfThreads)
+transform_f64_kernel(const double *__restrict__ pts, int64_t n, const double *__restrict__ pose,
+                     double *__restrict__ out) {
+    const Pose12 P = load_pose(pose);
+    for (int64_t i = (int64_t)blockIdx.x * kTfThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kTfThreads) {
+        const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        // same evaluation order as numpy's row . column product followed by "+ t"
+        const double ox = ((P.r[0] * x + P.r[1] * y) + P.r[2] * z) + P.t[0];
+        const double oy = ((P.r[3] * x + P.r[4] * y) + P.r[5] * z) + P.t[1];
+        const double oz = ((P.r[6] * x + P.r[7] * y) + P.r[8] * z) + P.t[2];
+        out[3 * i] = ox; out[3 * i + 1] = oy; out[3 * i + 2] = oz;
+    }
+}
+
 }  // namespace isr
 
 extern "C" {
+
+int isr_transform_points_f64(const double *pts, int64_t n, const double *pose, double *out, void *stream) {
+    using namespace isr;
+    ISR_REQUIRE(n >= 0, ISR_E_SHAPE, "transform_points_f64: negative size");
+    if (n == 0) return ISR_OK;
+    ISR_REQUIRE(pts && pose && out, ISR_E_INVALID_ARG, "transform_points_f64: null pointer");
+    int64_t blocks = (n + kTfThreads - 1) / kTfThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ProfScope prof(kProfTransform, (cudaStream_t)stream);
+    transform_f64_kernel<<<(unsigned)blocks, kTfThreads, 0, (cudaStream_t)stream>>>(pts, n, pose, out);
+    return launched("transform_f64_kernel");
+}
 
 int64_t isr_soa_padded_len(int64_t n) {
     return n <= 0 ? ISR_SOA_TILE : isr::round_up(n, ISR_SOA_TILE);

@@ -43,7 +43,7 @@ def evaluate_registration(source, target, max_correspondence_distance, transform
     if len(source) == 0 or len(target) == 0:
         return RegistrationResult(api.IcpResult(T.copy(), 0.0, 0.0, 0, 0, True))
     return RegistrationResult(api.evaluate_registration(
-        np.asarray(source.points), np.asarray(target.points), max_correspondence_distance, T))
+        source._for_kernel(), target._for_kernel(), max_correspondence_distance, T))
 
 
 def registration_icp(source, target, max_correspondence_distance, init=None,
@@ -56,5 +56,5 @@ def registration_icp(source, target, max_correspondence_distance, init=None,
     if len(source) == 0 or len(target) == 0:
         return RegistrationResult(api.IcpResult(T.copy(), 0.0, 0.0, 0, 0, True))
     return RegistrationResult(api.icp(
-        np.asarray(source.points), np.asarray(target.points), T, max_correspondence_distance,
+        source._for_kernel(), target._for_kernel(), T, max_correspondence_distance,
         c.max_iteration, c.relative_fitness, c.relative_rmse))

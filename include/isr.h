@@ -84,6 +84,11 @@ int64_t isr_soa_padded_len(int64_t n);
 int isr_transform_points(const float *pts, int64_t n, const double *poses, int64_t b,
                          float *out, void *stream);
 
+/* out[i][:] = R pts[i] + t in float64 for ONE pose (out may alias pts): Open3D's
+ * PointCloud.transform keeps double coordinates (icp.py:22,110). */
+int isr_transform_points_f64(const double *pts, int64_t n, const double *pose, double *out,
+                             void *stream);
+
 /* Same transform written as padded planes out[b][3][npad] (the layout K2 consumes).
  * poses == NULL copies the cloud unchanged (b must be 1).  `pose_stride` is in doubles
  * (16 for a dense [b][16] array; larger when poses live inside IsrIcpState records).

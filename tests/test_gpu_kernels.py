@@ -749,6 +749,45 @@ def test_knn_normals_equal_the_pytorch3d_restatement(gpu, n, k):
         assert np.all(np.abs(got2 @ got2[0]) > 1 - 1e-6)
 
 
+def test_pointcloud_shim_transforms_large_clouds_on_the_device(gpu):
+    """o3d_compat.PointCloud keeps float64 coordinates; a cloud of >= 50k points is transformed on
+    the device (isr_transform_points_f64) and equals the float64 numpy transform to the last
+    bit or two; transform returns self and is in place; `+`, distances and ICP then run on the
+    device copy and agree with the host path (icp.py:22,110-117)."""
+    import imagesequenceregistrationfor6dposeestimationlabeling_b200.o3d_compat as o3d
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import synth
+    src, tgt, _ = synth.icp_pair(60000, 61000, 4, 5)
+    R, t = synth.true_pose(3)
+    T = synth.pose_matrix(R, t)
+    big = o3d.geometry.PointCloud()
+    big.points = o3d.utility.Vector3dVector(src.astype(np.float64))
+    assert big.transform(T) is big and big._dev is not None and len(big) == len(src)
+    want = src.astype(np.float64) @ R.T + t
+    np.testing.assert_allclose(np.asarray(big.points), want, rtol=0, atol=2e-13 * 800)
+    small = o3d.geometry.PointCloud()
+    small.points = o3d.utility.Vector3dVector(src[:1000].astype(np.float64))
+    small.transform(T)
+    assert small._dev is None
+    np.testing.assert_array_equal(np.asarray(small.points), want[:1000])
+    # back to the target frame on the device, then the icp.py tail: ICP, transform, merge, distance
+    big.transform(np.linalg.inv(T))
+    np.testing.assert_allclose(np.asarray(big.points), src.astype(np.float64), atol=1e-9)
+    target = o3d.geometry.PointCloud()
+    target.points = o3d.utility.Vector3dVector(tgt)
+    reg = o3d.pipelines.registration.registration_icp(
+        big, target, 20, np.eye(4), o3d.pipelines.registration.TransformationEstimationPointToPoint())
+    ref = gpu.icp(np.asarray(big.points), tgt, np.eye(4), 20.0)
+    np.testing.assert_allclose(reg.transformation, ref.transformation, rtol=1e-9, atol=1e-9)
+    merged = big.transform(reg.transformation) + target
+    assert len(merged) == len(src) + len(tgt) and merged._dev is not None
+    d = np.asarray(merged.compute_point_cloud_distance(target))
+    assert d.shape == (len(src) + len(tgt),) and np.all(d[len(src):] == 0.0)
+    host = np.concatenate([src.astype(np.float64) @ reg.transformation[:3, :3].T + reg.transformation[:3, 3],
+                           tgt.astype(np.float64)])
+    dk, _ = oracle.nearest(host, tgt)
+    np.testing.assert_allclose(d, dk, rtol=1e-5, atol=1e-9)
+
+
 def test_remove_radius_outlier_shim(gpu):
     """o3d.geometry.PointCloud.remove_radius_outlier as generateCors.py:254-258 calls it."""
     import imagesequenceregistrationfor6dposeestimationlabeling_b200.o3d_compat as o3d
