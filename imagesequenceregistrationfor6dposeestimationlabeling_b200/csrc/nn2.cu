@@ -583,6 +583,7 @@ struct alignas(128) PrunedWarpSmem {
     unsigned rows[kFifo];      //   query rows that the coarse test could not rule out
     unsigned box[kFifo];       //   packed half-extents of its bounding box about the sphere's centre
     float4 row[Q];             // sphere (c, rho) of query row r = the 32 queries r*32 .. r*32+31
+    float4 row2[Q];            // FUSED: second sphere of a row that the curve leaves and re-enters (w < 0: none)
     float rowB[Q];             // max of their bounds dq (refreshed between batches of work)
     uint64_t full[kRing];
     uint64_t qbar;             // mbarrier of the prologue's bulk copies of the warp's queries
@@ -606,7 +607,8 @@ __host__ __device__ inline int code_of_part(int parts, int c) {
 // FUSED: the kernel is one whole ICP evaluation + update (IcpFuse, icp_device.cuh): the queries
 // are made from the original source and the start's pose in the prologue, and the epilogue turns
 // the neighbours into the 17 correspondence sums, reduces them across the grid and solves.
-template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS, int GROUPS = 2, bool FUSED = false>
+template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS, int GROUPS = 2, bool FUSED = false,
+          bool SPLIT = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     static_assert(SUB == ISR_SUB_TILE && ISR_SOA_TILE / SUB == 16 && Q == 8, "pruning uses the spheres of prepare.cu");
@@ -764,6 +766,11 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         dmax = m;
     }
 
+    // SPLIT: cut rows at curve jumps (below).  A separate instantiation, launched only when the grid
+    // is at most one wave of whole blocks deep: there the slowest warp IS the iteration; in deeper
+    // grids the extra code and coarse-test work cost more than the shorter tail gains (1M x 1M
+    // on one GPU: -5 %, also when the code is merely present behind a run-time flag)
+    constexpr bool split_rows = SPLIT;
     // ---- query-row spheres: row r is 32 consecutive stored queries, a compact patch ----------
 #pragma unroll 1
     for (int r = 0; r < Q; ++r) {
@@ -786,6 +793,59 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         if (lane == 0) {
             ws.row[r] = make_float4(cx, cy, cz, cn > 0.f ? __fsqrt_ru(m) * 1.00002f : -1.f);
             ws.rowB[r] = cn > 0.f ? CUDART_INF_F : 0.f;
+        }
+        if (split_rows) {
+            // A row is 32 consecutive points of the curve.  Where the curve leaves the surface and
+            // re-enters it elsewhere, the row is two compact patches far apart and its ONE sphere
+            // covers everything in between: most of the target's stages and hundreds of sub-tiles
+            // pass the coarse tests and get an exact test each -- the slowest warps of a sharded
+            // ICP iteration, i.e. its duration.  A row whose largest gap between consecutive
+            // points exceeds its own radius is cut there and keeps one sphere per side when that
+            // halves the radius; the coarse tests then pass what reaches EITHER side.
+            const unsigned full = 0xffffffffu;
+            float4 SA = make_float4(0.f, 0.f, 0.f, -1.f), SB = SA;
+            const float nx = __shfl_down_sync(full, qx, 1), ny = __shfl_down_sync(full, qy, 1),
+                        nz = __shfl_down_sync(full, qz, 1);
+            const bool nlive = __shfl_down_sync(full, live ? 1 : 0, 1) != 0 && lane < 31;
+            const float gx = nx - qx, gy = ny - qy, gz = nz - qz;
+            const float gap = live && nlive ? fmaf(gz, gz, fmaf(gy, gy, gx * gx)) : -1.f;
+            unsigned key = gap >= 0.f ? ((__float_as_uint(gap) & 0xFFFFFFE0u) | (unsigned)lane) : 0u;
+            key = __reduce_max_sync(full, key);
+            if (key != 0u && __uint_as_float(key & 0xFFFFFFE0u) > m) {  // warp-uniform, rare
+                const bool a_side = lane <= (int)(key & 31u);  // lanes up to the cut: side A
+                float sxa = live && a_side ? qx : 0.f, sya = live && a_side ? qy : 0.f, sza = live && a_side ? qz : 0.f,
+                      sna = live && a_side ? 1.f : 0.f;
+                float sxb = live && !a_side ? qx : 0.f, syb = live && !a_side ? qy : 0.f, szb = live && !a_side ? qz : 0.f,
+                      snb = live && !a_side ? 1.f : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sxa += __shfl_xor_sync(full, sxa, o); sya += __shfl_xor_sync(full, sya, o);
+                    sza += __shfl_xor_sync(full, sza, o); sna += __shfl_xor_sync(full, sna, o);
+                    sxb += __shfl_xor_sync(full, sxb, o); syb += __shfl_xor_sync(full, syb, o);
+                    szb += __shfl_xor_sync(full, szb, o); snb += __shfl_xor_sync(full, snb, o);
+                }
+                if (sna > 0.f && snb > 0.f) {
+                    const float ia = 1.f / sna, ib = 1.f / snb;
+                    sxa *= ia; sya *= ia; sza *= ia; sxb *= ib; syb *= ib; szb *= ib;
+                    const float ux = qx - (a_side ? sxa : sxb), uy = qy - (a_side ? sya : syb),
+                                uz = qz - (a_side ? sza : szb);
+                    const float d2 = live ? fmaf(uz, uz, fmaf(uy, uy, ux * ux)) : 0.f;
+                    float ma = a_side ? d2 : 0.f, mb = a_side ? 0.f : d2;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        ma = fmaxf(ma, __shfl_xor_sync(full, ma, o));
+                        mb = fmaxf(mb, __shfl_xor_sync(full, mb, o));
+                    }
+                    if (4.0f * fmaxf(ma, mb) < m) {  // both sides at most half as wide as the row
+                        SA = make_float4(sxa, sya, sza, __fsqrt_ru(ma) * 1.00002f);
+                        SB = make_float4(sxb, syb, szb, __fsqrt_ru(mb) * 1.00002f);
+                    }
+                }
+            }
+            if (lane == 0) {
+                if (SB.w >= 0.f) ws.row[r] = SA;  // (the seed of this row then starts from side A)
+                ws.row2[r] = SB;
+            }
         }
     }
     __syncwarp();
@@ -810,6 +870,14 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
             const float rr = (ws.rowB[r] + R.w + S.w) * 1.0001f;
             if (R.w >= 0.f && !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr)) rows |= 1u << r;
+            if (split_rows) {
+                const float4 R2 = ws.row2[r];
+                if (R2.w >= 0.f) {  // warp-uniform, rare
+                    const float ex = S.x - R2.x, ey = S.y - R2.y, ez = S.z - R2.z;
+                    const float r2 = (ws.rowB[r] + R2.w + S.w) * 1.0001f;
+                    if (!(fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > r2 * r2)) rows |= 1u << r;
+                }
+            }
         }
         return S.w >= 0.f ? rows : 0u;
     };
@@ -829,6 +897,18 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             const bool out = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr ||
                              fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > rb * rb;
             if (R.w >= 0.f && !out) rows |= 1u << r;
+            if (split_rows) {
+                const float4 R2 = ws.row2[r];
+                if (R2.w >= 0.f) {  // warp-uniform, rare
+                    const float fx = S.x - R2.x, fy = S.y - R2.y, fz = S.z - R2.z;
+                    const float rb2 = (ws.rowB[r] + R2.w) * 1.0001f, rr2 = rb2 + S.w * 1.0001f;
+                    const float gx = fmaxf(fabsf(fx) - hx, 0.f), gy = fmaxf(fabsf(fy) - hy, 0.f),
+                                gz = fmaxf(fabsf(fz) - hz, 0.f);
+                    const bool out2 = fmaf(fz, fz, fmaf(fy, fy, fx * fx)) > rr2 * rr2 ||
+                                      fmaf(gz, gz, fmaf(gy, gy, gx * gx)) > rb2 * rb2;
+                    if (!out2) rows |= 1u << r;
+                }
+            }
         }
         return S.w >= 0.f ? rows : 0u;
     };
@@ -1395,7 +1475,8 @@ struct NN2Variant {
 using NN2Main = NN2Variant<8, 128, 1024, 3, 64, 4, 1>;
 
 // the pruned kernel: WARPS independent warps of 32 x Q queries per CTA
-template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS, int GROUPS = 2, bool FUSED = false>
+template <int Q, int WARPS, int SUB, int MINB, int UNR, int FLAG, int PARTS, int GROUPS = 2, bool FUSED = false,
+          bool SPLIT = false>
 struct NN2PrunedVariant {
     static constexpr int kQueriesPerCta = Q * WARPS * 32;
     static constexpr int kStage = ISR_SOA_TILE;
@@ -1404,7 +1485,7 @@ struct NN2PrunedVariant {
     static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q>);
 
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &fuse) {
-        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS, GROUPS, FUSED>;
+        auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS, GROUPS, FUSED, SPLIT>;
         static thread_local int configured_dev = -1;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -1451,6 +1532,7 @@ using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4>;
 using NN2PrunedHalves = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2>;
 using NN2PrunedFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4, true>;
 using NN2PrunedHalvesFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2, true>;
+using NN2PrunedFusedSplit = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4, true, true>;
 #ifdef ISR_NN_TUNING
 using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 2>;
 using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 4>;
@@ -1727,6 +1809,11 @@ int nn2_search(const IsrCloud *q, const IsrCloud *t, int64_t batch, int use_lo, 
         ISR_REQUIRE(aligned16(t->sub_c), ISR_E_ALIGN, "nn: sub-tile spheres must be 16-byte aligned");
         // (a batch of starts = multi-start ICP: scan-heavy, see NN2PrunedHalves)
         if (batch > 1) return nn2_dispatch<NN2PrunedHalvesFused>(c);
+        // a single start whose whole blocks fit one wave (a source shard of a multi-GPU run, a
+        // small cloud): the iteration lasts as long as its slowest warp -- cut rows at curve jumps
+        static const int split_env = env_int("ISR_NN_SPLIT_ROWS", -1);
+        const bool shallow = nn2_query_blocks(q->n) <= sm_count() * NN2PrunedFused::ctas_per_sm(true);
+        if (split_env >= 0 ? split_env != 0 : shallow) return nn2_dispatch<NN2PrunedFusedSplit>(c);
         return nn2_dispatch<NN2PrunedFused>(c);
     }
     if (t->sub_c != nullptr && t->stage_c != nullptr && pruning_on()) {

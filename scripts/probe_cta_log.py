@@ -1,5 +1,5 @@
 """Developer probe: per-CTA cost of the pruned search inside one fused ICP iteration
-(isr_debug_cta_log).  python scripts/probe_cta_log.py [points] [world]"""
+(isr_debug_cta_log).  python scripts/probe_cta_log.py [points] [world] [rank]"""
 import ctypes
 import os
 import sys
@@ -12,12 +12,13 @@ from imagesequenceregistrationfor6dposeestimationlabeling_b200 import _lib, api,
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 world = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+rank = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 torch.cuda.set_device(0)
 lib = _lib.load()
 src, tgt, _ = synth.icp_pair(n, n, 4, 5)
 perm = api.spatial_order(src).cpu().numpy()
 m = (n + world - 1) // world
-shard = src[perm[:m]]
+shard = src[perm[rank * m:(rank + 1) * m]]
 prob = api.IcpProblem(shard, tgt, np.eye(4)[None])
 prob.run(20.0, 2, 0.0, 0.0)
 prob.reopen()
