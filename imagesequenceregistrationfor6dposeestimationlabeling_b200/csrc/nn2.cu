@@ -574,6 +574,8 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
 constexpr int kRing = 4;    // sub-tile buffers in flight per warp
 constexpr int kFifo = 96;   // candidate sub-tiles queued per warp
 constexpr int kAnchors = 8; // seeds per warp: one per query row
+constexpr float kCutGap = 3.0f;   // SPLIT: a row is cut at gaps wider than its radius / kCutGap ...
+constexpr float kCutGain = 0.75f; //        ... when every piece is then at most this fraction of its radius wide
 
 template <int SUB, int Q>
 struct alignas(128) PrunedWarpSmem {
@@ -583,7 +585,7 @@ struct alignas(128) PrunedWarpSmem {
     unsigned rows[kFifo];      //   query rows that the coarse test could not rule out
     unsigned box[kFifo];       //   packed half-extents of its bounding box about the sphere's centre
     float4 row[Q];             // sphere (c, rho) of query row r = the 32 queries r*32 .. r*32+31
-    float4 row2[Q];            // FUSED: second sphere of a row that the curve leaves and re-enters (w < 0: none)
+    float4 rowx[Q][3];         // SPLIT: further spheres of a row that the curve leaves and re-enters (w < 0: none)
     float rowB[Q];             // max of their bounds dq (refreshed between batches of work)
     uint64_t full[kRing];
     uint64_t qbar;             // mbarrier of the prologue's bulk copies of the warp's queries
@@ -796,55 +798,63 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         }
         if (split_rows) {
             // A row is 32 consecutive points of the curve.  Where the curve leaves the surface and
-            // re-enters it elsewhere, the row is two compact patches far apart and its ONE sphere
-            // covers everything in between: most of the target's stages and hundreds of sub-tiles
-            // pass the coarse tests and get an exact test each -- the slowest warps of a sharded
-            // ICP iteration, i.e. its duration.  A row whose largest gap between consecutive
-            // points exceeds its own radius is cut there and keeps one sphere per side when that
-            // halves the radius; the coarse tests then pass what reaches EITHER side.
+            // re-enters it elsewhere, the row is several compact patches far apart and its ONE
+            // sphere covers everything in between: most of the target's stages and hundreds of
+            // sub-tiles pass the coarse tests and get an exact test each -- the slowest warps of a
+            // sharded ICP iteration, i.e. its duration.  Such a row is cut at its (up to three)
+            // largest gaps between consecutive points that exceed a third of its radius, and keeps
+            // one sphere per piece when every piece is clearly tighter than the row; the coarse
+            // tests then pass what reaches ANY piece.
             const unsigned full = 0xffffffffu;
-            float4 SA = make_float4(0.f, 0.f, 0.f, -1.f), SB = SA;
             const float nx = __shfl_down_sync(full, qx, 1), ny = __shfl_down_sync(full, qy, 1),
                         nz = __shfl_down_sync(full, qz, 1);
             const bool nlive = __shfl_down_sync(full, live ? 1 : 0, 1) != 0 && lane < 31;
             const float gx = nx - qx, gy = ny - qy, gz = nz - qz;
-            const float gap = live && nlive ? fmaf(gz, gz, fmaf(gy, gy, gx * gx)) : -1.f;
-            unsigned key = gap >= 0.f ? ((__float_as_uint(gap) & 0xFFFFFFE0u) | (unsigned)lane) : 0u;
-            key = __reduce_max_sync(full, key);
-            if (key != 0u && __uint_as_float(key & 0xFFFFFFE0u) > m) {  // warp-uniform, rare
-                const bool a_side = lane <= (int)(key & 31u);  // lanes up to the cut: side A
-                float sxa = live && a_side ? qx : 0.f, sya = live && a_side ? qy : 0.f, sza = live && a_side ? qz : 0.f,
-                      sna = live && a_side ? 1.f : 0.f;
-                float sxb = live && !a_side ? qx : 0.f, syb = live && !a_side ? qy : 0.f, szb = live && !a_side ? qz : 0.f,
-                      snb = live && !a_side ? 1.f : 0.f;
+            float gap = live && nlive ? fmaf(gz, gz, fmaf(gy, gy, gx * gx)) : -1.f;
+            unsigned cuts = 0;  // bit l: the row is cut between lanes l and l + 1
+#pragma unroll 1
+            for (int c = 0; c < 3; ++c) {
+                unsigned key = gap >= 0.f ? ((__float_as_uint(gap) & 0xFFFFFFE0u) | (unsigned)lane) : 0u;
+                key = __reduce_max_sync(full, key);
+                if (key == 0u || !(kCutGap * kCutGap * __uint_as_float(key & 0xFFFFFFE0u) > m)) break;  // gap <= radius / kCutGap
+                cuts |= 1u << (key & 31u);
+                if (lane == (int)(key & 31u)) gap = -1.f;
+            }
+            float4 seg[4];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    sxa += __shfl_xor_sync(full, sxa, o); sya += __shfl_xor_sync(full, sya, o);
-                    sza += __shfl_xor_sync(full, sza, o); sna += __shfl_xor_sync(full, sna, o);
-                    sxb += __shfl_xor_sync(full, sxb, o); syb += __shfl_xor_sync(full, syb, o);
-                    szb += __shfl_xor_sync(full, szb, o); snb += __shfl_xor_sync(full, snb, o);
-                }
-                if (sna > 0.f && snb > 0.f) {
-                    const float ia = 1.f / sna, ib = 1.f / snb;
-                    sxa *= ia; sya *= ia; sza *= ia; sxb *= ib; syb *= ib; szb *= ib;
-                    const float ux = qx - (a_side ? sxa : sxb), uy = qy - (a_side ? sya : syb),
-                                uz = qz - (a_side ? sza : szb);
-                    const float d2 = live ? fmaf(uz, uz, fmaf(uy, uy, ux * ux)) : 0.f;
-                    float ma = a_side ? d2 : 0.f, mb = a_side ? 0.f : d2;
+            for (int k = 0; k < 4; ++k) seg[k] = make_float4(0.f, 0.f, 0.f, -1.f);
+            if (cuts != 0u) {  // warp-uniform, rare
+                const int mine = __popc(cuts & ((1u << lane) - 1u));  // piece of this lane
+                float worst = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool in = live && mine == k;
+                    float sx = in ? qx : 0.f, sy = in ? qy : 0.f, sz = in ? qz : 0.f, sn = in ? 1.f : 0.f;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
-                        ma = fmaxf(ma, __shfl_xor_sync(full, ma, o));
-                        mb = fmaxf(mb, __shfl_xor_sync(full, mb, o));
+                        sx += __shfl_xor_sync(full, sx, o); sy += __shfl_xor_sync(full, sy, o);
+                        sz += __shfl_xor_sync(full, sz, o); sn += __shfl_xor_sync(full, sn, o);
                     }
-                    if (4.0f * fmaxf(ma, mb) < m) {  // both sides at most half as wide as the row
-                        SA = make_float4(sxa, sya, sza, __fsqrt_ru(ma) * 1.00002f);
-                        SB = make_float4(sxb, syb, szb, __fsqrt_ru(mb) * 1.00002f);
-                    }
+                    if (!(sn > 0.f)) continue;
+                    const float is = 1.f / sn;
+                    sx *= is; sy *= is; sz *= is;
+                    const float ux = qx - sx, uy = qy - sy, uz = qz - sz;
+                    float d2 = in ? fmaf(uz, uz, fmaf(uy, uy, ux * ux)) : 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(full, d2, o));
+                    seg[k] = make_float4(sx, sy, sz, __fsqrt_ru(d2) * 1.00002f);
+                    worst = fmaxf(worst, d2);
+                }
+                if (!(worst < kCutGain * kCutGain * m)) {  // the widest piece is not clearly tighter than the row: keep it whole
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) seg[k].w = -1.f;
                 }
             }
             if (lane == 0) {
-                if (SB.w >= 0.f) ws.row[r] = SA;  // (the seed of this row then starts from side A)
-                ws.row2[r] = SB;
+                if (seg[0].w >= 0.f) ws.row[r] = seg[0];  // (the seed of this row then starts from its first piece)
+                ws.rowx[r][0] = seg[0].w >= 0.f ? seg[1] : make_float4(0.f, 0.f, 0.f, -1.f);
+                ws.rowx[r][1] = seg[0].w >= 0.f ? seg[2] : make_float4(0.f, 0.f, 0.f, -1.f);
+                ws.rowx[r][2] = seg[0].w >= 0.f ? seg[3] : make_float4(0.f, 0.f, 0.f, -1.f);
             }
         }
     }
@@ -870,9 +880,11 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
             const float rr = (ws.rowB[r] + R.w + S.w) * 1.0001f;
             if (R.w >= 0.f && !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr)) rows |= 1u << r;
-            if (split_rows) {
-                const float4 R2 = ws.row2[r];
-                if (R2.w >= 0.f) {  // warp-uniform, rare
+            if (split_rows && ws.rowx[r][0].w >= 0.f) {  // warp-uniform, rare
+#pragma unroll 1
+                for (int k = 0; k < 3; ++k) {
+                    const float4 R2 = ws.rowx[r][k];
+                    if (R2.w < 0.f) break;
                     const float ex = S.x - R2.x, ey = S.y - R2.y, ez = S.z - R2.z;
                     const float r2 = (ws.rowB[r] + R2.w + S.w) * 1.0001f;
                     if (!(fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > r2 * r2)) rows |= 1u << r;
@@ -897,9 +909,11 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             const bool out = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr ||
                              fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > rb * rb;
             if (R.w >= 0.f && !out) rows |= 1u << r;
-            if (split_rows) {
-                const float4 R2 = ws.row2[r];
-                if (R2.w >= 0.f) {  // warp-uniform, rare
+            if (split_rows && ws.rowx[r][0].w >= 0.f) {  // warp-uniform, rare
+#pragma unroll 1
+                for (int k = 0; k < 3; ++k) {
+                    const float4 R2 = ws.rowx[r][k];
+                    if (R2.w < 0.f) break;
                     const float fx = S.x - R2.x, fy = S.y - R2.y, fz = S.z - R2.z;
                     const float rb2 = (ws.rowB[r] + R2.w) * 1.0001f, rr2 = rb2 + S.w * 1.0001f;
                     const float gx = fmaxf(fabsf(fx) - hx, 0.f), gy = fmaxf(fabsf(fy) - hy, 0.f),

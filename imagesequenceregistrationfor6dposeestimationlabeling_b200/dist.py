@@ -414,11 +414,13 @@ def icp_sharded(source, target, init=None, max_correspondence_distance: float = 
         # is an integer sort of the same keys on every rank (deterministic), so the ranks agree.
         from . import api
 
-        perm = api.spatial_order(source)[lo:hi].to(torch.int64)
-        if isinstance(source, torch.Tensor):
-            source_shard = source[perm.to(source.device)]
-        else:
-            source_shard = np.asarray(source)[perm.cpu().numpy()]
+        # (one upload of the whole source; order and gather on the device -- a float64 source keeps
+        # its precision, the order only needs float32 coordinates)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        src_dev = source.to(dev) if isinstance(source, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(source)).to(dev)
+        perm = api.spatial_order(src_dev.to(torch.float32))[lo:hi].to(torch.int64)
+        source_shard = src_dev.index_select(0, perm)
     else:
         source_shard = source[lo:hi]
 
