@@ -1,4 +1,5 @@
-"""Short driver for ncu captures of the HBM-bound kernels: K1, K1', K3."""
+"""Short driver for ncu captures of the HBM / L2-bound kernels: K1, K1', tile spheres, the stepwise
+ICP accumulate kernel, the FP64 transform, the ADD-S sphere bounds."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -16,4 +17,10 @@ for _ in range(2):
 src, tgt, _ = synth.icp_pair(1000000, 1000000, 4, 5)
 prob = api.IcpProblem(src, tgt[:100000], np.eye(4)[None])   # 1M sources (real K3), small target to keep the NN short
 prob.accumulate(20.0); prob.accumulate(20.0)
+d64 = torch.from_numpy(src.astype(np.float64)).cuda()
+api.transform_points_f64(d64, P[0], out=d64); api.transform_points_f64(d64, P[1], out=d64)
+verts = synth.make_cloud(20000, seed=3)
+verts = verts[api.spatial_order(verts).cpu().numpy()]
+t7 = api.prepare_cloud(cd, centroid=cen, perm=api.spatial_order(cd), stage_centroids=True)
+api.adds_bounds(verts, Pd, t7, presorted=True); api.adds_bounds(verts, Pd, t7, presorted=True)
 torch.cuda.synchronize(); print("ok")
