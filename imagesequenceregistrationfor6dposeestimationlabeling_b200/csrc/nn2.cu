@@ -98,10 +98,19 @@ struct NN2Params {
     int sort_fifo;           // scan the queued sub-tiles nearest-first (0: in stage order)
     const unsigned *sub_h;   // [batch][stages_total * STAGE/SUB] packed half-extents of the sub-tile
     long long sub_h_bstride; //   boxes (isr_tile_spheres), or NULL: sphere tests only
+    // target parts (fused ICP, shallow grids): the heaviest single-row entries of the launch list run
+    // as kTargetParts CTAs that share the row's queries and own every kTargetParts-th target stage;
+    // the last part to finish merges the (FP64 distance, index) pairs and carries on with the row
+    const int *order_slot;   // [gridDim.x] merge slot of a launch-list entry with a part code
+    double *tp_D;            // [slots][kTargetParts][32]
+    int *tp_I;               // [slots][kTargetParts][32]
+    unsigned *tp_tick;       // [slots], zero between launches
     unsigned long long *cta_log;  // developer probe (isr_debug_cta_log): 4 words per CTA, or NULL
     long long cta_log_cap;        //   records that fit
 };
 
+constexpr int kTargetParts = 4;   // CTAs that share the target of one heavy query row (a power of two <= 4)
+constexpr int kTargetSlots = 96;  // rows per launch that can run that way
 constexpr unsigned kNoBox = 0x3FFFFFFFu;  // three 10-bit fractions of the radius, all ones
 
 // Can this lane rule out every point of the tile with sphere S for all of its Q queries?
@@ -286,6 +295,9 @@ __device__ __forceinline__ bool resolve_flagged(const NN2Params &p, const float 
             const float *fz = reinterpret_cast<const float *>(sz);
             for (; wmask != 0; wmask &= wmask - 1) {
                 const int j = __ffsll((long long)wmask) - 1;
+                // the point already held (a hinted search meets its own hint again in every
+                // iteration): same arithmetic, same D -- nothing to decide, and no trip to the lo planes
+                if (gbase + j == ib && Db < CUDART_INF) continue;  // (ib is a placeholder until Db is finite)
                 const float px = fx[j], py = fy[j], pz = fz[j];
 #ifdef ISR_NN_TUNING
                 if (p.dbg != nullptr) atomicAdd(p.dbg + 3, 1ull);  // exact evaluations
@@ -624,12 +636,13 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     // heaviest query blocks first (order from block_order_kernel): the grid is only a few
     // waves deep for a single cloud pair, and a late-starting heavy block would be its tail.
     // The very widest blocks are split over 8 CTAs that own one query row each (rowsel).
-    int blk = (int)blockIdx.x, rowsel = 0;
+    int blk = (int)blockIdx.x, rowsel = 0, tpart = 0;
     if (p.order != nullptr) {
         if ((int)blockIdx.x >= p.order_count[b]) return;
         const int entry = p.order[(long long)b * gridDim.x + blockIdx.x];
         blk = entry & 0xFFFFFF;
-        rowsel = entry >> 24;  // rows_of_code
+        rowsel = (entry >> 24) & 15;  // rows_of_code
+        tpart = FUSED && SPLIT ? (entry >> 28) & 7 : 0;  // 0: the whole target; k: part k - 1 of kTargetParts
     }
     const unsigned own = rows_of_code(rowsel);  // rows this CTA is responsible for
     const int q0 = blk * (WARPS * 32 * Q) + warp * (32 * Q) + lane;
@@ -639,8 +652,11 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     for (int r = 0; r < Q; ++r)
         if (q0 + r * 32 < p.nq && ((own >> r) & 1u)) livemask |= 1u << r;
     const unsigned liverows = __reduce_or_sync(0xffffffffu, livemask);  // rows with a live query
+    // (they are consecutive: a CTA owns a run of rows, a cloud ends inside one); the per-row loops
+    // of the coarse tests walk this range only
+    const int r_lo = liverows != 0 ? __ffs(liverows) - 1 : 0, r_hi = 32 - __clz(liverows);
     if (liverows == 0) {
-        if (FUSED) {  // nothing to search, but the reduction counts on every CTA of the launch list
+        if (FUSED && tpart <= 1) {  // nothing to search, but the reduction counts on every row of the launch list
             double rs0[Q];
 #pragma unroll 1
             for (int r = 0; r < Q; ++r) rs0[r] = 0.0;
@@ -701,14 +717,17 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         ibest_l[r] = 0;
         dq_l[r] = live ? CUDART_INF_F : 0.f;
     }
-    mbar_wait(&ws.qbar, 0);
+    // (FUSED: the start's pose is fetched while the query copy is in flight)
+    double Tf[12], cf[3];
     if (FUSED) {
-        // the arithmetic of prepare_soa7_kernel: FP64 R p + t - c, split into a float32 hi/lo pair
-        double Tf[12], cf[3];
 #pragma unroll
         for (int k = 0; k < 12; ++k) Tf[k] = f.states[b].T[k];
 #pragma unroll
         for (int k = 0; k < 3; ++k) cf[k] = f.centroid[k];
+    }
+    mbar_wait(&ws.qbar, 0);
+    if (FUSED) {
+        // the arithmetic of prepare_soa7_kernel: FP64 R p + t - c, split into a float32 hi/lo pair
 #pragma unroll 1
         for (int r = 0; r < Q; ++r) {
             if (!((own >> r) & 1u)) continue;  // (rows of other CTAs keep the raw copy; never read)
@@ -776,6 +795,14 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     // ---- query-row spheres: row r is 32 consecutive stored queries, a compact patch ----------
 #pragma unroll 1
     for (int r = 0; r < Q; ++r) {
+        if (!((liverows >> r) & 1u)) {  // warp-uniform: a row of another CTA of this block, or beyond the cloud
+            if (lane == 0) {
+                ws.row[r] = make_float4(0.f, 0.f, 0.f, -1.f);
+                ws.rowB[r] = 0.f;
+                if (split_rows) ws.rowx[r][0] = ws.rowx[r][1] = ws.rowx[r][2] = make_float4(0.f, 0.f, 0.f, -1.f);
+            }
+            continue;
+        }
         const bool live = (livemask >> r) & 1u;
         const float qx = ws.qs[0][r * 32 + lane], qy = ws.qs[1][r * 32 + lane], qz = ws.qs[2][r * 32 + lane];
         float cx = live ? qx : 0.f, cy = live ? qy : 0.f, cz = live ? qz : 0.f, cn = live ? 1.f : 0.f;
@@ -863,7 +890,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     // value is merely conservative)
     auto refresh_bounds = [&]() {
 #pragma unroll 1
-        for (int r = 0; r < Q; ++r) {
+        for (int r = r_lo; r < r_hi; ++r) {
             float m = dq_l[r];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -875,7 +902,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     auto coarse_rows = [&](const float4 S) {
         unsigned rows = 0;
 #pragma unroll 1
-        for (int r = 0; r < Q; ++r) {
+        for (int r = r_lo; r < r_hi; ++r) {
             const float4 R = ws.row[r];
             const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
             const float rr = (ws.rowB[r] + R.w + S.w) * 1.0001f;
@@ -900,7 +927,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                     hz = (float)((hb >> 20) & 1023u) * sc;
         unsigned rows = 0;
 #pragma unroll 1
-        for (int r = 0; r < Q; ++r) {
+        for (int r = r_lo; r < r_hi; ++r) {
             const float4 R = ws.row[r];
             const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
             const float rb = (ws.rowB[r] + R.w) * 1.0001f, rr = rb + S.w * 1.0001f;
@@ -1086,7 +1113,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                         S2[k] = ws.sph[e]; id2[k] = ws.id[e]; rows2[k] = ws.rows[e]; box2[k] = ws.box[e];
                         float d = CUDART_INF_F;
 #pragma unroll 1
-                        for (int r = 0; r < Q; ++r) {
+                        for (int r = r_lo; r < r_hi; ++r) {
                             const float4 R = ws.row[r];
                             const float dx = S2[k].x - R.x, dy = S2[k].y - R.y, dz = S2[k].z - R.z;
                             const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -1195,6 +1222,9 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             Sst = stage_c[min(s, stages - 1)];
             rows_st = s < stages ? coarse_rows(Sst) : 0u;
             smask = __ballot_sync(0xffffffffu, rows_st != 0);
+            // a target part owns every kTargetParts-th stage (cbase is a multiple of 32); which
+            // part looks at a stage does not depend on anyone's bounds, so no stage is lost
+            if (FUSED && SPLIT && tpart != 0) smask &= (0xFFFFFFFFu / ((1u << kTargetParts) - 1u)) << (tpart - 1);
             continue;
         }
         // two candidate stages per step: lanes 0-15 take the sub-tiles of the first, lanes
@@ -1266,6 +1296,41 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                                        (unsigned long long)(ntests & 0xFFFFFFu));
     }
 
+    if (FUSED && SPLIT && tpart != 0) {
+        // ---- target parts -> the row's neighbours ---------------------------------------------------
+        // Every part has searched its share of the stages (all of them from the same hints): the
+        // row's neighbour is the best of the kTargetParts answers.  The last part to arrive merges.
+        const int r0 = __ffs(own) - 1;  // a part entry owns exactly one row
+        const int slot = p.order_slot[blockIdx.x];
+        double *mD = p.tp_D + ((size_t)slot * kTargetParts) * 32;
+        int *mI = p.tp_I + ((size_t)slot * kTargetParts) * 32;
+        mD[(tpart - 1) * 32 + lane] = Dbest_l[r0];
+        mI[(tpart - 1) * 32 + lane] = ibest_l[r0];
+        __threadfence();
+        __syncwarp();
+        unsigned last = 0;
+        if (lane == 0) last = atomicAdd(&p.tp_tick[slot], 1u) + 1u == (unsigned)kTargetParts ? 1u : 0u;
+        if (__shfl_sync(0xffffffffu, last, 0) == 0) return;
+        __threadfence();
+        double Db = Dbest_l[r0];
+        int ib = ibest_l[r0];
+#pragma unroll 1
+        for (int pp = 0; pp < kTargetParts; ++pp) {
+            if (pp == tpart - 1) continue;
+            const double D = __ldcg(&mD[pp * 32 + lane]);
+            const int i2 = __ldcg(&mI[pp * 32 + lane]);
+            bool take = D < Db;
+            if (D == Db && i2 != ib) {  // exact tie between different points: the lower ORIGINAL index
+                const int oc = p.perm_t != nullptr ? p.perm_t[min(i2, p.nt - 1)] : i2;
+                const int ob = p.perm_t != nullptr ? p.perm_t[min(ib, p.nt - 1)] : ib;
+                take = oc < ob;
+            }
+            if (take) { Db = D; ib = i2; }
+        }
+        Dbest_l[r0] = Db;
+        ibest_l[r0] = ib;
+        if (lane == 0) p.tp_tick[slot] = 0;
+    }
     if (FUSED) {
         // ---- correspondences -> per-row sums (icp_device.cuh) --------------------------------------
         // Distances are re-derived in FP64 from the ORIGINAL source point, the FP64 pose and the
@@ -1339,7 +1404,7 @@ constexpr int kOrderMax = 4096;  // blocks per batch item that the single-CTA so
 template <int QB>
 __global__ void __launch_bounds__(128)
 block_weight_kernel(const float *__restrict__ q, long long q_bstride, int nq, int nq_pad, int nqb,
-                    int batch, u64 *__restrict__ keys) {
+                    int batch, u64 *__restrict__ keys, float *__restrict__ rowrad) {
     const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= nqb * batch) return;
@@ -1376,6 +1441,26 @@ block_weight_kernel(const float *__restrict__ q, long long q_bstride, int nq, in
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     // ascending sort of ~bits(weight) = descending weight; ties by ascending block index
     if (lane == 0) keys[w] = ((u64)(~__float_as_uint(m)) << 32) | (u64)(unsigned)blk;
+    if (rowrad != nullptr) {  // squared radius of every query row about its own centroid (target parts)
+#pragma unroll 1
+        for (int r = 0; r < QB / 32; ++r) {
+            const bool live = blk * QB + r * 32 + lane < nq;
+            float cx = live ? x[r] : 0.f, cy = live ? y[r] : 0.f, cz = live ? z[r] : 0.f, cn = live ? 1.f : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                cx += __shfl_xor_sync(0xffffffffu, cx, o);
+                cy += __shfl_xor_sync(0xffffffffu, cy, o);
+                cz += __shfl_xor_sync(0xffffffffu, cz, o);
+                cn += __shfl_xor_sync(0xffffffffu, cn, o);
+            }
+            const float in = cn > 0.f ? 1.f / cn : 0.f;
+            const float dx = x[r] - cx * in, dy = y[r] - cy * in, dz = z[r] - cz * in;
+            float rm = live ? dx * dx + dy * dy + dz * dz : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+            if (lane == 0) rowrad[(long long)w * (QB / 32) + r] = rm;
+        }
+    }
 }
 
 // one CTA per batch item: bitonic sort of its <= kOrderMax keys; then the launch list:
@@ -1385,9 +1470,13 @@ block_weight_kernel(const float *__restrict__ q, long long q_bstride, int nq, in
 constexpr int kSplitMax = 128;  // (512 was measured slower: 25 % more total work, tail no longer the limit)
 __global__ void __launch_bounds__(1024)
 block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, int split_max, int parts,
-                   float split_factor, int *__restrict__ order, int *__restrict__ order_count) {
+                   float split_factor, int *__restrict__ order, int *__restrict__ order_count,
+                   const float *__restrict__ rowrad, float tp_factor, int tp_slots, int *__restrict__ order_slot,
+                   unsigned *__restrict__ tp_tick) {
     __shared__ u64 s[kOrderMax];
-    __shared__ int nsplit;
+    __shared__ int nsplit, nsplit_entries;
+    __shared__ short rowpos[kSplitMax * 8];   // first launch-list entry of row r of split block i
+    __shared__ signed char rowslot[kSplitMax * 8];  // its merge slot when it runs as target parts, else -1
     static_assert(kSplitMax == 128, "order_workspace_bytes sizes the launch list for 128 split blocks");
     const int b = blockIdx.x;
     int n2 = 1;
@@ -1410,20 +1499,46 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
         int h = 0;
         while (h < split_max && h < nqb && __uint_as_float(~(unsigned)(s[h] >> 32)) > split_factor * wmed) ++h;
         nsplit = h;
-        order_count[b] = parts * (nqb - h) + rows * h;
+        // rows of the split blocks that are themselves several patches far apart (a jump of the curve
+        // inside the row) run as kTargetParts CTAs over disjoint shares of the target
+        int pos = rowrad != nullptr ? 0 : h * rows, used = 0;
+        for (int i = 0; i < h && rowrad != nullptr; ++i) {
+            const int blk = (int)(unsigned)(s[i] & 0xffffffffull);
+            for (int r = 0; r < rows; ++r) {
+                const bool tp = used < tp_slots && rowrad[((long long)b * nqb + blk) * rows + r] > tp_factor * wmed;
+                rowpos[i * rows + r] = (short)pos;
+                rowslot[i * rows + r] = tp ? (signed char)used : (signed char)-1;
+                if (tp && tp_tick != nullptr) tp_tick[used] = 0;
+                pos += tp ? kTargetParts : 1;
+                used += tp ? 1 : 0;
+            }
+        }
+        nsplit_entries = pos;
+        order_count[b] = parts * (nqb - h) + pos;
     }
     __syncthreads();
-    const int h = nsplit;
+    const int h = nsplit, hbase = nsplit_entries;
     int *out = order + (long long)b * stride;
     for (int i = threadIdx.x; i < nqb; i += 1024) {
         const int blk = (int)(unsigned)(s[i] & 0xffffffffull);
         if (i < h) {
-            for (int r = 0; r < rows; ++r) out[i * rows + r] = blk | ((r + 1) << 24);
+            for (int r = 0; r < rows; ++r) {
+                const int at = rowrad != nullptr ? rowpos[i * rows + r] : i * rows + r;
+                const int sl = rowrad != nullptr ? rowslot[i * rows + r] : -1;
+                if (sl < 0) {
+                    out[at] = blk | ((r + 1) << 24);
+                } else {
+                    for (int k = 0; k < kTargetParts; ++k) {
+                        out[at + k] = blk | ((r + 1) << 24) | ((k + 1) << 28);
+                        order_slot[at + k] = sl;
+                    }
+                }
+            }
         } else {
             // a grid that does not fill the machine: every block runs as `parts` CTAs of 8 / parts
             // query rows (the scan skips the rows a CTA does not own, so the split costs little
             // and shortens the tail)
-            for (int c = 0; c < parts; ++c) out[h * rows + parts * (i - h) + c] = blk | (code_of_part(parts, c) << 24);
+            for (int c = 0; c < parts; ++c) out[hbase + parts * (i - h) + c] = blk | (code_of_part(parts, c) << 24);
         }
     }
 }
@@ -1459,6 +1574,7 @@ struct NN2Variant {
     static constexpr size_t kSmem = (size_t)NSTAGES * 4 * STAGE * 4 + NSTAGES * 8;
 
     static constexpr bool kFused = false;
+    static constexpr bool kSplit = false;
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &) {
         auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR>;
         static thread_local int configured_dev = -1;
@@ -1496,6 +1612,7 @@ struct NN2PrunedVariant {
     static constexpr int kStage = ISR_SOA_TILE;
     static constexpr bool kPrune = true;
     static constexpr bool kFused = FUSED;
+    static constexpr bool kSplit = SPLIT;
     static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q>);
 
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &fuse) {
@@ -1546,7 +1663,10 @@ using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4>;
 using NN2PrunedHalves = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2>;
 using NN2PrunedFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4, true>;
 using NN2PrunedHalvesFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2, true>;
-using NN2PrunedFusedSplit = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4, true, true>;
+// (flags per quarter of the sub-tile, so that a resolve pass re-derives 16 filter values instead of
+// 64: in a shallow grid a warp's instruction count IS its latency -- 0.161 -> 0.155 ms per
+// iteration on a 1/8 shard; in deep grids the same change was measured 0 .. -2 %)
+using NN2PrunedFusedSplit = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 4, 4, true, true>;
 #ifdef ISR_NN_TUNING
 using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 2>;
 using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 4>;
@@ -1598,10 +1718,15 @@ static int choose_splits(long long ctas, int stages, int slots) {
     return splits;
 }
 
+constexpr size_t kTargetPartBytes =  // row radii are sized per call; these are the fixed pieces
+    (size_t)kTargetSlots * kTargetParts * 32 * (8 + 4) + (size_t)kTargetSlots * 4;
 static size_t order_workspace_bytes(long long nqb, long long batch) {
-    // keys, launch list (room for every block as 8 single-row entries), entry counts
-    return align256((size_t)nqb * batch * 8) + align256((size_t)(8 * nqb) * batch * 4) +
-           align256((size_t)batch * 4);
+    // keys, launch list (room for every block as 8 single-row entries, plus the extra entries of
+    // rows that run as target parts), entry counts; for target parts: merge slots of the entries,
+    // row radii, merge buffers and tickets
+    const size_t list = (size_t)(8 * nqb + kTargetParts * kTargetSlots) * batch * 4;
+    return align256((size_t)nqb * batch * 8) + 2 * align256(list) + align256((size_t)batch * 4) +
+           align256((size_t)nqb * batch * 8 * 4) + align256(kTargetPartBytes);
 }
 
 // run-time tuning knob, read once: ISR_<name> in the environment, else the default
@@ -1669,6 +1794,7 @@ static int nn2_dispatch(const NN2Call &c) {
 #endif
     p.order = nullptr;
     p.order_count = nullptr;
+    p.order_slot = nullptr; p.tp_D = nullptr; p.tp_I = nullptr; p.tp_tick = nullptr;
     int grid_x = nqb;
     if (V::kPrune && nqb > 1 && nqb <= kOrderMax && c.workspace != nullptr &&
         c.workspace_bytes >= order_workspace_bytes(nqb, c.batch)) {
@@ -1690,19 +1816,38 @@ static int nn2_dispatch(const NN2Call &c) {
         int parts = 1;
         while (parts < parts_max && 2ll * parts * nqb * c.batch <= slots) parts *= 2;
         if (split_max > nqb) split_max = nqb;
-        const int stride = parts * nqb + (kRows - parts) * split_max;
+        // target parts: only in the split instantiation of the fused ICP iteration (one start,
+        // shallow grid), where the slowest single row is the iteration
+        // (read per call, not cached: the tests switch them within one process)
+        const int tp_slots_env = env_int("ISR_NN_TP_SLOTS", kTargetSlots);
+        const float tp_factor = (float)env_int("ISR_NN_TP_FACTOR_X10", 40) * 0.1f;
+        const int tp_slots = V::kFused && V::kSplit && c.batch == 1 && split_max > 0
+                                 ? (tp_slots_env < kTargetSlots ? tp_slots_env : kTargetSlots) : 0;
+        const int stride = parts * nqb + (kRows - parts) * split_max + (kTargetParts - 1) * tp_slots;
         char *w = reinterpret_cast<char *>(c.workspace);
+        const size_t list = align256((size_t)(8 * nqb + kTargetParts * kTargetSlots) * c.batch * 4);
         u64 *keys = reinterpret_cast<u64 *>(w);
-        int *order = reinterpret_cast<int *>(w + align256((size_t)nqb * c.batch * 8));
-        int *count = reinterpret_cast<int *>(w + align256((size_t)nqb * c.batch * 8) +
-                                             align256((size_t)stride * c.batch * 4));
+        w += align256((size_t)nqb * c.batch * 8);
+        int *order = reinterpret_cast<int *>(w);
+        w += list;
+        int *order_slot = reinterpret_cast<int *>(w);
+        w += list;
+        int *count = reinterpret_cast<int *>(w);
+        w += align256((size_t)c.batch * 4);
+        float *rowrad = reinterpret_cast<float *>(w);
+        w += align256((size_t)nqb * c.batch * 8 * 4);
+        p.tp_D = reinterpret_cast<double *>(w);
+        p.tp_I = reinterpret_cast<int *>(w + (size_t)kTargetSlots * kTargetParts * 32 * 8);
+        p.tp_tick = reinterpret_cast<unsigned *>(w + (size_t)kTargetSlots * kTargetParts * 32 * 12);
+        p.order_slot = order_slot;
         const long long warps = (long long)nqb * c.batch;
         if (!c.reuse_order) {
             block_weight_kernel<V::kQueriesPerCta><<<(unsigned)((warps + 3) / 4), 128, 0, c.st>>>(
-                p.q, p.q_bstride, p.nq, p.nq_pad, nqb, (int)c.batch, keys);
+                p.q, p.q_bstride, p.nq, p.nq_pad, nqb, (int)c.batch, keys, tp_slots > 0 ? rowrad : nullptr);
             ISR_TRY(launched("block_weight_kernel"));
-            block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(keys, nqb, kRows, stride, split_max, parts,
-                                                                     split_factor, order, count);
+            block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(
+                keys, nqb, kRows, stride, split_max, parts, split_factor, order, count,
+                tp_slots > 0 ? rowrad : nullptr, tp_factor, tp_slots, order_slot, p.tp_tick);
             ISR_TRY(launched("block_order_kernel"));
         }
         p.order = order;
