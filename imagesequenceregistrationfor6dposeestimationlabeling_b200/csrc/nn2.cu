@@ -1815,6 +1815,7 @@ static int nn2_dispatch(const NN2Call &c) {
         static const int parts_max = env_int("ISR_NN_PARTS_MAX", 8);
         int parts = 1;
         while (parts < parts_max && 2ll * parts * nqb * c.batch <= slots) parts *= 2;
+        { const int force = env_int("ISR_NN_PARTS_FORCE", 0); if (force > 0) parts = force; }
         if (split_max > nqb) split_max = nqb;
         // target parts: only in the split instantiation of the fused ICP iteration (one start,
         // shallow grid), where the slowest single row is the iteration
