@@ -1279,7 +1279,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             o[0] = (unsigned long long)(clock64() - t_start);
             o[1] = ((unsigned long long)nscanned << 32) | ntests;
             o[2] = ((unsigned long long)nhalves << 32) | ncand;
-            o[3] = ((unsigned long long)(unsigned)blk << 32) | ((unsigned long long)rowsel << 24) | (npass & 0xFFFFFFu);
+            o[3] = ((unsigned long long)(unsigned)blk << 32) | ((unsigned long long)(rowsel | (tpart << 4)) << 24) | (npass & 0xFFFFFFu);
         }
     }
     if (p.evaluated != nullptr && lane == 0) {

@@ -588,6 +588,45 @@ def test_icp_kernel_fused_exchange_single_rank_equals_icp_run(gpu):
         dist.icp_sharded(src, tgt, np.tile(np.eye(4), (65, 1, 1)), 20.0, max_iteration=1, exchange="peer")
 
 
+def test_fused_icp_target_parts_are_bit_identical(gpu, monkeypatch):
+    """Shallow grids run the widest single rows of the split blocks as four CTAs that own
+    disjoint shares of the target's stages and merge their (FP64 distance, index) answers
+    (nn2.cu, kTargetParts).  With the threshold lowered so that every row of every split block
+    runs that way, poses, rmse and correspondences equal the run without target parts bit for
+    bit, and the per-CTA log shows that part CTAs did run."""
+    import ctypes
+    import torch
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import _lib, api, synth
+    n = 120_000
+    src, tgt, _ = synth.icp_pair(n, n, 4, 5)
+    perm = api.spatial_order(src).cpu().numpy()
+    shard = src[perm[: n // 4]]          # a compact run of the curve, as dist.icp_sharded cuts it
+    lib = _lib.load()
+    out = {}
+    for label, slots in (("off", "0"), ("on", "96")):
+        monkeypatch.setenv("ISR_NN_TP_SLOTS", slots)
+        monkeypatch.setenv("ISR_NN_TP_FACTOR_X10", "1")
+        prob = api.IcpProblem(shard, tgt, np.eye(4)[None])
+        cap = 20000
+        log = torch.zeros((cap, 4), dtype=torch.int64, device="cuda")
+        lib.isr_debug_cta_log(ctypes.c_void_p(log.data_ptr()), cap)
+        try:
+            prob.run(20.0, 6, 0.0, 0.0)
+            torch.cuda.synchronize()
+        finally:
+            lib.isr_debug_cta_log(None, 0)
+        codes = (log.cpu().numpy().astype(np.uint64)[:, 3] >> np.uint64(24)) & np.uint64(0xFF)
+        out[label] = (prob.results(True)[0], int((codes >= 16).sum()))
+    (a, parts_off), (b, parts_on) = out["off"], out["on"]
+    assert parts_off == 0 and parts_on >= 4, (parts_off, parts_on)
+    np.testing.assert_array_equal(a.transformation, b.transformation)
+    assert (a.fitness, a.inlier_rmse, a.iterations) == (b.fitness, b.inlier_rmse, b.iterations)
+    np.testing.assert_array_equal(np.asarray(a.correspondence_set), np.asarray(b.correspondence_set))
+    o = oracle.registration_icp(shard, tgt, 20.0, np.eye(4), max_iteration=6, relative_fitness=0.0, relative_rmse=0.0)
+    np.testing.assert_array_equal(np.asarray(b.correspondence_set), o.correspondence_set)
+    np.testing.assert_allclose(b.transformation, o.transformation, rtol=1e-7, atol=1e-7)
+
+
 @pytest.mark.parametrize("n,radius,scale,offset", [
     (1, 1.0, 1.0, 0.0), (300, 3.0, 1.0, 0.0), (6000, 4.0, 1.0, 0.0), (6000, 0.05 * 60 / 1.8, 1.0, 0.0),
     (5000, 0.002, 1.0 / 2000, 0.0), (4000, 4.0, 1.0, 700.0), (3000, 1e-3, 1.0, 900.0)])
