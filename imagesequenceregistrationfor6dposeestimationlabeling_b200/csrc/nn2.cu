@@ -47,7 +47,7 @@
 //   (3) when everything is queued, the entries are put in nearest-first order;
 //   (4) each entry gets the exact per-query test with the bounds of that moment (which also
 //       yields the rows that still need it); a survivor's 1 KB bulk copy is issued at once, up
-//       to four entries ahead of the scan, and it is scanned for the quarters (two rows each)
+//       to three entries ahead of the scan, and it is scanned for the quarters (two rows each)
 //       that need it.
 // The exactness argument above is untouched: the true neighbour's tile is never skipped
 // (its distance is <= every bound), so it is visited, flagged and resolved as before.
@@ -212,7 +212,7 @@ __device__ __forceinline__ void scan_rows(const float4 *sx, const float4 *sy, co
 // where the filter minimum of that piece came within the row's threshold; tm: the filter
 // minima over the whole sub-tile.  sx..sn point at the sub-tile's x, y, z, |p|^2 values in
 // shared memory; gbase is the stored index of its first target.  The resolve state (mt_l ..
-// dq_l) is indexed at run time, which places it in (L1-resident) local memory and keeps it
+// ibest_l) is indexed at run time, which places it in local memory and keeps it
 // out of the scan's registers.  Returns whether anything was flagged.
 template <int Q, int SUB, bool PRUNE, int PARTS>
 __device__ __forceinline__ bool resolve_flagged(const NN2Params &p, const float *__restrict__ gq,
@@ -222,7 +222,7 @@ __device__ __forceinline__ bool resolve_flagged(const NN2Params &p, const float 
                                                 const float (&tm)[Q], float *mt_l, float *thr_l,
                                                 float *tm_l, double *Dbest_l, int *ibest_l,
                                                 float *dq_l, float &dmax, unsigned &nflag,
-                                                unsigned &npass, const float *qsm) {
+                                                unsigned &npass, const float *qsm, const float *qlo) {
     // bit r: row r has a flagged piece
     const unsigned flags = (pflags | (pflags >> 8) | (pflags >> 16) | (pflags >> 24)) & 0xFFu;
     if (PRUNE && (p.evaluated != nullptr || p.cta_log != nullptr)) {  // profiling only
@@ -251,7 +251,7 @@ __device__ __forceinline__ bool resolve_flagged(const NN2Params &p, const float 
 #endif
             const int qi = min(q0 + r * 32, p.nq_pad - 1);
             // the query's coordinates: from the warp's shared-memory copy when there is one
-            // (qsm: [6][32 * Q], hi xyz then lo xyz), else from global memory
+            // (qsm: [3][32 * Q], hi xyz; the lo parts sit in the lane's local array qlo), else from global memory
             const int qs = r * 32 + lane;
             const float qhx = PRUNE ? qsm[qs] : gq[qi], qhy = PRUNE ? qsm[32 * Q + qs] : gq[p.nq_pad + qi],
                         qhz = PRUNE ? qsm[2 * 32 * Q + qs] : gq[2ll * p.nq_pad + qi];
@@ -263,9 +263,9 @@ __device__ __forceinline__ bool resolve_flagged(const NN2Params &p, const float 
             thr_l[r] = th;
             double qlx = 0.0, qly = 0.0, qlz = 0.0;
             if (p.use_lo) {
-                qlx = PRUNE ? qsm[3 * 32 * Q + qs] : gq[4ll * p.nq_pad + qi];
-                qly = PRUNE ? qsm[4 * 32 * Q + qs] : gq[5ll * p.nq_pad + qi];
-                qlz = PRUNE ? qsm[5 * 32 * Q + qs] : gq[6ll * p.nq_pad + qi];
+                qlx = PRUNE ? qlo[r] : gq[4ll * p.nq_pad + qi];
+                qly = PRUNE ? qlo[Q + r] : gq[5ll * p.nq_pad + qi];
+                qlz = PRUNE ? qlo[2 * Q + r] : gq[6ll * p.nq_pad + qi];
             }
             double Db = Dbest_l[r];
             int ib = ibest_l[r];
@@ -331,11 +331,11 @@ __device__ __forceinline__ bool resolve_flagged(const NN2Params &p, const float 
             ibest_l[r] = ib;
             // >= the exact best distance of the FP64 (hi + lo) query, rounded up
             if (PRUNE)
-                dq_l[r] = __fsqrt_ru(__double2float_ru(Db)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
+                dq_l[r * 32] = __fsqrt_ru(__double2float_ru(Db)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
         }
         if (PRUNE) {
             float m = 0.f;
-            for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r]);  // run-time loop on purpose
+            for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r * 32]);  // run-time loop on purpose
             dmax = m;
         }
     }
@@ -360,7 +360,7 @@ __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__
     unsigned pflags = 0;
     scan_rows<Q, 0, Q, SUB, UNR, 1>(sx, sy, sz, sn, q2x, q2y, q2z, thr, tm, pflags);
     if (resolve_flagged<Q, SUB, false, 1>(p, gq, gt, q0, lane, sx, sy, sz, sn, gbase, pflags, tm, mt_l, thr_l,
-                                          tm_l, Dbest_l, ibest_l, dq_l, dmax, nflag, npass, nullptr)) {
+                                          tm_l, Dbest_l, ibest_l, dq_l, dmax, nflag, npass, nullptr, nullptr)) {
 #pragma unroll
         for (int r = 0; r < Q; ++r) thr[r] = thr_l[r];
     }
@@ -370,7 +370,7 @@ __device__ __forceinline__ void scan_subtile(const NN2Params &p, const float *__
 // (GROUPS = 4: quarters of two rows) in which the exact test could not rule out every row
 // (`rows`): an unscanned row keeps tm = +inf and never flags.  A group's operands (-2 q and the
 // thresholds) are fetched for the scan
-// from the warp's shared-memory copy of its queries (qsm: [6][32 * Q], hi xyz then lo xyz)
+// from the warp's shared-memory copy of its queries (qsm: [3][32 * Q], hi xyz)
 // and from the resolve state, so that they occupy registers only while a scan runs.
 template <int Q, int SUB, int UNR, int PARTS, int GROUPS>
 __device__ __forceinline__ void scan_subtile_pruned(const NN2Params &p, const float *__restrict__ gq,
@@ -379,7 +379,7 @@ __device__ __forceinline__ void scan_subtile_pruned(const NN2Params &p, const fl
                                                     const float4 *sn, int gbase, float *mt_l, float *thr_l,
                                                     float *tm_l, double *Dbest_l, int *ibest_l, float *dq_l,
                                                     float &dmax, unsigned &nflag, unsigned &npass,
-                                                    const float *qsm, unsigned rows) {
+                                                    const float *qsm, const float *qlo, unsigned rows) {
     static_assert(Q == 8 && (GROUPS == 2 || GROUPS == 4), "halves of four rows or quarters of two");
     constexpr int H = Q / GROUPS;
     float tm[Q];
@@ -407,7 +407,7 @@ __device__ __forceinline__ void scan_subtile_pruned(const NN2Params &p, const fl
         }
     }
     resolve_flagged<Q, SUB, true, PARTS>(p, gq, gt, q0, lane, sx, sy, sz, sn, gbase, pflags, tm, mt_l, thr_l, tm_l,
-                                         Dbest_l, ibest_l, dq_l, dmax, nflag, npass, qsm);
+                                         Dbest_l, ibest_l, dq_l, dmax, nflag, npass, qsm, qlo);
 }
 
 // ---- exhaustive kernel: every stage, every sub-tile -----------------------------------------
@@ -583,13 +583,24 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
 }
 
 // ---- pruned kernel: warp-autonomous, sub-tile granularity ------------------------------------
-constexpr int kRing = 4;    // sub-tile buffers in flight per warp
-constexpr int kFifo = 96;   // candidate sub-tiles queued per warp
+// (developer A/B builds override these: scripts/build_variants.sh.  Measured with the bounds in shared
+// memory, 20 CTAs per SM unless noted -- verification candidates/s | 1M x 1M ICP ms | ADD-S pairs/s:
+// FIFO 96 / ring 3: 10628 | 0.529 | 47.3k;  72 / 4: 10499 | 0.528 | 47.0k;  64 / 4: 10455 | 0.525 | 47.1k;
+// 96 / 4 (19 CTAs per SM): 10419 | 0.530 | 47.1k;  before, bounds in local memory and the queries' lo
+// parts in shared memory (16 CTAs per SM for ICP): 10560 | 0.550 | 46.6k)
+#ifndef ISR_NN_RING
+#define ISR_NN_RING 3
+#endif
+#ifndef ISR_NN_FIFO
+#define ISR_NN_FIFO 96
+#endif
+constexpr int kRing = ISR_NN_RING;  // sub-tile buffers in flight per warp
+constexpr int kFifo = ISR_NN_FIFO;  // candidate sub-tiles queued per warp (the nearest-first sort handles up to 64)
 constexpr int kAnchors = 8; // seeds per warp: one per query row
 constexpr float kCutGap = 3.0f;   // SPLIT: a row is cut at gaps wider than its radius / kCutGap ...
 constexpr float kCutGain = 0.75f; //        ... when every piece is then at most this fraction of its radius wide
 
-template <int SUB, int Q>
+template <int SUB, int Q, bool SPLIT>
 struct alignas(128) PrunedWarpSmem {
     float buf[kRing][4][SUB];  // x, y, z, |p|^2 of one sub-tile per slot
     float4 sph[kFifo];         // queued candidates: sphere,
@@ -597,12 +608,17 @@ struct alignas(128) PrunedWarpSmem {
     unsigned rows[kFifo];      //   query rows that the coarse test could not rule out
     unsigned box[kFifo];       //   packed half-extents of its bounding box about the sphere's centre
     float4 row[Q];             // sphere (c, rho) of query row r = the 32 queries r*32 .. r*32+31
-    float4 rowx[Q][3];         // SPLIT: further spheres of a row that the curve leaves and re-enters (w < 0: none)
+    float4 rowx[SPLIT ? Q : 1][3];  // SPLIT: further spheres of a row that the curve leaves and re-enters (w < 0: none)
     float rowB[Q];             // max of their bounds dq (refreshed between batches of work)
     uint64_t full[kRing];
     uint64_t qbar;             // mbarrier of the prologue's bulk copies of the warp's queries
     int seed[kAnchors];        // sub-tiles scanned first (-1: none)
-    alignas(16) float qs[6][32 * Q];  // the warp's queries, hi xyz and lo xyz (read by the scan and the resolve path)
+    alignas(16) float qs[3][32 * Q];  // the warp's queries, hi xyz (read by the scan, the tests and the resolve path)
+    // dq[r][lane] >= the exact best distance so far of query r * 32 + lane (0: no such query).  Read by
+    // every exact test; in local memory (with the rest of the resolve state) five of six of those
+    // loads missed the small L1 that the shared-memory carve-out leaves.  The queries' lo parts, which
+    // only the hints and the resolve's FP64 pass read, went the other way (local memory).
+    float dq[Q][32];
 };
 
 // rows of a query block that launch-list code `rowsel` stands for: 0 all eight, 1..8 one row,
@@ -665,7 +681,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         return;
     }
     const long long t_start = clock64();
-    PrunedWarpSmem<SUB, Q> &ws = reinterpret_cast<PrunedWarpSmem<SUB, Q> *>(smem_raw)[warp];
+    PrunedWarpSmem<SUB, Q, SPLIT> &ws = reinterpret_cast<PrunedWarpSmem<SUB, Q, SPLIT> *>(smem_raw)[warp];
     const float *__restrict__ gq = p.q + (long long)b * p.q_bstride;
     const float *__restrict__ gt = p.t + (long long)b * p.t_bstride;
     const float4 *__restrict__ stage_c = p.stage_c + (long long)b * p.stage_c_bstride;
@@ -691,10 +707,11 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl)
             bulk_g2s(&ws.qs[pl][0], base + (long long)pl * p.nq_pad + qbase, 32u * Q * 4u, &ws.qbar);
-        if (lo) {
+        if (lo) {  // the lo planes pass through the (still idle) ring buffer on their way to local memory
 #pragma unroll
             for (int pl = 0; pl < 3; ++pl)
-                bulk_g2s(&ws.qs[3 + pl][0], base + (long long)(4 + pl) * p.nq_pad + qbase, 32u * Q * 4u, &ws.qbar);
+                bulk_g2s(&ws.buf[0][0][0] + pl * 32 * Q, base + (long long)(4 + pl) * p.nq_pad + qbase, 32u * Q * 4u,
+                         &ws.qbar);
         }
     }
 
@@ -703,7 +720,10 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     // for the instruction cache when the warps of an SM sit in different phases, and every
     // loop unrolled over the 8 rows multiplies it (124 KB of SASS before, no_instruction the
     // fastest-growing stall when more warps were made resident).
-    float mt_l[Q], thr_l[Q], tm_l[Q], dq_l[Q];
+    static_assert(sizeof(ws.buf) >= 3 * 32 * Q * sizeof(float), "lo planes land in the ring buffer");
+    float mt_l[Q], thr_l[Q], tm_l[Q];
+    float qlo[3 * Q];  // lo parts of the lane's queries: x of rows 0..7, then y, then z (local memory)
+    float *dq_l = &ws.dq[0][lane];  // this lane's bounds: dq_l[r * 32]
     double Dbest_l[Q];
     int ibest_l[Q];
     float dmax = 0.f;  // max over the lane's live queries of dq_l (0: no live query)
@@ -715,7 +735,8 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         thr_l[r] = live ? CUDART_INF_F : -CUDART_INF_F;
         Dbest_l[r] = CUDART_INF;
         ibest_l[r] = 0;
-        dq_l[r] = live ? CUDART_INF_F : 0.f;
+        dq_l[r * 32] = live ? CUDART_INF_F : 0.f;
+        qlo[r] = 0.f; qlo[Q + r] = 0.f; qlo[2 * Q + r] = 0.f;
     }
     // (FUSED: the start's pose is fetched while the query copy is in flight)
     double Tf[12], cf[3];
@@ -734,9 +755,10 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             const int qs = r * 32 + lane;
             float hx = ISR_PAD_COORD, hy = ISR_PAD_COORD, hz = ISR_PAD_COORD, lx = 0.f, ly = 0.f, lz = 0.f;
             if (q0 + r * 32 < p.nq) {
-                const double px = (double)ws.qs[0][qs] + (double)ws.qs[3][qs];
-                const double py = (double)ws.qs[1][qs] + (double)ws.qs[4][qs];
-                const double pz = (double)ws.qs[2][qs] + (double)ws.qs[5][qs];
+                const float *lo_in = &ws.buf[0][0][0];
+                const double px = (double)ws.qs[0][qs] + (double)lo_in[qs];
+                const double py = (double)ws.qs[1][qs] + (double)lo_in[32 * Q + qs];
+                const double pz = (double)ws.qs[2][qs] + (double)lo_in[2 * 32 * Q + qs];
                 double x, y, z;
                 icp_apply_pose(Tf, px, py, pz, x, y, z);
                 x -= cf[0]; y -= cf[1]; z -= cf[2];
@@ -744,9 +766,17 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                 lx = (float)(x - (double)hx); ly = (float)(y - (double)hy); lz = (float)(z - (double)hz);
             }
             ws.qs[0][qs] = hx; ws.qs[1][qs] = hy; ws.qs[2][qs] = hz;
-            ws.qs[3][qs] = lx; ws.qs[4][qs] = ly; ws.qs[5][qs] = lz;
+            qlo[r] = lx; qlo[Q + r] = ly; qlo[2 * Q + r] = lz;
+        }
+    } else if (p.use_lo) {
+        const float *lo_in = &ws.buf[0][0][0];
+#pragma unroll 1
+        for (int r = 0; r < Q; ++r) {
+            const int qs = r * 32 + lane;
+            qlo[r] = lo_in[qs]; qlo[Q + r] = lo_in[32 * Q + qs]; qlo[2 * Q + r] = lo_in[2 * 32 * Q + qs];
         }
     }
+    __syncwarp();  // every lane has its lo parts before the ring buffer is handed to the bulk copies
 
     // ---- starting bounds from the caller's hints (the previous search's neighbours) ----------
     // A hinted query starts as if its hint had already been scanned and resolved: running
@@ -768,9 +798,9 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                                       __fmaf_rn(-2.0f * qhz, pz, gt[3ll * p.nt_pad + h])));
             double dx = (double)qhx - (double)px, dy = (double)qhy - (double)py, dz = (double)qhz - (double)pz;
             if (p.use_lo) {
-                dx += (double)ws.qs[3][qs] - (double)gt[4ll * p.nt_pad + h];
-                dy += (double)ws.qs[4][qs] - (double)gt[5ll * p.nt_pad + h];
-                dz += (double)ws.qs[5][qs] - (double)gt[6ll * p.nt_pad + h];
+                dx += (double)qlo[r] - (double)gt[4ll * p.nt_pad + h];
+                dy += (double)qlo[Q + r] - (double)gt[5ll * p.nt_pad + h];
+                dz += (double)qlo[2 * Q + r] - (double)gt[6ll * p.nt_pad + h];
             }
             const double D = fma(dz, dz, fma(dy, dy, dx * dx));
             const float nq2 = __fmaf_rn(qhz, qhz, __fmaf_rn(qhy, qhy, qhx * qhx));
@@ -778,12 +808,12 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             thr_l[r] = filter_threshold(a, nq2, sqrtf(nq2));
             Dbest_l[r] = D;
             ibest_l[r] = h;
-            dq_l[r] = __fsqrt_ru(__double2float_ru(D)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
+            dq_l[r * 32] = __fsqrt_ru(__double2float_ru(D)) * 1.00002f + 1e-6f * sqrtf(nq2) + 1e-37f;
         }
         all_hinted = __all_sync(0xffffffffu, ok);
         float m = 0.f;
 #pragma unroll 1
-        for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r]);
+        for (int r = 0; r < Q; ++r) m = fmaxf(m, dq_l[r * 32]);
         dmax = m;
     }
 
@@ -891,7 +921,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     auto refresh_bounds = [&]() {
 #pragma unroll 1
         for (int r = r_lo; r < r_hi; ++r) {
-            float m = dq_l[r];
+            float m = dq_l[r * 32];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (lane == 0) ws.rowB[r] = m;
@@ -957,7 +987,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     auto exact_any = [&](const float4 S, unsigned rows) {
         float dq[Q];  // (unrolled with the bounds loaded together, like exact_rows_box below)
 #pragma unroll
-        for (int r = 0; r < Q; ++r) dq[r] = dq_l[r];
+        for (int r = 0; r < Q; ++r) dq[r] = dq_l[r * 32];
         bool need = false;
 #pragma unroll
         for (int r = 0; r < Q; ++r) {
@@ -984,7 +1014,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         // all samples on that one load; here the eight loads go out together)
         float dq[Q];
 #pragma unroll
-        for (int r = 0; r < Q; ++r) dq[r] = dq_l[r];
+        for (int r = 0; r < Q; ++r) dq[r] = dq_l[r * 32];
         unsigned need = 0;
 #pragma unroll
         for (int r = 0; r < Q; ++r) {
@@ -1186,7 +1216,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                                                      sx + 2 * (SUB / 4) + h * (FLAG / 4),
                                                      sx + 3 * (SUB / 4) + h * (FLAG / 4), id * SUB + h * FLAG,
                                                      mt_l, thr_l, tm_l, Dbest_l, ibest_l, dq_l, dmax, nflag,
-                                                     npass, &ws.qs[0][0], rows_e);
+                                                     npass, &ws.qs[0][0], qlo, rows_e);
                 ++nconsumed;
                 __syncwarp();  // every lane is done with the slot before lane 0 refills it
             }
@@ -1337,7 +1367,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         // neighbour's original float32 coordinates (one 16-byte gather; neighbours of consecutive
         // stored queries are stored close together): the strict d2 < max_d2 test, fitness, rmse
         // and the Kabsch sums carry no FP32 error, only the choice of neighbour was made in FP32.
-        using WS = PrunedWarpSmem<SUB, Q>;
+        using WS = PrunedWarpSmem<SUB, Q, SPLIT>;
         static_assert(offsetof(WS, sph) == sizeof(WS::buf) &&
                           sizeof(WS::buf) + sizeof(WS::sph) >= 32 * kNS * sizeof(double),
                       "the row reduction borrows the (idle) ring buffer and FIFO");
@@ -1613,7 +1643,7 @@ struct NN2PrunedVariant {
     static constexpr bool kPrune = true;
     static constexpr bool kFused = FUSED;
     static constexpr bool kSplit = SPLIT;
-    static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q>);
+    static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q, SPLIT>);
 
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &fuse) {
         auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS, GROUPS, FUSED, SPLIT>;
@@ -1628,15 +1658,12 @@ struct NN2PrunedVariant {
             configured_dev = dev;
         }
         ProfScope prof(kProfNN, st);
-        // the lo planes of the query copy (last 3 KB of the per-warp block) are only touched
-        // when the search uses the lo parts
-        const size_t smem = WARPS == 1 && !p.use_lo ? kSmem - 3 * 32 * Q * sizeof(float) : kSmem;
-        kern<<<grid, WARPS * 32, smem, st>>>(p, fuse);
+        kern<<<grid, WARPS * 32, kSmem, st>>>(p, fuse);
         return launched(FUSED ? "nn2_pruned_kernel<fused icp>" : "nn2_pruned_kernel");
     }
-    // resident CTAs per SM: MINB by registers; by shared memory fewer when the lo planes are kept
-    static int ctas_per_sm(bool use_lo) {
-        const size_t smem = (WARPS == 1 && !use_lo ? kSmem - 3 * 32 * Q * sizeof(float) : kSmem) + 1024;
+    // resident CTAs per SM: MINB by registers, and what shared memory allows
+    static int ctas_per_sm(bool) {
+        const size_t smem = kSmem + 1024;
         const int by_smem = (int)((size_t)233472 / smem);
         return by_smem < MINB ? by_smem : MINB;
     }
