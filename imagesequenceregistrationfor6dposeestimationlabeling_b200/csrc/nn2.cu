@@ -1502,9 +1502,9 @@ __global__ void __launch_bounds__(1024)
 block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, int split_max, int parts,
                    float split_factor, int *__restrict__ order, int *__restrict__ order_count,
                    const float *__restrict__ rowrad, float tp_factor, int tp_slots, int *__restrict__ order_slot,
-                   unsigned *__restrict__ tp_tick) {
+                   unsigned *__restrict__ tp_tick, int mix_slots) {
     __shared__ u64 s[kOrderMax];
-    __shared__ int nsplit, nsplit_entries;
+    __shared__ int nsplit, nsplit_entries, nmixed;
     __shared__ short rowpos[kSplitMax * 8];   // first launch-list entry of row r of split block i
     __shared__ signed char rowslot[kSplitMax * 8];  // its merge slot when it runs as target parts, else -1
     static_assert(kSplitMax == 128, "order_workspace_bytes sizes the launch list for 128 split blocks");
@@ -1544,10 +1544,18 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
             }
         }
         nsplit_entries = pos;
-        order_count[b] = parts * (nqb - h) + pos;
+        // A launch that leaves resident slots empty (mix_slots > 0: a one-wave grid) runs the widest
+        // of the remaining blocks as twice as many CTAs, as far as the slots go
+        int nm = 0;
+        if (mix_slots > 0 && parts < rows) {
+            nm = (mix_slots - pos - parts * (nqb - h)) / parts;
+            nm = nm < 0 ? 0 : (nm > nqb - h ? nqb - h : nm);
+        }
+        nmixed = nm;
+        order_count[b] = parts * (nqb - h) + parts * nm + pos;
     }
     __syncthreads();
-    const int h = nsplit, hbase = nsplit_entries;
+    const int h = nsplit, hbase = nsplit_entries, nm = nmixed;
     int *out = order + (long long)b * stride;
     for (int i = threadIdx.x; i < nqb; i += 1024) {
         const int blk = (int)(unsigned)(s[i] & 0xffffffffull);
@@ -1568,7 +1576,13 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
             // a grid that does not fill the machine: every block runs as `parts` CTAs of 8 / parts
             // query rows (the scan skips the rows a CTA does not own, so the split costs little
             // and shortens the tail)
-            for (int c = 0; c < parts; ++c) out[hbase + parts * (i - h) + c] = blk | (code_of_part(parts, c) << 24);
+            if (i - h < nm) {
+                for (int c = 0; c < 2 * parts; ++c)
+                    out[hbase + 2 * parts * (i - h) + c] = blk | (code_of_part(2 * parts, c) << 24);
+            } else {
+                for (int c = 0; c < parts; ++c)
+                    out[hbase + parts * nm + parts * (i - h) + c] = blk | (code_of_part(parts, c) << 24);
+            }
         }
     }
 }
@@ -1851,7 +1865,12 @@ static int nn2_dispatch(const NN2Call &c) {
         const float tp_factor = (float)env_int("ISR_NN_TP_FACTOR_X10", 40) * 0.1f;
         const int tp_slots = V::kFused && V::kSplit && c.batch == 1 && split_max > 0
                                  ? (tp_slots_env < kTargetSlots ? tp_slots_env : kTargetSlots) : 0;
-        const int stride = parts * nqb + (kRows - parts) * split_max + (kTargetParts - 1) * tp_slots;
+        // (mixing: only the fused single-start iteration, whose launch list is built once per run)
+        const int mix_env = env_int("ISR_NN_MIX", 1);
+        const int base_ctas = parts * nqb + (kRows - parts) * split_max + (kTargetParts - 1) * tp_slots;
+        const int mix_slots = V::kFused && V::kSplit && c.batch == 1 && mix_env != 0 && parts < kRows &&
+                                      (long long)parts * nqb <= slots ? slots : 0;
+        const int stride = mix_slots > base_ctas ? mix_slots : base_ctas;
         char *w = reinterpret_cast<char *>(c.workspace);
         const size_t list = align256((size_t)(8 * nqb + kTargetParts * kTargetSlots) * c.batch * 4);
         u64 *keys = reinterpret_cast<u64 *>(w);
@@ -1875,7 +1894,7 @@ static int nn2_dispatch(const NN2Call &c) {
             ISR_TRY(launched("block_weight_kernel"));
             block_order_kernel<<<(unsigned)c.batch, 1024, 0, c.st>>>(
                 keys, nqb, kRows, stride, split_max, parts, split_factor, order, count,
-                tp_slots > 0 ? rowrad : nullptr, tp_factor, tp_slots, order_slot, p.tp_tick);
+                tp_slots > 0 ? rowrad : nullptr, tp_factor, tp_slots, order_slot, p.tp_tick, mix_slots);
             ISR_TRY(launched("block_order_kernel"));
         }
         p.order = order;
