@@ -1,0 +1,29 @@
+"""Developer probe: where the wall clock of api.icp goes at 1M x 1M (host arrays in, result out)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from imagesequenceregistrationfor6dposeestimationlabeling_b200 import api, synth
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+iters = 50
+torch.cuda.set_device(0)
+src, tgt, _ = synth.icp_pair(n, n, 4, 5)
+api.icp(src[:5000], tgt[:5000], np.eye(4), 20.0, max_iteration=2)
+torch.cuda.synchronize()
+def T(label, t0):
+    torch.cuda.synchronize(); t1 = time.perf_counter(); print(f"  {label}: {1e3 * (t1 - t0):.2f} ms"); return t1
+for rep in range(2):
+    print("pass", rep)
+    t0 = time.perf_counter()
+    prob = api.IcpProblem(src, tgt, np.eye(4)[None]); t1 = T("IcpProblem (H2D, sort, prepare)", t0)
+    prob.run(20.0, iters - 1, 0.0, 0.0); t1 = T("run", t1)
+    r = prob.results(); t1 = T("results (with correspondences)", t1)
+    print(f"  total {1e3 * (t1 - t0):.2f} ms")
+    # inside the constructor
+    t0 = time.perf_counter()
+    s, slo = api._points_hilo(src, prob.device); t = api._points(tgt, prob.device); t1 = T("H2D", t0)
+    c = api.centroid_of(t, prob.device); t1 = T("centroid", t1)
+    po = api.spatial_order(t, prob.device); t1 = T("spatial_order tgt", t1)
+    soa = api.prepare_cloud(t, centroid=c, perm=po, stage_centroids=True, device=prob.device); t1 = T("prepare tgt", t1)
+    ps = api.spatial_order(s, prob.device); t1 = T("spatial_order src", t1)
+    rr = prob.results(False); t1 = T("results (no correspondences)", t1)
