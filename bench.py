@@ -483,13 +483,19 @@ def main():
                 ("sharded ICP differs from the single-GPU result", parity, rp.fitness, refh[16], rp.inlier_rmse, refh[17])
         # end to end through the public API from host arrays (H2D, curve sort, preparation, loop,
         # result read back): what a caller of api.icp / dist.icp_sharded sees
+        def icp_e2e():
+            if world > 1:
+                return dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=iters - 1, relative_fitness=0.0,
+                                        relative_rmse=0.0)[0]
+            return api.icp(src, tgt, np.eye(4), 20.0, max_iteration=iters - 1, relative_fitness=0.0, relative_rmse=0.0)
+
+        # (one untimed call first: the timed one then finds its buffers in torch's caching allocator,
+        # as the second and every later registration of a pipeline does; a cold call pays ~30 ms of cudaMalloc)
+        icp_e2e()
+        torch.cuda.synchronize()
         barrier()
         t0 = time.perf_counter()
-        if world > 1:
-            r_e2e = dist.icp_sharded(src, tgt, np.eye(4), 20.0, max_iteration=iters - 1, relative_fitness=0.0,
-                                     relative_rmse=0.0)[0]
-        else:
-            r_e2e = api.icp(src, tgt, np.eye(4), 20.0, max_iteration=iters - 1, relative_fitness=0.0, relative_rmse=0.0)
+        r_e2e = icp_e2e()
         torch.cuda.synchronize()
         t_icp_e2e = max_over_ranks(time.perf_counter() - t0)
         del pprob
@@ -555,7 +561,8 @@ def main():
                              "peer memory over NVLink (isr_icp_run_sharded), no NCCL call" if peer is not None else
                              f"source sharded x{world}, peer memory unavailable: NCCL all-reduce per iteration"),
             "icp_e2e_config": "api.icp / dist.icp_sharded from host arrays: H2D, curve sort, preparation, loop, result "
-                              "read back (wall clock)",
+                              "read back (wall clock of the second of two identical calls: buffers come from "
+                              "torch's caching allocator)",
             "icp_ms_per_iter": 1e3 * t_icp / iters,
             "icp_kernel_ms_per_iter": float(ms_icp[1]) / max(int(n_icp[1]), 1),
             "icp_sharded_max_abs_pose_diff_vs_single_gpu": parity,

@@ -1700,7 +1700,13 @@ struct NN2PrunedVariant {
 // whose starts are mostly far from aligned, took 0.40 s with quarters against 0.27 s with
 // halves, so a batched ICP search uses the halves; choosing per half at run time -- 4-row scan
 // when both quarters are needed -- kept config 5 at 0.30 s but gave the 4 % on verification back)
-using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4>;
+// (round 2 re-measured PARTS on the verification workload, same box: 1 -> 10 650, 2 -> 10 500, 4 -> 10 470
+// candidates/s although PARTS = 4 removes 18 % of all instructions: pass 1 is 16 independent
+// groups that issue back to back; what a warp waits for are its dependent chains elsewhere)
+#ifndef ISR_NN_VERIFY_PARTS
+#define ISR_NN_VERIFY_PARTS 1
+#endif
+using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, ISR_NN_VERIFY_PARTS, 4>;
 using NN2PrunedHalves = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2>;
 using NN2PrunedFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4, true>;
 using NN2PrunedHalvesFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2, true>;

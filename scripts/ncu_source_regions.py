@@ -56,6 +56,14 @@ marks = sorted(m for m in marks if m[0])
 reg = {}
 for (f, ln), (s, i, t) in agg.items():
     name = f if f != base else marks[bisect.bisect_right([m[0] for m in marks], ln) - 1][1]
+    # the inline-PTX helpers of isr_common.cuh are inlined into nn2.cu's phases: the packed FFMA2 /
+    # FMNMX3 (and their pack / unpack moves) are the filter scan itself (the resolve's pass 1 uses
+    # scalar __fmaf_rn), the mbarrier / bulk-copy helpers belong to the consume phase
+    if f == "isr_common.cuh":
+        if any(k in t for k in ("fma.rn.f32x2", "min.f32", "mov.b64")):
+            name = "scan (filter FFMA2 loop)"
+        elif any(k in t for k in ("mbarrier", "cp.async.bulk", "smem_u32", "try_wait")):
+            name = "consume: tests, bulk copies, wait"
     a = reg.setdefault(name, [0, 0])
     a[0] += s
     a[1] += i
