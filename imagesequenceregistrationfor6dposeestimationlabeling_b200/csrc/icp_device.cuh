@@ -64,11 +64,18 @@ __device__ inline void svd3(const double M[3][3], double U[3][3], double D[3], d
                 beta += A[k][q] * A[k][q];
                 gamma += A[k][p] * A[k][q];
             }
-            if (gamma == 0.0 || fabs(gamma) <= 2.3e-16 * sqrt(alpha * beta)) continue;
+            // (this runs on ONE thread at the very end of every ICP iteration, with every other warp of
+            // the machine waiting for it: software FP64 divisions and square roots are its cost.  One
+            // square root, one division and one reciprocal square root per rotation instead of three
+            // and three: the convergence test on squares, and
+            //   t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)),  zeta = (beta - alpha) / (2 gamma)
+            //     = sign(beta - alpha) 2 gamma / (|beta - alpha| + sqrt((beta - alpha)^2 + 4 gamma^2)))
+            if (gamma == 0.0 || gamma * gamma <= (2.3e-16 * 2.3e-16) * (alpha * beta)) continue;
             rotated = true;
-            const double zeta = (beta - alpha) / (2.0 * gamma);
-            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+            const double delta = beta - alpha, g2 = 2.0 * gamma;
+            double t = g2 / (fabs(delta) + sqrt(fma(delta, delta, g2 * g2)));
+            t = delta < 0.0 ? -t : t;
+            const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
             for (int k = 0; k < 3; ++k) {
                 const double ap = A[k][p], aq = A[k][q];
                 A[k][p] = c * ap - sn * aq;
@@ -96,7 +103,8 @@ __device__ inline void svd3(const double M[3][3], double U[3][3], double D[3], d
     int rank = 0;
     for (int j = 0; j < 3; ++j) {
         if (D[j] > tiny && D[j] > 0.0) {
-            for (int k = 0; k < 3; ++k) U[k][j] = A[k][j] / D[j];
+            const double inv = 1.0 / D[j];
+            for (int k = 0; k < 3; ++k) U[k][j] = A[k][j] * inv;
             ++rank;
         }
     }
@@ -303,6 +311,7 @@ static __device__ __noinline__ void icp_fused_tail(const IcpFuse &f, int b, int 
         if (__shfl_sync(full, last, 0) == 0) return;
         __threadfence();
         gs = 0.0;
+#pragma unroll 16
         for (int x = 0; x < g_count; ++x) gs = __dadd_rn(gs, ldcg_f64(bsum + (size_t)(g_first + x) * kNS + k));
         if (lane == 0) tick[f.nqb + g] = 0;
     }
@@ -318,6 +327,7 @@ static __device__ __noinline__ void icp_fused_tail(const IcpFuse &f, int b, int 
         if (__shfl_sync(full, last, 0) == 0) return;
         __threadfence();
         S = 0.0;
+#pragma unroll 8
         for (int x = 0; x < f.ngroups; ++x) S = __dadd_rn(S, ldcg_f64(gsum + (size_t)x * kNS + k));
         if (lane == 0) tick[f.nqb + f.ngroups] = 0;
     }

@@ -158,6 +158,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// programmatic dependent launch: a grid launched with the stream-serialization attribute may start
+// while its predecessor in the stream still runs; pdl_wait() returns once that grid has completed
+// and its writes are visible (at once for a normally launched grid), pdl_launch_dependents() lets
+// the successor's CTAs take the slots this grid frees
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -109,6 +109,16 @@ struct NN2Params {
     long long cta_log_cap;        //   records that fit
 };
 
+#ifdef ISR_PHASE_LOG
+// developer build (scripts/probe_phases.py): the CTA log carries phase stamps instead of event counts,
+// and its LAST record the launch's wall-clock marks (ns): first CTA start, last search end, last
+// epilogue end, kernel end (after the reduction tail, the exchange and the solve)
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
 constexpr int kTargetParts = 4;   // CTAs that share the target of one heavy query row (a power of two <= 4)
 constexpr int kTargetSlots = 96;  // rows per launch that can run that way
 constexpr unsigned kNoBox = 0x3FFFFFFFu;  // three 10-bit fractions of the radius, all ones
@@ -597,6 +607,12 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
 constexpr int kRing = ISR_NN_RING;  // sub-tile buffers in flight per warp
 constexpr int kFifo = ISR_NN_FIFO;  // candidate sub-tiles queued per warp (the nearest-first sort handles up to 64)
 constexpr int kAnchors = 8; // seeds per warp: one per query row
+#ifndef ISR_SEED_OWN
+#define ISR_SEED_OWN 0
+#endif
+#ifndef ISR_LO_PREFETCH
+#define ISR_LO_PREFETCH 0
+#endif
 constexpr float kCutGap = 3.0f;   // SPLIT: a row is cut at gaps wider than its radius / kCutGap ...
 constexpr float kCutGain = 0.75f; //        ... when every piece is then at most this fraction of its radius wide
 
@@ -613,6 +629,8 @@ struct alignas(128) PrunedWarpSmem {
     uint64_t full[kRing];
     uint64_t qbar;             // mbarrier of the prologue's bulk copies of the warp's queries
     int seed[kAnchors];        // sub-tiles scanned first (-1: none)
+    unsigned seedrows[kAnchors];  // query rows that a seed's first scan covers (the walk queues it for the others)
+    int seedpos[kAnchors];     // its FIFO entry
     alignas(16) float qs[3][32 * Q];  // the warp's queries, hi xyz (read by the scan, the tests and the resolve path)
     // dq[r][lane] >= the exact best distance so far of query r * 32 + lane (0: no such query).  Read by
     // every exact test; in local memory (with the rest of the resolve state) five of six of those
@@ -646,7 +664,9 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     constexpr int SUBS = ISR_SOA_TILE / SUB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.z;
-    if (p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) return;
+    // (FUSED: the skip flag is the start's `done`, written by the previous iteration's launch, which
+    // may still be running -- it is read after pdl_wait() below)
+    if (!FUSED && p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) return;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     // heaviest query blocks first (order from block_order_kernel): the grid is only a few
@@ -672,6 +692,11 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     // of the coarse tests walk this range only
     const int r_lo = liverows != 0 ? __ffs(liverows) - 1 : 0, r_hi = 32 - __clz(liverows);
     if (liverows == 0) {
+        if (FUSED) {
+            pdl_wait();
+            pdl_launch_dependents();
+            if (p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) return;
+        }
         if (FUSED && tpart <= 1) {  // nothing to search, but the reduction counts on every row of the launch list
             double rs0[Q];
 #pragma unroll 1
@@ -681,6 +706,10 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         return;
     }
     const long long t_start = clock64();
+#ifdef ISR_PHASE_LOG
+    long long ph_q = 0, ph_h = 0, ph_r = 0, ph_s = 0;
+    if (p.cta_log != nullptr && lane == 0) atomicMin(p.cta_log + 4 * (p.cta_log_cap - 1) + 0, global_ns());
+#endif
     PrunedWarpSmem<SUB, Q, SPLIT> &ws = reinterpret_cast<PrunedWarpSmem<SUB, Q, SPLIT> *>(smem_raw)[warp];
     const float *__restrict__ gq = p.q + (long long)b * p.q_bstride;
     const float *__restrict__ gt = p.t + (long long)b * p.t_bstride;
@@ -738,9 +767,20 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         dq_l[r * 32] = live ? CUDART_INF_F : 0.f;
         qlo[r] = 0.f; qlo[Q + r] = 0.f; qlo[2 * Q + r] = 0.f;
     }
-    // (FUSED: the start's pose is fetched while the query copy is in flight)
+    // FUSED: everything up to here -- the launch-list entry, the barriers, the copy of the ORIGINAL source
+    // points -- is the same in every iteration of a run; what follows reads what the previous
+    // iteration's launch wrote (done flag, pose, hints, tickets).  With programmatic dependent launch
+    // (isr_icp_run*: every launch after the first) this CTA may have started while that launch was
+    // still in its tail / exchange / solve: wait for it here, then let the next one queue up behind.
+    // (the start's pose is fetched while the query copy is in flight)
     double Tf[12], cf[3];
     if (FUSED) {
+        pdl_wait();
+        pdl_launch_dependents();
+        if (p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) {  // warp-uniform
+            mbar_wait(&ws.qbar, 0);  // no bulk copy may be in flight into a CTA that exits
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < 12; ++k) Tf[k] = f.states[b].T[k];
 #pragma unroll
@@ -777,6 +817,9 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         }
     }
     __syncwarp();  // every lane has its lo parts before the ring buffer is handed to the bulk copies
+#ifdef ISR_PHASE_LOG
+    ph_q = clock64() - t_start;
+#endif
 
     // ---- starting bounds from the caller's hints (the previous search's neighbours) ----------
     // A hinted query starts as if its hint had already been scanned and resolved: running
@@ -817,6 +860,9 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         dmax = m;
     }
 
+#ifdef ISR_PHASE_LOG
+    ph_h = clock64() - t_start;
+#endif
     // SPLIT: cut rows at curve jumps (below).  A separate instantiation, launched only when the grid
     // is at most one wave of whole blocks deep: there the slowest warp IS the iteration; in deeper
     // grids the extra code and coarse-test work cost more than the shorter tail gains (1M x 1M
@@ -1033,16 +1079,32 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         return need;
     };
 
+#ifdef ISR_PHASE_LOG
+    ph_r = clock64() - t_start;
+#endif
     // ---- seeds: for every query row, the sub-tile whose centre is nearest to the row's --------
     int head = 0, look = 0, tail = 0, nloads = 0, nconsumed = 0;  // FIFO / ring state, warp-uniform
-    if (lane < kAnchors) ws.seed[lane] = -1;
+    if (lane < kAnchors) { ws.seed[lane] = -1; ws.seedrows[lane] = 0u; }
     __syncwarp();
     if (!all_hinted) {  // (a fully hinted warp already holds near-final bounds)
         // anchors: the centres of the query rows (a dead row falls back to the first live one);
         // a run-time loop over the anchors, like everything per row
 #pragma unroll 1
         for (int a = 0; a < kAnchors && a < p.nanchors; ++a) {
+#if ISR_SEED_OWN
+            // a seed is first scanned for the rows of its own row group only: scanned for every row,
+            // seed k improved (and resolved, one FP64 pass each) every row that lies nearer to it than
+            // to seeds 0 .. k-1 -- up to 8 + 7 + .. + 1 passes along the curve, each overwritten by the
+            // row's own seed later.  The regular walk queues the seed's tile for the other rows
+            // like any other tile, against the bounds they hold by then.
+            constexpr int HS = Q / GROUPS;
+            const unsigned qrows = (((1u << HS) - 1u) << (HS * (a / HS))) & liverows;
+            if (!((liverows >> a) & 1u)) continue;  // warp-uniform: a row of another CTA, or beyond the cloud
+            const float4 R = ws.row[a];
+#else
+            const unsigned qrows = (1u << Q) - 1u;
             const float4 R = ws.row[a].w >= 0.f ? ws.row[a] : ws.row[__ffs(liverows) - 1];
+#endif
             u64 bk = ~0ull;
             for (int base = 0; base < stages; base += 32) {
                 const int s = base + lane;
@@ -1080,18 +1142,23 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             int sb = (int)(unsigned)(key & 31ull);
             if (key == ~0ull) sb = 0;
             const int sd = st * SUBS + sb;
-            bool dup = false;
-            for (int c = 0; c < a; ++c) dup = dup || ws.seed[c] == sd;
-            if (!dup) {
+            int dup = -1;
+            for (int c = 0; c < a; ++c) dup = ws.seed[c] == sd ? c : dup;
+            if (dup < 0) {
                 if (lane == 0) {
                     // +inf radius: never ruled out
                     ws.sph[tail % kFifo] = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
                     ws.id[tail % kFifo] = sd;
-                    ws.rows[tail % kFifo] = (1u << Q) - 1u;
+                    ws.rows[tail % kFifo] = qrows;
                     ws.box[tail % kFifo] = kNoBox;
                     ws.seed[a] = sd;
+                    ws.seedrows[a] = qrows;
+                    ws.seedpos[a] = tail % kFifo;
                 }
                 ++tail;
+            } else if (lane == 0) {  // the same tile serves another row group as well
+                ws.seedrows[dup] |= qrows;
+                ws.rows[ws.seedpos[dup]] |= qrows;
             }
             __syncwarp();
         }
@@ -1187,6 +1254,15 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                             bulk_g2s(&ws.buf[slot][pl][0], gt + (long long)pl * p.nt_pad + src, SUB * 4u,
                                      &ws.full[slot]);
                     }
+#if ISR_LO_PREFETCH
+                    // the lo planes of the sub-tile (read by the resolve's FP64 pass, one dependent trip per
+                    // window target) are asked into L2 now: six 128-byte lines, one per lane
+                    else if (lane <= 6 && p.use_lo) {
+                        const float *a = gt + (long long)(4 + (lane - 1) / 2) * p.nt_pad + (long long)ws.id[e] * SUB +
+                                         ((lane - 1) & 1) * 32;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                    }
+#endif
                     ++nloads;
                 } else {
                     if (lane == 0) ws.id[e] = -1;
@@ -1287,7 +1363,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                 if (sub_h != nullptr) hb = sub_h[gid];
                 rows = coarse_rows_box(S, hb);
 #pragma unroll
-                for (int a = 0; a < kAnchors; ++a) rows = gid == ws.seed[a] ? 0u : rows;  // already scanned
+                for (int a = 0; a < kAnchors; ++a) rows = gid == ws.seed[a] ? rows & ~ws.seedrows[a] : rows;  // already scanned
             }
             const unsigned m32 = __ballot_sync(0xffffffffu, rows != 0);
             if (rows != 0) {
@@ -1302,9 +1378,17 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         }
     }
 
+#ifdef ISR_PHASE_LOG
+    ph_s = clock64() - t_start;
+    if (p.cta_log != nullptr && lane == 0) atomicMax(p.cta_log + 4 * (p.cta_log_cap - 1) + 1, global_ns());
+    if (false) {
+        const long long rec = 0;
+        {
+#else
     if (p.cta_log != nullptr && lane == 0) {
         const long long rec = ((long long)b * gridDim.x + blockIdx.x);
         if (rec < p.cta_log_cap) {
+#endif
             unsigned long long *o = p.cta_log + 4 * rec;
             o[0] = (unsigned long long)(clock64() - t_start);
             o[1] = ((unsigned long long)nscanned << 32) | ntests;
@@ -1407,7 +1491,25 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             rs[r] = icp_row_sum(scratch, lane);  // lane k: component k over the row's 32 queries
             __syncwarp();
         }
+#ifdef ISR_PHASE_LOG
+        const long long ph_e = clock64() - t_start;
+        if (p.cta_log != nullptr && lane == 0) atomicMax(p.cta_log + 4 * (p.cta_log_cap - 1) + 2, global_ns());
+#endif
         icp_fused_tail(f, b, blk, own, lane, rs);
+#ifdef ISR_PHASE_LOG
+        if (p.cta_log != nullptr && lane == 0) {
+            atomicMax(p.cta_log + 4 * (p.cta_log_cap - 1) + 3, global_ns());
+            const long long rec = ((long long)b * gridDim.x + blockIdx.x);
+            if (rec < p.cta_log_cap - 1) {
+                unsigned long long *o = p.cta_log + 4 * rec;
+                o[0] = (unsigned long long)ph_s;
+                o[1] = (unsigned long long)ph_q | ((unsigned long long)ph_h << 32);
+                o[2] = (unsigned long long)ph_r | ((unsigned long long)ph_e << 32);
+                o[3] = ((unsigned long long)(unsigned)blk << 32) | ((unsigned long long)(rowsel | (tpart << 4)) << 24) |
+                       (unsigned long long)((clock64() - t_start) >> 8 & 0xFFFFFF);
+            }
+        }
+#endif
     } else {
 #pragma unroll 1
         for (int r = 0; r < Q; ++r) {
@@ -1619,7 +1721,7 @@ struct NN2Variant {
 
     static constexpr bool kFused = false;
     static constexpr bool kSplit = false;
-    static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &) {
+    static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &, bool) {
         auto kern = nn2_kernel<Q, THREADS, STAGE, NSTAGES, SUB, MINB, UNR>;
         static thread_local int configured_dev = -1;
         int dev = 0;
@@ -1659,7 +1761,7 @@ struct NN2PrunedVariant {
     static constexpr bool kSplit = SPLIT;
     static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q, SPLIT>);
 
-    static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &fuse) {
+    static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &fuse, bool pdl) {
         auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS, GROUPS, FUSED, SPLIT>;
         static thread_local int configured_dev = -1;
         int dev = 0;
@@ -1672,7 +1774,22 @@ struct NN2PrunedVariant {
             configured_dev = dev;
         }
         ProfScope prof(kProfNN, st);
-        kern<<<grid, WARPS * 32, kSmem, st>>>(p, fuse);
+        if (FUSED && pdl) {
+            // the previous operation of the stream is the previous iteration's launch of this kernel
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = grid;
+            cfg.blockDim = dim3(WARPS * 32);
+            cfg.dynamicSmemBytes = kSmem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            ISR_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, p, fuse), "nn2 fused launch (dependent)"));
+        } else {
+            kern<<<grid, WARPS * 32, kSmem, st>>>(p, fuse);
+        }
         return launched(FUSED ? "nn2_pruned_kernel<fused icp>" : "nn2_pruned_kernel");
     }
     // resident CTAs per SM: MINB by registers, and what shared memory allows
@@ -1941,7 +2058,11 @@ static int nn2_dispatch(const NN2Call &c) {
         ISR_REQUIRE(fuse.nqb == nqb && fuse.ngroups == (nqb + kFuseGroup - 1) / kFuseGroup, ISR_E_SHAPE,
                     "nn: fused search: reduction layout for %d blocks, launch has %d", fuse.nqb, nqb);
     }
-    if (splits == 1) return V::launch(p, grid, c.st, fuse);
+    // programmatic dependent launch of iteration k + 1 behind iteration k (same kernel, nothing else
+    // enqueued in between; profiling brackets every launch with events, which would break the pair)
+    static const int pdl_env = env_int("ISR_ICP_PDL", 1);
+    const bool pdl = V::kFused && c.reuse_order != 0 && pdl_env != 0 && !prof_enabled();
+    if (splits == 1) return V::launch(p, grid, c.st, fuse, pdl);
 
     const long long total = (long long)nq * c.batch;
     const size_t need = align256((size_t)total * splits * 8) + (size_t)total * splits * 4;
@@ -1951,7 +2072,7 @@ static int nn2_dispatch(const NN2Call &c) {
     p.part_idx = reinterpret_cast<int *>(reinterpret_cast<char *>(c.workspace) +
                                          align256((size_t)total * splits * 8));
     p.part_stride = total;
-    ISR_TRY(V::launch(p, grid, c.st, fuse));
+    ISR_TRY(V::launch(p, grid, c.st, fuse, false));
     nn2_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.st>>>(
         p.part_D, p.part_idx, total, splits, c.out_d2, c.out_idx, c.skip, c.skip_stride,
         (long long)nq);

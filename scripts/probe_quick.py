@@ -43,6 +43,20 @@ if "verify" in which:
     cd, Mqd, Mtd = api._points(cloud, dev), api._poses(Mq, dev), api._poses(Mt, dev)
     t = timed(lambda: api.verify_poses(cd, Mqd, Mtd))
     print(f"verify: {B / t:.0f} candidates/s ({t / B * 1e6:.1f} us per candidate)", flush=True)
+    if "ctr" in which:  # per-warp event counts of the pruned search (isr_profile_nn_counters)
+        import ctypes
+        from imagesequenceregistrationfor6dposeestimationlabeling_b200 import _lib
+        lib = _lib.load()
+        lib.isr_profile_enable(1)
+        lib.isr_profile_nn_pairs(None, None)
+        api.verify_poses(cd, Mqd, Mtd)
+        c = (ctypes.c_uint64 * 8)()
+        _lib.check(lib.isr_profile_nn_counters(c))
+        lib.isr_profile_enable(0)
+        w = max(int(c[4]), 1)
+        print(f"  per warp: {c[0] / w / 4:.2f} unit equivalents scanned, {c[3] / w:.1f} exact tests, {c[2] / w:.1f} "
+              f"candidate stages, {c[5] / w:.1f} flagged tiles, {c[6] / w:.1f} resolve passes; slowest warp "
+              f"{(int(c[7]) >> 44) * 1024} cycles", flush=True)
 if "adds" in which:
     B = 512
     surface = synth.make_cloud(100000, 1)
