@@ -28,6 +28,8 @@
 #include <math_constants.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "icp_device.cuh"
 #include "isr_common.cuh"
 
@@ -341,8 +343,12 @@ static int run_fused(IsrIcpState *states, int64_t starts, const float *src, cons
     for (int k = 0; k <= max_iteration; ++k) {
         f.final_eval = k == max_iteration ? 1 : 0;
         f.px = peer_view(peer, true);  // world == 0 without a peer
+        // (iterations 2 and 4 re-cut the launch list from the costs that the hinted iterations before
+        // them measured: nn2.cu, block_rebalance_kernel; iteration 0 is the unhinted search)
+        static const int recut_rounds = getenv("ISR_ICP_RECUT_ROUNDS") ? atoi(getenv("ISR_ICP_RECUT_ROUNDS")) : 2;
+        const int reuse = k == 0 ? 0 : (k % 2 == 0 && k <= 2 * recut_rounds) ? 2 : 1;
         const int s = nn2_search(&src_cloud, tgt_cloud, starts, 1, nullptr, nullptr, done, kStateInts,
-                                 ws + L.nnws, L.total - L.nnws, stream, k > 0, &f);
+                                 ws + L.nnws, L.total - L.nnws, stream, reuse, &f);
         if (peer != nullptr && s == ISR_OK) peer->seq += 1;  // the launch exists: so does its message
         ISR_TRY(s);
     }

@@ -105,6 +105,8 @@ struct NN2Params {
     double *tp_D;            // [slots][kTargetParts][32]
     int *tp_I;               // [slots][kTargetParts][32]
     unsigned *tp_tick;       // [slots], zero between launches
+    unsigned *cost;          // [gridDim.x] out: SM cycles of this launch-list entry's search (fused ICP,
+                             //   single start: block_rebalance_kernel re-cuts the launch list from them), or NULL
     unsigned long long *cta_log;  // developer probe (isr_debug_cta_log): 4 words per CTA, or NULL
     long long cta_log_cap;        //   records that fit
 };
@@ -697,6 +699,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             pdl_launch_dependents();
             if (p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) return;
         }
+        if (FUSED && p.cost != nullptr && lane == 0 && b == 0) p.cost[blockIdx.x] = 0u;
         if (FUSED && tpart <= 1) {  // nothing to search, but the reduction counts on every row of the launch list
             double rs0[Q];
 #pragma unroll 1
@@ -705,7 +708,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         }
         return;
     }
-    const long long t_start = clock64();
+    long long t_start = clock64();
 #ifdef ISR_PHASE_LOG
     long long ph_q = 0, ph_h = 0, ph_r = 0, ph_s = 0;
     if (p.cta_log != nullptr && lane == 0) atomicMin(p.cta_log + 4 * (p.cta_log_cap - 1) + 0, global_ns());
@@ -777,6 +780,9 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     if (FUSED) {
         pdl_wait();
         pdl_launch_dependents();
+#ifndef ISR_PHASE_LOG
+        t_start = clock64();  // (measured cost and CTA log: without the wait for the previous launch)
+#endif
         if (p.skip != nullptr && p.skip[(long long)b * p.skip_stride] != 0) {  // warp-uniform
             mbar_wait(&ws.qbar, 0);  // no bulk copy may be in flight into a CTA that exits
             return;
@@ -1378,6 +1384,10 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         }
     }
 
+    if (FUSED && p.cost != nullptr && lane == 0 && b == 0) {
+        const long long cyc = clock64() - t_start;
+        p.cost[blockIdx.x] = (unsigned)(cyc < 0x7FFFFFFFll ? cyc : 0x7FFFFFFFll);
+    }
 #ifdef ISR_PHASE_LOG
     ph_s = clock64() - t_start;
     if (p.cta_log != nullptr && lane == 0) atomicMax(p.cta_log + 4 * (p.cta_log_cap - 1) + 1, global_ns());
@@ -1689,6 +1699,190 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
     }
 }
 
+// ---- the launch list re-cut from measured costs (fused ICP, single start, one-wave grids) -------
+// An ICP run repeats nearly the same search 30-50 times, and in a one-wave grid an iteration lasts
+// as long as its slowest CTA (measured on a 1/8 shard of 1M points: median 121 k cycles, slowest
+// 228 k, with every slot of the machine taken).  Block radii predict the cost of a CTA only roughly;
+// the previous iteration MEASURED it (NN2Params::cost).  This kernel turns the measurements into a
+// variable cost per query row, v_r = (cycles - F) / rows of the CTA (F: the fixed cost of a CTA, the
+// cheapest one seen), and cuts every block again: a run of rows stays one CTA while its estimate
+// F + sum v_r stays under a level T, else it is halved (8 -> 4 -> 2 -> 1 rows, a single row -> target
+// parts); T is the lowest level (bisection) whose CTA count still fits the resident slots.  Light
+// blocks merge, heavy ones split, and the list is re-sorted heaviest-first.  The reduction tree of
+// the sums does not depend on how blocks are cut into CTAs (icp_fused_tail), so the iteration's
+// result is bit-identical before and after.
+#ifndef ISR_SPLIT_INFLATE
+#define ISR_SPLIT_INFLATE 1.15f
+#endif
+constexpr float kSplitInflate = ISR_SPLIT_INFLATE;  // a halved run costs more than half (repeated coarse walk and tests)
+__device__ __forceinline__ float rebalance_scale(int rows_new, int rows_old) {
+    float f = 1.f;
+    for (int a = rows_old; a > rows_new; a >>= 1) f *= kSplitInflate;
+    // (merged runs are taken at the sum of their parts: a row that straddles a jump of the curve is far
+    // cheaper on its own -- its CTA's coarse tests see one small sphere -- than inside a wider CTA)
+    return f;
+}
+// pieces of one block at level T; emit(code, tpart_count (1 or kTargetParts), estimate)
+// (merge: may rows that were measured in narrower CTAs be joined?  Only a one-wave list needs that, to
+// free slots for the cuts)
+template <class Emit>
+__device__ __forceinline__ void rebalance_block(const float *v, const unsigned char *g, float F, float T,
+                                                bool allow_tp, bool merge, Emit emit) {
+    auto est = [&](int r0, int n) {
+        float sum = 0.f;
+        for (int r = r0; r < r0 + n; ++r) {
+            sum += v[r] * rebalance_scale(n, g[r]);
+            if (!merge && g[r] < n) sum = CUDART_INF_F;
+        }
+        return F + sum;
+    };
+    const float e8 = est(0, 8);
+    if (e8 <= T) { emit(0, 1, e8); return; }
+    for (int h = 0; h < 2; ++h) {
+        const float e4 = est(4 * h, 4);
+        if (e4 <= T) { emit(9 + h, 1, e4); continue; }
+        for (int q = 2 * h; q < 2 * h + 2; ++q) {
+            const float e2 = est(2 * q, 2);
+            if (e2 <= T) { emit(11 + q, 1, e2); continue; }
+            for (int r = 2 * q; r < 2 * q + 2; ++r) {
+                const float e1 = est(r, 1);
+                if (e1 <= T || !allow_tp) { emit(1 + r, 1, e1); continue; }
+                emit(1 + r, kTargetParts, F + (e1 - F) * (1.1f / kTargetParts) + 0.15f * F);
+            }
+        }
+    }
+}
+// the eight row costs and measured CTA widths of one block, in three vector loads
+struct RebalanceRows {
+    float v[8];
+    unsigned char g[8];
+};
+__device__ __forceinline__ RebalanceRows rebalance_load(const float *vrow, const unsigned char *grow, int b) {
+    RebalanceRows o;
+    const float4 a = *reinterpret_cast<const float4 *>(vrow + b * 8), c = *reinterpret_cast<const float4 *>(vrow + b * 8 + 4);
+    const uint2 w = *reinterpret_cast<const uint2 *>(grow + b * 8);
+    o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = c.x; o.v[5] = c.y; o.v[6] = c.z; o.v[7] = c.w;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        o.g[r] = (unsigned char)((w.x >> (8 * r)) & 0xFFu);
+        o.g[4 + r] = (unsigned char)((w.y >> (8 * r)) & 0xFFu);
+    }
+    return o;
+}
+__global__ void __launch_bounds__(1024)
+block_rebalance_kernel(int *__restrict__ order, int *__restrict__ order_slot, int *__restrict__ order_count,
+                       const unsigned *__restrict__ cost, float *__restrict__ vrow, unsigned char *__restrict__ grow,
+                       int nqb, int slots, int max_entries, int tp_slots, unsigned *__restrict__ tp_tick,
+                       float deep_level) {
+    constexpr int kBins = 256;  // launch order: descending estimate, in this many levels
+    __shared__ unsigned fmin_s, n_s, tp_s, bin_n[kBins], bin_at[kBins];
+    __shared__ float top_s, sum_s;
+    const int tid = threadIdx.x;
+    const int n_old = order_count[0];
+    if (tid == 0) { fmin_s = 0x7FFFFFFFu; top_s = 0.f; sum_s = 0.f; }
+    __syncthreads();
+    // F: the cheapest CTA that searched at all
+    for (int e = tid; e < n_old; e += 1024) {
+        const unsigned c = cost[e];
+        if (c > 0u) atomicMin(&fmin_s, c);
+    }
+    for (int i = tid; i < nqb * 8; i += 1024) { vrow[i] = 0.f; grow[i] = 8; }
+    __syncthreads();
+    const float F = fmin_s == 0x7FFFFFFFu ? 1.f : (float)fmin_s;
+    // variable cost per query row (the parts of a target-part row add up)
+    float csum = 0.f;
+    for (int e = tid; e < n_old; e += 1024) {
+        const int entry = order[e];
+        const int blk = entry & 0xFFFFFF, code = (entry >> 24) & 15;
+        const unsigned rows = rows_of_code(code);
+        const int nrows = __popc(rows);
+        const float c = (float)cost[e];
+        const float share = fmaxf(c - F, 0.f) / (float)nrows;
+        for (int r = 0; r < 8; ++r)
+            if ((rows >> r) & 1u) {
+                atomicAdd(&vrow[blk * 8 + r], share);
+                grow[blk * 8 + r] = (unsigned char)nrows;
+            }
+        csum += c;
+    }
+    csum = (float)warp_sum((double)csum);
+    if ((tid & 31) == 0) atomicAdd(&sum_s, csum);
+    __syncthreads();
+    // the heaviest whole block: upper end of the bisection and of the launch-order levels
+    for (int b = tid; b < nqb; b += 1024) {
+        float sum = 0.f;
+        for (int r = 0; r < 8; ++r) sum += vrow[b * 8 + r];  // (deflated estimates are below this)
+        atomicMax(reinterpret_cast<int *>(&top_s), __float_as_int(F + sum));
+    }
+    __syncthreads();
+    const float top = top_s * 1.0001f + 1.f;
+    float level = top;
+    if (nqb <= slots) {
+        // one wave: the lowest level whose CTAs are all resident at once
+        float lo = F;
+        const int cap = min(slots, max_entries);
+        for (int it = 0; it < 12; ++it) {  // (to 2^-12 of the range: a few dozen cycles)
+            const float T = 0.5f * (lo + level);
+            if (tid == 0) { n_s = 0; tp_s = 0; }
+            __syncthreads();
+            unsigned n = 0, ntp = 0;
+            for (int b = tid; b < nqb; b += 1024) {
+                const RebalanceRows R = rebalance_load(vrow, grow, b);
+                rebalance_block(R.v, R.g, F, T, tp_slots > 0, true, [&](int, int parts, float) {
+                    n += (unsigned)parts;
+                    ntp += parts > 1 ? 1u : 0u;
+                });
+            }
+            atomicAdd(&n_s, n);
+            atomicAdd(&tp_s, ntp);
+            __syncthreads();
+            const bool ok = n_s <= (unsigned)cap && tp_s <= (unsigned)tp_slots;
+            __syncthreads();
+            if (ok) level = T; else lo = T;
+        }
+    } else {
+        // several waves, launched heaviest first: only a CTA that outlasts the average load of a slot
+        // can be the tail -- those are cut, everything else keeps its shape
+        level = fmaxf(deep_level * sum_s / (float)slots, 2.f * F);
+    }
+    // launch list at that level, heaviest first (counting sort over kBins levels of the estimate)
+    if (tid == 0) { n_s = 0; tp_s = 0; }
+    for (int i = tid; i < kBins; i += 1024) { bin_n[i] = 0; bin_at[i] = 0; }
+    __syncthreads();
+    const float bin_scale = (float)(kBins - 1) / fmaxf(top - F, 1.f);
+    auto bin_of = [&](float e) {
+        const int k = (int)(fminf(fmaxf(e - F, 0.f) * bin_scale, (float)(kBins - 1)));
+        return kBins - 1 - k;
+    };
+    for (int b = tid; b < nqb; b += 1024) {
+        const RebalanceRows R = rebalance_load(vrow, grow, b);
+        rebalance_block(R.v, R.g, F, level, tp_slots > 0, nqb <= slots,
+                        [&](int, int parts, float e) { atomicAdd(&bin_n[bin_of(e)], (unsigned)parts); });
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned at = 0;
+        for (int i = 0; i < kBins; ++i) { bin_at[i] = at; at += bin_n[i]; }
+        n_s = at;
+    }
+    __syncthreads();
+    const int n_new = (int)n_s;
+    if (n_new > max_entries) return;  // (cannot happen: the list has room for every row of every block)
+    for (int b = tid; b < nqb; b += 1024) {
+        const RebalanceRows R = rebalance_load(vrow, grow, b);
+        rebalance_block(R.v, R.g, F, level, tp_slots > 0, nqb <= slots, [&](int code, int parts, float e) {
+            const unsigned at = atomicAdd(&bin_at[bin_of(e)], (unsigned)parts);
+            const unsigned slot = parts > 1 ? atomicAdd(&tp_s, 1u) : 0u;
+            for (int k = 0; k < parts; ++k) {
+                order[at + k] = (int)((unsigned)b | ((unsigned)code << 24) | (parts > 1 ? (unsigned)(k + 1) << 28 : 0u));
+                order_slot[at + k] = (int)slot;
+            }
+        });
+    }
+    for (int i = tid; i < tp_slots; i += 1024) tp_tick[i] = 0u;
+    if (tid == 0) order_count[0] = n_new;
+}
+
 // partial results carry original indices; exact ties go to the lower one
 __global__ void nn2_combine_kernel(const double *__restrict__ part_D, const int *__restrict__ part_idx,
                                    long long total, int splits, float *__restrict__ out_d2,
@@ -1889,8 +2083,10 @@ static size_t order_workspace_bytes(long long nqb, long long batch) {
     // rows that run as target parts), entry counts; for target parts: merge slots of the entries,
     // row radii, merge buffers and tickets
     const size_t list = (size_t)(8 * nqb + kTargetParts * kTargetSlots) * batch * 4;
+    // (+ measured cost per launch-list entry and the rows-per-CTA of every row: block_rebalance_kernel)
     return align256((size_t)nqb * batch * 8) + 2 * align256(list) + align256((size_t)batch * 4) +
-           align256((size_t)nqb * batch * 8 * 4) + align256(kTargetPartBytes);
+           align256((size_t)nqb * batch * 8 * 4) + align256(kTargetPartBytes) + align256(list) +
+           align256((size_t)nqb * batch * 8);
 }
 
 // run-time tuning knob, read once: ISR_<name> in the environment, else the default
@@ -1959,6 +2155,7 @@ static int nn2_dispatch(const NN2Call &c) {
     p.order = nullptr;
     p.order_count = nullptr;
     p.order_slot = nullptr; p.tp_D = nullptr; p.tp_I = nullptr; p.tp_tick = nullptr;
+    p.cost = nullptr;
     int grid_x = nqb;
     if (V::kPrune && nqb > 1 && nqb <= kOrderMax && c.workspace != nullptr &&
         c.workspace_bytes >= order_workspace_bytes(nqb, c.batch)) {
@@ -2009,7 +2206,17 @@ static int nn2_dispatch(const NN2Call &c) {
         p.tp_D = reinterpret_cast<double *>(w);
         p.tp_I = reinterpret_cast<int *>(w + (size_t)kTargetSlots * kTargetParts * 32 * 8);
         p.tp_tick = reinterpret_cast<unsigned *>(w + (size_t)kTargetSlots * kTargetParts * 32 * 12);
+        w += align256(kTargetPartBytes);
+        unsigned *cost = reinterpret_cast<unsigned *>(w);
+        w += list;
+        unsigned char *grow = reinterpret_cast<unsigned char *>(w);
         p.order_slot = order_slot;
+        // measured-cost re-cut of the launch list (block_rebalance_kernel): the fused single-start
+        // iteration in a one-wave grid; the launch grid leaves room for every resident slot
+        const int rebalance_env = env_int("ISR_ICP_REBALANCE", 1);  // (read per call: the tests switch it)
+        const int max_entries = 8 * nqb + kTargetParts * kTargetSlots;
+        const bool can_rebalance = V::kFused && c.batch == 1 && rebalance_env != 0 && split_max > 0;
+        if (can_rebalance) p.cost = cost;
         const long long warps = (long long)nqb * c.batch;
         if (!c.reuse_order) {
             block_weight_kernel<V::kQueriesPerCta><<<(unsigned)((warps + 3) / 4), 128, 0, c.st>>>(
@@ -2023,6 +2230,19 @@ static int nn2_dispatch(const NN2Call &c) {
         p.order = order;
         p.order_count = count;
         grid_x = stride;
+        if (can_rebalance) {
+            // (entries beyond order_count return at once; a one-wave list grows to the resident slots at
+            // most, a deeper one by the CTAs that the cut adds -- a quarter more is never reached)
+            const int room = nqb <= slots ? (slots < max_entries ? slots : max_entries)
+                                          : (stride + stride / 4 < max_entries ? stride + stride / 4 : max_entries);
+            if (grid_x < room) grid_x = room;
+            if (c.reuse_order == 2) {
+                const float deep_level = (float)env_int("ISR_ICP_RECUT_LEVEL_X100", 100) * 0.01f;
+                block_rebalance_kernel<<<1, 1024, 0, c.st>>>(order, order_slot, count, cost, rowrad, grow, nqb, slots,
+                                                             room, V::kSplit ? tp_slots : 0, p.tp_tick, deep_level);
+                ISR_TRY(launched("block_rebalance_kernel"));
+            }
+        }
     }
     p.dbg = nullptr;
 #ifdef ISR_NN_TUNING
@@ -2061,7 +2281,7 @@ static int nn2_dispatch(const NN2Call &c) {
     // programmatic dependent launch of iteration k + 1 behind iteration k (same kernel, nothing else
     // enqueued in between; profiling brackets every launch with events, which would break the pair)
     static const int pdl_env = env_int("ISR_ICP_PDL", 1);
-    const bool pdl = V::kFused && c.reuse_order != 0 && pdl_env != 0 && !prof_enabled();
+    const bool pdl = V::kFused && c.reuse_order == 1 && pdl_env != 0 && !prof_enabled();
     if (splits == 1) return V::launch(p, grid, c.st, fuse, pdl);
 
     const long long total = (long long)nq * c.batch;

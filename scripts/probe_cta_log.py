@@ -26,11 +26,14 @@ torch.cuda.synchronize()
 cap = 40000
 log = torch.zeros((cap, 4), dtype=torch.int64, device="cuda")
 lib.isr_debug_cta_log(ctypes.c_void_p(log.data_ptr()), cap)
-prob.run(20.0, 0, 0.0, 0.0)
+# (iterations > 0: the log keeps the LAST launch of a longer run, i.e. the re-cut launch list)
+prob.run(20.0, int(sys.argv[4]) if len(sys.argv) > 4 else 0, 0.0, 0.0)
 torch.cuda.synchronize()
 lib.isr_debug_cta_log(None, 0)
 L = log.cpu().numpy().astype(np.uint64)
 L = L[L[:, 0] > 0]
+if len(sys.argv) > 4:
+    L = L[:int(api._lib.load().isr_version() * 0 + len(L))]
 cyc = L[:, 0].astype(np.float64)
 nscan = (L[:, 1] >> np.uint64(32)).astype(np.int64)
 ntest = (L[:, 1] & np.uint64(0xFFFFFFFF)).astype(np.int64)

@@ -69,7 +69,7 @@ if "adds" in which:
     t = timed(lambda: api.verify_poses(vd, Pqd, Ptd, cloud_t=sd, mode="adds"))
     print(f"adds: {B / t:.0f} pose pairs/s ({t / B * 1e6:.1f} us per pair)", flush=True)
 if "icp" in which:
-    n, iters = 1_000_000, 20
+    n, iters = 1_000_000, 50
     src, tgt, _ = synth.icp_pair(n, n, 4, 5)
     perm = api.spatial_order(src).cpu().numpy()
     for world in (1, 8):

@@ -627,6 +627,46 @@ def test_fused_icp_target_parts_are_bit_identical(gpu, monkeypatch):
     np.testing.assert_allclose(b.transformation, o.transformation, rtol=1e-7, atol=1e-7)
 
 
+def test_fused_icp_launch_list_recut_from_measured_costs_is_bit_identical(gpu, monkeypatch):
+    """One-wave grids re-cut the launch list of the fused ICP iteration from the cycles that the
+    previous iteration's CTAs measured (nn2.cu, block_rebalance_kernel: light blocks merge, heavy
+    ones split down to target parts).  The reduction order of the sums does not depend on how blocks
+    are cut into CTAs, so poses, rmse and correspondences equal the run with the static list bit for
+    bit (and the oracle), while the per-CTA log shows that the list did change."""
+    import ctypes
+    import torch
+    from imagesequenceregistrationfor6dposeestimationlabeling_b200 import _lib, api, synth
+    n = 200_000
+    src, tgt, _ = synth.icp_pair(n, n, 4, 5)
+    perm = api.spatial_order(src).cpu().numpy()
+    shard = src[perm[: n // 2]]
+    lib = _lib.load()
+    out = {}
+    for label in ("0", "1"):
+        monkeypatch.setenv("ISR_ICP_REBALANCE", label)
+        prob = api.IcpProblem(shard, tgt, np.eye(4)[None])
+        cap = 20000
+        log = torch.zeros((cap, 4), dtype=torch.int64, device="cuda")
+        lib.isr_debug_cta_log(ctypes.c_void_p(log.data_ptr()), cap)   # (every launch overwrites: the last one stays)
+        try:
+            prob.run(20.0, 6, 0.0, 0.0)
+            torch.cuda.synchronize()
+        finally:
+            lib.isr_debug_cta_log(None, 0)
+        L = log.cpu().numpy().astype(np.uint64)
+        L = L[L[:, 0] > 0]
+        codes = np.sort(((L[:, 3] >> np.uint64(24)) & np.uint64(0xFF)).astype(np.int64))
+        out[label] = (prob.results(True)[0], codes)
+    (a, codes_a), (b, codes_b) = out["0"], out["1"]
+    assert len(codes_a) != len(codes_b) or (codes_a != codes_b).any()   # the list was re-cut
+    np.testing.assert_array_equal(a.transformation, b.transformation)
+    assert (a.fitness, a.inlier_rmse, a.iterations) == (b.fitness, b.inlier_rmse, b.iterations)
+    np.testing.assert_array_equal(np.asarray(a.correspondence_set), np.asarray(b.correspondence_set))
+    o = oracle.registration_icp(shard, tgt, 20.0, np.eye(4), max_iteration=6, relative_fitness=0.0, relative_rmse=0.0)
+    np.testing.assert_array_equal(np.asarray(b.correspondence_set), o.correspondence_set)
+    np.testing.assert_allclose(b.transformation, o.transformation, rtol=1e-7, atol=1e-7)
+
+
 @pytest.mark.parametrize("n,radius,scale,offset", [
     (1, 1.0, 1.0, 0.0), (300, 3.0, 1.0, 0.0), (6000, 4.0, 1.0, 0.0), (6000, 0.05 * 60 / 1.8, 1.0, 0.0),
     (5000, 0.002, 1.0 / 2000, 0.0), (4000, 4.0, 1.0, 700.0), (3000, 1e-3, 1.0, 900.0)])
