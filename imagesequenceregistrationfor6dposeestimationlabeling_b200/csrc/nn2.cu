@@ -391,7 +391,11 @@ __device__ __forceinline__ void scan_subtile_pruned(const NN2Params &p, const fl
                                                     const float4 *sn, int gbase, float *mt_l, float *thr_l,
                                                     float *tm_l, double *Dbest_l, int *ibest_l, float *dq_l,
                                                     float &dmax, unsigned &nflag, unsigned &npass,
-                                                    const float *qsm, const float *qlo, unsigned rows) {
+                                                    const float *qsm, const float *qlo, unsigned rows
+#ifdef ISR_PHASE_LOG
+                                                    , long long &acc_resolve
+#endif
+                                                    ) {
     static_assert(Q == 8 && (GROUPS == 2 || GROUPS == 4), "halves of four rows or quarters of two");
     constexpr int H = Q / GROUPS;
     float tm[Q];
@@ -418,8 +422,14 @@ __device__ __forceinline__ void scan_subtile_pruned(const NN2Params &p, const fl
             for (int r = 0; r < H; ++r) tm[half * H + r] = tmh[r];
         }
     }
+#ifdef ISR_PHASE_LOG
+    const long long t_res = clock64();
+#endif
     resolve_flagged<Q, SUB, true, PARTS>(p, gq, gt, q0, lane, sx, sy, sz, sn, gbase, pflags, tm, mt_l, thr_l, tm_l,
                                          Dbest_l, ibest_l, dq_l, dmax, nflag, npass, qsm, qlo);
+#ifdef ISR_PHASE_LOG
+    acc_resolve += clock64() - t_res;
+#endif
 }
 
 // ---- exhaustive kernel: every stage, every sub-tile -----------------------------------------
@@ -1179,6 +1189,14 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     //            candidate stage the exact test, and its 16 sub-tile spheres -> coarse row test
     //            -> FIFO.
     unsigned nscanned = 0, nhalves = 0, ntests = 0, ncand = 0, nflag = 0, npass = 0;
+#ifdef ISR_PHASE_LOG
+    long long acc_sort = 0, acc_test = 0, acc_wait = 0, acc_scan = 0, acc_resolve = 0, acc_produce = 0;
+#define PH_T0 const long long ph_t0 = clock64();
+#define PH_ADD(acc) acc += clock64() - ph_t0;
+#else
+#define PH_T0
+#define PH_ADD(acc)
+#endif
     unsigned refreshed_at = ~0u;
     bool sorted = p.sort_fifo == 0;
     bool seeding = true;   // the seeds must be scanned before anything is produced
@@ -1200,6 +1218,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             // their exact test and fewer scans improve a neighbour that a later scan improves
             // again.  Rank sort of at most 64 keys, two per lane, through the idle ring buffer.
             sorted = true;
+            PH_T0
             const int cnt = tail - look;
             if (cnt > 2 && cnt <= 64 && look == head) {
                 u64 *keys = reinterpret_cast<u64 *>(&ws.buf[0][0][0]);
@@ -1243,8 +1262,12 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                 }
                 __syncwarp();
             }
+            PH_ADD(acc_sort)
         }
         if (pending > 0 && (seeding || produced_all || pending > kFifo - 2 * SUBS)) {
+#ifdef ISR_PHASE_LOG
+            const long long ph_c0 = clock64();
+#endif
             while (look < tail && nloads - nconsumed < kRing) {
                 const int e = look % kFifo;
                 ++ntests;
@@ -1276,10 +1299,21 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                 ++look;
             }
             __syncwarp();
+#ifdef ISR_PHASE_LOG
+            acc_test += clock64() - ph_c0;
+#endif
             const int id = ws.id[head % kFifo];
             if (id >= 0) {
                 const int slot = nconsumed % kRing;
+#ifdef ISR_PHASE_LOG
+                const long long ph_w0 = clock64();
+#endif
                 mbar_wait(&ws.full[slot], (nconsumed / kRing) & 1);
+#ifdef ISR_PHASE_LOG
+                const long long ph_w1 = clock64();
+                acc_wait += ph_w1 - ph_w0;
+                const long long res0 = acc_resolve;
+#endif
                 const unsigned rows_e = ws.rows[head % kFifo];
                 ++nscanned;
                 // counted in half units (4 rows x SUB targets): a quarter (2 rows) is half of one
@@ -1298,7 +1332,14 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                                                      sx + 2 * (SUB / 4) + h * (FLAG / 4),
                                                      sx + 3 * (SUB / 4) + h * (FLAG / 4), id * SUB + h * FLAG,
                                                      mt_l, thr_l, tm_l, Dbest_l, ibest_l, dq_l, dmax, nflag,
-                                                     npass, &ws.qs[0][0], qlo, rows_e);
+                                                     npass, &ws.qs[0][0], qlo, rows_e
+#ifdef ISR_PHASE_LOG
+                                                     , acc_resolve
+#endif
+                                                     );
+#ifdef ISR_PHASE_LOG
+                acc_scan += (clock64() - ph_w1) - (acc_resolve - res0);
+#endif
                 ++nconsumed;
                 __syncwarp();  // every lane is done with the slot before lane 0 refills it
             }
@@ -1307,6 +1348,10 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         }
         seeding = false;
         if (produced_all) break;
+#ifdef ISR_PHASE_LOG
+        struct PhScope { long long &a; long long t0; __device__ PhScope(long long &x) : a(x), t0(clock64()) {}
+                         __device__ ~PhScope() { a += clock64() - t0; } } ph_scope(acc_produce);
+#endif
         if (smask == 0) {
             // refresh the row bounds (if any scan ran since)
             if (nscanned != refreshed_at) {
@@ -1517,6 +1562,14 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                 o[2] = (unsigned long long)ph_r | ((unsigned long long)ph_e << 32);
                 o[3] = ((unsigned long long)(unsigned)blk << 32) | ((unsigned long long)(rowsel | (tpart << 4)) << 24) |
                        (unsigned long long)((clock64() - t_start) >> 8 & 0xFFFFFF);
+                unsigned long long *o2 = p.cta_log + 4 * (p.cta_log_cap / 2 + rec);  // main-loop shares
+                if (rec < p.cta_log_cap / 2 - 1) {
+                    o2[1] = (unsigned long long)acc_scan | ((unsigned long long)acc_resolve << 32);
+                    o2[0] = (unsigned long long)acc_test | ((unsigned long long)acc_wait << 32);
+                    o2[2] = (unsigned long long)acc_produce | ((unsigned long long)acc_sort << 32);
+                    o2[3] = ((unsigned long long)nscanned << 48) | ((unsigned long long)ntests << 32) |
+                            ((unsigned long long)npass << 16) | (unsigned long long)nhalves;
+                }
             }
         }
 #endif
@@ -2024,7 +2077,10 @@ using NN2PrunedHalvesFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2, true>;
 // (flags per quarter of the sub-tile, so that a resolve pass re-derives 16 filter values instead of
 // 64: in a shallow grid a warp's instruction count IS its latency -- 0.161 -> 0.155 ms per
 // iteration on a 1/8 shard; in deep grids the same change was measured 0 .. -2 %)
-using NN2PrunedFusedSplit = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 4, 4, true, true>;
+#ifndef ISR_SPLIT_UNR
+#define ISR_SPLIT_UNR 1
+#endif
+using NN2PrunedFusedSplit = NN2PrunedVariant<8, 1, 64, 20, ISR_SPLIT_UNR, 64, 4, 4, true, true>;
 #ifdef ISR_NN_TUNING
 using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 2>;
 using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 4>;

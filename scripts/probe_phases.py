@@ -24,18 +24,20 @@ prob.run(20.0, 3, 0.0, 0.0)
 prob.reopen()
 torch.cuda.synchronize()
 cap = 40000
-for rep in range(2):
-    log = torch.zeros((cap, 4), dtype=torch.int64, device="cuda")
-    log[cap - 1, 0] = torch.iinfo(torch.int64).max
-    lib.isr_debug_cta_log(ctypes.c_void_p(log.data_ptr()), cap)
-    prob.run(20.0, 0, 0.0, 0.0)
-    torch.cuda.synchronize()
-    lib.isr_debug_cta_log(None, 0)
-    prob.reopen()
+# (run with ISR_ICP_PDL=0: the stamps start at CTA start.  The log keeps the LAST launch of a
+# 7-launch run, i.e. the re-cut launch list)
+iters = int(sys.argv[4]) if len(sys.argv) > 4 else 6
+log = torch.zeros((cap, 4), dtype=torch.int64, device="cuda")
+lib.isr_debug_cta_log(ctypes.c_void_p(log.data_ptr()), cap)
+prob.run(20.0, iters, 0.0, 0.0)
+torch.cuda.synchronize()
+lib.isr_debug_cta_log(None, 0)
 L = log.cpu().numpy().astype(np.uint64)
 marks = L[cap - 1].astype(np.int64)
-L = L[:cap - 1]
-L = L[L[:, 0] > 0]
+L2 = L[cap // 2:cap - 1]
+L = L[:cap // 2 - 1]
+keep = L[:, 0] > 0
+L, L2 = L[keep], L2[:len(keep)][keep]
 lo32 = np.uint64(0xFFFFFFFF)
 search_end = L[:, 0].astype(np.float64)
 q_ready = (L[:, 1] & lo32).astype(np.float64)
@@ -44,8 +46,6 @@ rows = (L[:, 2] & lo32).astype(np.float64)
 epi = (L[:, 2] >> np.uint64(32)).astype(np.float64)
 total = ((L[:, 3] & np.uint64(0xFFFFFF)).astype(np.float64)) * 256
 print(f"{len(L)} CTAs logged (1/{world} shard, rank {rank}, {hi - lo} points)")
-print(f"wall clock (us): first start -> last search end {(marks[1] - marks[0]) / 1e3:.1f}, -> last epilogue end "
-      f"{(marks[2] - marks[0]) / 1e3:.1f}, -> kernel end (tail, solve) {(marks[3] - marks[0]) / 1e3:.1f}")
 def st(name, v):
     print(f"  {name}: median {np.median(v):.0f}  mean {v.mean():.0f}  p90 {np.percentile(v, 90):.0f}  max {v.max():.0f} cycles")
 st("query copy + pose + split", q_ready)
@@ -55,6 +55,23 @@ st("walk + tests + scans", search_end - rows)
 st("epilogue (gather, sums)", epi - search_end)
 st("tail (tickets .. solve)", total - epi)
 st("whole CTA", total)
+lo = np.uint64(0xFFFFFFFF)
+sh = np.uint64(32)
+print("inside walk + tests + scans:")
+st("  consume: exact tests + copy issue", (L2[:, 0] & lo).astype(np.float64))
+st("  wait for the sub-tile", (L2[:, 0] >> sh).astype(np.float64))
+st("  filter scan", (L2[:, 1] & lo).astype(np.float64))
+st("  resolve", (L2[:, 1] >> sh).astype(np.float64))
+st("  produce (sphere walk -> FIFO)", (L2[:, 2] & lo).astype(np.float64))
+st("  nearest-first sort", (L2[:, 2] >> sh).astype(np.float64))
+nsc = (L2[:, 3] >> np.uint64(48)).astype(np.float64)
+nte = ((L2[:, 3] >> sh) & np.uint64(0xFFFF)).astype(np.float64)
+npa = ((L2[:, 3] >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.float64)
+nqu = (L2[:, 3] & np.uint64(0xFFFF)).astype(np.float64)
+print(f"  per CTA: {nsc.mean():.1f} scanned tiles, {nqu.mean():.1f} quarter scans, {nte.mean():.1f} exact tests, {npa.mean():.1f} resolve passes")
+print(f"  per event (mean cycles): exact test {(L2[:, 0] & lo).astype(np.float64).sum() / max(nte.sum(), 1):.0f}, "
+      f"quarter scan {(L2[:, 1] & lo).astype(np.float64).sum() / max(nqu.sum(), 1):.0f}, "
+      f"resolve pass {(L2[:, 1] >> sh).astype(np.float64).sum() / max(npa.sum(), 1):.0f}")
 slow = np.argsort(-total)[:8]
 for o in slow:
     print(f"   slow CTA: total {total[o]:.0f}: copy {q_ready[o]:.0f} hints {hints[o] - q_ready[o]:.0f} rows {rows[o] - hints[o]:.0f} "
