@@ -46,83 +46,103 @@ constexpr size_t kPeerFlagBytes = (size_t)2 * kPeerRanks * kPeerStarts * sizeof(
 
 #ifdef __CUDACC__
 // ---- 3x3 SVD (one-sided Jacobi, FP64) and Kabsch ---------------------------------------
-__device__ inline void svd3(const double M[3][3], double U[3][3], double D[3], double V[3][3]) {
+// (Every index below is a compile-time constant once the loops are unrolled: the matrices live in
+// registers.  With the column pair (p, q) as a run-time index they sat in local memory, and this
+// function -- one thread, at the very end of every ICP iteration, the whole machine waiting -- spent
+// most of its ~15 k cycles on the round trips.)
+template <int P, int Q>
+__device__ __forceinline__ bool svd3_rotate(double (&A)[3][3], double (&V)[3][3]) {
+    double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        alpha += A[k][P] * A[k][P];
+        beta += A[k][Q] * A[k][Q];
+        gamma += A[k][P] * A[k][Q];
+    }
+    // one square root, one division and one reciprocal square root per rotation: the convergence
+    // test on squares, and
+    //   t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)),  zeta = (beta - alpha) / (2 gamma)
+    //     = sign(beta - alpha) 2 gamma / (|beta - alpha| + sqrt((beta - alpha)^2 + 4 gamma^2))
+    if (gamma == 0.0 || gamma * gamma <= (2.3e-16 * 2.3e-16) * (alpha * beta)) return false;
+    const double delta = beta - alpha, g2 = 2.0 * gamma;
+    double t = g2 / (fabs(delta) + sqrt(fma(delta, delta, g2 * g2)));
+    t = delta < 0.0 ? -t : t;
+    const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double ap = A[k][P], aq = A[k][Q];
+        A[k][P] = c * ap - sn * aq;
+        A[k][Q] = sn * ap + c * aq;
+        const double vp = V[k][P], vq = V[k][Q];
+        V[k][P] = c * vp - sn * vq;
+        V[k][Q] = sn * vp + c * vq;
+    }
+    return true;
+}
+template <int A_, int B_>
+__device__ __forceinline__ void svd3_order(double (&D)[3], double (&A)[3][3], double (&V)[3][3]) {
+    if (D[B_] > D[A_]) {
+        const double td = D[A_]; D[A_] = D[B_]; D[B_] = td;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double ta = A[k][A_]; A[k][A_] = A[k][B_]; A[k][B_] = ta;
+            const double tv = V[k][A_]; V[k][A_] = V[k][B_]; V[k][B_] = tv;
+        }
+    }
+}
+__device__ inline void svd3(const double (&M)[3][3], double (&U)[3][3], double (&D)[3], double (&V)[3][3]) {
     double A[3][3];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j) {
             A[i][j] = M[i][j];
             V[i][j] = (i == j) ? 1.0 : 0.0;
         }
-    const int P[3] = {0, 0, 1}, Qc[3] = {1, 2, 2};
+#pragma unroll 1
     for (int sweep = 0; sweep < 64; ++sweep) {
-        bool rotated = false;
-        for (int pr = 0; pr < 3; ++pr) {
-            const int p = P[pr], q = Qc[pr];
-            double alpha = 0, beta = 0, gamma = 0;
-            for (int k = 0; k < 3; ++k) {
-                alpha += A[k][p] * A[k][p];
-                beta += A[k][q] * A[k][q];
-                gamma += A[k][p] * A[k][q];
-            }
-            // (this runs on ONE thread at the very end of every ICP iteration, with every other warp of
-            // the machine waiting for it: software FP64 divisions and square roots are its cost.  One
-            // square root, one division and one reciprocal square root per rotation instead of three
-            // and three: the convergence test on squares, and
-            //   t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)),  zeta = (beta - alpha) / (2 gamma)
-            //     = sign(beta - alpha) 2 gamma / (|beta - alpha| + sqrt((beta - alpha)^2 + 4 gamma^2)))
-            if (gamma == 0.0 || gamma * gamma <= (2.3e-16 * 2.3e-16) * (alpha * beta)) continue;
-            rotated = true;
-            const double delta = beta - alpha, g2 = 2.0 * gamma;
-            double t = g2 / (fabs(delta) + sqrt(fma(delta, delta, g2 * g2)));
-            t = delta < 0.0 ? -t : t;
-            const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
-            for (int k = 0; k < 3; ++k) {
-                const double ap = A[k][p], aq = A[k][q];
-                A[k][p] = c * ap - sn * aq;
-                A[k][q] = sn * ap + c * aq;
-                const double vp = V[k][p], vq = V[k][q];
-                V[k][p] = c * vp - sn * vq;
-                V[k][q] = sn * vp + c * vq;
-            }
-        }
+        bool rotated = svd3_rotate<0, 1>(A, V);
+        rotated = svd3_rotate<0, 2>(A, V) || rotated;
+        rotated = svd3_rotate<1, 2>(A, V) || rotated;
         if (!rotated) break;
     }
+#pragma unroll
     for (int j = 0; j < 3; ++j)
         D[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
     // sort singular values descending (column permutation of A and V)
-    for (int a = 0; a < 2; ++a)
-        for (int b = a + 1; b < 3; ++b)
-            if (D[b] > D[a]) {
-                const double td = D[a]; D[a] = D[b]; D[b] = td;
-                for (int k = 0; k < 3; ++k) {
-                    const double ta = A[k][a]; A[k][a] = A[k][b]; A[k][b] = ta;
-                    const double tv = V[k][a]; V[k][a] = V[k][b]; V[k][b] = tv;
-                }
-            }
+    svd3_order<0, 1>(D, A, V);
+    svd3_order<0, 2>(D, A, V);
+    svd3_order<1, 2>(D, A, V);
     const double tiny = D[0] * 1e-14;
     int rank = 0;
+#pragma unroll
     for (int j = 0; j < 3; ++j) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) U[k][j] = 0.0;
         if (D[j] > tiny && D[j] > 0.0) {
             const double inv = 1.0 / D[j];
+#pragma unroll
             for (int k = 0; k < 3; ++k) U[k][j] = A[k][j] * inv;
             ++rank;
         }
     }
     if (rank == 0) {
+#pragma unroll
         for (int i = 0; i < 3; ++i)
+#pragma unroll
             for (int j = 0; j < 3; ++j) U[i][j] = (i == j) ? 1.0 : 0.0;
     } else {
         if (rank == 1) {
-            // any unit vector orthogonal to U[:,0]
+            // any unit vector orthogonal to U[:,0]: the axis of its smallest component, projected
             int m = 0;
-            if (fabs(U[1][0]) < fabs(U[m][0])) m = 1;
-            if (fabs(U[2][0]) < fabs(U[m][0])) m = 2;
-            double e[3] = {0, 0, 0};
-            e[m] = 1.0;
-            const double dp = U[m][0];
+            double um = U[0][0];
+            if (fabs(U[1][0]) < fabs(um)) { m = 1; um = U[1][0]; }
+            if (fabs(U[2][0]) < fabs(um)) { m = 2; um = U[2][0]; }
             double w[3], nn = 0;
-            for (int k = 0; k < 3; ++k) { w[k] = e[k] - dp * U[k][0]; nn += w[k] * w[k]; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { w[k] = (k == m ? 1.0 : 0.0) - um * U[k][0]; nn += w[k] * w[k]; }
             nn = sqrt(nn);
+#pragma unroll
             for (int k = 0; k < 3; ++k) U[k][1] = w[k] / nn;
         }
         if (rank <= 2) {
@@ -172,25 +192,35 @@ __device__ inline void icp_solve_state(IsrIcpState &st, const double *S, int64_t
     const double ms[3] = {S[0] * inv, S[1] * inv, S[2] * inv};
     const double mt[3] = {S[3] * inv, S[4] * inv, S[5] * inv};
     double Sig[3][3], U[3][3], V[3][3], D[3];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j) Sig[i][j] = S[6 + 3 * i + j] * inv - mt[i] * ms[j];
     svd3(Sig, U, D, V);
     const double sgn = (det3(U) * det3(V) < 0.0) ? -1.0 : 1.0;
     double R[3][3];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j)
             R[i][j] = U[i][0] * V[j][0] + U[i][1] * V[j][1] + sgn * U[i][2] * V[j][2];
     double tr[3];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
         tr[i] = mt[i] - (R[i][0] * ms[0] + R[i][1] * ms[1] + R[i][2] * ms[2]);
-    // T <- [R tr; 0 1] . T
-    double Tn[12];
+    // T <- [R tr; 0 1] . T   (the old pose is fetched in one go)
+    double To[12], Tn[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) To[k] = st.T[k];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
-            double v = R[i][0] * st.T[0 + j] + R[i][1] * st.T[4 + j] + R[i][2] * st.T[8 + j];
+            double v = R[i][0] * To[0 + j] + R[i][1] * To[4 + j] + R[i][2] * To[8 + j];
             if (j == 3) v += tr[i];
             Tn[4 * i + j] = v;
         }
+#pragma unroll
     for (int k = 0; k < 12; ++k) st.T[k] = Tn[k];
     st.T[12] = 0.0; st.T[13] = 0.0; st.T[14] = 0.0; st.T[15] = 1.0;
 }
