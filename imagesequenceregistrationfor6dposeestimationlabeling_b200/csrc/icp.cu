@@ -346,7 +346,9 @@ static int run_fused(IsrIcpState *states, int64_t starts, const float *src, cons
         // (iterations 2 and 4 re-cut the launch list from the costs that the hinted iterations before
         // them measured: nn2.cu, block_rebalance_kernel; iteration 0 is the unhinted search)
         static const int recut_rounds = getenv("ISR_ICP_RECUT_ROUNDS") ? atoi(getenv("ISR_ICP_RECUT_ROUNDS")) : 2;
-        const int reuse = k == 0 ? 0 : (k % 2 == 0 && k <= 2 * recut_rounds) ? 2 : 1;
+        // (a grid deeper than one wave is throughput-bound: one re-cut is all it gains from)
+        const int rounds = nn2_query_blocks(ns) * starts > (int64_t)sm_count() * 20 ? (recut_rounds < 1 ? recut_rounds : 1) : recut_rounds;
+        const int reuse = k == 0 ? 0 : (k % 2 == 0 && k <= 2 * rounds) ? 2 : 1;
         const int s = nn2_search(&src_cloud, tgt_cloud, starts, 1, nullptr, nullptr, done, kStateInts,
                                  ws + L.nnws, L.total - L.nnws, stream, reuse, &f);
         if (peer != nullptr && s == ISR_OK) peer->seq += 1;  // the launch exists: so does its message

@@ -1851,9 +1851,10 @@ block_rebalance_kernel(int *__restrict__ order, int *__restrict__ order_slot, in
         const int nrows = __popc(rows);
         const float c = (float)cost[e];
         const float share = fmaxf(c - F, 0.f) / (float)nrows;
+        const bool part = ((entry >> 28) & 7) != 0;  // (only the parts of a target-part row share a row)
         for (int r = 0; r < 8; ++r)
             if ((rows >> r) & 1u) {
-                atomicAdd(&vrow[blk * 8 + r], share);
+                if (part) atomicAdd(&vrow[blk * 8 + r], share); else vrow[blk * 8 + r] = share;
                 grow[blk * 8 + r] = (unsigned char)nrows;
             }
         csum += c;

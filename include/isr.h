@@ -332,8 +332,12 @@ int isr_icp_solve(IsrIcpState *states, int64_t starts, const double *sums, int64
  * With the pruned search (the default) one pass is ONE kernel launch: the search kernel
  * transforms the source itself, gathers each neighbour's original coordinates, reduces the
  * 17 sums in a fixed order across the grid and solves Kabsch in the last warp to arrive
- * (nn2.cu / icp_device.cuh); otherwise K1' + K2 + accumulate + solve per pass.  corr_idx and
- * inlier describe the LAST evaluation of every start.
+ * (nn2.cu / icp_device.cuh); otherwise K1' + K2 + accumulate + solve per pass.  A single start
+ * also measures the cycles of every CTA and, once or twice early in the run, cuts its launch
+ * list again from them (block_rebalance_kernel: heavy query blocks split, light ones merge);
+ * the sums are reduced in an order that does not depend on that cut, so results are
+ * bit-identical with and without.  Launches after the first are programmatic dependent
+ * launches of the one before.  corr_idx and inlier describe the LAST evaluation of every start.
  * o3d.pipelines.registration.registration_icp, icp.py:101-103; with max_iteration == 0
  * it is evaluate_registration, icp.py:97-98. */
 int isr_icp_run(IsrIcpState *states, int64_t starts, const float *src, const float *src_lo,
