@@ -72,7 +72,7 @@ def parse_args():
     ap.add_argument("--candidates", type=int, default=1000, help="candidates per GPU per step")
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--icp-points", type=int, default=1_000_000)
-    ap.add_argument("--icp-iters", type=int, default=10)
+    ap.add_argument("--icp-iters", type=int, default=50)   # BASELINE configs[3]: 50 iterations
     ap.add_argument("--skip-icp", action="store_true")
     ap.add_argument("--skip-extra", action="store_true", help="skip the config-5 / ADD-S timings")
     ap.add_argument("--skip-cpu", action="store_true")
