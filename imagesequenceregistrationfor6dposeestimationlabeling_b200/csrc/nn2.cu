@@ -91,7 +91,7 @@ struct NN2Params {
     const float4 *sub_c;     // [batch][stages_total * STAGE/SUB] sub-tile spheres (PRUNE)
     long long sub_c_bstride;
     unsigned long long *evaluated;  // profiling: scanned (warp, sub-tile) units, or NULL
-    const int *order;        // [batch][gridDim.x] (query block | (row + 1) << 24) run by CTA x, or NULL
+    const int *order;        // [batch][gridDim.x] launch-list entries (launch_entry()) run by CTA x, or NULL
     const int *order_count;  // [batch] entries of `order` in use
     int *hint;               // [batch][nq_pad] in/out starting neighbours (stored positions), or NULL
     int nanchors;            // seeds used (<= kAnchors; fewer only for tuning runs)
@@ -651,17 +651,15 @@ struct alignas(128) PrunedWarpSmem {
     float dq[Q][32];
 };
 
-// rows of a query block that launch-list code `rowsel` stands for: 0 all eight, 1..8 one row,
-// 9 / 10 a half (rows 0-3 / 4-7), 11..14 a quarter (rows 2k, 2k + 1)
-__host__ __device__ inline unsigned rows_of_code(int rowsel) {
-    if (rowsel == 0) return 0xFFu;
-    if (rowsel <= 8) return 1u << (rowsel - 1);
-    if (rowsel <= 10) return 0x0Fu << (4 * (rowsel - 9));
-    return 0x03u << (2 * (rowsel - 11));
+// A launch-list entry: query block (20 bits) | the rows of the block that the CTA owns (8-bit mask, a
+// run of consecutive rows) << 20 | target part (0: the whole target; k: part k - 1 of kTargetParts) << 28
+__host__ __device__ inline int launch_entry(int blk, unsigned rows, int tpart) {
+    return (int)((unsigned)blk | (rows << 20) | ((unsigned)tpart << 28));
 }
-// launch-list code of part c of a block that runs as `parts` CTAs
-__host__ __device__ inline int code_of_part(int parts, int c) {
-    return parts == 1 ? 0 : parts == 2 ? 9 + c : parts == 4 ? 11 + c : 1 + c;
+// rows of part c of a block that runs as `parts` CTAs of 8 / parts rows
+__host__ __device__ inline unsigned rows_of_part(int parts, int c) {
+    const int n = 8 / parts;
+    return ((1u << n) - 1u) << (n * c);
 }
 
 // FUSED: the kernel is one whole ICP evaluation + update (IcpFuse, icp_device.cuh): the queries
@@ -683,16 +681,16 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     const int lane = tid & 31, warp = tid >> 5;
     // heaviest query blocks first (order from block_order_kernel): the grid is only a few
     // waves deep for a single cloud pair, and a late-starting heavy block would be its tail.
-    // The very widest blocks are split over 8 CTAs that own one query row each (rowsel).
-    int blk = (int)blockIdx.x, rowsel = 0, tpart = 0;
+    // The very widest blocks are split over 8 CTAs that own one query row each 
+    int blk = (int)blockIdx.x, tpart = 0;
+    unsigned own = 0xFFu;  // rows this CTA is responsible for
     if (p.order != nullptr) {
         if ((int)blockIdx.x >= p.order_count[b]) return;
         const int entry = p.order[(long long)b * gridDim.x + blockIdx.x];
-        blk = entry & 0xFFFFFF;
-        rowsel = (entry >> 24) & 15;  // rows_of_code
+        blk = entry & 0xFFFFF;
+        own = ((unsigned)entry >> 20) & 0xFFu;
         tpart = FUSED && SPLIT ? (entry >> 28) & 7 : 0;  // 0: the whole target; k: part k - 1 of kTargetParts
     }
-    const unsigned own = rows_of_code(rowsel);  // rows this CTA is responsible for
     const int q0 = blk * (WARPS * 32 * Q) + warp * (32 * Q) + lane;
     if (!FUSED && q0 - lane >= p.nq) return;  // this warp has no live query; warps never meet at a barrier
     unsigned livemask = 0;  // bit r: query r * 32 + lane exists and belongs to this CTA
@@ -1448,7 +1446,8 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             o[0] = (unsigned long long)(clock64() - t_start);
             o[1] = ((unsigned long long)nscanned << 32) | ntests;
             o[2] = ((unsigned long long)nhalves << 32) | ncand;
-            o[3] = ((unsigned long long)(unsigned)blk << 32) | ((unsigned long long)(rowsel | (tpart << 4)) << 24) | (npass & 0xFFFFFFu);
+            o[3] = ((unsigned long long)(unsigned)blk << 32) | ((unsigned long long)own << 24) |
+                   ((unsigned long long)tpart << 20) | (npass & 0xFFFFFu);
         }
     }
     if (p.evaluated != nullptr && lane == 0) {
@@ -1560,8 +1559,8 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                 o[0] = (unsigned long long)ph_s;
                 o[1] = (unsigned long long)ph_q | ((unsigned long long)ph_h << 32);
                 o[2] = (unsigned long long)ph_r | ((unsigned long long)ph_e << 32);
-                o[3] = ((unsigned long long)(unsigned)blk << 32) | ((unsigned long long)(rowsel | (tpart << 4)) << 24) |
-                       (unsigned long long)((clock64() - t_start) >> 8 & 0xFFFFFF);
+                o[3] = ((unsigned long long)(unsigned)blk << 32) | ((unsigned long long)own << 24) |
+                       ((unsigned long long)tpart << 20) | (unsigned long long)((clock64() - t_start) >> 8 & 0xFFFFF);
                 unsigned long long *o2 = p.cta_log + 4 * (p.cta_log_cap / 2 + rec);  // main-loop shares
                 if (rec < p.cta_log_cap / 2 - 1) {
                     o2[1] = (unsigned long long)acc_scan | ((unsigned long long)acc_resolve << 32);
@@ -1729,10 +1728,10 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
                 const int at = rowrad != nullptr ? rowpos[i * rows + r] : i * rows + r;
                 const int sl = rowrad != nullptr ? rowslot[i * rows + r] : -1;
                 if (sl < 0) {
-                    out[at] = blk | ((r + 1) << 24);
+                    out[at] = launch_entry(blk, 1u << r, 0);
                 } else {
                     for (int k = 0; k < kTargetParts; ++k) {
-                        out[at + k] = blk | ((r + 1) << 24) | ((k + 1) << 28);
+                        out[at + k] = launch_entry(blk, 1u << r, k + 1);
                         order_slot[at + k] = sl;
                     }
                 }
@@ -1743,10 +1742,10 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
             // and shortens the tail)
             if (i - h < nm) {
                 for (int c = 0; c < 2 * parts; ++c)
-                    out[hbase + 2 * parts * (i - h) + c] = blk | (code_of_part(2 * parts, c) << 24);
+                    out[hbase + 2 * parts * (i - h) + c] = launch_entry(blk, rows_of_part(2 * parts, c), 0);
             } else {
                 for (int c = 0; c < parts; ++c)
-                    out[hbase + parts * nm + parts * (i - h) + c] = blk | (code_of_part(parts, c) << 24);
+                    out[hbase + parts * nm + parts * (i - h) + c] = launch_entry(blk, rows_of_part(parts, c), 0);
             }
         }
     }
@@ -1768,6 +1767,7 @@ block_order_kernel(const u64 *__restrict__ keys, int nqb, int rows, int stride, 
 #define ISR_SPLIT_INFLATE 1.15f
 #endif
 constexpr float kSplitInflate = ISR_SPLIT_INFLATE;  // a halved run costs more than half (repeated coarse walk and tests)
+// cost of a row inside a run of rows_new rows, measured inside a CTA of rows_old rows
 __device__ __forceinline__ float rebalance_scale(int rows_new, int rows_old) {
     float f = 1.f;
     for (int a = rows_old; a > rows_new; a >>= 1) f *= kSplitInflate;
@@ -1775,7 +1775,11 @@ __device__ __forceinline__ float rebalance_scale(int rows_new, int rows_old) {
     // cheaper on its own -- its CTA's coarse tests see one small sphere -- than inside a wider CTA)
     return f;
 }
-// pieces of one block at level T; emit(code, tpart_count (1 or kTargetParts), estimate)
+// The CTAs of one block at level T: a run of rows stays one CTA while its estimate F + sum v_r stays
+// under T, else it is halved (8 -> 4 -> 2 -> 1 rows; a single row above T runs as target parts).
+// emit(rows mask, CTAs (1 or kTargetParts), estimate).
+// (Runs of any length, packed greedily under T, were measured too: 1 882 single-row CTAs, the same
+// slowest CTA, iteration 4 % slower -- the estimates, not the granularity, limit the balance.)
 // (merge: may rows that were measured in narrower CTAs be joined?  Only a one-wave list needs that, to
 // free slots for the cuts)
 template <class Emit>
@@ -1790,17 +1794,17 @@ __device__ __forceinline__ void rebalance_block(const float *v, const unsigned c
         return F + sum;
     };
     const float e8 = est(0, 8);
-    if (e8 <= T) { emit(0, 1, e8); return; }
+    if (e8 <= T) { emit(0xFFu, 1, e8); return; }
     for (int h = 0; h < 2; ++h) {
         const float e4 = est(4 * h, 4);
-        if (e4 <= T) { emit(9 + h, 1, e4); continue; }
+        if (e4 <= T) { emit(0x0Fu << (4 * h), 1, e4); continue; }
         for (int q = 2 * h; q < 2 * h + 2; ++q) {
             const float e2 = est(2 * q, 2);
-            if (e2 <= T) { emit(11 + q, 1, e2); continue; }
+            if (e2 <= T) { emit(0x03u << (2 * q), 1, e2); continue; }
             for (int r = 2 * q; r < 2 * q + 2; ++r) {
                 const float e1 = est(r, 1);
-                if (e1 <= T || !allow_tp) { emit(1 + r, 1, e1); continue; }
-                emit(1 + r, kTargetParts, F + (e1 - F) * (1.1f / kTargetParts) + 0.15f * F);
+                if (e1 <= T || !allow_tp) { emit(1u << r, 1, e1); continue; }
+                emit(1u << r, kTargetParts, F + (e1 - F) * (1.1f / kTargetParts) + 0.15f * F);
             }
         }
     }
@@ -1846,8 +1850,8 @@ block_rebalance_kernel(int *__restrict__ order, int *__restrict__ order_slot, in
     float csum = 0.f;
     for (int e = tid; e < n_old; e += 1024) {
         const int entry = order[e];
-        const int blk = entry & 0xFFFFFF, code = (entry >> 24) & 15;
-        const unsigned rows = rows_of_code(code);
+        const int blk = entry & 0xFFFFF;
+        const unsigned rows = ((unsigned)entry >> 20) & 0xFFu;
         const int nrows = __popc(rows);
         const float c = (float)cost[e];
         const float share = fmaxf(c - F, 0.f) / (float)nrows;
@@ -1882,7 +1886,7 @@ block_rebalance_kernel(int *__restrict__ order, int *__restrict__ order_slot, in
             unsigned n = 0, ntp = 0;
             for (int b = tid; b < nqb; b += 1024) {
                 const RebalanceRows R = rebalance_load(vrow, grow, b);
-                rebalance_block(R.v, R.g, F, T, tp_slots > 0, true, [&](int, int parts, float) {
+                rebalance_block(R.v, R.g, F, T, tp_slots > 0, true, [&](unsigned, int parts, float) {
                     n += (unsigned)parts;
                     ntp += parts > 1 ? 1u : 0u;
                 });
@@ -1911,7 +1915,7 @@ block_rebalance_kernel(int *__restrict__ order, int *__restrict__ order_slot, in
     for (int b = tid; b < nqb; b += 1024) {
         const RebalanceRows R = rebalance_load(vrow, grow, b);
         rebalance_block(R.v, R.g, F, level, tp_slots > 0, nqb <= slots,
-                        [&](int, int parts, float e) { atomicAdd(&bin_n[bin_of(e)], (unsigned)parts); });
+                        [&](unsigned, int parts, float e) { atomicAdd(&bin_n[bin_of(e)], (unsigned)parts); });
     }
     __syncthreads();
     if (tid == 0) {
@@ -1924,11 +1928,11 @@ block_rebalance_kernel(int *__restrict__ order, int *__restrict__ order_slot, in
     if (n_new > max_entries) return;  // (cannot happen: the list has room for every row of every block)
     for (int b = tid; b < nqb; b += 1024) {
         const RebalanceRows R = rebalance_load(vrow, grow, b);
-        rebalance_block(R.v, R.g, F, level, tp_slots > 0, nqb <= slots, [&](int code, int parts, float e) {
+        rebalance_block(R.v, R.g, F, level, tp_slots > 0, nqb <= slots, [&](unsigned rows, int parts, float e) {
             const unsigned at = atomicAdd(&bin_at[bin_of(e)], (unsigned)parts);
             const unsigned slot = parts > 1 ? atomicAdd(&tp_s, 1u) : 0u;
             for (int k = 0; k < parts; ++k) {
-                order[at + k] = (int)((unsigned)b | ((unsigned)code << 24) | (parts > 1 ? (unsigned)(k + 1) << 28 : 0u));
+                order[at + k] = launch_entry(b, rows, parts > 1 ? k + 1 : 0);
                 order_slot[at + k] = (int)slot;
             }
         });

@@ -40,8 +40,8 @@ ntest = (L[:, 1] & np.uint64(0xFFFFFFFF)).astype(np.int64)
 nquart = (L[:, 2] >> np.uint64(32)).astype(np.int64)
 ncand = (L[:, 2] & np.uint64(0xFFFFFFFF)).astype(np.int64)
 blk = (L[:, 3] >> np.uint64(32)).astype(np.int64)
-code = ((L[:, 3] >> np.uint64(24)) & np.uint64(0xFF)).astype(np.int64)
-npass = (L[:, 3] & np.uint64(0xFFFFFF)).astype(np.int64)
+code = ((L[:, 3] >> np.uint64(20)) & np.uint64(0xFFF)).astype(np.int64)   # rows mask << 4 | target part
+npass = (L[:, 3] & np.uint64(0xFFFFF)).astype(np.int64)
 print(f"{len(L)} CTAs; cycles: mean {cyc.mean():.0f} median {np.median(cyc):.0f} p90 {np.percentile(cyc, 90):.0f} "
       f"p99 {np.percentile(cyc, 99):.0f} max {cyc.max():.0f}")
 print(f"sum of cycles / 148 SMs / 16 warps = {cyc.sum() / 148 / 16:.0f} (ideal balanced makespan at full occupancy)")
@@ -52,6 +52,9 @@ for name, v in (("scanned sub-tiles", nscan), ("exact tests", ntest), ("quarter 
 A = np.stack([np.ones_like(cyc), nscan, ntest, nquart, ncand, npass], 1).astype(np.float64)
 coef, *_ = np.linalg.lstsq(A, cyc, rcond=None)
 print("cycles ~ %.0f + %.0f*scanned + %.0f*tests + %.0f*quarters + %.0f*stages + %.0f*passes" % tuple(coef))
+nrows = np.array([bin(int(c) >> 4).count("1") for c in code])
+print("CTAs by rows owned: " + ", ".join(f"{k} rows: {int((nrows == k).sum())}" for k in range(1, 9)) +
+      f"; target-part CTAs: {int(((code & 7) != 0).sum())}")
 order = np.argsort(-cyc)[:12]
 # geometry of the slow blocks: radius of the block and of its rows (stored order of the shard)
 sp = api.spatial_order(shard).cpu().numpy()
@@ -63,7 +66,7 @@ for o in order:
     rad = np.sqrt(((pts - c) ** 2).sum(1).max())
     rows = [np.sqrt(((pts[r * 32:(r + 1) * 32] - pts[r * 32:(r + 1) * 32].mean(0)) ** 2).sum(1).max())
             for r in range(len(pts) // 32)]
-    print(f"  blk {b} code {code[o]}: {cyc[o]:.0f} cyc, scanned {nscan[o]}, tests {ntest[o]}, quarters {nquart[o]}, "
+    print(f"  blk {b} rows {code[o] >> 4:08b} part {code[o] & 7}: {cyc[o]:.0f} cyc, scanned {nscan[o]}, tests {ntest[o]}, quarters {nquart[o]}, "
           f"stages {ncand[o]}, passes {npass[o]}; block radius {rad:.2f} mm, row radii " +
           " ".join(f"{x:.1f}" for x in rows))
 med = np.argsort(cyc)[len(cyc) // 2]

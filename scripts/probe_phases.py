@@ -44,7 +44,7 @@ q_ready = (L[:, 1] & lo32).astype(np.float64)
 hints = (L[:, 1] >> np.uint64(32)).astype(np.float64)
 rows = (L[:, 2] & lo32).astype(np.float64)
 epi = (L[:, 2] >> np.uint64(32)).astype(np.float64)
-total = ((L[:, 3] & np.uint64(0xFFFFFF)).astype(np.float64)) * 256
+total = ((L[:, 3] & np.uint64(0xFFFFF)).astype(np.float64)) * 256
 print(f"{len(L)} CTAs logged (1/{world} shard, rank {rank}, {hi - lo} points)")
 def st(name, v):
     print(f"  {name}: median {np.median(v):.0f}  mean {v.mean():.0f}  p90 {np.percentile(v, 90):.0f}  max {v.max():.0f} cycles")

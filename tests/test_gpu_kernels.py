@@ -615,8 +615,8 @@ def test_fused_icp_target_parts_are_bit_identical(gpu, monkeypatch):
             torch.cuda.synchronize()
         finally:
             lib.isr_debug_cta_log(None, 0)
-        codes = (log.cpu().numpy().astype(np.uint64)[:, 3] >> np.uint64(24)) & np.uint64(0xFF)
-        out[label] = (prob.results(True)[0], int((codes >= 16).sum()))
+        tparts = (log.cpu().numpy().astype(np.uint64)[:, 3] >> np.uint64(20)) & np.uint64(7)   # target part of the CTA
+        out[label] = (prob.results(True)[0], int((tparts != 0).sum()))
     (a, parts_off), (b, parts_on) = out["off"], out["on"]
     assert parts_off == 0 and parts_on >= 4, (parts_off, parts_on)
     np.testing.assert_array_equal(a.transformation, b.transformation)
@@ -655,7 +655,7 @@ def test_fused_icp_launch_list_recut_from_measured_costs_is_bit_identical(gpu, m
             lib.isr_debug_cta_log(None, 0)
         L = log.cpu().numpy().astype(np.uint64)
         L = L[L[:, 0] > 0]
-        codes = np.sort(((L[:, 3] >> np.uint64(24)) & np.uint64(0xFF)).astype(np.int64))
+        codes = np.sort(((L[:, 3] >> np.uint64(20)) & np.uint64(0xFFF)).astype(np.int64))   # (rows mask, target part)
         out[label] = (prob.results(True)[0], codes)
     (a, codes_a), (b, codes_b) = out["0"], out["1"]
     assert len(codes_a) != len(codes_b) or (codes_a != codes_b).any()   # the list was re-cut
