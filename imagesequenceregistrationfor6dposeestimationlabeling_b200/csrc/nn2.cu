@@ -643,6 +643,7 @@ struct alignas(128) PrunedWarpSmem {
     int seed[kAnchors];        // sub-tiles scanned first (-1: none)
     unsigned seedrows[kAnchors];  // query rows that a seed's first scan covers (the walk queues it for the others)
     int seedpos[kAnchors];     // its FIFO entry
+    int seedsd[kAnchors];      // scratch of the seed search: nearest stage, then seed sub-tile, of every anchor
     alignas(16) float qs[3][32 * Q];  // the warp's queries, hi xyz (read by the scan, the tests and the resolve path)
     // dq[r][lane] >= the exact best distance so far of query r * 32 + lane (0: no such query).  Read by
     // every exact test; in local memory (with the rest of the resolve state) five of six of those
@@ -1101,61 +1102,122 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     if (lane < kAnchors) { ws.seed[lane] = -1; ws.seedrows[lane] = 0u; }
     __syncwarp();
     if (!all_hinted) {  // (a fully hinted warp already holds near-final bounds)
-        // anchors: the centres of the query rows (a dead row falls back to the first live one);
-        // a run-time loop over the anchors, like everything per row
+        // anchors: the centres of the query rows (a dead row falls back to the first live one)
+        const int na = kAnchors < p.nanchors ? kAnchors : p.nanchors;
+        // (A) the seed sub-tile of every anchor -> ws.seedsd[]
+        if (!ISR_SEED_OWN && stages <= 4 * 32) {
+            // a target of at most 128 stages (every verification / ADD-S cloud): each lane keeps its (up to)
+            // four stage spheres in registers and the sub-tile spheres of all anchors are fetched in one
+            // go, two anchors per step -- one round trip each instead of five per anchor (the seeds were
+            // 7 % of the verification kernel's samples, nearly all of it waiting for those loads)
+            float4 Sg[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int sidx = j * 32 + lane;
+                Sg[j] = sidx < stages ? stage_c[sidx] : make_float4(0.f, 0.f, 0.f, -1.f);
+            }
 #pragma unroll 1
-        for (int a = 0; a < kAnchors && a < p.nanchors; ++a) {
+            for (int a2 = 0; a2 < na; ++a2) {
+                const float4 R = ws.row[a2].w >= 0.f ? ws.row[a2] : ws.row[__ffs(liverows) - 1];
+                unsigned best = ~0u;  // squared distance (low 7 bits dropped) | stage
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float dx = Sg[j].x - R.x, dy = Sg[j].y - R.y, dz = Sg[j].z - R.z;
+                    const unsigned key = (__float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) & 0xFFFFFF80u) |
+                                         (unsigned)(j * 32 + lane);
+                    best = Sg[j].w >= 0.f && key < best ? key : best;
+                }
+                best = __reduce_min_sync(0xffffffffu, best);
+                if (lane == 0) ws.seedsd[a2] = best == ~0u ? 0 : (int)(best & 127u);
+            }
+            __syncwarp();
+            const int half = lane >> 4, sl = lane & (SUBS - 1);
+            float4 Sb[4];
+            int stv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int a2 = 2 * t + half;
+                stv[t] = a2 < na ? ws.seedsd[a2] : 0;
+                Sb[t] = a2 < na ? sub_c[(long long)stv[t] * SUBS + sl] : make_float4(0.f, 0.f, 0.f, -1.f);
+            }
+            __syncwarp();  // (every lane has read the stages before the slots are reused for the sub-tiles)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int a2 = 2 * t + half;
+                const float4 R = ws.row[a2].w >= 0.f ? ws.row[a2] : ws.row[__ffs(liverows) - 1];
+                const float dx = Sb[t].x - R.x, dy = Sb[t].y - R.y, dz = Sb[t].z - R.z;
+                unsigned key = Sb[t].w >= 0.f
+                                   ? ((__float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) & 0xFFFFFFF0u) | (unsigned)sl)
+                                   : ~0u;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));  // within the half
+                if (sl == 0 && a2 < na) ws.seedsd[a2] = stv[t] * SUBS + (key == ~0u ? 0 : (int)(key & 15u));
+            }
+            __syncwarp();
+        } else {
+#pragma unroll 1
+            for (int a = 0; a < na; ++a) {
+#if ISR_SEED_OWN
+                if (!((liverows >> a) & 1u)) continue;  // warp-uniform: a row of another CTA, or beyond the cloud
+                const float4 R = ws.row[a];
+#else
+                const float4 R = ws.row[a].w >= 0.f ? ws.row[a] : ws.row[__ffs(liverows) - 1];
+#endif
+                u64 bk = ~0ull;
+                for (int base = 0; base < stages; base += 32) {
+                    const int s = base + lane;
+                    if (s < stages) {
+                        const float4 S = stage_c[s];
+                        if (S.w >= 0.f) {
+                            const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
+                            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            const u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(unsigned)s;
+                            bk = key < bk ? key : bk;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const u64 other = __shfl_xor_sync(0xffffffffu, bk, o);
+                    bk = other < bk ? other : bk;
+                }
+                int st = (int)(unsigned)(bk & 0xffffffffull);
+                if (st >= stages) st = 0;
+                // nearest sub-tile centre inside that stage
+                u64 key = ~0ull;
+                if (lane < SUBS) {
+                    const float4 S = sub_c[(long long)st * SUBS + lane];
+                    if (S.w >= 0.f) {
+                        const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
+                        key = ((u64)__float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) << 32) | (u64)(unsigned)lane;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const u64 other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other < key ? other : key;
+                }
+                int sb = (int)(unsigned)(key & 31ull);
+                if (key == ~0ull) sb = 0;
+                if (lane == 0) ws.seedsd[a] = st * SUBS + sb;
+            }
+            __syncwarp();
+        }
+        // (B) queue them, each sub-tile once
+#pragma unroll 1
+        for (int a = 0; a < na; ++a) {
 #if ISR_SEED_OWN
             // a seed is first scanned for the rows of its own row group only: scanned for every row,
             // seed k improved (and resolved, one FP64 pass each) every row that lies nearer to it than
-            // to seeds 0 .. k-1 -- up to 8 + 7 + .. + 1 passes along the curve, each overwritten by the
-            // row's own seed later.  The regular walk queues the seed's tile for the other rows
-            // like any other tile, against the bounds they hold by then.
+            // to seeds 0 .. k-1.  The regular walk queues the seed's tile for the other rows like any other
+            // tile, against the bounds they hold by then.  (Measured: no gain.)
             constexpr int HS = Q / GROUPS;
             const unsigned qrows = (((1u << HS) - 1u) << (HS * (a / HS))) & liverows;
-            if (!((liverows >> a) & 1u)) continue;  // warp-uniform: a row of another CTA, or beyond the cloud
-            const float4 R = ws.row[a];
+            if (!((liverows >> a) & 1u)) continue;  // warp-uniform
 #else
             const unsigned qrows = (1u << Q) - 1u;
-            const float4 R = ws.row[a].w >= 0.f ? ws.row[a] : ws.row[__ffs(liverows) - 1];
 #endif
-            u64 bk = ~0ull;
-            for (int base = 0; base < stages; base += 32) {
-                const int s = base + lane;
-                if (s < stages) {
-                    const float4 S = stage_c[s];
-                    if (S.w >= 0.f) {
-                        const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
-                        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        const u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(unsigned)s;
-                        bk = key < bk ? key : bk;
-                    }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const u64 other = __shfl_xor_sync(0xffffffffu, bk, o);
-                bk = other < bk ? other : bk;
-            }
-            int st = (int)(unsigned)(bk & 0xffffffffull);
-            if (st >= stages) st = 0;
-            // nearest sub-tile centre inside that stage
-            u64 key = ~0ull;
-            if (lane < SUBS) {
-                const float4 S = sub_c[(long long)st * SUBS + lane];
-                if (S.w >= 0.f) {
-                    const float dx = S.x - R.x, dy = S.y - R.y, dz = S.z - R.z;
-                    key = ((u64)__float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) << 32) | (u64)(unsigned)lane;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const u64 other = __shfl_xor_sync(0xffffffffu, key, o);
-                key = other < key ? other : key;
-            }
-            int sb = (int)(unsigned)(key & 31ull);
-            if (key == ~0ull) sb = 0;
-            const int sd = st * SUBS + sb;
+            const int sd = ws.seedsd[a];
             int dup = -1;
             for (int c = 0; c < a; ++c) dup = ws.seed[c] == sd ? c : dup;
             if (dup < 0) {
