@@ -1250,6 +1250,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     //            -> FIFO.
     unsigned nscanned = 0, nhalves = 0, ntests = 0, ncand = 0, nflag = 0, npass = 0;
 #ifdef ISR_PHASE_LOG
+    const long long ph_m = clock64() - t_start;  // seeds found and queued
     long long acc_sort = 0, acc_test = 0, acc_wait = 0, acc_scan = 0, acc_resolve = 0, acc_produce = 0;
 #define PH_T0 const long long ph_t0 = clock64();
 #define PH_ADD(acc) acc += clock64() - ph_t0;
@@ -1647,6 +1648,25 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                 if (p.hint != nullptr) p.hint[(long long)b * p.nq_pad + i] = ibest_l[r];
             }
         }
+#ifdef ISR_PHASE_LOG
+        if (p.cta_log != nullptr && lane == 0) {
+            const long long rec = ((long long)b * gridDim.x + blockIdx.x);
+            if (rec < p.cta_log_cap / 2 - 1) {
+                unsigned long long *o = p.cta_log + 4 * rec;
+                o[0] = (unsigned long long)ph_s;
+                o[1] = (unsigned long long)ph_q | ((unsigned long long)ph_h << 32);
+                o[2] = (unsigned long long)ph_r | ((unsigned long long)ph_m << 32);
+                o[3] = ((unsigned long long)(unsigned)blk << 32) | ((unsigned long long)own << 24) |
+                       (unsigned long long)((clock64() - t_start) >> 8 & 0xFFFFF);
+                unsigned long long *o2 = p.cta_log + 4 * (p.cta_log_cap / 2 + rec);
+                o2[0] = (unsigned long long)acc_test | ((unsigned long long)acc_wait << 32);
+                o2[1] = (unsigned long long)acc_scan | ((unsigned long long)acc_resolve << 32);
+                o2[2] = (unsigned long long)acc_produce | ((unsigned long long)acc_sort << 32);
+                o2[3] = ((unsigned long long)nscanned << 48) | ((unsigned long long)ntests << 32) |
+                        ((unsigned long long)npass << 16) | (unsigned long long)nhalves;
+            }
+        }
+#endif
     }
 }
 
