@@ -616,8 +616,24 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
 #ifndef ISR_NN_FIFO
 #define ISR_NN_FIFO 96
 #endif
-constexpr int kRing = ISR_NN_RING;  // sub-tile buffers in flight per warp
+constexpr int kRing = ISR_NN_RING;  // sub-tile buffers in flight per warp (fused ICP iteration)
 constexpr int kFifo = ISR_NN_FIFO;  // candidate sub-tiles queued per warp (the nearest-first sort handles up to 64)
+// The plain search (verification, ADD-S, stepwise ICP) needs neither the fused epilogue's scratch nor
+// a third buffer (the wait for a sub-tile is 0.4 % of a CTA's cycles with three): a two-slot ring and a
+// shorter FIFO bring a warp's shared memory from 10.1 to 8.6 KB, and with the 80 registers the compiler
+// then settles for, 24 one-warp CTAs fit an SM instead of 20.
+#ifndef ISR_NN_RING_PLAIN
+#define ISR_NN_RING_PLAIN 2
+#endif
+#ifndef ISR_NN_FIFO_PLAIN
+#define ISR_NN_FIFO_PLAIN 96
+#endif
+#ifndef ISR_NN_MINB_PLAIN
+#define ISR_NN_MINB_PLAIN 21
+#endif
+#ifndef ISR_NN_MINB_FUSED
+#define ISR_NN_MINB_FUSED 20
+#endif
 constexpr int kAnchors = 8; // seeds per warp: one per query row
 #ifndef ISR_SEED_OWN
 #define ISR_SEED_OWN 0
@@ -628,17 +644,17 @@ constexpr int kAnchors = 8; // seeds per warp: one per query row
 constexpr float kCutGap = 3.0f;   // SPLIT: a row is cut at gaps wider than its radius / kCutGap ...
 constexpr float kCutGain = 0.75f; //        ... when every piece is then at most this fraction of its radius wide
 
-template <int SUB, int Q, bool SPLIT>
+template <int SUB, int Q, bool SPLIT, int RING, int FIFO>
 struct alignas(128) PrunedWarpSmem {
-    float buf[kRing][4][SUB];  // x, y, z, |p|^2 of one sub-tile per slot
-    float4 sph[kFifo];         // queued candidates: sphere,
-    int id[kFifo];             //   sub-tile index in the target (-1: dropped by the exact test),
-    unsigned rows[kFifo];      //   query rows that the coarse test could not rule out
-    unsigned box[kFifo];       //   packed half-extents of its bounding box about the sphere's centre
+    float buf[RING][4][SUB];   // x, y, z, |p|^2 of one sub-tile per slot
+    float4 sph[FIFO];          // queued candidates: sphere,
+    int id[FIFO];              //   sub-tile index in the target (-1: dropped by the exact test),
+    unsigned rows[FIFO];       //   query rows that the coarse test could not rule out
+    unsigned box[FIFO];        //   packed half-extents of its bounding box about the sphere's centre
     float4 row[Q];             // sphere (c, rho) of query row r = the 32 queries r*32 .. r*32+31
     float4 rowx[SPLIT ? Q : 1][3];  // SPLIT: further spheres of a row that the curve leaves and re-enters (w < 0: none)
     float rowB[Q];             // max of their bounds dq (refreshed between batches of work)
-    uint64_t full[kRing];
+    uint64_t full[RING];
     uint64_t qbar;             // mbarrier of the prologue's bulk copies of the warp's queries
     int seed[kAnchors];        // sub-tiles scanned first (-1: none)
     unsigned seedrows[kAnchors];  // query rows that a seed's first scan covers (the walk queues it for the others)
@@ -722,7 +738,9 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     long long ph_q = 0, ph_h = 0, ph_r = 0, ph_s = 0;
     if (p.cta_log != nullptr && lane == 0) atomicMin(p.cta_log + 4 * (p.cta_log_cap - 1) + 0, global_ns());
 #endif
-    PrunedWarpSmem<SUB, Q, SPLIT> &ws = reinterpret_cast<PrunedWarpSmem<SUB, Q, SPLIT> *>(smem_raw)[warp];
+    constexpr int RING = FUSED ? kRing : ISR_NN_RING_PLAIN, FIFO = FUSED ? kFifo : ISR_NN_FIFO_PLAIN;
+    using WS = PrunedWarpSmem<SUB, Q, SPLIT, RING, FIFO>;
+    WS &ws = reinterpret_cast<WS *>(smem_raw)[warp];
     const float *__restrict__ gq = p.q + (long long)b * p.q_bstride;
     const float *__restrict__ gt = p.t + (long long)b * p.t_bstride;
     const float4 *__restrict__ stage_c = p.stage_c + (long long)b * p.stage_c_bstride;
@@ -732,7 +750,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
 
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < kRing; ++i) mbar_init(&ws.full[i], 1);
+        for (int i = 0; i < RING; ++i) mbar_init(&ws.full[i], 1);
         mbar_init(&ws.qbar, 1);
         mbar_fence_init();
     }
@@ -761,7 +779,8 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     // for the instruction cache when the warps of an SM sit in different phases, and every
     // loop unrolled over the 8 rows multiplies it (124 KB of SASS before, no_instruction the
     // fastest-growing stall when more warps were made resident).
-    static_assert(sizeof(ws.buf) >= 3 * 32 * Q * sizeof(float), "lo planes land in the ring buffer");
+    static_assert(offsetof(WS, sph) == sizeof(WS::buf) && sizeof(WS::buf) + sizeof(WS::sph) >= 3 * 32 * Q * sizeof(float),
+                  "lo planes land in the ring buffer (and, with two slots, the still empty FIFO behind it)");
     float mt_l[Q], thr_l[Q], tm_l[Q];
     float qlo[3 * Q];  // lo parts of the lane's queries: x of rows 0..7, then y, then z (local memory)
     float *dq_l = &ws.dq[0][lane];  // this lane's bounds: dq_l[r * 32]
@@ -1223,13 +1242,13 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             if (dup < 0) {
                 if (lane == 0) {
                     // +inf radius: never ruled out
-                    ws.sph[tail % kFifo] = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
-                    ws.id[tail % kFifo] = sd;
-                    ws.rows[tail % kFifo] = qrows;
-                    ws.box[tail % kFifo] = kNoBox;
+                    ws.sph[tail % FIFO] = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
+                    ws.id[tail % FIFO] = sd;
+                    ws.rows[tail % FIFO] = qrows;
+                    ws.box[tail % FIFO] = kNoBox;
                     ws.seed[a] = sd;
                     ws.seedrows[a] = qrows;
-                    ws.seedpos[a] = tail % kFifo;
+                    ws.seedpos[a] = tail % FIFO;
                 }
                 ++tail;
             } else if (lane == 0) {  // the same tile serves another row group as well
@@ -1243,7 +1262,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
     // ---- main loop: ONE code path that either consumes a queued sub-tile or produces more -------
     // (a single scan site keeps the instruction footprint small: the warps of an SM sit in
     // different phases, so every inlined copy of the scan would compete for the instruction cache)
-    //   consume: exact-test queued entries up to kRing loads ahead (survivors get their bulk
+    //   consume: exact-test queued entries up to RING loads ahead (survivors get their bulk
     //            copy issued at once), then wait for the head entry's data and scan it;
     //   produce: next chunk of 32 stage spheres -> coarse row test, one per lane; then per
     //            candidate stage the exact test, and its 16 sub-tile spheres -> coarse row test
@@ -1292,7 +1311,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
                     const int j = k * 32 + lane;
                     key2[k] = ~0ull;
                     if (j < cnt) {
-                        const int e = (look + j) % kFifo;
+                        const int e = (look + j) % FIFO;
                         S2[k] = ws.sph[e]; id2[k] = ws.id[e]; rows2[k] = ws.rows[e]; box2[k] = ws.box[e];
                         float d = CUDART_INF_F;
 #pragma unroll 1
@@ -1317,7 +1336,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     if (k * 32 + lane < cnt) {
-                        const int e = (look + (k == 0 ? rank0 : rank1)) % kFifo;
+                        const int e = (look + (k == 0 ? rank0 : rank1)) % FIFO;
                         ws.sph[e] = S2[k]; ws.id[e] = id2[k]; ws.rows[e] = rows2[k]; ws.box[e] = box2[k];
                     }
                 }
@@ -1325,18 +1344,18 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             }
             PH_ADD(acc_sort)
         }
-        if (pending > 0 && (seeding || produced_all || pending > kFifo - 2 * SUBS)) {
+        if (pending > 0 && (seeding || produced_all || pending > FIFO - 2 * SUBS)) {
 #ifdef ISR_PHASE_LOG
             const long long ph_c0 = clock64();
 #endif
-            while (look < tail && nloads - nconsumed < kRing) {
-                const int e = look % kFifo;
+            while (look < tail && nloads - nconsumed < RING) {
+                const int e = look % FIFO;
                 ++ntests;
                 const unsigned need = exact_rows_box(ws.sph[e], ws.rows[e], ws.box[e]);
                 if (need != 0) {
                     if (lane == 0) {
                         ws.rows[e] = need;
-                        const int slot = nloads % kRing;
+                        const int slot = nloads % RING;
                         const long long src = (long long)ws.id[e] * SUB;
                         mbar_expect_tx(&ws.full[slot], 4u * SUB * 4u);
 #pragma unroll
@@ -1363,19 +1382,19 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
 #ifdef ISR_PHASE_LOG
             acc_test += clock64() - ph_c0;
 #endif
-            const int id = ws.id[head % kFifo];
+            const int id = ws.id[head % FIFO];
             if (id >= 0) {
-                const int slot = nconsumed % kRing;
+                const int slot = nconsumed % RING;
 #ifdef ISR_PHASE_LOG
                 const long long ph_w0 = clock64();
 #endif
-                mbar_wait(&ws.full[slot], (nconsumed / kRing) & 1);
+                mbar_wait(&ws.full[slot], (nconsumed / RING) & 1);
 #ifdef ISR_PHASE_LOG
                 const long long ph_w1 = clock64();
                 acc_wait += ph_w1 - ph_w0;
                 const long long res0 = acc_resolve;
 #endif
-                const unsigned rows_e = ws.rows[head % kFifo];
+                const unsigned rows_e = ws.rows[head % FIFO];
                 ++nscanned;
                 // counted in half units (4 rows x SUB targets): a quarter (2 rows) is half of one
                 if (GROUPS == 2) {
@@ -1479,7 +1498,7 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
             }
             const unsigned m32 = __ballot_sync(0xffffffffu, rows != 0);
             if (rows != 0) {
-                const int pos = (tail + __popc(m32 & ((1u << lane) - 1u))) % kFifo;
+                const int pos = (tail + __popc(m32 & ((1u << lane) - 1u))) % FIFO;
                 ws.sph[pos] = S;
                 ws.id[pos] = gid;
                 ws.rows[pos] = rows;
@@ -1568,10 +1587,11 @@ nn2_pruned_kernel(const NN2Params p, const __grid_constant__ IcpFuse f) {
         // neighbour's original float32 coordinates (one 16-byte gather; neighbours of consecutive
         // stored queries are stored close together): the strict d2 < max_d2 test, fitness, rmse
         // and the Kabsch sums carry no FP32 error, only the choice of neighbour was made in FP32.
-        using WS = PrunedWarpSmem<SUB, Q, SPLIT>;
-        static_assert(offsetof(WS, sph) == sizeof(WS::buf) &&
-                          sizeof(WS::buf) + sizeof(WS::sph) >= 32 * kNS * sizeof(double),
-                      "the row reduction borrows the (idle) ring buffer and FIFO");
+        static_assert(!FUSED || (offsetof(WS, sph) == sizeof(WS::buf) && offsetof(WS, id) == offsetof(WS, sph) + sizeof(WS::sph) &&
+                                 offsetof(WS, rows) == offsetof(WS, id) + sizeof(WS::id) &&
+                                 offsetof(WS, box) == offsetof(WS, rows) + sizeof(WS::rows) &&
+                                 offsetof(WS, box) + sizeof(WS::box) >= 32 * kNS * sizeof(double)),
+                      "the row reduction borrows the (idle) ring buffer and FIFO arrays");
         double *scratch = reinterpret_cast<double *>(&ws.buf[0][0][0]);  // [32 lanes][17]
         __syncwarp();
         double Te[12];  // (re-read: the pose must not sit in registers across the search)
@@ -2093,7 +2113,8 @@ struct NN2PrunedVariant {
     static constexpr bool kPrune = true;
     static constexpr bool kFused = FUSED;
     static constexpr bool kSplit = SPLIT;
-    static constexpr size_t kSmem = (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q, SPLIT>);
+    static constexpr size_t kSmem =
+        (size_t)WARPS * sizeof(PrunedWarpSmem<SUB, Q, SPLIT, FUSED ? kRing : ISR_NN_RING_PLAIN, FUSED ? kFifo : ISR_NN_FIFO_PLAIN>);
 
     static int launch(const NN2Params &p, dim3 grid, cudaStream_t st, const IcpFuse &fuse, bool pdl) {
         auto kern = nn2_pruned_kernel<Q, WARPS, SUB, MINB, UNR, FLAG, PARTS, GROUPS, FUSED, SPLIT>;
@@ -2157,17 +2178,17 @@ struct NN2PrunedVariant {
 #ifndef ISR_NN_VERIFY_PARTS
 #define ISR_NN_VERIFY_PARTS 1
 #endif
-using NN2Pruned = NN2PrunedVariant<8, 1, 64, 20, 1, 64, ISR_NN_VERIFY_PARTS, 4>;
-using NN2PrunedHalves = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2>;
-using NN2PrunedFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 4, true>;
-using NN2PrunedHalvesFused = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 1, 2, true>;
+using NN2Pruned = NN2PrunedVariant<8, 1, 64, ISR_NN_MINB_PLAIN, 1, 64, ISR_NN_VERIFY_PARTS, 4>;
+using NN2PrunedHalves = NN2PrunedVariant<8, 1, 64, ISR_NN_MINB_PLAIN, 1, 64, 1, 2>;
+using NN2PrunedFused = NN2PrunedVariant<8, 1, 64, ISR_NN_MINB_FUSED, 1, 64, 1, 4, true>;
+using NN2PrunedHalvesFused = NN2PrunedVariant<8, 1, 64, ISR_NN_MINB_FUSED, 1, 64, 1, 2, true>;
 // (flags per quarter of the sub-tile, so that a resolve pass re-derives 16 filter values instead of
 // 64: in a shallow grid a warp's instruction count IS its latency -- 0.161 -> 0.155 ms per
 // iteration on a 1/8 shard; in deep grids the same change was measured 0 .. -2 %)
 #ifndef ISR_SPLIT_UNR
 #define ISR_SPLIT_UNR 1
 #endif
-using NN2PrunedFusedSplit = NN2PrunedVariant<8, 1, 64, 20, ISR_SPLIT_UNR, 64, 4, 4, true, true>;
+using NN2PrunedFusedSplit = NN2PrunedVariant<8, 1, 64, ISR_NN_MINB_FUSED, ISR_SPLIT_UNR, 64, 4, 4, true, true>;
 #ifdef ISR_NN_TUNING
 using NN2PrunedP2 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 2>;
 using NN2PrunedP4 = NN2PrunedVariant<8, 1, 64, 20, 1, 64, 4>;
