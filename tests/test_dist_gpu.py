@@ -1,12 +1,12 @@
 """Multi-rank parity of the sharded paths against the oracle and the single-GPU results.
 
-  test_two_ranks_on_one_gpu   world 2 on ONE device: two processes share cuda:0, gloo carries the
-                              host-side collectives, and the kernel-fused exchange of the sharded
-                              ICP runs through CUDA IPC between the two processes -- so
+  test_two_ranks_match_oracle[gloo]   world 2 on ONE device: two processes share cuda:0, gloo
+                              carries the host-side collectives, and the kernel-fused exchange of the
+                              sharded ICP runs through CUDA IPC between the two processes -- so
                               isr_icp_run_sharded, target-sharded ICP, the candidate split and the
                               multi-start split are parity-checked on the driver's 1-GPU box
-  test_two_gpu_sharding...    the same with NCCL, one process per GPU (needs >= 2 GPUs:
-                              `gpurun --gpus 2 -- python -m pytest tests -m gpu`)"""
+  test_two_ranks_match_oracle[nccl]   the same with NCCL, one process per GPU (generated only where
+                              >= 2 GPUs are visible: `gpurun --gpus 2 -- python -m pytest tests -m gpu`)"""
 import os
 import socket
 
@@ -65,14 +65,14 @@ def _worker(rank, world, port, q, backend):
     q.put((rank, out))
 
 
-def test_two_gpu_sharding_matches_oracle():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (the one-GPU form of this test runs everywhere)")
-    _run_two_ranks("nccl")
+# gloo: two ranks share cuda:0 (runs on every GPU box); nccl: one rank per GPU -- NCCL refuses two
+# ranks on one device, so that form only exists where two GPUs are visible
+_BACKENDS = ["gloo"] + (["nccl"] if torch.cuda.device_count() >= 2 else [])
 
 
-def test_two_ranks_on_one_gpu_match_oracle():
-    _run_two_ranks("gloo")
+@pytest.mark.parametrize("backend", _BACKENDS)
+def test_two_ranks_match_oracle(backend):
+    _run_two_ranks(backend)
 
 
 def _run_two_ranks(backend):
