@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(THREADS, MINB) nn2_kernel(const NN2Params p) {
     }
 
     // Scan order: the target stage whose centre is nearest to this CTA's query block goes
-    // first (clouds are stored in Morton order, so both are compact patches).  After that
+    // first (clouds are stored in Hilbert order, so both are compact patches).  After that
     // one stage every query already holds a near-final bound and the remaining stages
     // almost never reach the resolve path.  The rest follows in ascending order.
     int s_first = 0;

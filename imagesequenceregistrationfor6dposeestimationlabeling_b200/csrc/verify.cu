@@ -169,7 +169,7 @@ int isr_verify_poses(const float *cloud_q, int64_t nq, const float *cloud_t, int
     uint32_t *box_y = reinterpret_cast<uint32_t *>(ws + L.box_y);
     if (!direct) {
         ISR_TRY(isr_centroid(cloud_t, nt, centroid, stream));
-        // Morton order once per cloud; every candidate's rigid copy inherits the coherence.
+        // Hilbert order once per cloud; every candidate's rigid copy inherits the coherence.
         // The losses are means over all points, so nothing has to be permuted back.
         ISR_TRY(isr_spatial_order(cloud_t, nt, perm_t, ws + L.sortws, L.nnws - L.sortws, stream));
         if (cloud_q == cloud_t && nq == nt) perm_q = perm_t;
