@@ -189,3 +189,33 @@ def test_synthetic_generators_are_seeded_and_shaped():
     np.testing.assert_allclose(Rs @ np.transpose(Rs, (0, 2, 1)), np.tile(np.eye(3), (50, 1, 1)), atol=1e-12)
     src, tgt, T = synth.icp_pair(100, 120, 4, 5)
     assert src.shape == (100, 3) and tgt.shape == (120, 3) and T.shape == (4, 4)
+
+
+def test_integration_doc_names_every_export():
+    """INTEGRATION.md's entry-point map covers the whole header (a *_workspace_bytes companion counts
+    as named when its function is)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(_lib.HEADER_PATH).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(isr_[a-z0-9_]+)\s*\(", header))
+    missing = sorted(n for n in declared
+                     if n not in doc and n.replace("_workspace_bytes", "") not in doc)
+    assert not missing, missing
+
+
+def test_committed_bench_line_keeps_the_contract():
+    """The bench line of the final build under profiles/ parses and carries the contract's keys."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.load(open(os.path.join(root, "profiles", "r02d_bench.json")))
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks",
+                "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["config"]["workload"] and line["gpu_launches"] > 0 and line["warmup"] >= 3
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    r = line["roofline"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
